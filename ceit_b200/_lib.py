@@ -1,0 +1,205 @@
+"""ctypes binding of libceit_b200.so (the C ABI in include/ceit_b200.h).
+
+PyTorch is used only for device buffers and the current stream; every numeric step on the path is
+a kernel of this library.  There is NO CPU fallback: if the shared library or a CUDA device is
+missing, the calls below raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libceit_b200.so")
+_lib = None
+
+SYMBOLS = [
+    "ceit_last_error", "ceit_version", "ceit_launch_count", "ceit_plan_create", "ceit_plan_destroy",
+    "ceit_plan_info", "ceit_plan_tables", "ceit_assemble", "ceit_factor", "ceit_jacobian_block",
+    "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm",
+]
+
+
+class CeitError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (building first if the .so is absent and nvcc is available) the native library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:  # pragma: no cover
+            raise CeitError(
+                f"native library {LIB_PATH} is missing and could not be built ({e}); "
+                "run `python -m ceit_b200.build` - there is no CPU fallback") from e
+    L = ctypes.CDLL(LIB_PATH)
+    c_i64, c_dbl, c_vp, c_int = ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int
+    L.ceit_last_error.restype = ctypes.c_char_p
+    L.ceit_version.restype = c_int
+    L.ceit_launch_count.restype = c_i64
+    L.ceit_plan_create.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_int,
+                                   ctypes.POINTER(c_vp)]
+    L.ceit_plan_destroy.argtypes = [c_vp]
+    L.ceit_plan_info.argtypes = [c_vp, c_vp]
+    L.ceit_plan_tables.argtypes = [c_vp] * 6
+    L.ceit_assemble.argtypes = [c_vp, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp]
+    L.ceit_factor.argtypes = [c_vp, c_int, c_vp]
+    L.ceit_jacobian_block.argtypes = [c_vp, c_i64, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_i64, c_vp, c_vp]
+    L.ceit_forward.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]
+    L.ceit_inverse_model.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_int,
+                                     c_dbl, c_vp, c_vp]
+    L.ceit_reconstruct.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]
+    L.ceit_dgemm.argtypes = [c_int, c_int, c_i64, c_i64, c_i64, c_dbl, c_vp, c_i64, c_vp, c_i64, c_dbl,
+                             c_vp, c_i64, c_vp]
+    L.ceit_set_option.argtypes = [ctypes.c_char_p, c_i64]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is None or (name not in ("ceit_last_error", "ceit_launch_count")):
+            if name not in ("ceit_last_error", "ceit_launch_count"):
+                fn.restype = c_int
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise CeitError(lib().ceit_last_error().decode("utf-8", "replace") + f" (code {rc})")
+
+
+def launch_count():
+    return int(lib().ceit_launch_count())
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise CeitError("ceit_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def tptr(t):
+    """Device pointer of a torch tensor used as a plain buffer (None -> NULL)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous()
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Plan:
+    """Opaque `ceit_plan_t*` + the few host tables the Python classes need."""
+
+    def __init__(self, nodes, elem, electrode_lists, target_block=0, upload=True):
+        nodes = np.ascontiguousarray(nodes, dtype=np.float64)
+        elem = np.ascontiguousarray(elem, dtype=np.int64)
+        if nodes.ndim != 2 or nodes.shape[1] != 2:
+            raise Exception("2D Node coordinates incorrect")      # FEMBasic.py:49-50
+        if elem.ndim != 2 or elem.shape[1] != 3:
+            raise Exception("2D Elements dimension incorrect")    # FEMBasic.py:54-55
+        ptr = np.zeros(len(electrode_lists) + 1, dtype=np.int64)
+        for i, e in enumerate(electrode_lists):
+            ptr[i + 1] = ptr[i] + len(e)
+        idx = np.ascontiguousarray(np.concatenate([np.asarray(e, dtype=np.int64) for e in electrode_lists])
+                                   if len(electrode_lists) else np.zeros(0, np.int64))
+        if upload:
+            require_cuda()
+        self._h = ctypes.c_void_p()
+        self.N, self.E, self.L = nodes.shape[0], elem.shape[0], len(electrode_lists)
+        check(lib().ceit_plan_create(_np_ptr(nodes), _np_ptr(elem), self.N, self.E, _np_ptr(ptr), _np_ptr(idx),
+                                     self.L, int(target_block), 1 if upload else 0, ctypes.byref(self._h)))
+        info = self.info()
+        self.nU, self.N0, self.n_blocks, self.max_block, self.nnz = (int(info[k]) for k in (3, 4, 5, 6, 7))
+
+    def info(self):
+        out = np.zeros(16, dtype=np.int64)
+        check(lib().ceit_plan_info(self._h, _np_ptr(out)))
+        return out
+
+    def tables(self):
+        rowptr = np.zeros(self.N + 1, np.int64)
+        colidx = np.zeros(self.nnz, np.int64)
+        pos = np.zeros(self.N, np.int64)
+        blk_ptr = np.zeros(self.n_blocks + 1, np.int64)
+        U = np.zeros(self.nU, np.int64)
+        check(lib().ceit_plan_tables(self._h, _np_ptr(rowptr), _np_ptr(colidx), _np_ptr(pos), _np_ptr(blk_ptr),
+                                     _np_ptr(U)))
+        return dict(rowptr=rowptr, colidx=colidx, pos=pos, blk_ptr=blk_ptr, U=U)
+
+    # -- numeric entry points (torch tensors as buffers) ------------------------------------------
+    def assemble(self, perm, var, omega, vals=None, elem_param=None):
+        check(lib().ceit_assemble(self._h, tptr(perm), tptr(var), float(omega), tptr(vals), tptr(elem_param),
+                                  stream_ptr()))
+
+    def factor(self, is_complex):
+        check(lib().ceit_factor(self._h, 1 if is_complex else 0, stream_ptr()))
+
+    def jacobian_block(self, i_from, i_to, e_from, e_to, c, omega, J, ldJ, base=None):
+        check(lib().ceit_jacobian_block(self._h, int(i_from), int(i_to), int(e_from), int(e_to), float(c),
+                                        float(omega), tptr(J), int(ldJ), tptr(base), stream_ptr()))
+
+    def forward(self, i, node_abs=None, elem_pot=None, electrode_pot=None):
+        check(lib().ceit_forward(self._h, int(i), tptr(node_abs), tptr(elem_pot), tptr(electrode_pot),
+                                 stream_ptr()))
+
+    def numeric_flag(self):
+        """0 = ok, 1 = a Cholesky pivot was not positive (synchronises)."""
+        return int(self.info()[13])
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().ceit_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def inverse_model(J, det_idx, lmbda, rows=None, shift=1.0, form=0, scale=1.0):
+    """J: cuda f64 (m, E) tensor; det_idx: cuda int64; returns cuda f64 (n_det, m_sel)."""
+    torch = require_cuda()
+    m, ldJ = J.shape[0], J.stride(0)
+    n_det = det_idx.numel()
+    m_sel = rows.numel() if rows is not None else m
+    out = torch.empty((n_det, m_sel), dtype=torch.float64, device=J.device)
+    check(lib().ceit_inverse_model(tptr(J), ldJ, m, tptr(det_idx), n_det, tptr(rows), m_sel, float(shift),
+                                   float(lmbda), int(form), float(scale), tptr(out), stream_ptr()))
+    return out
+
+
+def reconstruct(inv, dV, out=None):
+    """inv (n_det, m) . dV (m,) or (m, F) on the device."""
+    torch = require_cuda()
+    n_det, m = inv.shape
+    F = 1 if dV.dim() == 1 else dV.shape[1]
+    if out is None:
+        out = torch.empty((n_det,) if dV.dim() == 1 else (n_det, F), dtype=torch.float64, device=inv.device)
+    check(lib().ceit_reconstruct(tptr(inv), tptr(dV), tptr(out), n_det, m, F, stream_ptr()))
+    return out
+
+
+def dgemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, C=None):
+    torch = require_cuda()
+    M = A.shape[1] if transA else A.shape[0]
+    K = A.shape[0] if transA else A.shape[1]
+    N = B.shape[0] if transB else B.shape[1]
+    if C is None:
+        C = torch.zeros((M, N), dtype=torch.float64, device=A.device)
+    check(lib().ceit_dgemm(int(transA), int(transB), M, N, K, float(alpha), tptr(A), A.stride(0), tptr(B),
+                           B.stride(0), float(beta), tptr(C), C.stride(0), stream_ptr()))
+    return C

@@ -1,0 +1,594 @@
+// C ABI of libceit_b200 (see include/ceit_b200.h) and the host-side orchestration of the kernels.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ceit_b200.h"
+#include "dense.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+#include "plan.h"
+#include "scalar.cuh"
+
+namespace ceit {
+std::atomic<int64_t> g_launches{0};
+int g_force_simt = 0;
+static thread_local std::string g_err;
+}  // namespace ceit
+
+using namespace ceit;
+
+#define CEIT_FAIL(code, msg)     \
+  do {                           \
+    ceit::g_err = (msg);         \
+    return (code);               \
+  } while (0)
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      ceit::g_err = std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +        \
+                    std::to_string(__LINE__) + ")";                                                 \
+      return CEIT_ERR_CUDA;                                                                         \
+    }                                                                                               \
+  } while (0)
+#define KERNEL_CHECK() CUDA_TRY(cudaGetLastError())
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace
+
+struct ceit_plan {
+  HostPlan h;
+  bool uploaded = false;
+  size_t dev_bytes = 0;
+  std::vector<void*> allocs;
+  // static tables
+  double* d_nodes = nullptr;
+  int32_t* d_elem = nullptr;
+  int32_t* d_src_ptr = nullptr;
+  int32_t* d_src = nullptr;
+  int64_t* d_slot_dst = nullptr;
+  uint8_t* d_slot_kind = nullptr;
+  int32_t* d_pos = nullptr;
+  int32_t* d_elem_pos = nullptr;
+  int64_t* d_g0_off = nullptr;
+  uint8_t* d_inB = nullptr;
+  int32_t* d_we_ptr = nullptr;
+  int32_t* d_we_u = nullptr;
+  double* d_we_w = nullptr;
+  double* d_area = nullptr;
+  cd* d_vals = nullptr;  // CSR values of the last assemble
+  int* d_info = nullptr;
+  bool assembled = false;
+  // numeric state (type-erased; element size esz = 8 real / 16 complex)
+  int mode = 0;  // 0 none, 1 real, 2 complex
+  void *Ad = nullptr, *Bs = nullptr, *Ld = nullptr, *Linv = nullptr, *Lsub = nullptr, *Sel = nullptr;
+  void *K0U = nullptr, *Zw = nullptr, *Xh = nullptr, *KUU = nullptr, *SU = nullptr, *Ptmp = nullptr;
+  void *tmpPanel = nullptr, *g0e = nullptr;
+  int alloc_mode = 0;
+  // per-excitation workspace
+  int ex_cap = 0, ex_mode = 0;
+  void *St = nullptr, *Ls = nullptr, *Linvs = nullptr, *Sinv = nullptr, *Yh = nullptr, *phi0 = nullptr;
+  void *tvec = nullptr, *tmpS = nullptr;
+  double* d_elec = nullptr;
+  double* d_node_abs = nullptr;
+};
+
+namespace {
+
+int dev_alloc(ceit_plan* p, void** out, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  CUDA_TRY(cudaMalloc(out, bytes));
+  p->allocs.push_back(*out);
+  p->dev_bytes += bytes;
+  return 0;
+}
+
+template <class V>
+int upload_vec(ceit_plan* p, V** dptr, const std::vector<V>& v) {
+  int rc = dev_alloc(p, (void**)dptr, v.size() * sizeof(V));
+  if (rc) return rc;
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+void dev_free_tracked(ceit_plan* p, void*& ptr) {
+  if (!ptr) return;
+  for (auto& a : p->allocs)
+    if (a == ptr) {
+      cudaFree(a);
+      a = nullptr;
+    }
+  ptr = nullptr;
+}
+
+int upload_plan(ceit_plan* p) {
+  HostPlan& h = p->h;
+  int rc;
+  if ((rc = upload_vec(p, &p->d_nodes, h.nodes))) return rc;
+  if ((rc = upload_vec(p, &p->d_elem, h.elem))) return rc;
+  if ((rc = upload_vec(p, &p->d_src_ptr, h.src_ptr))) return rc;
+  if ((rc = upload_vec(p, &p->d_src, h.src))) return rc;
+  if ((rc = upload_vec(p, &p->d_slot_dst, h.slot_dst))) return rc;
+  if ((rc = upload_vec(p, &p->d_slot_kind, h.slot_kind))) return rc;
+  if ((rc = upload_vec(p, &p->d_pos, h.pos))) return rc;
+  if ((rc = upload_vec(p, &p->d_elem_pos, h.elem_pos))) return rc;
+  if ((rc = upload_vec(p, &p->d_g0_off, h.g0_off))) return rc;
+  if ((rc = upload_vec(p, &p->d_inB, h.inB))) return rc;
+  if ((rc = upload_vec(p, &p->d_we_ptr, h.we_ptr))) return rc;
+  if ((rc = upload_vec(p, &p->d_we_u, h.we_u))) return rc;
+  if ((rc = upload_vec(p, &p->d_we_w, h.we_w))) return rc;
+  if ((rc = dev_alloc(p, (void**)&p->d_area, h.E * sizeof(double)))) return rc;
+  if ((rc = dev_alloc(p, (void**)&p->d_vals, h.nnz * sizeof(cd)))) return rc;
+  if ((rc = dev_alloc(p, (void**)&p->d_info, sizeof(int)))) return rc;
+  CUDA_TRY(cudaMemset(p->d_info, 0, sizeof(int)));
+  elem_param_kernel<<<cdiv(h.E, 256), 256>>>((int)h.E, p->d_nodes, p->d_elem, nullptr, p->d_area);
+  CEIT_COUNT_LAUNCH();
+  KERNEL_CHECK();
+  CUDA_TRY(cudaDeviceSynchronize());
+  p->uploaded = true;
+  return 0;
+}
+
+template <class T>
+int alloc_numeric(ceit_plan* p) {
+  const int want = Sc<T>::is_complex ? 2 : 1;
+  if (p->alloc_mode == want) return 0;
+  void** bufs[] = {&p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
+                   &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->g0e};
+  for (auto b : bufs) dev_free_tracked(p, *b);
+  // excitation workspace depends on the type too
+  void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS};
+  for (auto b : ex) dev_free_tracked(p, *b);
+  p->ex_cap = 0;
+  p->alloc_mode = 0;
+  const HostPlan& h = p->h;
+  const size_t es = sizeof(T);
+  int64_t maxS = 0;
+  for (int64_t k = 0; k + 1 < h.nb; ++k) maxS = std::max<int64_t>(maxS, h.offS[k + 1] - h.offS[k]);
+  int rc;
+  if ((rc = dev_alloc(p, &p->Ad, h.szD * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Bs, h.szS * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Ld, h.szD * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Linv, h.szD * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Lsub, h.szS * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Sel, (h.szD + h.szS) * es))) return rc;
+  if ((rc = dev_alloc(p, &p->K0U, h.N0 * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Zw, h.N0 * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Xh, h.N * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->KUU, h.nU * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->SU, h.nU * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Ptmp, maxS * es))) return rc;
+  if ((rc = dev_alloc(p, &p->tmpPanel, (int64_t)TILE * h.max_block * es))) return rc;
+  if ((rc = dev_alloc(p, &p->g0e, 6 * h.E * es))) return rc;
+  p->alloc_mode = want;
+  return 0;
+}
+
+template <class T>
+int alloc_excitation_ws(ceit_plan* p, int want_cap) {
+  const int want_mode = Sc<T>::is_complex ? 2 : 1;
+  if (p->ex_cap >= want_cap && p->ex_mode == want_mode) return 0;
+  void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS};
+  for (auto b : ex) dev_free_tracked(p, *b);
+  if (p->d_elec) { void* q = p->d_elec; dev_free_tracked(p, q); p->d_elec = nullptr; }
+  const HostPlan& h = p->h;
+  const size_t es = sizeof(T);
+  const int64_t c = want_cap, u2 = h.nU * h.nU;
+  int rc;
+  if ((rc = dev_alloc(p, &p->St, c * u2 * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Ls, c * u2 * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Linvs, c * u2 * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Sinv, c * u2 * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Yh, c * h.N * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->phi0, c * h.N * es))) return rc;
+  if ((rc = dev_alloc(p, &p->tvec, c * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->tmpS, c * (int64_t)TILE * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, (void**)&p->d_elec, c * h.L * sizeof(double)))) return rc;
+  p->ex_cap = want_cap;
+  p->ex_mode = want_mode;
+  return 0;
+}
+
+// ---- base stage -----------------------------------------------------------------------------------
+template <class T>
+int factor_impl(ceit_plan* p, cudaStream_t st) {
+  const HostPlan& h = p->h;
+  int rc = alloc_numeric<T>(p);
+  if (rc) return rc;
+  T *Ad = (T*)p->Ad, *Bs = (T*)p->Bs, *Ld = (T*)p->Ld, *Linv = (T*)p->Linv, *Lsub = (T*)p->Lsub;
+  T *Sel = (T*)p->Sel, *K0U = (T*)p->K0U, *Zw = (T*)p->Zw, *Xh = (T*)p->Xh, *KUU = (T*)p->KUU;
+  T *SU = (T*)p->SU, *Ptmp = (T*)p->Ptmp, *tmpPanel = (T*)p->tmpPanel, *g0e = (T*)p->g0e;
+  T* Sd = Sel;
+  T* So = Sel + h.szD;
+  const size_t es = sizeof(T);
+  const int64_t nU = h.nU, N0 = h.N0;
+  const T one = Sc<T>::one(), zero = Sc<T>::zero(), mone = neg(Sc<T>::one());
+  CUDA_TRY(cudaMemsetAsync(Ad, 0, h.szD * es, st));
+  CUDA_TRY(cudaMemsetAsync(Bs, 0, h.szS * es, st));
+  CUDA_TRY(cudaMemsetAsync(Ld, 0, h.szD * es, st));
+  CUDA_TRY(cudaMemsetAsync(Linv, 0, h.szD * es, st));
+  CUDA_TRY(cudaMemsetAsync(K0U, 0, N0 * nU * es, st));
+  CUDA_TRY(cudaMemsetAsync(KUU, 0, nU * nU * es, st));
+  CUDA_TRY(cudaMemsetAsync(p->d_info, 0, sizeof(int), st));
+  scatter_dense_kernel<T><<<cdiv(h.nnz, 256), 256, 0, st>>>((int)h.nnz, p->d_vals, p->d_slot_dst, p->d_slot_kind, Ad,
+                                                            Bs, K0U, KUU);
+  CEIT_COUNT_LAUNCH();
+  KERNEL_CHECK();
+  CUDA_TRY(cudaMemcpyAsync(Zw, K0U, N0 * nU * es, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(SU, KUU, nU * nU * es, cudaMemcpyDeviceToDevice, st));
+  auto n_of = [&](int64_t k) { return (int64_t)(h.blk_ptr[k + 1] - h.blk_ptr[k]); };
+  // forward sweep: block Cholesky + forward substitution of the nU right-hand sides
+  for (int64_t k = 0; k < h.nb; ++k) {
+    const int64_t nk = n_of(k), r0 = h.blk_ptr[k];
+    T* Ak = Ad + h.offD[k];
+    T* Lk = Ld + h.offD[k];
+    T* Lik = Linv + h.offD[k];
+    potrf_trtri_blocked<T>(st, nk, Ak, nk, 0, Lk, nk, 0, Lik, nk, 0, tmpPanel, 0, 1, p->d_info);
+    if (k > 0) {
+      const int64_t np = n_of(k - 1), rp = h.blk_ptr[k - 1];
+      // RHS_k -= Lsub_{k-1} Z_{k-1}   (Z_{k-1} lives in Xh rows of block k-1 during the forward sweep)
+      gemm<T>(st, 0, 0, nk, nU, np, mone, Lsub + h.offS[k - 1], np, 0, Xh + rp * nU, nU, 0, one, Zw + r0 * nU, nU, 0);
+    }
+    // Z_k = Linv_k RHS_k
+    gemm<T>(st, 0, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
+    if (k + 1 < h.nb) {
+      const int64_t nn = n_of(k + 1);
+      // Lsub_k = B_k Linv_k^T ; A_{k+1} -= Lsub_k Lsub_k^T
+      gemm<T>(st, 0, 1, nn, nk, nk, one, Bs + h.offS[k], nk, 0, Lik, nk, 0, zero, Lsub + h.offS[k], nk, 0);
+      gemm<T>(st, 0, 1, nn, nn, nk, mone, Lsub + h.offS[k], nk, 0, Lsub + h.offS[k], nk, 0, one, Ad + h.offD[k + 1],
+              nn, 0);
+    }
+  }
+  // backward sweep: X_k = Linv_k^T (Z_k - Lsub_k^T X_{k+1}); selected inverse blocks
+  for (int64_t k = h.nb - 1; k >= 0; --k) {
+    const int64_t nk = n_of(k), r0 = h.blk_ptr[k];
+    T* Lik = Linv + h.offD[k];
+    if (k + 1 < h.nb) {
+      const int64_t nn = n_of(k + 1), rn = h.blk_ptr[k + 1];
+      gemm<T>(st, 1, 0, nk, nU, nn, mone, Lsub + h.offS[k], nk, 0, Xh + rn * nU, nU, 0, one, Xh + r0 * nU, nU, 0);
+    }
+    // in-place is not allowed in the GEMM: go through Zw rows of this block
+    CUDA_TRY(cudaMemcpyAsync(Zw + r0 * nU, Xh + r0 * nU, nk * nU * es, cudaMemcpyDeviceToDevice, st));
+    gemm<T>(st, 1, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
+    // Sd_k = Linv_k^T Linv_k
+    gemm<T>(st, 1, 0, nk, nk, nk, one, Lik, nk, 0, Lik, nk, 0, zero, Sd + h.offD[k], nk, 0);
+    if (k + 1 < h.nb) {
+      const int64_t nn = n_of(k + 1);
+      // P = Lsub_k Linv_k ; So_k = -Sd_{k+1} P ; Sd_k -= P^T So_k
+      gemm<T>(st, 0, 0, nn, nk, nk, one, Lsub + h.offS[k], nk, 0, Lik, nk, 0, zero, Ptmp, nk, 0);
+      gemm<T>(st, 0, 0, nn, nk, nn, mone, Sd + h.offD[k + 1], nn, 0, Ptmp, nk, 0, zero, So + h.offS[k], nk, 0);
+      gemm<T>(st, 1, 0, nk, nk, nn, mone, Ptmp, nk, 0, So + h.offS[k], nk, 0, one, Sd + h.offD[k], nk, 0);
+    }
+  }
+  // S_U = K_UU - K_0U^T X
+  gemm<T>(st, 1, 0, nU, nU, N0, mone, K0U, nU, 0, Xh, nU, 0, one, SU, nU, 0);
+  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, st>>>((int)nU, Xh + N0 * nU);
+  CEIT_COUNT_LAUNCH();
+  gather_g0_kernel<T><<<cdiv(6 * h.E, 256), 256, 0, st>>>(6 * h.E, p->d_g0_off, Sel, g0e);
+  CEIT_COUNT_LAUNCH();
+  KERNEL_CHECK();
+  p->mode = Sc<T>::is_complex ? 2 : 1;
+  return 0;
+}
+
+// ---- per-excitation stage for excitations [i0, i0+nb) into workspace slots [0, nb) -------------------
+template <class T>
+int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
+  const HostPlan& h = p->h;
+  const int64_t nU = h.nU, N = h.N, N0 = h.N0, u2 = nU * nU;
+  T *St = (T*)p->St, *Ls = (T*)p->Ls, *Linvs = (T*)p->Linvs, *Sinv = (T*)p->Sinv, *Yh = (T*)p->Yh;
+  T *phi0 = (T*)p->phi0, *tvec = (T*)p->tvec, *tmpS = (T*)p->tmpS, *Xh = (T*)p->Xh, *SU = (T*)p->SU;
+  const T one = Sc<T>::one(), zero = Sc<T>::zero();
+  const size_t es = sizeof(T);
+  dim3 g2(cdiv(u2, 256), nbatch);
+  build_stilde_kernel<T><<<g2, 256, 0, st>>>((int)nU, SU, p->d_inB, i0, St);
+  CEIT_COUNT_LAUNCH();
+  CUDA_TRY(cudaMemsetAsync(Ls, 0, nbatch * u2 * es, st));
+  CUDA_TRY(cudaMemsetAsync(Linvs, 0, nbatch * u2 * es, st));
+  potrf_trtri_blocked<T>(st, nU, St, nU, u2, Ls, nU, u2, Linvs, nU, u2, tmpS, (int64_t)TILE * nU, nbatch, p->d_info);
+  gemm<T>(st, 1, 0, nU, nU, nU, one, Linvs, nU, u2, Linvs, nU, u2, zero, Sinv, nU, u2, nbatch);
+  mask_sinv_kernel<T><<<g2, 256, 0, st>>>((int)nU, p->d_inB, i0, Sinv);
+  CEIT_COUNT_LAUNCH();
+  // Yh[b] = Xh Sinv[b]
+  gemm<T>(st, 0, 0, N, nU, nU, one, Xh, nU, 0, Sinv, nU, u2, zero, Yh, nU, N * nU, nbatch);
+  dim3 g3(cdiv(nU, 8), nbatch);
+  phi_u_kernel<T><<<g3, 256, 0, st>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 0);
+  CEIT_COUNT_LAUNCH();
+  phi_u_kernel<T><<<g3, 256, 0, st>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 1);
+  CEIT_COUNT_LAUNCH();
+  dim3 g4(cdiv(N0, 8), nbatch);
+  phi_f_kernel<T><<<g4, 256, 0, st>>>(N0, (int)nU, Xh, phi0, N);
+  CEIT_COUNT_LAUNCH();
+  KERNEL_CHECK();
+  return 0;
+}
+
+int excitation_chunk_cap(const ceit_plan* p, size_t es) {
+  const HostPlan& h = p->h;
+  const double budget = 24.0e9;  // bytes of Yh kept at once
+  double per = (double)h.N * h.nU * es + 4.0 * h.nU * h.nU * es;
+  int cap = (int)std::max(1.0, std::min((double)h.L, budget / per));
+  return cap;
+}
+
+template <class T>
+int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, int64_t e_to, double c, double omega,
+                  double* J, int64_t ldJ, double* base, cudaStream_t st) {
+  const HostPlan& h = p->h;
+  const int cap = std::min<int64_t>(excitation_chunk_cap(p, sizeof(T)), i_to - i_from);
+  int rc = alloc_excitation_ws<T>(p, cap);
+  if (rc) return rc;
+  const int warps = 8;
+  const size_t smem = (size_t)warps * h.nU * sizeof(double);
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(woodbury_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int64_t i0 = i_from; i0 < i_to; i0 += cap) {
+    const int nbatch = (int)std::min<int64_t>(cap, i_to - i0);
+    rc = excitation_impl<T>(p, (int)i0, nbatch, st);
+    if (rc) return rc;
+    if (base) {
+      baseline_kernel<T><<<nbatch, 64, 0, st>>>((int)h.L, (int)h.nU, h.N, h.N0, (const T*)p->phi0, p->d_we_ptr,
+                                                p->d_we_u, p->d_we_w, (int)i0, base, nullptr);
+      CEIT_COUNT_LAUNCH();
+    }
+    if (e_to > e_from && J) {
+      dim3 grid(cdiv(e_to - e_from, warps), nbatch);
+      woodbury_kernel<T><<<grid, warps * 32, smem, st>>>((int)e_from, (int)e_to, (int)h.L, (int)h.nU, h.N, h.N0,
+                                                         p->d_elem_pos, p->d_area, (const T*)p->g0e, (const T*)p->Xh,
+                                                         (const T*)p->Yh, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
+                                                         p->d_we_w, (int)i0, 2.0 * omega * c, J, ldJ);
+      CEIT_COUNT_LAUNCH();
+    }
+    KERNEL_CHECK();
+  }
+  return 0;
+}
+
+template <class T>
+int forward_impl(ceit_plan* p, int64_t i, double* node_abs, double* elem_pot, double* electrode_pot,
+                 cudaStream_t st) {
+  const HostPlan& h = p->h;
+  int rc = alloc_excitation_ws<T>(p, std::max(1, p->ex_cap));
+  if (rc) return rc;
+  rc = excitation_impl<T>(p, (int)i, 1, st);
+  if (rc) return rc;
+  if (electrode_pot) {
+    baseline_kernel<T><<<1, 64, 0, st>>>((int)h.L, (int)h.nU, h.N, h.N0, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
+                                         p->d_we_w, (int)i, nullptr, electrode_pot);
+    CEIT_COUNT_LAUNCH();
+  }
+  if (node_abs || elem_pot) {
+    double* na = node_abs;
+    if (!na) {
+      if (!p->d_node_abs) {
+        rc = dev_alloc(p, (void**)&p->d_node_abs, h.N * sizeof(double));
+        if (rc) return rc;
+      }
+      na = p->d_node_abs;
+    }
+    node_abs_kernel<T><<<cdiv(h.N, 256), 256, 0, st>>>(h.N, (const T*)p->phi0, p->d_pos, na);
+    CEIT_COUNT_LAUNCH();
+    if (elem_pot) {
+      elem_mean_kernel<<<cdiv(h.E, 256), 256, 0, st>>>(h.E, p->d_elem, na, elem_pot);
+      CEIT_COUNT_LAUNCH();
+    }
+  }
+  KERNEL_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+// ====================================================================================================
+extern "C" {
+
+const char* ceit_last_error(void) { return ceit::g_err.c_str(); }
+int ceit_version(void) { return 100; }
+int64_t ceit_launch_count(void) { return ceit::g_launches.load(); }
+
+int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_t E, const int64_t* el_ptr,
+                     const int64_t* el_elems, int64_t L, int64_t target_block, int upload, ceit_plan_t** out) {
+  if (!nodes || !elem || !el_ptr || !el_elems || !out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_create: null argument");
+  ceit_plan* p = new ceit_plan();
+  try {
+    build_host_plan(p->h, nodes, elem, N, E, el_ptr, el_elems, L, target_block);
+  } catch (const std::exception& e) {
+    delete p;
+    CEIT_FAIL(CEIT_ERR_ARG, e.what());
+  }
+  if (upload) {
+    int rc = upload_plan(p);
+    if (rc) {
+      ceit_plan_destroy(p);
+      return rc;
+    }
+  }
+  *out = p;
+  return CEIT_OK;
+}
+
+int ceit_plan_destroy(ceit_plan_t* p) {
+  if (!p) return CEIT_OK;
+  for (void* a : p->allocs)
+    if (a) cudaFree(a);
+  delete p;
+  return CEIT_OK;
+}
+
+int ceit_plan_info(const ceit_plan_t* p, int64_t* info) {
+  if (!p || !info) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_info: null argument");
+  const HostPlan& h = p->h;
+  std::memset(info, 0, 16 * sizeof(int64_t));
+  info[0] = h.N; info[1] = h.E; info[2] = h.L; info[3] = h.nU; info[4] = h.N0; info[5] = h.nb;
+  info[6] = h.max_block; info[7] = h.nnz; info[8] = h.n_levels; info[9] = h.szD; info[10] = h.szS;
+  info[11] = (int64_t)p->dev_bytes; info[12] = p->mode;
+  if (p->uploaded && p->d_info) {
+    int flag = 0;
+    if (cudaMemcpy(&flag, p->d_info, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) info[13] = flag;
+  }
+  return CEIT_OK;
+}
+
+int ceit_plan_tables(const ceit_plan_t* p, int64_t* rowptr, int64_t* colidx, int64_t* pos, int64_t* blk_ptr,
+                     int64_t* U) {
+  if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_tables: null plan");
+  const HostPlan& h = p->h;
+  if (rowptr) for (int64_t k = 0; k <= h.N; ++k) rowptr[k] = h.rowptr[k];
+  if (colidx) for (int64_t k = 0; k < h.nnz; ++k) colidx[k] = h.colidx[k];
+  if (pos) for (int64_t k = 0; k < h.N; ++k) pos[k] = h.pos[k];
+  if (blk_ptr) for (int64_t k = 0; k <= h.nb; ++k) blk_ptr[k] = h.blk_ptr[k];
+  if (U) for (int64_t k = 0; k < h.nU; ++k) U[k] = h.U[k];
+  return CEIT_OK;
+}
+
+int ceit_assemble(ceit_plan_t* p, const double* perm, const double* var, double omega, double* vals,
+                  double* elem_param, void* stream) {
+  if (!p || !perm || !var) CEIT_FAIL(CEIT_ERR_ARG, "ceit_assemble: null argument");
+  if (!p->uploaded) CEIT_FAIL(CEIT_ERR_STATE, "ceit_assemble: plan has no device tables (created with upload=0)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const HostPlan& h = p->h;
+  assemble_csr_kernel<<<cdiv(h.nnz, 256), 256, 0, st>>>((int)h.nnz, p->d_src_ptr, p->d_src, p->d_nodes, p->d_elem,
+                                                        perm, var, omega, p->d_vals);
+  CEIT_COUNT_LAUNCH();
+  KERNEL_CHECK();
+  if (vals) CUDA_TRY(cudaMemcpyAsync(vals, p->d_vals, h.nnz * sizeof(cd), cudaMemcpyDeviceToDevice, st));
+  if (elem_param) {
+    elem_param_kernel<<<cdiv(h.E, 256), 256, 0, st>>>((int)h.E, p->d_nodes, p->d_elem, elem_param, nullptr);
+    CEIT_COUNT_LAUNCH();
+    KERNEL_CHECK();
+  }
+  p->assembled = true;
+  p->mode = 0;
+  return CEIT_OK;
+}
+
+int ceit_factor(ceit_plan_t* p, int is_complex, void* stream) {
+  if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_factor: null plan");
+  if (!p->assembled) CEIT_FAIL(CEIT_ERR_STATE, "ceit_factor: call ceit_assemble first");
+  cudaStream_t st = (cudaStream_t)stream;
+  return is_complex ? factor_impl<cd>(p, st) : factor_impl<double>(p, st);
+}
+
+int ceit_jacobian_block(ceit_plan_t* p, int64_t i_from, int64_t i_to, int64_t e_from, int64_t e_to, double c,
+                        double omega, double* J, int64_t ldJ, double* base, void* stream) {
+  if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_jacobian_block: null plan");
+  if (p->mode == 0) CEIT_FAIL(CEIT_ERR_STATE, "ceit_jacobian_block: call ceit_factor first");
+  const HostPlan& h = p->h;
+  if (i_from < 0 || i_to > h.L || i_from > i_to || e_from < 0 || e_to > h.E || e_from > e_to)
+    CEIT_FAIL(CEIT_ERR_ARG, "ceit_jacobian_block: range out of bounds");
+  if (J && ldJ < h.E) CEIT_FAIL(CEIT_ERR_ARG, "ceit_jacobian_block: ldJ < E");
+  if (i_from == i_to) return CEIT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  return p->mode == 2 ? jacobian_impl<cd>(p, i_from, i_to, e_from, e_to, c, omega, J, ldJ, base, st)
+                      : jacobian_impl<double>(p, i_from, i_to, e_from, e_to, c, omega, J, ldJ, base, st);
+}
+
+int ceit_forward(ceit_plan_t* p, int64_t i, double* node_abs, double* elem_pot, double* electrode_pot,
+                 void* stream) {
+  if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_forward: null plan");
+  if (p->mode == 0) CEIT_FAIL(CEIT_ERR_STATE, "ceit_forward: call ceit_factor first");
+  if (i < 0 || i >= p->h.L) CEIT_FAIL(CEIT_ERR_ARG, "ceit_forward: electrode index out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  return p->mode == 2 ? forward_impl<cd>(p, i, node_abs, elem_pot, electrode_pot, st)
+                      : forward_impl<double>(p, i, node_abs, elem_pot, electrode_pot, st);
+}
+
+int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* det_idx, int64_t n_det,
+                       const int64_t* rows, int64_t m_sel, double shift, double lambda, int form, double scale_,
+                       double* inv_out, void* stream) {
+  if (!J || !det_idx || !inv_out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_model: null argument");
+  if (m <= 0 || n_det <= 0 || ldJ <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_model: bad shape");
+  if (!rows) m_sel = m;
+  if (m_sel <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_model: empty row selection");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (form == 0) form = (m_sel <= n_det) ? 2 : 1;
+  const int64_t n = (form == 2) ? m_sel : n_det;  // size of the SPD system
+  double *Jt = nullptr, *G = nullptr, *Lg = nullptr, *Li = nullptr, *Gi = nullptr, *tmp = nullptr;
+  int* info = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&Jt, m_sel * n_det * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&G, n * n * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&Lg, n * n * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&Li, n * n * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&Gi, std::max(n * n, n_det * m_sel) * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&tmp, (int64_t)TILE * n * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&info, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(Lg, 0, n * n * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(Li, 0, n * n * sizeof(double), st));
+  gather_shift_kernel<<<cdiv(m_sel * n_det, 256), 256, 0, st>>>(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
+  CEIT_COUNT_LAUNCH();
+  if (form == 2) {
+    // G = Jt Jt^T + lambda^2 I (m x m);  inv = Jt^T G^-1
+    gemm<double>(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0);
+    add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, G, n);
+    CEIT_COUNT_LAUNCH();
+    potrf_trtri_blocked<double>(st, n, G, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info);
+    gemm<double>(st, 1, 0, n, n, n, 1.0, Li, n, 0, Li, n, 0, 0.0, Gi, n, 0);
+    gemm<double>(st, 1, 0, n_det, m_sel, m_sel, scale_, Jt, n_det, 0, Gi, n, 0, 0.0, inv_out, m_sel, 0);
+  } else {
+    // A = Jt^T Jt + lambda^2 I (n_det x n_det); inv = Linv^T (Linv Jt^T)
+    gemm<double>(st, 1, 0, n, n, m_sel, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0);
+    add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, G, n);
+    CEIT_COUNT_LAUNCH();
+    potrf_trtri_blocked<double>(st, n, G, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info);
+    gemm<double>(st, 0, 1, n, m_sel, n, 1.0, Li, n, 0, Jt, n_det, 0, 0.0, Gi, m_sel, 0);
+    gemm<double>(st, 1, 0, n, m_sel, n, scale_, Li, n, 0, Gi, m_sel, 0, 0.0, inv_out, m_sel, 0);
+  }
+  KERNEL_CHECK();
+  CUDA_TRY(cudaFreeAsync(Jt, st));
+  CUDA_TRY(cudaFreeAsync(G, st));
+  CUDA_TRY(cudaFreeAsync(Lg, st));
+  CUDA_TRY(cudaFreeAsync(Li, st));
+  CUDA_TRY(cudaFreeAsync(Gi, st));
+  CUDA_TRY(cudaFreeAsync(tmp, st));
+  CUDA_TRY(cudaFreeAsync(info, st));
+  return CEIT_OK;
+}
+
+int ceit_reconstruct(const double* inv, const double* dV, double* out, int64_t n_det, int64_t m, int64_t F,
+                     void* stream) {
+  if (!inv || !dV || !out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_reconstruct: null argument");
+  if (n_det <= 0 || m <= 0 || F <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_reconstruct: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (F == 1) {
+    gemv_rows_kernel<<<cdiv(n_det, 8), 256, 0, st>>>(n_det, (int)m, inv, dV, out);
+    CEIT_COUNT_LAUNCH();
+  } else {
+    gemm<double>(st, 0, 0, n_det, F, m, 1.0, inv, m, 0, dV, F, 0, 0.0, out, F, 0);
+  }
+  KERNEL_CHECK();
+  return CEIT_OK;
+}
+
+int ceit_dgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+               const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream) {
+  if (!A || !B || !C) CEIT_FAIL(CEIT_ERR_ARG, "ceit_dgemm: null argument");
+  gemm<double>((cudaStream_t)stream, opA, opB, M, N, K, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0);
+  KERNEL_CHECK();
+  return CEIT_OK;
+}
+
+int ceit_set_option(const char* name, int64_t value) {
+  if (!name) CEIT_FAIL(CEIT_ERR_ARG, "ceit_set_option: null name");
+  if (std::strcmp(name, "force_simt_gemm") == 0) {
+    ceit::g_force_simt = (int)value;
+    return CEIT_OK;
+  }
+  CEIT_FAIL(CEIT_ERR_ARG, std::string("ceit_set_option: unknown option ") + name);
+}
+
+}  // extern "C"

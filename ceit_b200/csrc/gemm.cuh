@@ -1,0 +1,293 @@
+// Dense row-major GEMM used by every dense step of the path (block Cholesky, selected inverse,
+// Schur complements, Y_i = Xh Sinv_i, inverse model, batched reconstruction):
+//     C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b],   b = 0..batch-1 (strided)
+//   * f64: FP64 tensor cores, mma.sync.aligned.m8n8k4.f64 (SASS DMMA).  tcgen05 has no f64
+//     kind, so on sm_100a DMMA *is* the FP64 tensor path.
+//   * complex f64: SIMT FMA tile kernel (same tiling, no tensor path yet).
+#pragma once
+#include <atomic>
+#include "scalar.cuh"
+
+namespace ceit {
+
+extern std::atomic<int64_t> g_launches;
+extern int g_force_simt;
+
+#define CEIT_COUNT_LAUNCH() (::ceit::g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// ------------------------------------------------------------------------------------------------
+// FP64 tensor-core kernel: CTA tile 64x64, BK = 16, 4 warps (2x2), warp tile 32x32 = 4x4 m8n8k4.
+// Shared-memory row strides are chosen == 4 (mod 16) doubles so the 16 lanes of a half-warp that
+// fetch one fragment hit 16 distinct 8-byte banks.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int OPA, int OPB>
+__global__ void __launch_bounds__(128)
+gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int64_t lda,
+                 int64_t sA, const double* __restrict__ B, int64_t ldb, int64_t sB, double beta,
+                 double* __restrict__ C, int64_t ldc, int64_t sC) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  constexpr int SA = (OPA == 0) ? BK + 4 : BM + 4;
+  constexpr int SB = (OPB == 0) ? BN + 4 : BK + 4;
+  __shared__ double As[2][1280];
+  __shared__ double Bs[2][1280];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  A += (int64_t)blockIdx.z * sA;
+  B += (int64_t)blockIdx.z * sB;
+  C += (int64_t)blockIdx.z * sC;
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  double ra[8], rb[8];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      int m, k;
+      if (OPA == 0) {
+        k = tid & 15;
+        m = (tid >> 4) + 8 * r;
+      } else {
+        m = tid & 63;
+        k = (tid >> 6) + 2 * r;
+      }
+      int gm = m0 + m, gk = k0 + k;
+      double v = 0.0;
+      if (gm < M && gk < K) v = (OPA == 0) ? A[(int64_t)gm * lda + gk] : A[(int64_t)gk * lda + gm];
+      ra[r] = v;
+      int n;
+      if (OPB == 0) {
+        n = tid & 63;
+        k = (tid >> 6) + 2 * r;
+      } else {
+        k = tid & 15;
+        n = (tid >> 4) + 8 * r;
+      }
+      int gn = n0 + n;
+      gk = k0 + k;
+      v = 0.0;
+      if (gn < N && gk < K) v = (OPB == 0) ? B[(int64_t)gk * ldb + gn] : B[(int64_t)gn * ldb + gk];
+      rb[r] = v;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      int m, k, n;
+      if (OPA == 0) {
+        k = tid & 15;
+        m = (tid >> 4) + 8 * r;
+        As[buf][m * SA + k] = ra[r];
+      } else {
+        m = tid & 63;
+        k = (tid >> 6) + 2 * r;
+        As[buf][k * SA + m] = ra[r];
+      }
+      if (OPB == 0) {
+        n = tid & 63;
+        k = (tid >> 6) + 2 * r;
+        Bs[buf][k * SB + n] = rb[r];
+      } else {
+        k = tid & 15;
+        n = (tid >> 4) + 8 * r;
+        Bs[buf][n * SB + k] = rb[r];
+      }
+    }
+  };
+
+  const int nk = (K + BK - 1) / BK;
+  if (nk > 0) {
+    load_tiles(0);
+    store_tiles(0);
+  }
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int m = wm + i * 8 + g, k = kk + t;
+        af[i] = (OPA == 0) ? As[buf][m * SA + k] : As[buf][k * SA + m];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int n = wn + j * 8 + g, k = kk + t;
+        bf[j] = (OPB == 0) ? Bs[buf][k * SB + n] : Bs[buf][n * SB + k];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    if (kt + 1 < nk) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int row = m0 + wm + i * 8 + g;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int col = n0 + wn + j * 8 + 2 * t;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (col + q < N) {
+          double* p = C + (int64_t)row * ldc + col + q;
+          double v = alpha * acc[i][j][q];
+          if (beta != 0.0) v = fma(beta, *p, v);
+          *p = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic SIMT tile kernel (any scalar type): 64x64 tile, BK = 16, 256 threads, 4x4 per thread.
+// ------------------------------------------------------------------------------------------------
+template <class T, int OPA, int OPB>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(int M, int N, int K, T alpha, const T* __restrict__ A, int64_t lda, int64_t sA,
+                 const T* __restrict__ B, int64_t ldb, int64_t sB, T beta, T* __restrict__ C,
+                 int64_t ldc, int64_t sC, int beta_zero) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ T As[BK][BM + 1];
+  __shared__ T Bs[BK][BN + 1];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  A += (int64_t)blockIdx.z * sA;
+  B += (int64_t)blockIdx.z * sB;
+  C += (int64_t)blockIdx.z * sC;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = Sc<T>::zero();
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int m, k;
+      if (OPA == 0) {
+        k = tid & 15;
+        m = (tid >> 4) + 16 * r;
+      } else {
+        m = tid & 63;
+        k = (tid >> 6) + 4 * r;
+      }
+      int gm = m0 + m, gk = k0 + k;
+      T v = Sc<T>::zero();
+      if (gm < M && gk < K) v = (OPA == 0) ? A[(int64_t)gm * lda + gk] : A[(int64_t)gk * lda + gm];
+      As[k][m] = v;
+      int n;
+      if (OPB == 0) {
+        n = tid & 63;
+        k = (tid >> 6) + 4 * r;
+      } else {
+        k = tid & 15;
+        n = (tid >> 4) + 16 * r;
+      }
+      int gn = n0 + n;
+      gk = k0 + k;
+      v = Sc<T>::zero();
+      if (gn < N && gk < K) v = (OPB == 0) ? B[(int64_t)gk * ldb + gn] : B[(int64_t)gn * ldb + gk];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma_(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int row = m0 + ty * 4 + i;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int col = n0 + tx * 4 + j;
+      if (col < N) {
+        T* p = C + (int64_t)row * ldc + col;
+        T v = mul(alpha, acc[i][j]);
+        if (!beta_zero) v = fma_(beta, *p, v);
+        *p = v;
+      }
+    }
+  }
+}
+
+inline bool is_zero(double a) { return a == 0.0; }
+inline bool is_zero(cd a) { return a.x == 0.0 && a.y == 0.0; }
+
+template <class T>
+inline void gemm_simt_launch(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K,
+                             T alpha, const T* A, int64_t lda, int64_t sA, const T* B, int64_t ldb,
+                             int64_t sB, T beta, T* C, int64_t ldc, int64_t sC, int batch) {
+  dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64), (unsigned)batch), block(256);
+  int bz = is_zero(beta) ? 1 : 0;
+#define CEIT_SIMT_CASE(a, b)                                                                      \
+  gemm_simt_kernel<T, a, b><<<grid, block, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, sA, B, \
+                                                    ldb, sB, beta, C, ldc, sC, bz)
+  if (opA == 0 && opB == 0) CEIT_SIMT_CASE(0, 0);
+  else if (opA == 0 && opB == 1) CEIT_SIMT_CASE(0, 1);
+  else if (opA == 1 && opB == 0) CEIT_SIMT_CASE(1, 0);
+  else CEIT_SIMT_CASE(1, 1);
+#undef CEIT_SIMT_CASE
+  CEIT_COUNT_LAUNCH();
+}
+
+// C[b] = alpha op(A[b]) op(B[b]) + beta C[b]; strides sA/sB/sC in elements (0 = shared operand).
+template <class T>
+inline void gemm(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, T alpha,
+                 const T* A, int64_t lda, int64_t sA, const T* B, int64_t ldb, int64_t sB, T beta,
+                 T* C, int64_t ldc, int64_t sC, int batch = 1) {
+  if (M <= 0 || N <= 0 || batch <= 0) return;
+  gemm_simt_launch<T>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+}
+
+template <>
+inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K,
+                         double alpha, const double* A, int64_t lda, int64_t sA, const double* B,
+                         int64_t ldb, int64_t sB, double beta, double* C, int64_t ldc, int64_t sC,
+                         int batch) {
+  if (M <= 0 || N <= 0 || batch <= 0) return;
+  if (g_force_simt) {
+    gemm_simt_launch<double>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+    return;
+  }
+  dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64), (unsigned)batch), block(128);
+#define CEIT_DMMA_CASE(a, b)                                                                     \
+  gemm_dmma_kernel<a, b><<<grid, block, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, sA, B,   \
+                                                 ldb, sB, beta, C, ldc, sC)
+  if (opA == 0 && opB == 0) CEIT_DMMA_CASE(0, 0);
+  else if (opA == 0 && opB == 1) CEIT_DMMA_CASE(0, 1);
+  else if (opA == 1 && opB == 0) CEIT_DMMA_CASE(1, 0);
+  else CEIT_DMMA_CASE(1, 1);
+#undef CEIT_DMMA_CASE
+  CEIT_COUNT_LAUNCH();
+}
+
+}  // namespace ceit

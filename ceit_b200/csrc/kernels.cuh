@@ -1,0 +1,383 @@
+// Path-specific kernels: element assembly (K1), dense scatter, Schur/Woodbury helpers and the
+// per-(excitation, element) Woodbury kernel (K2).  All HBM-bound byte/f64 work: coalesced row reads,
+// warp-level reductions, no atomics on the data path.
+#pragma once
+#include "gemm.cuh"
+
+namespace ceit {
+
+// ------------------------------------------------------------------------------------------------
+// K1  element matrices -> CSR values, deterministic gather form.
+// One thread per CSR slot sums the (element, a, b) contributions listed for it in ascending element
+// order, recomputing the linear-triangle gradients from the node coordinates:
+//   k_ab = perm_e (b_a b_b + c_a c_b) 4A  +  j omega var_e A (1/6 | 1/12)       (CEIT/EFEM.py:59-65)
+//   K[n_a, n_b] += 2 k_ab                                                        (EFEM.py:61-62,66-67)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tri_geometry(const double* __restrict__ nodes, const int32_t* __restrict__ elem,
+                                             int e, double& area, double b[3], double c[3], double& xb,
+                                             double& yb) {
+  const int n0 = elem[3 * e], n1 = elem[3 * e + 1], n2 = elem[3 * e + 2];
+  const double2 p0 = reinterpret_cast<const double2*>(nodes)[n0];
+  const double2 p1 = reinterpret_cast<const double2*>(nodes)[n1];
+  const double2 p2 = reinterpret_cast<const double2*>(nodes)[n2];
+  const double det = p0.x * (p1.y - p2.y) - p0.y * (p1.x - p2.x) + (p1.x * p2.y - p2.x * p1.y);
+  const double id = 1.0 / det;
+  area = fabs(det * 0.5);
+  b[0] = (p1.y - p2.y) * id;
+  b[1] = (p2.y - p0.y) * id;
+  b[2] = (p0.y - p1.y) * id;
+  c[0] = (p2.x - p1.x) * id;
+  c[1] = (p0.x - p2.x) * id;
+  c[2] = (p1.x - p0.x) * id;
+  xb = (p0.x + p1.x + p2.x) / 3.0;
+  yb = (p0.y + p1.y + p2.y) / 3.0;
+}
+
+__global__ void __launch_bounds__(256)
+assemble_csr_kernel(int nnz, const int32_t* __restrict__ src_ptr, const int32_t* __restrict__ src,
+                    const double* __restrict__ nodes, const int32_t* __restrict__ elem,
+                    const double* __restrict__ perm, const double* __restrict__ var, double omega,
+                    cd* __restrict__ vals) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nnz) return;
+  double re = 0.0, im = 0.0;
+  for (int q = src_ptr[s]; q < src_ptr[s + 1]; ++q) {
+    const int code = src[q];
+    const int e = code / 9, ab = code - 9 * e, a = ab / 3, bb = ab - 3 * a;
+    double area, b[3], c[3], xb, yb;
+    tri_geometry(nodes, elem, e, area, b, c, xb, yb);
+    const double kst = perm[e] * (b[a] * b[bb] + c[a] * c[bb]) * (4.0 * area);
+    const double kms = (a == bb) ? (omega * var[e] * area / 6.0) : (omega * var[e] * area / 12.0);
+    re += 2.0 * kst;   // added to [i][j] and [j][i]; the pattern lists both orders
+    im += 2.0 * kms;
+  }
+  vals[s] = mk(re, im);
+}
+
+__global__ void __launch_bounds__(256)
+elem_param_kernel(int E, const double* __restrict__ nodes, const int32_t* __restrict__ elem,
+                  double* __restrict__ param, double* __restrict__ area_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  double area, b[3], c[3], xb, yb;
+  tri_geometry(nodes, elem, e, area, b, c, xb, yb);
+  if (area_out) area_out[e] = area;
+  if (param) {
+    double* p = param + 9 * (int64_t)e;
+    p[0] = area;
+    p[1] = b[0]; p[2] = b[1]; p[3] = b[2];
+    p[4] = c[0]; p[5] = c[1]; p[6] = c[2];
+    p[7] = xb; p[8] = yb;
+  }
+}
+
+// CSR values -> dense block storage (diag blocks, sub-diagonal blocks, K0U, KUU), type T.
+template <class T>
+__global__ void __launch_bounds__(256)
+scatter_dense_kernel(int nnz, const cd* __restrict__ vals, const int64_t* __restrict__ dst,
+                     const uint8_t* __restrict__ kind, T* __restrict__ Ad, T* __restrict__ Bs,
+                     T* __restrict__ K0U, T* __restrict__ KUU) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nnz) return;
+  const int k = kind[s];
+  if (k == 0) return;
+  const T v = Sc<T>::from_cd(vals[s]);
+  const int64_t d = dst[s];
+  if (k == 1) Ad[d] = v;
+  else if (k == 2) Bs[d] = v;
+  else if (k == 3) K0U[d] = v;
+  else KUU[d] = v;
+}
+
+// rows [N0, N) of Xh = -I
+template <class T>
+__global__ void fill_neg_identity_kernel(int nU, T* __restrict__ Xh_tail) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nU * nU) return;
+  const int r = q / nU, c = q - r * nU;
+  Xh_tail[q] = (r == c) ? neg(Sc<T>::one()) : Sc<T>::zero();
+}
+
+// g0e[e][q] = selected-inverse entry for the element's node pair, 0 if either node is an electrode node
+template <class T>
+__global__ void gather_g0_kernel(int64_t n, const int64_t* __restrict__ off, const T* __restrict__ Sel,
+                                 T* __restrict__ g0e) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  const int64_t o = off[q];
+  g0e[q] = (o < 0) ? Sc<T>::zero() : Sel[o];
+}
+
+// St[b] = S_U with the rows/cols of B_i replaced by identity (i = i0 + b)
+template <class T>
+__global__ void build_stilde_kernel(int nU, const T* __restrict__ SU, const uint8_t* __restrict__ inB, int i0,
+                                    T* __restrict__ St) {
+  const int b = blockIdx.y;
+  const uint8_t* mask = inB + (int64_t)(i0 + b) * nU;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nU * nU) return;
+  const int r = q / nU, c = q - r * nU;
+  T v = SU[q];
+  if (mask[r] || mask[c]) v = (r == c) ? Sc<T>::one() : Sc<T>::zero();
+  St[(int64_t)b * nU * nU + q] = v;
+}
+
+// zero rows/cols of B_i in Sinv[b]
+template <class T>
+__global__ void mask_sinv_kernel(int nU, const uint8_t* __restrict__ inB, int i0, T* __restrict__ Sinv) {
+  const int b = blockIdx.y;
+  const uint8_t* mask = inB + (int64_t)(i0 + b) * nU;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nU * nU) return;
+  const int r = q / nU, c = q - r * nU;
+  if (mask[r] || mask[c]) Sinv[(int64_t)b * nU * nU + q] = Sc<T>::zero();
+}
+
+// phiU[b] = -Sinv[b] * (sum_{u in B_i} SU[:,u]);  phiU[B_i] = 1.   One warp per row.
+template <class T>
+__global__ void __launch_bounds__(256)
+phi_u_kernel(int nU, const T* __restrict__ SU, const T* __restrict__ Sinv, const uint8_t* __restrict__ inB,
+             int i0, T* __restrict__ tvec, T* __restrict__ phi0, int64_t N, int64_t N0, int stage) {
+  const int b = blockIdx.y;
+  const uint8_t* mask = inB + (int64_t)(i0 + b) * nU;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= nU) return;
+  T acc = Sc<T>::zero();
+  if (stage == 0) {  // tvec[row] = sum_{u in B_i} SU[row][u]
+    const T* r = SU + (int64_t)row * nU;
+    for (int u = lane; u < nU; u += 32)
+      if (mask[u]) acc = add(acc, r[u]);
+  } else {           // phiU[row] = -sum_k Sinv[row][k] tvec[k]
+    const T* r = Sinv + (int64_t)b * nU * nU + (int64_t)row * nU;
+    const T* tv = tvec + (int64_t)b * nU;
+    for (int k = lane; k < nU; k += 32) acc = fma_(r[k], tv[k], acc);
+  }
+  cd a = to_cd(acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+    a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+  }
+  if (lane == 0) {
+    if (stage == 0) tvec[(int64_t)b * nU + row] = Sc<T>::from_cd(a);
+    else phi0[(int64_t)b * N + N0 + row] = mask[row] ? Sc<T>::one() : neg(Sc<T>::from_cd(a));
+  }
+}
+
+// phi0[b][row] = -sum_u X[row][u] phiU[b][u] for rows in F0. One warp per row.
+template <class T>
+__global__ void __launch_bounds__(256)
+phi_f_kernel(int64_t N0, int nU, const T* __restrict__ X, T* __restrict__ phi0, int64_t N) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N0) return;
+  const T* r = X + row * nU;
+  const T* pu = phi0 + (int64_t)b * N + N0;
+  T acc = Sc<T>::zero();
+  for (int u = lane; u < nU; u += 32) acc = fma_(r[u], pu[u], acc);
+  cd a = to_cd(acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+    a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+  }
+  if (lane == 0) phi0[(int64_t)b * N + row] = neg(Sc<T>::from_cd(a));
+}
+
+// electrode amplitudes of the unperturbed solution: base rows (m != i) and/or all L electrode values
+template <class T>
+__global__ void baseline_kernel(int L, int nU, int64_t N, int64_t N0, const T* __restrict__ phi0,
+                                const int32_t* __restrict__ we_ptr, const int32_t* __restrict__ we_u,
+                                const double* __restrict__ we_w, int i0, double* __restrict__ base,
+                                double* __restrict__ electrode_pot) {
+  const int b = blockIdx.x;
+  const int i = i0 + b;
+  const T* pu = phi0 + (int64_t)b * N + N0;
+  for (int m = threadIdx.x; m < L; m += blockDim.x) {
+    double s = 0.0;
+    for (int q = we_ptr[m]; q < we_ptr[m + 1]; ++q) s = fma(we_w[q], abs_(pu[we_u[q]]), s);
+    if (electrode_pot) electrode_pot[(int64_t)b * L + m] = s;
+    if (base && m != i) base[(int64_t)i * (L - 1) + m - (m > i ? 1 : 0)] = fabs(s);
+  }
+}
+
+// node / element amplitudes in ORIGINAL numbering (EFEM.sync_back_potential, FEMBasic.py:118-127)
+template <class T>
+__global__ void node_abs_kernel(int64_t N, const T* __restrict__ phi0, const int32_t* __restrict__ pos,
+                                double* __restrict__ node_abs) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < N) node_abs[v] = abs_(phi0[pos[v]]);
+}
+__global__ void elem_mean_kernel(int64_t E, const int32_t* __restrict__ elem, const double* __restrict__ node_abs,
+                                 double* __restrict__ elem_pot) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) elem_pot[e] = (node_abs[elem[3 * e]] + node_abs[elem[3 * e + 1]] + node_abs[elem[3 * e + 2]]) / 3.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  Woodbury kernel: one warp per (excitation, element).
+//   G   = G0e + Yh[p] Xh[p]^T                         (3x3, = Kff^-1 on the element's nodes)
+//   y   = (I + D G)^-1 D phi0[p],  D = j s M,  s = 2 omega c A_j,  M = (1 + I)/12
+//   dU  = Yh[p]^T y  (perturbation at the nU electrode nodes),  amp = |phi0_U + dU|
+//   J[i(L-1)+cnt(m), j] = | sum_u w[m,u] amp_u |,  m != i           (CEIT/EJAC.py:127-132)
+// Rows of electrode / Dirichlet nodes need no special case: Xh/Yh are padded so that the same
+// formula holds.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ cd cmul(cd a, cd b) { return mul(a, b); }
+__device__ __forceinline__ cd csub(cd a, cd b) { return sub(a, b); }
+__device__ __forceinline__ cd cadd(cd a, cd b) { return add(a, b); }
+
+__device__ __forceinline__ void solve3(const cd A[3][3], const cd r[3], cd y[3]) {
+  // adjugate / Cramer; A = I + small, no pivoting needed
+  const cd c00 = csub(cmul(A[1][1], A[2][2]), cmul(A[1][2], A[2][1]));
+  const cd c01 = csub(cmul(A[1][2], A[2][0]), cmul(A[1][0], A[2][2]));
+  const cd c02 = csub(cmul(A[1][0], A[2][1]), cmul(A[1][1], A[2][0]));
+  const cd det = cadd(cadd(cmul(A[0][0], c00), cmul(A[0][1], c01)), cmul(A[0][2], c02));
+  const cd idet = inv_(det);
+  const cd c10 = csub(cmul(A[0][2], A[2][1]), cmul(A[0][1], A[2][2]));
+  const cd c11 = csub(cmul(A[0][0], A[2][2]), cmul(A[0][2], A[2][0]));
+  const cd c12 = csub(cmul(A[0][1], A[2][0]), cmul(A[0][0], A[2][1]));
+  const cd c20 = csub(cmul(A[0][1], A[1][2]), cmul(A[0][2], A[1][1]));
+  const cd c21 = csub(cmul(A[0][2], A[1][0]), cmul(A[0][0], A[1][2]));
+  const cd c22 = csub(cmul(A[0][0], A[1][1]), cmul(A[0][1], A[1][0]));
+  // inverse = adj / det, adj[i][j] = cofactor[j][i]
+  y[0] = cmul(idet, cadd(cadd(cmul(c00, r[0]), cmul(c10, r[1])), cmul(c20, r[2])));
+  y[1] = cmul(idet, cadd(cadd(cmul(c01, r[0]), cmul(c11, r[1])), cmul(c21, r[2])));
+  y[2] = cmul(idet, cadd(cadd(cmul(c02, r[0]), cmul(c12, r[1])), cmul(c22, r[2])));
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+woodbury_kernel(int e_from, int e_to, int L, int nU, int64_t N, int64_t N0,
+                const int32_t* __restrict__ elem_pos, const double* __restrict__ area,
+                const T* __restrict__ g0e, const T* __restrict__ Xh, const T* __restrict__ Yh,
+                const T* __restrict__ phi0, const int32_t* __restrict__ we_ptr,
+                const int32_t* __restrict__ we_u, const double* __restrict__ we_w, int i0, double s_coef,
+                double* __restrict__ J, int64_t ldJ) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* amp = reinterpret_cast<double*>(smem_raw) + (int64_t)warp * nU;
+  const int b = blockIdx.y;
+  const int i = i0 + b;
+  const int j = e_from + blockIdx.x * warps + warp;
+  if (j >= e_to) return;   // whole warp exits together; no block-level sync below
+  const T* Y = Yh + (int64_t)b * N * nU;
+  const T* ph = phi0 + (int64_t)b * N;
+  const int p0 = elem_pos[3 * j], p1 = elem_pos[3 * j + 1], p2 = elem_pos[3 * j + 2];
+  const T* y0 = Y + (int64_t)p0 * nU;
+  const T* y1 = Y + (int64_t)p1 * nU;
+  const T* y2 = Y + (int64_t)p2 * nU;
+  const T* x0 = Xh + (int64_t)p0 * nU;
+  const T* x1 = Xh + (int64_t)p1 * nU;
+  const T* x2 = Xh + (int64_t)p2 * nU;
+  // ---- six dot products: (0,0) (1,1) (2,2) (0,1) (1,2) (2,0)
+  T d[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) d[q] = Sc<T>::zero();
+  for (int k = lane; k < nU; k += 32) {
+    const T a0 = y0[k], a1 = y1[k], a2 = y2[k];
+    const T b0 = x0[k], b1 = x1[k], b2 = x2[k];
+    d[0] = fma_(a0, b0, d[0]);
+    d[1] = fma_(a1, b1, d[1]);
+    d[2] = fma_(a2, b2, d[2]);
+    d[3] = fma_(a0, b1, d[3]);
+    d[4] = fma_(a1, b2, d[4]);
+    d[5] = fma_(a2, b0, d[5]);
+  }
+  cd G6[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    cd a = to_cd(d[q]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+      a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+    }
+    G6[q] = cadd(a, to_cd(g0e[6 * (int64_t)j + q]));
+  }
+  cd G[3][3];
+  G[0][0] = G6[0]; G[1][1] = G6[1]; G[2][2] = G6[2];
+  G[0][1] = G[1][0] = G6[3];
+  G[1][2] = G[2][1] = G6[4];
+  G[2][0] = G[0][2] = G6[5];
+  // ---- 3x3 system  (I + j s M G) y = j s M phi0[p]
+  const double s = s_coef * area[j];
+  const cd f[3] = {to_cd(ph[p0]), to_cd(ph[p1]), to_cd(ph[p2])};
+  cd A3[3][3], r[3], y[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    cd mr = mk(0.0, 0.0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double mac = (a == c) ? (2.0 / 12.0) : (1.0 / 12.0);
+      mr = cadd(mr, scale(mac, f[c]));
+    }
+    r[a] = mk(-s * mr.y, s * mr.x);   // j*s*mr
+#pragma unroll
+    for (int bb = 0; bb < 3; ++bb) {
+      cd mg = mk(0.0, 0.0);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double mac = (a == c) ? (2.0 / 12.0) : (1.0 / 12.0);
+        mg = cadd(mg, scale(mac, G[c][bb]));
+      }
+      cd v = mk(-s * mg.y, s * mg.x);
+      if (a == bb) v.x += 1.0;
+      A3[a][bb] = v;
+    }
+  }
+  solve3(A3, r, y);
+  // ---- perturbation at the electrode nodes, amplitude
+  const T* pu = ph + N0;
+  for (int k = lane; k < nU; k += 32) {
+    cd v = to_cd(pu[k]);
+    v = fma_(to_cd(y0[k]), y[0], v);
+    v = fma_(to_cd(y1[k]), y[1], v);
+    v = fma_(to_cd(y2[k]), y[2], v);
+    amp[k] = sqrt(fma(v.x, v.x, v.y * v.y));
+  }
+  __syncwarp();
+  for (int m = lane; m < L; m += 32) {
+    if (m == i) continue;
+    double acc = 0.0;
+    for (int q = we_ptr[m]; q < we_ptr[m + 1]; ++q) acc = fma(we_w[q], amp[we_u[q]], acc);
+    J[((int64_t)i * (L - 1) + m - (m > i ? 1 : 0)) * ldJ + j] = fabs(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// inverse model / realtime helpers
+// ------------------------------------------------------------------------------------------------
+// Jt[r][c] = J[rows[r]][det[c]] - shift           (Solver.py:76-86,119)
+__global__ void gather_shift_kernel(int64_t m_sel, int64_t n_det, const double* __restrict__ J, int64_t ldJ,
+                                    const int64_t* __restrict__ rows, const int64_t* __restrict__ det,
+                                    double shift, double* __restrict__ Jt) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m_sel * n_det) return;
+  const int64_t r = q / n_det, c = q - r * n_det;
+  const int64_t rr = rows ? rows[r] : r;
+  Jt[q] = J[rr * ldJ + det[c]] - shift;
+}
+__global__ void add_diag_kernel(int64_t n, double v, double* __restrict__ A, int64_t lda) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) A[q * lda + q] += v;
+}
+// out[r] = sum_k inv[r][k] dV[k]; one warp per row (single-frame Solver.solve)
+__global__ void __launch_bounds__(256)
+gemv_rows_kernel(int64_t n_det, int m, const double* __restrict__ inv, const double* __restrict__ dV,
+                 double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_det) return;
+  const double* r = inv + row * m;
+  double acc = 0.0;
+  for (int k = lane; k < m; k += 32) acc = fma(r[k], dV[k], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[row] = acc;
+}
+
+}  // namespace ceit

@@ -1,0 +1,273 @@
+// Host-side symbolic analysis for the CEIT hot path (pure C++).
+//
+// What the reference recomputes inside every one of its L*E forward solves - the Dirichlet node
+// set of the excitation electrode (CEIT/EFEM.py:79-86), the row/column swaps that move it to the
+// tail (EFEM.py:87-96,136-142), the node->element->electrode averaging (CEIT/FEMBasic.py:118-137)
+// - is turned here, once per mesh, into static index tables.  Nothing below is a translation of
+// reference code: the reference has no ordering, no sparse pattern and no electrode-node union.
+#include "plan.h"
+
+#include <algorithm>
+#include <cstring>
+#include <stdexcept>
+
+namespace ceit {
+
+namespace {
+
+// BFS over nodes with keep[v] && committed[v] < 0; fills `levels` (each sorted ascending).
+void bfs_levels(const std::vector<int32_t>& rowptr, const std::vector<int32_t>& colidx,
+                const std::vector<uint8_t>& keep, const std::vector<int32_t>& committed,
+                std::vector<int32_t>& stamp, int32_t stamp_val, int32_t start,
+                std::vector<std::vector<int32_t>>& levels) {
+  levels.clear();
+  std::vector<int32_t> frontier{start};
+  stamp[start] = stamp_val;
+  while (!frontier.empty()) {
+    levels.push_back(frontier);
+    std::vector<int32_t> next;
+    for (int32_t v : frontier) {
+      for (int32_t q = rowptr[v]; q < rowptr[v + 1]; ++q) {
+        int32_t w = colidx[q];
+        if (keep[w] && committed[w] < 0 && stamp[w] != stamp_val) {
+          stamp[w] = stamp_val;
+          next.push_back(w);
+        }
+      }
+    }
+    std::sort(next.begin(), next.end());
+    frontier.swap(next);
+  }
+}
+
+}  // namespace
+
+void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
+                     const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
+                     int64_t target_block) {
+  if (N <= 0 || E <= 0 || L <= 0) throw std::runtime_error("plan: N, E, L must be positive");
+  if (N > (int64_t)2000000000 / 16 || E > (int64_t)2000000000 / 16)
+    throw std::runtime_error("plan: mesh too large for 32-bit indices");
+  if (target_block <= 0) target_block = 192;
+  p.N = N;
+  p.E = E;
+  p.L = L;
+  p.nodes.assign(nodes, nodes + 2 * N);
+  p.elem.resize(3 * E);
+  for (int64_t k = 0; k < 3 * E; ++k) {
+    if (elem[k] < 0 || elem[k] >= N) throw std::runtime_error("plan: element node index out of range");
+    p.elem[k] = (int32_t)elem[k];
+  }
+  // ---- electrodes: element lists, node sets, union U, weights --------------------------------
+  p.el_ptr.resize(L + 1);
+  for (int64_t i = 0; i <= L; ++i) p.el_ptr[i] = (int32_t)el_ptr[i];
+  if (el_ptr[0] != 0) throw std::runtime_error("plan: el_ptr[0] must be 0");
+  p.el_elems.resize(el_ptr[L]);
+  for (int64_t k = 0; k < el_ptr[L]; ++k) {
+    if (el_elems[k] < 0 || el_elems[k] >= E) throw std::runtime_error("plan: electrode element index out of range");
+    p.el_elems[k] = (int32_t)el_elems[k];
+  }
+  p.u_of.assign(N, -1);
+  p.U.clear();
+  std::vector<std::vector<int32_t>> node_sets(L);
+  for (int64_t i = 0; i < L; ++i) {
+    if (el_ptr[i + 1] <= el_ptr[i]) throw std::runtime_error("No element is selected, please check the input");
+    auto& s = node_sets[i];
+    for (int32_t q = p.el_ptr[i]; q < p.el_ptr[i + 1]; ++q)
+      for (int a = 0; a < 3; ++a) s.push_back(p.elem[3 * p.el_elems[q] + a]);
+    std::sort(s.begin(), s.end());
+    s.erase(std::unique(s.begin(), s.end()), s.end());
+    for (int32_t n : s)
+      if (p.u_of[n] < 0) {
+        p.u_of[n] = (int32_t)p.U.size();
+        p.U.push_back(n);
+      }
+  }
+  p.nU = (int64_t)p.U.size();
+  p.N0 = N - p.nU;
+  if (p.N0 <= 0) throw std::runtime_error("plan: every node belongs to an electrode");
+  p.inB.assign(L * p.nU, 0);
+  for (int64_t i = 0; i < L; ++i)
+    for (int32_t n : node_sets[i]) p.inB[i * p.nU + p.u_of[n]] = 1;
+  // weights: electrode_pot[m] = mean over its elements of mean over the 3 node amplitudes
+  p.we_ptr.assign(L + 1, 0);
+  p.we_u.clear();
+  p.we_w.clear();
+  {
+    std::vector<double> acc(p.nU, 0.0);
+    for (int64_t m = 0; m < L; ++m) {
+      int32_t cnt = p.el_ptr[m + 1] - p.el_ptr[m];
+      for (int32_t n : node_sets[m]) acc[p.u_of[n]] = 0.0;
+      for (int32_t q = p.el_ptr[m]; q < p.el_ptr[m + 1]; ++q)
+        for (int a = 0; a < 3; ++a) acc[p.u_of[p.elem[3 * p.el_elems[q] + a]]] += 1.0;
+      for (int32_t n : node_sets[m]) {
+        p.we_u.push_back(p.u_of[n]);
+        p.we_w.push_back(acc[p.u_of[n]] / (3.0 * cnt));
+      }
+      p.we_ptr[m + 1] = (int32_t)p.we_u.size();
+    }
+  }
+  // ---- CSR pattern of K: node adjacency incl. diagonal ---------------------------------------
+  {
+    std::vector<int32_t> deg(N + 1, 0);
+    for (int64_t e = 0; e < E; ++e)
+      for (int a = 0; a < 3; ++a) deg[p.elem[3 * e + a] + 1] += 3;
+    std::vector<int64_t> start(N + 1, 0);
+    for (int64_t v = 0; v < N; ++v) start[v + 1] = start[v] + deg[v + 1];
+    std::vector<int32_t> tmp(start[N]);
+    std::vector<int64_t> fill(start.begin(), start.end() - 1);
+    for (int64_t e = 0; e < E; ++e)
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) tmp[fill[p.elem[3 * e + a]]++] = p.elem[3 * e + b];
+    p.rowptr.assign(N + 1, 0);
+    p.colidx.clear();
+    p.colidx.reserve(7 * N);
+    for (int64_t v = 0; v < N; ++v) {
+      auto b = tmp.begin() + start[v], en = tmp.begin() + start[v + 1];
+      std::sort(b, en);
+      en = std::unique(b, en);
+      p.colidx.insert(p.colidx.end(), b, en);
+      p.rowptr[v + 1] = (int32_t)p.colidx.size();
+    }
+    p.nnz = (int64_t)p.colidx.size();
+  }
+  // ---- level sets of the F0 graph (pseudo-peripheral start, restart per component) ----------
+  std::vector<uint8_t> keep(N);
+  for (int64_t v = 0; v < N; ++v) keep[v] = p.u_of[v] < 0;
+  std::vector<int32_t> committed(N, -1), stamp(N, -1);
+  std::vector<std::vector<int32_t>> all_levels, lv;
+  int32_t stamp_val = 0;
+  for (int32_t s = 0; s < (int32_t)N; ++s) {
+    if (!keep[s] || committed[s] >= 0) continue;
+    bfs_levels(p.rowptr, p.colidx, keep, committed, stamp, stamp_val++, s, lv);
+    int32_t far = lv.back()[0];
+    bfs_levels(p.rowptr, p.colidx, keep, committed, stamp, stamp_val++, far, lv);
+    far = lv.back()[0];
+    bfs_levels(p.rowptr, p.colidx, keep, committed, stamp, stamp_val++, far, lv);
+    for (auto& l : lv) {
+      for (int32_t v : l) committed[v] = (int32_t)all_levels.size();
+      all_levels.push_back(l);
+    }
+  }
+  p.n_levels = (int64_t)all_levels.size();
+  // ---- merge consecutive levels into blocks of >= target_block nodes ------------------------
+  std::vector<std::vector<int32_t>> blocks;
+  {
+    std::vector<int32_t> cur;
+    for (auto& l : all_levels) {
+      cur.insert(cur.end(), l.begin(), l.end());
+      if ((int64_t)cur.size() >= target_block) {
+        blocks.push_back(cur);
+        cur.clear();
+      }
+    }
+    if (!cur.empty()) {
+      if (!blocks.empty() && (int64_t)cur.size() < target_block / 2)
+        blocks.back().insert(blocks.back().end(), cur.begin(), cur.end());
+      else
+        blocks.push_back(cur);
+    }
+  }
+  p.nb = (int64_t)blocks.size();
+  p.pos.assign(N, -1);
+  p.node_at.assign(N, -1);
+  p.blk_ptr.assign(p.nb + 1, 0);
+  p.blk_of.assign(p.N0, 0);
+  p.max_block = 0;
+  {
+    int32_t q = 0;
+    for (int64_t k = 0; k < p.nb; ++k) {
+      for (int32_t v : blocks[k]) {
+        p.pos[v] = q;
+        p.node_at[q] = v;
+        p.blk_of[q] = (int32_t)k;
+        ++q;
+      }
+      p.blk_ptr[k + 1] = q;
+      p.max_block = std::max<int64_t>(p.max_block, (int64_t)blocks[k].size());
+    }
+    if (q != p.N0) throw std::runtime_error("plan: level sets do not cover F0");
+    for (int64_t u = 0; u < p.nU; ++u) {
+      p.pos[p.U[u]] = (int32_t)(p.N0 + u);
+      p.node_at[p.N0 + u] = p.U[u];
+    }
+  }
+  p.offD.assign(p.nb + 1, 0);
+  p.offS.assign(p.nb + 1, 0);
+  for (int64_t k = 0; k < p.nb; ++k) {
+    int64_t nk = p.blk_ptr[k + 1] - p.blk_ptr[k];
+    p.offD[k + 1] = p.offD[k] + nk * nk;
+    int64_t nk1 = (k + 1 < p.nb) ? p.blk_ptr[k + 2] - p.blk_ptr[k + 1] : 0;
+    p.offS[k + 1] = p.offS[k] + nk1 * nk;
+  }
+  p.szD = p.offD[p.nb];
+  p.szS = p.offS[p.nb];
+  auto bsz = [&](int64_t k) { return (int64_t)(p.blk_ptr[k + 1] - p.blk_ptr[k]); };
+  // offset of the pair (positions pa, pb < N0) inside [diag blocks | sub-diagonal blocks]
+  auto pair_off = [&](int32_t pa, int32_t pb) -> int64_t {
+    int32_t ka = p.blk_of[pa], kb = p.blk_of[pb];
+    int64_t la = pa - p.blk_ptr[ka], lb = pb - p.blk_ptr[kb];
+    if (ka == kb) return p.offD[ka] + la * bsz(ka) + lb;
+    if (ka == kb + 1) return p.szD + p.offS[kb] + la * bsz(kb) + lb;
+    if (kb == ka + 1) return p.szD + p.offS[ka] + lb * bsz(ka) + la;
+    throw std::runtime_error("plan: ordering is not block-tridiagonal");
+  };
+  // ---- gather lists for the deterministic assembly + dense destinations ----------------------
+  p.src_ptr.assign(p.nnz + 1, 0);
+  p.src.assign(9 * E, 0);
+  {
+    std::vector<int32_t> slot_of(9 * E);
+    for (int64_t e = 0; e < E; ++e)
+      for (int a = 0; a < 3; ++a) {
+        int32_t r = p.elem[3 * e + a];
+        for (int b = 0; b < 3; ++b) {
+          int32_t c = p.elem[3 * e + b];
+          auto it = std::lower_bound(p.colidx.begin() + p.rowptr[r], p.colidx.begin() + p.rowptr[r + 1], c);
+          int32_t s = (int32_t)(it - p.colidx.begin());
+          slot_of[9 * e + 3 * a + b] = s;
+          p.src_ptr[s + 1]++;
+        }
+      }
+    for (int64_t s = 0; s < p.nnz; ++s) p.src_ptr[s + 1] += p.src_ptr[s];
+    std::vector<int32_t> fill(p.src_ptr.begin(), p.src_ptr.end() - 1);
+    for (int64_t q = 0; q < 9 * E; ++q) p.src[fill[slot_of[q]]++] = (int32_t)q;  // ascending element order
+  }
+  p.slot_dst.assign(p.nnz, -1);
+  p.slot_kind.assign(p.nnz, 0);
+  for (int64_t r = 0; r < N; ++r)
+    for (int32_t s = p.rowptr[r]; s < p.rowptr[r + 1]; ++s) {
+      int32_t c = p.colidx[s];
+      int32_t pr = p.pos[r], pc = p.pos[c];
+      if (pr < p.N0 && pc < p.N0) {
+        int32_t kr = p.blk_of[pr], kc = p.blk_of[pc];
+        if (kr == kc) {
+          p.slot_kind[s] = 1;
+          p.slot_dst[s] = pair_off(pr, pc);
+        } else if (kr == kc + 1) {
+          p.slot_kind[s] = 2;
+          p.slot_dst[s] = pair_off(pr, pc) - p.szD;
+        } else if (kc != kr + 1) {
+          throw std::runtime_error("plan: ordering is not block-tridiagonal");
+        }
+      } else if (pr < p.N0) {
+        p.slot_kind[s] = 3;
+        p.slot_dst[s] = (int64_t)pr * p.nU + (pc - p.N0);
+      } else if (pc >= p.N0) {
+        p.slot_kind[s] = 4;
+        p.slot_dst[s] = (int64_t)(pr - p.N0) * p.nU + (pc - p.N0);
+      }
+    }
+  // ---- per-element positions and selected-inverse gather offsets -------------------------------
+  p.elem_pos.resize(3 * E);
+  p.g0_off.assign(6 * E, -1);
+  static const int PA[6] = {0, 1, 2, 0, 1, 2}, PB[6] = {0, 1, 2, 1, 2, 0};
+  for (int64_t e = 0; e < E; ++e) {
+    for (int a = 0; a < 3; ++a) p.elem_pos[3 * e + a] = p.pos[p.elem[3 * e + a]];
+    for (int q = 0; q < 6; ++q) {
+      int32_t pa = p.elem_pos[3 * e + PA[q]], pb = p.elem_pos[3 * e + PB[q]];
+      if (pa < p.N0 && pb < p.N0) p.g0_off[6 * e + q] = pair_off(pa, pb);
+    }
+  }
+}
+
+}  // namespace ceit

@@ -1,0 +1,45 @@
+// Host-side symbolic plan (pure C++, no CUDA): everything about a mesh + electrode layout that
+// does not depend on material values.  See include/ceit_b200.h and DESIGN.md §3.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace ceit {
+
+struct HostPlan {
+  int64_t N = 0, E = 0, L = 0;
+  int64_t nU = 0, N0 = 0, nb = 0, max_block = 0, nnz = 0, n_levels = 0;
+  std::vector<double> nodes;       // N*2
+  std::vector<int32_t> elem;       // E*3
+  // electrodes
+  std::vector<int32_t> el_ptr, el_elems;      // electrode -> elements
+  std::vector<int32_t> U;                     // electrode nodes, electrode order, first occurrence
+  std::vector<int32_t> u_of;                  // node -> index in U or -1
+  std::vector<uint8_t> inB;                   // L*nU: 1 if U-node is Dirichlet for excitation i
+  std::vector<int32_t> we_ptr, we_u;          // electrode -> (U index, weight) lists
+  std::vector<double> we_w;
+  // ordering
+  std::vector<int32_t> pos;                   // node -> position (F0 block order, then N0+u)
+  std::vector<int32_t> node_at;               // position -> node
+  std::vector<int32_t> blk_ptr;               // nb+1 (positions)
+  std::vector<int32_t> blk_of;                // N0: block of position
+  std::vector<int64_t> offD, offS;            // nb (+1): element offsets of diagonal / sub-diagonal blocks
+  int64_t szD = 0, szS = 0;                   // total elements in diag / sub-diag storage
+  // CSR pattern of K (original numbering) and deterministic gather lists
+  std::vector<int32_t> rowptr, colidx;        // N+1, nnz
+  std::vector<int32_t> src_ptr, src;          // nnz+1, 9E: source code = e*9 + a*3 + b
+  std::vector<int64_t> slot_dst;              // nnz: offset into the dense destination or -1
+  std::vector<uint8_t> slot_kind;             // 0 none, 1 diag block, 2 sub block, 3 K0U, 4 KUU
+  // per-element gather offsets into the selected inverse [Sd | So] for pairs
+  // (0,0),(1,1),(2,2),(0,1),(1,2),(2,0); -1 => 0
+  std::vector<int64_t> g0_off;                // E*6
+  std::vector<int32_t> elem_pos;              // E*3 node positions
+};
+
+// Throws std::runtime_error on invalid input.
+void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
+                     const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
+                     int64_t target_block);
+
+}  // namespace ceit

@@ -1,0 +1,128 @@
+/* ceit_b200 - C ABI of the B200-native CEIT Jacobian / Gauss-Newton hot path.
+ *
+ * The reference (zehao99/CEIT) is pure Python/numpy and has no FFI; the seam it offers is its
+ * Python class surface.  Every entry point below names the reference method whose arithmetic it
+ * replaces (file:line relative to the reference root).  The Python drop-in classes in
+ * `ceit_b200/` (EFEM, EJAC, Solver) call these through ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; `ceit_last_error()` gives the message
+ *     (thread-local, valid until the next failing call on that thread);
+ *   - pointers marked [host] are host memory, [dev] are device memory owned by the caller
+ *     (torch tensors used as plain buffers); nothing is retained past the call except what the
+ *     opaque plan owns (freed by ceit_plan_destroy);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it, no hidden sync unless
+ *     the function is documented as `_host` (those synchronise the stream before returning);
+ *   - matrices are row-major (C / numpy order); complex values are interleaved (re, im) f64;
+ *   - there is NO CPU fallback: every compute entry fails with CEIT_ERR_CUDA if no device.
+ */
+#ifndef CEIT_B200_H
+#define CEIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CEIT_OK 0
+#define CEIT_ERR_ARG (-1)
+#define CEIT_ERR_CUDA (-2)
+#define CEIT_ERR_STATE (-3)
+#define CEIT_ERR_NUMERIC (-4)
+
+typedef struct ceit_plan ceit_plan_t;
+
+const char* ceit_last_error(void);
+int ceit_version(void);
+/* number of this library's kernels launched by the calling process so far (bench `gpu_launches`) */
+int64_t ceit_launch_count(void);
+
+/* ---- plan: symbolic analysis of mesh + electrodes (host), static tables uploaded -----------
+ * Replaces the bookkeeping the reference redoes on every forward solve:
+ *   EFEM.set_boundary_condition / swap (CEIT/EFEM.py:71-96,136-142), FEMBasic.calc_init
+ *   (CEIT/FEMBasic.py:105-114) and the node->element->electrode averaging lists
+ *   (CEIT/FEMBasic.py:118-137).
+ * nodes [host] f64[N*2]; elem [host] i64[E*3] (0-based, MeshObj.elem, CEIT/models/mesh.py:31);
+ * el_ptr [host] i64[L+1], el_elems [host] i64[el_ptr[L]]: electrode_mesh (mesh.py:90-113).
+ * target_block: minimum nodes per diagonal block of the level-set block-tridiagonal ordering
+ * (<=0: default).  Works without a GPU when `upload` is 0 (host tables only, for CPU tests). */
+int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_t E,
+                     const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
+                     int64_t target_block, int upload, ceit_plan_t** out);
+int ceit_plan_destroy(ceit_plan_t* plan);
+
+/* info[0..15]: N, E, L, nU, N0, n_blocks, max_block, nnz, n_levels, sum n_k^2, sum n_k n_k+1,
+ *              device bytes held, factor state (0 none,1 real,2 complex), reserved... */
+int ceit_plan_info(const ceit_plan_t* plan, int64_t* info16);
+/* host copies of the symbolic tables (any pointer may be NULL):
+ * rowptr i64[N+1], colidx i64[nnz] (CSR pattern of K, sorted, == scipy.sparse.csr_matrix of the
+ * reference's dense K_sparse), pos i64[N] (node -> position: F0 nodes in block order, then U),
+ * blk_ptr i64[n_blocks+1], U i64[nU]. */
+int ceit_plan_tables(const ceit_plan_t* plan, int64_t* rowptr, int64_t* colidx, int64_t* pos,
+                     int64_t* blk_ptr, int64_t* U);
+
+/* ---- K1: element matrices -> CSR values ------------------------------------------------------
+ * Replaces EFEM.construct_sparse_matrix (CEIT/EFEM.py:47-69) incl. its uniform factor 2 and the
+ * per-element geometry of MeshObj.initialize_parameters (CEIT/models/mesh.py:41-75).
+ * perm [dev] f64[E] (= mesh.elem_perm, already scaled by 1/resistance, FEMBasic.py:57-58),
+ * var [dev] f64[E] (= elem_variable), omega = 2*pi*signal_frequency (FEMBasic.py:60).
+ * vals [dev] complex f64[nnz] (may be NULL: only the internal block storage is filled).
+ * elem_param [dev] f64[E*9] optional output: [A,b0,b1,b2,c0,c1,c2,xbar,ybar] (mesh.py:70-71). */
+int ceit_assemble(ceit_plan_t* plan, const double* perm, const double* var, double omega,
+                  double* vals, double* elem_param, void* stream);
+
+/* ---- K3: base stage (factor once per material state) ------------------------------------------
+ * Replaces the np.linalg.inv(K_ff) of EVERY forward solve (CEIT/EFEM.py:111-119): block Cholesky
+ * of K00 = K[F0,F0], X = K00^-1 K0U, S_U, selected inverse on the mesh pattern.
+ * is_complex: 0 = real path (requires var == 0 everywhere), 1 = complex symmetric path. */
+int ceit_factor(ceit_plan_t* plan, int is_complex, void* stream);
+
+/* ---- K2: Jacobian block ------------------------------------------------------------------------
+ * Replaces EJAC.JAC_calculation's double loop (CEIT/EJAC.py:115-133): for excitations
+ * [i_from,i_to) (calc_from/calc_end semantics) and elements [e_from,e_to): perturb element j by
+ * c = variable_change_for_JAC, solve, store |electrode_potential[m]|, m != i ascending, at
+ * J[(i*(L-1)+cnt) * ldJ + j].  J [dev] f64, row-major, ldJ >= E.
+ * base [dev] f64[L*(L-1)] optional: electrode_original_potential (EJAC.calc_origin_potential,
+ * CEIT/EJAC.py:87-98) rows of the same excitation range.
+ * Requires ceit_assemble + ceit_factor on the current material state. */
+int ceit_jacobian_block(ceit_plan_t* plan, int64_t i_from, int64_t i_to, int64_t e_from,
+                        int64_t e_to, double c, double omega, double* J, int64_t ldJ,
+                        double* base, void* stream);
+
+/* ---- single forward solve -----------------------------------------------------------------------
+ * Replaces EFEM.calculation(i) (CEIT/FEMBasic.py:67-86; EFEM.py:37-45,98-134):
+ * node_abs [dev] f64[N] = |phi| per node in ORIGINAL node order, elem_pot [dev] f64[E],
+ * electrode_pot [dev] f64[L] (any may be NULL). Requires assemble + factor. */
+int ceit_forward(ceit_plan_t* plan, int64_t i, double* node_abs, double* elem_pot,
+                 double* electrode_pot, void* stream);
+
+/* ---- inverse model -----------------------------------------------------------------------------
+ * Replaces Solver.get_inv_matrix / EJAC.save_inv_matrix (CEIT/Solver.py:110-124,
+ * CEIT/EJAC.py:231-243) including eliminate_non_detect_JAC (Solver.py:76-86) and the "-1":
+ *   Jt = J[:, det] - shift ;  inv = (Jt^T Jt + lambda^2 I)^-1 Jt^T      (n_det x m)
+ * J [dev] f64[m*ldJ]; det_idx [dev] i64[n_det]; rows [dev] i64[m_sel] optional row subset
+ * (eit_solve_on_some_electrodes, EJAC.py:210-220; NULL = all m rows);
+ * form: 0 = auto, 1 = primal (n_det x n_det normal equations, as the reference writes it),
+ *       2 = dual (m x m push-through form, identical operator); scale multiplies the result
+ * (1e-4 in EJAC.py:228).  inv_out [dev] f64[n_det * m_sel]. */
+int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* det_idx,
+                       int64_t n_det, const int64_t* rows, int64_t m_sel, double shift,
+                       double lambda, int form, double scale, double* inv_out, void* stream);
+
+/* ---- realtime reconstruction ---------------------------------------------------------------------
+ * Replaces Solver.solve (CEIT/Solver.py:95-108): out = inv_mat . delta_V
+ * inv [dev] f64[n_det*m]; dV [dev] f64[m*F] row-major (F=1: a vector); out [dev] f64[n_det*F]. */
+int ceit_reconstruct(const double* inv, const double* dV, double* out, int64_t n_det, int64_t m,
+                     int64_t F, void* stream);
+
+/* ---- generic dense helper exposed for tests/benchmarks: C = alpha op(A) op(B) + beta C ---------
+ * row-major f64, op: 0 = N, 1 = T. Uses the same DMMA kernel as the factorisation. */
+int ceit_dgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+               int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,205 @@
+"""Jacobian + one-shot Gauss-Newton variants (host-side mirror of CEIT/EJAC.py) on the B200 path.
+
+The reference's double loop - for every excitation i and element j: perturb, re-assemble the dense
+matrix, invert it, read the electrode amplitudes (EJAC.py:115-133) - becomes ONE call of
+`ceit_jacobian_block`, which applies the exact rank-<=3 Woodbury update of a single factorised
+system per (i, j).  File formats, config keys (`calc_from`/`calc_end`,
+`is_first_JAC_calculation`, `variable_change_for_JAC`, `overall_origin_variable`) and the row layout
+J[i(L-1)+cnt, j] are the reference's.
+"""
+import csv
+
+import numpy as np
+
+from . import _lib
+from .EFEM import EFEM
+from .models.mesh import MeshObj
+from .util.utilities import get_config
+
+
+class EJAC(object):
+    def __init__(self, mesh=None):
+        if mesh is None:
+            self.mesh = MeshObj()
+        else:
+            self.mesh = mesh
+        self.config = get_config()
+        self.mode = 'n'
+        self.first = self.config["is_first_JAC_calculation"]
+        self.detection_bound = self.config["detection_bound"]
+        self.overall_variable = self.config["overall_origin_variable"]
+        self.electrode_centers = self.config["electrode_centers"]
+        self.fwd_FEM = EFEM(self.mesh)
+        self.electrode_num = len(self.electrode_centers)
+        self.pattern_num = self.electrode_num * (self.electrode_num - 1)
+        self.elem_num = self.fwd_FEM.elem_num
+        self.electrode_original_potential = np.zeros((self.pattern_num))
+        self.JAC_matrix = np.zeros((self.pattern_num, self.elem_num))
+        if self.mode == 'n':
+            self.fwd_FEM.reset_variable(overall_variable=self.overall_variable)
+        else:
+            raise Exception('No Such Mode, Please check.')
+        self.initial_variable = np.copy(self.fwd_FEM.elem_variable)
+        self._eng = self.fwd_FEM._engine
+        self._J_dev = None
+        self.calc_origin_potential()
+
+    # -- device helpers -----------------------------------------------------------------------------
+    def _device_J(self):
+        t = self._eng.torch
+        if self._J_dev is None:
+            self._J_dev = t.zeros((self.pattern_num, self.elem_num), dtype=t.float64, device=self._eng.dev)
+        return self._J_dev
+
+    def _upload_J(self):
+        t = self._eng.torch
+        J = self._device_J()
+        J.copy_(t.from_numpy(np.ascontiguousarray(self.JAC_matrix, dtype=np.float64)))
+        return J
+
+    def calc_origin_potential(self):
+        """Unperturbed electrode amplitudes for every excitation (EJAC.py:87-98)."""
+        t = self._eng.torch
+        if self.fwd_FEM._sync_material():
+            self._eng.check_numeric()
+        base = t.zeros(self.pattern_num, dtype=t.float64, device=self._eng.dev)
+        L = self.electrode_num
+        self._eng.plan.jacobian_block(0, L, 0, 0, 0.0, self.fwd_FEM.freq, None, self.elem_num, base)
+        self.electrode_original_potential = base.cpu().numpy()
+
+    def JAC_calculation(self, e_from=None, e_to=None):
+        """Calculate (or load) the Jacobian; saves JAC_cache.npy (EJAC.py:100-140).
+
+        e_from/e_to (extension): restrict to an element range - the second sharding axis used by the
+        multi-GPU driver (ceit_b200.sharding); the reference only has calc_from/calc_end."""
+        calc_from = self.config["calc_from"]
+        calc_end = self.config["calc_end"]
+        variable_change = self.config["variable_change_for_JAC"]
+        if self.first:
+            if calc_from > 0:
+                self.read_JAC_np()
+            L = self.electrode_num
+            i_from, i_to = max(0, calc_from), min(L, calc_end)
+            e_from = 0 if e_from is None else e_from
+            e_to = self.elem_num if e_to is None else e_to
+            if i_to > i_from:
+                if self.fwd_FEM._sync_material():
+                    self._eng.check_numeric()
+                J = self._device_J()
+                self._eng.plan.jacobian_block(i_from, i_to, e_from, e_to, variable_change, self.fwd_FEM.freq,
+                                              J, self.elem_num)
+                r0, r1 = i_from * (L - 1), i_to * (L - 1)
+                self.JAC_matrix[r0:r1, e_from:e_to] = J[r0:r1, e_from:e_to].cpu().numpy()
+                self._eng.check_numeric()
+            self.save_JAC_np()
+            return self.JAC_matrix
+        else:
+            self.read_JAC_np()
+            return self.JAC_matrix
+
+    def eliminate_non_detect_JAC(self):
+        """J[:, detection_index] (EJAC.py:142-152)."""
+        return np.array(self.JAC_matrix[:, np.asarray(self.fwd_FEM.mesh.detection_index)])
+
+    # -- inverse models on the device ------------------------------------------------------------------
+    def _inv_model(self, lmbda, shift, rows=None, scale=1.0):
+        t = self._eng.torch
+        J = self._upload_J()
+        det = t.from_numpy(np.ascontiguousarray(self.fwd_FEM.mesh.detection_index, dtype=np.int64)).to(self._eng.dev)
+        rows_d = None if rows is None else t.tensor(rows, dtype=t.int64, device=self._eng.dev)
+        return _lib.inverse_model(J, det, lmbda, rows=rows_d, shift=shift, scale=scale)
+
+    def _apply(self, inv, delta_V):
+        t = self._eng.torch
+        dV = t.from_numpy(np.ascontiguousarray(delta_V, dtype=np.float64)).to(self._eng.dev)
+        return _lib.reconstruct(inv, dV).cpu().numpy()
+
+    def eit_solve(self, detect_potential, lmbda=295):
+        """EJAC.py:154-170."""
+        delta_V = detect_potential - np.copy(self.electrode_original_potential)
+        return self._apply(self._inv_model(lmbda, 1.0), delta_V)
+
+    def eit_solve_delta_V(self, delta_V, lmbda=295):
+        """EJAC.py:172-182 (the reference does NOT subtract 1 here; kept as is)."""
+        return self._apply(self._inv_model(lmbda, 0.0), delta_V)
+
+    def eit_solve_4electrodes(self, detect_potential, lmbda=90):
+        return self.eit_solve_on_some_electrodes([2, 6, 10, 14], detect_potential, lmbda, mode="direct")
+
+    def eit_solve_4electrodes_delta_V(self, delta_V, lmbda=90):
+        return self.eit_solve_on_some_electrodes([2, 6, 10, 14], delta_V, lmbda, mode="diff")
+
+    def eit_solve_8electrodes(self, detect_potential, lmbda=265):
+        return self.eit_solve_on_some_electrodes([0, 2, 4, 6, 8, 10, 12, 14], detect_potential, lmbda, mode="direct")
+
+    def eit_solve_8electrodes_delta_V(self, delta_V, lmbda=265):
+        return self.eit_solve_on_some_electrodes([0, 2, 4, 6, 8, 10, 12, 14], delta_V, lmbda, mode="diff")
+
+    def eit_solve_on_some_electrodes(self, electrode_list, potential, lmbda, mode="diff"):
+        """Row-subset inverse model (EJAC.py:184-229), result scaled by 1e-4 (EJAC.py:228)."""
+        assert mode == "diff" or mode == "direct", "Please enter the right solver mode"
+        slice_list = []
+        for i in electrode_list:
+            for j in electrode_list:
+                if j < i:
+                    slice_list.append(i * (self.electrode_num - 1) + j)
+                if j > i:
+                    slice_list.append(i * (self.electrode_num - 1) + j - 1)
+        if mode == "direct":
+            delta_V = potential - np.copy(self.electrode_original_potential)
+            delta_V = np.copy(delta_V[slice_list])
+        else:
+            delta_V = potential
+        return self._apply(self._inv_model(lmbda, 1.0, rows=slice_list, scale=1e-4), delta_V)
+
+    def save_inv_matrix(self, lmbda=203):
+        """EJAC.py:231-243."""
+        JAC_inv = self._inv_model(lmbda, 1.0).cpu().numpy()
+        np.save(self.config["rootdir"] + "/" + self.config["folder_name"] + '/inv_mat.npy', JAC_inv)
+
+    def read_inv_matrix(self):
+        return np.load(self.config["rootdir"] + "/" + self.config["folder_name"] + '/inv_mat.npy')
+
+    def eit_solve_direct(self, detect_potential):
+        """EJAC.py:252-259."""
+        t = self._eng.torch
+        JAC_p = t.from_numpy(self.read_inv_matrix()).to(self._eng.dev)
+        delta_V = detect_potential - np.copy(self.electrode_original_potential)
+        return self._apply(JAC_p, delta_V)
+
+    # -- persistence (EJAC.py:261-294) ------------------------------------------------------------------
+    def save_JAC_np(self):
+        np.save(self.config["rootdir"] + "/" + self.config["folder_name"] + '/JAC_cache.npy', self.JAC_matrix)
+
+    def read_JAC_np(self):
+        self.JAC_matrix = np.load(self.config["rootdir"] + "/" + self.config["folder_name"] + '/JAC_cache.npy')
+
+    def save_JAC_2file(self):
+        with open(self.config["rootdir"] + "/" + self.config["folder_name"] + '/jac_cache.csv', "w",
+                  newline='') as csvfile:
+            writer = csv.writer(csvfile, delimiter=',')
+            for row in self.JAC_matrix:
+                writer.writerow(row)
+
+    def read_JAC_2file(self, mode='normal'):
+        if mode == 'normal':
+            with open(self.config["rootdir"] + "/" + self.config["folder_name"] + '/jac_cache.csv',
+                      newline='') as csvfile:
+                for i, line in enumerate(csv.reader(csvfile, delimiter=',')):
+                    self.JAC_matrix[i] = line
+        else:
+            raise Exception('Mode do not exist.')
+
+    def get_sensitivity_list(self):
+        """EJAC.py:303-308."""
+        return np.sum(self.JAC_matrix, axis=0)
+
+    def normalize_sensitivity(self):
+        """DEPRECATED in the reference (EJAC.py:310-318); kept for interface parity."""
+        sensitivity = self.get_sensitivity_list()
+        self.JAC_matrix = self.JAC_matrix / sensitivity.T * np.mean(sensitivity)
+
+    def show_JAC(self):
+        raise NotImplementedError("plotting is outside the scope of ceit_b200")
+
+    plot_sensitivity = plot_map_in_detection_range = show_JAC

@@ -16,7 +16,8 @@ _lib = None
 SYMBOLS = [
     "ceit_last_error", "ceit_version", "ceit_launch_count", "ceit_plan_create", "ceit_plan_destroy",
     "ceit_plan_info", "ceit_plan_tables", "ceit_assemble", "ceit_factor", "ceit_jacobian_block",
-    "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm",
+    "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm", "ceit_plan_csr_values",
+    "ceit_set_option",
 ]
 
 
@@ -57,11 +58,10 @@ def lib():
     L.ceit_dgemm.argtypes = [c_int, c_int, c_i64, c_i64, c_i64, c_dbl, c_vp, c_i64, c_vp, c_i64, c_dbl,
                              c_vp, c_i64, c_vp]
     L.ceit_set_option.argtypes = [ctypes.c_char_p, c_i64]
+    L.ceit_plan_csr_values.argtypes = [c_vp, c_vp, c_vp]
     for name in SYMBOLS:
-        fn = getattr(L, name)
-        if fn.restype is None or (name not in ("ceit_last_error", "ceit_launch_count")):
-            if name not in ("ceit_last_error", "ceit_launch_count"):
-                fn.restype = c_int
+        if name not in ("ceit_last_error", "ceit_launch_count"):
+            getattr(L, name).restype = c_int
     _lib = L
     return L
 
@@ -142,6 +142,9 @@ class Plan:
     def assemble(self, perm, var, omega, vals=None, elem_param=None):
         check(lib().ceit_assemble(self._h, tptr(perm), tptr(var), float(omega), tptr(vals), tptr(elem_param),
                                   stream_ptr()))
+
+    def csr_values(self, vals):
+        check(lib().ceit_plan_csr_values(self._h, tptr(vals), stream_ptr()))
 
     def factor(self, is_complex):
         check(lib().ceit_factor(self._h, 1 if is_complex else 0, stream_ptr()))

@@ -476,6 +476,13 @@ int ceit_assemble(ceit_plan_t* p, const double* perm, const double* var, double 
   return CEIT_OK;
 }
 
+int ceit_plan_csr_values(const ceit_plan_t* p, double* vals, void* stream) {
+  if (!p || !vals) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_csr_values: null argument");
+  if (!p->assembled) CEIT_FAIL(CEIT_ERR_STATE, "ceit_plan_csr_values: call ceit_assemble first");
+  CUDA_TRY(cudaMemcpyAsync(vals, p->d_vals, p->h.nnz * sizeof(cd), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return CEIT_OK;
+}
+
 int ceit_factor(ceit_plan_t* p, int is_complex, void* stream) {
   if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_factor: null plan");
   if (!p->assembled) CEIT_FAIL(CEIT_ERR_STATE, "ceit_factor: call ceit_assemble first");

@@ -1,0 +1,70 @@
+"""config.json access and cache helpers (host-side mirror of CEIT/util/utilities.py:12-75).
+
+`get_config()` keeps the reference's semantics: the file is `config.json` two directories above
+this module (CEIT/util/utilities.py:20-23), it is re-read on every call, mm -> SI conversion of
+`electrode_centers`, `electrode_radius`, `detection_bound` (utilities.py:28-35), `rootdir` injected
+(utilities.py:27).  One addition: the environment variable CEIT_B200_CONFIG may point at another
+config.json (its directory then becomes `rootdir`) so that tests and benchmarks can run several
+configurations from one checkout.
+"""
+import os
+import pickle
+from json import loads
+
+import numpy as np
+
+
+def config_path():
+    env = os.environ.get("CEIT_B200_CONFIG")
+    if env:
+        return os.path.abspath(env)
+    path = os.path.dirname(os.path.realpath(__file__))
+    path = os.path.dirname(os.path.dirname(path))
+    return os.path.join(path, "config.json")
+
+
+def get_config():
+    """Get info in the config.json file and turn all data to SI units."""
+    cfg_file = config_path()
+    path = os.path.dirname(cfg_file)
+    with open(cfg_file, "r", encoding="utf-8") as f:
+        config = loads(f.read())
+    param_unit = config["sensor_param_unit"]
+    assert (isinstance(param_unit, str) and (param_unit == "mm" or param_unit == "SI")) or \
+        isinstance(param_unit, float), "Please enter the accurate unit."
+    config["rootdir"] = path
+    if param_unit == "mm":
+        config["electrode_centers"] = list(np.array(config["electrode_centers"]) / 1000)
+        config["electrode_radius"] = config["electrode_radius"] / 1000
+        config["detection_bound"] = config["detection_bound"] / 1000
+    elif isinstance(param_unit, float):
+        config["electrode_centers"] = list(np.array(config["electrode_centers"]) * param_unit)
+        config["electrode_radius"] *= param_unit
+        config["detection_bound"] *= param_unit
+    return config
+
+
+def insert_zero_to_delta_v(data, electrode_num):
+    """utilities.py:39-45: put a 0 in front of every (L-1)-block."""
+    data = np.asarray(data)
+    out = np.zeros(len(data) + (len(data) + electrode_num - 2) // (electrode_num - 1), dtype=data.dtype)
+    k = 0
+    for i, v in enumerate(data):
+        if i % (electrode_num - 1) == 0:
+            out[k] = 0
+            k += 1
+        out[k] = v
+        k += 1
+    return out[:k]
+
+
+def save_parameter(param, filename, path_name="."):
+    """Pickle to `cache_<filename>.pkl` (utilities.py:48-59)."""
+    with open(os.path.join(path_name, "cache_" + filename + ".pkl"), "wb") as file:
+        pickle.dump(param, file)
+
+
+def read_parameter(filename, path_name):
+    """Read `cache_<filename>.pkl` (utilities.py:62-75)."""
+    with open(os.path.join(path_name, "cache_" + filename + ".pkl"), "rb") as file:
+        return pickle.load(file)

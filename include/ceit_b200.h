@@ -72,6 +72,9 @@ int ceit_plan_tables(const ceit_plan_t* plan, int64_t* rowptr, int64_t* colidx, 
 int ceit_assemble(ceit_plan_t* plan, const double* perm, const double* var, double omega,
                   double* vals, double* elem_param, void* stream);
 
+/* copy the CSR values of the last ceit_assemble into vals [dev] complex f64[nnz] */
+int ceit_plan_csr_values(const ceit_plan_t* plan, double* vals, void* stream);
+
 /* ---- K3: base stage (factor once per material state) ------------------------------------------
  * Replaces the np.linalg.inv(K_ff) of EVERY forward solve (CEIT/EFEM.py:111-119): block Cholesky
  * of K00 = K[F0,F0], X = K00^-1 K0U, S_U, selected inverse on the mesh pattern.
@@ -121,6 +124,9 @@ int ceit_reconstruct(const double* inv, const double* dV, double* out, int64_t n
 int ceit_dgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
                int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
                void* stream);
+
+/* debug/test switches: "force_simt_gemm" = 1 routes f64 GEMMs through the non-tensor kernel */
+int ceit_set_option(const char* name, int64_t value);
 
 #ifdef __cplusplus
 }

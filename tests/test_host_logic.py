@@ -1,0 +1,178 @@
+"""Host-side logic and the C ABI surface, CPU only (no compute calls)."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ceit_b200 import _lib, meshgen
+from ceit_b200.sharding import all_shards
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture()
+def workspace(tmp_path, golden, monkeypatch):
+    def make(tag, **overrides):
+        m, _ = golden(tag)
+        cfg = dict(meshgen.REFERENCE_CONFIG)
+        cfg["folder_name"] = "MESH_" + tag
+        cfg.update(overrides)
+        path = meshgen.make_workspace(str(tmp_path / tag), m["nodes"], m["elem"], cfg)
+        monkeypatch.setenv("CEIT_B200_CONFIG", path)
+        return path
+    return make
+
+
+def test_header_symbols_are_exported():
+    hdr = open(os.path.join(ROOT, "include", "ceit_b200.h")).read()
+    names = set(re.findall(r"\b(ceit_[a-z_0-9]+)\s*\(", hdr))
+    assert {"ceit_plan_create", "ceit_jacobian_block", "ceit_inverse_model", "ceit_reconstruct"} <= names
+    L = _lib.lib()
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ceit_b200.h but not exported"
+    assert set(_lib.SYMBOLS) <= names
+    assert L.ceit_version() >= 100
+
+
+def test_compute_entry_fails_loudly_without_plan_state():
+    L = _lib.lib()
+    assert L.ceit_factor(ctypes.c_void_p(0), 0, ctypes.c_void_p(0)) < 0
+    assert b"null" in L.ceit_last_error()
+
+
+@pytest.mark.parametrize("tag", ["21_21", "50_50"])
+@pytest.mark.parametrize("target", [0, 1, 64, 10 ** 6])
+def test_plan_tables(golden, tag, target):
+    m, r = golden(tag)
+    p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"], target_block=target, upload=False)
+    tb = p.tables()
+    # CSR pattern bit-exact with scipy.sparse.csr_matrix(reference K_sparse)
+    assert np.array_equal(tb["rowptr"], r["K_indptr"]) and np.array_equal(tb["colidx"], r["K_indices"])
+    N = p.N
+    pos = tb["pos"]
+    assert sorted(pos.tolist()) == list(range(N))                     # a permutation
+    U = tb["U"]
+    expect_U = []
+    for e in m["electrodes"]:
+        for n in np.unique(m["elem"][np.asarray(e)].reshape(-1)):
+            if n not in expect_U:
+                expect_U.append(int(n))
+    assert U.tolist() == expect_U
+    assert np.array_equal(pos[U], p.N0 + np.arange(p.nU))
+    # block-tridiagonal: every edge between F0 nodes joins the same or adjacent blocks
+    blk = np.searchsorted(tb["blk_ptr"], np.arange(p.N0), side="right") - 1
+    rows = np.repeat(np.arange(N), np.diff(tb["rowptr"]))
+    pr, pc = pos[rows], pos[tb["colidx"]]
+    both = (pr < p.N0) & (pc < p.N0)
+    assert np.abs(blk[pr[both]] - blk[pc[both]]).max() <= 1
+    if target == 10 ** 6:
+        assert p.n_blocks == 1
+    p.close()
+
+
+def test_plan_rejects_bad_input(golden):
+    m, _ = golden("21_21")
+    bad = m["elem"].copy()
+    bad[0, 0] = len(m["nodes"]) + 5
+    with pytest.raises(_lib.CeitError):
+        _lib.Plan(m["nodes"], bad, m["electrodes"], upload=False)
+    with pytest.raises(_lib.CeitError, match="No element is selected"):
+        _lib.Plan(m["nodes"], m["elem"], [m["electrodes"][0], []], upload=False)
+    with pytest.raises(Exception, match="2D Node coordinates incorrect"):
+        _lib.Plan(np.zeros((4, 3)), m["elem"], m["electrodes"], upload=False)
+
+
+@pytest.mark.parametrize("tag", ["21_21", "50_50"])
+def test_meshobj_matches_reference(workspace, golden, tag):
+    workspace(tag)
+    from ceit_b200.models.mesh import MeshObj
+    m, _ = golden(tag)
+    mesh = MeshObj()
+    assert np.array_equal(mesh.elem, m["elem"]) and np.array_equal(mesh.nodes, m["nodes"])
+    scale = np.abs(m["elem_param"]).max(axis=0)
+    assert (np.abs(mesh.elem_param - m["elem_param"]) / scale).max() < 1e-12
+    for i, e in enumerate(m["electrodes"]):
+        assert mesh.electrode_mesh[i] == [int(x) for x in e]
+    assert np.array_equal(mesh.detection_index, m["detection_index"])
+    assert np.array_equal(mesh.detection_elem, m["detection_elem"])
+    hull = mesh.get_perimeter()
+    assert len(hull) >= 4 and len(set(hull.tolist())) == len(hull)
+
+
+def test_get_config_semantics(workspace):
+    path = workspace("21_21", sensor_param_unit="mm")
+    from ceit_b200.util.utilities import get_config
+    cfg = get_config()
+    assert cfg["rootdir"] == os.path.dirname(path)
+    assert abs(cfg["electrode_radius"] - 0.003) < 1e-18 and abs(cfg["detection_bound"] - 0.045) < 1e-18
+    assert abs(cfg["electrode_centers"][1][1] - 0.0235) < 1e-18
+    raw = json.load(open(path))
+    raw["sensor_param_unit"] = "SI"
+    json.dump(raw, open(path, "w"))
+    assert get_config()["electrode_radius"] == 3          # re-read on every call, no conversion for SI
+
+
+def test_fem_roundtrip_and_cache_formats(tmp_path, golden, monkeypatch):
+    """write_fem -> init_mesh (parse, unit scale, duplicate merge, csv + pkl cache) -> read back."""
+    m, _ = golden("21_21")
+    from ceit_b200 import readmesh
+    root = tmp_path / "ws"
+    folder = root / "MESH_X"
+    folder.mkdir(parents=True)
+    nodes_mm = m["nodes"] * 1000.0
+    # append a duplicate of node 3 and let one element use it: it must be merged away
+    nodes_dup = np.concatenate([nodes_mm, nodes_mm[3:4]], 0)
+    elem = m["elem"].copy()
+    hit = np.argwhere(elem == 3)[0]
+    elem[hit[0], hit[1]] = len(nodes_mm)
+    readmesh.write_fem(str(folder / "EITMesh.fem"), nodes_dup, elem)
+    cfg = dict(meshgen.REFERENCE_CONFIG)
+    cfg["folder_name"] = "MESH_X"
+    json.dump(cfg, open(root / "config.json", "w"))
+    monkeypatch.setenv("CEIT_B200_CONFIG", str(root / "config.json"))
+    mesh_obj, L, centers, radius = readmesh.init_mesh()
+    assert L == 16 and mesh_obj["node"].shape == m["nodes"].shape
+    assert np.array_equal(mesh_obj["element"], m["elem"])
+    assert np.abs(mesh_obj["node"] - m["nodes"]).max() < 5e-7          # 8-char Nastran fields
+    for mode in ("pkl", "csv"):
+        mo, _, _, _ = readmesh.read_mesh_from_csv(mode=mode).return_mesh()
+        assert np.array_equal(mo["element"], m["elem"])
+        assert np.allclose(mo["node"], mesh_obj["node"], rtol=0, atol=1e-15)
+    import pickle
+    nodes_pkl = pickle.load(open(folder / "cache_Mesh_nodes.pkl", "rb"))
+    elems_pkl = pickle.load(open(folder / "cache_Mesh_elements.pkl", "rb"))
+    assert isinstance(nodes_pkl, list) and nodes_pkl[0].shape == (2,) and isinstance(elems_pkl[0], list)
+    assert readmesh.string_to_float("1.5-3") == 1.5e-3 and readmesh.string_to_float("-2.5-2") == -2.5e-2
+
+
+def test_reference_fem_parses_identically(golden):
+    """When the reference tree is present (build container only), its decks parse to the goldens."""
+    path = "/root/reference/MESH_21_21/EITMesh.fem"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present")
+    from ceit_b200.readmesh import parse_fem
+    m, _ = golden("21_21")
+    n, e = parse_fem(path)
+    assert np.array_equal(np.array(e), m["elem"]) and np.abs(np.array(n) * 0.001 - m["nodes"]).max() == 0
+
+
+def test_synthetic_mesh_generator():
+    nodes, elem = meshgen.structured_mesh(9)
+    assert nodes.shape == (81, 2) and elem.shape == (128, 3)
+    x, y = nodes[elem, 0], nodes[elem, 1]
+    det = (x[:, 1] - x[:, 0]) * (y[:, 2] - y[:, 0]) - (x[:, 2] - x[:, 0]) * (y[:, 1] - y[:, 0])
+    assert np.all(det > 0)                                             # all CCW
+    assert meshgen.perimeter_electrodes(47, 5) == [[float(a), float(b)] for a, b in
+                                                   meshgen.REFERENCE_CONFIG["electrode_centers"]]
+    assert len(meshgen.perimeter_electrodes(100, 9)) == 32
+
+
+@pytest.mark.parametrize("L,E,ws", [(16, 5000, 1), (16, 5000, 8), (16, 101, 3), (4, 10, 6), (32, 77, 8), (3, 50, 7)])
+def test_shards_cover_every_column_once(L, E, ws):
+    cover = np.zeros((L, E), dtype=int)
+    for (i0, i1, e0, e1) in all_shards(L, E, ws):
+        cover[i0:i1, e0:e1] += 1
+    assert np.all(cover == 1)

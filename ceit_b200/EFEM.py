@@ -31,6 +31,10 @@ class EFEM(FEMBasic):
     def _sync_material(self):
         return self._engine.set_material(self.mesh.elem_perm, self.elem_variable, self.freq)
 
+    def invalidate(self):
+        """Forget the cached factorisation: the next solve re-assembles and re-factorises."""
+        self._engine._factored = None
+
     def my_solver(self, electrode_input):
         """Assemble + factor (cached per material state), then one Schur solve (EFEM.py:37-45)."""
         if not (0 <= electrode_input < self.mesh.electrode_num):

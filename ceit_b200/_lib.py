@@ -17,7 +17,7 @@ SYMBOLS = [
     "ceit_last_error", "ceit_version", "ceit_launch_count", "ceit_plan_create", "ceit_plan_destroy",
     "ceit_plan_info", "ceit_plan_tables", "ceit_assemble", "ceit_factor", "ceit_jacobian_block",
     "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm", "ceit_plan_csr_values",
-    "ceit_set_option",
+    "ceit_set_option", "ceit_stage_times",
 ]
 
 
@@ -59,6 +59,7 @@ def lib():
                              c_vp, c_i64, c_vp]
     L.ceit_set_option.argtypes = [ctypes.c_char_p, c_i64]
     L.ceit_plan_csr_values.argtypes = [c_vp, c_vp, c_vp]
+    L.ceit_stage_times.argtypes = [c_vp, c_vp]
     for name in SYMBOLS:
         if name not in ("ceit_last_error", "ceit_launch_count"):
             getattr(L, name).restype = c_int
@@ -69,6 +70,21 @@ def lib():
 def check(rc):
     if rc != 0:
         raise CeitError(lib().ceit_last_error().decode("utf-8", "replace") + f" (code {rc})")
+
+
+STAGES = ["assemble", "factor", "excitation", "woodbury", "inverse_model", "reconstruct", "s6", "s7"]
+
+
+def set_option(name, value):
+    check(lib().ceit_set_option(name.encode(), int(value)))
+
+
+def stage_times():
+    """{stage: (total ms, launches)} since the last call (needs set_option('stage_timers', 1))."""
+    ms = np.zeros(8, dtype=np.float64)
+    cnt = np.zeros(8, dtype=np.int64)
+    check(lib().ceit_stage_times(_np_ptr(ms), _np_ptr(cnt)))
+    return {STAGES[k]: (float(ms[k]), int(cnt[k])) for k in range(8)}
 
 
 def launch_count():

@@ -41,9 +41,32 @@ using namespace ceit;
 
 namespace {
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
+// ---- optional per-stage device timers (cudaEvent pairs on the caller's stream) ---------------------
+// Enabled with ceit_set_option("stage_timers", 1); read (and reset) with ceit_stage_times(), which
+// synchronises.  Stages: 0 assemble, 1 factor (base stage), 2 per-excitation stage, 3 Woodbury kernel,
+// 4 inverse model, 5 reconstruct, 6 forward extras.
+constexpr int N_STAGES = 8;
+int g_stage_timers = 0;
+struct StageEv {
+  int stage;
+  cudaEvent_t a, b;
+};
+std::vector<StageEv> g_stage_events;
+struct StageScope {
+  int stage;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  StageScope(int s, cudaStream_t st_) : stage(s), st(st_) {
+    if (!g_stage_timers) return;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+  }
+  ~StageScope() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    g_stage_events.push_back({stage, a, b});
+  }
 };
 
 inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
@@ -338,7 +361,10 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
     CUDA_TRY(cudaFuncSetAttribute(woodbury_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   for (int64_t i0 = i_from; i0 < i_to; i0 += cap) {
     const int nbatch = (int)std::min<int64_t>(cap, i_to - i0);
-    rc = excitation_impl<T>(p, (int)i0, nbatch, st);
+    {
+      StageScope sc(2, st);
+      rc = excitation_impl<T>(p, (int)i0, nbatch, st);
+    }
     if (rc) return rc;
     if (base) {
       baseline_kernel<T><<<nbatch, 64, 0, st>>>((int)h.L, (int)h.nU, h.N, h.N0, (const T*)p->phi0, p->d_we_ptr,
@@ -346,6 +372,7 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
       CEIT_COUNT_LAUNCH();
     }
     if (e_to > e_from && J) {
+      StageScope sc(3, st);
       dim3 grid(cdiv(e_to - e_from, warps), nbatch);
       woodbury_kernel<T><<<grid, warps * 32, smem, st>>>((int)e_from, (int)e_to, (int)h.L, (int)h.nU, h.N, h.N0,
                                                          p->d_elem_pos, p->d_area, (const T*)p->g0e, (const T*)p->Xh,
@@ -461,6 +488,7 @@ int ceit_assemble(ceit_plan_t* p, const double* perm, const double* var, double 
   if (!p->uploaded) CEIT_FAIL(CEIT_ERR_STATE, "ceit_assemble: plan has no device tables (created with upload=0)");
   cudaStream_t st = (cudaStream_t)stream;
   const HostPlan& h = p->h;
+  StageScope sc(0, st);
   assemble_csr_kernel<<<cdiv(h.nnz, 256), 256, 0, st>>>((int)h.nnz, p->d_src_ptr, p->d_src, p->d_nodes, p->d_elem,
                                                         perm, var, omega, p->d_vals);
   CEIT_COUNT_LAUNCH();
@@ -487,6 +515,7 @@ int ceit_factor(ceit_plan_t* p, int is_complex, void* stream) {
   if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_factor: null plan");
   if (!p->assembled) CEIT_FAIL(CEIT_ERR_STATE, "ceit_factor: call ceit_assemble first");
   cudaStream_t st = (cudaStream_t)stream;
+  StageScope sc(1, st);
   return is_complex ? factor_impl<cd>(p, st) : factor_impl<double>(p, st);
 }
 
@@ -522,6 +551,7 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
   if (!rows) m_sel = m;
   if (m_sel <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_model: empty row selection");
   cudaStream_t st = (cudaStream_t)stream;
+  StageScope sc(4, st);
   if (form == 0) form = (m_sel <= n_det) ? 2 : 1;
   const int64_t n = (form == 2) ? m_sel : n_det;  // size of the SPD system
   double *Jt = nullptr, *G = nullptr, *Lg = nullptr, *Li = nullptr, *Gi = nullptr, *tmp = nullptr;
@@ -571,6 +601,7 @@ int ceit_reconstruct(const double* inv, const double* dV, double* out, int64_t n
   if (!inv || !dV || !out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_reconstruct: null argument");
   if (n_det <= 0 || m <= 0 || F <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_reconstruct: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
+  StageScope sc(5, st);
   if (F == 1) {
     gemv_rows_kernel<<<cdiv(n_det, 8), 256, 0, st>>>(n_det, (int)m, inv, dV, out);
     CEIT_COUNT_LAUNCH();
@@ -589,10 +620,33 @@ int ceit_dgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, 
   return CEIT_OK;
 }
 
+int ceit_stage_times(double* ms, int64_t* counts) {
+  if (!ms || !counts) CEIT_FAIL(CEIT_ERR_ARG, "ceit_stage_times: null argument");
+  for (int k = 0; k < N_STAGES; ++k) {
+    ms[k] = 0.0;
+    counts[k] = 0;
+  }
+  for (auto& e : g_stage_events) {
+    CUDA_TRY(cudaEventSynchronize(e.b));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, e.a, e.b));
+    ms[e.stage] += t;
+    counts[e.stage] += 1;
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  g_stage_events.clear();
+  return CEIT_OK;
+}
+
 int ceit_set_option(const char* name, int64_t value) {
   if (!name) CEIT_FAIL(CEIT_ERR_ARG, "ceit_set_option: null name");
   if (std::strcmp(name, "force_simt_gemm") == 0) {
     ceit::g_force_simt = (int)value;
+    return CEIT_OK;
+  }
+  if (std::strcmp(name, "stage_timers") == 0) {
+    g_stage_timers = (int)value;
     return CEIT_OK;
   }
   CEIT_FAIL(CEIT_ERR_ARG, std::string("ceit_set_option: unknown option ") + name);

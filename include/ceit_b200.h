@@ -125,6 +125,12 @@ int ceit_dgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, 
                int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
                void* stream);
 
+/* per-stage device times (CUDA events on the caller's stream) accumulated since the last call, when
+ * ceit_set_option("stage_timers", 1) is on.  ms f64[8], counts i64[8]; stages: 0 assemble, 1 base
+ * factorisation, 2 per-excitation stage, 3 Woodbury kernel, 4 inverse model, 5 reconstruct.
+ * Synchronises on the recorded events. */
+int ceit_stage_times(double* ms, int64_t* counts);
+
 /* debug/test switches: "force_simt_gemm" = 1 routes f64 GEMMs through the non-tensor kernel */
 int ceit_set_option(const char* name, int64_t value);
 

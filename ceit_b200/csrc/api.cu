@@ -18,6 +18,7 @@
 namespace ceit {
 std::atomic<int64_t> g_launches{0};
 int g_force_simt = 0;
+int g_gemm_tile = 0;
 static thread_local std::string g_err;
 }  // namespace ceit
 
@@ -639,10 +640,21 @@ int ceit_stage_times(double* ms, int64_t* counts) {
   return CEIT_OK;
 }
 
+int ceit_debug_tile_clocks(int64_t* out) {
+  long long h[8];
+  CUDA_TRY(cudaMemcpyFromSymbol(h, ceit::g_tile_clk, sizeof(h)));
+  for (int k = 0; k < 8; ++k) out[k] = h[k];
+  return CEIT_OK;
+}
+
 int ceit_set_option(const char* name, int64_t value) {
   if (!name) CEIT_FAIL(CEIT_ERR_ARG, "ceit_set_option: null name");
   if (std::strcmp(name, "force_simt_gemm") == 0) {
     ceit::g_force_simt = (int)value;
+    return CEIT_OK;
+  }
+  if (std::strcmp(name, "gemm_tile") == 0) {
+    ceit::g_gemm_tile = (int)value;
     return CEIT_OK;
   }
   if (std::strcmp(name, "stage_timers") == 0) {

@@ -8,74 +8,199 @@
 namespace ceit {
 
 constexpr int TILE = 64;
+// phase clocks of the tile kernel (tools/tile_clocks.py); compiled in only with -DCEIT_TILE_CLOCKS
+__device__ long long g_tile_clk[8];
+#ifdef CEIT_TILE_CLOCKS
+#define CEIT_CLK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_tile_clk[k] = clock64(); } while (0)
+#else
+#define CEIT_CLK(k) do { } while (0)
+#endif
+
+// One level of the block recursion for the inverse of a lower-triangular 64x64 tile held in shared
+// memory (leading dimension 65): for every pair of diagonal blocks of size HALF,
+//   W = L21 X11 (X11 lower triangular),  X21 = -X22 W (X22 lower triangular).
+// 256 threads; each thread produces NOUT = 64*HALF/256 outputs of one column so that the k-loop carries
+// NOUT independent accumulators.
+template <class T, int HALF>
+__device__ __forceinline__ void tri_inverse_level(const T* __restrict__ S, T* __restrict__ X, T* __restrict__ W,
+                                                  int tid) {
+  constexpr int LD = TILE + 1;
+  constexpr int NPAIR = TILE / (2 * HALF);
+  constexpr int NOUT = (NPAIR * HALF * HALF) / 256;   // 2 for HALF=16, 4 for HALF=32
+  constexpr int RSTEP = HALF / NOUT;
+  const int c = tid % HALF;
+  const int rest = tid / HALF;            // 0 .. 256/HALF-1
+  const int r0 = rest % RSTEP;            // base row inside the block
+  const int pr = rest / RSTEP;            // pair index
+  const int o = pr * 2 * HALF;
+  T acc[NOUT];
+#pragma unroll
+  for (int u = 0; u < NOUT; ++u) acc[u] = Sc<T>::zero();
+  for (int k = c; k < HALF; ++k) {
+    const T xv = X[(o + k) * LD + o + c];
+#pragma unroll
+    for (int u = 0; u < NOUT; ++u) acc[u] = fma_(S[(o + HALF + r0 + u * RSTEP) * LD + o + k], xv, acc[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < NOUT; ++u) W[(o + HALF + r0 + u * RSTEP) * LD + o + c] = acc[u];
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < NOUT; ++u) acc[u] = Sc<T>::zero();
+  for (int k = 0; k < HALF; ++k) {
+    const T wv = W[(o + HALF + k) * LD + o + c];
+#pragma unroll
+    for (int u = 0; u < NOUT; ++u)   // X22 is lower triangular: entries with k > row are exact zeros
+      acc[u] = fma_(X[(o + HALF + r0 + u * RSTEP) * LD + o + HALF + k], wv, acc[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < NOUT; ++u) X[(o + HALF + r0 + u * RSTEP) * LD + o + c] = neg(acc[u]);
+  __syncthreads();
+}
 
 // One CTA factors one n x n (n <= 64) tile held in shared memory.
 //   A (read), L (write, lower incl. zeros above the diagonal), Linv (write, same shape).
 // info: set to 1 if a pivot is not positive (real) / zero (complex).
+//
+// Elimination is done UNSCALED (S[i][k] -= S[i][j] S[k][j] / S[j][j]) so that a column step needs one
+// barrier and no serial sqrt: the pivots are final when their column is reached, and L = S diag(p)^-1/2
+// is applied in one pass at the end.  The triangular inverse is built by block recursion
+// (16 -> 32 -> 64): X21 = -X22 (L21 X11), i.e. small matrix products that use all 256 threads.
 template <class T>
 __global__ void __launch_bounds__(256)
 potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA, T* __restrict__ L,
                         int64_t ldl, int64_t sL, T* __restrict__ Linv, int64_t ldi, int64_t sI,
                         int* __restrict__ info) {
+  constexpr int LD = TILE + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* S = reinterpret_cast<T*>(smem_raw);        // [64][65]
-  T* X = S + TILE * (TILE + 1);                 // [64][65]
-  __shared__ T rinv_s;
+  T* S = reinterpret_cast<T*>(smem_raw);   // [64][65] matrix -> L
+  T* X = S + TILE * LD;                    // [64][65] inverse
+  T* W = X + TILE * LD;                    // [64][65] scratch for the recursion
+  __shared__ T rdiag[TILE];
+  __shared__ T rpiv[TILE + 1];
   const int tid = threadIdx.x;
   A += (int64_t)blockIdx.x * sA;
   L += (int64_t)blockIdx.x * sL;
   Linv += (int64_t)blockIdx.x * sI;
-  for (int q = tid; q < n * n; q += 256) {
-    int r = q / n, c = q - r * n;
-    S[r * (TILE + 1) + c] = A[(int64_t)r * lda + c];
+  CEIT_CLK(0);
+  {
+    T v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {   // all 16 global loads in flight before the first shared store
+      const int r = (tid >> 6) + 4 * u, cc = tid & 63;
+      v[u] = (r == cc) ? Sc<T>::one() : Sc<T>::zero();   // identity padding for n < 64
+      if (r < n && cc < n) v[u] = A[(int64_t)r * lda + cc];
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int r = (tid >> 6) + 4 * u, cc = tid & 63;
+      S[r * LD + cc] = v[u];
+      X[r * LD + cc] = Sc<T>::zero();
+    }
   }
   __syncthreads();
-  // right-looking Cholesky on the lower triangle
+  CEIT_CLK(1);
+  // ---- unscaled right-looking elimination, one barrier per column --------------------------------
+  // Thread (rb, cb) owns the 4x4 interleaved register tile {rb+16u} x {cb+16v} for the whole
+  // elimination (interleaving balances the triangular work and keeps shared accesses conflict-free).
+  // Per step it loads 4 values of the pivot column (its rows) and 4 multipliers (its columns): 9 shared
+  // loads for 16 FMAs.  A column is published to shared memory once, when it becomes final, together
+  // with the reciprocal of its pivot, which its owner starts FIRST so that the reciprocal's latency
+  // overlaps the rest of the update.  Entries above the diagonal are carried along unpredicated: they
+  // only feed other above-diagonal entries, which are never read for results.
+  const int cb = tid & 15, rb = tid >> 4;
+  T c[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) c[u][v] = S[(rb + 16 * u) * LD + cb + 16 * v];
+  if (tid == 0) rpiv[0] = rcp_fast(S[0]);
+  __syncthreads();
   for (int j = 0; j < n; ++j) {
-    if (tid == 0) {
-      T d = S[j * (TILE + 1) + j];
-      if (bad_pivot(d)) atomicExch(info, 1);
-      d = sqrt_(d);
-      S[j * (TILE + 1) + j] = d;
-      rinv_s = inv_(d);
-    }
-    __syncthreads();
-    T rinv = rinv_s;
-    for (int i = j + 1 + tid; i < n; i += 256) S[i * (TILE + 1) + j] = mul(S[i * (TILE + 1) + j], rinv);
-    __syncthreads();
-    const int rem = n - j - 1;
-    for (int q = tid; q < rem * rem; q += 256) {
-      int a = q / rem, b = q - a * rem;
-      if (b <= a) {
-        int i = j + 1 + a, k = j + 1 + b;
-        S[i * (TILE + 1) + k] = sub(S[i * (TILE + 1) + k], mul(S[i * (TILE + 1) + j], S[k * (TILE + 1) + j]));
+    if (cb + 48 > j) {                 // the thread still owns a column that is not final
+      const T rp = rpiv[j];
+      T cj[4], tk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cj[u] = S[(rb + 16 * u) * LD + j];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int k = cb + 16 * v;
+        tk[v] = (k > j) ? mul(S[k * LD + j], rp) : Sc<T>::zero();
+      }
+      const int jn = j + 1;
+      const int vn = jn >> 4;          // which of my columns could be column j+1
+      const bool own_next = ((jn & 15) == cb);
+      if (own_next && ((jn & 15) == rb)) {
+        // I own the next pivot element (row j+1, col j+1): update it first and start its reciprocal
+        T pv = Sc<T>::zero();
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (u == vn && v == vn) pv = sub(c[u][v], mul(cj[u], tk[v]));
+        rpiv[jn] = rcp_fast(pv);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) c[u][v] = sub(c[u][v], mul(cj[u], tk[v]));
+      if (own_next) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (v == vn) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) S[(rb + 16 * u) * LD + jn] = c[u][v];
+          }
       }
     }
     __syncthreads();
   }
-  // Linv: column c by forward substitution, one thread per column
-  if (tid < n) {
-    const int c = tid;
-    for (int r = 0; r < c; ++r) X[r * (TILE + 1) + c] = Sc<T>::zero();
-    for (int r = c; r < n; ++r) {
-      T s0 = (r == c) ? Sc<T>::one() : Sc<T>::zero();
-      T s1 = Sc<T>::zero();
-      int k = c;
-      for (; k + 1 < r; k += 2) {
-        s0 = sub(s0, mul(S[r * (TILE + 1) + k], X[k * (TILE + 1) + c]));
-        s1 = sub(s1, mul(S[r * (TILE + 1) + k + 1], X[(k + 1) * (TILE + 1) + c]));
-      }
-      if (k < r) s0 = sub(s0, mul(S[r * (TILE + 1) + k], X[k * (TILE + 1) + c]));
-      X[r * (TILE + 1) + c] = mul(add(s0, s1), inv_(S[r * (TILE + 1) + r]));
+  CEIT_CLK(2);
+  // ---- L = S diag(p)^-1/2 ; rdiag = 1 / L_jj --------------------------------------------------------
+  {
+    T rs[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int k = cb + 16 * v;
+      const T p = S[k * LD + k];
+      if (rb == 0 && bad_pivot(p)) atomicExch(info, 1);
+      rs[v] = inv_(sqrt_(p));
+      if (rb == 0) rdiag[k] = rs[v];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        S[(rb + 16 * u) * LD + cb + 16 * v] = (rb + 16 * u >= cb + 16 * v) ? mul(c[u][v], rs[v]) : Sc<T>::zero();
+  }
+  __syncthreads();
+  CEIT_CLK(3);
+  // ---- X = L^-1: four 16x16 diagonal blocks by forward substitution, column in registers ---------------
+  if (tid < 64) {
+    const int o = (tid >> 4) << 4, cc = tid & 15;
+    T x[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      T s0 = (r == cc) ? Sc<T>::one() : Sc<T>::zero();
+#pragma unroll
+      for (int k = 0; k < r; ++k) s0 = sub(s0, mul(S[(o + r) * LD + o + k], x[k]));
+      x[r] = mul(s0, rdiag[o + r]);
+      X[(o + r) * LD + o + cc] = x[r];
     }
   }
   __syncthreads();
+  // ---- recursion X21 = -X22 (L21 X11): half = 16 (two pairs, 2 outputs/thread), half = 32 (4/thread) ----
+  CEIT_CLK(4);
+  tri_inverse_level<T, 16>(S, X, W, tid);
+  tri_inverse_level<T, 32>(S, X, W, tid);
+  CEIT_CLK(5);
   for (int q = tid; q < n * n; q += 256) {
-    int r = q / n, c = q - r * n;
-    T z = Sc<T>::zero();
-    L[(int64_t)r * ldl + c] = (c <= r) ? S[r * (TILE + 1) + c] : z;
-    Linv[(int64_t)r * ldi + c] = (c <= r) ? X[r * (TILE + 1) + c] : z;
+    const int r = q / n, c = q - r * n;
+    const T z = Sc<T>::zero();
+    L[(int64_t)r * ldl + c] = (c <= r) ? S[r * LD + c] : z;
+    Linv[(int64_t)r * ldi + c] = (c <= r) ? X[r * LD + c] : z;
   }
+  CEIT_CLK(6);
 }
 
 template <class T>
@@ -83,7 +208,7 @@ inline cudaError_t potrf_tile_prepare() {
   static bool done = false;
   if (done) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(potrf_trtri_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(2 * TILE * (TILE + 1) * sizeof(T)));
+                                       (int)(3 * TILE * (TILE + 1) * sizeof(T)));
   if (e == cudaSuccess) done = true;
   return e;
 }
@@ -98,7 +223,7 @@ inline void potrf_trtri_blocked(cudaStream_t st, int64_t n, T* A, int64_t lda, i
                                 int64_t sT, int batch, int* info) {
   if (n <= 0 || batch <= 0) return;
   potrf_tile_prepare<T>();
-  const size_t smem = 2 * TILE * (TILE + 1) * sizeof(T);
+  const size_t smem = 3 * TILE * (TILE + 1) * sizeof(T);
   const T one = Sc<T>::one(), zero = Sc<T>::zero(), mone = neg(Sc<T>::one());
   const int64_t nt = (n + TILE - 1) / TILE;
   for (int64_t t = 0; t < nt; ++t) {

@@ -12,137 +12,149 @@ namespace ceit {
 
 extern std::atomic<int64_t> g_launches;
 extern int g_force_simt;
+extern int g_gemm_tile;
 
 #define CEIT_COUNT_LAUNCH() (::ceit::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 // ------------------------------------------------------------------------------------------------
-// FP64 tensor-core kernel: CTA tile 64x64, BK = 16, 4 warps (2x2), warp tile 32x32 = 4x4 m8n8k4.
-// Shared-memory row strides are chosen == 4 (mod 16) doubles so the 16 lanes of a half-warp that
-// fetch one fragment hit 16 distinct 8-byte banks.
+// FP64 tensor-core kernel, templated on the CTA tile (BM x BN, BK = 16), the warp grid (WM x WN) and
+// the number of cp.async stages.  Each warp owns a (BM/WM) x (BN/WN) block of m8n8k4 accumulators.
+// Operands are copied global -> shared with 8-byte cp.async (zero-fill out of bounds, so any M, N, K,
+// lda work) in their natural layout; the transpose variants differ only in how fragments are read.
+// Shared-memory row strides are == 4 (mod 16) doubles so the 16 lanes of a half-warp that fetch one
+// fragment hit 16 distinct 8-byte banks.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
 
-template <int OPA, int OPB>
-__global__ void __launch_bounds__(128)
+template <int BM, int BN, int OPA, int OPB>
+struct DmmaSmem {
+  static constexpr int BK = 16;
+  static constexpr int SA = (OPA == 0) ? BK + 4 : BM + 4;
+  static constexpr int SB = (OPB == 0) ? BN + 4 : BK + 4;
+  static constexpr int A_ELEMS = (OPA == 0) ? BM * SA : BK * SA;
+  static constexpr int B_ELEMS = (OPB == 0) ? BK * SB : BN * SB;
+  static constexpr int STAGE = A_ELEMS + B_ELEMS;
+};
+
+template <int BM, int BN, int WM, int WN, int OPA, int OPB, int STAGES>
+__global__ void __launch_bounds__(WM * WN * 32)
 gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int64_t lda,
                  int64_t sA, const double* __restrict__ B, int64_t ldb, int64_t sB, double beta,
                  double* __restrict__ C, int64_t ldc, int64_t sC) {
-  constexpr int BM = 64, BN = 64, BK = 16;
-  constexpr int SA = (OPA == 0) ? BK + 4 : BM + 4;
-  constexpr int SB = (OPB == 0) ? BN + 4 : BK + 4;
-  __shared__ double As[2][1280];
-  __shared__ double Bs[2][1280];
+  using SM = DmmaSmem<BM, BN, OPA, OPB>;
+  constexpr int BK = 16, NT = WM * WN * 32;
+  constexpr int SA = SM::SA, SB = SM::SB;
+  constexpr int TM = BM / WM, TN = BN / WN, MI = TM / 8, NI = TN / 8;
+  extern __shared__ __align__(16) double dsm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int wm = (warp / WN) * TM, wn = (warp % WN) * TN;
   A += (int64_t)blockIdx.z * sA;
   B += (int64_t)blockIdx.z * sB;
   C += (int64_t)blockIdx.z * sC;
 
-  double acc[4][4][2];
+  double acc[MI][NI][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  double ra[8], rb[8];
-  auto load_tiles = [&](int k0) {
+  auto issue = [&](int kt, int buf) {
+    double* As = dsm + buf * SM::STAGE;
+    double* Bs = As + SM::A_ELEMS;
+    const int k0 = kt * BK;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < (BM * BK) / NT; ++r) {
+      const int idx = tid + r * NT;
       int m, k;
       if (OPA == 0) {
-        k = tid & 15;
-        m = (tid >> 4) + 8 * r;
+        k = idx & 15;
+        m = idx >> 4;
       } else {
-        m = tid & 63;
-        k = (tid >> 6) + 2 * r;
+        m = idx % BM;
+        k = idx / BM;
       }
-      int gm = m0 + m, gk = k0 + k;
-      double v = 0.0;
-      if (gm < M && gk < K) v = (OPA == 0) ? A[(int64_t)gm * lda + gk] : A[(int64_t)gk * lda + gm];
-      ra[r] = v;
-      int n;
-      if (OPB == 0) {
-        n = tid & 63;
-        k = (tid >> 6) + 2 * r;
-      } else {
-        k = tid & 15;
-        n = (tid >> 4) + 8 * r;
-      }
-      int gn = n0 + n;
-      gk = k0 + k;
-      v = 0.0;
-      if (gn < N && gk < K) v = (OPB == 0) ? B[(int64_t)gk * ldb + gn] : B[(int64_t)gn * ldb + gk];
-      rb[r] = v;
+      const int gm = m0 + m, gk = k0 + k;
+      const bool ok = (gm < M) && (gk < K);
+      const double* src = ok ? ((OPA == 0) ? A + (int64_t)gm * lda + gk : A + (int64_t)gk * lda + gm) : A;
+      cp_async8(As + ((OPA == 0) ? m * SA + k : k * SA + m), src, ok);
     }
-  };
-  auto store_tiles = [&](int buf) {
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      int m, k, n;
-      if (OPA == 0) {
-        k = tid & 15;
-        m = (tid >> 4) + 8 * r;
-        As[buf][m * SA + k] = ra[r];
-      } else {
-        m = tid & 63;
-        k = (tid >> 6) + 2 * r;
-        As[buf][k * SA + m] = ra[r];
-      }
+    for (int r = 0; r < (BN * BK) / NT; ++r) {
+      const int idx = tid + r * NT;
+      int n, k;
       if (OPB == 0) {
-        n = tid & 63;
-        k = (tid >> 6) + 2 * r;
-        Bs[buf][k * SB + n] = rb[r];
+        n = idx % BN;
+        k = idx / BN;
       } else {
-        k = tid & 15;
-        n = (tid >> 4) + 8 * r;
-        Bs[buf][n * SB + k] = rb[r];
+        k = idx & 15;
+        n = idx >> 4;
       }
+      const int gn = n0 + n, gk = k0 + k;
+      const bool ok = (gn < N) && (gk < K);
+      const double* src = ok ? ((OPB == 0) ? B + (int64_t)gk * ldb + gn : B + (int64_t)gn * ldb + gk) : B;
+      cp_async8(Bs + ((OPB == 0) ? k * SB + n : n * SB + k), src, ok);
     }
   };
 
   const int nk = (K + BK - 1) / BK;
-  if (nk > 0) {
-    load_tiles(0);
-    store_tiles(0);
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) issue(s, s);
+    cp_async_commit();
   }
-  __syncthreads();
   for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = kt + STAGES - 1;
+      if (nxt < nk) issue(nxt, nxt % STAGES);
+      cp_async_commit();
+    }
+    const double* As = dsm + (kt % STAGES) * SM::STAGE;
+    const double* Bs = As + SM::A_ELEMS;
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
-      double af[4], bf[4];
+      double af[MI], bf[NI];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int m = wm + i * 8 + g, k = kk + t;
-        af[i] = (OPA == 0) ? As[buf][m * SA + k] : As[buf][k * SA + m];
+      for (int i = 0; i < MI; ++i) {
+        const int m = wm + i * 8 + g, k = kk + t;
+        af[i] = (OPA == 0) ? As[m * SA + k] : As[k * SA + m];
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int n = wn + j * 8 + g, k = kk + t;
-        bf[j] = (OPB == 0) ? Bs[buf][k * SB + n] : Bs[buf][n * SB + k];
+      for (int j = 0; j < NI; ++j) {
+        const int n = wn + j * 8 + g, k = kk + t;
+        bf[j] = (OPB == 0) ? Bs[k * SB + n] : Bs[n * SB + k];
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NI; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
-    if (kt + 1 < nk) store_tiles(buf ^ 1);
-    __syncthreads();
   }
+  cp_async_wait<0>();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int row = m0 + wm + i * 8 + g;
+  for (int i = 0; i < MI; ++i) {
+    const int row = m0 + wm + i * 8 + g;
     if (row >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int col = n0 + wn + j * 8 + 2 * t;
+    for (int j = 0; j < NI; ++j) {
+      const int col = n0 + wn + j * 8 + 2 * t;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (col + q < N) {
@@ -268,6 +280,31 @@ inline void gemm(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_
   gemm_simt_launch<T>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
 }
 
+template <int BM, int BN, int WM, int WN, int STAGES>
+inline void gemm_dmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha,
+                             const double* A, int64_t lda, int64_t sA, const double* B, int64_t ldb, int64_t sB,
+                             double beta, double* C, int64_t ldc, int64_t sC, int batch) {
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch), block(WM * WN * 32);
+#define CEIT_DMMA_CASE(a, b)                                                                              \
+  {                                                                                                       \
+    constexpr size_t smem = (size_t)STAGES * DmmaSmem<BM, BN, a, b>::STAGE * sizeof(double);              \
+    static bool attr_done = false;                                                                        \
+    if (!attr_done) {                                                                                     \
+      cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WM, WN, a, b, STAGES>,                                \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
+      attr_done = true;                                                                                   \
+    }                                                                                                     \
+    gemm_dmma_kernel<BM, BN, WM, WN, a, b, STAGES><<<grid, block, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, \
+                                                                             sA, B, ldb, sB, beta, C, ldc, sC);     \
+  }
+  if (opA == 0 && opB == 0) CEIT_DMMA_CASE(0, 0)
+  else if (opA == 0 && opB == 1) CEIT_DMMA_CASE(0, 1)
+  else if (opA == 1 && opB == 0) CEIT_DMMA_CASE(1, 0)
+  else CEIT_DMMA_CASE(1, 1)
+#undef CEIT_DMMA_CASE
+  CEIT_COUNT_LAUNCH();
+}
+
 template <>
 inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K,
                          double alpha, const double* A, int64_t lda, int64_t sA, const double* B,
@@ -278,16 +315,15 @@ inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N
     gemm_simt_launch<double>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
     return;
   }
-  dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64), (unsigned)batch), block(128);
-#define CEIT_DMMA_CASE(a, b)                                                                     \
-  gemm_dmma_kernel<a, b><<<grid, block, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, sA, B,   \
-                                                 ldb, sB, beta, C, ldc, sC)
-  if (opA == 0 && opB == 0) CEIT_DMMA_CASE(0, 0);
-  else if (opA == 0 && opB == 1) CEIT_DMMA_CASE(0, 1);
-  else if (opA == 1 && opB == 0) CEIT_DMMA_CASE(1, 0);
-  else CEIT_DMMA_CASE(1, 1);
-#undef CEIT_DMMA_CASE
-  CEIT_COUNT_LAUNCH();
+  auto ctas = [&](int64_t bm, int64_t bn) { return ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch; };
+  int cfg = g_gemm_tile;                       // 0 = auto, 1 = 32x32, 2 = 64x64, 3 = 128x128
+  if (cfg == 0) cfg = (ctas(128, 128) >= 148) ? 3 : (ctas(64, 64) >= 120 ? 2 : 1);
+  if (cfg == 3)
+    gemm_dmma_launch<128, 128, 2, 4, 3>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+  else if (cfg == 2)
+    gemm_dmma_launch<64, 64, 2, 2, 4>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+  else
+    gemm_dmma_launch<32, 32, 2, 2, 4>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
 }
 
 }  // namespace ceit

@@ -67,6 +67,17 @@ CEIT_HD cd inv_(cd a) {
   double d = fma(a.x, a.x, a.y * a.y);
   return mk(a.x / d, -a.y / d);
 }
+// reciprocal to ~1 ulp without the slow-path checks of 1.0/x: MUFU seed + two Newton steps (device);
+// used on the serial critical path of the tile factorisation
+__device__ __forceinline__ double rcp_fast(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  r = fma(fma(-a, r, 1.0), r, r);
+  r = fma(fma(-a, r, 1.0), r, r);
+  r = fma(fma(-a, r, 1.0), r, r);   // seed has ~20 bits: 40, 80 after two steps; the third is insurance
+  return r;
+}
+__device__ __forceinline__ cd rcp_fast(cd a) { return inv_(a); }
 CEIT_HD double sqrt_(double a) { return sqrt(a); }
 // principal square root (Re >= 0); pivots of the complex-symmetric Cholesky have Re > 0
 CEIT_HD cd sqrt_(cd a) {

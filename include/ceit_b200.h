@@ -131,6 +131,9 @@ int ceit_dgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, 
  * Synchronises on the recorded events. */
 int ceit_stage_times(double* ms, int64_t* counts);
 
+/* debug: clock64 phase stamps of the last tile-factorisation CTA (only with -DCEIT_TILE_CLOCKS) */
+int ceit_debug_tile_clocks(int64_t* out8);
+
 /* debug/test switches: "force_simt_gemm" = 1 routes f64 GEMMs through the non-tensor kernel */
 int ceit_set_option(const char* name, int64_t value);
 

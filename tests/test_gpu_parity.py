@@ -53,11 +53,21 @@ def _rows(i, L):
 # ---------------------------------------------------------------------------------------------------
 # C ABI level
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tile", [0, 1, 2, 3])
 @pytest.mark.parametrize("shape", [(64, 64, 16), (1, 1, 1), (100, 37, 53), (273, 264, 202), (515, 129, 70)])
-def test_dgemm_matches_torch_fp64(torch_cuda, shape):
+def test_dgemm_matches_torch_fp64(torch_cuda, shape, tile):
+    """every CTA-tile configuration of the DMMA kernel (0 = automatic choice) x every transpose case"""
     t = torch_cuda
     M, N, K = shape
     g = t.Generator(device="cuda").manual_seed(1)
+    _lib.set_option("gemm_tile", tile)
+    try:
+        _dgemm_cases(t, M, N, K, g)
+    finally:
+        _lib.set_option("gemm_tile", 0)
+
+
+def _dgemm_cases(t, M, N, K, g):
     for ta in (False, True):
         for tb in (False, True):
             A = t.randn((K, M) if ta else (M, K), dtype=t.float64, device="cuda", generator=g)

@@ -29,6 +29,8 @@ LAMBDA = 289
 C_PERT = 1e-3
 FREQ = 20000.0
 N_FRAMES = 100000
+WORKLOAD = ("MESH_50_50 full Jacobian (16 x 5000 = 80000 columns) + Gauss-Newton inverse model "
+            "(lambda=289, n_det=4050, m=240)")
 
 
 def load_mesh(tag="50_50"):
@@ -71,6 +73,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    try:  # torchrun exports OMP_NUM_THREADS=1: give the CPU arm every host thread it can use
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     mesh = load_mesh()
     per_step = 2
     for _ in range(args.warmup):
@@ -91,7 +98,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128",
         "data": "MESH_50_50 mesh fixture (tests/golden), deterministic",
-        "config": {"workload": "MESH_50_50 full Jacobian + Gauss-Newton inverse model (lambda=289), 16 electrodes"},
+        "config": {"workload": WORKLOAD},
         "cpu_baseline": {"value": val, "unit": "columns/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "columns/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -164,6 +171,8 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if ws > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     mesh = load_mesh()
     N, E, L = len(mesh["nodes"]), len(mesh["elem"]), len(mesh["electrodes"])
@@ -364,8 +373,7 @@ def run_gpu(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "MESH_50_50 mesh fixture (tests/golden/mesh_50_50.npz), zero base variable; seeded synthetic frames",
-            "config": {"workload": "MESH_50_50 full Jacobian (16 x 5000 = 80000 columns) + Gauss-Newton inverse model "
-                                   "(lambda=289, n_det=4050, m=240)",
+            "config": {"workload": WORKLOAD,
                        "N": N, "E": E, "L": L, "columns_per_step": n_cols, "l2": "flushed between timed steps (256 MiB memset)",
                        "sharding": f"excitation blocks over {ws} rank(s), all-gather J, inverse model replicated"},
             "gpu_launches": int(launches), "wall_s_timed_region": wall,

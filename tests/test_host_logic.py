@@ -176,3 +176,30 @@ def test_shards_cover_every_column_once(L, E, ws):
     for (i0, i1, e0, e1) in all_shards(L, E, ws):
         cover[i0:i1, e0:e1] += 1
     assert np.all(cover == 1)
+
+
+def test_reference_module_paths_import():
+    """CEIT.* re-exports (the reference's Example scripts import these paths)."""
+    import importlib
+    for mod, names in (("CEIT.EFEM", ["EFEM"]), ("CEIT.EJAC", ["EJAC"]), ("CEIT.Solver", ["Solver", "reinitialize_solver"]),
+                       ("CEIT.readmesh", ["init_mesh", "read_mesh_from_csv"]), ("CEIT.models.mesh", ["MeshObj"]),
+                       ("CEIT.util.utilities", ["get_config", "read_parameter", "save_parameter"]),
+                       ("CEIT.Simulator", ["Simulator"]), ("CEIT.FEMBasic", ["FEMBasic"])):
+        m = importlib.import_module(mod)
+        for n in names:
+            assert hasattr(m, n), (mod, n)
+
+
+def test_cpu_device_is_rejected_and_no_gpu_fails_loudly(workspace):
+    workspace("21_21", device="cpu")
+    from ceit_b200.EFEM import EFEM
+    with pytest.raises(Exception, match="no CPU path"):
+        EFEM()
+    workspace("21_21", device="tpu")
+    with pytest.raises(Exception, match='specified device inside the config file'):
+        EFEM()
+    import torch
+    if not torch.cuda.is_available():
+        workspace("21_21")
+        with pytest.raises(_lib.CeitError, match="no CPU fallback"):
+            EFEM()

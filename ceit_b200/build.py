@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
     "--expt-relaxed-constexpr",
-]
+] + (["-DCEIT_TILE_CLOCKS"] if os.environ.get("CEIT_TILE_CLOCKS") else [])
 
 
 def _newest_source_mtime():

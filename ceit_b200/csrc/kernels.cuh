@@ -349,6 +349,240 @@ woodbury_kernel(int e_from, int e_to, int L, int nU, int64_t N, int64_t N0,
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2, patch form: one CTA per (element patch, excitation).
+//  * The rows of Yh_i and Xh of the patch's (<= cap) distinct nodes are staged ONCE in shared memory
+//    (coalesced; odd row pitch so that lanes reading different rows hit different banks).  Elements of a
+//    patch share nodes: ~0.7 distinct nodes per element on a triangulated grid instead of 3.
+//  * Elements are processed 32 at a time with ONE LANE PER ELEMENT, so the 3x3 complex solve and every
+//    reduction are private to a lane (no shuffles, no redundant work); the 8 warps of the CTA split the
+//    nU electrode nodes by electrode: each warp accumulates partial dot products over its electrodes'
+//    nodes (combined through shared memory) and then produces the amplitudes and the weighted electrode
+//    sums of exactly those electrodes, writing their J entries itself.
+// Requires the electrode node ranges to be contiguous in U (no node shared by two electrodes).
+// ------------------------------------------------------------------------------------------------
+// |phi0 + d| = |phi0| sqrt(1 + x), x = (2 Re(conj(phi0) d) + |d|^2) / |phi0|^2.  For the finite-difference
+// perturbations of this path |x| ~ 1e-8, so sqrt(1+x) - 1 is evaluated by its Taylor polynomial (error
+// < 7/256 x^5 < 3e-17 for |x| <= 1e-3): 5 FMAs instead of a ~28-instruction DSQRT, and free of the
+// cancellation in sqrt(1+x) - 1.  Larger |x| takes the exact branch.
+__device__ __forceinline__ double sqrt1p_minus1(double x) {
+  if (fabs(x) <= 1e-3) {
+    double t = fma(x, -0.0390625, 0.0625);
+    t = fma(x, t, -0.125);
+    t = fma(x, t, 0.5);
+    return x * t;
+  }
+  return sqrt(1.0 + x) - 1.0;
+}
+
+constexpr int WBP_WARPS = 8;
+
+__device__ long long g_wb_clk[8];
+#ifdef CEIT_TILE_CLOCKS
+#define WB_CLK(q) do { if (threadIdx.x == 0 && blockIdx.x == 5 && blockIdx.y == 1) g_wb_clk[q] = clock64(); } while (0)
+#else
+#define WB_CLK(q) do { } while (0)
+#endif
+
+// Real-base closed form of y = (I + j B)^-1 (j g), B = s M G real, g = s M f real (f = phi0 at the
+// element's nodes, real on the real path):  (I + jB)^-1 = C (I - jB), C = (I + B^2)^-1  =>
+// Re y = C B g,  Im y = C g.   ~120 real FMAs instead of a complex 3x3 adjugate.
+__device__ __forceinline__ void solve3_real(const double G6[6], double s, const double f[3], double yr[3],
+                                            double yi[3]) {
+  // G (symmetric): [0]=00 [1]=11 [2]=22 [3]=01 [4]=12 [5]=20
+  const double G[3][3] = {{G6[0], G6[3], G6[5]}, {G6[3], G6[1], G6[4]}, {G6[5], G6[4], G6[2]}};
+  double B[3][3], g[3];
+  const double s12 = s * (1.0 / 12.0);
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    const double cs = G[0][b] + G[1][b] + G[2][b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) B[a][b] = s12 * (G[a][b] + cs);      // (M G)_ab = (G_ab + colsum_b) / 12
+  }
+  {
+    const double fs = f[0] + f[1] + f[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) g[a] = s12 * (f[a] + fs);
+  }
+  double A[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      double v = (a == b) ? 1.0 : 0.0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v = fma(B[a][c], B[c][b], v);
+      A[a][b] = v;
+    }
+  const double c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
+  const double c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2];
+  const double c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+  const double det = A[0][0] * c00 + A[0][1] * c01 + A[0][2] * c02;
+  const double id = 1.0 / det;
+  const double c10 = A[0][2] * A[2][1] - A[0][1] * A[2][2];
+  const double c11 = A[0][0] * A[2][2] - A[0][2] * A[2][0];
+  const double c12 = A[0][1] * A[2][0] - A[0][0] * A[2][1];
+  const double c20 = A[0][1] * A[1][2] - A[0][2] * A[1][1];
+  const double c21 = A[0][2] * A[1][0] - A[0][0] * A[1][2];
+  const double c22 = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+  double bg[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) bg[a] = B[a][0] * g[0] + B[a][1] * g[1] + B[a][2] * g[2];
+  // C = adj(A) / det, adj[i][j] = cofactor[j][i]
+  yi[0] = id * (c00 * g[0] + c10 * g[1] + c20 * g[2]);
+  yi[1] = id * (c01 * g[0] + c11 * g[1] + c21 * g[2]);
+  yi[2] = id * (c02 * g[0] + c12 * g[1] + c22 * g[2]);
+  yr[0] = id * (c00 * bg[0] + c10 * bg[1] + c20 * bg[2]);
+  yr[1] = id * (c01 * bg[0] + c11 * bg[1] + c21 * bg[2]);
+  yr[2] = id * (c02 * bg[0] + c12 * bg[1] + c22 * bg[2]);
+}
+
+// Per-excitation constants of the electrode nodes for the real path: {2/phi0, 1/phi0^2, w |phi0|, 0}.
+__global__ void node_consts_kernel(int nU, int64_t N, int64_t N0, const double* __restrict__ phi0,
+                                   const double* __restrict__ wk, double4* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nU) return;
+  const double f = phi0[(int64_t)b * N + N0 + k];
+  const double r = 1.0 / f;
+  out[(int64_t)b * nU + k] = make_double4(2.0 * r, r * r, wk[k] * fabs(f), 0.0);
+}
+
+// Real path (zero base variable). One CTA per (patch of <= 32 elements, excitation); lane = element.
+__global__ void __launch_bounds__(WBP_WARPS * 32)
+woodbury_patch_kernel(int e_from, int e_to, int L, int nU, int pitch, int64_t N, int64_t N0,
+                      const int32_t* __restrict__ patch_eptr, const int32_t* __restrict__ patch_elems,
+                      const int32_t* __restrict__ patch_nptr, const int32_t* __restrict__ patch_nodes,
+                      const uint8_t* __restrict__ patch_local, const double* __restrict__ area,
+                      const double* __restrict__ g0e, const double* __restrict__ Xh,
+                      const double* __restrict__ Yh, const double* __restrict__ phi0,
+                      const int32_t* __restrict__ ue_ptr, const double4* __restrict__ node_consts, int i0,
+                      double s_coef, double* __restrict__ J, int64_t ldJ, int cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int WARPS = WBP_WARPS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int patch = blockIdx.x, b = blockIdx.y;
+  const int i = i0 + b;
+  const int n_beg = patch_nptr[patch], nn = patch_nptr[patch + 1] - n_beg;
+  const int el_beg = patch_eptr[patch], ne = patch_eptr[patch + 1] - el_beg;
+  double4* cU = reinterpret_cast<double4*>(smem_raw);           // [nU] {2/phi0, 1/phi0^2, w |phi0|, -}
+  double* Ys = reinterpret_cast<double*>(cU + nU);              // [cap][pitch]
+  double* Xs = Ys + (int64_t)cap * pitch;                       // [cap][pitch]
+  double* part = Xs + (int64_t)cap * pitch;                     // [WARPS][6][32] partial dots
+  double* ybuf = part + WARPS * 6 * 32;                         // [6][32] Re y0..2, Im y0..2
+  double* phs = ybuf + 6 * 32;                                  // [cap] phi0 at the patch nodes
+  const double* Y = Yh + (int64_t)b * N * nU;
+  const double* ph = phi0 + (int64_t)b * N;
+  WB_CLK(0);
+  // ---- stage node rows with cp.async: every copy of the CTA is in flight at once -----------------
+  for (int n = warp; n < nn; n += WARPS) {
+    const int64_t p = patch_nodes[n_beg + n];
+    const double* ys = Y + p * nU;
+    const double* xs = Xh + p * nU;
+    double* yd = Ys + (int64_t)n * pitch;
+    double* xd = Xs + (int64_t)n * pitch;
+    for (int k = lane; k < nU; k += 32) {
+      cp_async8(yd + k, ys + k, true);
+      cp_async8(xd + k, xs + k, true);
+    }
+    if (lane == 0) phs[n] = ph[p];
+  }
+  cp_async_commit();
+  {
+    const double4* cg = node_consts + (int64_t)b * nU;   // written once per excitation by node_consts_kernel
+    for (int k = threadIdx.x; k < nU; k += WARPS * 32) cU[k] = cg[k];
+  }
+  // this lane's element
+  const bool have = lane < ne;
+  const int lq = have ? lane : 0;
+  const int j = patch_elems[el_beg + lq];
+  const int l0 = patch_local[3 * (el_beg + lq)], l1 = patch_local[3 * (el_beg + lq) + 1],
+            l2 = patch_local[3 * (el_beg + lq) + 2];
+  double g6[6];
+  double sj = 0.0;
+  if (warp == 0) {                                       // the solver warp prefetches its scalars
+#pragma unroll
+    for (int q = 0; q < 6; ++q) g6[q] = g0e[6 * (int64_t)j + q];
+    sj = s_coef * area[j];
+  }
+  WB_CLK(1);
+  cp_async_wait<0>();
+  __syncthreads();
+  WB_CLK(2);
+  const double* y0 = Ys + (int64_t)l0 * pitch;
+  const double* y1 = Ys + (int64_t)l1 * pitch;
+  const double* y2 = Ys + (int64_t)l2 * pitch;
+  const double* x0 = Xs + (int64_t)l0 * pitch;
+  const double* x1 = Xs + (int64_t)l1 * pitch;
+  const double* x2 = Xs + (int64_t)l2 * pitch;
+  // ---- pass 1: partial dots over this warp's electrodes' nodes -----------------------------------
+  // Lanes read DIFFERENT rows at the same k: the odd row pitch spreads the row bases over all 16
+  // 8-byte bank pairs.
+  double d[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int m = warp; m < L; m += WARPS) {
+    if (m == i) continue;                                // Dirichlet columns of Yh_i are zero
+    const int ks = ue_ptr[m], ke = ue_ptr[m + 1];
+#pragma unroll 4
+    for (int k = ks; k < ke; ++k) {
+      const double a0 = y0[k], a1 = y1[k], a2 = y2[k];
+      const double b0 = x0[k], b1 = x1[k], b2 = x2[k];
+      d[0] = fma(a0, b0, d[0]);
+      d[1] = fma(a1, b1, d[1]);
+      d[2] = fma(a2, b2, d[2]);
+      d[3] = fma(a0, b1, d[3]);
+      d[4] = fma(a1, b2, d[4]);
+      d[5] = fma(a2, b0, d[5]);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) part[(warp * 6 + q) * 32 + lane] = d[q];
+  WB_CLK(3);
+  __syncthreads();
+  // ---- one warp combines the partial dots and solves the 3x3 systems of the 32 elements ----------
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      double acc = g6[q];
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) acc += part[(w * 6 + q) * 32 + lane];
+      g6[q] = acc;
+    }
+    const double f[3] = {phs[l0], phs[l1], phs[l2]};
+    double yr[3], yi[3];
+    solve3_real(g6, sj, f, yr, yi);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      ybuf[a * 32 + lane] = yr[a];
+      ybuf[(3 + a) * 32 + lane] = yi[a];
+    }
+  }
+  WB_CLK(4);
+  __syncthreads();
+  WB_CLK(5);
+  const double yr0 = ybuf[lane], yr1 = ybuf[32 + lane], yr2 = ybuf[64 + lane];
+  const double yi0 = ybuf[96 + lane], yi1 = ybuf[128 + lane], yi2 = ybuf[160 + lane];
+  // ---- pass 2: amplitudes and weighted sums of this warp's electrodes ----------------------------
+  const bool write = have && j >= e_from && j < e_to;
+  for (int m = warp; m < L; m += WARPS) {
+    if (m == i) continue;
+    const int ks = ue_ptr[m], ke = ue_ptr[m + 1];
+    double sum0 = 0.0, sumt = 0.0;
+#pragma unroll 4
+    for (int k = ks; k < ke; ++k) {
+      const double4 cu = cU[k];
+      const double a0 = y0[k], a1 = y1[k], a2 = y2[k];
+      const double dr = fma(a0, yr0, fma(a1, yr1, a2 * yr2));
+      const double di = fma(a0, yi0, fma(a1, yi1, a2 * yi2));
+      const double qq = fma(dr, dr, di * di);
+      const double x = fma(cu.x, dr, qq * cu.y);         // (2 phi0 dr + |d|^2) / phi0^2, phi0 real
+      sum0 += cu.z;
+      sumt = fma(cu.z, sqrt1p_minus1(x), sumt);
+    }
+    if (write) J[((int64_t)i * (L - 1) + m - (m > i ? 1 : 0)) * ldJ + j] = fabs(sum0 + sumt);
+  }
+  WB_CLK(6);
+}
+
+// ------------------------------------------------------------------------------------------------
 // inverse model / realtime helpers
 // ------------------------------------------------------------------------------------------------
 // Jt[r][c] = J[rows[r]][det[c]] - shift           (Solver.py:76-86,119)

@@ -107,6 +107,19 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
       p.we_ptr[m + 1] = (int32_t)p.we_u.size();
     }
   }
+  // contiguous form (valid when no node is shared between electrodes)
+  p.u_contiguous = ((int64_t)p.we_u.size() == p.nU);
+  p.ue_ptr.assign(L + 1, 0);
+  p.wk.assign(p.nU, 0.0);
+  if (p.u_contiguous) {
+    for (int64_t m = 0; m < L && p.u_contiguous; ++m) {
+      p.ue_ptr[m + 1] = p.we_ptr[m + 1];
+      for (int32_t q = p.we_ptr[m]; q < p.we_ptr[m + 1]; ++q) {
+        if (p.we_u[q] != q) p.u_contiguous = false;
+        else p.wk[q] = p.we_w[q];
+      }
+    }
+  }
   // ---- CSR pattern of K: node adjacency incl. diagonal ---------------------------------------
   {
     std::vector<int32_t> deg(N + 1, 0);
@@ -267,6 +280,85 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
       int32_t pa = p.elem_pos[3 * e + PA[q]], pb = p.elem_pos[3 * e + PB[q]];
       if (pa < p.N0 && pb < p.N0) p.g0_off[6 * e + q] = pair_off(pa, pb);
     }
+  }
+}
+
+
+// Greedy clustering: grow a patch breadth-first over the element adjacency (elements sharing a node),
+// always taking a queued element if it fits the node cap; close the patch when nothing queued fits.
+void build_patches(HostPlan& p, int32_t node_cap, int32_t elem_cap) {
+  if (node_cap > 255) node_cap = 255;
+  if (node_cap < 3) node_cap = 3;
+  const int64_t N = p.N, E = p.E;
+  p.patch_node_cap = node_cap;
+  // node -> elements
+  std::vector<int32_t> nptr(N + 1, 0), nel(3 * E);
+  for (int64_t q = 0; q < 3 * E; ++q) nptr[p.elem[q] + 1]++;
+  for (int64_t v = 0; v < N; ++v) nptr[v + 1] += nptr[v];
+  {
+    std::vector<int32_t> fill(nptr.begin(), nptr.end() - 1);
+    for (int64_t e = 0; e < E; ++e)
+      for (int a = 0; a < 3; ++a) nel[fill[p.elem[3 * e + a]]++] = (int32_t)e;
+  }
+  std::vector<uint8_t> done(E, 0), queued(E, 0);
+  std::vector<int32_t> local_of(N, -1);
+  p.patch_eptr.assign(1, 0);
+  p.patch_nptr.assign(1, 0);
+  p.patch_elems.clear();
+  p.patch_nodes.clear();
+  p.patch_local.clear();
+  p.patch_elems.reserve(E);
+  p.patch_local.reserve(3 * E);
+  std::vector<int32_t> queue, cur_nodes, leftovers;
+  for (int64_t seed = 0; seed < E; ++seed) {
+    if (done[seed]) continue;
+    queue.clear();
+    cur_nodes.clear();
+    leftovers.clear();
+    queue.push_back((int32_t)seed);
+    queued[seed] = 1;
+    size_t head = 0;
+    int32_t n_in_patch = 0;
+    while (head < queue.size() && n_in_patch < elem_cap) {
+      const int32_t e = queue[head++];
+      int add = 0;
+      for (int a = 0; a < 3; ++a)
+        if (local_of[p.elem[3 * e + a]] < 0) ++add;
+      // count distinct new nodes (a degenerate element could repeat a node; meshes here do not)
+      if ((int32_t)cur_nodes.size() + add > node_cap) {
+        leftovers.push_back(e);
+        continue;
+      }
+      done[e] = 1;
+      ++n_in_patch;
+      p.patch_elems.push_back(e);
+      for (int a = 0; a < 3; ++a) {
+        const int32_t v = p.elem[3 * e + a];
+        if (local_of[v] < 0) {
+          local_of[v] = (int32_t)cur_nodes.size();
+          cur_nodes.push_back(v);
+        }
+        p.patch_local.push_back((uint8_t)local_of[v]);
+      }
+      for (int a = 0; a < 3; ++a) {
+        const int32_t v = p.elem[3 * e + a];
+        for (int32_t q = nptr[v]; q < nptr[v + 1]; ++q) {
+          const int32_t f = nel[q];
+          if (!done[f] && !queued[f]) {
+            queued[f] = 1;
+            queue.push_back(f);
+          }
+        }
+      }
+    }
+    for (int32_t e : queue)
+      if (!done[e]) queued[e] = 0;
+    for (int32_t v : cur_nodes) {
+      local_of[v] = -1;
+      p.patch_nodes.push_back(p.pos[v]);
+    }
+    p.patch_eptr.push_back((int32_t)p.patch_elems.size());
+    p.patch_nptr.push_back((int32_t)p.patch_nodes.size());
   }
 }
 

@@ -19,6 +19,9 @@ struct HostPlan {
   std::vector<uint8_t> inB;                   // L*nU: 1 if U-node is Dirichlet for excitation i
   std::vector<int32_t> we_ptr, we_u;          // electrode -> (U index, weight) lists
   std::vector<double> we_w;
+  bool u_contiguous = false;                  // electrode m owns U[ue_ptr[m]:ue_ptr[m+1]] exclusively
+  std::vector<int32_t> ue_ptr;                // L+1
+  std::vector<double> wk;                     // nU: weight of the node inside its electrode
   // ordering
   std::vector<int32_t> pos;                   // node -> position (F0 block order, then N0+u)
   std::vector<int32_t> node_at;               // position -> node
@@ -35,7 +38,16 @@ struct HostPlan {
   // (0,0),(1,1),(2,2),(0,1),(1,2),(2,0); -1 => 0
   std::vector<int64_t> g0_off;                // E*6
   std::vector<int32_t> elem_pos;              // E*3 node positions
+  // element patches for the Woodbury kernel: elements that share nodes are grouped so that a CTA stages
+  // each node row of Yh / Xh in shared memory once (<= patch_node_cap distinct nodes per patch)
+  int32_t patch_node_cap = 0;
+  std::vector<int32_t> patch_eptr, patch_elems;    // patch -> element ids
+  std::vector<int32_t> patch_nptr, patch_nodes;    // patch -> node POSITIONS
+  std::vector<uint8_t> patch_local;                // 3 per patch element (patch order): local node index
 };
+
+// (Re)build the element patches: <= node_cap distinct nodes (<= 255) and <= elem_cap elements per patch.
+void build_patches(HostPlan& p, int32_t node_cap, int32_t elem_cap);
 
 // Throws std::runtime_error on invalid input.
 void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,

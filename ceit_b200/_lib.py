@@ -138,9 +138,10 @@ class Plan:
                                      self.L, int(target_block), 1 if upload else 0, ctypes.byref(self._h)))
         info = self.info()
         self.nU, self.N0, self.n_blocks, self.max_block, self.nnz = (int(info[k]) for k in (3, 4, 5, 6, 7))
+        self.P, self.nI, self.bmax, self.nC, self.NP, self.N0P = (int(info[k]) for k in range(16, 22))
 
     def info(self):
-        out = np.zeros(16, dtype=np.int64)
+        out = np.zeros(24, dtype=np.int64)
         check(lib().ceit_plan_info(self._h, _np_ptr(out)))
         return out
 

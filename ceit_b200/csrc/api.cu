@@ -49,6 +49,7 @@ namespace {
 constexpr int N_STAGES = 8;
 int g_stage_timers = 0;
 int g_no_patch = 0;
+int64_t g_nd_interior = 64;   // target nodes per nested-dissection interior; <= 0 disables level 1
 struct StageEv {
   int stage;
   cudaEvent_t a, b;
@@ -127,6 +128,11 @@ struct ceit_plan {
   void *Ad = nullptr, *Bs = nullptr, *Ld = nullptr, *Linv = nullptr, *Lsub = nullptr, *Sel = nullptr;
   void *K0U = nullptr, *Zw = nullptr, *Xh = nullptr, *KUU = nullptr, *SU = nullptr, *Ptmp = nullptr;
   void *tmpPanel = nullptr, *g0e = nullptr;
+  void *Aint = nullptr, *Lint = nullptr, *LintInv = nullptr, *Ainv = nullptr, *Bt = nullptr, *Wn = nullptr;
+  void *Tm = nullptr, *G1 = nullptr;
+  int32_t *d_node_at = nullptr, *d_bnd_loc = nullptr, *d_m2_src_ptr = nullptr, *d_m2_src = nullptr;
+  int32_t *d_rc_ptr = nullptr, *d_rc_src = nullptr;
+  int64_t *d_m2_dst = nullptr, *d_sg_off = nullptr;
   int alloc_mode = 0;
   // per-excitation workspace
   int ex_cap = 0, ex_mode = 0;
@@ -186,6 +192,14 @@ int upload_plan(ceit_plan* p) {
   if ((rc = upload_vec(p, &p->d_patch_nodes, h.patch_nodes))) return rc;
   if ((rc = upload_vec(p, &p->d_patch_local, h.patch_local))) return rc;
   p->n_patches = (int)h.patch_eptr.size() - 1;
+  if ((rc = upload_vec(p, &p->d_node_at, h.node_at))) return rc;
+  if ((rc = upload_vec(p, &p->d_bnd_loc, h.bnd_loc))) return rc;
+  if ((rc = upload_vec(p, &p->d_m2_dst, h.m2_dst))) return rc;
+  if ((rc = upload_vec(p, &p->d_m2_src_ptr, h.m2_src_ptr))) return rc;
+  if ((rc = upload_vec(p, &p->d_m2_src, h.m2_src))) return rc;
+  if ((rc = upload_vec(p, &p->d_rc_ptr, h.rc_ptr))) return rc;
+  if ((rc = upload_vec(p, &p->d_rc_src, h.rc_src))) return rc;
+  if ((rc = upload_vec(p, &p->d_sg_off, h.sg_off))) return rc;
   if ((rc = upload_vec(p, &p->d_ue_ptr, h.ue_ptr))) return rc;
   if ((rc = upload_vec(p, &p->d_wk, h.wk))) return rc;
   if ((rc = dev_alloc(p, (void**)&p->d_area, h.E * sizeof(double)))) return rc;
@@ -205,7 +219,8 @@ int alloc_numeric(ceit_plan* p) {
   const int want = Sc<T>::is_complex ? 2 : 1;
   if (p->alloc_mode == want) return 0;
   void** bufs[] = {&p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
-                   &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->g0e};
+                   &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->g0e, &p->Aint, &p->Lint,
+                   &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1};
   for (auto b : bufs) dev_free_tracked(p, *b);
   // excitation workspace depends on the type too
   void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS};
@@ -222,10 +237,18 @@ int alloc_numeric(ceit_plan* p) {
   if ((rc = dev_alloc(p, &p->Ld, h.szD * es))) return rc;
   if ((rc = dev_alloc(p, &p->Linv, h.szD * es))) return rc;
   if ((rc = dev_alloc(p, &p->Lsub, h.szS * es))) return rc;
-  if ((rc = dev_alloc(p, &p->Sel, (h.szD + h.szS) * es))) return rc;
-  if ((rc = dev_alloc(p, &p->K0U, h.N0 * h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->Zw, h.N0 * h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->Xh, h.N * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Sel, (h.szD + h.szS + h.szPP + h.szV) * es))) return rc;
+  if ((rc = dev_alloc(p, &p->K0U, h.N0P * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Zw, h.N0P * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Xh, h.NP * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Aint, h.szPP * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Lint, h.szPP * es))) return rc;
+  if ((rc = dev_alloc(p, &p->LintInv, h.szPP * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Ainv, h.szPP * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Bt, h.szV * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Wn, h.szV * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Tm, h.P * h.bmax * h.bmax * es))) return rc;
+  if ((rc = dev_alloc(p, &p->G1, h.P * h.bmax * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->KUU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->SU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Ptmp, maxS * es))) return rc;
@@ -250,8 +273,8 @@ int alloc_excitation_ws(ceit_plan* p, int want_cap) {
   if ((rc = dev_alloc(p, &p->Ls, c * u2 * es))) return rc;
   if ((rc = dev_alloc(p, &p->Linvs, c * u2 * es))) return rc;
   if ((rc = dev_alloc(p, &p->Sinv, c * u2 * es))) return rc;
-  if ((rc = dev_alloc(p, &p->Yh, c * h.N * h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->phi0, c * h.N * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Yh, c * h.NP * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->phi0, c * h.NP * es))) return rc;
   if ((rc = dev_alloc(p, &p->tvec, c * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->tmpS, c * (int64_t)TILE * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, (void**)&p->d_elec, c * h.L * sizeof(double)))) return rc;
@@ -261,6 +284,12 @@ int alloc_excitation_ws(ceit_plan* p, int want_cap) {
 }
 
 // ---- base stage -----------------------------------------------------------------------------------
+// K00 = K[F0,F0] in the ordering [interiors | separators]:
+//   level 1: the P mutually disconnected interiors (<= 64 nodes each) are factorised and eliminated as
+//            ONE batch (one tile kernel + a handful of batched GEMMs);
+//   level 2: the separator Schur complement M2 = K_CC - sum_p Bt_p^T A_p^-1 Bt_p is block-tridiagonal
+//            over its BFS level sets: block Cholesky, nU right-hand sides, selected inverse;
+//   then the interior parts of X and of the selected inverse follow from batched GEMMs.
 template <class T>
 int factor_impl(ceit_plan* p, cudaStream_t st) {
   const HostPlan& h = p->h;
@@ -269,34 +298,66 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   T *Ad = (T*)p->Ad, *Bs = (T*)p->Bs, *Ld = (T*)p->Ld, *Linv = (T*)p->Linv, *Lsub = (T*)p->Lsub;
   T *Sel = (T*)p->Sel, *K0U = (T*)p->K0U, *Zw = (T*)p->Zw, *Xh = (T*)p->Xh, *KUU = (T*)p->KUU;
   T *SU = (T*)p->SU, *Ptmp = (T*)p->Ptmp, *tmpPanel = (T*)p->tmpPanel, *g0e = (T*)p->g0e;
+  T *Aint = (T*)p->Aint, *Lint = (T*)p->Lint, *LintInv = (T*)p->LintInv, *Ainv = (T*)p->Ainv;
+  T *Bt = (T*)p->Bt, *Wn = (T*)p->Wn, *Tm = (T*)p->Tm, *G1 = (T*)p->G1;
   T* Sd = Sel;
   T* So = Sel + h.szD;
+  T* SigPP = Sel + h.szD + h.szS;
+  T* Vneg = SigPP + h.szPP;
   const size_t es = sizeof(T);
-  const int64_t nU = h.nU, N0 = h.N0;
+  const int64_t nU = h.nU, N0P = h.N0P, NI = h.NI, P = h.P, nI = h.nI, bmax = h.bmax, nC = h.nC;
+  const int64_t sPP = nI * nI, sV = nI * bmax, sT = bmax * bmax, sG = bmax * nU, sX = nI * nU;
   const T one = Sc<T>::one(), zero = Sc<T>::zero(), mone = neg(Sc<T>::one());
   CUDA_TRY(cudaMemsetAsync(Ad, 0, h.szD * es, st));
   CUDA_TRY(cudaMemsetAsync(Bs, 0, h.szS * es, st));
   CUDA_TRY(cudaMemsetAsync(Ld, 0, h.szD * es, st));
   CUDA_TRY(cudaMemsetAsync(Linv, 0, h.szD * es, st));
-  CUDA_TRY(cudaMemsetAsync(K0U, 0, N0 * nU * es, st));
+  CUDA_TRY(cudaMemsetAsync(K0U, 0, N0P * nU * es, st));
   CUDA_TRY(cudaMemsetAsync(KUU, 0, nU * nU * es, st));
   CUDA_TRY(cudaMemsetAsync(p->d_info, 0, sizeof(int), st));
+  if (P > 0) {
+    CUDA_TRY(cudaMemsetAsync(Aint, 0, h.szPP * es, st));
+    CUDA_TRY(cudaMemsetAsync(Bt, 0, h.szV * es, st));
+    pad_identity_kernel<T><<<cdiv(P * nI, 256), 256, 0, st>>>((int)P, (int)nI, p->d_node_at, Aint);
+    CEIT_COUNT_LAUNCH();
+  }
   scatter_dense_kernel<T><<<cdiv(h.nnz, 256), 256, 0, st>>>((int)h.nnz, p->d_vals, p->d_slot_dst, p->d_slot_kind, Ad,
-                                                            Bs, K0U, KUU);
+                                                            Bs, K0U, KUU, Aint, Bt);
   CEIT_COUNT_LAUNCH();
   KERNEL_CHECK();
-  CUDA_TRY(cudaMemcpyAsync(Zw, K0U, N0 * nU * es, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(SU, KUU, nU * nU * es, cudaMemcpyDeviceToDevice, st));
+  // ---- level 1: eliminate the interiors (batched) -----------------------------------------------------
+  if (P > 0) {
+    potrf_trtri_blocked<T>(st, nI, Aint, nI, sPP, Lint, nI, sPP, LintInv, nI, sPP, nullptr, 0, (int)P, p->d_info);
+    gemm<T>(st, 1, 0, nI, nI, nI, one, LintInv, nI, sPP, LintInv, nI, sPP, zero, Ainv, nI, sPP, (int)P);   // A_p^-1
+    gemm<T>(st, 0, 0, nI, bmax, nI, one, Ainv, nI, sPP, Bt, bmax, sV, zero, Wn, bmax, sV, (int)P);          // W_p
+    gemm<T>(st, 1, 0, bmax, bmax, nI, one, Bt, bmax, sV, Wn, bmax, sV, zero, Tm, bmax, sT, (int)P);         // Bt^T W
+    const int64_t nd = (int64_t)h.m2_dst.size();
+    if (nd > 0) {
+      m2_gather_kernel<T><<<cdiv(nd, 256), 256, 0, st>>>(nd, p->d_m2_dst, p->d_m2_src_ptr, p->d_m2_src, Tm, h.szD, Ad, Bs);
+      CEIT_COUNT_LAUNCH();
+    }
+    // right-hand sides: t_I = A^-1 K_IU (kept in the interior rows of Xh), r_C = K_CU - Bt^T t_I
+    gemm<T>(st, 0, 0, nI, nU, nI, one, Ainv, nI, sPP, K0U, nU, sX, zero, Xh, nU, sX, (int)P);
+    gemm<T>(st, 1, 0, bmax, nU, nI, one, Bt, bmax, sV, Xh, nU, sX, zero, G1, nU, sG, (int)P);
+    rc_gather_kernel<T><<<cdiv(nC, 8), 256, 0, st>>>(nC, (int)nU, p->d_rc_ptr, p->d_rc_src, G1, K0U + NI * nU,
+                                                     Zw + NI * nU);
+    CEIT_COUNT_LAUNCH();
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(Zw, K0U, N0P * nU * es, cudaMemcpyDeviceToDevice, st));
+  }
+  KERNEL_CHECK();
+  // ---- level 2: block-tridiagonal Cholesky of M2 + forward substitution ----------------------------
   auto n_of = [&](int64_t k) { return (int64_t)(h.blk_ptr[k + 1] - h.blk_ptr[k]); };
-  // forward sweep: block Cholesky + forward substitution of the nU right-hand sides
+  auto row_of = [&](int64_t k) { return NI + (int64_t)h.blk_ptr[k]; };
   for (int64_t k = 0; k < h.nb; ++k) {
-    const int64_t nk = n_of(k), r0 = h.blk_ptr[k];
+    const int64_t nk = n_of(k), r0 = row_of(k);
     T* Ak = Ad + h.offD[k];
     T* Lk = Ld + h.offD[k];
     T* Lik = Linv + h.offD[k];
     potrf_trtri_blocked<T>(st, nk, Ak, nk, 0, Lk, nk, 0, Lik, nk, 0, tmpPanel, 0, 1, p->d_info);
     if (k > 0) {
-      const int64_t np = n_of(k - 1), rp = h.blk_ptr[k - 1];
+      const int64_t np = n_of(k - 1), rp = row_of(k - 1);
       // RHS_k -= Lsub_{k-1} Z_{k-1}   (Z_{k-1} lives in Xh rows of block k-1 during the forward sweep)
       gemm<T>(st, 0, 0, nk, nU, np, mone, Lsub + h.offS[k - 1], np, 0, Xh + rp * nU, nU, 0, one, Zw + r0 * nU, nU, 0);
     }
@@ -312,10 +373,10 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   }
   // backward sweep: X_k = Linv_k^T (Z_k - Lsub_k^T X_{k+1}); selected inverse blocks
   for (int64_t k = h.nb - 1; k >= 0; --k) {
-    const int64_t nk = n_of(k), r0 = h.blk_ptr[k];
+    const int64_t nk = n_of(k), r0 = row_of(k);
     T* Lik = Linv + h.offD[k];
     if (k + 1 < h.nb) {
-      const int64_t nn = n_of(k + 1), rn = h.blk_ptr[k + 1];
+      const int64_t nn = n_of(k + 1), rn = row_of(k + 1);
       gemm<T>(st, 1, 0, nk, nU, nn, mone, Lsub + h.offS[k], nk, 0, Xh + rn * nU, nU, 0, one, Xh + r0 * nU, nU, 0);
     }
     // in-place is not allowed in the GEMM: go through Zw rows of this block
@@ -331,9 +392,20 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
       gemm<T>(st, 1, 0, nk, nk, nn, mone, Ptmp, nk, 0, So + h.offS[k], nk, 0, one, Sd + h.offD[k], nk, 0);
     }
   }
+  // ---- back to the interiors: x_I = t_I - W x_C[bnd], selected inverse blocks ------------------------
+  if (P > 0) {
+    bnd_rows_gather_kernel<T><<<cdiv(P * bmax, 8), 256, 0, st>>>(P * bmax, (int)nU, p->d_bnd_loc, Xh + NI * nU, G1);
+    CEIT_COUNT_LAUNCH();
+    gemm<T>(st, 0, 0, nI, nU, bmax, mone, Wn, bmax, sV, G1, nU, sG, one, Xh, nU, sX, (int)P);
+    gather_g0_kernel<T><<<cdiv(P * sT, 256), 256, 0, st>>>(P * sT, p->d_sg_off, Sel, Tm);        // Sigma2 on the cliques
+    CEIT_COUNT_LAUNCH();
+    gemm<T>(st, 0, 0, nI, bmax, bmax, mone, Wn, bmax, sV, Tm, bmax, sT, zero, Vneg, bmax, sV, (int)P);   // -W Sg
+    CUDA_TRY(cudaMemcpyAsync(SigPP, Ainv, h.szPP * es, cudaMemcpyDeviceToDevice, st));
+    gemm<T>(st, 0, 1, nI, nI, bmax, mone, Vneg, bmax, sV, Wn, bmax, sV, one, SigPP, nI, sPP, (int)P);    // + V W^T
+  }
   // S_U = K_UU - K_0U^T X
-  gemm<T>(st, 1, 0, nU, nU, N0, mone, K0U, nU, 0, Xh, nU, 0, one, SU, nU, 0);
-  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, st>>>((int)nU, Xh + N0 * nU);
+  gemm<T>(st, 1, 0, nU, nU, N0P, mone, K0U, nU, 0, Xh, nU, 0, one, SU, nU, 0);
+  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, st>>>((int)nU, Xh + N0P * nU);
   CEIT_COUNT_LAUNCH();
   gather_g0_kernel<T><<<cdiv(6 * h.E, 256), 256, 0, st>>>(6 * h.E, p->d_g0_off, Sel, g0e);
   CEIT_COUNT_LAUNCH();
@@ -346,7 +418,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
 template <class T>
 int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
   const HostPlan& h = p->h;
-  const int64_t nU = h.nU, N = h.N, N0 = h.N0, u2 = nU * nU;
+  const int64_t nU = h.nU, N = h.NP, N0 = h.N0P, u2 = nU * nU;   // position space (padded)
   T *St = (T*)p->St, *Ls = (T*)p->Ls, *Linvs = (T*)p->Linvs, *Sinv = (T*)p->Sinv, *Yh = (T*)p->Yh;
   T *phi0 = (T*)p->phi0, *tvec = (T*)p->tvec, *tmpS = (T*)p->tmpS, *Xh = (T*)p->Xh, *SU = (T*)p->SU;
   const T one = Sc<T>::one(), zero = Sc<T>::zero();
@@ -377,7 +449,7 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
 int excitation_chunk_cap(const ceit_plan* p, size_t es) {
   const HostPlan& h = p->h;
   const double budget = 24.0e9;  // bytes of Yh kept at once
-  double per = (double)h.N * h.nU * es + 4.0 * h.nU * h.nU * es;
+  double per = (double)h.NP * h.nU * es + 4.0 * h.nU * h.nU * es;
   int cap = (int)std::max(1.0, std::min((double)h.L, budget / per));
   return cap;
 }
@@ -388,12 +460,12 @@ int launch_woodbury_patch(ceit_plan* p, const double* g0e, const double* Xh, con
   const HostPlan& h = p->h;
   const size_t psm = woodbury_patch_smem(h.nU, h.patch_node_cap);
   double4* consts = (double4*)p->tmpS;      // free after the batched factorisation of the excitation stage
-  node_consts_kernel<<<dim3(cdiv(h.nU, 128), nbatch), 128, 0, st>>>((int)h.nU, h.N, h.N0, phi0, p->d_wk, consts);
+  node_consts_kernel<<<dim3(cdiv(h.nU, 128), nbatch), 128, 0, st>>>((int)h.nU, h.NP, h.N0P, phi0, p->d_wk, consts);
   CEIT_COUNT_LAUNCH();
   CUDA_TRY(cudaFuncSetAttribute(woodbury_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
   dim3 grid(p->n_patches, nbatch);
   woodbury_patch_kernel<<<grid, WBP_WARPS * 32, psm, st>>>(e_from, e_to, (int)h.L, (int)h.nU, (int)woodbury_pitch(h.nU),
-                                                          h.N, h.N0, p->d_patch_eptr, p->d_patch_elems, p->d_patch_nptr,
+                                                          h.NP, h.N0P, p->d_patch_eptr, p->d_patch_elems, p->d_patch_nptr,
                                                           p->d_patch_nodes, p->d_patch_local, p->d_area, g0e, Xh, Yh,
                                                           phi0, p->d_ue_ptr, consts, i0, s_coef, J, ldJ,
                                                           (int)h.patch_node_cap);
@@ -424,7 +496,7 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
     }
     if (rc) return rc;
     if (base) {
-      baseline_kernel<T><<<nbatch, 64, 0, st>>>((int)h.L, (int)h.nU, h.N, h.N0, (const T*)p->phi0, p->d_we_ptr,
+      baseline_kernel<T><<<nbatch, 64, 0, st>>>((int)h.L, (int)h.nU, h.NP, h.N0P, (const T*)p->phi0, p->d_we_ptr,
                                                 p->d_we_u, p->d_we_w, (int)i0, base, nullptr);
       CEIT_COUNT_LAUNCH();
     }
@@ -437,7 +509,7 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
     } else if (e_to > e_from && J) {
       StageScope sc(3, st);
       dim3 grid(cdiv(e_to - e_from, warps), nbatch);
-      woodbury_kernel<T><<<grid, warps * 32, smem, st>>>((int)e_from, (int)e_to, (int)h.L, (int)h.nU, h.N, h.N0,
+      woodbury_kernel<T><<<grid, warps * 32, smem, st>>>((int)e_from, (int)e_to, (int)h.L, (int)h.nU, h.NP, h.N0P,
                                                          p->d_elem_pos, p->d_area, (const T*)p->g0e, (const T*)p->Xh,
                                                          (const T*)p->Yh, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
                                                          p->d_we_w, (int)i0, 2.0 * omega * c, J, ldJ);
@@ -457,7 +529,7 @@ int forward_impl(ceit_plan* p, int64_t i, double* node_abs, double* elem_pot, do
   rc = excitation_impl<T>(p, (int)i, 1, st);
   if (rc) return rc;
   if (electrode_pot) {
-    baseline_kernel<T><<<1, 64, 0, st>>>((int)h.L, (int)h.nU, h.N, h.N0, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
+    baseline_kernel<T><<<1, 64, 0, st>>>((int)h.L, (int)h.nU, h.NP, h.N0P, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
                                          p->d_we_w, (int)i, nullptr, electrode_pot);
     CEIT_COUNT_LAUNCH();
   }
@@ -495,7 +567,7 @@ int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_
   if (!nodes || !elem || !el_ptr || !el_elems || !out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_create: null argument");
   ceit_plan* p = new ceit_plan();
   try {
-    build_host_plan(p->h, nodes, elem, N, E, el_ptr, el_elems, L, target_block);
+    build_host_plan(p->h, nodes, elem, N, E, el_ptr, el_elems, L, target_block, g_nd_interior);
     {
       // patches of <= 32 elements whose distinct node rows fit the shared-memory budget
       int64_t cap = woodbury_patch_cap(p->h.nU);
@@ -528,11 +600,12 @@ int ceit_plan_destroy(ceit_plan_t* p) {
 int ceit_plan_info(const ceit_plan_t* p, int64_t* info) {
   if (!p || !info) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_info: null argument");
   const HostPlan& h = p->h;
-  std::memset(info, 0, 16 * sizeof(int64_t));
+  std::memset(info, 0, 24 * sizeof(int64_t));
   info[0] = h.N; info[1] = h.E; info[2] = h.L; info[3] = h.nU; info[4] = h.N0; info[5] = h.nb;
   info[6] = h.max_block; info[7] = h.nnz; info[8] = h.n_levels; info[9] = h.szD; info[10] = h.szS;
   info[11] = (int64_t)p->dev_bytes; info[12] = p->mode;
-  info[14] = (int64_t)h.patch_eptr.size() - 1; info[15] = (int64_t)h.patch_nodes.size();
+  info[13] = 0; info[14] = (int64_t)h.patch_eptr.size() - 1; info[15] = (int64_t)h.patch_nodes.size();
+  info[16] = h.P; info[17] = h.nI; info[18] = h.bmax; info[19] = h.nC; info[20] = h.NP; info[21] = h.N0P;
   if (p->uploaded && p->d_info) {
     int flag = 0;
     if (cudaMemcpy(&flag, p->d_info, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) info[13] = flag;
@@ -727,6 +800,10 @@ int ceit_set_option(const char* name, int64_t value) {
   if (!name) CEIT_FAIL(CEIT_ERR_ARG, "ceit_set_option: null name");
   if (std::strcmp(name, "force_simt_gemm") == 0) {
     ceit::g_force_simt = (int)value;
+    return CEIT_OK;
+  }
+  if (std::strcmp(name, "nd_interior") == 0) {
+    g_nd_interior = value;
     return CEIT_OK;
   }
   if (std::strcmp(name, "no_patch_kernel") == 0) {

@@ -76,7 +76,7 @@ template <class T>
 __global__ void __launch_bounds__(256)
 scatter_dense_kernel(int nnz, const cd* __restrict__ vals, const int64_t* __restrict__ dst,
                      const uint8_t* __restrict__ kind, T* __restrict__ Ad, T* __restrict__ Bs,
-                     T* __restrict__ K0U, T* __restrict__ KUU) {
+                     T* __restrict__ K0U, T* __restrict__ KUU, T* __restrict__ Aint, T* __restrict__ Bt) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nnz) return;
   const int k = kind[s];
@@ -86,7 +86,59 @@ scatter_dense_kernel(int nnz, const cd* __restrict__ vals, const int64_t* __rest
   if (k == 1) Ad[d] = v;
   else if (k == 2) Bs[d] = v;
   else if (k == 3) K0U[d] = v;
-  else KUU[d] = v;
+  else if (k == 4) KUU[d] = v;
+  else if (k == 5) Aint[d] = v;
+  else Bt[d] = v;
+}
+
+// nested dissection helpers ------------------------------------------------------------------------
+// identity on the diagonal of the unused (padding) slots of every interior block
+template <class T>
+__global__ void pad_identity_kernel(int P, int nI, const int32_t* __restrict__ node_at, T* __restrict__ Aint) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= P * nI) return;
+  if (node_at[q] < 0) {
+    const int p = q / nI, a = q - p * nI;
+    Aint[(int64_t)p * nI * nI + (int64_t)a * nI + a] = Sc<T>::one();
+  }
+}
+// level-2 block storage -= sum of the interiors' Schur contributions (fixed order: deterministic)
+template <class T>
+__global__ void m2_gather_kernel(int64_t nd, const int64_t* __restrict__ dst, const int32_t* __restrict__ src_ptr,
+                                 const int32_t* __restrict__ src, const T* __restrict__ Tm, int64_t szD,
+                                 T* __restrict__ Ad, T* __restrict__ Bs) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nd) return;
+  T acc = Sc<T>::zero();
+  for (int s = src_ptr[q]; s < src_ptr[q + 1]; ++s) acc = add(acc, Tm[src[s]]);
+  const int64_t d = dst[q];
+  if (d < szD) Ad[d] = sub(Ad[d], acc);
+  else Bs[d - szD] = sub(Bs[d - szD], acc);
+}
+// r_C[c,:] = K0U[c,:] - sum over boundary occurrences of row (p,a) of G1; one warp per separator node
+template <class T>
+__global__ void __launch_bounds__(256)
+rc_gather_kernel(int64_t nC, int nU, const int32_t* __restrict__ rc_ptr, const int32_t* __restrict__ rc_src,
+                 const T* __restrict__ G1, const T* __restrict__ K0U_C, T* __restrict__ Z_C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= nC) return;
+  for (int k = lane; k < nU; k += 32) {
+    T acc = K0U_C[c * nU + k];
+    for (int s = rc_ptr[c]; s < rc_ptr[c + 1]; ++s) acc = sub(acc, G1[(int64_t)rc_src[s] * nU + k]);
+    Z_C[c * nU + k] = acc;
+  }
+}
+// G1[(p,a),:] = X_C[bnd_loc[p,a],:] (zero rows for padding)
+template <class T>
+__global__ void __launch_bounds__(256)
+bnd_rows_gather_kernel(int64_t nrows, int nU, const int32_t* __restrict__ bnd_loc, const T* __restrict__ X_C,
+                       T* __restrict__ G1) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= nrows) return;
+  const int32_t c = bnd_loc[r];
+  for (int k = lane; k < nU; k += 32) G1[r * nU + k] = (c < 0) ? Sc<T>::zero() : X_C[(int64_t)c * nU + k];
 }
 
 // rows [N0, N) of Xh = -I

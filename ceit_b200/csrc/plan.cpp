@@ -8,6 +8,7 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 
@@ -44,7 +45,7 @@ void bfs_levels(const std::vector<int32_t>& rowptr, const std::vector<int32_t>& 
 
 void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
                      const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
-                     int64_t target_block) {
+                     int64_t target_block, int64_t nd_interior) {
   if (N <= 0 || E <= 0 || L <= 0) throw std::runtime_error("plan: N, E, L must be positive");
   if (N > (int64_t)2000000000 / 16 || E > (int64_t)2000000000 / 16)
     throw std::runtime_error("plan: mesh too large for 32-bit indices");
@@ -144,19 +145,111 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
     }
     p.nnz = (int64_t)p.colidx.size();
   }
-  // ---- level sets of the F0 graph (pseudo-peripheral start, restart per component) ----------
+  // ---- level 1 (nested dissection): geometric boxes -> interiors I_p (<= 64 nodes, mutually
+  // disconnected) and the separator set C.  A node goes to C when it has an F0 neighbour in a box with
+  // a larger id, so every edge between two boxes has its lower endpoint in C. ----------------------
+  std::vector<int32_t> interior_of(N, -1);      // node -> interior id, -1 for C / U
+  std::vector<std::vector<int32_t>> interiors;
+  const int64_t kMaxInterior = 64;
+  if (nd_interior > 0 && p.N0 > 4 * kMaxInterior) {
+    double xmin = 1e300, xmax = -1e300, ymin = 1e300, ymax = -1e300;
+    for (int64_t v = 0; v < N; ++v)
+      if (p.u_of[v] < 0) {
+        xmin = std::min(xmin, nodes[2 * v]); xmax = std::max(xmax, nodes[2 * v]);
+        ymin = std::min(ymin, nodes[2 * v + 1]); ymax = std::max(ymax, nodes[2 * v + 1]);
+      }
+    int64_t g = (int64_t)std::ceil(std::sqrt((double)p.N0 / (double)nd_interior));
+    if (g < 2) g = 2;
+    for (int attempt = 0; attempt < 12; ++attempt, g = g + 1 + g / 8) {
+      const double wx = (xmax - xmin) / g * (1.0 + 1e-12) + 1e-300, wy = (ymax - ymin) / g * (1.0 + 1e-12) + 1e-300;
+      std::vector<int64_t> box(N, -1);
+      for (int64_t v = 0; v < N; ++v)
+        if (p.u_of[v] < 0) {
+          int64_t bx = std::min<int64_t>(g - 1, (int64_t)((nodes[2 * v] - xmin) / wx));
+          int64_t by = std::min<int64_t>(g - 1, (int64_t)((nodes[2 * v + 1] - ymin) / wy));
+          box[v] = by * g + bx;
+        }
+      std::vector<uint8_t> is_sep(N, 0);
+      for (int64_t v = 0; v < N; ++v) {
+        if (box[v] < 0) continue;
+        for (int32_t q = p.rowptr[v]; q < p.rowptr[v + 1]; ++q) {
+          const int32_t w = p.colidx[q];
+          if (box[w] > box[v]) { is_sep[v] = 1; break; }
+        }
+      }
+      std::vector<int32_t> cnt(g * g, 0);
+      int64_t worst = 0;
+      for (int64_t v = 0; v < N; ++v)
+        if (box[v] >= 0 && !is_sep[v]) worst = std::max<int64_t>(worst, ++cnt[box[v]]);
+      if (worst > kMaxInterior) continue;       // refine the grid
+      std::vector<int32_t> id_of_box(g * g, -1);
+      interiors.clear();
+      for (int64_t v = 0; v < N; ++v)
+        if (box[v] >= 0 && !is_sep[v]) {
+          int32_t& id = id_of_box[box[v]];
+          if (id < 0) { id = (int32_t)interiors.size(); interiors.emplace_back(); }
+          interior_of[v] = id;
+          interiors[id].push_back((int32_t)v);
+        }
+      break;
+    }
+  }
+  p.P = (int64_t)interiors.size();
+  p.nI = 0;
+  for (auto& s : interiors) p.nI = std::max<int64_t>(p.nI, (int64_t)s.size());
+  p.nI = (p.nI + 7) / 8 * 8;
+  // separator nodes (level-2 unknowns) and each interior's boundary list
   std::vector<uint8_t> keep(N);
-  for (int64_t v = 0; v < N; ++v) keep[v] = p.u_of[v] < 0;
+  p.nC = 0;
+  for (int64_t v = 0; v < N; ++v) {
+    keep[v] = (p.u_of[v] < 0 && interior_of[v] < 0);
+    p.nC += keep[v];
+  }
+  std::vector<std::vector<int32_t>> bnd(p.P);   // separator NODE ids adjacent to interior p
+  for (int64_t ip = 0; ip < p.P; ++ip) {
+    auto& b = bnd[ip];
+    for (int32_t v : interiors[ip])
+      for (int32_t q = p.rowptr[v]; q < p.rowptr[v + 1]; ++q) {
+        const int32_t w = p.colidx[q];
+        if (keep[w]) b.push_back(w);
+        else if (p.u_of[w] < 0 && interior_of[w] != ip) throw std::runtime_error("plan: interiors are not separated");
+      }
+    std::sort(b.begin(), b.end());
+    b.erase(std::unique(b.begin(), b.end()), b.end());
+    p.bmax = std::max<int64_t>(p.bmax, (int64_t)b.size());
+  }
+  p.bmax = (p.bmax + 7) / 8 * 8;
+  // ---- level-2 graph on C: mesh edges inside C plus a clique on every boundary list (the fill of
+  // eliminating that interior) ---------------------------------------------------------------------
+  std::vector<int32_t> rowptr2(N + 1, 0), colidx2;
+  {
+    std::vector<std::vector<int32_t>> adj(N);
+    for (int64_t v = 0; v < N; ++v)
+      if (keep[v])
+        for (int32_t q = p.rowptr[v]; q < p.rowptr[v + 1]; ++q)
+          if (keep[p.colidx[q]]) adj[v].push_back(p.colidx[q]);
+    for (auto& b : bnd)
+      for (int32_t a : b)
+        for (int32_t c2 : b) adj[a].push_back(c2);
+    for (int64_t v = 0; v < N; ++v) {
+      auto& a = adj[v];
+      std::sort(a.begin(), a.end());
+      a.erase(std::unique(a.begin(), a.end()), a.end());
+      colidx2.insert(colidx2.end(), a.begin(), a.end());
+      rowptr2[v + 1] = (int32_t)colidx2.size();
+    }
+  }
+  // ---- level sets of the level-2 graph (pseudo-peripheral start, restart per component) ----------
   std::vector<int32_t> committed(N, -1), stamp(N, -1);
   std::vector<std::vector<int32_t>> all_levels, lv;
   int32_t stamp_val = 0;
   for (int32_t s = 0; s < (int32_t)N; ++s) {
     if (!keep[s] || committed[s] >= 0) continue;
-    bfs_levels(p.rowptr, p.colidx, keep, committed, stamp, stamp_val++, s, lv);
+    bfs_levels(rowptr2, colidx2, keep, committed, stamp, stamp_val++, s, lv);
     int32_t far = lv.back()[0];
-    bfs_levels(p.rowptr, p.colidx, keep, committed, stamp, stamp_val++, far, lv);
+    bfs_levels(rowptr2, colidx2, keep, committed, stamp, stamp_val++, far, lv);
     far = lv.back()[0];
-    bfs_levels(p.rowptr, p.colidx, keep, committed, stamp, stamp_val++, far, lv);
+    bfs_levels(rowptr2, colidx2, keep, committed, stamp, stamp_val++, far, lv);
     for (auto& l : lv) {
       for (int32_t v : l) committed[v] = (int32_t)all_levels.size();
       all_levels.push_back(l);
@@ -182,27 +275,36 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
     }
   }
   p.nb = (int64_t)blocks.size();
+  // ---- positions: [interior 0 (nI slots) | ... | interior P-1 | C in block order | U] --------------
+  p.NI = p.P * p.nI;
+  p.N0P = p.NI + p.nC;
+  p.NP = p.N0P + p.nU;
   p.pos.assign(N, -1);
-  p.node_at.assign(N, -1);
+  p.node_at.assign(p.NP, -1);
   p.blk_ptr.assign(p.nb + 1, 0);
-  p.blk_of.assign(p.N0, 0);
+  p.blk_of.assign(p.nC, 0);
   p.max_block = 0;
+  for (int64_t ip = 0; ip < p.P; ++ip)
+    for (size_t a = 0; a < interiors[ip].size(); ++a) {
+      p.pos[interiors[ip][a]] = (int32_t)(ip * p.nI + (int64_t)a);
+      p.node_at[ip * p.nI + a] = interiors[ip][a];
+    }
   {
     int32_t q = 0;
     for (int64_t k = 0; k < p.nb; ++k) {
       for (int32_t v : blocks[k]) {
-        p.pos[v] = q;
-        p.node_at[q] = v;
+        p.pos[v] = (int32_t)(p.NI + q);
+        p.node_at[p.NI + q] = v;
         p.blk_of[q] = (int32_t)k;
         ++q;
       }
       p.blk_ptr[k + 1] = q;
       p.max_block = std::max<int64_t>(p.max_block, (int64_t)blocks[k].size());
     }
-    if (q != p.N0) throw std::runtime_error("plan: level sets do not cover F0");
+    if (q != p.nC) throw std::runtime_error("plan: level sets do not cover the separator set");
     for (int64_t u = 0; u < p.nU; ++u) {
-      p.pos[p.U[u]] = (int32_t)(p.N0 + u);
-      p.node_at[p.N0 + u] = p.U[u];
+      p.pos[p.U[u]] = (int32_t)(p.N0P + u);
+      p.node_at[p.N0P + u] = p.U[u];
     }
   }
   p.offD.assign(p.nb + 1, 0);
@@ -215,8 +317,10 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
   }
   p.szD = p.offD[p.nb];
   p.szS = p.offS[p.nb];
+  p.szPP = p.P * p.nI * p.nI;
+  p.szV = p.P * p.nI * p.bmax;
   auto bsz = [&](int64_t k) { return (int64_t)(p.blk_ptr[k + 1] - p.blk_ptr[k]); };
-  // offset of the pair (positions pa, pb < N0) inside [diag blocks | sub-diagonal blocks]
+  // offset of the separator pair (LOCAL level-2 positions) inside [diag blocks | sub-diagonal blocks]
   auto pair_off = [&](int32_t pa, int32_t pb) -> int64_t {
     int32_t ka = p.blk_of[pa], kb = p.blk_of[pb];
     int64_t la = pa - p.blk_ptr[ka], lb = pb - p.blk_ptr[kb];
@@ -225,6 +329,65 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
     if (kb == ka + 1) return p.szD + p.offS[ka] + lb * bsz(ka) + la;
     throw std::runtime_error("plan: ordering is not block-tridiagonal");
   };
+  // boundary lists in level-2 local positions + index of a separator node inside a boundary list
+  p.bnd_loc.assign(p.P * p.bmax, -1);
+  std::vector<int32_t> bcount(p.P, 0);
+  for (int64_t ip = 0; ip < p.P; ++ip) {
+    bcount[ip] = (int32_t)bnd[ip].size();
+    for (size_t a = 0; a < bnd[ip].size(); ++a) p.bnd_loc[ip * p.bmax + a] = p.pos[bnd[ip][a]] - (int32_t)p.NI;
+  }
+  auto bnd_index = [&](int64_t ip, int32_t node) -> int64_t {
+    auto it = std::lower_bound(bnd[ip].begin(), bnd[ip].end(), node);
+    if (it == bnd[ip].end() || *it != node) throw std::runtime_error("plan: node is not on the interior's boundary");
+    return (int64_t)(it - bnd[ip].begin());
+  };
+  // ---- Schur-complement scatter of the interiors into the level-2 blocks, as gather lists ---------
+  // T_p = Bt_p^T A_p^-1 Bt_p (bmax x bmax); entry (a, b) is subtracted from the level-2 entry of
+  // (bnd_p[a], bnd_p[b]) when that entry is stored (same block, or row block = column block + 1).
+  {
+    std::vector<std::pair<int64_t, int32_t>> items;     // (destination code, source index)
+    for (int64_t ip = 0; ip < p.P; ++ip)
+      for (int32_t a = 0; a < bcount[ip]; ++a)
+        for (int32_t b2 = 0; b2 < bcount[ip]; ++b2) {
+          const int32_t la = p.bnd_loc[ip * p.bmax + a], lb = p.bnd_loc[ip * p.bmax + b2];
+          const int32_t ka = p.blk_of[la], kb = p.blk_of[lb];
+          if (ka == kb || ka == kb + 1)
+            items.emplace_back(pair_off(la, lb), (int32_t)(ip * p.bmax * p.bmax + a * p.bmax + b2));
+          else if (kb != ka + 1)
+            throw std::runtime_error("plan: level-2 ordering is not block-tridiagonal");
+        }
+    std::sort(items.begin(), items.end());
+    p.m2_dst.clear();
+    p.m2_src_ptr.assign(1, 0);
+    p.m2_src.clear();
+    for (size_t q = 0; q < items.size(); ++q) {
+      if (q == 0 || items[q].first != items[q - 1].first) {
+        if (q) p.m2_src_ptr.push_back((int32_t)p.m2_src.size());
+        p.m2_dst.push_back(items[q].first);
+      }
+      p.m2_src.push_back(items[q].second);
+    }
+    if (!items.empty()) p.m2_src_ptr.push_back((int32_t)p.m2_src.size());
+    // right-hand side: r_C[c] -= sum over (p, a) with bnd_p[a] == c of row a of Bt_p^T t_p
+    std::vector<std::pair<int32_t, int32_t>> ritems;
+    for (int64_t ip = 0; ip < p.P; ++ip)
+      for (int32_t a = 0; a < bcount[ip]; ++a) ritems.emplace_back(p.bnd_loc[ip * p.bmax + a], (int32_t)(ip * p.bmax + a));
+    std::sort(ritems.begin(), ritems.end());
+    p.rc_ptr.assign(p.nC + 1, 0);
+    p.rc_src.clear();
+    for (auto& it : ritems) {
+      p.rc_ptr[it.first + 1]++;
+      p.rc_src.push_back(it.second);
+    }
+    for (int64_t c2 = 0; c2 < p.nC; ++c2) p.rc_ptr[c2 + 1] += p.rc_ptr[c2];
+    // gather of the level-2 selected inverse on the boundary cliques
+    p.sg_off.assign(p.P * p.bmax * p.bmax, -1);
+    for (int64_t ip = 0; ip < p.P; ++ip)
+      for (int32_t a = 0; a < bcount[ip]; ++a)
+        for (int32_t b2 = 0; b2 < bcount[ip]; ++b2)
+          p.sg_off[ip * p.bmax * p.bmax + a * p.bmax + b2] =
+              pair_off(p.bnd_loc[ip * p.bmax + a], p.bnd_loc[ip * p.bmax + b2]);
+  }
   // ---- gather lists for the deterministic assembly + dense destinations ----------------------
   p.src_ptr.assign(p.nnz + 1, 0);
   p.src.assign(9 * E, 0);
@@ -234,8 +397,8 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
       for (int a = 0; a < 3; ++a) {
         int32_t r = p.elem[3 * e + a];
         for (int b = 0; b < 3; ++b) {
-          int32_t c = p.elem[3 * e + b];
-          auto it = std::lower_bound(p.colidx.begin() + p.rowptr[r], p.colidx.begin() + p.rowptr[r + 1], c);
+          int32_t c2 = p.elem[3 * e + b];
+          auto it = std::lower_bound(p.colidx.begin() + p.rowptr[r], p.colidx.begin() + p.rowptr[r + 1], c2);
           int32_t s = (int32_t)(it - p.colidx.begin());
           slot_of[9 * e + 3 * a + b] = s;
           p.src_ptr[s + 1]++;
@@ -245,40 +408,72 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
     std::vector<int32_t> fill(p.src_ptr.begin(), p.src_ptr.end() - 1);
     for (int64_t q = 0; q < 9 * E; ++q) p.src[fill[slot_of[q]]++] = (int32_t)q;  // ascending element order
   }
+  // node classes: 0 interior, 1 separator, 2 electrode
+  auto cls = [&](int32_t v) { return p.u_of[v] >= 0 ? 2 : (interior_of[v] >= 0 ? 0 : 1); };
   p.slot_dst.assign(p.nnz, -1);
   p.slot_kind.assign(p.nnz, 0);
   for (int64_t r = 0; r < N; ++r)
     for (int32_t s = p.rowptr[r]; s < p.rowptr[r + 1]; ++s) {
-      int32_t c = p.colidx[s];
-      int32_t pr = p.pos[r], pc = p.pos[c];
-      if (pr < p.N0 && pc < p.N0) {
-        int32_t kr = p.blk_of[pr], kc = p.blk_of[pc];
+      const int32_t c2 = p.colidx[s];
+      const int cr = cls((int32_t)r), cc = cls(c2);
+      const int32_t pr = p.pos[r], pc = p.pos[c2];
+      if (cr == 1 && cc == 1) {
+        const int32_t lr = pr - (int32_t)p.NI, lc = pc - (int32_t)p.NI;
+        const int32_t kr = p.blk_of[lr], kc = p.blk_of[lc];
         if (kr == kc) {
           p.slot_kind[s] = 1;
-          p.slot_dst[s] = pair_off(pr, pc);
+          p.slot_dst[s] = pair_off(lr, lc);
         } else if (kr == kc + 1) {
           p.slot_kind[s] = 2;
-          p.slot_dst[s] = pair_off(pr, pc) - p.szD;
+          p.slot_dst[s] = pair_off(lr, lc) - p.szD;
         } else if (kc != kr + 1) {
           throw std::runtime_error("plan: ordering is not block-tridiagonal");
         }
-      } else if (pr < p.N0) {
+      } else if (cr == 0 && cc == 0) {
+        const int64_t ip = interior_of[r];
+        if (interior_of[c2] != ip) throw std::runtime_error("plan: interiors are not separated");
+        p.slot_kind[s] = 5;
+        p.slot_dst[s] = ip * p.nI * p.nI + (pr - ip * p.nI) * p.nI + (pc - ip * p.nI);
+      } else if (cr == 0 && cc == 1) {
+        const int64_t ip = interior_of[r];
+        p.slot_kind[s] = 6;
+        p.slot_dst[s] = ip * p.nI * p.bmax + (pr - ip * p.nI) * p.bmax + bnd_index(ip, c2);
+      } else if (cr <= 1 && cc == 2) {
         p.slot_kind[s] = 3;
-        p.slot_dst[s] = (int64_t)pr * p.nU + (pc - p.N0);
-      } else if (pc >= p.N0) {
+        p.slot_dst[s] = (int64_t)pr * p.nU + (pc - p.N0P);
+      } else if (cr == 2 && cc == 2) {
         p.slot_kind[s] = 4;
-        p.slot_dst[s] = (int64_t)(pr - p.N0) * p.nU + (pc - p.N0);
+        p.slot_dst[s] = (int64_t)(pr - p.N0P) * p.nU + (pc - p.N0P);
       }
     }
-  // ---- per-element positions and selected-inverse gather offsets -------------------------------
+  // ---- per-element positions and selected-inverse gather offsets into
+  //      [Sd | So | Sigma_pp (P nI nI) | -V (P nI bmax)] ----------------------------------------------
   p.elem_pos.resize(3 * E);
   p.g0_off.assign(6 * E, -1);
   static const int PA[6] = {0, 1, 2, 0, 1, 2}, PB[6] = {0, 1, 2, 1, 2, 0};
+  const int64_t basePP = p.szD + p.szS, baseV = basePP + p.szPP;
   for (int64_t e = 0; e < E; ++e) {
     for (int a = 0; a < 3; ++a) p.elem_pos[3 * e + a] = p.pos[p.elem[3 * e + a]];
     for (int q = 0; q < 6; ++q) {
-      int32_t pa = p.elem_pos[3 * e + PA[q]], pb = p.elem_pos[3 * e + PB[q]];
-      if (pa < p.N0 && pb < p.N0) p.g0_off[6 * e + q] = pair_off(pa, pb);
+      const int32_t va = p.elem[3 * e + PA[q]], vb = p.elem[3 * e + PB[q]];
+      const int ca = cls(va), cb = cls(vb);
+      if (ca == 2 || cb == 2) continue;
+      const int32_t pa = p.pos[va], pb = p.pos[vb];
+      int64_t off;
+      if (ca == 1 && cb == 1) {
+        off = pair_off(pa - (int32_t)p.NI, pb - (int32_t)p.NI);
+      } else if (ca == 0 && cb == 0) {
+        const int64_t ip = interior_of[va];
+        if (interior_of[vb] != ip) throw std::runtime_error("plan: interiors are not separated");
+        off = basePP + ip * p.nI * p.nI + (pa - ip * p.nI) * p.nI + (pb - ip * p.nI);
+      } else if (ca == 0) {
+        const int64_t ip = interior_of[va];
+        off = baseV + ip * p.nI * p.bmax + (pa - ip * p.nI) * p.bmax + bnd_index(ip, vb);
+      } else {
+        const int64_t ip = interior_of[vb];
+        off = baseV + ip * p.nI * p.bmax + (pb - ip * p.nI) * p.bmax + bnd_index(ip, va);
+      }
+      p.g0_off[6 * e + q] = off;
     }
   }
 }

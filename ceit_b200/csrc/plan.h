@@ -10,6 +10,15 @@ namespace ceit {
 struct HostPlan {
   int64_t N = 0, E = 0, L = 0;
   int64_t nU = 0, N0 = 0, nb = 0, max_block = 0, nnz = 0, n_levels = 0;
+  // nested dissection level 1: P interiors of <= nI nodes (padded to nI slots each), boundary lists of
+  // <= bmax separator nodes; level 2: the nC separator nodes in block-tridiagonal order.
+  // Position space: [P*nI interior slots | nC separators | nU electrode nodes] = NP rows.
+  int64_t P = 0, nI = 0, bmax = 0, nC = 0, NI = 0, N0P = 0, NP = 0, szPP = 0, szV = 0;
+  std::vector<int32_t> bnd_loc;               // P*bmax level-2 local positions (-1 padding)
+  std::vector<int64_t> m2_dst;                // destinations (offsets in [Sd|So]-shaped block storage)
+  std::vector<int32_t> m2_src_ptr, m2_src;    // sources: p*bmax*bmax + a*bmax + b
+  std::vector<int32_t> rc_ptr, rc_src;        // separator local pos -> sources p*bmax + a
+  std::vector<int64_t> sg_off;                // P*bmax*bmax offsets into [Sd|So] (-1 padding)
   std::vector<double> nodes;       // N*2
   std::vector<int32_t> elem;       // E*3
   // electrodes
@@ -25,8 +34,8 @@ struct HostPlan {
   // ordering
   std::vector<int32_t> pos;                   // node -> position (F0 block order, then N0+u)
   std::vector<int32_t> node_at;               // position -> node
-  std::vector<int32_t> blk_ptr;               // nb+1 (positions)
-  std::vector<int32_t> blk_of;                // N0: block of position
+  std::vector<int32_t> blk_ptr;               // nb+1 (level-2 local positions)
+  std::vector<int32_t> blk_of;                // nC: block of level-2 local position
   std::vector<int64_t> offD, offS;            // nb (+1): element offsets of diagonal / sub-diagonal blocks
   int64_t szD = 0, szS = 0;                   // total elements in diag / sub-diag storage
   // CSR pattern of K (original numbering) and deterministic gather lists
@@ -52,6 +61,6 @@ void build_patches(HostPlan& p, int32_t node_cap, int32_t elem_cap);
 // Throws std::runtime_error on invalid input.
 void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
                      const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
-                     int64_t target_block);
+                     int64_t target_block, int64_t nd_interior);
 
 }  // namespace ceit

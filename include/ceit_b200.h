@@ -45,20 +45,24 @@ int64_t ceit_launch_count(void);
  *   (CEIT/FEMBasic.py:118-137).
  * nodes [host] f64[N*2]; elem [host] i64[E*3] (0-based, MeshObj.elem, CEIT/models/mesh.py:31);
  * el_ptr [host] i64[L+1], el_elems [host] i64[el_ptr[L]]: electrode_mesh (mesh.py:90-113).
- * target_block: minimum nodes per diagonal block of the level-set block-tridiagonal ordering
- * (<=0: default).  Works without a GPU when `upload` is 0 (host tables only, for CPU tests). */
+ * target_block: minimum nodes per diagonal block of the level-set block-tridiagonal ordering of the
+ * separator system (<=0: default); ceit_set_option("nd_interior", n) sets the target size of the
+ * nested-dissection interiors (<= 0: no interiors, every node is a level-2 node).  Works without a GPU when `upload` is 0 (host tables only, for CPU tests). */
 int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_t E,
                      const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
                      int64_t target_block, int upload, ceit_plan_t** out);
 int ceit_plan_destroy(ceit_plan_t* plan);
 
-/* info[0..15]: N, E, L, nU, N0, n_blocks, max_block, nnz, n_levels, sum n_k^2, sum n_k n_k+1,
- *              device bytes held, factor state (0 none,1 real,2 complex), reserved... */
-int ceit_plan_info(const ceit_plan_t* plan, int64_t* info16);
+/* info[0..23]: N, E, L, nU, N0, n_blocks, max_block, nnz, n_levels, sum n_k^2, sum n_k n_k+1,
+ *              device bytes held, factor state (0 none,1 real,2 complex), numeric flag, n_patches,
+ *              patch nodes, P (interiors), nI (slots per interior), bmax, nC (separator nodes),
+ *              NP (position rows), N0P (position of the first electrode node), reserved x2 */
+int ceit_plan_info(const ceit_plan_t* plan, int64_t* info24);
 /* host copies of the symbolic tables (any pointer may be NULL):
  * rowptr i64[N+1], colidx i64[nnz] (CSR pattern of K, sorted, == scipy.sparse.csr_matrix of the
- * reference's dense K_sparse), pos i64[N] (node -> position: F0 nodes in block order, then U),
- * blk_ptr i64[n_blocks+1], U i64[nU]. */
+ * reference's dense K_sparse), pos i64[N] (node -> row in position space: interior p slot a ->
+ * p*nI + a, separator nodes in level-2 block order from P*nI, electrode nodes from N0P),
+ * blk_ptr i64[n_blocks+1] (level-2 local), U i64[nU]. */
 int ceit_plan_tables(const ceit_plan_t* plan, int64_t* rowptr, int64_t* colidx, int64_t* pos,
                      int64_t* blk_ptr, int64_t* U);
 

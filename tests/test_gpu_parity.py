@@ -80,14 +80,21 @@ def _dgemm_cases(t, M, N, K, g):
 
 
 @pytest.mark.parametrize("tag", ["21_21", "50_50"])
-@pytest.mark.parametrize("target", [0, 64, 10 ** 6])
-def test_cabi_pipeline_against_reference(torch_cuda, golden, tag, target):
+@pytest.mark.parametrize("target,nd", [(0, 64), (64, 0), (10 ** 6, 0), (0, 20), (100, 40)])
+def test_cabi_pipeline_against_reference(torch_cuda, golden, tag, target, nd):
+    """every ordering variant: nested-dissection interiors on/off x block-tridiagonal block size
+    (target 10**6 with nd 0 = one dense block)"""
     t = torch_cuda
     m, r = golden(tag)
     N, E, L = len(m["nodes"]), len(m["elem"]), 16
     omega = 2 * np.pi * float(r["signal_frequency"])
     c = float(r["variable_change_for_JAC"])
-    p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"], target_block=target)
+    _lib.set_option("nd_interior", nd)
+    try:
+        p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"], target_block=target)
+    finally:
+        _lib.set_option("nd_interior", 64)
+    assert (p.P > 0) == (nd > 0)
     perm = t.tensor(m["elem_perm"], device="cuda")
     var = t.zeros(E, dtype=t.float64, device="cuda")
     vals = t.zeros((p.nnz, 2), dtype=t.float64, device="cuda")

@@ -44,16 +44,20 @@ def test_compute_entry_fails_loudly_without_plan_state():
 
 
 @pytest.mark.parametrize("tag", ["21_21", "50_50"])
-@pytest.mark.parametrize("target", [0, 1, 64, 10 ** 6])
-def test_plan_tables(golden, tag, target):
+@pytest.mark.parametrize("target,nd", [(0, 40), (1, 40), (64, 0), (10 ** 6, 0), (0, 20)])
+def test_plan_tables(golden, tag, target, nd):
     m, r = golden(tag)
-    p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"], target_block=target, upload=False)
+    _lib.set_option("nd_interior", nd)
+    try:
+        p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"], target_block=target, upload=False)
+    finally:
+        _lib.set_option("nd_interior", 64)
     tb = p.tables()
     # CSR pattern bit-exact with scipy.sparse.csr_matrix(reference K_sparse)
     assert np.array_equal(tb["rowptr"], r["K_indptr"]) and np.array_equal(tb["colidx"], r["K_indices"])
     N = p.N
     pos = tb["pos"]
-    assert sorted(pos.tolist()) == list(range(N))                     # a permutation
+    assert len(set(pos.tolist())) == N and pos.min() >= 0 and pos.max() < p.NP     # injective into position space
     U = tb["U"]
     expect_U = []
     for e in m["electrodes"]:
@@ -61,15 +65,27 @@ def test_plan_tables(golden, tag, target):
             if n not in expect_U:
                 expect_U.append(int(n))
     assert U.tolist() == expect_U
-    assert np.array_equal(pos[U], p.N0 + np.arange(p.nU))
-    # block-tridiagonal: every edge between F0 nodes joins the same or adjacent blocks
-    blk = np.searchsorted(tb["blk_ptr"], np.arange(p.N0), side="right") - 1
+    assert np.array_equal(pos[U], p.N0P + np.arange(p.nU))
+    NI = p.P * p.nI
+    assert p.N0P == NI + p.nC and p.NP == p.N0P + p.nU
     rows = np.repeat(np.arange(N), np.diff(tb["rowptr"]))
     pr, pc = pos[rows], pos[tb["colidx"]]
-    both = (pr < p.N0) & (pc < p.N0)
-    assert np.abs(blk[pr[both]] - blk[pc[both]]).max() <= 1
-    if target == 10 ** 6:
-        assert p.n_blocks == 1
+    # level 2: every edge between separator nodes joins the same or adjacent blocks
+    sep = (pr >= NI) & (pr < p.N0P) & (pc >= NI) & (pc < p.N0P)
+    blk = np.searchsorted(tb["blk_ptr"], np.arange(p.nC), side="right") - 1
+    if sep.any():
+        assert np.abs(blk[pr[sep] - NI] - blk[pc[sep] - NI]).max() <= 1
+    # level 1: an interior node only touches its own interior, separators or electrode nodes
+    inter = (pr < NI) & (pc < NI)
+    if p.P:
+        assert np.all(pr[inter] // p.nI == pc[inter] // p.nI)
+        assert p.nI <= 64
+    else:
+        assert not inter.any()
+    if nd == 0 and target == 10 ** 6:
+        assert p.n_blocks == 1 and p.P == 0
+    if nd > 0 and tag == "50_50":
+        assert p.P > 4
     p.close()
 
 

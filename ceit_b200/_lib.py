@@ -47,7 +47,7 @@ def lib():
                                    ctypes.POINTER(c_vp)]
     L.ceit_plan_destroy.argtypes = [c_vp]
     L.ceit_plan_info.argtypes = [c_vp, c_vp]
-    L.ceit_plan_tables.argtypes = [c_vp] * 6
+    L.ceit_plan_tables.argtypes = [c_vp] * 7
     L.ceit_assemble.argtypes = [c_vp, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp]
     L.ceit_factor.argtypes = [c_vp, c_int, c_vp]
     L.ceit_jacobian_block.argtypes = [c_vp, c_i64, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_i64, c_vp, c_vp]
@@ -151,9 +151,10 @@ class Plan:
         pos = np.zeros(self.N, np.int64)
         blk_ptr = np.zeros(self.n_blocks + 1, np.int64)
         U = np.zeros(self.nU, np.int64)
+        ppos = np.zeros(self.N, np.int64)
         check(lib().ceit_plan_tables(self._h, _np_ptr(rowptr), _np_ptr(colidx), _np_ptr(pos), _np_ptr(blk_ptr),
-                                     _np_ptr(U)))
-        return dict(rowptr=rowptr, colidx=colidx, pos=pos, blk_ptr=blk_ptr, U=U)
+                                     _np_ptr(U), _np_ptr(ppos)))
+        return dict(rowptr=rowptr, colidx=colidx, pos=pos, blk_ptr=blk_ptr, U=U, ppos=ppos)
 
     # -- numeric entry points (torch tensors as buffers) ------------------------------------------
     def assemble(self, perm, var, omega, vals=None, elem_param=None):

@@ -126,7 +126,8 @@ struct ceit_plan {
   // numeric state (type-erased; element size esz = 8 real / 16 complex)
   int mode = 0;  // 0 none, 1 real, 2 complex
   void *Ad = nullptr, *Bs = nullptr, *Ld = nullptr, *Linv = nullptr, *Lsub = nullptr, *Sel = nullptr;
-  void *K0U = nullptr, *Zw = nullptr, *Xh = nullptr, *KUU = nullptr, *SU = nullptr, *Ptmp = nullptr;
+  void *K0U = nullptr, *Zw = nullptr, *Xh = nullptr, *XP = nullptr, *KUU = nullptr, *SU = nullptr, *Ptmp = nullptr;
+  int32_t* d_row_map = nullptr;
   void *tmpPanel = nullptr, *g0e = nullptr;
   void *Aint = nullptr, *Lint = nullptr, *LintInv = nullptr, *Ainv = nullptr, *Bt = nullptr, *Wn = nullptr;
   void *Tm = nullptr, *G1 = nullptr;
@@ -193,6 +194,7 @@ int upload_plan(ceit_plan* p) {
   if ((rc = upload_vec(p, &p->d_patch_local, h.patch_local))) return rc;
   p->n_patches = (int)h.patch_eptr.size() - 1;
   if ((rc = upload_vec(p, &p->d_node_at, h.node_at))) return rc;
+  if ((rc = upload_vec(p, &p->d_row_map, h.row_map))) return rc;
   if ((rc = upload_vec(p, &p->d_bnd_loc, h.bnd_loc))) return rc;
   if ((rc = upload_vec(p, &p->d_m2_dst, h.m2_dst))) return rc;
   if ((rc = upload_vec(p, &p->d_m2_src_ptr, h.m2_src_ptr))) return rc;
@@ -220,7 +222,7 @@ int alloc_numeric(ceit_plan* p) {
   if (p->alloc_mode == want) return 0;
   void** bufs[] = {&p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
                    &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->g0e, &p->Aint, &p->Lint,
-                   &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1};
+                   &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1, &p->XP};
   for (auto b : bufs) dev_free_tracked(p, *b);
   // excitation workspace depends on the type too
   void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS};
@@ -240,7 +242,8 @@ int alloc_numeric(ceit_plan* p) {
   if ((rc = dev_alloc(p, &p->Sel, (h.szD + h.szS + h.szPP + h.szV) * es))) return rc;
   if ((rc = dev_alloc(p, &p->K0U, h.N0P * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Zw, h.N0P * h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->Xh, h.NP * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Xh, h.N * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->XP, h.N0P * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Aint, h.szPP * es))) return rc;
   if ((rc = dev_alloc(p, &p->Lint, h.szPP * es))) return rc;
   if ((rc = dev_alloc(p, &p->LintInv, h.szPP * es))) return rc;
@@ -273,8 +276,8 @@ int alloc_excitation_ws(ceit_plan* p, int want_cap) {
   if ((rc = dev_alloc(p, &p->Ls, c * u2 * es))) return rc;
   if ((rc = dev_alloc(p, &p->Linvs, c * u2 * es))) return rc;
   if ((rc = dev_alloc(p, &p->Sinv, c * u2 * es))) return rc;
-  if ((rc = dev_alloc(p, &p->Yh, c * h.NP * h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->phi0, c * h.NP * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Yh, c * h.N * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->phi0, c * h.N * es))) return rc;
   if ((rc = dev_alloc(p, &p->tvec, c * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->tmpS, c * (int64_t)TILE * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, (void**)&p->d_elec, c * h.L * sizeof(double)))) return rc;
@@ -296,7 +299,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   int rc = alloc_numeric<T>(p);
   if (rc) return rc;
   T *Ad = (T*)p->Ad, *Bs = (T*)p->Bs, *Ld = (T*)p->Ld, *Linv = (T*)p->Linv, *Lsub = (T*)p->Lsub;
-  T *Sel = (T*)p->Sel, *K0U = (T*)p->K0U, *Zw = (T*)p->Zw, *Xh = (T*)p->Xh, *KUU = (T*)p->KUU;
+  T *Sel = (T*)p->Sel, *K0U = (T*)p->K0U, *Zw = (T*)p->Zw, *Xh = (T*)p->XP, *Xc = (T*)p->Xh, *KUU = (T*)p->KUU;   // Xh: padded rows here
   T *SU = (T*)p->SU, *Ptmp = (T*)p->Ptmp, *tmpPanel = (T*)p->tmpPanel, *g0e = (T*)p->g0e;
   T *Aint = (T*)p->Aint, *Lint = (T*)p->Lint, *LintInv = (T*)p->LintInv, *Ainv = (T*)p->Ainv;
   T *Bt = (T*)p->Bt, *Wn = (T*)p->Wn, *Tm = (T*)p->Tm, *G1 = (T*)p->G1;
@@ -405,7 +408,9 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   }
   // S_U = K_UU - K_0U^T X
   gemm<T>(st, 1, 0, nU, nU, N0P, mone, K0U, nU, 0, Xh, nU, 0, one, SU, nU, 0);
-  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, st>>>((int)nU, Xh + N0P * nU);
+  compact_rows_kernel<T><<<cdiv(h.N0, 8), 256, 0, st>>>(h.N0, (int)nU, p->d_row_map, Xh, Xc);
+  CEIT_COUNT_LAUNCH();
+  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, st>>>((int)nU, Xc + h.N0 * nU);
   CEIT_COUNT_LAUNCH();
   gather_g0_kernel<T><<<cdiv(6 * h.E, 256), 256, 0, st>>>(6 * h.E, p->d_g0_off, Sel, g0e);
   CEIT_COUNT_LAUNCH();
@@ -418,7 +423,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
 template <class T>
 int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
   const HostPlan& h = p->h;
-  const int64_t nU = h.nU, N = h.NP, N0 = h.N0P, u2 = nU * nU;   // position space (padded)
+  const int64_t nU = h.nU, N = h.N, N0 = h.N0, u2 = nU * nU;   // compact position space
   T *St = (T*)p->St, *Ls = (T*)p->Ls, *Linvs = (T*)p->Linvs, *Sinv = (T*)p->Sinv, *Yh = (T*)p->Yh;
   T *phi0 = (T*)p->phi0, *tvec = (T*)p->tvec, *tmpS = (T*)p->tmpS, *Xh = (T*)p->Xh, *SU = (T*)p->SU;
   const T one = Sc<T>::one(), zero = Sc<T>::zero();
@@ -449,7 +454,7 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
 int excitation_chunk_cap(const ceit_plan* p, size_t es) {
   const HostPlan& h = p->h;
   const double budget = 24.0e9;  // bytes of Yh kept at once
-  double per = (double)h.NP * h.nU * es + 4.0 * h.nU * h.nU * es;
+  double per = (double)h.N * h.nU * es + 4.0 * h.nU * h.nU * es;
   int cap = (int)std::max(1.0, std::min((double)h.L, budget / per));
   return cap;
 }
@@ -460,12 +465,12 @@ int launch_woodbury_patch(ceit_plan* p, const double* g0e, const double* Xh, con
   const HostPlan& h = p->h;
   const size_t psm = woodbury_patch_smem(h.nU, h.patch_node_cap);
   double4* consts = (double4*)p->tmpS;      // free after the batched factorisation of the excitation stage
-  node_consts_kernel<<<dim3(cdiv(h.nU, 128), nbatch), 128, 0, st>>>((int)h.nU, h.NP, h.N0P, phi0, p->d_wk, consts);
+  node_consts_kernel<<<dim3(cdiv(h.nU, 128), nbatch), 128, 0, st>>>((int)h.nU, h.N, h.N0, phi0, p->d_wk, consts);
   CEIT_COUNT_LAUNCH();
   CUDA_TRY(cudaFuncSetAttribute(woodbury_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
   dim3 grid(p->n_patches, nbatch);
   woodbury_patch_kernel<<<grid, WBP_WARPS * 32, psm, st>>>(e_from, e_to, (int)h.L, (int)h.nU, (int)woodbury_pitch(h.nU),
-                                                          h.NP, h.N0P, p->d_patch_eptr, p->d_patch_elems, p->d_patch_nptr,
+                                                          h.N, h.N0, p->d_patch_eptr, p->d_patch_elems, p->d_patch_nptr,
                                                           p->d_patch_nodes, p->d_patch_local, p->d_area, g0e, Xh, Yh,
                                                           phi0, p->d_ue_ptr, consts, i0, s_coef, J, ldJ,
                                                           (int)h.patch_node_cap);
@@ -496,7 +501,7 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
     }
     if (rc) return rc;
     if (base) {
-      baseline_kernel<T><<<nbatch, 64, 0, st>>>((int)h.L, (int)h.nU, h.NP, h.N0P, (const T*)p->phi0, p->d_we_ptr,
+      baseline_kernel<T><<<nbatch, 64, 0, st>>>((int)h.L, (int)h.nU, h.N, h.N0, (const T*)p->phi0, p->d_we_ptr,
                                                 p->d_we_u, p->d_we_w, (int)i0, base, nullptr);
       CEIT_COUNT_LAUNCH();
     }
@@ -509,7 +514,7 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
     } else if (e_to > e_from && J) {
       StageScope sc(3, st);
       dim3 grid(cdiv(e_to - e_from, warps), nbatch);
-      woodbury_kernel<T><<<grid, warps * 32, smem, st>>>((int)e_from, (int)e_to, (int)h.L, (int)h.nU, h.NP, h.N0P,
+      woodbury_kernel<T><<<grid, warps * 32, smem, st>>>((int)e_from, (int)e_to, (int)h.L, (int)h.nU, h.N, h.N0,
                                                          p->d_elem_pos, p->d_area, (const T*)p->g0e, (const T*)p->Xh,
                                                          (const T*)p->Yh, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
                                                          p->d_we_w, (int)i0, 2.0 * omega * c, J, ldJ);
@@ -529,7 +534,7 @@ int forward_impl(ceit_plan* p, int64_t i, double* node_abs, double* elem_pot, do
   rc = excitation_impl<T>(p, (int)i, 1, st);
   if (rc) return rc;
   if (electrode_pot) {
-    baseline_kernel<T><<<1, 64, 0, st>>>((int)h.L, (int)h.nU, h.NP, h.N0P, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
+    baseline_kernel<T><<<1, 64, 0, st>>>((int)h.L, (int)h.nU, h.N, h.N0, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
                                          p->d_we_w, (int)i, nullptr, electrode_pot);
     CEIT_COUNT_LAUNCH();
   }
@@ -614,12 +619,13 @@ int ceit_plan_info(const ceit_plan_t* p, int64_t* info) {
 }
 
 int ceit_plan_tables(const ceit_plan_t* p, int64_t* rowptr, int64_t* colidx, int64_t* pos, int64_t* blk_ptr,
-                     int64_t* U) {
+                     int64_t* U, int64_t* ppos) {
   if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_tables: null plan");
   const HostPlan& h = p->h;
   if (rowptr) for (int64_t k = 0; k <= h.N; ++k) rowptr[k] = h.rowptr[k];
   if (colidx) for (int64_t k = 0; k < h.nnz; ++k) colidx[k] = h.colidx[k];
   if (pos) for (int64_t k = 0; k < h.N; ++k) pos[k] = h.pos[k];
+  if (ppos) for (int64_t k = 0; k < h.N; ++k) ppos[k] = h.ppos[k];
   if (blk_ptr) for (int64_t k = 0; k <= h.nb; ++k) blk_ptr[k] = h.blk_ptr[k];
   if (U) for (int64_t k = 0; k < h.nU; ++k) U[k] = h.U[k];
   return CEIT_OK;
@@ -694,6 +700,20 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
   if (!rows) m_sel = m;
   if (m_sel <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_model: empty row selection");
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // keep the stream-ordered pool's memory across synchronisations (the default threshold of 0 hands
+    // gigabytes back to the driver at every sync and re-maps them on the next call)
+    static bool pool_set = false;
+    if (!pool_set) {
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+      pool_set = true;
+    }
+  }
   StageScope sc(4, st);
   if (form == 0) form = (m_sel <= n_det) ? 2 : 1;
   const int64_t n = (form == 2) ? m_sel : n_det;  // size of the SPD system

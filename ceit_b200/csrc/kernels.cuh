@@ -141,6 +141,18 @@ bnd_rows_gather_kernel(int64_t nrows, int nU, const int32_t* __restrict__ bnd_lo
   for (int k = lane; k < nU; k += 32) G1[r * nU + k] = (c < 0) ? Sc<T>::zero() : X_C[(int64_t)c * nU + k];
 }
 
+// Xh[c,:] = XP[row_map[c],:]: drop the padding slots of the interiors (one warp per row)
+template <class T>
+__global__ void __launch_bounds__(256)
+compact_rows_kernel(int64_t N0, int nU, const int32_t* __restrict__ row_map, const T* __restrict__ XP,
+                    T* __restrict__ Xh) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= N0) return;
+  const T* s = XP + (int64_t)row_map[r] * nU;
+  for (int k = lane; k < nU; k += 32) Xh[r * nU + k] = s[k];
+}
+
 // rows [N0, N) of Xh = -I
 template <class T>
 __global__ void fill_neg_identity_kernel(int nU, T* __restrict__ Xh_tail) {

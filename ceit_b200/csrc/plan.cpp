@@ -476,6 +476,23 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
       p.g0_off[6 * e + q] = off;
     }
   }
+  // ---- compact position space for everything downstream of the base stage (Xh, Yh, phi0, Woodbury):
+  // the padding slots of the interiors are dropped; row_map sends a compact F0 row to its padded row ----
+  p.ppos = p.pos;
+  p.row_map.assign(p.N0, -1);
+  {
+    int32_t q = 0;
+    for (int64_t r = 0; r < p.N0P; ++r)
+      if (p.node_at[r] >= 0) {
+        p.pos[p.node_at[r]] = q;
+        p.row_map[q] = (int32_t)r;
+        ++q;
+      }
+    if (q != p.N0) throw std::runtime_error("plan: position compaction lost nodes");
+    for (int64_t u = 0; u < p.nU; ++u) p.pos[p.U[u]] = (int32_t)(p.N0 + u);
+  }
+  for (int64_t e = 0; e < E; ++e)
+    for (int a = 0; a < 3; ++a) p.elem_pos[3 * e + a] = p.pos[p.elem[3 * e + a]];
 }
 
 

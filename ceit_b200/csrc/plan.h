@@ -32,7 +32,9 @@ struct HostPlan {
   std::vector<int32_t> ue_ptr;                // L+1
   std::vector<double> wk;                     // nU: weight of the node inside its electrode
   // ordering
-  std::vector<int32_t> pos;                   // node -> position (F0 block order, then N0+u)
+  std::vector<int32_t> pos;                   // node -> COMPACT position (F0 nodes in padded order, then N0+u)
+  std::vector<int32_t> ppos;                  // node -> padded position (factor stage)
+  std::vector<int32_t> row_map;               // N0: compact F0 row -> padded row
   std::vector<int32_t> node_at;               // position -> node
   std::vector<int32_t> blk_ptr;               // nb+1 (level-2 local positions)
   std::vector<int32_t> blk_of;                // nC: block of level-2 local position

@@ -60,11 +60,12 @@ int ceit_plan_destroy(ceit_plan_t* plan);
 int ceit_plan_info(const ceit_plan_t* plan, int64_t* info24);
 /* host copies of the symbolic tables (any pointer may be NULL):
  * rowptr i64[N+1], colidx i64[nnz] (CSR pattern of K, sorted, == scipy.sparse.csr_matrix of the
- * reference's dense K_sparse), pos i64[N] (node -> row in position space: interior p slot a ->
- * p*nI + a, separator nodes in level-2 block order from P*nI, electrode nodes from N0P),
- * blk_ptr i64[n_blocks+1] (level-2 local), U i64[nU]. */
+ * reference's dense K_sparse), pos i64[N] (node -> row of Xh / Yh / phi0: a permutation, F0 nodes
+ * first, electrode node u at N0 + u), blk_ptr i64[n_blocks+1] (level-2 local), U i64[nU],
+ * ppos i64[N] (node -> padded row of the factor stage: interior p slot a -> p*nI + a, separator nodes
+ * in level-2 block order from P*nI, electrode nodes from N0P). */
 int ceit_plan_tables(const ceit_plan_t* plan, int64_t* rowptr, int64_t* colidx, int64_t* pos,
-                     int64_t* blk_ptr, int64_t* U);
+                     int64_t* blk_ptr, int64_t* U, int64_t* ppos);
 
 /* ---- K1: element matrices -> CSR values ------------------------------------------------------
  * Replaces EFEM.construct_sparse_matrix (CEIT/EFEM.py:47-69) incl. its uniform factor 2 and the

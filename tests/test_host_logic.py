@@ -56,8 +56,10 @@ def test_plan_tables(golden, tag, target, nd):
     # CSR pattern bit-exact with scipy.sparse.csr_matrix(reference K_sparse)
     assert np.array_equal(tb["rowptr"], r["K_indptr"]) and np.array_equal(tb["colidx"], r["K_indices"])
     N = p.N
-    pos = tb["pos"]
-    assert len(set(pos.tolist())) == N and pos.min() >= 0 and pos.max() < p.NP     # injective into position space
+    assert sorted(tb["pos"].tolist()) == list(range(N))                            # compact: a permutation
+    assert np.array_equal(tb["pos"][tb["U"]], p.N0 + np.arange(p.nU))
+    pos = tb["ppos"]
+    assert len(set(pos.tolist())) == N and pos.min() >= 0 and pos.max() < p.NP     # padded: injective
     U = tb["U"]
     expect_U = []
     for e in m["electrodes"]:

@@ -116,7 +116,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -343,9 +343,18 @@ def run_gpu(args):
             per_launch_ms = wb_ms / wb_n
             cols_per_launch = my_cols * args.steps / wb_n
             ach = bytes_per_col * cols_per_launch / (per_launch_ms * 1e-3) / 1e9
-            k2 = {"kernel": "woodbury_kernel<double>", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                  "frac": ach / hbm, "traffic": None, "peak_source": hbm_src, "ms_per_launch": per_launch_ms,
-                  "algorithmic_bytes_per_launch": bytes_per_col * cols_per_launch}
+            traffic, traffic_src = None, None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))["woodbury_patch_kernel"]
+                if ws == 1:          # the capture is of the full 16 x 5000 launch
+                    traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            except Exception:
+                pass
+            k2 = {"kernel": "woodbury_patch_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                  "frac": ach / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
+                  "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": bytes_per_col * cols_per_launch,
+                  "note": "algorithmic bytes = (8 r + 96 + 8 (L-1)) per column (SURVEY.md 8d); at this size Yh is "
+                          "largely L2-resident, the kernel is shared-memory/FP64-issue bound (profiles/)"}
         stage_ms = {k: v[0] / args.steps for k, v in stages.items() if v[1]}
         rooflines = {"stage_ms_per_step": stage_ms, "woodbury": k2}
         if realtime:
@@ -389,7 +398,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -131,6 +131,9 @@ struct ceit_plan {
   void *tmpPanel = nullptr, *g0e = nullptr;
   void *Aint = nullptr, *Lint = nullptr, *LintInv = nullptr, *Ainv = nullptr, *Bt = nullptr, *Wn = nullptr;
   void *Tm = nullptr, *G1 = nullptr;
+  void *Mreg = nullptr, *LT = nullptr, *LinvT = nullptr, *Tinv = nullptr, *te = nullptr, *YT = nullptr, *ye = nullptr;
+  double* d_gamma = nullptr;
+  void *TBB = nullptr, *LB = nullptr, *LinvB = nullptr, *Dcat = nullptr;
   int32_t *d_node_at = nullptr, *d_bnd_loc = nullptr, *d_m2_src_ptr = nullptr, *d_m2_src = nullptr;
   int32_t *d_rc_ptr = nullptr, *d_rc_src = nullptr;
   int64_t *d_m2_dst = nullptr, *d_sg_off = nullptr;
@@ -222,10 +225,12 @@ int alloc_numeric(ceit_plan* p) {
   if (p->alloc_mode == want) return 0;
   void** bufs[] = {&p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
                    &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->g0e, &p->Aint, &p->Lint,
-                   &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1, &p->XP};
+                   &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1, &p->XP, &p->Mreg, &p->LT,
+                   &p->LinvT, &p->Tinv, &p->te, &p->YT, &p->ye};
   for (auto b : bufs) dev_free_tracked(p, *b);
   // excitation workspace depends on the type too
-  void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS};
+  void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS,
+                 &p->TBB, &p->LB, &p->LinvB, &p->Dcat};
   for (auto b : ex) dev_free_tracked(p, *b);
   p->ex_cap = 0;
   p->alloc_mode = 0;
@@ -252,6 +257,14 @@ int alloc_numeric(ceit_plan* p) {
   if ((rc = dev_alloc(p, &p->Wn, h.szV * es))) return rc;
   if ((rc = dev_alloc(p, &p->Tm, h.P * h.bmax * h.bmax * es))) return rc;
   if ((rc = dev_alloc(p, &p->G1, h.P * h.bmax * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Mreg, h.nU * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->LT, h.nU * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->LinvT, h.nU * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Tinv, h.nU * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->te, h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->YT, h.N * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->ye, h.N * es))) return rc;
+  if (!p->d_gamma && (rc = dev_alloc(p, (void**)&p->d_gamma, sizeof(double)))) return rc;
   if ((rc = dev_alloc(p, &p->KUU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->SU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Ptmp, maxS * es))) return rc;
@@ -265,7 +278,8 @@ template <class T>
 int alloc_excitation_ws(ceit_plan* p, int want_cap) {
   const int want_mode = Sc<T>::is_complex ? 2 : 1;
   if (p->ex_cap >= want_cap && p->ex_mode == want_mode) return 0;
-  void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS};
+  void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS,
+                 &p->TBB, &p->LB, &p->LinvB, &p->Dcat};
   for (auto b : ex) dev_free_tracked(p, *b);
   if (p->d_elec) { void* q = p->d_elec; dev_free_tracked(p, q); p->d_elec = nullptr; }
   const HostPlan& h = p->h;
@@ -280,10 +294,22 @@ int alloc_excitation_ws(ceit_plan* p, int want_cap) {
   if ((rc = dev_alloc(p, &p->phi0, c * h.N * es))) return rc;
   if ((rc = dev_alloc(p, &p->tvec, c * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->tmpS, c * (int64_t)TILE * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->TBB, c * (int64_t)h.bp * h.bp * es))) return rc;
+  if ((rc = dev_alloc(p, &p->LB, c * (int64_t)h.bp * h.bp * es))) return rc;
+  if ((rc = dev_alloc(p, &p->LinvB, c * (int64_t)h.bp * h.bp * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Dcat, c * (int64_t)(h.bp + 1) * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, (void**)&p->d_elec, c * h.L * sizeof(double)))) return rc;
   p->ex_cap = want_cap;
   p->ex_mode = want_mode;
   return 0;
+}
+
+// the rank-(b+1) excitation path needs contiguous electrode ranges in U, <= 64 nodes per electrode and
+// nU <= 1024; otherwise every excitation factorises its own padded S_U (excitation_direct)
+int g_direct_excitation = 0;
+inline bool use_rank_update(const ceit_plan* p) {
+  const HostPlan& h = p->h;
+  return !g_direct_excitation && h.u_contiguous && h.bp <= 64 && h.nU <= 1024 && h.nU > h.bp;
 }
 
 // ---- base stage -----------------------------------------------------------------------------------
@@ -414,6 +440,24 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   CEIT_COUNT_LAUNCH();
   gather_g0_kernel<T><<<cdiv(6 * h.E, 256), 256, 0, st>>>(6 * h.E, p->d_g0_off, Sel, g0e);
   CEIT_COUNT_LAUNCH();
+  if (use_rank_update(p)) {
+    // T = (S_U + gamma e e^T)^-1, t_e = T e, Y_T = Xh T, y_e = Y_T e: shared by every excitation
+    T *Mreg = (T*)p->Mreg, *LT = (T*)p->LT, *LinvT = (T*)p->LinvT, *Tinv = (T*)p->Tinv, *te = (T*)p->te;
+    T *YT = (T*)p->YT, *ye = (T*)p->ye;
+    trace_gamma_kernel<T><<<1, 256, 0, st>>>((int)nU, SU, p->d_gamma);
+    CEIT_COUNT_LAUNCH();
+    add_rank1_e_kernel<T><<<cdiv(nU * nU, 256), 256, 0, st>>>((int)nU, SU, p->d_gamma, Mreg);
+    CEIT_COUNT_LAUNCH();
+    CUDA_TRY(cudaMemsetAsync(LT, 0, nU * nU * es, st));
+    CUDA_TRY(cudaMemsetAsync(LinvT, 0, nU * nU * es, st));
+    potrf_trtri_blocked<T>(st, nU, Mreg, nU, 0, LT, nU, 0, LinvT, nU, 0, (T*)p->Zw /* free by now */, 0, 1, p->d_info);
+    gemm<T>(st, 1, 0, nU, nU, nU, one, LinvT, nU, 0, LinvT, nU, 0, zero, Tinv, nU, 0);
+    rowsum_e_kernel<T><<<cdiv(nU, 8), 256, 0, st>>>(nU, (int)nU, Tinv, te);
+    CEIT_COUNT_LAUNCH();
+    gemm<T>(st, 0, 0, h.N, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);
+    rowsum_e_kernel<T><<<cdiv(h.N, 8), 256, 0, st>>>(h.N, (int)nU, YT, ye);
+    CEIT_COUNT_LAUNCH();
+  }
   KERNEL_CHECK();
   p->mode = Sc<T>::is_complex ? 2 : 1;
   return 0;
@@ -428,6 +472,33 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
   T *phi0 = (T*)p->phi0, *tvec = (T*)p->tvec, *tmpS = (T*)p->tmpS, *Xh = (T*)p->Xh, *SU = (T*)p->SU;
   const T one = Sc<T>::one(), zero = Sc<T>::zero();
   const size_t es = sizeof(T);
+  if (use_rank_update(p)) {
+    // rank-(b+1) update of the shared inverse T (kernels.cuh): no per-excitation nU x nU factorisation
+    const int bp = h.bp;
+    T *TBB = (T*)p->TBB, *LB = (T*)p->LB, *LinvB = (T*)p->LinvB, *Dcat = (T*)p->Dcat;
+    T *Tinv = (T*)p->Tinv, *te = (T*)p->te, *YT = (T*)p->YT, *ye = (T*)p->ye;
+    gather_tbb_kernel<T><<<dim3(cdiv(bp * bp, 256), nbatch), 256, 0, st>>>((int)nU, bp, Tinv, p->d_ue_ptr, i0, TBB);
+    CEIT_COUNT_LAUNCH();
+    potrf_trtri_blocked<T>(st, bp, TBB, bp, (int64_t)bp * bp, LB, bp, (int64_t)bp * bp, LinvB, bp, (int64_t)bp * bp,
+                           nullptr, 0, nbatch, p->d_info);
+    const size_t sm1 = (size_t)(2 * bp * bp + bp + nU + 256) * es;
+    const size_t sm2 = (size_t)((bp + 1) * nU + 16 * (bp + 1)) * es;
+    static bool attr_done = false;
+    if (!attr_done) {
+      CUDA_TRY(cudaFuncSetAttribute(excite_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+    excite_small_kernel<T><<<nbatch, 256, sm1, st>>>((int)nU, bp, Tinv, te, LinvB, p->d_ue_ptr, i0, p->d_gamma, Dcat);
+    CEIT_COUNT_LAUNCH();
+    constexpr int RT = Sc<T>::is_complex ? 8 : 16;
+    rank_update_kernel<T><<<dim3(cdiv(nU, RT), nbatch), 256, sm2, st>>>(nU, (int)nU, bp, Tinv, te, Dcat, p->d_ue_ptr, i0,
+                                                                       1, Sinv, u2);
+    CEIT_COUNT_LAUNCH();
+    rank_update_kernel<T><<<dim3(cdiv(N, RT), nbatch), 256, sm2, st>>>(N, (int)nU, bp, YT, ye, Dcat, p->d_ue_ptr, i0, 0,
+                                                                      Yh, N * nU);
+    CEIT_COUNT_LAUNCH();
+  } else {
   dim3 g2(cdiv(u2, 256), nbatch);
   build_stilde_kernel<T><<<g2, 256, 0, st>>>((int)nU, SU, p->d_inB, i0, St);
   CEIT_COUNT_LAUNCH();
@@ -439,10 +510,15 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
   CEIT_COUNT_LAUNCH();
   // Yh[b] = Xh Sinv[b]
   gemm<T>(st, 0, 0, N, nU, nU, one, Xh, nU, 0, Sinv, nU, u2, zero, Yh, nU, N * nU, nbatch);
+  }
   dim3 g3(cdiv(nU, 8), nbatch);
   phi_u_kernel<T><<<g3, 256, 0, st>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 0);
   CEIT_COUNT_LAUNCH();
   phi_u_kernel<T><<<g3, 256, 0, st>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 1);
+  CEIT_COUNT_LAUNCH();
+  phi_u_kernel<T><<<g3, 256, 0, st>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 2);
+  CEIT_COUNT_LAUNCH();
+  phi_u_kernel<T><<<g3, 256, 0, st>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 3);
   CEIT_COUNT_LAUNCH();
   dim3 g4(cdiv(N0, 8), nbatch);
   phi_f_kernel<T><<<g4, 256, 0, st>>>(N0, (int)nU, Xh, phi0, N);
@@ -820,6 +896,10 @@ int ceit_set_option(const char* name, int64_t value) {
   if (!name) CEIT_FAIL(CEIT_ERR_ARG, "ceit_set_option: null name");
   if (std::strcmp(name, "force_simt_gemm") == 0) {
     ceit::g_force_simt = (int)value;
+    return CEIT_OK;
+  }
+  if (std::strcmp(name, "direct_excitation") == 0) {
+    g_direct_excitation = (int)value;
     return CEIT_OK;
   }
   if (std::strcmp(name, "nd_interior") == 0) {

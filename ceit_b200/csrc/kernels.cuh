@@ -197,7 +197,205 @@ __global__ void mask_sinv_kernel(int nU, const uint8_t* __restrict__ inB, int i0
   if (mask[r] || mask[c]) Sinv[(int64_t)b * nU * nU + q] = Sc<T>::zero();
 }
 
-// phiU[b] = -Sinv[b] * (sum_{u in B_i} SU[:,u]);  phiU[B_i] = 1.   One warp per row.
+// ------------------------------------------------------------------------------------------------
+// Per-excitation Schur stage as a rank-(b+1) update of ONE inverse:
+//   M = S_U + gamma e e^T (e = 1/sqrt(nU): S_U 1 = 0 on the real base),  T = M^-1,  Y_T = Xh T,
+//   Sinv_i = T - T[:,B] C_i + alpha q q^T,  C_i = T_BB^-1 T[B,:],  q = T e - T[:,B] C_i e (zero on B),
+//   alpha = gamma / (1 - gamma e.q),   Yh_i = Y_T - Y_T[:,B] D_i + alpha (Y_T e) q^T,
+//   D_i = C_i + alpha (C_i e) q^T.   B = B_i is the contiguous range [lo, lo+b) of U.
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void trace_gamma_kernel(int nU, const T* __restrict__ SU, double* __restrict__ gamma) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int k = threadIdx.x; k < nU; k += 256) s += to_cd(SU[(int64_t)k * nU + k]).x;
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) gamma[0] = red[0] / nU;
+}
+template <class T>
+__global__ void add_rank1_e_kernel(int nU, const T* __restrict__ SU, const double* __restrict__ gamma,
+                                   T* __restrict__ M) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nU * nU) return;
+  M[q] = add(SU[q], Sc<T>::from_real(gamma[0] / nU));
+}
+// out[r] = (1/sqrt(nU)) sum_k A[r,k]; one warp per row
+template <class T>
+__global__ void __launch_bounds__(256)
+rowsum_e_kernel(int64_t rows, int nU, const T* __restrict__ A, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  T acc = Sc<T>::zero();
+  for (int k = lane; k < nU; k += 32) acc = add(acc, A[r * nU + k]);
+  cd a = to_cd(acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+    a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+  }
+  if (lane == 0) out[r] = Sc<T>::from_cd(scale(rsqrt((double)nU), a));
+}
+// TBB[b] = T[B_i, B_i] padded to bp x bp with identity
+template <class T>
+__global__ void gather_tbb_kernel(int nU, int bp, const T* __restrict__ Tm, const int32_t* __restrict__ ue_ptr,
+                                  int i0, T* __restrict__ out) {
+  const int i = i0 + blockIdx.y;
+  const int lo = ue_ptr[i], b = ue_ptr[i + 1] - lo;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= bp * bp) return;
+  const int a = q / bp, c = q - a * bp;
+  T v = (a == c) ? Sc<T>::one() : Sc<T>::zero();
+  if (a < b && c < b) v = Tm[(int64_t)(lo + a) * nU + lo + c];
+  out[(int64_t)blockIdx.y * bp * bp + q] = v;
+}
+// one CTA per excitation: Dcat[b] ((bp+1) x nU): rows j < b = D_i, row bp = alpha q, other rows 0
+template <class T>
+__global__ void __launch_bounds__(256)
+excite_small_kernel(int nU, int bp, const T* __restrict__ Tm, const T* __restrict__ te,
+                    const T* __restrict__ LinvB, const int32_t* __restrict__ ue_ptr, int i0,
+                    const double* __restrict__ gamma, T* __restrict__ Dcat) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* Li = reinterpret_cast<T*>(smem_raw);   // [bp][bp]
+  T* Bi = Li + bp * bp;                     // [bp][bp]  T_BB^-1
+  T* ce = Bi + bp * bp;                     // [bp]
+  T* q = ce + bp;                           // [nU]
+  T* red = q + nU;                          // [256]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = i0 + blockIdx.x;
+  const int lo = ue_ptr[i], b = ue_ptr[i + 1] - lo;
+  T* D = Dcat + (int64_t)blockIdx.x * (bp + 1) * nU;
+  const T* Lg = LinvB + (int64_t)blockIdx.x * bp * bp;
+  for (int t = tid; t < bp * bp; t += 256) Li[t] = Lg[t];
+  __syncthreads();
+  for (int t = tid; t < bp * bp; t += 256) {
+    const int a = t / bp, c = t - a * bp;
+    T acc = Sc<T>::zero();
+    for (int k = (a > c ? a : c); k < bp; ++k) acc = fma_(Li[k * bp + a], Li[k * bp + c], acc);
+    Bi[t] = acc;
+  }
+  __syncthreads();
+  // C = T_BB^-1 T[B,:]  (stored in D for now); rows >= b are zero
+  for (int t = tid; t < bp * nU; t += 256) {
+    const int j = t / nU, k = t - j * nU;
+    T acc = Sc<T>::zero();
+    if (j < b)
+      for (int m = 0; m < b; ++m) acc = fma_(Bi[j * bp + m], Tm[(int64_t)(lo + m) * nU + k], acc);
+    D[(int64_t)j * nU + k] = acc;
+  }
+  __syncthreads();
+  // ce = C e
+  const double se = rsqrt((double)nU);
+  for (int j = warp; j < bp; j += 8) {
+    T acc = Sc<T>::zero();
+    for (int k = lane; k < nU; k += 32) acc = add(acc, D[(int64_t)j * nU + k]);
+    cd a = to_cd(acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+      a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+    }
+    if (lane == 0) ce[j] = Sc<T>::from_cd(scale(se, a));
+  }
+  __syncthreads();
+  // q = T e - T[:,B] ce (T symmetric: T[k, lo+j] = T[lo+j, k]); zero on B
+  T part = Sc<T>::zero();
+  for (int k = tid; k < nU; k += 256) {
+    T v = te[k];
+    for (int j = 0; j < b; ++j) v = sub(v, mul(Tm[(int64_t)(lo + j) * nU + k], ce[j]));
+    if (k >= lo && k < lo + b) v = Sc<T>::zero();
+    q[k] = v;
+    part = add(part, v);
+  }
+  red[tid] = part;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) red[tid] = add(red[tid], red[tid + o]);
+    __syncthreads();
+  }
+  const T eq = Sc<T>::from_cd(scale(se, to_cd(red[0])));
+  const double g = gamma[0];
+  const T alpha = mul(Sc<T>::from_real(g), inv_(sub(Sc<T>::one(), scale(g, eq))));
+  for (int t = tid; t < bp * nU; t += 256) {
+    const int j = t / nU, k = t - j * nU;
+    if (j < b) D[(int64_t)j * nU + k] = add(D[(int64_t)j * nU + k], mul(mul(alpha, ce[j]), q[k]));
+  }
+  for (int k = tid; k < nU; k += 256) D[(int64_t)bp * nU + k] = mul(alpha, q[k]);
+}
+// out[b][n,k] = src[n,k] - sum_{j<b} src[n, lo+j] D[j,k] + yv[n] D[bp,k]; columns (and, if zero_rows, rows)
+// of B_i are set to exactly zero.  CTA = 16 rows x all columns of one excitation.
+template <class T>
+__global__ void __launch_bounds__(256)
+rank_update_kernel(int64_t rows, int nU, int bp, const T* __restrict__ src, const T* __restrict__ yv,
+                   const T* __restrict__ Dcat, const int32_t* __restrict__ ue_ptr, int i0, int zero_rows,
+                   T* __restrict__ out, int64_t out_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int RT = Sc<T>::is_complex ? 8 : 16, CMAX = 4;   // nU <= 1024
+  T* Ds = reinterpret_cast<T*>(smem_raw);   // [(bp+1)][nU]
+  T* As = Ds + (int64_t)(bp + 1) * nU;      // [RT][bp+1]
+  const int tid = threadIdx.x;
+  const int i = i0 + blockIdx.y;
+  const int lo = ue_ptr[i], b = ue_ptr[i + 1] - lo;
+  const int64_t n0 = (int64_t)blockIdx.x * RT;
+  const T* D = Dcat + (int64_t)blockIdx.y * (bp + 1) * nU;
+  for (int t = tid; t < (bp + 1) * nU; t += 256) Ds[t] = D[t];
+  for (int t = tid; t < RT * (bp + 1); t += 256) {
+    const int r = t / (bp + 1), j = t - r * (bp + 1);
+    const int64_t n = n0 + r;
+    T v = Sc<T>::zero();
+    if (n < rows) {
+      if (j < b) v = src[n * nU + lo + j];
+      else if (j == bp) v = neg(yv[n]);
+    }
+    As[t] = v;
+  }
+  __syncthreads();
+  T acc[RT][CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    const int k = tid + 256 * c;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) acc[r][c] = (k < nU && n0 + r < rows) ? src[(n0 + r) * nU + k] : Sc<T>::zero();
+  }
+  for (int j = 0; j <= bp; ++j) {
+    if (j >= b && j < bp) continue;
+    T dv[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      const int k = tid + 256 * c;
+      dv[c] = (k < nU) ? Ds[(int64_t)j * nU + k] : Sc<T>::zero();
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const T a = As[r * (bp + 1) + j];
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) acc[r][c] = sub(acc[r][c], mul(a, dv[c]));
+    }
+  }
+  T* o = out + (int64_t)blockIdx.y * out_stride;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    const int k = tid + 256 * c;
+    if (k >= nU) continue;
+    const bool colB = (k >= lo && k < lo + b);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int64_t n = n0 + r;
+      if (n >= rows) continue;
+      const bool rowB = zero_rows && (n >= lo && n < lo + b);
+      o[n * nU + k] = (colB || rowB) ? Sc<T>::zero() : acc[r][c];
+    }
+  }
+}
+
+// phiU[b] = -Sinv[b] * (sum_{u in B_i} SU[:,u]);  phiU[B_i] = 1, followed by one step of iterative
+// refinement against S_U itself (stages 2, 3) so that phi0 does not inherit the rounding of Sinv.
+// One warp per row.
 template <class T>
 __global__ void __launch_bounds__(256)
 phi_u_kernel(int nU, const T* __restrict__ SU, const T* __restrict__ Sinv, const uint8_t* __restrict__ inB,
@@ -212,10 +410,14 @@ phi_u_kernel(int nU, const T* __restrict__ SU, const T* __restrict__ Sinv, const
     const T* r = SU + (int64_t)row * nU;
     for (int u = lane; u < nU; u += 32)
       if (mask[u]) acc = add(acc, r[u]);
-  } else {           // phiU[row] = -sum_k Sinv[row][k] tvec[k]
+  } else if (stage == 1 || stage == 3) {   // sum_k Sinv[row][k] tvec[k]
     const T* r = Sinv + (int64_t)b * nU * nU + (int64_t)row * nU;
     const T* tv = tvec + (int64_t)b * nU;
     for (int k = lane; k < nU; k += 32) acc = fma_(r[k], tv[k], acc);
+  } else {                                 // stage 2: residual of S_RR phi_R = -S_RB 1 with the current phi
+    const T* r = SU + (int64_t)row * nU;
+    const T* pu = phi0 + (int64_t)b * N + N0;
+    for (int k = lane; k < nU; k += 32) acc = fma_(r[k], pu[k], acc);
   }
   cd a = to_cd(acc);
 #pragma unroll
@@ -224,8 +426,11 @@ phi_u_kernel(int nU, const T* __restrict__ SU, const T* __restrict__ Sinv, const
     a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
   }
   if (lane == 0) {
+    T* pu = phi0 + (int64_t)b * N + N0;
     if (stage == 0) tvec[(int64_t)b * nU + row] = Sc<T>::from_cd(a);
-    else phi0[(int64_t)b * N + N0 + row] = mask[row] ? Sc<T>::one() : neg(Sc<T>::from_cd(a));
+    else if (stage == 1) pu[row] = mask[row] ? Sc<T>::one() : neg(Sc<T>::from_cd(a));
+    else if (stage == 2) tvec[(int64_t)b * nU + row] = mask[row] ? Sc<T>::zero() : neg(Sc<T>::from_cd(a));
+    else if (!mask[row]) pu[row] = add(pu[row], Sc<T>::from_cd(a));      // stage 3: one refinement step
   }
 }
 

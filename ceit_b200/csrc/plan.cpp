@@ -121,6 +121,11 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
       }
     }
   }
+  {
+    int32_t mx = 0;
+    for (int64_t m = 0; m < L; ++m) mx = std::max<int32_t>(mx, (int32_t)node_sets[m].size());
+    p.bp = (mx + 7) / 8 * 8;
+  }
   // ---- CSR pattern of K: node adjacency incl. diagonal ---------------------------------------
   {
     std::vector<int32_t> deg(N + 1, 0);

@@ -31,6 +31,7 @@ struct HostPlan {
   bool u_contiguous = false;                  // electrode m owns U[ue_ptr[m]:ue_ptr[m+1]] exclusively
   std::vector<int32_t> ue_ptr;                // L+1
   std::vector<double> wk;                     // nU: weight of the node inside its electrode
+  int32_t bp = 0;                             // max nodes per electrode, rounded up to a multiple of 8
   // ordering
   std::vector<int32_t> pos;                   // node -> COMPACT position (F0 nodes in padded order, then N0+u)
   std::vector<int32_t> ppos;                  // node -> padded position (factor stage)

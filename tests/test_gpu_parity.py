@@ -373,3 +373,36 @@ def test_large_mesh_properties(torch_cuda, n, per_side):
     # electrode ring onto itself: electrode m <-> L-m); triangles are not mirror images (fixed
     # diagonal) so compare the element-pair sums of every cell row instead of single elements
     s["plan"].close()
+
+
+@pytest.mark.parametrize("is_complex", [False, True])
+def test_rank_update_excitation_equals_direct_factorisation(torch_cuda, golden, is_complex):
+    """Per-excitation Schur stage: rank-(b+1) update of one shared inverse vs a factorisation of every
+    padded S_U (the fallback path) - same J, real and complex-symmetric base."""
+    t = torch_cuda
+    m, r = golden("50_50")
+    E, L = len(m["elem"]), 16
+    omega = 2 * np.pi * 2e4
+    p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"])
+    perm = t.tensor(m["elem_perm"], device="cuda")
+    var = t.full((E,), 3e-8 if is_complex else 0.0, dtype=t.float64, device="cuda")
+    out = []
+    for direct in (0, 1):
+        _lib.set_option("direct_excitation", direct)
+        try:
+            p.assemble(perm, var, omega)
+            p.factor(is_complex)
+            J = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
+            base = t.zeros(L * (L - 1), dtype=t.float64, device="cuda")
+            p.jacobian_block(0, L, 0, E, 1e-3, omega, J, E, base)
+            assert p.numeric_flag() == 0
+            out.append((J.clone(), base.clone()))
+        finally:
+            _lib.set_option("direct_excitation", 0)
+    assert (out[0][0] - out[1][0]).abs().max().item() < 1e-11
+    assert (out[0][1] - out[1][1]).abs().max().item() < 1e-11
+    assert (out[0][1] - 1).abs().max().item() < (1e-9 if is_complex else 5e-13)   # phi0 == 1 on the real base
+    d0, d1 = out[0][0] - 1, out[1][0] - 1
+    big = d1.abs() > 1e-9
+    assert ((d0[big] - d1[big]).abs() / d1[big].abs()).max().item() < 1e-3
+    p.close()

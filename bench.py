@@ -40,6 +40,44 @@ def load_mesh(tag="50_50"):
     return m
 
 
+CONFIGS = {
+    # BASELINE.json configs[1] (the N=1 headline), [2] and [3]
+    "50_50": dict(kind="fixture", tag="50_50", workload=None),
+    "200": dict(kind="synthetic", n=200, per_side=5,
+                workload="synthetic structured 200x200-node mesh (79202 elements, pitch 2 mm), 16 electrodes: full "
+                         "Jacobian (1267232 columns) + Gauss-Newton inverse model (lambda=289)"),
+    "400": dict(kind="synthetic", n=400, per_side=9,
+                workload="synthetic structured 400x400-node mesh (318402 elements, pitch 2 mm), 32 electrodes: full "
+                         "Jacobian (10188864 columns) + Gauss-Newton inverse model (lambda=289)"),
+}
+
+
+def load_workload(name):
+    """mesh arrays + electrode element lists + detection index, built with the product's own mesh model."""
+    cfg = CONFIGS[name]
+    if cfg["kind"] == "fixture":
+        m = load_mesh(cfg["tag"])
+        return dict(nodes=m["nodes"], elem=m["elem"], elem_perm=m["elem_perm"], elem_param=m["elem_param"],
+                    electrodes=m["electrodes"], detection_index=m["detection_index"], workload=WORKLOAD)
+    from ceit_b200 import meshgen
+    from ceit_b200.models.mesh import MeshObj
+    td = tempfile.mkdtemp(prefix="ceit_bench_")
+    old = os.environ.get("CEIT_B200_CONFIG")
+    os.environ["CEIT_B200_CONFIG"] = meshgen.make_synthetic_workspace(td, cfg["n"], cfg["per_side"])
+    try:
+        mesh = MeshObj()
+    finally:
+        if old is None:
+            del os.environ["CEIT_B200_CONFIG"]
+        else:
+            os.environ["CEIT_B200_CONFIG"] = old
+        import shutil
+        shutil.rmtree(td, ignore_errors=True)
+    return dict(nodes=mesh.nodes, elem=mesh.elem, elem_perm=mesh.elem_perm,
+                electrodes=[mesh.electrode_mesh[i] for i in range(mesh.electrode_num)],
+                detection_index=mesh.detection_index, workload=cfg["workload"])
+
+
 # ------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle's literal restatement of the reference's CPU path
 # ------------------------------------------------------------------------------------------------------
@@ -171,10 +209,13 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if ws > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")           # keep stdout to the single JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    mesh = load_mesh()
+    mesh = load_workload(args.config)
+    workload = mesh["workload"]
+    is_headline = args.config == "50_50"
     N, E, L = len(mesh["nodes"]), len(mesh["elem"]), len(mesh["electrodes"])
     m_rows = L * (L - 1)
     omega = 2 * np.pi * FREQ
@@ -189,6 +230,9 @@ def run_gpu(args):
     base = torch.zeros(m_rows, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     i0, i1, e0, e1 = shard_ranges(L, E, ws, rank)
+    # inverse model: detection elements sharded over ranks (each rank produces its rows of inv_mat)
+    dlo, dhi = (n_det * rank) // ws, (n_det * (rank + 1)) // ws
+    det_local = det[dlo:dhi].contiguous()
     inv_holder = {}
 
     def step():
@@ -197,7 +241,9 @@ def run_gpu(args):
         plan.jacobian_block(i0, i1, e0, e1, C_PERT, omega, J, E, base)
         if ws > 1:
             gather_jacobian(J, L, E)
-        inv_holder["inv"] = _lib.inverse_model(J, det, LAMBDA, shift=1.0, form=0)
+            inv_holder["inv"] = _lib.inverse_model_sharded(J, det_local, LAMBDA, shift=1.0)
+        else:
+            inv_holder["inv"] = _lib.inverse_model(J, det, LAMBDA, shift=1.0, form=0)
 
     def barrier():
         torch.cuda.synchronize()
@@ -238,8 +284,10 @@ def run_gpu(args):
 
     # ---- realtime reconstruction: 100k batched frames resident in HBM, and single frames ---------------
     inv = inv_holder["inv"]
+    if ws > 1:   # the rows of inv_mat live on their ranks; the realtime leg below runs on rank 0 with the full matrix
+        inv = _lib.inverse_model(J, det, LAMBDA, shift=1.0, form=0)
     realtime = None
-    if rank == 0:
+    if rank == 0 and is_headline:
         g = torch.Generator(device=dev).manual_seed(0)
         dV = torch.rand((m_rows, N_FRAMES), dtype=torch.float64, device=dev, generator=g)
         out = torch.empty((n_det, N_FRAMES), dtype=torch.float64, device=dev)
@@ -288,7 +336,7 @@ def run_gpu(args):
 
     # ---- e2e: the drop-in classes, host (numpy) in / out, cache files written like the reference -----
     e2e = None
-    if rank == 0:
+    if rank == 0 and is_headline:
         shm = "/dev/shm" if os.path.isdir("/dev/shm") else None
         with tempfile.TemporaryDirectory(dir=shm) as td:
             cfg = dict(meshgen.REFERENCE_CONFIG)
@@ -346,7 +394,7 @@ def run_gpu(args):
             traffic, traffic_src = None, None
             try:
                 tj = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))["woodbury_patch_kernel"]
-                if ws == 1:          # the capture is of the full 16 x 5000 launch
+                if ws == 1 and is_headline:          # the capture is of the full 16 x 5000 launch
                     traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
             except Exception:
                 pass
@@ -364,6 +412,7 @@ def run_gpu(args):
                 "frac": realtime["batched_frac_of_cublas_dgemm"], "traffic": None,
                 "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (no f64 entry in MEASURED_PEAKS.json)"}
         roofline = k2
+    if rank == 0 and is_headline:
         cpu_cols = 6
         v = cpu_baseline_columns(mesh, cpu_cols)
         cpu = {"value": v, "unit": "columns/s", "cores": blas_threads(), "kind": "port",
@@ -381,10 +430,12 @@ def run_gpu(args):
             "metric": "jacobian_columns_per_s", "value": value, "unit": "columns/s", "n_gpus": ws,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "MESH_50_50 mesh fixture (tests/golden/mesh_50_50.npz), zero base variable; seeded synthetic frames",
-            "config": {"workload": WORKLOAD,
+            "data": ("MESH_50_50 mesh fixture (tests/golden/mesh_50_50.npz), zero base variable; seeded synthetic frames"
+                     if is_headline else "synthetic structured mesh (ceit_b200.meshgen), zero base variable"),
+            "config": {"workload": workload,
                        "N": N, "E": E, "L": L, "columns_per_step": n_cols, "l2": "flushed between timed steps (256 MiB memset)",
-                       "sharding": f"excitation blocks over {ws} rank(s), all-gather J, inverse model replicated"},
+                       "sharding": f"excitation blocks over {ws} rank(s), all-gather J (NCCL), inverse model sharded "
+                                   f"over detection elements (one all-reduce of the m x m Gram matrix)"},
             "gpu_launches": int(launches), "wall_s_timed_region": wall,
             "clocks": clocks, "e2e": e2e, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu,
             "realtime": realtime,
@@ -401,6 +452,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="50_50", choices=sorted(CONFIGS), help="workload (default: the headline MESH_50_50)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -17,7 +17,7 @@ SYMBOLS = [
     "ceit_last_error", "ceit_version", "ceit_launch_count", "ceit_plan_create", "ceit_plan_destroy",
     "ceit_plan_info", "ceit_plan_tables", "ceit_assemble", "ceit_factor", "ceit_jacobian_block",
     "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm", "ceit_plan_csr_values",
-    "ceit_set_option", "ceit_stage_times",
+    "ceit_set_option", "ceit_stage_times", "ceit_gram_partial", "ceit_inverse_from_gram", "ceit_debug_tile_clocks",
 ]
 
 
@@ -60,6 +60,9 @@ def lib():
     L.ceit_set_option.argtypes = [ctypes.c_char_p, c_i64]
     L.ceit_plan_csr_values.argtypes = [c_vp, c_vp, c_vp]
     L.ceit_stage_times.argtypes = [c_vp, c_vp]
+    L.ceit_gram_partial.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_vp]
+    L.ceit_inverse_from_gram.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp]
+    L.ceit_debug_tile_clocks.argtypes = [c_vp]
     for name in SYMBOLS:
         if name not in ("ceit_last_error", "ceit_launch_count"):
             getattr(L, name).restype = c_int
@@ -200,6 +203,25 @@ def inverse_model(J, det_idx, lmbda, rows=None, shift=1.0, form=0, scale=1.0):
     out = torch.empty((n_det, m_sel), dtype=torch.float64, device=J.device)
     check(lib().ceit_inverse_model(tptr(J), ldJ, m, tptr(det_idx), n_det, tptr(rows), m_sel, float(shift),
                                    float(lmbda), int(form), float(scale), tptr(out), stream_ptr()))
+    return out
+
+
+def inverse_model_sharded(J, det_idx_local, lmbda, shift=1.0, scale=1.0, group=None):
+    """Dual-form inverse model with the detection elements sharded over the ranks of `group`:
+    partial Gram matrices are summed with one all-reduce; returns this rank's rows (n_det_local, m)."""
+    torch = require_cuda()
+    import torch.distributed as dist
+    m, ldJ = J.shape[0], J.stride(0)
+    n_loc = det_idx_local.numel()
+    G = torch.empty((m, m), dtype=torch.float64, device=J.device)
+    check(lib().ceit_gram_partial(tptr(J), ldJ, m, tptr(det_idx_local), n_loc, tptr(None), m, float(shift), tptr(G),
+                                  stream_ptr()))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+    out = torch.empty((n_loc, m), dtype=torch.float64, device=J.device)
+    if n_loc:
+        check(lib().ceit_inverse_from_gram(tptr(J), ldJ, m, tptr(det_idx_local), n_loc, tptr(None), m, float(shift),
+                                           float(lmbda), float(scale), tptr(G), tptr(out), stream_ptr()))
     return out
 
 

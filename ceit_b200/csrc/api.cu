@@ -835,6 +835,68 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
   return CEIT_OK;
 }
 
+// ---- sharded inverse model (dual form): partial Gram matrix, then rows of inv from the reduced Gram ----
+int ceit_gram_partial(const double* J, int64_t ldJ, int64_t m, const int64_t* det_idx, int64_t n_det,
+                      const int64_t* rows, int64_t m_sel, double shift, double* G, void* stream) {
+  if (!J || !det_idx || !G) CEIT_FAIL(CEIT_ERR_ARG, "ceit_gram_partial: null argument");
+  if (!rows) m_sel = m;
+  if (m <= 0 || n_det < 0 || m_sel <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_gram_partial: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  StageScope sc(4, st);
+  if (n_det == 0) {
+    CUDA_TRY(cudaMemsetAsync(G, 0, m_sel * m_sel * sizeof(double), st));
+    return CEIT_OK;
+  }
+  double* Jt = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&Jt, m_sel * n_det * sizeof(double), st));
+  gather_shift_kernel<<<cdiv(m_sel * n_det, 256), 256, 0, st>>>(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
+  CEIT_COUNT_LAUNCH();
+  gemm<double>(st, 0, 1, m_sel, m_sel, n_det, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, m_sel, 0);
+  KERNEL_CHECK();
+  CUDA_TRY(cudaFreeAsync(Jt, st));
+  return CEIT_OK;
+}
+
+int ceit_inverse_from_gram(const double* J, int64_t ldJ, int64_t m, const int64_t* det_idx, int64_t n_det,
+                           const int64_t* rows, int64_t m_sel, double shift, double lambda, double scale_,
+                           const double* G, double* inv_out, void* stream) {
+  if (!J || !det_idx || !G || !inv_out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_from_gram: null argument");
+  if (!rows) m_sel = m;
+  if (m <= 0 || n_det <= 0 || m_sel <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_from_gram: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  StageScope sc(4, st);
+  const int64_t n = m_sel;
+  double *Jt = nullptr, *Gw = nullptr, *Lg = nullptr, *Li = nullptr, *Gi = nullptr, *tmp = nullptr;
+  int* info = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&Jt, m_sel * n_det * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&Gw, n * n * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&Lg, n * n * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&Li, n * n * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&Gi, n * n * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&tmp, (int64_t)TILE * n * sizeof(double), st));
+  CUDA_TRY(cudaMallocAsync((void**)&info, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(Lg, 0, n * n * sizeof(double), st));
+  CUDA_TRY(cudaMemsetAsync(Li, 0, n * n * sizeof(double), st));
+  CUDA_TRY(cudaMemcpyAsync(Gw, G, n * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, Gw, n);
+  CEIT_COUNT_LAUNCH();
+  gather_shift_kernel<<<cdiv(m_sel * n_det, 256), 256, 0, st>>>(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
+  CEIT_COUNT_LAUNCH();
+  potrf_trtri_blocked<double>(st, n, Gw, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info);
+  gemm<double>(st, 1, 0, n, n, n, 1.0, Li, n, 0, Li, n, 0, 0.0, Gi, n, 0);
+  gemm<double>(st, 1, 0, n_det, m_sel, m_sel, scale_, Jt, n_det, 0, Gi, n, 0, 0.0, inv_out, m_sel, 0);
+  KERNEL_CHECK();
+  CUDA_TRY(cudaFreeAsync(Jt, st));
+  CUDA_TRY(cudaFreeAsync(Gw, st));
+  CUDA_TRY(cudaFreeAsync(Lg, st));
+  CUDA_TRY(cudaFreeAsync(Li, st));
+  CUDA_TRY(cudaFreeAsync(Gi, st));
+  CUDA_TRY(cudaFreeAsync(tmp, st));
+  CUDA_TRY(cudaFreeAsync(info, st));
+  return CEIT_OK;
+}
+
 int ceit_reconstruct(const double* inv, const double* dV, double* out, int64_t n_det, int64_t m, int64_t F,
                      void* stream) {
   if (!inv || !dV || !out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_reconstruct: null argument");

@@ -118,6 +118,18 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
                        int64_t n_det, const int64_t* rows, int64_t m_sel, double shift,
                        double lambda, int form, double scale, double* inv_out, void* stream);
 
+/* ---- inverse model sharded over detection elements (multi-GPU, dual form) -------------------------
+ * Each rank holds a slice det_idx[0..n_det) of the detection elements (J replicated):
+ *   ceit_gram_partial      G_r = Jt_r Jt_r^T (m_sel x m_sel) over its slice; the caller sums G over ranks
+ *                          (one all-reduce of m_sel^2 doubles);
+ *   ceit_inverse_from_gram rows of inv for the slice: Jt_r^T (G + lambda^2 I)^-1  (n_det x m_sel).
+ * Same arithmetic as ceit_inverse_model(form = 2) (CEIT/Solver.py:110-124). */
+int ceit_gram_partial(const double* J, int64_t ldJ, int64_t m, const int64_t* det_idx, int64_t n_det,
+                      const int64_t* rows, int64_t m_sel, double shift, double* G, void* stream);
+int ceit_inverse_from_gram(const double* J, int64_t ldJ, int64_t m, const int64_t* det_idx, int64_t n_det,
+                           const int64_t* rows, int64_t m_sel, double shift, double lambda, double scale,
+                           const double* G, double* inv_out, void* stream);
+
 /* ---- realtime reconstruction ---------------------------------------------------------------------
  * Replaces Solver.solve (CEIT/Solver.py:95-108): out = inv_mat . delta_V
  * inv [dev] f64[n_det*m]; dV [dev] f64[m*F] row-major (F=1: a vector); out [dev] f64[n_det*F]. */

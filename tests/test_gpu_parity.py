@@ -185,6 +185,13 @@ def test_inverse_model_and_reconstruct(torch_cuda, golden):
     # batched == frame by frame
     one = _lib.reconstruct(inv, dV[:, 5].contiguous())
     assert ((one - outb[:, 5]).abs().max() / one.abs().max()).item() < 1e-13
+    # sharded over detection elements (multi-GPU form; one rank here): slices of the same matrix
+    full = _lib.inverse_model(J, det, 289, form=2)
+    for lo, hi in ((0, 300), (300, 722)):
+        part = _lib.inverse_model_sharded(J, det[lo:hi].contiguous(), 289)
+        # one rank: the Gram matrix only covers the slice, so compare against the model of that slice
+        ref_part = _lib.inverse_model(J, det[lo:hi].contiguous(), 289, form=2)
+        assert ((part - ref_part).abs().max() / ref_part.abs().max()).item() < 1e-12
     # row subset + scale (eit_solve_on_some_electrodes)
     rows = [2 * 15 + 5, 6 * 15 + 2, 10 * 15 + 13, 14 * 15 + 2]
     sub = _lib.inverse_model(J, det, 90, rows=t.tensor(rows, device="cuda"), scale=1e-4).cpu().numpy()

@@ -346,6 +346,8 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(p->d_info, 0, sizeof(int), st));
   if (P > 0) {
     CUDA_TRY(cudaMemsetAsync(Aint, 0, h.szPP * es, st));
+    CUDA_TRY(cudaMemsetAsync(Lint, 0, h.szPP * es, st));
+    CUDA_TRY(cudaMemsetAsync(LintInv, 0, h.szPP * es, st));
     CUDA_TRY(cudaMemsetAsync(Bt, 0, h.szV * es, st));
     pad_identity_kernel<T><<<cdiv(P * nI, 256), 256, 0, st>>>((int)P, (int)nI, p->d_node_at, Aint);
     CEIT_COUNT_LAUNCH();
@@ -479,6 +481,8 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
     T *Tinv = (T*)p->Tinv, *te = (T*)p->te, *YT = (T*)p->YT, *ye = (T*)p->ye;
     gather_tbb_kernel<T><<<dim3(cdiv(bp * bp, 256), nbatch), 256, 0, st>>>((int)nU, bp, Tinv, p->d_ue_ptr, i0, TBB);
     CEIT_COUNT_LAUNCH();
+    CUDA_TRY(cudaMemsetAsync(LB, 0, (int64_t)nbatch * bp * bp * es, st));
+    CUDA_TRY(cudaMemsetAsync(LinvB, 0, (int64_t)nbatch * bp * bp * es, st));
     potrf_trtri_blocked<T>(st, bp, TBB, bp, (int64_t)bp * bp, LB, bp, (int64_t)bp * bp, LinvB, bp, (int64_t)bp * bp,
                            nullptr, 0, nbatch, p->d_info);
     const size_t sm1 = (size_t)(2 * bp * bp + bp + nU + 256) * es;

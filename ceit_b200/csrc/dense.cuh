@@ -16,6 +16,54 @@ __device__ long long g_tile_clk[8];
 #define CEIT_CLK(k) do { } while (0)
 #endif
 
+// One phase (16 pivot columns j = 16 PH .. 16 PH + 15) of the unscaled elimination of a 64 x 64 tile.
+// Thread (rb, cb) holds c[u][v] = S[rb + 16 u][cb + 16 v].  Every step ends with one barrier; the loop
+// runs to the block-uniform bound n, so all threads execute the same number of barriers.
+template <class T, int PH>
+__device__ __forceinline__ void tile_eliminate_phase(T* __restrict__ S, T* __restrict__ rpiv, T (&c)[4][4], int rb,
+                                                     int cb, int n) {
+  constexpr int LD = TILE + 1;
+#pragma unroll 1
+  for (int jj = 0; jj < 16; ++jj) {
+    const int j = 16 * PH + jj;
+    if (j >= n) break;
+    const T rp = rpiv[j];
+    T cj[4], tk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cj[u] = S[(rb + 16 * u) * LD + j];
+#pragma unroll
+    for (int v = PH; v < 4; ++v) tk[v] = mul(S[(cb + 16 * v) * LD + j], rp);
+    if (cb <= jj) tk[PH] = Sc<T>::zero();                 // my column of this phase is already final
+    if (jj < 15) {
+      // next pivot column is cb == jj + 1 of block PH; its diagonal element is row block PH as well
+      if (cb == jj + 1 && rb == jj + 1) rpiv[j + 1] = rcp_fast(sub(c[PH][PH], mul(cj[PH], tk[PH])));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = PH; v < 4; ++v) c[u][v] = sub(c[u][v], mul(cj[u], tk[v]));
+      if (cb == jj + 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) S[(rb + 16 * u) * LD + j + 1] = c[u][PH];
+      }
+    } else {
+      // last step of the phase: the next pivot column is column 0 of block PH + 1
+      if (PH < 3) {
+        if (cb == 0 && rb == 0) rpiv[j + 1] = rcp_fast(sub(c[PH < 3 ? PH + 1 : 3][PH < 3 ? PH + 1 : 3],
+                                                          mul(cj[PH < 3 ? PH + 1 : 3], tk[PH < 3 ? PH + 1 : 3])));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = PH; v < 4; ++v) c[u][v] = sub(c[u][v], mul(cj[u], tk[v]));
+      if (PH < 3 && cb == 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) S[(rb + 16 * u) * LD + j + 1] = c[u][PH < 3 ? PH + 1 : 3];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // One level of the block recursion for the inverse of a lower-triangular 64x64 tile held in shared
 // memory (leading dimension 65): for every pair of diagonal blocks of size HALF,
 //   W = L21 X11 (X11 lower triangular),  X21 = -X22 W (X22 lower triangular).
@@ -36,7 +84,8 @@ __device__ __forceinline__ void tri_inverse_level(const T* __restrict__ S, T* __
   T acc[NOUT];
 #pragma unroll
   for (int u = 0; u < NOUT; ++u) acc[u] = Sc<T>::zero();
-  for (int k = c; k < HALF; ++k) {
+#pragma unroll 8
+  for (int k = 0; k < HALF; ++k) {                 // X11 is lower triangular: rows k < c are exact zeros
     const T xv = X[(o + k) * LD + o + c];
 #pragma unroll
     for (int u = 0; u < NOUT; ++u) acc[u] = fma_(S[(o + HALF + r0 + u * RSTEP) * LD + o + k], xv, acc[u]);
@@ -46,6 +95,7 @@ __device__ __forceinline__ void tri_inverse_level(const T* __restrict__ S, T* __
   __syncthreads();
 #pragma unroll
   for (int u = 0; u < NOUT; ++u) acc[u] = Sc<T>::zero();
+#pragma unroll 8
   for (int k = 0; k < HALF; ++k) {
     const T wv = W[(o + HALF + k) * LD + o + c];
 #pragma unroll
@@ -115,45 +165,13 @@ potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA,
     for (int v = 0; v < 4; ++v) c[u][v] = S[(rb + 16 * u) * LD + cb + 16 * v];
   if (tid == 0) rpiv[0] = rcp_fast(S[0]);
   __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    if (cb + 48 > j) {                 // the thread still owns a column that is not final
-      const T rp = rpiv[j];
-      T cj[4], tk[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) cj[u] = S[(rb + 16 * u) * LD + j];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        const int k = cb + 16 * v;
-        tk[v] = (k > j) ? mul(S[k * LD + j], rp) : Sc<T>::zero();
-      }
-      const int jn = j + 1;
-      const int vn = jn >> 4;          // which of my columns could be column j+1
-      const bool own_next = ((jn & 15) == cb);
-      if (own_next && ((jn & 15) == rb)) {
-        // I own the next pivot element (row j+1, col j+1): update it first and start its reciprocal
-        T pv = Sc<T>::zero();
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v)
-            if (u == vn && v == vn) pv = sub(c[u][v], mul(cj[u], tk[v]));
-        rpiv[jn] = rcp_fast(pv);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) c[u][v] = sub(c[u][v], mul(cj[u], tk[v]));
-      if (own_next) {
-#pragma unroll
-        for (int v = 0; v < 4; ++v)
-          if (v == vn) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) S[(rb + 16 * u) * LD + jn] = c[u][v];
-          }
-      }
-    }
-    __syncthreads();
-  }
+  // The 64 steps are split into 4 phases of 16 (PH = j >> 4, a compile-time constant inside a phase), so
+  // that "which of my columns are still live" and "which register holds the next pivot column" are static:
+  // columns v < PH are final, v > PH always live, v == PH live iff cb > (j & 15).
+  tile_eliminate_phase<T, 0>(S, rpiv, c, rb, cb, n);
+  tile_eliminate_phase<T, 1>(S, rpiv, c, rb, cb, n);
+  tile_eliminate_phase<T, 2>(S, rpiv, c, rb, cb, n);
+  tile_eliminate_phase<T, 3>(S, rpiv, c, rb, cb, n);
   CEIT_CLK(2);
   // ---- L = S diag(p)^-1/2 ; rdiag = 1 / L_jj --------------------------------------------------------
   {
@@ -194,11 +212,13 @@ potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA,
   tri_inverse_level<T, 16>(S, X, W, tid);
   tri_inverse_level<T, 32>(S, X, W, tid);
   CEIT_CLK(5);
-  for (int q = tid; q < n * n; q += 256) {
-    const int r = q / n, c = q - r * n;
-    const T z = Sc<T>::zero();
-    L[(int64_t)r * ldl + c] = (c <= r) ? S[r * LD + c] : z;
-    Linv[(int64_t)r * ldi + c] = (c <= r) ? X[r * LD + c] : z;
+  // the caller zero-initialises L and Linv, so only the lower triangle is written
+  for (int q = tid; q < TILE * TILE; q += 256) {
+    const int r = q >> 6, cc = q & 63;
+    if (r < n && cc <= r) {
+      L[(int64_t)r * ldl + cc] = S[r * LD + cc];
+      Linv[(int64_t)r * ldi + cc] = X[r * LD + cc];
+    }
   }
   CEIT_CLK(6);
 }

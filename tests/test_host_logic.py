@@ -221,3 +221,17 @@ def test_cpu_device_is_rejected_and_no_gpu_fails_loudly(workspace):
         workspace("21_21")
         with pytest.raises(_lib.CeitError, match="no CPU fallback"):
             EFEM()
+
+
+def test_bench_reference_arm_contract(capsys):
+    """`bench.py --impl reference` prints one JSON line with the contract's keys (1 tiny step, CPU only)."""
+    import argparse
+    import bench
+    bench.run_reference(argparse.Namespace(gpus=1, steps=1, warmup=0, impl="reference", config="50_50"))
+    line = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["metric"] == "jacobian_columns_per_s" and d["unit"] == "columns/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["config"]["workload"] == bench.WORKLOAD

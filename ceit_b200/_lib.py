@@ -17,7 +17,7 @@ SYMBOLS = [
     "ceit_last_error", "ceit_version", "ceit_launch_count", "ceit_plan_create", "ceit_plan_destroy",
     "ceit_plan_info", "ceit_plan_tables", "ceit_assemble", "ceit_factor", "ceit_jacobian_block",
     "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm", "ceit_plan_csr_values",
-    "ceit_set_option", "ceit_stage_times", "ceit_gram_partial", "ceit_inverse_from_gram", "ceit_debug_tile_clocks",
+    "ceit_set_option", "ceit_stage_times", "ceit_gram_partial", "ceit_inverse_from_gram", "ceit_debug_tile_clocks", "ceit_zgemm",
 ]
 
 
@@ -63,6 +63,8 @@ def lib():
     L.ceit_gram_partial.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_vp]
     L.ceit_inverse_from_gram.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp]
     L.ceit_debug_tile_clocks.argtypes = [c_vp]
+    L.ceit_zgemm.argtypes = [c_int, c_int, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl,
+                             c_vp, c_i64, c_vp]
     for name in SYMBOLS:
         if name not in ("ceit_last_error", "ceit_launch_count"):
             getattr(L, name).restype = c_int
@@ -245,4 +247,18 @@ def dgemm(A, B, transA=False, transB=False, alpha=1.0, beta=0.0, C=None):
         C = torch.zeros((M, N), dtype=torch.float64, device=A.device)
     check(lib().ceit_dgemm(int(transA), int(transB), M, N, K, float(alpha), tptr(A), A.stride(0), tptr(B),
                            B.stride(0), float(beta), tptr(C), C.stride(0), stream_ptr()))
+    return C
+
+
+def zgemm(A, B, transA=False, transB=False, alpha=1.0 + 0j, beta=0j, C=None):
+    """complex128 tensors; non-conjugating transposes."""
+    torch = require_cuda()
+    M = A.shape[1] if transA else A.shape[0]
+    K = A.shape[0] if transA else A.shape[1]
+    N = B.shape[0] if transB else B.shape[1]
+    if C is None:
+        C = torch.zeros((M, N), dtype=torch.complex128, device=A.device)
+    alpha, beta = complex(alpha), complex(beta)
+    check(lib().ceit_zgemm(int(transA), int(transB), M, N, K, alpha.real, alpha.imag, tptr(A), A.stride(0), tptr(B),
+                           B.stride(0), beta.real, beta.imag, tptr(C), C.stride(0), stream_ptr()))
     return C

@@ -925,6 +925,16 @@ int ceit_dgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, 
   return CEIT_OK;
 }
 
+int ceit_zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha_re, double alpha_im, const double* A,
+               int64_t lda, const double* B, int64_t ldb, double beta_re, double beta_im, double* C, int64_t ldc,
+               void* stream) {
+  if (!A || !B || !C) CEIT_FAIL(CEIT_ERR_ARG, "ceit_zgemm: null argument");
+  gemm<cd>((cudaStream_t)stream, opA, opB, M, N, K, mk(alpha_re, alpha_im), (const cd*)A, lda, 0, (const cd*)B, ldb, 0,
+           mk(beta_re, beta_im), (cd*)C, ldc, 0);
+  KERNEL_CHECK();
+  return CEIT_OK;
+}
+
 int ceit_stage_times(double* ms, int64_t* counts) {
   if (!ms || !counts) CEIT_FAIL(CEIT_ERR_ARG, "ceit_stage_times: null argument");
   for (int k = 0; k < N_STAGES; ++k) {

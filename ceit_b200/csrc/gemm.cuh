@@ -3,7 +3,8 @@
 //     C[b] = alpha * op(A[b]) * op(B[b]) + beta * C[b],   b = 0..batch-1 (strided)
 //   * f64: FP64 tensor cores, mma.sync.aligned.m8n8k4.f64 (SASS DMMA).  tcgen05 has no f64
 //     kind, so on sm_100a DMMA *is* the FP64 tensor path.
-//   * complex f64: SIMT FMA tile kernel (same tiling, no tensor path yet).
+//   * complex f64: the same DMMA kernel structure on split re/im planes (four DMMA chains per complex
+//     tile product); a SIMT FMA tile kernel is kept as a cross-check (force_simt_gemm).
 #pragma once
 #include <atomic>
 #include "scalar.cuh"
@@ -169,6 +170,151 @@ gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A
 }
 
 // ------------------------------------------------------------------------------------------------
+// Complex f64 on the FP64 tensor cores: the interleaved (re, im) operands are split into real and
+// imaginary planes while they are copied to shared memory (two 8-byte cp.async per element), and every
+// complex tile product is four DMMA chains:  Cr += Ar Br + (-Ai) Bi,  Ci += Ar Bi + Ai Br.
+// Same tiling, pipeline and bank-conflict-free strides as the real kernel.
+// ------------------------------------------------------------------------------------------------
+template <int BM, int BN, int WM, int WN, int OPA, int OPB, int STAGES>
+__global__ void __launch_bounds__(WM * WN * 32)
+gemm_zdmma_kernel(int M, int N, int K, cd alpha, const cd* __restrict__ A, int64_t lda, int64_t sA,
+                  const cd* __restrict__ B, int64_t ldb, int64_t sB, cd beta, cd* __restrict__ C, int64_t ldc,
+                  int64_t sC, int beta_zero) {
+  using SM = DmmaSmem<BM, BN, OPA, OPB>;
+  constexpr int BK = 16, NT = WM * WN * 32;
+  constexpr int SA = SM::SA, SB = SM::SB;
+  constexpr int TM = BM / WM, TN = BN / WN, MI = TM / 8, NI = TN / 8;
+  constexpr int ZSTAGE = 2 * SM::STAGE;            // re + im planes of A and B
+  extern __shared__ __align__(16) double dsm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int wm = (warp / WN) * TM, wn = (warp % WN) * TN;
+  A += (int64_t)blockIdx.z * sA;
+  B += (int64_t)blockIdx.z * sB;
+  C += (int64_t)blockIdx.z * sC;
+
+  double cr[MI][NI][2], ci[MI][NI][2];
+#pragma unroll
+  for (int i = 0; i < MI; ++i)
+#pragma unroll
+    for (int j = 0; j < NI; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+
+  auto issue = [&](int kt, int buf) {
+    double* Ar = dsm + buf * ZSTAGE;
+    double* Ai = Ar + SM::A_ELEMS;
+    double* Br = Ai + SM::A_ELEMS;
+    double* Bi = Br + SM::B_ELEMS;
+    const int k0 = kt * BK;
+#pragma unroll
+    for (int r = 0; r < (BM * BK) / NT; ++r) {
+      const int idx = tid + r * NT;
+      int m, k;
+      if (OPA == 0) {
+        k = idx & 15;
+        m = idx >> 4;
+      } else {
+        m = idx % BM;
+        k = idx / BM;
+      }
+      const int gm = m0 + m, gk = k0 + k;
+      const bool ok = (gm < M) && (gk < K);
+      const double* src =
+          reinterpret_cast<const double*>(ok ? ((OPA == 0) ? A + (int64_t)gm * lda + gk : A + (int64_t)gk * lda + gm) : A);
+      const int so = (OPA == 0) ? m * SA + k : k * SA + m;
+      cp_async8(Ar + so, src, ok);
+      cp_async8(Ai + so, src + 1, ok);
+    }
+#pragma unroll
+    for (int r = 0; r < (BN * BK) / NT; ++r) {
+      const int idx = tid + r * NT;
+      int n, k;
+      if (OPB == 0) {
+        n = idx % BN;
+        k = idx / BN;
+      } else {
+        k = idx & 15;
+        n = idx >> 4;
+      }
+      const int gn = n0 + n, gk = k0 + k;
+      const bool ok = (gn < N) && (gk < K);
+      const double* src =
+          reinterpret_cast<const double*>(ok ? ((OPB == 0) ? B + (int64_t)gk * ldb + gn : B + (int64_t)gn * ldb + gk) : B);
+      const int so = (OPB == 0) ? k * SB + n : n * SB + k;
+      cp_async8(Br + so, src, ok);
+      cp_async8(Bi + so, src + 1, ok);
+    }
+  };
+
+  const int nk = (K + BK - 1) / BK;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) issue(s, s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = kt + STAGES - 1;
+      if (nxt < nk) issue(nxt, nxt % STAGES);
+      cp_async_commit();
+    }
+    const double* Ar = dsm + (kt % STAGES) * ZSTAGE;
+    const double* Ai = Ar + SM::A_ELEMS;
+    const double* Br = Ai + SM::A_ELEMS;
+    const double* Bi = Br + SM::B_ELEMS;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double ar[MI], ai[MI], nai[MI], br[NI], bi[NI];
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const int m = wm + i * 8 + g, k = kk + t;
+        const int so = (OPA == 0) ? m * SA + k : k * SA + m;
+        ar[i] = Ar[so];
+        ai[i] = Ai[so];
+        nai[i] = -ai[i];
+      }
+#pragma unroll
+      for (int j = 0; j < NI; ++j) {
+        const int n = wn + j * 8 + g, k = kk + t;
+        const int so = (OPB == 0) ? k * SB + n : n * SB + k;
+        br[j] = Br[so];
+        bi[j] = Bi[so];
+      }
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) {
+          dmma_884(cr[i][j][0], cr[i][j][1], ar[i], br[j]);
+          dmma_884(ci[i][j][0], ci[i][j][1], ar[i], bi[j]);
+          dmma_884(cr[i][j][0], cr[i][j][1], nai[i], bi[j]);
+          dmma_884(ci[i][j][0], ci[i][j][1], ai[i], br[j]);
+        }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < MI; ++i) {
+    const int row = m0 + wm + i * 8 + g;
+    if (row >= M) continue;
+#pragma unroll
+    for (int j = 0; j < NI; ++j) {
+      const int col = n0 + wn + j * 8 + 2 * t;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (col + q < N) {
+          cd* p = C + (int64_t)row * ldc + col + q;
+          cd v = mul(alpha, mk(cr[i][j][q], ci[i][j][q]));
+          if (!beta_zero) v = fma_(beta, *p, v);
+          *p = v;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic SIMT tile kernel (any scalar type): 64x64 tile, BK = 16, 256 threads, 4x4 per thread.
 // ------------------------------------------------------------------------------------------------
 template <class T, int OPA, int OPB>
@@ -275,9 +421,50 @@ inline void gemm_simt_launch(cudaStream_t st, int opA, int opB, int64_t M, int64
 template <class T>
 inline void gemm(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, T alpha,
                  const T* A, int64_t lda, int64_t sA, const T* B, int64_t ldb, int64_t sB, T beta,
-                 T* C, int64_t ldc, int64_t sC, int batch = 1) {
+                 T* C, int64_t ldc, int64_t sC, int batch = 1);   // specialised for double and cd below
+
+template <int BM, int BN, int WM, int WN, int STAGES>
+inline void gemm_zdmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, cd alpha,
+                              const cd* A, int64_t lda, int64_t sA, const cd* B, int64_t ldb, int64_t sB, cd beta,
+                              cd* C, int64_t ldc, int64_t sC, int batch) {
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch), block(WM * WN * 32);
+  const int bz = is_zero(beta) ? 1 : 0;
+#define CEIT_ZDMMA_CASE(a, b)                                                                              \
+  {                                                                                                        \
+    constexpr size_t smem = (size_t)STAGES * 2 * DmmaSmem<BM, BN, a, b>::STAGE * sizeof(double);           \
+    static bool attr_done = false;                                                                         \
+    if (!attr_done) {                                                                                      \
+      cudaFuncSetAttribute(gemm_zdmma_kernel<BM, BN, WM, WN, a, b, STAGES>,                                \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
+      attr_done = true;                                                                                    \
+    }                                                                                                      \
+    gemm_zdmma_kernel<BM, BN, WM, WN, a, b, STAGES><<<grid, block, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, \
+                                                                              sA, B, ldb, sB, beta, C, ldc, sC, bz); \
+  }
+  if (opA == 0 && opB == 0) CEIT_ZDMMA_CASE(0, 0)
+  else if (opA == 0 && opB == 1) CEIT_ZDMMA_CASE(0, 1)
+  else if (opA == 1 && opB == 0) CEIT_ZDMMA_CASE(1, 0)
+  else CEIT_ZDMMA_CASE(1, 1)
+#undef CEIT_ZDMMA_CASE
+  CEIT_COUNT_LAUNCH();
+}
+
+template <>
+inline void gemm<cd>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, cd alpha, const cd* A,
+                     int64_t lda, int64_t sA, const cd* B, int64_t ldb, int64_t sB, cd beta, cd* C, int64_t ldc,
+                     int64_t sC, int batch) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
-  gemm_simt_launch<T>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+  if (g_force_simt) {
+    gemm_simt_launch<cd>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+    return;
+  }
+  auto ctas = [&](int64_t bm, int64_t bn) { return ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch; };
+  int cfg = g_gemm_tile;                       // 0 = auto, 1 = 32x32, 2/3 = 64x64
+  if (cfg == 0) cfg = (ctas(64, 64) >= 120) ? 2 : 1;
+  if (cfg >= 2)
+    gemm_zdmma_launch<64, 64, 2, 2, 3>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+  else
+    gemm_zdmma_launch<32, 32, 2, 2, 4>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
 }
 
 template <int BM, int BN, int WM, int WN, int STAGES>

@@ -142,6 +142,11 @@ int ceit_dgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, 
                int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
                void* stream);
 
+/* complex (interleaved re, im) variant: lda/ldb/ldc in complex elements; non-conjugating transposes */
+int ceit_zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha_re, double alpha_im,
+               const double* A, int64_t lda, const double* B, int64_t ldb, double beta_re, double beta_im,
+               double* C, int64_t ldc, void* stream);
+
 /* per-stage device times (CUDA events on the caller's stream) accumulated since the last call, when
  * ceit_set_option("stage_timers", 1) is on.  ms f64[8], counts i64[8]; stages: 0 assemble, 1 base
  * factorisation, 2 per-excitation stage, 3 Woodbury kernel, 4 inverse model, 5 reconstruct.

@@ -79,6 +79,32 @@ def _dgemm_cases(t, M, N, K, g):
             assert ((C - ref).abs().max() / ref.abs().max()).item() < 1e-13
 
 
+@pytest.mark.parametrize("tile", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(64, 64, 16), (1, 1, 1), (100, 37, 53), (273, 264, 202)])
+def test_zgemm_matches_torch_complex128(torch_cuda, shape, tile):
+    """complex DMMA kernel (split re/im planes, four DMMA chains) against torch.matmul in complex128"""
+    t = torch_cuda
+    M, N, K = shape
+    g = t.Generator(device="cuda").manual_seed(2)
+
+    def rnd(*s):
+        return t.complex(t.randn(*s, dtype=t.float64, device="cuda", generator=g),
+                         t.randn(*s, dtype=t.float64, device="cuda", generator=g))
+    _lib.set_option("gemm_tile", tile)
+    try:
+        for ta in (False, True):
+            for tb in (False, True):
+                A = rnd(*((K, M) if ta else (M, K)))
+                B = rnd(*((N, K) if tb else (K, N)))
+                C0 = rnd(M, N)
+                C = C0.clone()
+                _lib.zgemm(A, B, ta, tb, alpha=0.7 - 0.2j, beta=-0.3 + 0.1j, C=C)
+                ref = (0.7 - 0.2j) * ((A.T if ta else A) @ (B.T if tb else B)) + (-0.3 + 0.1j) * C0
+                assert ((C - ref).abs().max() / ref.abs().max()).item() < 1e-13
+    finally:
+        _lib.set_option("gemm_tile", 0)
+
+
 @pytest.mark.parametrize("tag", ["21_21", "50_50"])
 @pytest.mark.parametrize("target,nd", [(0, 64), (64, 0), (10 ** 6, 0), (0, 20), (100, 40)])
 def test_cabi_pipeline_against_reference(torch_cuda, golden, tag, target, nd):
@@ -413,3 +439,49 @@ def test_rank_update_excitation_equals_direct_factorisation(torch_cuda, golden, 
     big = d1.abs() > 1e-9
     assert ((d0[big] - d1[big]).abs() / d1[big].abs()).max().item() < 1e-3
     p.close()
+
+
+def test_overlapping_electrodes_use_the_fallback_paths(torch_cuda):
+    """Electrodes wide enough to share nodes: U ranges are no longer contiguous per electrode, so the
+    rank-update excitation stage and the patch Woodbury kernel hand over to the direct factorisation and
+    the warp-per-column kernel.  Checked against the brute-force oracle."""
+    t = torch_cuda
+    n = 30
+    cfg = meshgen.synthetic_config(n, 5, radius_mm=7.6)
+    nodes, elem = meshgen.structured_mesh(n)
+    param = o.elem_param(nodes, elem)
+    els = o.electrode_elements(param, np.array(cfg["electrode_centers"]) / 1000, cfg["electrode_radius"] / 1000)
+    sets = [set(np.unique(elem[np.asarray(e)].reshape(-1)).tolist()) for e in els]
+    assert any(sets[i] & sets[j] for i in range(len(sets)) for j in range(i + 1, len(sets)))   # they overlap
+    L, E = len(els), len(elem)
+    omega = 2 * np.pi * cfg["signal_frequency"]
+    p = _lib.Plan(nodes, elem, els)
+    p.assemble(t.ones(E, dtype=t.float64, device="cuda"), t.zeros(E, dtype=t.float64, device="cuda"), omega)
+    p.factor(False)
+    J = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
+    p.jacobian_block(0, L, 0, E, 1e-3, omega, J, E)
+    assert p.numeric_flag() == 0
+    rng = np.random.default_rng(2)
+    pairs = [(int(rng.integers(L)), int(rng.integers(E))) for _ in range(10)] + [(1, int(els[1][0])), (2, int(els[3][0]))]
+    cols = o.jacobian_columns_bruteforce(elem, param, np.ones(E), np.zeros(E), omega, els, pairs, 1e-3, len(nodes))
+    Jh = J.cpu().numpy()
+    for k, (i, j) in enumerate(pairs):
+        assert np.abs(Jh[_rows(i, L), j] - cols[k]).max() < RAW_TOL
+    p.close()
+
+
+def test_32_electrodes_small_mesh_against_oracle(torch_cuda):
+    s = _synthetic(torch_cuda, 70, 9)
+    L, E = s["L"], s["E"]
+    assert L == 32
+    rng = np.random.default_rng(9)
+    pairs = [(int(rng.integers(L)), int(rng.integers(E))) for _ in range(10)]
+    cols = o.jacobian_columns_bruteforce(s["elem"], s["param"], np.ones(E), np.zeros(E), s["omega"], s["els"], pairs,
+                                         1e-3, len(s["nodes"]))
+    Jh = s["J"].cpu().numpy()
+    for k, (i, j) in enumerate(pairs):
+        assert np.abs(Jh[_rows(i, L), j] - cols[k]).max() < RAW_TOL
+        sig = np.abs(cols[k] - 1).max()
+        if sig > 1e-10:
+            assert np.abs(Jh[_rows(i, L), j] - cols[k]).max() < 1e-3 * sig
+    s["plan"].close()

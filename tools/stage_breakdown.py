@@ -7,6 +7,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from ceit_b200 import _lib, meshgen
 import bench
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
+cplx = False
 target = int(sys.argv[sys.argv.index("--target") + 1]) if "--target" in sys.argv else 0
 if "--target" in sys.argv: args = [a for a in args if a != str(target)] if False else args
 tag = args[0] if args else "50_50"
@@ -29,9 +30,11 @@ perm = torch.tensor(perm_h, device="cuda"); var = torch.zeros(E, dtype=torch.flo
 det = torch.tensor(det_h, device="cuda")
 J = torch.zeros((L * (L - 1), E), dtype=torch.float64, device="cuda"); base = torch.zeros(L * (L - 1), dtype=torch.float64, device="cuda")
 def step(inv=True):
-    plan.assemble(perm, var, omega); plan.factor(False)
+    plan.assemble(perm, var, omega); plan.factor(cplx)
     plan.jacobian_block(0, L, 0, E, 1e-3, omega, J, E, base)
     if inv: return _lib.inverse_model(J, det, 289)
+cplx = "--complex" in sys.argv
+if cplx: var += 3e-8
 big = len(det_h) * L * (L - 1) * 8 > 20e9
 step(not big); torch.cuda.synchronize()
 _lib.set_option("stage_timers", 1); _lib.stage_times(); l0 = _lib.launch_count()

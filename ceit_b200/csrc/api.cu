@@ -490,18 +490,29 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
       CUDA_TRY(cudaFuncSetAttribute(excite_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_done = true;
     }
     excite_small_kernel<T><<<nbatch, 256, sm1, st>>>((int)nU, bp, Tinv, te, LinvB, p->d_ue_ptr, i0, p->d_gamma, Dcat);
     CEIT_COUNT_LAUNCH();
     constexpr int RT = Sc<T>::is_complex ? 8 : 16;
-    rank_update_kernel<T><<<dim3(cdiv(nU, RT), nbatch), 256, sm2, st>>>(nU, (int)nU, bp, Tinv, te, Dcat, p->d_ue_ptr, i0,
-                                                                       1, Sinv, u2);
-    CEIT_COUNT_LAUNCH();
-    rank_update_kernel<T><<<dim3(cdiv(N, RT), nbatch), 256, sm2, st>>>(N, (int)nU, bp, YT, ye, Dcat, p->d_ue_ptr, i0, 0,
-                                                                      Yh, N * nU);
-    CEIT_COUNT_LAUNCH();
+    auto update = [&](int64_t rows, const T* src, const T* yv, int zero_rows, T* out, int64_t stride) {
+      dim3 grid(nbatch, cdiv(rows, RT));
+      const int cmax = (int)((nU + 255) / 256);
+#define CEIT_RU(c) rank_update_kernel<T, c><<<grid, 256, sm2, st>>>(rows, (int)nU, bp, src, yv, Dcat, p->d_ue_ptr, i0, \
+                                                                  zero_rows, out, stride)
+      if (cmax <= 1) CEIT_RU(1);
+      else if (cmax == 2) CEIT_RU(2);
+      else if (cmax == 3) CEIT_RU(3);
+      else CEIT_RU(4);
+#undef CEIT_RU
+      CEIT_COUNT_LAUNCH();
+    };
+    update(nU, Tinv, te, 1, Sinv, u2);
+    update(N, YT, ye, 0, Yh, N * nU);
   } else {
   dim3 g2(cdiv(u2, 256), nbatch);
   build_stilde_kernel<T><<<g2, 256, 0, st>>>((int)nU, SU, p->d_inB, i0, St);

@@ -329,20 +329,20 @@ excite_small_kernel(int nU, int bp, const T* __restrict__ Tm, const T* __restric
 }
 // out[b][n,k] = src[n,k] - sum_{j<b} src[n, lo+j] D[j,k] + yv[n] D[bp,k]; columns (and, if zero_rows, rows)
 // of B_i are set to exactly zero.  CTA = 16 rows x all columns of one excitation.
-template <class T>
+template <class T, int CMAX>
 __global__ void __launch_bounds__(256)
 rank_update_kernel(int64_t rows, int nU, int bp, const T* __restrict__ src, const T* __restrict__ yv,
                    const T* __restrict__ Dcat, const int32_t* __restrict__ ue_ptr, int i0, int zero_rows,
                    T* __restrict__ out, int64_t out_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int RT = Sc<T>::is_complex ? 8 : 16, CMAX = 4;   // nU <= 1024
+  constexpr int RT = Sc<T>::is_complex ? 8 : 16;             // CMAX = ceil(nU / 256) <= 4
   T* Ds = reinterpret_cast<T*>(smem_raw);   // [(bp+1)][nU]
   T* As = Ds + (int64_t)(bp + 1) * nU;      // [RT][bp+1]
   const int tid = threadIdx.x;
-  const int i = i0 + blockIdx.y;
+  const int i = i0 + blockIdx.x;      // excitation fastest: the 32 CTAs that share a row tile of src run together
   const int lo = ue_ptr[i], b = ue_ptr[i + 1] - lo;
-  const int64_t n0 = (int64_t)blockIdx.x * RT;
-  const T* D = Dcat + (int64_t)blockIdx.y * (bp + 1) * nU;
+  const int64_t n0 = (int64_t)blockIdx.y * RT;
+  const T* D = Dcat + (int64_t)blockIdx.x * (bp + 1) * nU;
   for (int t = tid; t < (bp + 1) * nU; t += 256) Ds[t] = D[t];
   for (int t = tid; t < RT * (bp + 1); t += 256) {
     const int r = t / (bp + 1), j = t - r * (bp + 1);
@@ -377,7 +377,7 @@ rank_update_kernel(int64_t rows, int nU, int bp, const T* __restrict__ src, cons
       for (int c = 0; c < CMAX; ++c) acc[r][c] = sub(acc[r][c], mul(a, dv[c]));
     }
   }
-  T* o = out + (int64_t)blockIdx.y * out_stride;
+  T* o = out + (int64_t)blockIdx.x * out_stride;
 #pragma unroll
   for (int c = 0; c < CMAX; ++c) {
     const int k = tid + 256 * c;

@@ -399,7 +399,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
       // Lsub_k = B_k Linv_k^T ; A_{k+1} -= Lsub_k Lsub_k^T
       gemm<T>(st, 0, 1, nn, nk, nk, one, Bs + h.offS[k], nk, 0, Lik, nk, 0, zero, Lsub + h.offS[k], nk, 0);
       gemm<T>(st, 0, 1, nn, nn, nk, mone, Lsub + h.offS[k], nk, 0, Lsub + h.offS[k], nk, 0, one, Ad + h.offD[k + 1],
-              nn, 0);
+              nn, 0, 1, /*lower_only=*/1);
     }
   }
   // backward sweep: X_k = Linv_k^T (Z_k - Lsub_k^T X_{k+1}); selected inverse blocks
@@ -559,12 +559,12 @@ int launch_woodbury_patch(ceit_plan* p, const double* g0e, const double* Xh, con
   node_consts_kernel<<<dim3(cdiv(h.nU, 128), nbatch), 128, 0, st>>>((int)h.nU, h.N, h.N0, phi0, p->d_wk, consts);
   CEIT_COUNT_LAUNCH();
   CUDA_TRY(cudaFuncSetAttribute(woodbury_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-  dim3 grid(p->n_patches, nbatch);
+  dim3 grid((unsigned)((int64_t)p->n_patches * nbatch));
   woodbury_patch_kernel<<<grid, WBP_WARPS * 32, psm, st>>>(e_from, e_to, (int)h.L, (int)h.nU, (int)woodbury_pitch(h.nU),
                                                           h.N, h.N0, p->d_patch_eptr, p->d_patch_elems, p->d_patch_nptr,
                                                           p->d_patch_nodes, p->d_patch_local, p->d_area, g0e, Xh, Yh,
                                                           phi0, p->d_ue_ptr, consts, i0, s_coef, J, ldJ,
-                                                          (int)h.patch_node_cap);
+                                                          (int)h.patch_node_cap, nbatch);
   CEIT_COUNT_LAUNCH();
   return 0;
 }
@@ -824,7 +824,7 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
   CEIT_COUNT_LAUNCH();
   if (form == 2) {
     // G = Jt Jt^T + lambda^2 I (m x m);  inv = Jt^T G^-1
-    gemm<double>(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0);
+    gemm<double>(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0, 1, /*lower_only=*/1);
     add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, G, n);
     CEIT_COUNT_LAUNCH();
     potrf_trtri_blocked<double>(st, n, G, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info);
@@ -832,7 +832,7 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
     gemm<double>(st, 1, 0, n_det, m_sel, m_sel, scale_, Jt, n_det, 0, Gi, n, 0, 0.0, inv_out, m_sel, 0);
   } else {
     // A = Jt^T Jt + lambda^2 I (n_det x n_det); inv = Linv^T (Linv Jt^T)
-    gemm<double>(st, 1, 0, n, n, m_sel, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0);
+    gemm<double>(st, 1, 0, n, n, m_sel, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0, 1, /*lower_only=*/1);
     add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, G, n);
     CEIT_COUNT_LAUNCH();
     potrf_trtri_blocked<double>(st, n, G, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info);

@@ -259,7 +259,7 @@ inline void potrf_trtri_blocked(cudaStream_t st, int64_t n, T* A, int64_t lda, i
               L + o2 * ldl + o, ldl, sL, batch);
       // trailing: A[o2:, o2:] -= Lp Lp^T
       gemm<T>(st, 0, 1, mr, mr, bt, mone, L + o2 * ldl + o, ldl, sL, L + o2 * ldl + o, ldl, sL, one,
-              A + o2 * lda + o2, lda, sA, batch);
+              A + o2 * lda + o2, lda, sA, batch, /*lower_only=*/1);
     }
   }
   // Linv row-block s, columns [0, o): Linv[s,0:s] = -Linv_ss * (L[s,0:s] * Linv[0:s,0:s])

@@ -55,8 +55,11 @@ template <int BM, int BN, int WM, int WN, int OPA, int OPB, int STAGES>
 __global__ void __launch_bounds__(WM * WN * 32)
 gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int64_t lda,
                  int64_t sA, const double* __restrict__ B, int64_t ldb, int64_t sB, double beta,
-                 double* __restrict__ C, int64_t ldc, int64_t sC) {
+                 double* __restrict__ C, int64_t ldc, int64_t sC, int lower_only) {
   using SM = DmmaSmem<BM, BN, OPA, OPB>;
+  // symmetric results whose consumers read the lower triangle only (A -= L L^T before a Cholesky):
+  // tiles strictly above the block diagonal are skipped
+  if (lower_only && (int)(blockIdx.x * BN) > (int)(blockIdx.y * BM + BM - 1)) return;
   constexpr int BK = 16, NT = WM * WN * 32;
   constexpr int SA = SM::SA, SB = SM::SB;
   constexpr int TM = BM / WM, TN = BN / WN, MI = TM / 8, NI = TN / 8;
@@ -421,7 +424,7 @@ inline void gemm_simt_launch(cudaStream_t st, int opA, int opB, int64_t M, int64
 template <class T>
 inline void gemm(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, T alpha,
                  const T* A, int64_t lda, int64_t sA, const T* B, int64_t ldb, int64_t sB, T beta,
-                 T* C, int64_t ldc, int64_t sC, int batch = 1);   // specialised for double and cd below
+                 T* C, int64_t ldc, int64_t sC, int batch = 1, int lower_only = 0);   // specialised below
 
 template <int BM, int BN, int WM, int WN, int STAGES>
 inline void gemm_zdmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, cd alpha,
@@ -452,7 +455,7 @@ inline void gemm_zdmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int6
 template <>
 inline void gemm<cd>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, cd alpha, const cd* A,
                      int64_t lda, int64_t sA, const cd* B, int64_t ldb, int64_t sB, cd beta, cd* C, int64_t ldc,
-                     int64_t sC, int batch) {
+                     int64_t sC, int batch, int /*lower_only: full result for complex*/) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
   if (g_force_simt) {
     gemm_simt_launch<cd>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
@@ -470,7 +473,7 @@ inline void gemm<cd>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, in
 template <int BM, int BN, int WM, int WN, int STAGES>
 inline void gemm_dmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha,
                              const double* A, int64_t lda, int64_t sA, const double* B, int64_t ldb, int64_t sB,
-                             double beta, double* C, int64_t ldc, int64_t sC, int batch) {
+                             double beta, double* C, int64_t ldc, int64_t sC, int batch, int lower_only) {
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch), block(WM * WN * 32);
 #define CEIT_DMMA_CASE(a, b)                                                                              \
   {                                                                                                       \
@@ -482,7 +485,8 @@ inline void gemm_dmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int64
       attr_done = true;                                                                                   \
     }                                                                                                     \
     gemm_dmma_kernel<BM, BN, WM, WN, a, b, STAGES><<<grid, block, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, \
-                                                                             sA, B, ldb, sB, beta, C, ldc, sC);     \
+                                                                             sA, B, ldb, sB, beta, C, ldc, sC,      \
+                                                                             lower_only);                           \
   }
   if (opA == 0 && opB == 0) CEIT_DMMA_CASE(0, 0)
   else if (opA == 0 && opB == 1) CEIT_DMMA_CASE(0, 1)
@@ -496,7 +500,7 @@ template <>
 inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K,
                          double alpha, const double* A, int64_t lda, int64_t sA, const double* B,
                          int64_t ldb, int64_t sB, double beta, double* C, int64_t ldc, int64_t sC,
-                         int batch) {
+                         int batch, int lower_only) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
   if (g_force_simt) {
     gemm_simt_launch<double>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
@@ -504,13 +508,18 @@ inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N
   }
   auto ctas = [&](int64_t bm, int64_t bn) { return ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch; };
   int cfg = g_gemm_tile;                       // 0 = auto, 1 = 32x32, 2 = 64x64, 3 = 128x128
-  if (cfg == 0) cfg = (ctas(128, 128) >= 148) ? 3 : (ctas(64, 64) >= 120 ? 2 : 1);
+  // measured on B200 (tools/time_gemm.py): the 64x64 tile (2 CTAs/SM) beats 128x128 (1 CTA/SM) at every size
+  // of this path (28.7 vs 25.3 TFLOP/s on the inverse-model GEMM); 32x32 when 64x64 cannot fill the chip
+  if (cfg == 0) cfg = (ctas(64, 64) >= 120) ? 2 : 1;
   if (cfg == 3)
-    gemm_dmma_launch<128, 128, 2, 4, 3>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+    gemm_dmma_launch<128, 128, 2, 4, 3>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
+                                        lower_only);
   else if (cfg == 2)
-    gemm_dmma_launch<64, 64, 2, 2, 4>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+    gemm_dmma_launch<64, 64, 2, 2, 4>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
+                                      lower_only);
   else
-    gemm_dmma_launch<32, 32, 2, 2, 4>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
+    gemm_dmma_launch<32, 32, 2, 2, 4>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
+                                      lower_only);
 }
 
 }  // namespace ceit

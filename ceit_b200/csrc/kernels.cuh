@@ -647,7 +647,7 @@ constexpr int WBP_WARPS = 8;
 
 __device__ long long g_wb_clk[8];
 #ifdef CEIT_TILE_CLOCKS
-#define WB_CLK(q) do { if (threadIdx.x == 0 && blockIdx.x == 5 && blockIdx.y == 1) g_wb_clk[q] = clock64(); } while (0)
+#define WB_CLK(q) do { if (threadIdx.x == 0 && blockIdx.x == 81) g_wb_clk[q] = clock64(); } while (0)
 #else
 #define WB_CLK(q) do { } while (0)
 #endif
@@ -725,11 +725,12 @@ woodbury_patch_kernel(int e_from, int e_to, int L, int nU, int pitch, int64_t N,
                       const double* __restrict__ g0e, const double* __restrict__ Xh,
                       const double* __restrict__ Yh, const double* __restrict__ phi0,
                       const int32_t* __restrict__ ue_ptr, const double4* __restrict__ node_consts, int i0,
-                      double s_coef, double* __restrict__ J, int64_t ldJ, int cap) {
+                      double s_coef, double* __restrict__ J, int64_t ldJ, int cap, int nbatch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = WBP_WARPS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int patch = blockIdx.x, b = blockIdx.y;
+  // excitation fastest: the CTAs that share a patch (same Xh rows) are scheduled together
+  const int b = blockIdx.x % nbatch, patch = blockIdx.x / nbatch;
   const int i = i0 + b;
   const int n_beg = patch_nptr[patch], nn = patch_nptr[patch + 1] - n_beg;
   const int el_beg = patch_eptr[patch], ne = patch_eptr[patch + 1] - el_beg;

@@ -509,14 +509,14 @@ inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N
   auto ctas = [&](int64_t bm, int64_t bn) { return ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch; };
   int cfg = g_gemm_tile;                       // 0 = auto, 1 = 32x32, 2 = 64x64, 3 = 128x128
   // measured on B200 (tools/time_gemm.py): the 64x64 tile (2 CTAs/SM) beats 128x128 (1 CTA/SM) at every size
-  // of this path (28.7 vs 25.3 TFLOP/s on the inverse-model GEMM); 32x32 when 64x64 cannot fill the chip
+  // of this path (30.3 vs 25.3 TFLOP/s on the inverse-model GEMM, cuBLAS 34.9); 32x32 when 64x64 cannot fill the chip
   if (cfg == 0) cfg = (ctas(64, 64) >= 120) ? 2 : 1;
   if (cfg == 3)
     gemm_dmma_launch<128, 128, 2, 4, 3>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
                                         lower_only);
   else if (cfg == 2)
-    gemm_dmma_launch<64, 64, 2, 2, 4>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
-                                      lower_only);
+    gemm_dmma_launch<64, 64, 2, 2, 3>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
+                                      lower_only);   // 3 stages = 60 KB: 3 CTAs/SM
   else
     gemm_dmma_launch<32, 32, 2, 2, 4>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
                                       lower_only);

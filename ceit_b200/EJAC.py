@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from .EFEM import EFEM
 from .models.mesh import MeshObj
-from .util.utilities import get_config
+from .util.utilities import get_config, save_npy
 
 
 class EJAC(object):
@@ -34,7 +34,12 @@ class EJAC(object):
         self.pattern_num = self.electrode_num * (self.electrode_num - 1)
         self.elem_num = self.fwd_FEM.elem_num
         self.electrode_original_potential = np.zeros((self.pattern_num))
-        self.JAC_matrix = np.zeros((self.pattern_num, self.elem_num))
+        # JAC_matrix lives in pinned host memory (a numpy view of a pinned tensor) so that the device <-> host
+        # copies of the 240 x E matrix run at PCIe speed; it is an ordinary ndarray to callers
+        import torch
+        self._J_pinned = torch.zeros((self.pattern_num, self.elem_num), dtype=torch.float64, pin_memory=True)
+        self.JAC_matrix = self._J_pinned.numpy()
+        self._inv_pinned = None
         if self.mode == 'n':
             self.fwd_FEM.reset_variable(overall_variable=self.overall_variable)
         else:
@@ -54,8 +59,16 @@ class EJAC(object):
     def _upload_J(self):
         t = self._eng.torch
         J = self._device_J()
-        J.copy_(t.from_numpy(np.ascontiguousarray(self.JAC_matrix, dtype=np.float64)))
+        if not self._J_is_pinned():
+            # the user replaced JAC_matrix (read_JAC_np, assignment): stage it through the pinned buffer
+            self._J_pinned.numpy()[...] = np.asarray(self.JAC_matrix, dtype=np.float64)
+        J.copy_(self._J_pinned, non_blocking=True)
         return J
+
+    def _J_is_pinned(self):
+        Jm = self.JAC_matrix
+        return (isinstance(Jm, np.ndarray) and Jm.shape == tuple(self._J_pinned.shape) and Jm.dtype == np.float64
+                and Jm.ctypes.data == self._J_pinned.data_ptr())
 
     def calc_origin_potential(self):
         """Unperturbed electrode amplitudes for every excitation (EJAC.py:87-98)."""
@@ -83,13 +96,16 @@ class EJAC(object):
             e_from = 0 if e_from is None else e_from
             e_to = self.elem_num if e_to is None else e_to
             if i_to > i_from:
-                if self.fwd_FEM._sync_material():
-                    self._eng.check_numeric()
+                self.fwd_FEM._sync_material()
                 J = self._device_J()
                 self._eng.plan.jacobian_block(i_from, i_to, e_from, e_to, variable_change, self.fwd_FEM.freq,
                                               J, self.elem_num)
                 r0, r1 = i_from * (L - 1), i_to * (L - 1)
-                self.JAC_matrix[r0:r1, e_from:e_to] = J[r0:r1, e_from:e_to].cpu().numpy()
+                if self._J_is_pinned() and e_from == 0 and e_to == self.elem_num:
+                    self._J_pinned[r0:r1].copy_(J[r0:r1], non_blocking=True)       # D2H into the pinned matrix
+                    self._eng.torch.cuda.current_stream().synchronize()
+                else:
+                    self.JAC_matrix[r0:r1, e_from:e_to] = J[r0:r1, e_from:e_to].cpu().numpy()
                 self._eng.check_numeric()
             self.save_JAC_np()
             return self.JAC_matrix
@@ -154,8 +170,13 @@ class EJAC(object):
 
     def save_inv_matrix(self, lmbda=203):
         """EJAC.py:231-243."""
-        JAC_inv = self._inv_model(lmbda, 1.0).cpu().numpy()
-        np.save(self.config["rootdir"] + "/" + self.config["folder_name"] + '/inv_mat.npy', JAC_inv)
+        inv = self._inv_model(lmbda, 1.0)
+        t = self._eng.torch
+        if self._inv_pinned is None or tuple(self._inv_pinned.shape) != tuple(inv.shape):
+            self._inv_pinned = t.empty(tuple(inv.shape), dtype=t.float64, pin_memory=True)
+        self._inv_pinned.copy_(inv, non_blocking=True)
+        t.cuda.current_stream().synchronize()
+        save_npy(self.config["rootdir"] + "/" + self.config["folder_name"] + '/inv_mat.npy', self._inv_pinned.numpy())
 
     def read_inv_matrix(self):
         return np.load(self.config["rootdir"] + "/" + self.config["folder_name"] + '/inv_mat.npy')
@@ -169,7 +190,7 @@ class EJAC(object):
 
     # -- persistence (EJAC.py:261-294) ------------------------------------------------------------------
     def save_JAC_np(self):
-        np.save(self.config["rootdir"] + "/" + self.config["folder_name"] + '/JAC_cache.npy', self.JAC_matrix)
+        save_npy(self.config["rootdir"] + "/" + self.config["folder_name"] + '/JAC_cache.npy', self.JAC_matrix)
 
     def read_JAC_np(self):
         self.JAC_matrix = np.load(self.config["rootdir"] + "/" + self.config["folder_name"] + '/JAC_cache.npy')

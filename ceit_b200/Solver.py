@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from .models.mesh import MeshObj
 from .readmesh import read_mesh_from_csv
-from .util.utilities import get_config
+from .util.utilities import get_config, save_npy
 
 
 class Solver(object):
@@ -83,7 +83,7 @@ class Solver(object):
         det = t.from_numpy(np.ascontiguousarray(self.mesh.detection_index, dtype=np.int64)).to(self._dev)
         self._inv_dev = _lib.inverse_model(J, det, lmbda, shift=1.0, form=form)
         self.inv_mat = self._inv_dev.cpu().numpy()
-        np.save(self._path('inv_mat.npy'), self.inv_mat)
+        save_npy(self._path('inv_mat.npy'), self.inv_mat)
 
     def adaptive_solver(self, delta_V):
         """NOT COMPLETED in the reference either (Solver.py:126-130)."""

@@ -68,3 +68,25 @@ def read_parameter(filename, path_name):
     """Read `cache_<filename>.pkl` (utilities.py:62-75)."""
     with open(os.path.join(path_name, "cache_" + filename + ".pkl"), "rb") as file:
         return pickle.load(file)
+
+
+def save_npy(path, arr):
+    """np.save-compatible writer (format 1.0, same bytes): when the file already exists with exactly the same
+    size it is overwritten in place instead of being truncated and re-allocated (the Jacobian / inverse-model
+    caches are rewritten with identical shapes on every run)."""
+    import io
+    arr = np.ascontiguousarray(arr)
+    hdr = io.BytesIO()
+    np.lib.format.write_array_header_1_0(hdr, np.lib.format.header_data_from_array_1_0(arr))
+    h = hdr.getvalue()
+    try:
+        if os.path.getsize(path) == len(h) + arr.nbytes:
+            with open(path, "r+b") as f:
+                f.write(h)
+                f.write(arr.data)
+            return
+    except OSError:
+        pass
+    with open(path, "wb") as f:
+        f.write(h)
+        f.write(arr.data)

@@ -133,6 +133,7 @@ struct ceit_plan {
   void *Tm = nullptr, *G1 = nullptr;
   void *Mreg = nullptr, *LT = nullptr, *LinvT = nullptr, *Tinv = nullptr, *te = nullptr, *YT = nullptr, *ye = nullptr;
   double* d_gamma = nullptr;
+  void* splitk_ws = nullptr;
   void *TBB = nullptr, *LB = nullptr, *LinvB = nullptr, *Dcat = nullptr;
   int32_t *d_node_at = nullptr, *d_bnd_loc = nullptr, *d_m2_src_ptr = nullptr, *d_m2_src = nullptr;
   int32_t *d_rc_ptr = nullptr, *d_rc_src = nullptr;
@@ -226,7 +227,7 @@ int alloc_numeric(ceit_plan* p) {
   void** bufs[] = {&p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
                    &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->g0e, &p->Aint, &p->Lint,
                    &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1, &p->XP, &p->Mreg, &p->LT,
-                   &p->LinvT, &p->Tinv, &p->te, &p->YT, &p->ye};
+                   &p->LinvT, &p->Tinv, &p->te, &p->YT, &p->ye, &p->splitk_ws};
   for (auto b : bufs) dev_free_tracked(p, *b);
   // excitation workspace depends on the type too
   void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS,
@@ -265,6 +266,7 @@ int alloc_numeric(ceit_plan* p) {
   if ((rc = dev_alloc(p, &p->YT, h.N * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->ye, h.N * es))) return rc;
   if (!p->d_gamma && (rc = dev_alloc(p, (void**)&p->d_gamma, sizeof(double)))) return rc;
+  if ((rc = dev_alloc(p, &p->splitk_ws, (size_t)splitk_slices(h.nU, h.nU, h.N0P) * h.nU * h.nU * sizeof(double)))) return rc;
   if ((rc = dev_alloc(p, &p->KUU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->SU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Ptmp, maxS * es))) return rc;
@@ -310,6 +312,14 @@ int g_direct_excitation = 0;
 inline bool use_rank_update(const ceit_plan* p) {
   const HostPlan& h = p->h;
   return !g_direct_excitation && h.u_contiguous && h.bp <= 64 && h.nU <= 1024 && h.nU > h.bp;
+}
+
+inline void schur_u_gemm(ceit_plan* p, cudaStream_t st, int64_t nU, int64_t N0P, const double* K0U, const double* X,
+                         double* SU) {
+  gemm_splitk(st, 1, 0, nU, nU, N0P, -1.0, K0U, nU, X, nU, 1.0, SU, nU, (double*)p->splitk_ws);
+}
+inline void schur_u_gemm(ceit_plan*, cudaStream_t st, int64_t nU, int64_t N0P, const cd* K0U, const cd* X, cd* SU) {
+  gemm<cd>(st, 1, 0, nU, nU, N0P, neg(Sc<cd>::one()), K0U, nU, 0, X, nU, 0, Sc<cd>::one(), SU, nU, 0);
 }
 
 // ---- base stage -----------------------------------------------------------------------------------
@@ -434,8 +444,8 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
     CUDA_TRY(cudaMemcpyAsync(SigPP, Ainv, h.szPP * es, cudaMemcpyDeviceToDevice, st));
     gemm<T>(st, 0, 1, nI, nI, bmax, mone, Vneg, bmax, sV, Wn, bmax, sV, one, SigPP, nI, sPP, (int)P);    // + V W^T
   }
-  // S_U = K_UU - K_0U^T X
-  gemm<T>(st, 1, 0, nU, nU, N0P, mone, K0U, nU, 0, Xh, nU, 0, one, SU, nU, 0);
+  // S_U = K_UU - K_0U^T X  (small output, long inner dimension: split-K on the real path)
+  schur_u_gemm(p, st, nU, N0P, K0U, Xh, SU);
   compact_rows_kernel<T><<<cdiv(h.N0, 8), 256, 0, st>>>(h.N0, (int)nU, p->d_row_map, Xh, Xc);
   CEIT_COUNT_LAUNCH();
   fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, st>>>((int)nU, Xc + h.N0 * nU);
@@ -824,7 +834,14 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
   CEIT_COUNT_LAUNCH();
   if (form == 2) {
     // G = Jt Jt^T + lambda^2 I (m x m);  inv = Jt^T G^-1
-    gemm<double>(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0, 1, /*lower_only=*/1);
+    {
+      const int S = splitk_slices(n, n, n_det);
+      double* ws = nullptr;
+      if (S > 1) CUDA_TRY(cudaMallocAsync((void**)&ws, (size_t)S * n * n * sizeof(double), st));
+      if (S > 1) gemm_splitk(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, Jt, n_det, 0.0, G, n, ws);
+      else gemm<double>(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0, 1, /*lower_only=*/1);
+      if (ws) CUDA_TRY(cudaFreeAsync(ws, st));
+    }
     add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, G, n);
     CEIT_COUNT_LAUNCH();
     potrf_trtri_blocked<double>(st, n, G, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info);

@@ -522,4 +522,54 @@ inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N
                                       lower_only);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Split-K for small outputs with a long inner dimension (S_U = K_UU - K_0U^T X, G = Jt Jt^T): the K range
+// is cut into `S` slices that run as one strided batch into partial results, then summed in fixed order.
+// ------------------------------------------------------------------------------------------------
+__global__ void splitk_reduce_kernel(int64_t n, int S, const double* __restrict__ P, double beta, double* __restrict__ C,
+                                     int64_t M, int64_t N, int64_t ldc) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  double acc = 0.0;
+  for (int s = 0; s < S; ++s) acc += P[(int64_t)s * n + q];
+  const int64_t r = q / N, c = q - r * N;
+  double* p = C + r * ldc + c;
+  *p = (beta != 0.0) ? fma(beta, *p, acc) : acc;
+}
+
+inline int splitk_slices(int64_t M, int64_t N, int64_t K) {
+  const int64_t tiles = ((M + 31) / 32) * ((N + 31) / 32);
+  if (K < 1024 || tiles >= 296) return 1;
+  int64_t S = (592 + tiles - 1) / tiles;              // aim at ~4 CTAs per SM
+  const int64_t maxS = K / 256;                       // keep slices >= 256 deep
+  if (S > maxS) S = maxS;
+  if (S > 64) S = 64;
+  return (int)(S < 2 ? 1 : S);
+}
+
+// workspace: at least splitk_slices(M, N, K) * M * N doubles (ignored when no split is used)
+inline void gemm_splitk(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+                        int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+                        double* workspace) {
+  const int S = workspace ? splitk_slices(M, N, K) : 1;
+  if (S <= 1) {
+    gemm<double>(st, opA, opB, M, N, K, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0);
+    return;
+  }
+  int64_t Ks = ((K + S - 1) / S + 15) / 16 * 16;
+  const int full = (int)(K / Ks);                     // slices of exactly Ks
+  const int64_t rem = K - (int64_t)full * Ks;
+  const int64_t sA = (opA == 0) ? Ks : Ks * lda, sB = (opB == 0) ? Ks * ldb : Ks;
+  if (full > 0) gemm<double>(st, opA, opB, M, N, Ks, alpha, A, lda, sA, B, ldb, sB, 0.0, workspace, N, M * N, full);
+  int parts = full;
+  if (rem > 0) {
+    gemm<double>(st, opA, opB, M, N, rem, alpha, A + (int64_t)full * sA, lda, 0, B + (int64_t)full * sB, ldb, 0, 0.0,
+                 workspace + (int64_t)full * M * N, N, 0, 1);
+    ++parts;
+  }
+  splitk_reduce_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(M * N, parts, workspace, beta, C, M, N, ldc);
+  CEIT_COUNT_LAUNCH();
+}
+
 }  // namespace ceit

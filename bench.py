@@ -251,14 +251,21 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    step()                                 # first call allocates the library workspaces (not capturable)
+    barrier()
+    # the ~130 short dependent kernels of a step are replayed from ONE CUDA graph (no launch gaps);
+    # --no-graph launches them on the stream one by one
+    use_graph = not args.no_graph and (ws == 1 or args.graph_multi)
+    run_step = step
+    if use_graph:
+        graph = _lib.StepGraph(step)
+        run_step = graph.replay
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
-        step()
+        run_step()
     barrier()
     if plan.numeric_flag() != 0:
         raise SystemExit("numeric failure in the factorisation")
-    _lib.set_option("stage_timers", 1)
-    _lib.stage_times()
     launches0 = _lib.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -267,15 +274,24 @@ def run_gpu(args):
     for k in range(args.steps):
         flush.zero_()                      # L2 flush between timed iterations (outside the event pair)
         ev[k][0].record()
-        step()
+        run_step()
         ev[k][1].record()
     barrier()
     wall = time.perf_counter() - wall0
     ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    # second pass over the same K steps with CUDA events around every stage inside the library (stream
+    # launches of the same kernels: event records are not part of the captured graph): stage breakdown and
+    # the duration of the roofline kernel
+    _lib.set_option("stage_timers", 1)
+    _lib.stage_times()
+    for k in range(args.steps):
+        flush.zero_()
+        step()
+    barrier()
     stages = _lib.stage_times()
     _lib.set_option("stage_timers", 0)
-    clocks = sampler.stop() if sampler else None
     if ws > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -407,14 +423,16 @@ def run_gpu(args):
             ach = bytes_per_col * cols_per_launch / (per_launch_ms * 1e-3) / 1e9
             traffic, traffic_src = None, None
             try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))["woodbury_patch_kernel"]
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))["woodbury_lr_kernel"]
                 if ws == 1 and is_headline:          # the capture is of the full 16 x 5000 launch
                     traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
             except Exception:
                 pass
-            k2 = {"kernel": "woodbury_patch_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+            k2 = {"kernel": "woodbury_lr_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
                   "frac": ach / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
                   "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": bytes_per_col * cols_per_launch,
+                  "timing": "CUDA events around the launch, second pass over the same K steps (stream launches; "
+                            "the timed region replays the same kernels from a CUDA graph)",
                   "note": "algorithmic bytes = (8 r + 96 + 8 (L-1)) per column (SURVEY.md 8d); at this size Yh is "
                           "largely L2-resident, the kernel is shared-memory/FP64-issue bound (profiles/)"}
         stage_ms = {k: v[0] / args.steps for k, v in stages.items() if v[1]}
@@ -450,7 +468,8 @@ def run_gpu(args):
                        "N": N, "E": E, "L": L, "columns_per_step": n_cols, "l2": "flushed between timed steps (256 MiB memset)",
                        "sharding": f"excitation blocks over {ws} rank(s), all-gather J (NCCL), inverse model sharded "
                                    f"over detection elements (one all-reduce of the m x m Gram matrix)"},
-            "gpu_launches": int(launches), "wall_s_timed_region": wall,
+            "gpu_launches": int(launches), "launch_mode": "cuda_graph" if use_graph else "stream",
+            "wall_s_timed_region": wall,
             "clocks": clocks, "e2e": e2e, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu,
             "realtime": realtime,
         }))
@@ -466,6 +485,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--graph-multi", action="store_true", help="also capture the N>1 step (with its NCCL collectives) into a graph")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--config", default="50_50", choices=sorted(CONFIGS), help="workload (default: the headline MESH_50_50)")
     args = ap.parse_args()
     if args.impl == "reference":

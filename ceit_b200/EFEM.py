@@ -41,7 +41,9 @@ class EFEM(FEMBasic):
             raise IndexError("list index out of range")      # electrode_list[electrode_input], EFEM.py:81
         if self._sync_material():
             self._engine.check_numeric()
-        self._engine.plan.forward(electrode_input, self._d_node, self._d_elem, self._d_elec)
+        self._engine.graphed(("fwd", int(electrode_input), self._d_node.data_ptr()),
+                             lambda: self._engine.plan.forward(electrode_input, self._d_node, self._d_elem,
+                                                               self._d_elec))
         nb = len(np.unique(self.mesh.elem[np.asarray(self.mesh.electrode_mesh[electrode_input])].reshape(-1)))
         self.node_num_bound = nb
         self.node_num_f = self.node_num - nb

@@ -47,6 +47,8 @@ class EJAC(object):
         self.initial_variable = np.copy(self.fwd_FEM.elem_variable)
         self._eng = self.fwd_FEM._engine
         self._J_dev = None
+        self._base_dev = None
+        self._det_dev = None
         self.calc_origin_potential()
 
     # -- device helpers -----------------------------------------------------------------------------
@@ -75,9 +77,11 @@ class EJAC(object):
         t = self._eng.torch
         if self.fwd_FEM._sync_material():
             self._eng.check_numeric()
-        base = t.zeros(self.pattern_num, dtype=t.float64, device=self._eng.dev)
-        L = self.electrode_num
-        self._eng.plan.jacobian_block(0, L, 0, 0, 0.0, self.fwd_FEM.freq, None, self.elem_num, base)
+        if self._base_dev is None:
+            self._base_dev = t.zeros(self.pattern_num, dtype=t.float64, device=self._eng.dev)
+        base, L, freq = self._base_dev, self.electrode_num, self.fwd_FEM.freq
+        self._eng.graphed(("base", float(freq), base.data_ptr()),
+                          lambda: self._eng.plan.jacobian_block(0, L, 0, 0, 0.0, freq, None, self.elem_num, base))
         self.electrode_original_potential = base.cpu().numpy()
 
     def JAC_calculation(self, e_from=None, e_to=None):
@@ -98,8 +102,10 @@ class EJAC(object):
             if i_to > i_from:
                 self.fwd_FEM._sync_material()
                 J = self._device_J()
-                self._eng.plan.jacobian_block(i_from, i_to, e_from, e_to, variable_change, self.fwd_FEM.freq,
-                                              J, self.elem_num)
+                freq, E = self.fwd_FEM.freq, self.elem_num
+                self._eng.graphed(
+                    ("jac", i_from, i_to, e_from, e_to, float(variable_change), float(freq), J.data_ptr()),
+                    lambda: self._eng.plan.jacobian_block(i_from, i_to, e_from, e_to, variable_change, freq, J, E))
                 r0, r1 = i_from * (L - 1), i_to * (L - 1)
                 if self._J_is_pinned() and e_from == 0 and e_to == self.elem_num:
                     self._J_pinned[r0:r1].copy_(J[r0:r1], non_blocking=True)       # D2H into the pinned matrix
@@ -121,9 +127,16 @@ class EJAC(object):
     def _inv_model(self, lmbda, shift, rows=None, scale=1.0):
         t = self._eng.torch
         J = self._upload_J()
-        det = t.from_numpy(np.ascontiguousarray(self.fwd_FEM.mesh.detection_index, dtype=np.int64)).to(self._eng.dev)
-        rows_d = None if rows is None else t.tensor(rows, dtype=t.int64, device=self._eng.dev)
-        return _lib.inverse_model(J, det, lmbda, rows=rows_d, shift=shift, scale=scale)
+        det_h = np.ascontiguousarray(self.fwd_FEM.mesh.detection_index, dtype=np.int64)
+        if self._det_dev is None or self._det_dev[0].shape != det_h.shape or not np.array_equal(self._det_dev[0], det_h):
+            self._det_dev = (det_h.copy(), t.from_numpy(det_h).to(self._eng.dev))
+        det = self._det_dev[1]
+        if rows is not None:
+            rows_d = t.tensor(rows, dtype=t.int64, device=self._eng.dev)
+            return _lib.inverse_model(J, det, lmbda, rows=rows_d, shift=shift, scale=scale)
+        # the result lives in the graph's memory pool: valid until the same model is computed again
+        return self._eng.graphed(("inv", float(lmbda), float(shift), float(scale), J.data_ptr(), det.data_ptr()),
+                                 lambda: _lib.inverse_model(J, det, lmbda, shift=shift, scale=scale))
 
     def _apply(self, inv, delta_V):
         t = self._eng.torch

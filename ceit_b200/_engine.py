@@ -22,6 +22,9 @@ class Engine:
         self._factored = None        # None | False (real) | True (complex)
         self.perm_d = torch.empty(self.E, dtype=torch.float64, device=self.dev)
         self.var_d = torch.empty(self.E, dtype=torch.float64, device=self.dev)
+        # CUDA graphs of library-call sequences on static buffers, keyed by their frozen scalar arguments
+        self.use_graphs = True
+        self._graphs = {}
 
     @staticmethod
     def for_mesh(mesh):
@@ -30,6 +33,24 @@ class Engine:
             eng = Engine(mesh)
             mesh._ceit_engine = eng
         return eng
+
+    MAX_GRAPHS = 16
+
+    def graphed(self, key, fn):
+        """Run `fn` (library calls on buffers owned by this engine / its users, all arguments determined by
+        `key`).  The first call per key runs eagerly (workspace allocation), the second is captured into a
+        CUDA graph, later ones replay it: no launch gaps between the ~100 short kernels of a step."""
+        if not self.use_graphs or _lib._options.get("stage_timers", 0):
+            return fn()
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self.MAX_GRAPHS:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = "warm"
+            return fn()
+        if ent == "warm":
+            ent = self._graphs[key] = _lib.StepGraph(fn)
+        return ent.replay()
 
     def set_material(self, perm, var, omega):
         """Upload perm / var if they changed; (re)assemble + factor when needed.
@@ -44,9 +65,12 @@ class Engine:
         self.perm_d.copy_(torch.from_numpy(perm))
         self.var_d.copy_(torch.from_numpy(var))
         self._perm_host, self._var_host, self._omega = perm.copy(), var.copy(), omega
-        self.plan.assemble(self.perm_d, self.var_d, omega)
         is_complex = bool(np.any(var != 0.0))
-        self.plan.factor(is_complex)
+
+        def factor():
+            self.plan.assemble(self.perm_d, self.var_d, omega)
+            self.plan.factor(is_complex)
+        self.graphed(("factor", float(omega), is_complex), factor)
         self._factored = is_complex
         return True
 

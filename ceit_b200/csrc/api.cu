@@ -49,6 +49,8 @@ namespace {
 constexpr int N_STAGES = 8;
 int g_stage_timers = 0;
 int g_no_patch = 0;
+int g_no_lowrank = 0;
+int g_patch_nodes = 0;   // experiment: override the node cap of the element patches
 int64_t g_nd_interior = 64;   // target nodes per nested-dissection interior; <= 0 disables level 1
 struct StageEv {
   int stage;
@@ -134,6 +136,8 @@ struct ceit_plan {
   void *Mreg = nullptr, *LT = nullptr, *LinvT = nullptr, *Tinv = nullptr, *te = nullptr, *YT = nullptr, *ye = nullptr;
   double* d_gamma = nullptr;
   void* splitk_ws = nullptr;
+  void* g1e = nullptr;
+  void* ZW = nullptr;
   void *TBB = nullptr, *LB = nullptr, *LinvB = nullptr, *Dcat = nullptr;
   int32_t *d_node_at = nullptr, *d_bnd_loc = nullptr, *d_m2_src_ptr = nullptr, *d_m2_src = nullptr;
   int32_t *d_rc_ptr = nullptr, *d_rc_src = nullptr;
@@ -227,11 +231,11 @@ int alloc_numeric(ceit_plan* p) {
   void** bufs[] = {&p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
                    &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->g0e, &p->Aint, &p->Lint,
                    &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1, &p->XP, &p->Mreg, &p->LT,
-                   &p->LinvT, &p->Tinv, &p->te, &p->YT, &p->ye, &p->splitk_ws};
+                   &p->LinvT, &p->Tinv, &p->te, &p->YT, &p->ye, &p->splitk_ws, &p->g1e};
   for (auto b : bufs) dev_free_tracked(p, *b);
   // excitation workspace depends on the type too
   void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS,
-                 &p->TBB, &p->LB, &p->LinvB, &p->Dcat};
+                 &p->TBB, &p->LB, &p->LinvB, &p->Dcat, &p->ZW};
   for (auto b : ex) dev_free_tracked(p, *b);
   p->ex_cap = 0;
   p->alloc_mode = 0;
@@ -266,6 +270,7 @@ int alloc_numeric(ceit_plan* p) {
   if ((rc = dev_alloc(p, &p->YT, h.N * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->ye, h.N * es))) return rc;
   if (!p->d_gamma && (rc = dev_alloc(p, (void**)&p->d_gamma, sizeof(double)))) return rc;
+  if ((rc = dev_alloc(p, &p->g1e, 6 * h.E * es))) return rc;
   if ((rc = dev_alloc(p, &p->splitk_ws, (size_t)splitk_slices(h.nU, h.nU, h.N0P) * h.nU * h.nU * sizeof(double)))) return rc;
   if ((rc = dev_alloc(p, &p->KUU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->SU, h.nU * h.nU * es))) return rc;
@@ -281,7 +286,7 @@ int alloc_excitation_ws(ceit_plan* p, int want_cap) {
   const int want_mode = Sc<T>::is_complex ? 2 : 1;
   if (p->ex_cap >= want_cap && p->ex_mode == want_mode) return 0;
   void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS,
-                 &p->TBB, &p->LB, &p->LinvB, &p->Dcat};
+                 &p->TBB, &p->LB, &p->LinvB, &p->Dcat, &p->ZW};
   for (auto b : ex) dev_free_tracked(p, *b);
   if (p->d_elec) { void* q = p->d_elec; dev_free_tracked(p, q); p->d_elec = nullptr; }
   const HostPlan& h = p->h;
@@ -300,6 +305,7 @@ int alloc_excitation_ws(ceit_plan* p, int want_cap) {
   if ((rc = dev_alloc(p, &p->LB, c * (int64_t)h.bp * h.bp * es))) return rc;
   if ((rc = dev_alloc(p, &p->LinvB, c * (int64_t)h.bp * h.bp * es))) return rc;
   if ((rc = dev_alloc(p, &p->Dcat, c * (int64_t)(h.bp + 1) * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->ZW, c * h.N * (int64_t)(h.bp + 1) * es))) return rc;
   if ((rc = dev_alloc(p, (void**)&p->d_elec, c * h.L * sizeof(double)))) return rc;
   p->ex_cap = want_cap;
   p->ex_mode = want_mode;
@@ -313,6 +319,14 @@ inline bool use_rank_update(const ceit_plan* p) {
   const HostPlan& h = p->h;
   return !g_direct_excitation && h.u_contiguous && h.bp <= 64 && h.nU <= 1024 && h.nU > h.bp;
 }
+
+// excitation-independent part of the element blocks for the low-rank Woodbury kernel (real path only)
+inline void launch_g1(ceit_plan* p, const double* g0e, const double* YT, const double* Xh, cudaStream_t st) {
+  const HostPlan& h = p->h;
+  g1_kernel<<<cdiv(h.E, 8), 256, 0, st>>>(h.E, (int)h.nU, p->d_elem_pos, g0e, YT, Xh, (double*)p->g1e);
+  CEIT_COUNT_LAUNCH();
+}
+inline void launch_g1(ceit_plan*, const cd*, const cd*, const cd*, cudaStream_t) {}
 
 inline void schur_u_gemm(ceit_plan* p, cudaStream_t st, int64_t nU, int64_t N0P, const double* K0U, const double* X,
                          double* SU) {
@@ -469,6 +483,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
     gemm<T>(st, 0, 0, h.N, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);
     rowsum_e_kernel<T><<<cdiv(h.N, 8), 256, 0, st>>>(h.N, (int)nU, YT, ye);
     CEIT_COUNT_LAUNCH();
+    launch_g1(p, g0e, YT, Xc, st);
   }
   KERNEL_CHECK();
   p->mode = Sc<T>::is_complex ? 2 : 1;
@@ -523,6 +538,10 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
     };
     update(nU, Tinv, te, 1, Sinv, u2);
     update(N, YT, ye, 0, Yh, N * nU);
+    // ZW_i = Xh Dcat_i^T (N x (bp+1)): the rank-(b+1) correction of the element blocks (woodbury_lr_kernel)
+    // all excitations of the chunk in one product: Dcat is a (nbatch (bp+1)) x nU matrix
+    gemm<T>(st, 0, 1, N, (int64_t)nbatch * (bp + 1), nU, one, Xh, nU, 0, Dcat, nU, 0, zero, (T*)p->ZW,
+            (int64_t)nbatch * (bp + 1), 0, 1);
   } else {
   dim3 g2(cdiv(u2, 256), nbatch);
   build_stilde_kernel<T><<<g2, 256, 0, st>>>((int)nU, SU, p->d_inB, i0, St);
@@ -578,6 +597,28 @@ int launch_woodbury_patch(ceit_plan* p, const double* g0e, const double* Xh, con
   CEIT_COUNT_LAUNCH();
   return 0;
 }
+inline size_t woodbury_lr_smem(int64_t nU, int64_t cap, int64_t bp) {
+  return (size_t)(nU * 32 + cap * woodbury_pitch(nU) * 8 + cap * bp * 8 + cap * (bp + 1) * 8 + 2 * cap * 8 + 6 * 32 * 8 + 64);
+}
+int launch_woodbury_lr(ceit_plan* p, int e_from, int e_to, int nbatch, int i0, double s_coef, double* J, int64_t ldJ,
+                       cudaStream_t st) {
+  const HostPlan& h = p->h;
+  const size_t psm = woodbury_lr_smem(h.nU, h.patch_node_cap, h.bp);
+  double4* consts = (double4*)p->tmpS;
+  node_consts_kernel<<<dim3(cdiv(h.nU, 128), nbatch), 128, 0, st>>>((int)h.nU, h.N, h.N0, (const double*)p->phi0, p->d_wk,
+                                                                   consts);
+  CEIT_COUNT_LAUNCH();
+  CUDA_TRY(cudaFuncSetAttribute(woodbury_lr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+  dim3 grid((unsigned)((int64_t)p->n_patches * nbatch));
+  woodbury_lr_kernel<<<grid, WBP_WARPS * 32, psm, st>>>(
+      e_from, e_to, (int)h.L, (int)h.nU, (int)woodbury_pitch(h.nU), (int)h.bp, h.N, h.N0, p->d_patch_eptr, p->d_patch_elems,
+      p->d_patch_nptr, p->d_patch_nodes, p->d_patch_local, p->d_area, (const double*)p->g1e, (const double*)p->YT,
+      (const double*)p->ye, (const double*)p->ZW, (const double*)p->Yh, (const double*)p->phi0, p->d_ue_ptr, consts, i0,
+      s_coef, J, ldJ, (int)h.patch_node_cap, nbatch);
+  CEIT_COUNT_LAUNCH();
+  return 0;
+}
+
 int launch_woodbury_patch(ceit_plan*, const cd*, const cd*, const cd*, const cd*, int, int, int, int, double, double*,
                           int64_t, cudaStream_t) {
   return CEIT_ERR_STATE;   // the patch kernel is the real-base path; complex uses woodbury_kernel<cd>
@@ -609,8 +650,11 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
     const bool use_patch = !g_no_patch && !Sc<T>::is_complex && h.patch_node_cap >= 12 && h.u_contiguous;
     if (e_to > e_from && J && use_patch) {
       StageScope sc(3, st);
-      rc = launch_woodbury_patch(p, (const T*)p->g0e, (const T*)p->Xh, (const T*)p->Yh, (const T*)p->phi0, (int)e_from,
-                                 (int)e_to, nbatch, (int)i0, 2.0 * omega * c, J, ldJ, st);
+      if (use_rank_update(p) && !g_no_lowrank)
+        rc = launch_woodbury_lr(p, (int)e_from, (int)e_to, nbatch, (int)i0, 2.0 * omega * c, J, ldJ, st);
+      else
+        rc = launch_woodbury_patch(p, (const T*)p->g0e, (const T*)p->Xh, (const T*)p->Yh, (const T*)p->phi0, (int)e_from,
+                                   (int)e_to, nbatch, (int)i0, 2.0 * omega * c, J, ldJ, st);
       if (rc) return rc;
     } else if (e_to > e_from && J) {
       StageScope sc(3, st);
@@ -676,7 +720,7 @@ int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_
     build_host_plan(p->h, nodes, elem, N, E, el_ptr, el_elems, L, target_block, g_nd_interior);
     {
       // patches of <= 32 elements whose distinct node rows fit the shared-memory budget
-      int64_t cap = woodbury_patch_cap(p->h.nU);
+      int64_t cap = g_patch_nodes > 0 ? g_patch_nodes : woodbury_patch_cap(p->h.nU);
       if (cap < 3) cap = 3;
       build_patches(p->h, (int32_t)cap, 32);
     }
@@ -1008,6 +1052,14 @@ int ceit_set_option(const char* name, int64_t value) {
   }
   if (std::strcmp(name, "nd_interior") == 0) {
     g_nd_interior = value;
+    return CEIT_OK;
+  }
+  if (std::strcmp(name, "patch_nodes") == 0) {
+    g_patch_nodes = (int)value;
+    return CEIT_OK;
+  }
+  if (std::strcmp(name, "no_lowrank_kernel") == 0) {
+    g_no_lowrank = (int)value;
     return CEIT_OK;
   }
   if (std::strcmp(name, "no_patch_kernel") == 0) {

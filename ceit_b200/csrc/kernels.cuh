@@ -853,6 +853,156 @@ woodbury_patch_kernel(int e_from, int e_to, int L, int nU, int pitch, int64_t N,
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2, low-rank form (rank-update excitation path).  With Yh_i = Y_T - Y_T[:,B] D_i + y_e (alpha q)^T the
+// 3x3 block of Kff(i)^-1 on an element's nodes splits into an excitation-INDEPENDENT part and a
+// rank-(b+1) correction:
+//   G[a,b'] = g1e[pair] - sum_{j<b} Y_T[a,B_j] ZW_i[b'][j] + y_e[a] ZW_i[b'][bp],
+//   g1e = G0 + (Y_T Xh^T)[a,b'] (once per material state, g1_kernel),  ZW_i = Xh Dcat_i^T (one batched GEMM).
+// So the per-(excitation, element) dot products over all nU electrode nodes (6 nU FMAs and 6 nU shared loads)
+// become 6 (b+1) FMAs, the Xh rows are no longer staged, and a patch needs half the shared memory.
+// ------------------------------------------------------------------------------------------------
+// g1e[e][q] = g0e[e][q] + sum_k Y_T[pa,k] Xh[pb,k]; one warp per element
+__global__ void __launch_bounds__(256)
+g1_kernel(int64_t E, int nU, const int32_t* __restrict__ elem_pos, const double* __restrict__ g0e,
+          const double* __restrict__ YT, const double* __restrict__ Xh, double* __restrict__ g1e) {
+  const int lane = threadIdx.x & 31;
+  const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= E) return;
+  const int64_t p0 = elem_pos[3 * e], p1 = elem_pos[3 * e + 1], p2 = elem_pos[3 * e + 2];
+  const double *y0 = YT + p0 * nU, *y1 = YT + p1 * nU, *y2 = YT + p2 * nU;
+  const double *x0 = Xh + p0 * nU, *x1 = Xh + p1 * nU, *x2 = Xh + p2 * nU;
+  double d[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int k = lane; k < nU; k += 32) {
+    const double a0 = y0[k], a1 = y1[k], a2 = y2[k];
+    const double b0 = x0[k], b1 = x1[k], b2 = x2[k];
+    d[0] = fma(a0, b0, d[0]);
+    d[1] = fma(a1, b1, d[1]);
+    d[2] = fma(a2, b2, d[2]);
+    d[3] = fma(a0, b1, d[3]);
+    d[4] = fma(a1, b2, d[4]);
+    d[5] = fma(a2, b0, d[5]);
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d[q] += __shfl_xor_sync(0xffffffffu, d[q], o);
+  }
+  if (lane < 6) {
+    double v = d[0];
+#pragma unroll
+    for (int q = 1; q < 6; ++q) v = (lane == q) ? d[q] : v;
+    g1e[6 * e + lane] = g0e[6 * e + lane] + v;
+  }
+}
+
+__global__ void __launch_bounds__(WBP_WARPS * 32)
+woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64_t N, int64_t N0,
+                   const int32_t* __restrict__ patch_eptr, const int32_t* __restrict__ patch_elems,
+                   const int32_t* __restrict__ patch_nptr, const int32_t* __restrict__ patch_nodes,
+                   const uint8_t* __restrict__ patch_local, const double* __restrict__ area,
+                   const double* __restrict__ g1e, const double* __restrict__ YT, const double* __restrict__ ye,
+                   const double* __restrict__ ZW, const double* __restrict__ Yh, const double* __restrict__ phi0,
+                   const int32_t* __restrict__ ue_ptr, const double4* __restrict__ node_consts, int i0,
+                   double s_coef, double* __restrict__ J, int64_t ldJ, int cap, int nbatch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int WARPS = WBP_WARPS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x % nbatch, patch = blockIdx.x / nbatch;   // excitation fastest
+  const int i = i0 + b;
+  const int n_beg = patch_nptr[patch], nn = patch_nptr[patch + 1] - n_beg;
+  const int el_beg = patch_eptr[patch], ne = patch_eptr[patch + 1] - el_beg;
+  const int lo = ue_ptr[i], nb = ue_ptr[i + 1] - lo;
+  const int zp = bp + 1;
+  double4* cU = reinterpret_cast<double4*>(smem_raw);           // [nU] {2/phi0, 1/phi0^2, w |phi0|, -}
+  double* Ys = reinterpret_cast<double*>(cU + nU);              // [cap][pitch]  rows of Yh_i
+  double* YB = Ys + (int64_t)cap * pitch;                       // [cap][bp]     Y_T[node, B_i]
+  double* ZWs = YB + cap * bp;                                  // [cap][bp+1]   ZW_i[node, :]
+  double* yes = ZWs + cap * zp;                                 // [cap]         y_e[node]
+  double* phs = yes + cap;                                      // [cap]         phi0[node]
+  double* ybuf = phs + cap;                                     // [6][32]       Re y0..2, Im y0..2
+  const double* Y = Yh + (int64_t)b * N * nU;
+  const double* ph = phi0 + (int64_t)b * N;
+  const double* Z = ZW + (int64_t)b * zp;                        // ZW is N x (nbatch zp), excitation b's columns
+  const int64_t ldz = (int64_t)nbatch * zp;
+  for (int n = warp; n < nn; n += WARPS) {
+    const int64_t p = patch_nodes[n_beg + n];
+    const double* ys = Y + p * nU;
+    double* yd = Ys + (int64_t)n * pitch;
+    for (int k = lane; k < nU; k += 32) cp_async8(yd + k, ys + k, true);
+    for (int k = lane; k < nb; k += 32) YB[n * bp + k] = YT[p * nU + lo + k];
+    for (int k = lane; k < zp; k += 32) ZWs[n * zp + k] = Z[p * ldz + k];
+    if (lane == 0) {
+      yes[n] = ye[p];
+      phs[n] = ph[p];
+    }
+  }
+  cp_async_commit();
+  {
+    const double4* cg = node_consts + (int64_t)b * nU;
+    for (int k = threadIdx.x; k < nU; k += WARPS * 32) cU[k] = cg[k];
+  }
+  const bool have = lane < ne;
+  const int lq = have ? lane : 0;
+  const int j = patch_elems[el_beg + lq];
+  const int l0 = patch_local[3 * (el_beg + lq)], l1 = patch_local[3 * (el_beg + lq) + 1],
+            l2 = patch_local[3 * (el_beg + lq) + 2];
+  double g6[6];
+  double sj = 0.0;
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) g6[q] = g1e[6 * (int64_t)j + q];
+    sj = s_coef * area[j];
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- one warp: rank-(b+1) correction of the 3x3 block + the 3x3 solve, one lane per element -----------
+  if (warp == 0) {
+    const int la[6] = {l0, l1, l2, l0, l1, l2}, lb[6] = {l0, l1, l2, l1, l2, l0};
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const double* yb = YB + la[q] * bp;
+      const double* zw = ZWs + lb[q] * zp;
+      double acc = yes[la[q]] * zw[bp];
+      for (int jj = 0; jj < nb; ++jj) acc = fma(-yb[jj], zw[jj], acc);
+      g6[q] += acc;
+    }
+    const double f[3] = {phs[l0], phs[l1], phs[l2]};
+    double yr[3], yi[3];
+    solve3_real(g6, sj, f, yr, yi);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      ybuf[a * 32 + lane] = yr[a];
+      ybuf[(3 + a) * 32 + lane] = yi[a];
+    }
+  }
+  __syncthreads();
+  const double yr0 = ybuf[lane], yr1 = ybuf[32 + lane], yr2 = ybuf[64 + lane];
+  const double yi0 = ybuf[96 + lane], yi1 = ybuf[128 + lane], yi2 = ybuf[160 + lane];
+  const double* y0 = Ys + (int64_t)l0 * pitch;
+  const double* y1 = Ys + (int64_t)l1 * pitch;
+  const double* y2 = Ys + (int64_t)l2 * pitch;
+  // ---- amplitudes and weighted sums of this warp's electrodes -------------------------------------------
+  const bool write = have && j >= e_from && j < e_to;
+  for (int m = warp; m < L; m += WARPS) {
+    if (m == i) continue;
+    const int ks = ue_ptr[m], ke = ue_ptr[m + 1];
+    double sum0 = 0.0, sumt = 0.0;
+#pragma unroll 4
+    for (int k = ks; k < ke; ++k) {
+      const double4 cu = cU[k];
+      const double a0 = y0[k], a1 = y1[k], a2 = y2[k];
+      const double dr = fma(a0, yr0, fma(a1, yr1, a2 * yr2));
+      const double di = fma(a0, yi0, fma(a1, yi1, a2 * yi2));
+      const double qq = fma(dr, dr, di * di);
+      const double x = fma(cu.x, dr, qq * cu.y);         // (2 phi0 dr + |d|^2) / phi0^2, phi0 real
+      sum0 += cu.z;
+      sumt = fma(cu.z, sqrt1p_minus1(x), sumt);
+    }
+    if (write) J[((int64_t)i * (L - 1) + m - (m > i ? 1 : 0)) * ldJ + j] = fabs(sum0 + sumt);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // inverse model / realtime helpers
 // ------------------------------------------------------------------------------------------------
 // Jt[r][c] = J[rows[r]][det[c]] - shift           (Solver.py:76-86,119)

@@ -1,12 +1,15 @@
 """Stage timing (CUDA events inside the library) of the hot path on a shipped or synthetic mesh.
-usage: python tools/stage_breakdown.py [50_50|21_21|<n> [per_side]] [--target B]"""
+usage: python tools/stage_breakdown.py [50_50|21_21|<n> [per_side]] [--target B] [--complex] [--opt name=value ...]"""
 import sys, os, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from ceit_b200 import _lib, meshgen
 import bench
-args = [a for a in sys.argv[1:] if not a.startswith("--")]
+opts = [sys.argv[k + 1] for k, a in enumerate(sys.argv[:-1]) if a == "--opt"]     # --opt name=value (ceit_set_option)
+for o_ in opts:
+    _lib.set_option(o_.split("=")[0], float(o_.split("=")[1]))
+args = [a for a in sys.argv[1:] if not a.startswith("--") and a not in opts]
 cplx = False
 target = int(sys.argv[sys.argv.index("--target") + 1]) if "--target" in sys.argv else 0
 if "--target" in sys.argv: args = [a for a in args if a != str(target)] if False else args

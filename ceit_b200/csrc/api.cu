@@ -50,6 +50,7 @@ constexpr int N_STAGES = 8;
 int g_stage_timers = 0;
 int g_no_patch = 0;
 int g_no_lowrank = 0;
+int g_direct_excitation = 0;
 int g_patch_nodes = 0;   // experiment: override the node cap of the element patches
 int64_t g_nd_interior = 64;   // target nodes per nested-dissection interior; <= 0 disables level 1
 struct StageEv {
@@ -84,6 +85,21 @@ constexpr int64_t WB_SMEM_SM = 226 * 1024;
 inline int64_t woodbury_pitch(int64_t nU) { return nU | 1; }   // odd: row bases hit all 16 bank pairs
 inline size_t woodbury_patch_smem(int64_t nU, int64_t cap) {
   return (size_t)(nU * 32 + 2 * cap * woodbury_pitch(nU) * 8 + WBP_WARPS * 6 * 32 * 8 + 6 * 32 * 8 + cap * 8 + 64);
+}
+// low-rank kernel: only the Yh rows are staged (plus 2 bp + 3 small values per node)
+inline size_t woodbury_lr_smem(int64_t nU, int64_t cap, int64_t bp) {
+  return (size_t)(nU * 32 + cap * woodbury_pitch(nU) * 8 + cap * bp * 8 + cap * (bp + 1) * 8 + 2 * cap * 8 + 12 * 32 * 8 + 64);
+}
+// node cap of a patch for the low-rank kernel: 3 CTAs per SM if that leaves >= 20 nodes (~24 elements) per
+// patch, else 2 (measured: occupancy beats patch size, 400x400 mesh 30 -> 18 ms)
+inline int woodbury_lr_cap(int64_t nU, int64_t bp) {
+  for (int per_sm = 3; per_sm >= 1; --per_sm) {
+    const int64_t budget = (227 * 1024) / per_sm - 1024 - 256;
+    int64_t cap = 40;
+    while (cap > 0 && (int64_t)woodbury_lr_smem(nU, cap, bp) > budget) --cap;
+    if (cap >= (per_sm == 3 ? 20 : 16) || per_sm == 1) return (int)cap;
+  }
+  return 0;
 }
 inline int woodbury_patch_cap(int64_t nU) {
   for (int per_sm = 2; per_sm >= 1; --per_sm) {
@@ -314,11 +330,10 @@ int alloc_excitation_ws(ceit_plan* p, int want_cap) {
 
 // the rank-(b+1) excitation path needs contiguous electrode ranges in U, <= 64 nodes per electrode and
 // nU <= 1024; otherwise every excitation factorises its own padded S_U (excitation_direct)
-int g_direct_excitation = 0;
-inline bool use_rank_update(const ceit_plan* p) {
-  const HostPlan& h = p->h;
-  return !g_direct_excitation && h.u_contiguous && h.bp <= 64 && h.nU <= 1024 && h.nU > h.bp;
+inline bool rank_update_shape_ok(const HostPlan& h) {
+  return h.u_contiguous && h.bp <= 64 && h.nU <= 1024 && h.nU > h.bp;
 }
+inline bool use_rank_update(const ceit_plan* p) { return !g_direct_excitation && rank_update_shape_ok(p->h); }
 
 // excitation-independent part of the element blocks for the low-rank Woodbury kernel (real path only)
 inline void launch_g1(ceit_plan* p, const double* g0e, const double* YT, const double* Xh, cudaStream_t st) {
@@ -511,28 +526,34 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
     potrf_trtri_blocked<T>(st, bp, TBB, bp, (int64_t)bp * bp, LB, bp, (int64_t)bp * bp, LinvB, bp, (int64_t)bp * bp,
                            nullptr, 0, nbatch, p->d_info);
     const size_t sm1 = (size_t)(2 * bp * bp + bp + nU + 256) * es;
-    const size_t sm2 = (size_t)((bp + 1) * nU + 16 * (bp + 1)) * es;
     static bool attr_done = false;
     if (!attr_done) {
       CUDA_TRY(cudaFuncSetAttribute(excite_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+#define CEIT_RU_ATTR(c) \
+  CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
+      CEIT_RU_ATTR(1); CEIT_RU_ATTR(2); CEIT_RU_ATTR(3);
+#undef CEIT_RU_ATTR
       attr_done = true;
     }
     excite_small_kernel<T><<<nbatch, 256, sm1, st>>>((int)nU, bp, Tinv, te, LinvB, p->d_ue_ptr, i0, p->d_gamma, Dcat);
     CEIT_COUNT_LAUNCH();
-    constexpr int RT = Sc<T>::is_complex ? 8 : 16;
     auto update = [&](int64_t rows, const T* src, const T* yv, int zero_rows, T* out, int64_t stride) {
-      dim3 grid(nbatch, cdiv(rows, RT));
-      const int cmax = (int)((nU + 255) / 256);
-#define CEIT_RU(c) rank_update_kernel<T, c><<<grid, 256, sm2, st>>>(rows, (int)nU, bp, src, yv, Dcat, p->d_ue_ptr, i0, \
-                                                                  zero_rows, out, stride)
-      if (cmax <= 1) CEIT_RU(1);
-      else if (cmax == 2) CEIT_RU(2);
-      else if (cmax == 3) CEIT_RU(3);
-      else CEIT_RU(4);
+      // columns in chunks of <= 384 (3 per thread) so that the staged part of D_i stays small enough for
+      // several CTAs per SM; D_i is staged once per CTA, so a CTA takes several row tiles, but keep >= 2 waves
+      const int nz = (int)cdiv(nU, 384);
+      const int cw = (int)cdiv(nU, nz);
+      const int cpt = (cw + 127) / 128;
+      const int rt = Sc<T>::is_complex ? 8 : 16;                             // rows per pass (kernel: 2 RH)
+      const size_t smu = (size_t)((bp + 1) * cw + 16 * (bp + 1)) * es;
+      const int64_t tiles = cdiv(rows, rt);
+      const int64_t slots = 148 * std::max<int64_t>(1, std::min<int64_t>(2, (200 * 1024) / (int64_t)smu));
+      const int passes = (int)std::max<int64_t>(1, std::min<int64_t>(8, (tiles * nbatch * nz) / (2 * slots)));
+      dim3 grid(nbatch, cdiv(tiles, passes), nz);
+#define CEIT_RU(c) rank_update_kernel<T, c><<<grid, 256, smu, st>>>(rows, (int)nU, bp, src, yv, Dcat, p->d_ue_ptr, i0, \
+                                                                  zero_rows, out, stride, passes, cw)
+      if (cpt <= 1) CEIT_RU(1);
+      else if (cpt == 2) CEIT_RU(2);
+      else CEIT_RU(3);
 #undef CEIT_RU
       CEIT_COUNT_LAUNCH();
     };
@@ -597,9 +618,6 @@ int launch_woodbury_patch(ceit_plan* p, const double* g0e, const double* Xh, con
   CEIT_COUNT_LAUNCH();
   return 0;
 }
-inline size_t woodbury_lr_smem(int64_t nU, int64_t cap, int64_t bp) {
-  return (size_t)(nU * 32 + cap * woodbury_pitch(nU) * 8 + cap * bp * 8 + cap * (bp + 1) * 8 + 2 * cap * 8 + 6 * 32 * 8 + 64);
-}
 int launch_woodbury_lr(ceit_plan* p, int e_from, int e_to, int nbatch, int i0, double s_coef, double* J, int64_t ldJ,
                        cudaStream_t st) {
   const HostPlan& h = p->h;
@@ -647,10 +665,13 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
                                                 p->d_we_u, p->d_we_w, (int)i0, base, nullptr);
       CEIT_COUNT_LAUNCH();
     }
-    const bool use_patch = !g_no_patch && !Sc<T>::is_complex && h.patch_node_cap >= 12 && h.u_contiguous;
+    const bool lowrank = use_rank_update(p) && !g_no_lowrank &&
+                         woodbury_lr_smem(h.nU, h.patch_node_cap, h.bp) <= (size_t)WB_SMEM_SM;
+    const bool use_patch = !g_no_patch && !Sc<T>::is_complex && h.patch_node_cap >= 12 && h.u_contiguous &&
+                           (lowrank || woodbury_patch_smem(h.nU, h.patch_node_cap) <= (size_t)WB_SMEM_SM);
     if (e_to > e_from && J && use_patch) {
       StageScope sc(3, st);
-      if (use_rank_update(p) && !g_no_lowrank)
+      if (lowrank)
         rc = launch_woodbury_lr(p, (int)e_from, (int)e_to, nbatch, (int)i0, 2.0 * omega * c, J, ldJ, st);
       else
         rc = launch_woodbury_patch(p, (const T*)p->g0e, (const T*)p->Xh, (const T*)p->Yh, (const T*)p->phi0, (int)e_from,
@@ -720,7 +741,9 @@ int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_
     build_host_plan(p->h, nodes, elem, N, E, el_ptr, el_elems, L, target_block, g_nd_interior);
     {
       // patches of <= 32 elements whose distinct node rows fit the shared-memory budget
-      int64_t cap = g_patch_nodes > 0 ? g_patch_nodes : woodbury_patch_cap(p->h.nU);
+      const bool lr = rank_update_shape_ok(p->h) && !g_direct_excitation && !g_no_lowrank;
+      int64_t cap = g_patch_nodes > 0 ? std::min(g_patch_nodes, 64)
+                                      : (lr ? woodbury_lr_cap(p->h.nU, p->h.bp) : woodbury_patch_cap(p->h.nU));
       if (cap < 3) cap = 3;
       build_patches(p->h, (int32_t)cap, 32);
     }

@@ -16,51 +16,78 @@ __device__ long long g_tile_clk[8];
 #define CEIT_CLK(k) do { } while (0)
 #endif
 
-// One phase (16 pivot columns j = 16 PH .. 16 PH + 15) of the unscaled elimination of a 64 x 64 tile.
-// Thread (rb, cb) holds c[u][v] = S[rb + 16 u][cb + 16 v].  Every step ends with one barrier; the loop
-// runs to the block-uniform bound n, so all threads execute the same number of barriers.
+// Two pivot columns per barrier: phase PH (columns 16 PH .. 16 PH + 15) of the unscaled elimination of a
+// 64 x 64 tile, done as 8 eliminations of a 2 x 2 pivot block P = [[p00, p10], [p10, p11]] (columns j, j+1):
+//   C -= [a0 a1] P^-1 [b0 b1]^T,  P^-1 = [[p11, -p10], [-p10, p00]] / det.
+// Thread (rb, cb) holds c[u][v] = S[rb + 16 u][cb + 16 v]; only the blocks u >= v, v >= PH are live (lower
+// triangle, columns not yet eliminated).  Shared memory holds columns j and j+1 updated through column j-1
+// (published by their owners at the end of the previous double step); every thread forms the multipliers
+// itself, so a double step has ONE barrier and ONE reciprocal on its dependent chain.  The second column of a
+// pair is frozen in its published state; the rank-1 update by its partner that it still lacks is applied
+// after the last phase (tile_fix_odd_columns).
 template <class T, int PH>
-__device__ __forceinline__ void tile_eliminate_phase(T* __restrict__ S, T* __restrict__ rpiv, T (&c)[4][4], int rb,
-                                                     int cb, int n) {
+__device__ __forceinline__ void tile_eliminate_phase2(T* __restrict__ S, T (&c)[4][4], int rb, int cb, int n) {
   constexpr int LD = TILE + 1;
+  constexpr int PN = PH < 3 ? PH + 1 : 3;
 #pragma unroll 1
-  for (int jj = 0; jj < 16; ++jj) {
+  for (int jj = 0; jj < 16; jj += 2) {
     const int j = 16 * PH + jj;
-    if (j >= n) break;
-    const T rp = rpiv[j];
-    T cj[4], tk[4];
+    if (j >= n) break;                       // n odd: the identity padding makes the extra column a no-op
+    const T p00 = S[j * LD + j], p10 = S[(j + 1) * LD + j], p11 = S[(j + 1) * LD + j + 1];
+    T a0[4], a1[4], t0[4], t1[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) cj[u] = S[(rb + 16 * u) * LD + j];
+    for (int u = PH; u < 4; ++u) {
+      a0[u] = S[(rb + 16 * u) * LD + j];
+      a1[u] = S[(rb + 16 * u) * LD + j + 1];
+    }
 #pragma unroll
-    for (int v = PH; v < 4; ++v) tk[v] = mul(S[(cb + 16 * v) * LD + j], rp);
-    if (cb <= jj) tk[PH] = Sc<T>::zero();                 // my column of this phase is already final
-    if (jj < 15) {
-      // next pivot column is cb == jj + 1 of block PH; its diagonal element is row block PH as well
-      if (cb == jj + 1 && rb == jj + 1) rpiv[j + 1] = rcp_fast(sub(c[PH][PH], mul(cj[PH], tk[PH])));
+    for (int v = PH; v < 4; ++v) {
+      t0[v] = S[(cb + 16 * v) * LD + j];
+      t1[v] = S[(cb + 16 * v) * LD + j + 1];
+    }
+    const T rdet = rcp_fast(sub(mul(p00, p11), mul(p10, p10)));
+    const T q11 = mul(p11, rdet), q10 = mul(p10, rdet), q00 = mul(p00, rdet);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+    for (int v = PH; v < 4; ++v) {
+      const T b0 = t0[v], b1 = t1[v];
+      t0[v] = sub(mul(q11, b0), mul(q10, b1));
+      t1[v] = sub(mul(q00, b1), mul(q10, b0));
+    }
+    if (cb <= jj + 1) {                      // my column of this phase is final (or frozen: second of the pair)
+      t0[PH] = Sc<T>::zero();
+      t1[PH] = Sc<T>::zero();
+    }
 #pragma unroll
-        for (int v = PH; v < 4; ++v) c[u][v] = sub(c[u][v], mul(cj[u], tk[v]));
-      if (cb == jj + 1) {
+    for (int v = PH; v < 4; ++v)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) S[(rb + 16 * u) * LD + j + 1] = c[u][PH];
+      for (int u = v; u < 4; ++u) c[u][v] = sub(sub(c[u][v], mul(a0[u], t0[v])), mul(a1[u], t1[v]));
+    if (jj < 14) {
+      if (cb == jj + 2 || cb == jj + 3) {
+#pragma unroll
+        for (int u = PH; u < 4; ++u) S[(rb + 16 * u) * LD + 16 * PH + cb] = c[u][PH];
       }
-    } else {
-      // last step of the phase: the next pivot column is column 0 of block PH + 1
-      if (PH < 3) {
-        if (cb == 0 && rb == 0) rpiv[j + 1] = rcp_fast(sub(c[PH < 3 ? PH + 1 : 3][PH < 3 ? PH + 1 : 3],
-                                                          mul(cj[PH < 3 ? PH + 1 : 3], tk[PH < 3 ? PH + 1 : 3])));
-      }
+    } else if (PH < 3) {
+      if (cb < 2) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = PH; v < 4; ++v) c[u][v] = sub(c[u][v], mul(cj[u], tk[v]));
-      if (PH < 3 && cb == 0) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) S[(rb + 16 * u) * LD + j + 1] = c[u][PH < 3 ? PH + 1 : 3];
+        for (int u = PN; u < 4; ++u) S[(rb + 16 * u) * LD + 16 * PN + cb] = c[u][PN];
       }
     }
     __syncthreads();
+  }
+}
+// Odd columns k were frozen one rank-1 update short: c[.][k] -= S[.][k-1] S[k][k-1] / S[k-1][k-1] (column k-1 is
+// final in shared memory).
+template <class T>
+__device__ __forceinline__ void tile_fix_odd_columns(const T* __restrict__ S, T (&c)[4][4], int rb, int cb) {
+  constexpr int LD = TILE + 1;
+  if (cb & 1) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int k = cb + 16 * v;
+      const T m = mul(S[k * LD + k - 1], rcp_fast(S[(k - 1) * LD + k - 1]));
+#pragma unroll
+      for (int u = v; u < 4; ++u) c[u][v] = sub(c[u][v], mul(S[(rb + 16 * u) * LD + k - 1], m));
+    }
   }
 }
 
@@ -149,13 +176,12 @@ potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA,
   }
   __syncthreads();
   CEIT_CLK(1);
-  // ---- unscaled right-looking elimination, one barrier per column --------------------------------
+  // ---- unscaled right-looking elimination, one barrier per TWO columns -----------------------------
   // Thread (rb, cb) owns the 4x4 interleaved register tile {rb+16u} x {cb+16v} for the whole
   // elimination (interleaving balances the triangular work and keeps shared accesses conflict-free).
-  // Per step it loads 4 values of the pivot column (its rows) and 4 multipliers (its columns): 9 shared
-  // loads for 16 FMAs.  A column is published to shared memory once, when it becomes final, together
-  // with the reciprocal of its pivot, which its owner starts FIRST so that the reciprocal's latency
-  // overlaps the rest of the update.  Entries above the diagonal are carried along unpredicated: they
+  // Per double step it loads 2 x 4 values of the two pivot columns for its rows, 2 x 4 for its columns and
+  // the 2 x 2 pivot block, for 32 FMAs.  A column pair is published to shared memory once, when the
+  // eliminations before it are complete.  Entries above the diagonal are carried along unpredicated: they
   // only feed other above-diagonal entries, which are never read for results.
   const int cb = tid & 15, rb = tid >> 4;
   T c[4][4];
@@ -163,23 +189,29 @@ potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA,
   for (int u = 0; u < 4; ++u)
 #pragma unroll
     for (int v = 0; v < 4; ++v) c[u][v] = S[(rb + 16 * u) * LD + cb + 16 * v];
-  if (tid == 0) rpiv[0] = rcp_fast(S[0]);
   __syncthreads();
   // The 64 steps are split into 4 phases of 16 (PH = j >> 4, a compile-time constant inside a phase), so
   // that "which of my columns are still live" and "which register holds the next pivot column" are static:
   // columns v < PH are final, v > PH always live, v == PH live iff cb > (j & 15).
-  tile_eliminate_phase<T, 0>(S, rpiv, c, rb, cb, n);
-  tile_eliminate_phase<T, 1>(S, rpiv, c, rb, cb, n);
-  tile_eliminate_phase<T, 2>(S, rpiv, c, rb, cb, n);
-  tile_eliminate_phase<T, 3>(S, rpiv, c, rb, cb, n);
+  tile_eliminate_phase2<T, 0>(S, c, rb, cb, n);
+  tile_eliminate_phase2<T, 1>(S, c, rb, cb, n);
+  tile_eliminate_phase2<T, 2>(S, c, rb, cb, n);
+  tile_eliminate_phase2<T, 3>(S, c, rb, cb, n);
+  tile_fix_odd_columns<T>(S, c, rb, cb);
   CEIT_CLK(2);
+  // final pivots: the diagonal entry (cb + 16 v, cb + 16 v) lives in c[v][v] of the thread with rb == cb
+  if (rb == cb) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) rpiv[cb + 16 * v] = c[v][v];
+  }
+  __syncthreads();
   // ---- L = S diag(p)^-1/2 ; rdiag = 1 / L_jj --------------------------------------------------------
   {
     T rs[4];
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       const int k = cb + 16 * v;
-      const T p = S[k * LD + k];
+      const T p = rpiv[k];
       if (rb == 0 && bad_pivot(p)) atomicExch(info, 1);
       rs[v] = inv_(sqrt_(p));
       if (rb == 0) rdiag[k] = rs[v];
@@ -196,14 +228,17 @@ potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA,
   // ---- X = L^-1: four 16x16 diagonal blocks by forward substitution, column in registers ---------------
   if (tid < 64) {
     const int o = (tid >> 4) << 4, cc = tid & 15;
-    T x[16];
+    // column-oriented (axpy) form: x_r is final after ONE dependent multiply, then updates all later rows
+    // with independent FMAs, so the dependent chain is 2 operations per row instead of r
+    T s[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s[r] = (r == cc) ? Sc<T>::one() : Sc<T>::zero();
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-      T s0 = (r == cc) ? Sc<T>::one() : Sc<T>::zero();
+      const T x = mul(s[r], rdiag[o + r]);
+      X[(o + r) * LD + o + cc] = x;
 #pragma unroll
-      for (int k = 0; k < r; ++k) s0 = sub(s0, mul(S[(o + r) * LD + o + k], x[k]));
-      x[r] = mul(s0, rdiag[o + r]);
-      X[(o + r) * LD + o + cc] = x[r];
+      for (int r2 = r + 1; r2 < 16; ++r2) s[r2] = sub(s[r2], mul(S[(o + r2) * LD + o + r], x));
     }
   }
   __syncthreads();

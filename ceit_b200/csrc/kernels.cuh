@@ -328,67 +328,82 @@ excite_small_kernel(int nU, int bp, const T* __restrict__ Tm, const T* __restric
   for (int k = tid; k < nU; k += 256) D[(int64_t)bp * nU + k] = mul(alpha, q[k]);
 }
 // out[b][n,k] = src[n,k] - sum_{j<b} src[n, lo+j] D[j,k] + yv[n] D[bp,k]; columns (and, if zero_rows, rows)
-// of B_i are set to exactly zero.  CTA = 16 rows x all columns of one excitation.
-template <class T, int CMAX>
+// of B_i are set to exactly zero.  CTA = one excitation x `passes` tiles of RT rows x all columns: D_i is
+// staged in shared memory once per CTA; 128 threads span the columns (CPT = ceil(nU / 128) each), the two
+// thread halves take alternate rows of the tile.
+template <class T, int CPT>
 __global__ void __launch_bounds__(256)
 rank_update_kernel(int64_t rows, int nU, int bp, const T* __restrict__ src, const T* __restrict__ yv,
                    const T* __restrict__ Dcat, const int32_t* __restrict__ ue_ptr, int i0, int zero_rows,
-                   T* __restrict__ out, int64_t out_stride) {
+                   T* __restrict__ out, int64_t out_stride, int passes, int cw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int RT = Sc<T>::is_complex ? 8 : 16;             // CMAX = ceil(nU / 256) <= 4
-  T* Ds = reinterpret_cast<T*>(smem_raw);   // [(bp+1)][nU]
-  T* As = Ds + (int64_t)(bp + 1) * nU;      // [RT][bp+1]
-  const int tid = threadIdx.x;
-  const int i = i0 + blockIdx.x;      // excitation fastest: the 32 CTAs that share a row tile of src run together
+  constexpr int RH = Sc<T>::is_complex ? 4 : 8;   // rows per thread
+  constexpr int RT = 2 * RH;                       // rows per pass
+  T* Ds = reinterpret_cast<T*>(smem_raw);   // [(bp+1)][cw]   columns [k_lo, k_lo + cw) of D_i
+  T* As = Ds + (int64_t)(bp + 1) * cw;      // [RT][bp+1]
+  const int tid = threadIdx.x, tx = tid & 127, ty = tid >> 7;
+  const int i = i0 + blockIdx.x;      // excitation fastest: the CTAs that share a row tile of src run together
   const int lo = ue_ptr[i], b = ue_ptr[i + 1] - lo;
-  const int64_t n0 = (int64_t)blockIdx.y * RT;
+  const int k_lo = blockIdx.z * cw, kw = min(cw, nU - k_lo);
   const T* D = Dcat + (int64_t)blockIdx.x * (bp + 1) * nU;
-  for (int t = tid; t < (bp + 1) * nU; t += 256) Ds[t] = D[t];
-  for (int t = tid; t < RT * (bp + 1); t += 256) {
-    const int r = t / (bp + 1), j = t - r * (bp + 1);
-    const int64_t n = n0 + r;
-    T v = Sc<T>::zero();
-    if (n < rows) {
-      if (j < b) v = src[n * nU + lo + j];
-      else if (j == bp) v = neg(yv[n]);
-    }
-    As[t] = v;
-  }
-  __syncthreads();
-  T acc[RT][CMAX];
-#pragma unroll
-  for (int c = 0; c < CMAX; ++c) {
-    const int k = tid + 256 * c;
-#pragma unroll
-    for (int r = 0; r < RT; ++r) acc[r][c] = (k < nU && n0 + r < rows) ? src[(n0 + r) * nU + k] : Sc<T>::zero();
-  }
-  for (int j = 0; j <= bp; ++j) {
-    if (j >= b && j < bp) continue;
-    T dv[CMAX];
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-      const int k = tid + 256 * c;
-      dv[c] = (k < nU) ? Ds[(int64_t)j * nU + k] : Sc<T>::zero();
-    }
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      const T a = As[r * (bp + 1) + j];
-#pragma unroll
-      for (int c = 0; c < CMAX; ++c) acc[r][c] = sub(acc[r][c], mul(a, dv[c]));
-    }
+  for (int t = tid; t < (bp + 1) * kw; t += 256) {
+    const int j = t / kw, k = t - j * kw;
+    Ds[j * cw + k] = D[(int64_t)j * nU + k_lo + k];
   }
   T* o = out + (int64_t)blockIdx.x * out_stride;
-#pragma unroll
-  for (int c = 0; c < CMAX; ++c) {
-    const int k = tid + 256 * c;
-    if (k >= nU) continue;
-    const bool colB = (k >= lo && k < lo + b);
-#pragma unroll
-    for (int r = 0; r < RT; ++r) {
+  for (int ps = 0; ps < passes; ++ps) {
+    const int64_t n0 = ((int64_t)blockIdx.y * passes + ps) * RT;
+    if (n0 >= rows) break;
+    __syncthreads();                        // Ds staged / As of the previous pass consumed
+    for (int t = tid; t < RT * (bp + 1); t += 256) {
+      const int r = t / (bp + 1), j = t - r * (bp + 1);
       const int64_t n = n0 + r;
-      if (n >= rows) continue;
-      const bool rowB = zero_rows && (n >= lo && n < lo + b);
-      o[n * nU + k] = (colB || rowB) ? Sc<T>::zero() : acc[r][c];
+      T v = Sc<T>::zero();
+      if (n < rows) {
+        if (j < b) v = src[n * nU + lo + j];
+        else if (j == bp) v = neg(yv[n]);
+      }
+      As[t] = v;
+    }
+    T acc[RH][CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int k = tx + 128 * c;
+#pragma unroll
+      for (int r = 0; r < RH; ++r) {
+        const int64_t n = n0 + 2 * r + ty;
+        acc[r][c] = (k < kw && n < rows) ? src[n * nU + k_lo + k] : Sc<T>::zero();
+      }
+    }
+    __syncthreads();
+    for (int j = 0; j <= bp; ++j) {
+      if (j >= b && j < bp) continue;
+      T dv[CPT];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        const int k = tx + 128 * c;
+        dv[c] = (k < kw) ? Ds[j * cw + k] : Sc<T>::zero();
+      }
+#pragma unroll
+      for (int r = 0; r < RH; ++r) {
+        const T a = As[(2 * r + ty) * (bp + 1) + j];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) acc[r][c] = sub(acc[r][c], mul(a, dv[c]));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int k = tx + 128 * c;
+      if (k >= kw) continue;
+      const int kg = k_lo + k;
+      const bool colB = (kg >= lo && kg < lo + b);
+#pragma unroll
+      for (int r = 0; r < RH; ++r) {
+        const int64_t n = n0 + 2 * r + ty;
+        if (n >= rows) continue;
+        const bool rowB = zero_rows && (n >= lo && n < lo + b);
+        o[n * nU + kg] = (colB || rowB) ? Sc<T>::zero() : acc[r][c];
+      }
     }
   }
 }
@@ -920,21 +935,24 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
   double* yes = ZWs + cap * zp;                                 // [cap]         y_e[node]
   double* phs = yes + cap;                                      // [cap]         phi0[node]
   double* ybuf = phs + cap;                                     // [6][32]       Re y0..2, Im y0..2
+  double* gbuf = ybuf + 6 * 32;                                 // [6][32]       corrected 3x3 blocks
   const double* Y = Yh + (int64_t)b * N * nU;
   const double* ph = phi0 + (int64_t)b * N;
   const double* Z = ZW + (int64_t)b * zp;                        // ZW is N x (nbatch zp), excitation b's columns
   const int64_t ldz = (int64_t)nbatch * zp;
+  // node positions of the patch: one coalesced load, then everything is staged with cp.async (no load -> store
+  // round trips in the staging loop)
+  const int pn_a = (lane < nn) ? patch_nodes[n_beg + lane] : 0;
+  const int pn_b = (lane + 32 < nn) ? patch_nodes[n_beg + lane + 32] : 0;
   for (int n = warp; n < nn; n += WARPS) {
-    const int64_t p = patch_nodes[n_beg + n];
+    const int64_t p = __shfl_sync(0xffffffffu, (n < 32) ? pn_a : pn_b, n & 31);
     const double* ys = Y + p * nU;
     double* yd = Ys + (int64_t)n * pitch;
     for (int k = lane; k < nU; k += 32) cp_async8(yd + k, ys + k, true);
-    for (int k = lane; k < nb; k += 32) YB[n * bp + k] = YT[p * nU + lo + k];
-    for (int k = lane; k < zp; k += 32) ZWs[n * zp + k] = Z[p * ldz + k];
-    if (lane == 0) {
-      yes[n] = ye[p];
-      phs[n] = ph[p];
-    }
+    for (int k = lane; k < nb; k += 32) cp_async8(YB + n * bp + k, YT + p * nU + lo + k, true);
+    for (int k = lane; k < zp; k += 32) cp_async8(ZWs + n * zp + k, Z + p * ldz + k, true);
+    if (lane == 0) cp_async8(yes + n, ye + p, true);
+    if (lane == 1) cp_async8(phs + n, ph + p, true);
   }
   cp_async_commit();
   {
@@ -946,26 +964,33 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
   const int j = patch_elems[el_beg + lq];
   const int l0 = patch_local[3 * (el_beg + lq)], l1 = patch_local[3 * (el_beg + lq) + 1],
             l2 = patch_local[3 * (el_beg + lq) + 2];
-  double g6[6];
-  double sj = 0.0;
-  if (warp == 0) {
-#pragma unroll
-    for (int q = 0; q < 6; ++q) g6[q] = g1e[6 * (int64_t)j + q];
-    sj = s_coef * area[j];
-  }
+  // warps 0..5 each correct one entry of the symmetric 3x3 block (pairs (0,0),(1,1),(2,2),(0,1),(1,2),(2,0))
+  // for the 32 elements; warp 0 then solves
+  const int la = (warp == 0 || warp == 3) ? l0 : ((warp == 1 || warp == 4) ? l1 : l2);
+  const int lb = (warp == 0 || warp == 5) ? l0 : ((warp == 1 || warp == 3) ? l1 : l2);
+  double gq = 0.0, sj = 0.0;
+  if (warp < 6) gq = g1e[6 * (int64_t)j + warp];
+  if (warp == 0) sj = s_coef * area[j];
   cp_async_wait<0>();
   __syncthreads();
-  // ---- one warp: rank-(b+1) correction of the 3x3 block + the 3x3 solve, one lane per element -----------
-  if (warp == 0) {
-    const int la[6] = {l0, l1, l2, l0, l1, l2}, lb[6] = {l0, l1, l2, l1, l2, l0};
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      const double* yb = YB + la[q] * bp;
-      const double* zw = ZWs + lb[q] * zp;
-      double acc = yes[la[q]] * zw[bp];
-      for (int jj = 0; jj < nb; ++jj) acc = fma(-yb[jj], zw[jj], acc);
-      g6[q] += acc;
+  if (warp < 6) {
+    const double* yb = YB + la * bp;
+    const double* zw = ZWs + lb * zp;
+    double a0 = yes[la] * zw[bp], a1 = 0.0;
+    int jj = 0;
+    for (; jj + 1 < nb; jj += 2) {
+      a0 = fma(-yb[jj], zw[jj], a0);
+      a1 = fma(-yb[jj + 1], zw[jj + 1], a1);
     }
+    if (jj < nb) a0 = fma(-yb[jj], zw[jj], a0);
+    gbuf[warp * 32 + lane] = gq + (a0 + a1);
+  }
+  __syncthreads();
+  // ---- one warp: the 3x3 solve, one lane per element -----------------------------------------------------
+  if (warp == 0) {
+    double g6[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) g6[q] = gbuf[q * 32 + lane];
     const double f[3] = {phs[l0], phs[l1], phs[l2]};
     double yr[3], yi[3];
     solve3_real(g6, sj, f, yr, yi);

@@ -67,14 +67,15 @@ CEIT_HD cd inv_(cd a) {
   double d = fma(a.x, a.x, a.y * a.y);
   return mk(a.x / d, -a.y / d);
 }
-// reciprocal to ~1 ulp without the slow-path checks of 1.0/x: MUFU seed + two Newton steps (device);
-// used on the serial critical path of the tile factorisation
+// reciprocal to ~1 ulp without the slow-path checks of 1.0/x (device); used on the serial critical path of the
+// tile factorisation.  MUFU seed r0 with relative error e = 1 - a r0, |e| <= 2^-20; one cubic step
+// r0 (1 + e + e^2) leaves e^3 (3 dependent FMAs), a final Newton step rounds it off.
 __device__ __forceinline__ double rcp_fast(double a) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  const double e = fma(-a, r, 1.0);
+  r = fma(r, fma(e, e, e), r);
   r = fma(fma(-a, r, 1.0), r, r);
-  r = fma(fma(-a, r, 1.0), r, r);
-  r = fma(fma(-a, r, 1.0), r, r);   // seed has ~20 bits: 40, 80 after two steps; the third is insurance
   return r;
 }
 __device__ __forceinline__ cd rcp_fast(cd a) { return inv_(a); }

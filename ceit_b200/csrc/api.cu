@@ -152,6 +152,11 @@ struct ceit_plan {
   void *Mreg = nullptr, *LT = nullptr, *LinvT = nullptr, *Tinv = nullptr, *te = nullptr, *YT = nullptr, *ye = nullptr;
   double* d_gamma = nullptr;
   void* splitk_ws = nullptr;
+  // auxiliary stream + events: independent chains of a stage (right-hand-side sweep vs selected inverse, ...)
+  // run concurrently and join before the stage ends; also valid under stream capture (fork/join in the graph)
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_ring[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int ev_next = 0;
   void* g1e = nullptr;
   void* ZW = nullptr;
   void *TBB = nullptr, *LB = nullptr, *LinvB = nullptr, *Dcat = nullptr;
@@ -330,6 +335,24 @@ int alloc_excitation_ws(ceit_plan* p, int want_cap) {
 
 // the rank-(b+1) excitation path needs contiguous electrode ranges in U, <= 64 nodes per electrode and
 // nU <= 1024; otherwise every excitation factorises its own padded S_U (excitation_direct)
+int g_multi_stream = 1;
+// `to` waits for everything enqueued on `from` so far
+inline int stream_after(ceit_plan* p, cudaStream_t from, cudaStream_t to) {
+  if (from == to) return 0;
+  cudaEvent_t e = p->ev_ring[p->ev_next];
+  p->ev_next = (p->ev_next + 1) & 7;
+  CUDA_TRY(cudaEventRecord(e, from));
+  CUDA_TRY(cudaStreamWaitEvent(to, e, 0));
+  return 0;
+}
+inline int ensure_aux_stream(ceit_plan* p) {
+  if (p->s2) return 0;
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->s2, cudaStreamNonBlocking));
+  for (auto& e : p->ev_ring) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return 0;
+}
+#define CEIT_AFTER(from, to) do { int rc_ = stream_after(p, from, to); if (rc_) return rc_; } while (0)
+
 inline bool rank_update_shape_ok(const HostPlan& h) {
   return h.u_contiguous && h.bp <= 64 && h.nU <= 1024 && h.nU > h.bp;
 }
@@ -396,10 +419,20 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   CEIT_COUNT_LAUNCH();
   KERNEL_CHECK();
   CUDA_TRY(cudaMemcpyAsync(SU, KUU, nU * nU * es, cudaMemcpyDeviceToDevice, st));
+  // Two chains share the factorisation: the MATRIX chain (factor blocks, selected inverse, G0) stays on `st`,
+  // the RIGHT-HAND-SIDE chain (forward / backward sweeps with K_0U, S_U, T, Y_T) runs on `sr`; they only meet
+  // at the factor blocks (sr waits for st) and at the very end.  Buffers are disjoint: sr writes Xh, Zw, G1,
+  // SU, Xc, Mreg/LT/LinvT/Tinv/te/YT/ye; st writes Ad, Bs, Ld, Linv, Lsub, Sel, Ptmp, Tm, g0e.
+  cudaStream_t sr = st;
+  if (g_multi_stream) {
+    if ((rc = ensure_aux_stream(p))) return rc;
+    sr = p->s2;
+  }
   // ---- level 1: eliminate the interiors (batched) -----------------------------------------------------
   if (P > 0) {
     potrf_trtri_blocked<T>(st, nI, Aint, nI, sPP, Lint, nI, sPP, LintInv, nI, sPP, nullptr, 0, (int)P, p->d_info);
     gemm<T>(st, 1, 0, nI, nI, nI, one, LintInv, nI, sPP, LintInv, nI, sPP, zero, Ainv, nI, sPP, (int)P);   // A_p^-1
+    CEIT_AFTER(st, sr);
     gemm<T>(st, 0, 0, nI, bmax, nI, one, Ainv, nI, sPP, Bt, bmax, sV, zero, Wn, bmax, sV, (int)P);          // W_p
     gemm<T>(st, 1, 0, bmax, bmax, nI, one, Bt, bmax, sV, Wn, bmax, sV, zero, Tm, bmax, sT, (int)P);         // Bt^T W
     const int64_t nd = (int64_t)h.m2_dst.size();
@@ -408,13 +441,14 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
       CEIT_COUNT_LAUNCH();
     }
     // right-hand sides: t_I = A^-1 K_IU (kept in the interior rows of Xh), r_C = K_CU - Bt^T t_I
-    gemm<T>(st, 0, 0, nI, nU, nI, one, Ainv, nI, sPP, K0U, nU, sX, zero, Xh, nU, sX, (int)P);
-    gemm<T>(st, 1, 0, bmax, nU, nI, one, Bt, bmax, sV, Xh, nU, sX, zero, G1, nU, sG, (int)P);
-    rc_gather_kernel<T><<<cdiv(nC, 8), 256, 0, st>>>(nC, (int)nU, p->d_rc_ptr, p->d_rc_src, G1, K0U + NI * nU,
+    gemm<T>(sr, 0, 0, nI, nU, nI, one, Ainv, nI, sPP, K0U, nU, sX, zero, Xh, nU, sX, (int)P);
+    gemm<T>(sr, 1, 0, bmax, nU, nI, one, Bt, bmax, sV, Xh, nU, sX, zero, G1, nU, sG, (int)P);
+    rc_gather_kernel<T><<<cdiv(nC, 8), 256, 0, sr>>>(nC, (int)nU, p->d_rc_ptr, p->d_rc_src, G1, K0U + NI * nU,
                                                      Zw + NI * nU);
     CEIT_COUNT_LAUNCH();
   } else {
-    CUDA_TRY(cudaMemcpyAsync(Zw, K0U, N0P * nU * es, cudaMemcpyDeviceToDevice, st));
+    CEIT_AFTER(st, sr);
+    CUDA_TRY(cudaMemcpyAsync(Zw, K0U, N0P * nU * es, cudaMemcpyDeviceToDevice, sr));
   }
   KERNEL_CHECK();
   // ---- level 2: block-tridiagonal Cholesky of M2 + forward substitution ----------------------------
@@ -426,13 +460,14 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
     T* Lk = Ld + h.offD[k];
     T* Lik = Linv + h.offD[k];
     potrf_trtri_blocked<T>(st, nk, Ak, nk, 0, Lk, nk, 0, Lik, nk, 0, tmpPanel, 0, 1, p->d_info);
+    CEIT_AFTER(st, sr);                  // Linv_k (and Lsub_{k-1}, W_p) are ready for the sweep
     if (k > 0) {
       const int64_t np = n_of(k - 1), rp = row_of(k - 1);
       // RHS_k -= Lsub_{k-1} Z_{k-1}   (Z_{k-1} lives in Xh rows of block k-1 during the forward sweep)
-      gemm<T>(st, 0, 0, nk, nU, np, mone, Lsub + h.offS[k - 1], np, 0, Xh + rp * nU, nU, 0, one, Zw + r0 * nU, nU, 0);
+      gemm<T>(sr, 0, 0, nk, nU, np, mone, Lsub + h.offS[k - 1], np, 0, Xh + rp * nU, nU, 0, one, Zw + r0 * nU, nU, 0);
     }
     // Z_k = Linv_k RHS_k
-    gemm<T>(st, 0, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
+    gemm<T>(sr, 0, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
     if (k + 1 < h.nb) {
       const int64_t nn = n_of(k + 1);
       // Lsub_k = B_k Linv_k^T ; A_{k+1} -= Lsub_k Lsub_k^T
@@ -441,17 +476,17 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
               nn, 0, 1, /*lower_only=*/1);
     }
   }
-  // backward sweep: X_k = Linv_k^T (Z_k - Lsub_k^T X_{k+1}); selected inverse blocks
+  // backward sweep (sr): X_k = Linv_k^T (Z_k - Lsub_k^T X_{k+1}); selected inverse blocks (st)
   for (int64_t k = h.nb - 1; k >= 0; --k) {
     const int64_t nk = n_of(k), r0 = row_of(k);
     T* Lik = Linv + h.offD[k];
     if (k + 1 < h.nb) {
       const int64_t nn = n_of(k + 1), rn = row_of(k + 1);
-      gemm<T>(st, 1, 0, nk, nU, nn, mone, Lsub + h.offS[k], nk, 0, Xh + rn * nU, nU, 0, one, Xh + r0 * nU, nU, 0);
+      gemm<T>(sr, 1, 0, nk, nU, nn, mone, Lsub + h.offS[k], nk, 0, Xh + rn * nU, nU, 0, one, Xh + r0 * nU, nU, 0);
     }
     // in-place is not allowed in the GEMM: go through Zw rows of this block
-    CUDA_TRY(cudaMemcpyAsync(Zw + r0 * nU, Xh + r0 * nU, nk * nU * es, cudaMemcpyDeviceToDevice, st));
-    gemm<T>(st, 1, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
+    CUDA_TRY(cudaMemcpyAsync(Zw + r0 * nU, Xh + r0 * nU, nk * nU * es, cudaMemcpyDeviceToDevice, sr));
+    gemm<T>(sr, 1, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
     // Sd_k = Linv_k^T Linv_k
     gemm<T>(st, 1, 0, nk, nk, nk, one, Lik, nk, 0, Lik, nk, 0, zero, Sd + h.offD[k], nk, 0);
     if (k + 1 < h.nb) {
@@ -462,43 +497,47 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
       gemm<T>(st, 1, 0, nk, nk, nn, mone, Ptmp, nk, 0, So + h.offS[k], nk, 0, one, Sd + h.offD[k], nk, 0);
     }
   }
-  // ---- back to the interiors: x_I = t_I - W x_C[bnd], selected inverse blocks ------------------------
+  // ---- back to the interiors: x_I = t_I - W x_C[bnd] (sr), selected inverse blocks (st) ----------------
   if (P > 0) {
-    bnd_rows_gather_kernel<T><<<cdiv(P * bmax, 8), 256, 0, st>>>(P * bmax, (int)nU, p->d_bnd_loc, Xh + NI * nU, G1);
+    if (h.nb == 0) CEIT_AFTER(st, sr);   // W_p (no separator block ordered the streams yet)
+    bnd_rows_gather_kernel<T><<<cdiv(P * bmax, 8), 256, 0, sr>>>(P * bmax, (int)nU, p->d_bnd_loc, Xh + NI * nU, G1);
     CEIT_COUNT_LAUNCH();
-    gemm<T>(st, 0, 0, nI, nU, bmax, mone, Wn, bmax, sV, G1, nU, sG, one, Xh, nU, sX, (int)P);
+    gemm<T>(sr, 0, 0, nI, nU, bmax, mone, Wn, bmax, sV, G1, nU, sG, one, Xh, nU, sX, (int)P);
     gather_g0_kernel<T><<<cdiv(P * sT, 256), 256, 0, st>>>(P * sT, p->d_sg_off, Sel, Tm);        // Sigma2 on the cliques
     CEIT_COUNT_LAUNCH();
     gemm<T>(st, 0, 0, nI, bmax, bmax, mone, Wn, bmax, sV, Tm, bmax, sT, zero, Vneg, bmax, sV, (int)P);   // -W Sg
     CUDA_TRY(cudaMemcpyAsync(SigPP, Ainv, h.szPP * es, cudaMemcpyDeviceToDevice, st));
     gemm<T>(st, 0, 1, nI, nI, bmax, mone, Vneg, bmax, sV, Wn, bmax, sV, one, SigPP, nI, sPP, (int)P);    // + V W^T
   }
-  // S_U = K_UU - K_0U^T X  (small output, long inner dimension: split-K on the real path)
-  schur_u_gemm(p, st, nU, N0P, K0U, Xh, SU);
-  compact_rows_kernel<T><<<cdiv(h.N0, 8), 256, 0, st>>>(h.N0, (int)nU, p->d_row_map, Xh, Xc);
-  CEIT_COUNT_LAUNCH();
-  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, st>>>((int)nU, Xc + h.N0 * nU);
-  CEIT_COUNT_LAUNCH();
   gather_g0_kernel<T><<<cdiv(6 * h.E, 256), 256, 0, st>>>(6 * h.E, p->d_g0_off, Sel, g0e);
+  CEIT_COUNT_LAUNCH();
+  // S_U = K_UU - K_0U^T X  (small output, long inner dimension: split-K on the real path)
+  schur_u_gemm(p, sr, nU, N0P, K0U, Xh, SU);
+  compact_rows_kernel<T><<<cdiv(h.N0, 8), 256, 0, sr>>>(h.N0, (int)nU, p->d_row_map, Xh, Xc);
+  CEIT_COUNT_LAUNCH();
+  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>((int)nU, Xc + h.N0 * nU);
   CEIT_COUNT_LAUNCH();
   if (use_rank_update(p)) {
     // T = (S_U + gamma e e^T)^-1, t_e = T e, Y_T = Xh T, y_e = Y_T e: shared by every excitation
     T *Mreg = (T*)p->Mreg, *LT = (T*)p->LT, *LinvT = (T*)p->LinvT, *Tinv = (T*)p->Tinv, *te = (T*)p->te;
     T *YT = (T*)p->YT, *ye = (T*)p->ye;
-    trace_gamma_kernel<T><<<1, 256, 0, st>>>((int)nU, SU, p->d_gamma);
+    trace_gamma_kernel<T><<<1, 256, 0, sr>>>((int)nU, SU, p->d_gamma);
     CEIT_COUNT_LAUNCH();
-    add_rank1_e_kernel<T><<<cdiv(nU * nU, 256), 256, 0, st>>>((int)nU, SU, p->d_gamma, Mreg);
+    add_rank1_e_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>((int)nU, SU, p->d_gamma, Mreg);
     CEIT_COUNT_LAUNCH();
-    CUDA_TRY(cudaMemsetAsync(LT, 0, nU * nU * es, st));
-    CUDA_TRY(cudaMemsetAsync(LinvT, 0, nU * nU * es, st));
-    potrf_trtri_blocked<T>(st, nU, Mreg, nU, 0, LT, nU, 0, LinvT, nU, 0, (T*)p->Zw /* free by now */, 0, 1, p->d_info);
-    gemm<T>(st, 1, 0, nU, nU, nU, one, LinvT, nU, 0, LinvT, nU, 0, zero, Tinv, nU, 0);
-    rowsum_e_kernel<T><<<cdiv(nU, 8), 256, 0, st>>>(nU, (int)nU, Tinv, te);
+    CUDA_TRY(cudaMemsetAsync(LT, 0, nU * nU * es, sr));
+    CUDA_TRY(cudaMemsetAsync(LinvT, 0, nU * nU * es, sr));
+    potrf_trtri_blocked<T>(sr, nU, Mreg, nU, 0, LT, nU, 0, LinvT, nU, 0, (T*)p->Zw /* free by now */, 0, 1, p->d_info);
+    gemm<T>(sr, 1, 0, nU, nU, nU, one, LinvT, nU, 0, LinvT, nU, 0, zero, Tinv, nU, 0);
+    rowsum_e_kernel<T><<<cdiv(nU, 8), 256, 0, sr>>>(nU, (int)nU, Tinv, te);
     CEIT_COUNT_LAUNCH();
-    gemm<T>(st, 0, 0, h.N, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);
-    rowsum_e_kernel<T><<<cdiv(h.N, 8), 256, 0, st>>>(h.N, (int)nU, YT, ye);
+    gemm<T>(sr, 0, 0, h.N, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);
+    rowsum_e_kernel<T><<<cdiv(h.N, 8), 256, 0, sr>>>(h.N, (int)nU, YT, ye);
     CEIT_COUNT_LAUNCH();
+    CEIT_AFTER(sr, st);
     launch_g1(p, g0e, YT, Xc, st);
+  } else {
+    CEIT_AFTER(sr, st);
   }
   KERNEL_CHECK();
   p->mode = Sc<T>::is_complex ? 2 : 1;
@@ -514,6 +553,7 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
   T *phi0 = (T*)p->phi0, *tvec = (T*)p->tvec, *tmpS = (T*)p->tmpS, *Xh = (T*)p->Xh, *SU = (T*)p->SU;
   const T one = Sc<T>::one(), zero = Sc<T>::zero();
   const size_t es = sizeof(T);
+  cudaStream_t sx = st;
   if (use_rank_update(p)) {
     // rank-(b+1) update of the shared inverse T (kernels.cuh): no per-excitation nU x nU factorisation
     const int bp = h.bp;
@@ -537,7 +577,7 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
     }
     excite_small_kernel<T><<<nbatch, 256, sm1, st>>>((int)nU, bp, Tinv, te, LinvB, p->d_ue_ptr, i0, p->d_gamma, Dcat);
     CEIT_COUNT_LAUNCH();
-    auto update = [&](int64_t rows, const T* src, const T* yv, int zero_rows, T* out, int64_t stride) {
+    auto update = [&](cudaStream_t su, int64_t rows, const T* src, const T* yv, int zero_rows, T* out, int64_t stride) {
       // columns in chunks of <= 384 (3 per thread) so that the staged part of D_i stays small enough for
       // several CTAs per SM; D_i is staged once per CTA, so a CTA takes several row tiles, but keep >= 2 waves
       const int nz = (int)cdiv(nU, 384);
@@ -549,7 +589,7 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
       const int64_t slots = 148 * std::max<int64_t>(1, std::min<int64_t>(2, (200 * 1024) / (int64_t)smu));
       const int passes = (int)std::max<int64_t>(1, std::min<int64_t>(8, (tiles * nbatch * nz) / (2 * slots)));
       dim3 grid(nbatch, cdiv(tiles, passes), nz);
-#define CEIT_RU(c) rank_update_kernel<T, c><<<grid, 256, smu, st>>>(rows, (int)nU, bp, src, yv, Dcat, p->d_ue_ptr, i0, \
+#define CEIT_RU(c) rank_update_kernel<T, c><<<grid, 256, smu, su>>>(rows, (int)nU, bp, src, yv, Dcat, p->d_ue_ptr, i0, \
                                                                   zero_rows, out, stride, passes, cw)
       if (cpt <= 1) CEIT_RU(1);
       else if (cpt == 2) CEIT_RU(2);
@@ -557,11 +597,17 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
 #undef CEIT_RU
       CEIT_COUNT_LAUNCH();
     };
-    update(nU, Tinv, te, 1, Sinv, u2);
-    update(N, YT, ye, 0, Yh, N * nU);
+    update(st, nU, Tinv, te, 1, Sinv, u2);
+    // the big materialisation Yh_i (st) runs beside ZW and the baseline potentials (sx), which only need Sinv
+    if (g_multi_stream) {
+      if (int rc_ = ensure_aux_stream(p)) return rc_;
+      sx = p->s2;
+      CEIT_AFTER(st, sx);
+    }
+    update(st, N, YT, ye, 0, Yh, N * nU);
     // ZW_i = Xh Dcat_i^T (N x (bp+1)): the rank-(b+1) correction of the element blocks (woodbury_lr_kernel)
     // all excitations of the chunk in one product: Dcat is a (nbatch (bp+1)) x nU matrix
-    gemm<T>(st, 0, 1, N, (int64_t)nbatch * (bp + 1), nU, one, Xh, nU, 0, Dcat, nU, 0, zero, (T*)p->ZW,
+    gemm<T>(sx, 0, 1, N, (int64_t)nbatch * (bp + 1), nU, one, Xh, nU, 0, Dcat, nU, 0, zero, (T*)p->ZW,
             (int64_t)nbatch * (bp + 1), 0, 1);
   } else {
   dim3 g2(cdiv(u2, 256), nbatch);
@@ -577,17 +623,18 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
   gemm<T>(st, 0, 0, N, nU, nU, one, Xh, nU, 0, Sinv, nU, u2, zero, Yh, nU, N * nU, nbatch);
   }
   dim3 g3(cdiv(nU, 8), nbatch);
-  phi_u_kernel<T><<<g3, 256, 0, st>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 0);
+  phi_u_kernel<T><<<g3, 256, 0, sx>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 0);
   CEIT_COUNT_LAUNCH();
-  phi_u_kernel<T><<<g3, 256, 0, st>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 1);
+  phi_u_kernel<T><<<g3, 256, 0, sx>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 1);
   CEIT_COUNT_LAUNCH();
-  phi_u_kernel<T><<<g3, 256, 0, st>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 2);
+  phi_u_kernel<T><<<g3, 256, 0, sx>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 2);
   CEIT_COUNT_LAUNCH();
-  phi_u_kernel<T><<<g3, 256, 0, st>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 3);
+  phi_u_kernel<T><<<g3, 256, 0, sx>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 3);
   CEIT_COUNT_LAUNCH();
   dim3 g4(cdiv(N0, 8), nbatch);
-  phi_f_kernel<T><<<g4, 256, 0, st>>>(N0, (int)nU, Xh, phi0, N);
+  phi_f_kernel<T><<<g4, 256, 0, sx>>>(N0, (int)nU, Xh, phi0, N);
   CEIT_COUNT_LAUNCH();
+  CEIT_AFTER(sx, st);
   KERNEL_CHECK();
   return 0;
 }
@@ -764,6 +811,12 @@ int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_
 
 int ceit_plan_destroy(ceit_plan_t* p) {
   if (!p) return CEIT_OK;
+  if (p->s2) {
+    cudaStreamSynchronize(p->s2);
+    cudaStreamDestroy(p->s2);
+    for (auto e : p->ev_ring)
+      if (e) cudaEventDestroy(e);
+  }
   for (void* a : p->allocs)
     if (a) cudaFree(a);
   delete p;
@@ -1075,6 +1128,10 @@ int ceit_set_option(const char* name, int64_t value) {
   }
   if (std::strcmp(name, "nd_interior") == 0) {
     g_nd_interior = value;
+    return CEIT_OK;
+  }
+  if (std::strcmp(name, "multi_stream") == 0) {
+    g_multi_stream = (int)value;
     return CEIT_OK;
   }
   if (std::strcmp(name, "patch_nodes") == 0) {

@@ -146,7 +146,7 @@ struct ceit_plan {
   void *Ad = nullptr, *Bs = nullptr, *Ld = nullptr, *Linv = nullptr, *Lsub = nullptr, *Sel = nullptr;
   void *K0U = nullptr, *Zw = nullptr, *Xh = nullptr, *XP = nullptr, *KUU = nullptr, *SU = nullptr, *Ptmp = nullptr;
   int32_t* d_row_map = nullptr;
-  void *tmpPanel = nullptr, *g0e = nullptr;
+  void *tmpPanel = nullptr, *g0e = nullptr, *tmpT = nullptr;
   void *Aint = nullptr, *Lint = nullptr, *LintInv = nullptr, *Ainv = nullptr, *Bt = nullptr, *Wn = nullptr;
   void *Tm = nullptr, *G1 = nullptr;
   void *Mreg = nullptr, *LT = nullptr, *LinvT = nullptr, *Tinv = nullptr, *te = nullptr, *YT = nullptr, *ye = nullptr;
@@ -154,7 +154,8 @@ struct ceit_plan {
   void* splitk_ws = nullptr;
   // auxiliary stream + events: independent chains of a stage (right-hand-side sweep vs selected inverse, ...)
   // run concurrently and join before the stage ends; also valid under stream capture (fork/join in the graph)
-  cudaStream_t s2 = nullptr;
+  cudaStream_t s2 = nullptr, s3 = nullptr;
+  SideLane lane_a, lane_b;   // Linv row blocks of the blocked factorisations on st / on s3
   cudaEvent_t ev_ring[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int ev_next = 0;
   void* g1e = nullptr;
@@ -250,7 +251,7 @@ int alloc_numeric(ceit_plan* p) {
   const int want = Sc<T>::is_complex ? 2 : 1;
   if (p->alloc_mode == want) return 0;
   void** bufs[] = {&p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
-                   &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->g0e, &p->Aint, &p->Lint,
+                   &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->tmpT, &p->g0e, &p->Aint, &p->Lint,
                    &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1, &p->XP, &p->Mreg, &p->LT,
                    &p->LinvT, &p->Tinv, &p->te, &p->YT, &p->ye, &p->splitk_ws, &p->g1e};
   for (auto b : bufs) dev_free_tracked(p, *b);
@@ -297,6 +298,7 @@ int alloc_numeric(ceit_plan* p) {
   if ((rc = dev_alloc(p, &p->SU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Ptmp, maxS * es))) return rc;
   if ((rc = dev_alloc(p, &p->tmpPanel, (int64_t)TILE * h.max_block * es))) return rc;
+  if ((rc = dev_alloc(p, &p->tmpT, (int64_t)TILE * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->g0e, 6 * h.E * es))) return rc;
   p->alloc_mode = want;
   return 0;
@@ -348,10 +350,20 @@ inline int stream_after(ceit_plan* p, cudaStream_t from, cudaStream_t to) {
 inline int ensure_aux_stream(ceit_plan* p) {
   if (p->s2) return 0;
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s2, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->s3, cudaStreamNonBlocking));
+  CUDA_TRY(p->lane_a.init());
+  CUDA_TRY(p->lane_b.init());
   for (auto& e : p->ev_ring) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return 0;
 }
 #define CEIT_AFTER(from, to) do { int rc_ = stream_after(p, from, to); if (rc_) return rc_; } while (0)
+
+// lane for the plan-less inverse-model entry points (one per calling thread)
+inline SideLane* inv_lane() {
+  static thread_local SideLane lane;
+  if (!g_multi_stream) return nullptr;
+  return lane.init() == cudaSuccess ? &lane : nullptr;
+}
 
 inline bool rank_update_shape_ok(const HostPlan& h) {
   return h.u_contiguous && h.bp <= 64 && h.nU <= 1024 && h.nU > h.bp;
@@ -459,7 +471,8 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
     T* Ak = Ad + h.offD[k];
     T* Lk = Ld + h.offD[k];
     T* Lik = Linv + h.offD[k];
-    potrf_trtri_blocked<T>(st, nk, Ak, nk, 0, Lk, nk, 0, Lik, nk, 0, tmpPanel, 0, 1, p->d_info);
+    potrf_trtri_blocked<T>(st, nk, Ak, nk, 0, Lk, nk, 0, Lik, nk, 0, tmpPanel, 0, 1, p->d_info,
+                           g_multi_stream ? &p->lane_a : nullptr);
     CEIT_AFTER(st, sr);                  // Linv_k (and Lsub_{k-1}, W_p) are ready for the sweep
     if (k > 0) {
       const int64_t np = n_of(k - 1), rp = row_of(k - 1);
@@ -475,6 +488,32 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
       gemm<T>(st, 0, 1, nn, nn, nk, mone, Lsub + h.offS[k], nk, 0, Lsub + h.offS[k], nk, 0, one, Ad + h.offD[k + 1],
               nn, 0, 1, /*lower_only=*/1);
     }
+  }
+  // S_U = K_UU - K_0U^T K00^-1 K_0U = K_UU - K_IU^T t_I - Z_C^T Z_C is complete after the FORWARD sweep (t_I and Z
+  // still sit in Xh), so T = (S_U + gamma e e^T)^-1, the longest chain of the stage, starts here on its own
+  // stream (s_t) beside the backward sweep (sr) and the selected inverse (st).  Small outputs with long inner
+  // dimensions: split-K on the real path.
+  if (P > 0) schur_u_gemm(p, sr, nU, NI, K0U, Xh, SU);
+  if (nC > 0) schur_u_gemm(p, sr, nU, nC, Xh + NI * nU, Xh + NI * nU, SU);
+  cudaStream_t s_t = sr;
+  if (g_multi_stream) {
+    s_t = p->s3;
+    CEIT_AFTER(sr, s_t);
+  }
+  if (use_rank_update(p)) {
+    // T, t_e = T e: shared by every excitation (Y_T = Xh T and y_e = Y_T e follow once X is complete)
+    T *Mreg = (T*)p->Mreg, *LT = (T*)p->LT, *LinvT = (T*)p->LinvT, *Tinv = (T*)p->Tinv, *te = (T*)p->te;
+    trace_gamma_kernel<T><<<1, 256, 0, s_t>>>((int)nU, SU, p->d_gamma);
+    CEIT_COUNT_LAUNCH();
+    add_rank1_e_kernel<T><<<cdiv(nU * nU, 256), 256, 0, s_t>>>((int)nU, SU, p->d_gamma, Mreg);
+    CEIT_COUNT_LAUNCH();
+    CUDA_TRY(cudaMemsetAsync(LT, 0, nU * nU * es, s_t));
+    CUDA_TRY(cudaMemsetAsync(LinvT, 0, nU * nU * es, s_t));
+    potrf_trtri_blocked<T>(s_t, nU, Mreg, nU, 0, LT, nU, 0, LinvT, nU, 0, (T*)p->tmpT, 0, 1, p->d_info,
+                           g_multi_stream ? &p->lane_b : nullptr);
+    gemm<T>(s_t, 1, 0, nU, nU, nU, one, LinvT, nU, 0, LinvT, nU, 0, zero, Tinv, nU, 0);
+    rowsum_e_kernel<T><<<cdiv(nU, 8), 256, 0, s_t>>>(nU, (int)nU, Tinv, te);
+    CEIT_COUNT_LAUNCH();
   }
   // backward sweep (sr): X_k = Linv_k^T (Z_k - Lsub_k^T X_{k+1}); selected inverse blocks (st)
   for (int64_t k = h.nb - 1; k >= 0; --k) {
@@ -511,32 +550,20 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   }
   gather_g0_kernel<T><<<cdiv(6 * h.E, 256), 256, 0, st>>>(6 * h.E, p->d_g0_off, Sel, g0e);
   CEIT_COUNT_LAUNCH();
-  // S_U = K_UU - K_0U^T X  (small output, long inner dimension: split-K on the real path)
-  schur_u_gemm(p, sr, nU, N0P, K0U, Xh, SU);
   compact_rows_kernel<T><<<cdiv(h.N0, 8), 256, 0, sr>>>(h.N0, (int)nU, p->d_row_map, Xh, Xc);
   CEIT_COUNT_LAUNCH();
   fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>((int)nU, Xc + h.N0 * nU);
   CEIT_COUNT_LAUNCH();
   if (use_rank_update(p)) {
-    // T = (S_U + gamma e e^T)^-1, t_e = T e, Y_T = Xh T, y_e = Y_T e: shared by every excitation
-    T *Mreg = (T*)p->Mreg, *LT = (T*)p->LT, *LinvT = (T*)p->LinvT, *Tinv = (T*)p->Tinv, *te = (T*)p->te;
-    T *YT = (T*)p->YT, *ye = (T*)p->ye;
-    trace_gamma_kernel<T><<<1, 256, 0, sr>>>((int)nU, SU, p->d_gamma);
-    CEIT_COUNT_LAUNCH();
-    add_rank1_e_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>((int)nU, SU, p->d_gamma, Mreg);
-    CEIT_COUNT_LAUNCH();
-    CUDA_TRY(cudaMemsetAsync(LT, 0, nU * nU * es, sr));
-    CUDA_TRY(cudaMemsetAsync(LinvT, 0, nU * nU * es, sr));
-    potrf_trtri_blocked<T>(sr, nU, Mreg, nU, 0, LT, nU, 0, LinvT, nU, 0, (T*)p->Zw /* free by now */, 0, 1, p->d_info);
-    gemm<T>(sr, 1, 0, nU, nU, nU, one, LinvT, nU, 0, LinvT, nU, 0, zero, Tinv, nU, 0);
-    rowsum_e_kernel<T><<<cdiv(nU, 8), 256, 0, sr>>>(nU, (int)nU, Tinv, te);
-    CEIT_COUNT_LAUNCH();
-    gemm<T>(sr, 0, 0, h.N, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);
+    T *Tinv = (T*)p->Tinv, *YT = (T*)p->YT, *ye = (T*)p->ye;
+    CEIT_AFTER(s_t, sr);
+    gemm<T>(sr, 0, 0, h.N, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);                 // Y_T = Xh T
     rowsum_e_kernel<T><<<cdiv(h.N, 8), 256, 0, sr>>>(h.N, (int)nU, YT, ye);
     CEIT_COUNT_LAUNCH();
     CEIT_AFTER(sr, st);
     launch_g1(p, g0e, YT, Xc, st);
   } else {
+    CEIT_AFTER(s_t, sr);
     CEIT_AFTER(sr, st);
   }
   KERNEL_CHECK();
@@ -814,6 +841,12 @@ int ceit_plan_destroy(ceit_plan_t* p) {
   if (p->s2) {
     cudaStreamSynchronize(p->s2);
     cudaStreamDestroy(p->s2);
+    if (p->s3) {
+      cudaStreamSynchronize(p->s3);
+      cudaStreamDestroy(p->s3);
+    }
+    p->lane_a.destroy();
+    p->lane_b.destroy();
     for (auto e : p->ev_ring)
       if (e) cudaEventDestroy(e);
   }
@@ -964,7 +997,7 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
     }
     add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, G, n);
     CEIT_COUNT_LAUNCH();
-    potrf_trtri_blocked<double>(st, n, G, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info);
+    potrf_trtri_blocked<double>(st, n, G, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info, inv_lane());
     gemm<double>(st, 1, 0, n, n, n, 1.0, Li, n, 0, Li, n, 0, 0.0, Gi, n, 0);
     gemm<double>(st, 1, 0, n_det, m_sel, m_sel, scale_, Jt, n_det, 0, Gi, n, 0, 0.0, inv_out, m_sel, 0);
   } else {
@@ -972,7 +1005,7 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
     gemm<double>(st, 1, 0, n, n, m_sel, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0, 1, /*lower_only=*/1);
     add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, G, n);
     CEIT_COUNT_LAUNCH();
-    potrf_trtri_blocked<double>(st, n, G, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info);
+    potrf_trtri_blocked<double>(st, n, G, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info, inv_lane());
     gemm<double>(st, 0, 1, n, m_sel, n, 1.0, Li, n, 0, Jt, n_det, 0, 0.0, Gi, m_sel, 0);
     gemm<double>(st, 1, 0, n, m_sel, n, scale_, Li, n, 0, Gi, m_sel, 0, 0.0, inv_out, m_sel, 0);
   }
@@ -1035,7 +1068,7 @@ int ceit_inverse_from_gram(const double* J, int64_t ldJ, int64_t m, const int64_
   CEIT_COUNT_LAUNCH();
   gather_shift_kernel<<<cdiv(m_sel * n_det, 256), 256, 0, st>>>(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
   CEIT_COUNT_LAUNCH();
-  potrf_trtri_blocked<double>(st, n, Gw, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info);
+  potrf_trtri_blocked<double>(st, n, Gw, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info, inv_lane());
   gemm<double>(st, 1, 0, n, n, n, 1.0, Li, n, 0, Li, n, 0, 0.0, Gi, n, 0);
   gemm<double>(st, 1, 0, n_det, m_sel, m_sel, scale_, Jt, n_det, 0, Gi, n, 0, 0.0, inv_out, m_sel, 0);
   KERNEL_CHECK();

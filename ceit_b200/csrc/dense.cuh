@@ -268,24 +268,70 @@ inline cudaError_t potrf_tile_prepare() {
   return e;
 }
 
+// A helper stream with its own event ring: work that is independent of the caller's next kernels is pushed to
+// `s` (order(from, s)) and joined back later (order(s, to)).  Valid under stream capture (fork / join branches).
+struct SideLane {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int next = 0;
+  cudaError_t init() {
+    if (s) return cudaSuccess;
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+    return e;
+  }
+  void destroy() {
+    if (!s) return;
+    cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    for (auto e : ev)
+      if (e) cudaEventDestroy(e);
+    s = nullptr;
+  }
+  // `to` waits for everything enqueued on `from` so far
+  cudaError_t order(cudaStream_t from, cudaStream_t to) {
+    if (from == to) return cudaSuccess;
+    cudaEvent_t e = ev[next];
+    next = (next + 1) & 7;
+    cudaError_t rc = cudaEventRecord(e, from);
+    return rc == cudaSuccess ? cudaStreamWaitEvent(to, e, 0) : rc;
+  }
+};
+
 // Blocked factorisation of `batch` n x n SPD / complex-symmetric matrices:
 //   A  (destroyed: trailing updates are applied in place), L and Linv must be ZERO-initialised by the
 //   caller above their block diagonal (they are treated as dense by the GEMMs that follow);
 //   tmp: workspace of at least TILE * n elements per batch entry (stride sT).
+//   lane (optional): the off-diagonal row blocks of Linv are not needed by the factorisation itself; with a
+//   lane, row block t is computed on the lane's stream right after tile t, beside the panel / trailing update
+//   of step t and the tiles that follow, and only the last row block remains after the last tile.
 template <class T>
 inline void potrf_trtri_blocked(cudaStream_t st, int64_t n, T* A, int64_t lda, int64_t sA, T* L,
                                 int64_t ldl, int64_t sL, T* Linv, int64_t ldi, int64_t sI, T* tmp,
-                                int64_t sT, int batch, int* info) {
+                                int64_t sT, int batch, int* info, SideLane* lane = nullptr) {
   if (n <= 0 || batch <= 0) return;
   potrf_tile_prepare<T>();
   const size_t smem = 3 * TILE * (TILE + 1) * sizeof(T);
   const T one = Sc<T>::one(), zero = Sc<T>::zero(), mone = neg(Sc<T>::one());
   const int64_t nt = (n + TILE - 1) / TILE;
+  if (nt < 3 || !lane || !lane->s) lane = nullptr;
+  cudaStream_t sl = lane ? lane->s : st;
+  // Linv row-block s, columns [0, o): Linv[s,0:s] = -Linv_ss * (L[s,0:s] * Linv[0:s,0:s])
+  auto linv_row = [&](int64_t s) {
+    const int64_t o = s * TILE, bs = (n - o < TILE) ? n - o : TILE;
+    gemm<T>(sl, 0, 0, bs, o, o, one, L + o * ldl, ldl, sL, Linv, ldi, sI, zero, tmp, o, sT, batch);
+    gemm<T>(sl, 0, 0, bs, o, bs, mone, Linv + o * ldi + o, ldi, sI, tmp, o, sT, zero, Linv + o * ldi, ldi, sI,
+            batch);
+  };
   for (int64_t t = 0; t < nt; ++t) {
     const int64_t o = t * TILE, bt = (n - o < TILE) ? n - o : TILE;
     potrf_trtri_tile_kernel<T><<<batch, 256, smem, st>>>((int)bt, A + o * lda + o, lda, sA, L + o * ldl + o, ldl, sL,
                                                          Linv + o * ldi + o, ldi, sI, info);
     CEIT_COUNT_LAUNCH();
+    if (lane && t >= 1) {
+      lane->order(st, sl);          // tile t (Linv_tt) and the panels L[t, 0:t] of the earlier steps
+      linv_row(t);
+    }
     const int64_t mr = n - o - bt;
     if (mr > 0) {
       const int64_t o2 = o + bt;
@@ -297,12 +343,10 @@ inline void potrf_trtri_blocked(cudaStream_t st, int64_t n, T* A, int64_t lda, i
               A + o2 * lda + o2, lda, sA, batch, /*lower_only=*/1);
     }
   }
-  // Linv row-block s, columns [0, o): Linv[s,0:s] = -Linv_ss * (L[s,0:s] * Linv[0:s,0:s])
-  for (int64_t s = 1; s < nt; ++s) {
-    const int64_t o = s * TILE, bs = (n - o < TILE) ? n - o : TILE;
-    gemm<T>(st, 0, 0, bs, o, o, one, L + o * ldl, ldl, sL, Linv, ldi, sI, zero, tmp, o, sT, batch);
-    gemm<T>(st, 0, 0, bs, o, bs, mone, Linv + o * ldi + o, ldi, sI, tmp, o, sT, zero, Linv + o * ldi, ldi, sI,
-            batch);
+  if (lane) {
+    lane->order(sl, st);
+  } else {
+    for (int64_t s = 1; s < nt; ++s) linv_row(s);
   }
 }
 

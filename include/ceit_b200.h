@@ -156,7 +156,23 @@ int ceit_stage_times(double* ms, int64_t* counts);
 /* debug: clock64 phase stamps of the last tile-factorisation CTA (only with -DCEIT_TILE_CLOCKS) */
 int ceit_debug_tile_clocks(int64_t* out8);
 
-/* debug/test switches: "force_simt_gemm" = 1 routes f64 GEMMs through the non-tensor kernel */
+/* switches (value 0/1 unless noted):
+ *   "stage_timers"      record CUDA events around every stage (ceit_stage_times); not capturable
+ *   "multi_stream"      (default 1) independent chains of a stage run on the plan's helper streams and
+ *                       join before the call returns its work to `stream`; 0 = everything on `stream`
+ *   "nd_interior"       target nodes per nested-dissection interior for plans created afterwards (default 64)
+ *   "patch_nodes"       node cap of the element patches for plans created afterwards (0 = automatic)
+ *   "gemm_tile"         force the CTA tile of the DMMA GEMM (32 / 64 / 128, 0 = automatic)
+ *   "force_simt_gemm", "direct_excitation", "no_patch_kernel", "no_lowrank_kernel"
+ *                       route around the tensor-core GEMM / rank-update excitation stage / patch Woodbury
+ *                       kernels (test coverage of the fallback kernels)
+ *
+ * CUDA graphs: after ONE eager call sequence (the library allocates its workspaces on first use), any
+ * sequence of ceit_assemble / ceit_factor / ceit_jacobian_block / ceit_forward / ceit_inverse_model /
+ * ceit_reconstruct calls on one stream may be captured with cudaStreamBeginCapture and replayed: no entry
+ * point synchronises, the helper streams fork from and join back into `stream` with events, and the
+ * workspace of ceit_inverse_model comes from cudaMallocAsync (allocation nodes).  Replaying the ~140 short
+ * dependent kernels of a MESH_50_50 step from a graph removes ~0.2 ms of launch gaps (bench.py does). */
 int ceit_set_option(const char* name, int64_t value);
 
 #ifdef __cplusplus

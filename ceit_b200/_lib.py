@@ -18,6 +18,7 @@ SYMBOLS = [
     "ceit_plan_info", "ceit_plan_tables", "ceit_assemble", "ceit_factor", "ceit_jacobian_block",
     "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm", "ceit_plan_csr_values",
     "ceit_set_option", "ceit_stage_times", "ceit_gram_partial", "ceit_inverse_from_gram", "ceit_debug_tile_clocks", "ceit_zgemm",
+    "ceit_center_of_position",
 ]
 
 
@@ -63,6 +64,7 @@ def lib():
     L.ceit_gram_partial.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_vp]
     L.ceit_inverse_from_gram.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp]
     L.ceit_debug_tile_clocks.argtypes = [c_vp]
+    L.ceit_center_of_position.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_dbl, c_vp, c_vp]
     L.ceit_zgemm.argtypes = [c_int, c_int, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl,
                              c_vp, c_i64, c_vp]
     for name in SYMBOLS:
@@ -270,6 +272,18 @@ def reconstruct(inv, dV, out=None):
     if out is None:
         out = torch.empty((n_det,) if dV.dim() == 1 else (n_det, F), dtype=torch.float64, device=inv.device)
     check(lib().ceit_reconstruct(tptr(inv), tptr(dV), tptr(out), n_det, m, F, stream_ptr()))
+    return out
+
+
+def center_of_position(maps, cx, cy, frac=0.9, out=None):
+    """Batched DataPlotter.get_COP: maps (n_det,) or (n_det, F) cuda f64 -> (F, 4) = x, y, v means and count."""
+    torch = require_cuda()
+    m2 = maps if maps.dim() == 2 else maps.reshape(-1, 1)
+    assert m2.is_contiguous() and m2.dtype == torch.float64 and cx.numel() == m2.shape[0] == cy.numel()
+    n_det, F = m2.shape
+    if out is None:
+        out = torch.empty((F, 4), dtype=torch.float64, device=m2.device)
+    check(lib().ceit_center_of_position(tptr(m2), n_det, F, tptr(cx), tptr(cy), float(frac), tptr(out), stream_ptr()))
     return out
 
 

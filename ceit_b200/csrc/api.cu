@@ -1098,6 +1098,17 @@ int ceit_reconstruct(const double* inv, const double* dV, double* out, int64_t n
   return CEIT_OK;
 }
 
+int ceit_center_of_position(const double* maps, int64_t n_det, int64_t F, const double* cx, const double* cy,
+                            double frac, double* out, void* stream) {
+  if (!maps || !cx || !cy || !out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_center_of_position: null argument");
+  if (n_det <= 0 || F <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_center_of_position: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  cop_frames_kernel<<<cdiv(F, 32), 256, 0, st>>>(n_det, F, maps, cx, cy, frac, out);
+  CEIT_COUNT_LAUNCH();
+  KERNEL_CHECK();
+  return CEIT_OK;
+}
+
 int ceit_dgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                const double* B, int64_t ldb, double beta, double* C, int64_t ldc, void* stream) {
   if (!A || !B || !C) CEIT_FAIL(CEIT_ERR_ARG, "ceit_dgemm: null argument");

@@ -1059,4 +1059,67 @@ gemv_rows_kernel(int64_t n_det, int m, const double* __restrict__ inv, const dou
   if (lane == 0) out[row] = acc;
 }
 
+// Centre of position of reconstructed maps (DataHandler.get_COP, CEIT/datahandler/DataHandler.py:28-56), batched:
+// maps[n_det][F] row-major (the layout ceit_reconstruct writes).  Per frame: threshold = frac max + (1 - frac) min,
+// then the mean centroid (cx, cy) and mean value of the detection elements strictly above it.
+// CTA = 32 consecutive frames (one per lane: coalesced row reads) x 8 warps over the rows; the warps' partial
+// results are combined in warp order, so the result does not depend on scheduling.  out[F][4] = x, y, v, count.
+__global__ void __launch_bounds__(256)
+cop_frames_kernel(int64_t n_det, int64_t F, const double* __restrict__ maps, const double* __restrict__ cx,
+                  const double* __restrict__ cy, double frac, double* __restrict__ out) {
+  __shared__ double red[4][8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t f = (int64_t)blockIdx.x * 32 + lane;
+  const bool ok = f < F;
+  double vmax = -INFINITY, vmin = INFINITY;
+  if (ok) {
+    for (int64_t r = warp; r < n_det; r += 8) {
+      const double v = maps[r * F + f];
+      vmax = fmax(vmax, v);
+      vmin = fmin(vmin, v);
+    }
+  }
+  red[0][warp][lane] = vmax;
+  red[1][warp][lane] = vmin;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    vmax = fmax(vmax, red[0][w][lane]);
+    vmin = fmin(vmin, red[1][w][lane]);
+  }
+  __syncthreads();
+  const double th = vmax * frac + vmin * (1.0 - frac);
+  double sx = 0.0, sy = 0.0, sv = 0.0, cnt = 0.0;
+  if (ok) {
+    for (int64_t r = warp; r < n_det; r += 8) {
+      const double v = maps[r * F + f];
+      if (v > th) {
+        sx += cx[r];
+        sy += cy[r];
+        sv += v;
+        cnt += 1.0;
+      }
+    }
+  }
+  red[0][warp][lane] = sx;
+  red[1][warp][lane] = sy;
+  red[2][warp][lane] = sv;
+  red[3][warp][lane] = cnt;
+  __syncthreads();
+  if (warp == 0 && ok) {
+    sx = sy = sv = cnt = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      sx += red[0][w][lane];
+      sy += red[1][w][lane];
+      sv += red[2][w][lane];
+      cnt += red[3][w][lane];
+    }
+    out[4 * f + 0] = sx / cnt;
+    out[4 * f + 1] = sy / cnt;
+    out[4 * f + 2] = sv / cnt;
+    out[4 * f + 3] = cnt;
+  }
+}
+
 }  // namespace ceit

@@ -136,6 +136,17 @@ int ceit_inverse_from_gram(const double* J, int64_t ldJ, int64_t m, const int64_
 int ceit_reconstruct(const double* inv, const double* dV, double* out, int64_t n_det, int64_t m,
                      int64_t F, void* stream);
 
+/* ---- consumer of the reconstructed maps: centre of position -------------------------------------------
+ * Replaces DataPlotter.get_COP (CEIT/datahandler/DataHandler.py:28-56), batched over frames:
+ * threshold = frac * max + (1 - frac) * min of a frame (the reference's THRESHOLD_PERCENTAGE = 0.9), then the
+ * mean of (cx, cy, value) over the detection elements strictly above it.
+ * maps [dev] f64[n_det*F] row-major (what ceit_reconstruct writes); cx, cy [dev] f64[n_det]: centroid coordinates
+ * of the detection elements (elem_param[detection_index][7|8], CEIT/models/mesh.py:70-71);
+ * out [dev] f64[F*4] = x_mean, y_mean, v_mean, count per frame (count = 0 gives NaN means, where the reference
+ * raises ZeroDivisionError). */
+int ceit_center_of_position(const double* maps, int64_t n_det, int64_t F, const double* cx, const double* cy,
+                            double frac, double* out, void* stream);
+
 /* ---- generic dense helper exposed for tests/benchmarks: C = alpha op(A) op(B) + beta C ---------
  * row-major f64, op: 0 = N, 1 = T. Uses the same DMMA kernel as the factorisation. */
 int ceit_dgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, const double* A,

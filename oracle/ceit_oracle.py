@@ -264,3 +264,33 @@ def inverse_model_dual(J, det_index, lmbda):
 def reconstruct(inv_mat, delta_V):
     """Solver.solve, Solver.py:95-108: np.dot(inv_mat, delta_V); (m,) or (m,F)."""
     return np.dot(inv_mat, delta_V)
+
+
+# ---------------------------------------------------------------------------------------------------
+# datahandler row of SURVEY.md 8(f): the consumers of Solver.solve outputs
+# ---------------------------------------------------------------------------------------------------
+def recording_mean(data, electrode_num=16, contain_excitation=False):
+    """BasicData.__init__ / exclude_excitation (CEIT/datahandler/Data.py:18-30): mean over the recorded
+    samples (rows); with contain_excitation the channels i with i % electrode_num == 0 are dropped."""
+    mean = np.mean(np.asarray(data), axis=0)
+    if contain_excitation:
+        mean = np.array([v for i, v in enumerate(mean) if i % electrode_num != 0])
+    return mean
+
+
+def center_of_position(capacitance, detection_index, elem_param, threshold_percentage=0.9):
+    """DataPlotter.get_COP after the solve (CEIT/datahandler/DataHandler.py:41-56): threshold between min and
+    max, then the mean centroid / value of the detection elements strictly above it, accumulated in index order
+    like the reference's loop.  Raises ZeroDivisionError (as the reference does) when nothing passes."""
+    capacitance = np.asarray(capacitance, dtype=np.float64)
+    threshold = np.max(capacitance) * threshold_percentage + np.min(capacitance) * (1 - threshold_percentage)
+    x_sum = y_sum = v_sum = 0.0
+    count = 0.0
+    for i, c in enumerate(capacitance):
+        if c > threshold:
+            idx = detection_index[i]
+            x_sum += elem_param[idx][7]
+            y_sum += elem_param[idx][8]
+            v_sum += c
+            count += 1
+    return x_sum / count, y_sum / count, v_sum / count

@@ -611,10 +611,12 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
       const int cw = (int)cdiv(nU, nz);
       const int cpt = (cw + 127) / 128;
       const int rt = Sc<T>::is_complex ? 8 : 16;                             // rows per pass (kernel: 2 RH)
-      const size_t smu = (size_t)((bp + 1) * cw + 16 * (bp + 1)) * es;
+      const size_t smu = (size_t)((bp + 1) * 128 * cpt + 16 * (bp + 1)) * es;
       const int64_t tiles = cdiv(rows, rt);
+      // one wave of persistent-style CTAs: D_i is staged once per CTA, each CTA walks `passes` row tiles
       const int64_t slots = 148 * std::max<int64_t>(1, std::min<int64_t>(2, (200 * 1024) / (int64_t)smu));
-      const int passes = (int)std::max<int64_t>(1, std::min<int64_t>(8, (tiles * nbatch * nz) / (2 * slots)));
+      const int64_t groups = std::max<int64_t>(1, slots / ((int64_t)nbatch * nz));     // CTAs per (excitation, chunk)
+      const int passes = (int)std::max<int64_t>(1, cdiv(tiles, groups));
       dim3 grid(nbatch, cdiv(tiles, passes), nz);
 #define CEIT_RU(c) rank_update_kernel<T, c><<<grid, 256, smu, su>>>(rows, (int)nU, bp, src, yv, Dcat, p->d_ue_ptr, i0, \
                                                                   zero_rows, out, stride, passes, cw)

@@ -35,6 +35,18 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, 
   const int sz = valid ? 8 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+// one element of either scalar type (zero fill when !valid)
+__device__ __forceinline__ void cp_async_elem(double* smem_dst, const double* gsrc, bool valid) {
+  cp_async8(smem_dst, gsrc, valid);
+}
+__device__ __forceinline__ void cp_async_elem(cd* smem_dst, const cd* gsrc, bool valid) {
+  cp_async16(smem_dst, gsrc, valid);
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

@@ -338,71 +338,89 @@ rank_update_kernel(int64_t rows, int nU, int bp, const T* __restrict__ src, cons
                    T* __restrict__ out, int64_t out_stride, int passes, int cw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int RH = Sc<T>::is_complex ? 4 : 8;   // rows per thread
-  constexpr int RT = 2 * RH;                       // rows per pass
-  T* Ds = reinterpret_cast<T*>(smem_raw);   // [(bp+1)][cw]   columns [k_lo, k_lo + cw) of D_i
-  T* As = Ds + (int64_t)(bp + 1) * cw;      // [RT][bp+1]
+  constexpr int RT = 2 * RH;                       // rows per pass (power of two)
+  constexpr int CWP = 128 * CPT;                   // padded chunk width: no column predicates in the inner loop
   const int tid = threadIdx.x, tx = tid & 127, ty = tid >> 7;
   const int i = i0 + blockIdx.x;      // excitation fastest: the CTAs that share a row tile of src run together
   const int lo = ue_ptr[i], b = ue_ptr[i + 1] - lo;
   const int k_lo = blockIdx.z * cw, kw = min(cw, nU - k_lo);
-  const T* D = Dcat + (int64_t)blockIdx.x * (bp + 1) * nU;
-  for (int t = tid; t < (bp + 1) * kw; t += 256) {
-    const int j = t / kw, k = t - j * kw;
-    Ds[j * cw + k] = D[(int64_t)j * nU + k_lo + k];
+  // compact copies: rows 0..b-1 of D_i and the alpha q row (stored as row b); As likewise [j][RT]
+  T* Ds = reinterpret_cast<T*>(smem_raw);   // [b+1][CWP], zero beyond kw
+  T* As = Ds + (int64_t)(bp + 1) * CWP;     // [b+1][RT]
+  const T* D = Dcat + (int64_t)blockIdx.x * (bp + 1) * nU + k_lo;
+  for (int j = 0; j <= b; ++j) {          // cp.async: all rows in flight at once, zero fill beyond kw
+    const T* dr = D + (int64_t)(j < b ? j : bp) * nU;
+    for (int k = tid; k < CWP; k += 256) cp_async_elem(Ds + j * CWP + k, dr + (k < kw ? k : 0), k < kw);
   }
-  T* o = out + (int64_t)blockIdx.x * out_stride;
+  cp_async_commit();
+  bool keep[CPT];                       // column inside the chunk and not a Dirichlet column of this excitation
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int k = tx + 128 * c, kg = k_lo + k;
+    keep[c] = k < kw && !(kg >= lo && kg < lo + b);
+  }
+  T* o = out + (int64_t)blockIdx.x * out_stride + k_lo + tx;
+  const T* sbase = src + k_lo + tx;
   for (int ps = 0; ps < passes; ++ps) {
     const int64_t n0 = ((int64_t)blockIdx.y * passes + ps) * RT;
     if (n0 >= rows) break;
-    __syncthreads();                        // Ds staged / As of the previous pass consumed
-    for (int t = tid; t < RT * (bp + 1); t += 256) {
-      const int r = t / (bp + 1), j = t - r * (bp + 1);
-      const int64_t n = n0 + r;
-      T v = Sc<T>::zero();
-      if (n < rows) {
-        if (j < b) v = src[n * nU + lo + j];
-        else if (j == bp) v = neg(yv[n]);
-      }
-      As[t] = v;
+    __syncthreads();                        // As of the previous pass consumed
+    for (int t = tid; t < RT * (b + 1); t += 256) {
+      const int j = t / RT, r = t % RT;     // RT is a power of two
+      const int64_t n = n0 + r, nc = n < rows ? n : 0;
+      cp_async_elem(As + t, (j < b) ? src + nc * nU + lo + j : yv + nc, n < rows);
     }
+    cp_async_commit();
     T acc[RH][CPT];
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      const int k = tx + 128 * c;
+    {
+      const T* sp = sbase + (n0 + ty) * nU;
 #pragma unroll
       for (int r = 0; r < RH; ++r) {
-        const int64_t n = n0 + 2 * r + ty;
-        acc[r][c] = (k < kw && n < rows) ? src[n * nU + k_lo + k] : Sc<T>::zero();
+        const bool rok = n0 + 2 * r + ty < rows;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) acc[r][c] = (rok && tx + 128 * c < kw) ? sp[128 * c] : Sc<T>::zero();
+        sp += 2 * (int64_t)nU;
       }
     }
+    cp_async_wait<0>();
     __syncthreads();
-    for (int j = 0; j <= bp; ++j) {
-      if (j >= b && j < bp) continue;
-      T dv[CPT];
+    {
+      const T* dp = Ds + tx;
+      const T* ap = As + ty;
+#pragma unroll 2
+      for (int j = 0; j < b; ++j) {
+        T dv[CPT];
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        const int k = tx + 128 * c;
-        dv[c] = (k < kw) ? Ds[j * cw + k] : Sc<T>::zero();
+        for (int c = 0; c < CPT; ++c) dv[c] = dp[128 * c];
+#pragma unroll
+        for (int r = 0; r < RH; ++r) {
+          const T a = ap[2 * r];
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) acc[r][c] = sub(acc[r][c], mul(a, dv[c]));
+        }
+        dp += CWP;
+        ap += RT;
       }
+      // + y_e (alpha q)^T
 #pragma unroll
       for (int r = 0; r < RH; ++r) {
-        const T a = As[(2 * r + ty) * (bp + 1) + j];
+        const T a = ap[2 * r];
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) acc[r][c] = sub(acc[r][c], mul(a, dv[c]));
+        for (int c = 0; c < CPT; ++c) acc[r][c] = fma_(a, dp[128 * c], acc[r][c]);
       }
     }
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      const int k = tx + 128 * c;
-      if (k >= kw) continue;
-      const int kg = k_lo + k;
-      const bool colB = (kg >= lo && kg < lo + b);
+    {
+      T* op = o + (n0 + ty) * nU;
 #pragma unroll
       for (int r = 0; r < RH; ++r) {
         const int64_t n = n0 + 2 * r + ty;
-        if (n >= rows) continue;
-        const bool rowB = zero_rows && (n >= lo && n < lo + b);
-        o[n * nU + kg] = (colB || rowB) ? Sc<T>::zero() : acc[r][c];
+        if (n < rows) {
+          const bool rowB = zero_rows && (n >= lo && n < lo + b);
+#pragma unroll
+          for (int c = 0; c < CPT; ++c)
+            if (tx + 128 * c < kw) op[128 * c] = (keep[c] && !rowB) ? acc[r][c] : Sc<T>::zero();
+        }
+        op += 2 * (int64_t)nU;
       }
     }
   }

@@ -592,7 +592,9 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
     CUDA_TRY(cudaMemsetAsync(LinvB, 0, (int64_t)nbatch * bp * bp * es, st));
     potrf_trtri_blocked<T>(st, bp, TBB, bp, (int64_t)bp * bp, LB, bp, (int64_t)bp * bp, LinvB, bp, (int64_t)bp * bp,
                            nullptr, 0, nbatch, p->d_info);
-    const size_t sm1 = (size_t)(2 * bp * bp + bp + nU + 256) * es;
+    const size_t sm1_base = (size_t)(2 * bp * bp + bp + nU + 256 + 8 * bp) * es;
+    const int stage_rows = sm1_base + (size_t)bp * nU * es <= 200 * 1024;     // T[B_i,:] in shared memory if it fits
+    const size_t sm1 = sm1_base + (stage_rows ? (size_t)bp * nU * es : 0);
     static bool attr_done = false;
     if (!attr_done) {
       CUDA_TRY(cudaFuncSetAttribute(excite_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -602,7 +604,8 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
 #undef CEIT_RU_ATTR
       attr_done = true;
     }
-    excite_small_kernel<T><<<nbatch, 256, sm1, st>>>((int)nU, bp, Tinv, te, LinvB, p->d_ue_ptr, i0, p->d_gamma, Dcat);
+    excite_small_kernel<T><<<nbatch, 256, sm1, st>>>((int)nU, bp, Tinv, te, LinvB, p->d_ue_ptr, i0, p->d_gamma, Dcat,
+                                                    stage_rows);
     CEIT_COUNT_LAUNCH();
     auto update = [&](cudaStream_t su, int64_t rows, const T* src, const T* yv, int zero_rows, T* out, int64_t stride) {
       // columns in chunks of <= 384 (3 per thread) so that the staged part of D_i stays small enough for

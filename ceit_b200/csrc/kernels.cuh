@@ -254,23 +254,31 @@ __global__ void gather_tbb_kernel(int nU, int bp, const T* __restrict__ Tm, cons
   if (a < b && c < b) v = Tm[(int64_t)(lo + a) * nU + lo + c];
   out[(int64_t)blockIdx.y * bp * bp + q] = v;
 }
-// one CTA per excitation: Dcat[b] ((bp+1) x nU): rows j < b = D_i, row bp = alpha q, other rows 0
+// one CTA per excitation: Dcat[b] ((bp+1) x nU): rows j < b = D_i, row bp = alpha q, other rows 0.
+// The b rows T[B_i,:] are staged in shared memory once (cp.async); a thread owns columns k = tid, tid + 256, ...
+// and forms C[:,k] = T_BB^-1 T[B,k] in registers (8 rows at a time), so the kernel has no global-latency chains.
 template <class T>
 __global__ void __launch_bounds__(256)
 excite_small_kernel(int nU, int bp, const T* __restrict__ Tm, const T* __restrict__ te,
                     const T* __restrict__ LinvB, const int32_t* __restrict__ ue_ptr, int i0,
-                    const double* __restrict__ gamma, T* __restrict__ Dcat) {
+                    const double* __restrict__ gamma, T* __restrict__ Dcat, int stage_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Li = reinterpret_cast<T*>(smem_raw);   // [bp][bp]
   T* Bi = Li + bp * bp;                     // [bp][bp]  T_BB^-1
   T* ce = Bi + bp * bp;                     // [bp]
   T* q = ce + bp;                           // [nU]
   T* red = q + nU;                          // [256]
+  T* cep = red + 256;                       // [8][bp]   per-warp partial row sums of C
+  T* Tsm = cep + 8 * bp;                    // [b][nU]   T[B_i, :] (only when stage_rows: it must fit)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i = i0 + blockIdx.x;
   const int lo = ue_ptr[i], b = ue_ptr[i + 1] - lo;
   T* D = Dcat + (int64_t)blockIdx.x * (bp + 1) * nU;
   const T* Lg = LinvB + (int64_t)blockIdx.x * bp * bp;
+  const T* Ts = stage_rows ? Tsm : Tm + (int64_t)lo * nU;                                            // rows lo..lo+b-1
+  if (stage_rows)
+    for (int t = tid; t < b * nU; t += 256) cp_async_elem(Tsm + t, Tm + (int64_t)lo * nU + t, true);
+  cp_async_commit();
   for (int t = tid; t < bp * bp; t += 256) Li[t] = Lg[t];
   __syncthreads();
   for (int t = tid; t < bp * bp; t += 256) {
@@ -279,35 +287,56 @@ excite_small_kernel(int nU, int bp, const T* __restrict__ Tm, const T* __restric
     for (int k = (a > c ? a : c); k < bp; ++k) acc = fma_(Li[k * bp + a], Li[k * bp + c], acc);
     Bi[t] = acc;
   }
+  cp_async_wait<0>();
   __syncthreads();
-  // C = T_BB^-1 T[B,:]  (stored in D for now); rows >= b are zero
-  for (int t = tid; t < bp * nU; t += 256) {
-    const int j = t / nU, k = t - j * nU;
-    T acc = Sc<T>::zero();
-    if (j < b)
-      for (int m = 0; m < b; ++m) acc = fma_(Bi[j * bp + m], Tm[(int64_t)(lo + m) * nU + k], acc);
-    D[(int64_t)j * nU + k] = acc;
+  // C = T_BB^-1 T[B,:]  (stored in D for now); rows >= b are zero.  ce = C e from per-warp partial sums.
+  for (int j0 = 0; j0 < bp; j0 += 8) {
+    T rs[8];
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) rs[jj] = Sc<T>::zero();
+    for (int k = tid; k < nU; k += 256) {
+      T acc[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) acc[jj] = Sc<T>::zero();
+      if (j0 < b) {
+        for (int m = 0; m < b; ++m) {
+          const T tm = Ts[m * nU + k];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) acc[jj] = fma_(Bi[(j0 + jj) * bp + m], tm, acc[jj]);   // rows >= b of Bi: identity pad
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const T v = (j0 + jj < b) ? acc[jj] : Sc<T>::zero();
+        D[(int64_t)(j0 + jj) * nU + k] = v;
+        rs[jj] = add(rs[jj], v);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      cd a = to_cd(rs[jj]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
+      }
+      if (lane == 0) cep[warp * bp + j0 + jj] = Sc<T>::from_cd(a);
+    }
   }
   __syncthreads();
-  // ce = C e
   const double se = rsqrt((double)nU);
-  for (int j = warp; j < bp; j += 8) {
-    T acc = Sc<T>::zero();
-    for (int k = lane; k < nU; k += 32) acc = add(acc, D[(int64_t)j * nU + k]);
-    cd a = to_cd(acc);
+  if (tid < bp) {
+    T a = Sc<T>::zero();
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a.x += __shfl_xor_sync(0xffffffffu, a.x, o);
-      a.y += __shfl_xor_sync(0xffffffffu, a.y, o);
-    }
-    if (lane == 0) ce[j] = Sc<T>::from_cd(scale(se, a));
+    for (int w = 0; w < 8; ++w) a = add(a, cep[w * bp + tid]);
+    ce[tid] = Sc<T>::from_cd(scale(se, to_cd(a)));
   }
   __syncthreads();
   // q = T e - T[:,B] ce (T symmetric: T[k, lo+j] = T[lo+j, k]); zero on B
   T part = Sc<T>::zero();
   for (int k = tid; k < nU; k += 256) {
     T v = te[k];
-    for (int j = 0; j < b; ++j) v = sub(v, mul(Tm[(int64_t)(lo + j) * nU + k], ce[j]));
+    for (int j = 0; j < b; ++j) v = sub(v, mul(Ts[j * nU + k], ce[j]));
     if (k >= lo && k < lo + b) v = Sc<T>::zero();
     q[k] = v;
     part = add(part, v);
@@ -321,11 +350,12 @@ excite_small_kernel(int nU, int bp, const T* __restrict__ Tm, const T* __restric
   const T eq = Sc<T>::from_cd(scale(se, to_cd(red[0])));
   const double g = gamma[0];
   const T alpha = mul(Sc<T>::from_real(g), inv_(sub(Sc<T>::one(), scale(g, eq))));
-  for (int t = tid; t < bp * nU; t += 256) {
-    const int j = t / nU, k = t - j * nU;
-    if (j < b) D[(int64_t)j * nU + k] = add(D[(int64_t)j * nU + k], mul(mul(alpha, ce[j]), q[k]));
+  // D = C + alpha (C e) q^T: every thread revisits the (j, k) entries it wrote itself
+  for (int k = tid; k < nU; k += 256) {
+    const T aq = mul(alpha, q[k]);
+    for (int j2 = 0; j2 < b; ++j2) D[(int64_t)j2 * nU + k] = add(D[(int64_t)j2 * nU + k], mul(ce[j2], aq));
+    D[(int64_t)bp * nU + k] = aq;
   }
-  for (int k = tid; k < nU; k += 256) D[(int64_t)bp * nU + k] = mul(alpha, q[k]);
 }
 // out[b][n,k] = src[n,k] - sum_{j<b} src[n, lo+j] D[j,k] + yv[n] D[bp,k]; columns (and, if zero_rows, rows)
 // of B_i are set to exactly zero.  CTA = one excitation x `passes` tiles of RT rows x all columns: D_i is

@@ -235,15 +235,21 @@ def run_gpu(args):
     det_local = det[dlo:dhi].contiguous()
     inv_holder = {}
 
-    def step():
+    def local_part():                      # this rank's library calls, no collective: capturable
         plan.assemble(perm, var, omega)
         plan.factor(False)
         plan.jacobian_block(i0, i1, e0, e1, C_PERT, omega, J, E, base)
+        if ws == 1:
+            inv_holder["inv"] = _lib.inverse_model(J, det, LAMBDA, shift=1.0, form=0)
+
+    def exchange_part():                   # N > 1: all-gather of J, sharded inverse model (one all-reduce)
         if ws > 1:
             gather_jacobian(J, L, E)
             inv_holder["inv"] = _lib.inverse_model_sharded(J, det_local, LAMBDA, shift=1.0)
-        else:
-            inv_holder["inv"] = _lib.inverse_model(J, det, LAMBDA, shift=1.0, form=0)
+
+    def step():
+        local_part()
+        exchange_part()
 
     def barrier():
         torch.cuda.synchronize()
@@ -255,11 +261,14 @@ def run_gpu(args):
     barrier()
     # the ~130 short dependent kernels of a step are replayed from ONE CUDA graph (no launch gaps);
     # --no-graph launches them on the stream one by one
-    use_graph = not args.no_graph and (ws == 1 or args.graph_multi)
+    use_graph = not args.no_graph
     run_step = step
-    if use_graph:
-        graph = _lib.StepGraph(step)
-        run_step = graph.replay
+    if use_graph:                          # the NCCL exchange of N > 1 stays outside the graph
+        graph = _lib.StepGraph(local_part)
+
+        def run_step():
+            graph.replay()
+            exchange_part()
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         run_step()
@@ -468,7 +477,7 @@ def run_gpu(args):
                        "N": N, "E": E, "L": L, "columns_per_step": n_cols, "l2": "flushed between timed steps (256 MiB memset)",
                        "sharding": f"excitation blocks over {ws} rank(s), all-gather J (NCCL), inverse model sharded "
                                    f"over detection elements (one all-reduce of the m x m Gram matrix)"},
-            "gpu_launches": int(launches), "launch_mode": "cuda_graph" if use_graph else "stream",
+            "gpu_launches": int(launches), "launch_mode": ("cuda_graph" if ws == 1 else "cuda_graph(local part) + NCCL exchange") if use_graph else "stream",
             "wall_s_timed_region": wall,
             "clocks": clocks, "e2e": e2e, "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu,
             "realtime": realtime,
@@ -485,7 +494,6 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--graph-multi", action="store_true", help="also capture the N>1 step (with its NCCL collectives) into a graph")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--config", default="50_50", choices=sorted(CONFIGS), help="workload (default: the headline MESH_50_50)")
     args = ap.parse_args()

@@ -9,10 +9,9 @@ import bench
 opts = [sys.argv[k + 1] for k, a in enumerate(sys.argv[:-1]) if a == "--opt"]     # --opt name=value (ceit_set_option)
 for o_ in opts:
     _lib.set_option(o_.split("=")[0], float(o_.split("=")[1]))
-args = [a for a in sys.argv[1:] if not a.startswith("--") and a not in opts]
+args = [a for k, a in enumerate(sys.argv[1:], 1) if not a.startswith("--") and a not in opts and sys.argv[k - 1] != "--target"]
 cplx = False
 target = int(sys.argv[sys.argv.index("--target") + 1]) if "--target" in sys.argv else 0
-if "--target" in sys.argv: args = [a for a in args if a != str(target)] if False else args
 tag = args[0] if args else "50_50"
 if tag in ("50_50", "21_21"):
     mesh = bench.load_mesh(tag)

@@ -146,7 +146,7 @@ struct ceit_plan {
   void *Ad = nullptr, *Bs = nullptr, *Ld = nullptr, *Linv = nullptr, *Lsub = nullptr, *Sel = nullptr;
   void *K0U = nullptr, *Zw = nullptr, *Xh = nullptr, *XP = nullptr, *KUU = nullptr, *SU = nullptr, *Ptmp = nullptr;
   int32_t* d_row_map = nullptr;
-  void *tmpPanel = nullptr, *g0e = nullptr, *tmpT = nullptr;
+  void *tmpPanel = nullptr, *g0e = nullptr, *tmpT = nullptr, *tmpPanel2 = nullptr, *Ptmp2 = nullptr;
   void *Aint = nullptr, *Lint = nullptr, *LintInv = nullptr, *Ainv = nullptr, *Bt = nullptr, *Wn = nullptr;
   void *Tm = nullptr, *G1 = nullptr;
   void *Mreg = nullptr, *LT = nullptr, *LinvT = nullptr, *Tinv = nullptr, *te = nullptr, *YT = nullptr, *ye = nullptr;
@@ -154,8 +154,8 @@ struct ceit_plan {
   void* splitk_ws = nullptr;
   // auxiliary stream + events: independent chains of a stage (right-hand-side sweep vs selected inverse, ...)
   // run concurrently and join before the stage ends; also valid under stream capture (fork/join in the graph)
-  cudaStream_t s2 = nullptr, s3 = nullptr;
-  SideLane lane_a, lane_b;   // Linv row blocks of the blocked factorisations on st / on s3
+  cudaStream_t s2 = nullptr, s3 = nullptr, s4 = nullptr, s5 = nullptr;
+  SideLane lane_a, lane_b, lane_c;   // Linv row blocks of the blocked factorisations on st / on s3 / on s4
   cudaEvent_t ev_ring[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int ev_next = 0;
   void* g1e = nullptr;
@@ -251,7 +251,7 @@ int alloc_numeric(ceit_plan* p) {
   const int want = Sc<T>::is_complex ? 2 : 1;
   if (p->alloc_mode == want) return 0;
   void** bufs[] = {&p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
-                   &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->tmpT, &p->g0e, &p->Aint, &p->Lint,
+                   &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->tmpT, &p->tmpPanel2, &p->Ptmp2, &p->g0e, &p->Aint, &p->Lint,
                    &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1, &p->XP, &p->Mreg, &p->LT,
                    &p->LinvT, &p->Tinv, &p->te, &p->YT, &p->ye, &p->splitk_ws, &p->g1e};
   for (auto b : bufs) dev_free_tracked(p, *b);
@@ -297,8 +297,10 @@ int alloc_numeric(ceit_plan* p) {
   if ((rc = dev_alloc(p, &p->KUU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->SU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Ptmp, maxS * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Ptmp2, maxS * es))) return rc;
   if ((rc = dev_alloc(p, &p->tmpPanel, (int64_t)TILE * h.max_block * es))) return rc;
   if ((rc = dev_alloc(p, &p->tmpT, (int64_t)TILE * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->tmpPanel2, (int64_t)TILE * h.max_block * es))) return rc;
   if ((rc = dev_alloc(p, &p->g0e, 6 * h.E * es))) return rc;
   p->alloc_mode = want;
   return 0;
@@ -351,6 +353,9 @@ inline int ensure_aux_stream(ceit_plan* p) {
   if (p->s2) return 0;
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s2, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&p->s3, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->s4, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->s5, cudaStreamNonBlocking));
+  CUDA_TRY(p->lane_c.init());
   CUDA_TRY(p->lane_a.init());
   CUDA_TRY(p->lane_b.init());
   for (auto& e : p->ev_ring) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -464,30 +469,71 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   }
   KERNEL_CHECK();
   // ---- level 2: block-tridiagonal Cholesky of M2 + forward substitution ----------------------------
+  // The chain of nb blocks is eliminated from BOTH ends towards the middle block m ("burn at both ends"): blocks
+  // 0..m-1 downwards (Lsub_k = B_k Linv_k^T, as in a plain block Cholesky) on st/sr, blocks nb-1..m+1 upwards
+  // (Vsub_k = Linv_k B_{k-1}, D_{k-1} -= Vsub_k^T Vsub_k) on sb/srb, so the serial spine is nb/2 + 1 blocks long.
   auto n_of = [&](int64_t k) { return (int64_t)(h.blk_ptr[k + 1] - h.blk_ptr[k]); };
   auto row_of = [&](int64_t k) { return NI + (int64_t)h.blk_ptr[k]; };
-  for (int64_t k = 0; k < h.nb; ++k) {
-    const int64_t nk = n_of(k), r0 = row_of(k);
-    T* Ak = Ad + h.offD[k];
-    T* Lk = Ld + h.offD[k];
+  const int64_t nbk = h.nb, mid = nbk / 2;
+  cudaStream_t sb = st, srb = sr;
+  if (g_multi_stream && nbk >= 3) {
+    sb = p->s4;
+    srb = p->s5;
+    CEIT_AFTER(st, sb);
+    CEIT_AFTER(sr, srb);
+  }
+  auto factor_block = [&](int64_t k, cudaStream_t sm, cudaStream_t sx, T* tmp, SideLane* lane) -> int {
+    const int64_t nk = n_of(k);
+    potrf_trtri_blocked<T>(sm, nk, Ad + h.offD[k], nk, 0, Ld + h.offD[k], nk, 0, Linv + h.offD[k], nk, 0, tmp, 0, 1,
+                           p->d_info, g_multi_stream ? lane : nullptr);
+    CEIT_AFTER(sm, sx);                  // Linv_k (and the coupling factors before it, W_p) are ready for the sweep
+    return 0;
+  };
+  for (int64_t k = 0; k < mid; ++k) {                                  // downward arm
+    const int64_t nk = n_of(k), r0 = row_of(k), nn = n_of(k + 1);
     T* Lik = Linv + h.offD[k];
-    potrf_trtri_blocked<T>(st, nk, Ak, nk, 0, Lk, nk, 0, Lik, nk, 0, tmpPanel, 0, 1, p->d_info,
-                           g_multi_stream ? &p->lane_a : nullptr);
-    CEIT_AFTER(st, sr);                  // Linv_k (and Lsub_{k-1}, W_p) are ready for the sweep
+    if ((rc = factor_block(k, st, sr, tmpPanel, &p->lane_a))) return rc;
     if (k > 0) {
       const int64_t np = n_of(k - 1), rp = row_of(k - 1);
       // RHS_k -= Lsub_{k-1} Z_{k-1}   (Z_{k-1} lives in Xh rows of block k-1 during the forward sweep)
       gemm<T>(sr, 0, 0, nk, nU, np, mone, Lsub + h.offS[k - 1], np, 0, Xh + rp * nU, nU, 0, one, Zw + r0 * nU, nU, 0);
     }
-    // Z_k = Linv_k RHS_k
-    gemm<T>(sr, 0, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
-    if (k + 1 < h.nb) {
-      const int64_t nn = n_of(k + 1);
-      // Lsub_k = B_k Linv_k^T ; A_{k+1} -= Lsub_k Lsub_k^T
-      gemm<T>(st, 0, 1, nn, nk, nk, one, Bs + h.offS[k], nk, 0, Lik, nk, 0, zero, Lsub + h.offS[k], nk, 0);
-      gemm<T>(st, 0, 1, nn, nn, nk, mone, Lsub + h.offS[k], nk, 0, Lsub + h.offS[k], nk, 0, one, Ad + h.offD[k + 1],
-              nn, 0, 1, /*lower_only=*/1);
+    gemm<T>(sr, 0, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);   // Z_k = Linv_k RHS_k
+    // Lsub_k = B_k Linv_k^T ; A_{k+1} -= Lsub_k Lsub_k^T
+    gemm<T>(st, 0, 1, nn, nk, nk, one, Bs + h.offS[k], nk, 0, Lik, nk, 0, zero, Lsub + h.offS[k], nk, 0);
+    gemm<T>(st, 0, 1, nn, nn, nk, mone, Lsub + h.offS[k], nk, 0, Lsub + h.offS[k], nk, 0, one, Ad + h.offD[k + 1], nn, 0,
+            1, /*lower_only=*/1);
+  }
+  for (int64_t k = nbk - 1; k > mid; --k) {                            // upward arm
+    const int64_t nk = n_of(k), r0 = row_of(k), np = n_of(k - 1);
+    T* Lik = Linv + h.offD[k];
+    if ((rc = factor_block(k, sb, srb, (T*)p->tmpPanel2, &p->lane_c))) return rc;
+    if (k + 1 < nbk) {
+      const int64_t nn = n_of(k + 1), rn = row_of(k + 1);
+      // RHS_k -= Vsub_{k+1}^T Z_{k+1}
+      gemm<T>(srb, 1, 0, nk, nU, nn, mone, Lsub + h.offS[k], nk, 0, Xh + rn * nU, nU, 0, one, Zw + r0 * nU, nU, 0);
     }
+    gemm<T>(srb, 0, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
+    // Vsub_k = Linv_k B_{k-1} (n_k x n_{k-1}, stored in the slot of B_{k-1}) ; A_{k-1} -= Vsub_k^T Vsub_k
+    gemm<T>(sb, 0, 0, nk, np, nk, one, Lik, nk, 0, Bs + h.offS[k - 1], np, 0, zero, Lsub + h.offS[k - 1], np, 0);
+    gemm<T>(sb, 1, 0, np, np, nk, mone, Lsub + h.offS[k - 1], np, 0, Lsub + h.offS[k - 1], np, 0, one,
+            Ad + h.offD[k - 1], np, 0, 1, /*lower_only=*/1);
+  }
+  if (nbk > 0) {                                                       // middle block: both arms meet
+    const int64_t nk = n_of(mid), r0 = row_of(mid);
+    T* Lik = Linv + h.offD[mid];
+    CEIT_AFTER(sb, st);
+    CEIT_AFTER(srb, sr);
+    if ((rc = factor_block(mid, st, sr, tmpPanel, &p->lane_a))) return rc;
+    if (mid > 0) {
+      const int64_t np = n_of(mid - 1), rp = row_of(mid - 1);
+      gemm<T>(sr, 0, 0, nk, nU, np, mone, Lsub + h.offS[mid - 1], np, 0, Xh + rp * nU, nU, 0, one, Zw + r0 * nU, nU, 0);
+    }
+    if (mid + 1 < nbk) {
+      const int64_t nn = n_of(mid + 1), rn = row_of(mid + 1);
+      gemm<T>(sr, 1, 0, nk, nU, nn, mone, Lsub + h.offS[mid], nk, 0, Xh + rn * nU, nU, 0, one, Zw + r0 * nU, nU, 0);
+    }
+    gemm<T>(sr, 0, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
   }
   // S_U = K_UU - K_0U^T K00^-1 K_0U = K_UU - K_IU^T t_I - Z_C^T Z_C is complete after the FORWARD sweep (t_I and Z
   // still sit in Xh), so T = (S_U + gamma e e^T)^-1, the longest chain of the stage, starts here on its own
@@ -515,27 +561,47 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
     rowsum_e_kernel<T><<<cdiv(nU, 8), 256, 0, s_t>>>(nU, (int)nU, Tinv, te);
     CEIT_COUNT_LAUNCH();
   }
-  // backward sweep (sr): X_k = Linv_k^T (Z_k - Lsub_k^T X_{k+1}); selected inverse blocks (st)
-  for (int64_t k = h.nb - 1; k >= 0; --k) {
+  // backward sweep and selected inverse, from the middle block outwards along both arms:
+  //   X_k = Linv_k^T (Z_k - Lsub_k^T X_{k+1}) (k < m),  X_k = Linv_k^T (Z_k - Vsub_k X_{k-1}) (k > m)
+  //   k < m: P = Lsub_k Linv_k,  So_k = -Sd_{k+1} P,      Sd_k = Linv_k^T Linv_k - P^T So_k
+  //   k > m: R = Linv_k^T Vsub_k, So_{k-1} = -R Sd_{k-1}, Sd_k = Linv_k^T Linv_k - So_{k-1} R^T
+  auto back_block = [&](int64_t k, cudaStream_t sx) -> int {       // X_k from Z_k (after the coupling term was applied)
     const int64_t nk = n_of(k), r0 = row_of(k);
-    T* Lik = Linv + h.offD[k];
-    if (k + 1 < h.nb) {
-      const int64_t nn = n_of(k + 1), rn = row_of(k + 1);
-      gemm<T>(sr, 1, 0, nk, nU, nn, mone, Lsub + h.offS[k], nk, 0, Xh + rn * nU, nU, 0, one, Xh + r0 * nU, nU, 0);
-    }
     // in-place is not allowed in the GEMM: go through Zw rows of this block
-    CUDA_TRY(cudaMemcpyAsync(Zw + r0 * nU, Xh + r0 * nU, nk * nU * es, cudaMemcpyDeviceToDevice, sr));
-    gemm<T>(sr, 1, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
-    // Sd_k = Linv_k^T Linv_k
-    gemm<T>(st, 1, 0, nk, nk, nk, one, Lik, nk, 0, Lik, nk, 0, zero, Sd + h.offD[k], nk, 0);
-    if (k + 1 < h.nb) {
-      const int64_t nn = n_of(k + 1);
-      // P = Lsub_k Linv_k ; So_k = -Sd_{k+1} P ; Sd_k -= P^T So_k
-      gemm<T>(st, 0, 0, nn, nk, nk, one, Lsub + h.offS[k], nk, 0, Lik, nk, 0, zero, Ptmp, nk, 0);
-      gemm<T>(st, 0, 0, nn, nk, nn, mone, Sd + h.offD[k + 1], nn, 0, Ptmp, nk, 0, zero, So + h.offS[k], nk, 0);
-      gemm<T>(st, 1, 0, nk, nk, nn, mone, Ptmp, nk, 0, So + h.offS[k], nk, 0, one, Sd + h.offD[k], nk, 0);
-    }
+    CUDA_TRY(cudaMemcpyAsync(Zw + r0 * nU, Xh + r0 * nU, nk * nU * es, cudaMemcpyDeviceToDevice, sx));
+    gemm<T>(sx, 1, 0, nk, nU, nk, one, Linv + h.offD[k], nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
+    return 0;
+  };
+  if (nbk > 0) {
+    if ((rc = back_block(mid, sr))) return rc;
+    gemm<T>(st, 1, 0, n_of(mid), n_of(mid), n_of(mid), one, Linv + h.offD[mid], n_of(mid), 0, Linv + h.offD[mid], n_of(mid),
+            0, zero, Sd + h.offD[mid], n_of(mid), 0);
+    CEIT_AFTER(sr, srb);
+    CEIT_AFTER(st, sb);
   }
+  for (int64_t k = mid - 1; k >= 0; --k) {                             // downward arm, outwards
+    const int64_t nk = n_of(k), r0 = row_of(k), nn = n_of(k + 1), rn = row_of(k + 1);
+    T* Lik = Linv + h.offD[k];
+    gemm<T>(sr, 1, 0, nk, nU, nn, mone, Lsub + h.offS[k], nk, 0, Xh + rn * nU, nU, 0, one, Xh + r0 * nU, nU, 0);
+    if ((rc = back_block(k, sr))) return rc;
+    gemm<T>(st, 1, 0, nk, nk, nk, one, Lik, nk, 0, Lik, nk, 0, zero, Sd + h.offD[k], nk, 0);
+    gemm<T>(st, 0, 0, nn, nk, nk, one, Lsub + h.offS[k], nk, 0, Lik, nk, 0, zero, Ptmp, nk, 0);
+    gemm<T>(st, 0, 0, nn, nk, nn, mone, Sd + h.offD[k + 1], nn, 0, Ptmp, nk, 0, zero, So + h.offS[k], nk, 0);
+    gemm<T>(st, 1, 0, nk, nk, nn, mone, Ptmp, nk, 0, So + h.offS[k], nk, 0, one, Sd + h.offD[k], nk, 0);
+  }
+  for (int64_t k = mid + 1; k < nbk; ++k) {                            // upward arm, outwards
+    const int64_t nk = n_of(k), r0 = row_of(k), np = n_of(k - 1), rp = row_of(k - 1);
+    T* Lik = Linv + h.offD[k];
+    T* Rt = (T*)p->Ptmp2;
+    gemm<T>(srb, 0, 0, nk, nU, np, mone, Lsub + h.offS[k - 1], np, 0, Xh + rp * nU, nU, 0, one, Xh + r0 * nU, nU, 0);
+    if ((rc = back_block(k, srb))) return rc;
+    gemm<T>(sb, 1, 0, nk, nk, nk, one, Lik, nk, 0, Lik, nk, 0, zero, Sd + h.offD[k], nk, 0);
+    gemm<T>(sb, 1, 0, nk, np, nk, one, Lik, nk, 0, Lsub + h.offS[k - 1], np, 0, zero, Rt, np, 0);
+    gemm<T>(sb, 0, 0, nk, np, np, mone, Rt, np, 0, Sd + h.offD[k - 1], np, 0, zero, So + h.offS[k - 1], np, 0);
+    gemm<T>(sb, 0, 1, nk, nk, np, mone, So + h.offS[k - 1], np, 0, Rt, np, 0, one, Sd + h.offD[k], nk, 0);
+  }
+  CEIT_AFTER(srb, sr);
+  CEIT_AFTER(sb, st);
   // ---- back to the interiors: x_I = t_I - W x_C[bnd] (sr), selected inverse blocks (st) ----------------
   if (P > 0) {
     if (h.nb == 0) CEIT_AFTER(st, sr);   // W_p (no separator block ordered the streams yet)
@@ -846,10 +912,12 @@ int ceit_plan_destroy(ceit_plan_t* p) {
   if (p->s2) {
     cudaStreamSynchronize(p->s2);
     cudaStreamDestroy(p->s2);
-    if (p->s3) {
-      cudaStreamSynchronize(p->s3);
-      cudaStreamDestroy(p->s3);
-    }
+    for (cudaStream_t s : {p->s3, p->s4, p->s5})
+      if (s) {
+        cudaStreamSynchronize(s);
+        cudaStreamDestroy(s);
+      }
+    p->lane_c.destroy();
     p->lane_a.destroy();
     p->lane_b.destroy();
     for (auto e : p->ev_ring)

@@ -87,16 +87,19 @@ inline size_t woodbury_patch_smem(int64_t nU, int64_t cap) {
   return (size_t)(nU * 32 + 2 * cap * woodbury_pitch(nU) * 8 + WBP_WARPS * 6 * 32 * 8 + 6 * 32 * 8 + cap * 8 + 64);
 }
 // low-rank kernel: only the Yh rows are staged (plus 2 bp + 3 small values per node)
-inline size_t woodbury_lr_smem(int64_t nU, int64_t cap, int64_t bp) {
-  return (size_t)(nU * 32 + cap * woodbury_pitch(nU) * 8 + cap * bp * 8 + cap * (bp + 1) * 8 + 2 * cap * 8 + 12 * 32 * 8 + 64);
+// (layout in woodbury_lr_kernel: mbarrier, SoA constants, Yh rows at an even pitch, YB/ZW at stride bp+1, ...)
+inline int64_t woodbury_lr_cst_len(int64_t nU, int64_t L) { return 3 * ((nU + 1) & ~1LL) + ((L + 1) & ~1LL); }
+inline size_t woodbury_lr_smem(int64_t nU, int64_t cap, int64_t bp, int64_t L) {
+  return (size_t)(16 + woodbury_lr_cst_len(nU, L) * 8 + cap * woodbury_lr_pitch((int)nU) * 8 + 2 * cap * (bp + 1) * 8 +
+                  2 * cap * 8 + 12 * 32 * 8 + 64);
 }
 // node cap of a patch for the low-rank kernel: 3 CTAs per SM if that leaves >= 20 nodes (~24 elements) per
 // patch, else 2 (measured: occupancy beats patch size, 400x400 mesh 30 -> 18 ms)
-inline int woodbury_lr_cap(int64_t nU, int64_t bp) {
+inline int woodbury_lr_cap(int64_t nU, int64_t bp, int64_t L) {
   for (int per_sm = 3; per_sm >= 1; --per_sm) {
     const int64_t budget = (227 * 1024) / per_sm - 1024 - 256;
     int64_t cap = 40;
-    while (cap > 0 && (int64_t)woodbury_lr_smem(nU, cap, bp) > budget) --cap;
+    while (cap > 0 && (int64_t)woodbury_lr_smem(nU, cap, bp, L) > budget) --cap;
     if (cap >= (per_sm == 3 ? 20 : 16) || per_sm == 1) return (int)cap;
   }
   return 0;
@@ -766,18 +769,19 @@ int launch_woodbury_patch(ceit_plan* p, const double* g0e, const double* Xh, con
 int launch_woodbury_lr(ceit_plan* p, int e_from, int e_to, int nbatch, int i0, double s_coef, double* J, int64_t ldJ,
                        cudaStream_t st) {
   const HostPlan& h = p->h;
-  const size_t psm = woodbury_lr_smem(h.nU, h.patch_node_cap, h.bp);
-  double4* consts = (double4*)p->tmpS;
-  node_consts_kernel<<<dim3(cdiv(h.nU, 128), nbatch), 128, 0, st>>>((int)h.nU, h.N, h.N0, (const double*)p->phi0, p->d_wk,
-                                                                   consts);
+  const size_t psm = woodbury_lr_smem(h.nU, h.patch_node_cap, h.bp, h.L);
+  const int nUp = (int)((h.nU + 1) & ~1LL), cst_len = (int)woodbury_lr_cst_len(h.nU, h.L);
+  double* consts = (double*)p->tmpS;        // free after the batched factorisation of the excitation stage
+  node_consts_soa_kernel<<<dim3(cdiv(std::max(h.nU, h.L), 128), nbatch), 128, 0, st>>>(
+      (int)h.nU, nUp, (int)h.L, cst_len, h.N, h.N0, (const double*)p->phi0, p->d_wk, p->d_ue_ptr, consts);
   CEIT_COUNT_LAUNCH();
   CUDA_TRY(cudaFuncSetAttribute(woodbury_lr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
   dim3 grid((unsigned)((int64_t)p->n_patches * nbatch));
   woodbury_lr_kernel<<<grid, WBP_WARPS * 32, psm, st>>>(
-      e_from, e_to, (int)h.L, (int)h.nU, (int)woodbury_pitch(h.nU), (int)h.bp, h.N, h.N0, p->d_patch_eptr, p->d_patch_elems,
-      p->d_patch_nptr, p->d_patch_nodes, p->d_patch_local, p->d_area, (const double*)p->g1e, (const double*)p->YT,
-      (const double*)p->ye, (const double*)p->ZW, (const double*)p->Yh, (const double*)p->phi0, p->d_ue_ptr, consts, i0,
-      s_coef, J, ldJ, (int)h.patch_node_cap, nbatch);
+      e_from, e_to, (int)h.L, (int)h.nU, woodbury_lr_pitch((int)h.nU), (int)h.bp, h.N, h.N0, p->d_patch_eptr,
+      p->d_patch_elems, p->d_patch_nptr, p->d_patch_nodes, p->d_patch_local, p->d_area, (const double*)p->g1e,
+      (const double*)p->YT, (const double*)p->ye, (const double*)p->ZW, (const double*)p->Yh, (const double*)p->phi0,
+      p->d_ue_ptr, consts, i0, s_coef, J, ldJ, (int)h.patch_node_cap, nbatch);
   CEIT_COUNT_LAUNCH();
   return 0;
 }
@@ -811,7 +815,7 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
       CEIT_COUNT_LAUNCH();
     }
     const bool lowrank = use_rank_update(p) && !g_no_lowrank &&
-                         woodbury_lr_smem(h.nU, h.patch_node_cap, h.bp) <= (size_t)WB_SMEM_SM;
+                         woodbury_lr_smem(h.nU, h.patch_node_cap, h.bp, h.L) <= (size_t)WB_SMEM_SM;
     const bool use_patch = !g_no_patch && !Sc<T>::is_complex && h.patch_node_cap >= 12 && h.u_contiguous &&
                            (lowrank || woodbury_patch_smem(h.nU, h.patch_node_cap) <= (size_t)WB_SMEM_SM);
     if (e_to > e_from && J && use_patch) {
@@ -888,7 +892,7 @@ int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_
       // patches of <= 32 elements whose distinct node rows fit the shared-memory budget
       const bool lr = rank_update_shape_ok(p->h) && !g_direct_excitation && !g_no_lowrank;
       int64_t cap = g_patch_nodes > 0 ? std::min(g_patch_nodes, 64)
-                                      : (lr ? woodbury_lr_cap(p->h.nU, p->h.bp) : woodbury_patch_cap(p->h.nU));
+                                      : (lr ? woodbury_lr_cap(p->h.nU, p->h.bp, p->h.L) : woodbury_patch_cap(p->h.nU));
       if (cap < 3) cap = 3;
       build_patches(p->h, (int32_t)cap, 32);
     }
@@ -1219,10 +1223,10 @@ int ceit_stage_times(double* ms, int64_t* counts) {
   return CEIT_OK;
 }
 
-int ceit_debug_wb_clocks(int64_t* out) {
-  long long h[8];
+int ceit_debug_wb_clocks(int64_t* out) {   // out[16]: CTA 81 (first wave) in [0,8), CTA 1500 in [8,16)
+  long long h[16];
   CUDA_TRY(cudaMemcpyFromSymbol(h, ceit::g_wb_clk, sizeof(h)));
-  for (int k = 0; k < 8; ++k) out[k] = h[k];
+  for (int k = 0; k < 16; ++k) out[k] = h[k];
   return CEIT_OK;
 }
 

@@ -705,12 +705,23 @@ __device__ __forceinline__ double sqrt1p_minus1(double x) {
   }
   return sqrt(1.0 + x) - 1.0;
 }
+// The polynomial alone (no branch), for loops that check the range of x once per electrode: a loop body with the
+// DSQRT branch is not if-converted, so its unrolled iterations serialise on convergence barriers.
+__device__ __forceinline__ double sqrt1p_minus1_poly(double x) {
+  double t = fma(x, -0.0390625, 0.0625);
+  t = fma(x, t, -0.125);
+  t = fma(x, t, 0.5);
+  return x * t;
+}
+// high word of |x|: integer-pipe range tracking (hi >= SQRT1P_HI_LIMIT  <=>  |x| >= ~1e-3, conservative)
+__device__ __forceinline__ unsigned abs_hi(double x) { return (unsigned)__double2hiint(x) & 0x7fffffffu; }
+constexpr unsigned SQRT1P_HI_LIMIT = 0x3f50624du;      // high word of 1e-3
 
 constexpr int WBP_WARPS = 8;
 
-__device__ long long g_wb_clk[8];
+__device__ long long g_wb_clk[16];
 #ifdef CEIT_TILE_CLOCKS
-#define WB_CLK(q) do { if (threadIdx.x == 0 && blockIdx.x == 81) g_wb_clk[q] = clock64(); } while (0)
+#define WB_CLK(q) do { if (threadIdx.x == 0 && (blockIdx.x == 81 || blockIdx.x == 1500)) g_wb_clk[(blockIdx.x == 81 ? 0 : 8) + q] = clock64(); } while (0)
 #else
 #define WB_CLK(q) do { } while (0)
 #endif
@@ -899,6 +910,7 @@ woodbury_patch_kernel(int e_from, int e_to, int L, int nU, int pitch, int64_t N,
     if (m == i) continue;
     const int ks = ue_ptr[m], ke = ue_ptr[m + 1];
     double sum0 = 0.0, sumt = 0.0;
+    unsigned hmax = 0u;
 #pragma unroll 4
     for (int k = ks; k < ke; ++k) {
       const double4 cu = cU[k];
@@ -907,8 +919,20 @@ woodbury_patch_kernel(int e_from, int e_to, int L, int nU, int pitch, int64_t N,
       const double di = fma(a0, yi0, fma(a1, yi1, a2 * yi2));
       const double qq = fma(dr, dr, di * di);
       const double x = fma(cu.x, dr, qq * cu.y);         // (2 phi0 dr + |d|^2) / phi0^2, phi0 real
+      hmax = max(hmax, abs_hi(x));
       sum0 += cu.z;
-      sumt = fma(cu.z, sqrt1p_minus1(x), sumt);
+      sumt = fma(cu.z, sqrt1p_minus1_poly(x), sumt);
+    }
+    if (hmax >= SQRT1P_HI_LIMIT) {                       // rare: a large perturbation, exact square roots
+      sumt = 0.0;
+      for (int k = ks; k < ke; ++k) {
+        const double4 cu = cU[k];
+        const double a0 = y0[k], a1 = y1[k], a2 = y2[k];
+        const double dr = fma(a0, yr0, fma(a1, yr1, a2 * yr2));
+        const double di = fma(a0, yi0, fma(a1, yi1, a2 * yi2));
+        const double qq = fma(dr, dr, di * di);
+        sumt = fma(cu.z, sqrt1p_minus1(fma(cu.x, dr, qq * cu.y)), sumt);
+      }
     }
     if (write) J[((int64_t)i * (L - 1) + m - (m > i ? 1 : 0)) * ldJ + j] = fabs(sum0 + sumt);
   }
@@ -958,6 +982,70 @@ g1_kernel(int64_t E, int nU, const int32_t* __restrict__ elem_pos, const double*
   }
 }
 
+// ---- TMA bulk copy (1-D cp.async.bulk, SASS UBLKCP) + mbarrier helpers --------------------------------------------
+// One instruction moves a whole node row (nU * 8 bytes) global -> shared; an 8-byte LDGSTS costs ~8 LSU cycles per
+// warp instruction whatever its size, which made the staging loop of this kernel 30 % of a CTA's life.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Per-excitation constants of the low-rank kernel, structure of arrays so that ONE bulk copy stages them and the
+// main loop reads two electrode nodes per 16-byte broadcast load:
+//   out[b] = [ 2/phi0 (nUp) | 1/phi0^2 (nUp) | w |phi0| (nUp) | sum over electrode m of w |phi0| (Lp) ]
+__global__ void node_consts_soa_kernel(int nU, int nUp, int L, int cst_len, int64_t N, int64_t N0,
+                                       const double* __restrict__ phi0, const double* __restrict__ wk,
+                                       const int32_t* __restrict__ ue_ptr, double* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* ph = phi0 + (int64_t)b * N + N0;
+  double* o = out + (int64_t)b * cst_len;
+  if (k < nU) {
+    const double f = ph[k];
+    const double r = 1.0 / f;
+    o[k] = 2.0 * r;
+    o[nUp + k] = r * r;
+    o[2 * nUp + k] = wk[k] * fabs(f);
+  }
+  if (k < L) {
+    double s0 = 0.0;
+    for (int q = ue_ptr[k]; q < ue_ptr[k + 1]; ++q) s0 += wk[q] * fabs(ph[q]);
+    o[3 * nUp + k] = s0;
+  }
+}
+
+// Row pitch of the staged Yh rows: even (16-byte rows for the bulk copy and the 16-byte loads) with pitch/2 odd, so
+// that the 8 lanes of a quarter warp reading different rows at the same column pair hit 8 different 16-byte bank groups.
+__host__ __device__ inline int woodbury_lr_pitch(int nU) {
+  int p = (nU + 1) & ~1;
+  if (((p >> 1) & 1) == 0) p += 2;
+  return p;
+}
+
 __global__ void __launch_bounds__(WBP_WARPS * 32)
 woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64_t N, int64_t N0,
                    const int32_t* __restrict__ patch_eptr, const int32_t* __restrict__ patch_elems,
@@ -965,7 +1053,7 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
                    const uint8_t* __restrict__ patch_local, const double* __restrict__ area,
                    const double* __restrict__ g1e, const double* __restrict__ YT, const double* __restrict__ ye,
                    const double* __restrict__ ZW, const double* __restrict__ Yh, const double* __restrict__ phi0,
-                   const int32_t* __restrict__ ue_ptr, const double4* __restrict__ node_consts, int i0,
+                   const int32_t* __restrict__ ue_ptr, const double* __restrict__ node_consts, int i0,
                    double s_coef, double* __restrict__ J, int64_t ldJ, int cap, int nbatch) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = WBP_WARPS;
@@ -975,38 +1063,58 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
   const int n_beg = patch_nptr[patch], nn = patch_nptr[patch + 1] - n_beg;
   const int el_beg = patch_eptr[patch], ne = patch_eptr[patch + 1] - el_beg;
   const int lo = ue_ptr[i], nb = ue_ptr[i + 1] - lo;
-  const int zp = bp + 1;
-  double4* cU = reinterpret_cast<double4*>(smem_raw);           // [nU] {2/phi0, 1/phi0^2, w |phi0|, -}
-  double* Ys = reinterpret_cast<double*>(cU + nU);              // [cap][pitch]  rows of Yh_i
-  double* YB = Ys + (int64_t)cap * pitch;                       // [cap][bp]     Y_T[node, B_i]
-  double* ZWs = YB + cap * bp;                                  // [cap][bp+1]   ZW_i[node, :]
-  double* yes = ZWs + cap * zp;                                 // [cap]         y_e[node]
-  double* phs = yes + cap;                                      // [cap]         phi0[node]
-  double* ybuf = phs + cap;                                     // [6][32]       Re y0..2, Im y0..2
-  double* gbuf = ybuf + 6 * 32;                                 // [6][32]       corrected 3x3 blocks
+  const int zp = bp + 1;                                         // odd stride of the small per-node arrays
+  const int nUp = (nU + 1) & ~1, Lp = (L + 1) & ~1, cst_len = 3 * nUp + Lp;
+  const bool bulk = (nU & 1) == 0;                               // 16-byte aligned rows: TMA bulk copies
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);         // 16 bytes reserved
+  double* cst = reinterpret_cast<double*>(smem_raw + 16);        // [3 nUp + Lp]  per-excitation constants (SoA)
+  double* Ys = cst + cst_len;                                    // [cap][pitch]  rows of Yh_i
+  double* YB = Ys + (int64_t)cap * pitch;                        // [cap][zp]     Y_T[node, B_i]
+  double* ZWs = YB + cap * zp;                                   // [cap][zp]     ZW_i[node, :]
+  double* yes = ZWs + cap * zp;                                  // [cap]         y_e[node]
+  double* phs = yes + cap;                                       // [cap]         phi0[node]
+  double* ybuf = phs + cap;                                      // [6][32]       Re y0..2, Im y0..2
+  double* gbuf = ybuf + 6 * 32;                                  // [6][32]       corrected 3x3 blocks
   const double* Y = Yh + (int64_t)b * N * nU;
   const double* ph = phi0 + (int64_t)b * N;
   const double* Z = ZW + (int64_t)b * zp;                        // ZW is N x (nbatch zp), excitation b's columns
   const int64_t ldz = (int64_t)nbatch * zp;
-  // node positions of the patch: one coalesced load, then everything is staged with cp.async (no load -> store
-  // round trips in the staging loop)
+  const double* cg = node_consts + (int64_t)b * cst_len;
+  WB_CLK(0);
+  if (threadIdx.x == 0 && bulk) mbar_init(bar, 1);
+  // node positions of the patch: one coalesced load
   const int pn_a = (lane < nn) ? patch_nodes[n_beg + lane] : 0;
   const int pn_b = (lane + 32 < nn) ? patch_nodes[n_beg + lane + 32] : 0;
+  __syncthreads();                                               // barrier initialised before anyone polls it
+  WB_CLK(1);
+  if (bulk) {
+    // warp 0: one bulk copy per node row of Yh_i (lane = node) + the constants; everything lands on `bar`
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_expect_tx(bar, (uint32_t)(((int64_t)nn * nU + cst_len) * 8));
+        bulk_g2s(cst, cg, (uint32_t)(cst_len * 8), bar);
+      }
+      __syncwarp();
+      if (lane < nn) bulk_g2s(Ys + (int64_t)lane * pitch, Y + (int64_t)pn_a * nU, (uint32_t)(nU * 8), bar);
+      if (lane + 32 < nn) bulk_g2s(Ys + (int64_t)(lane + 32) * pitch, Y + (int64_t)pn_b * nU, (uint32_t)(nU * 8), bar);
+    }
+  } else {
+    for (int n = warp; n < nn; n += WARPS) {
+      const int64_t p = __shfl_sync(0xffffffffu, (n < 32) ? pn_a : pn_b, n & 31);
+      for (int k = lane; k < nU; k += 32) cp_async8(Ys + (int64_t)n * pitch + k, Y + p * nU + k, true);
+    }
+    for (int k = threadIdx.x; k < cst_len; k += WARPS * 32) cp_async8(cst + k, cg + k, true);
+  }
+  // the small per-node arrays (unaligned sources): 8-byte cp.async, a few instructions per warp
   for (int n = warp; n < nn; n += WARPS) {
     const int64_t p = __shfl_sync(0xffffffffu, (n < 32) ? pn_a : pn_b, n & 31);
-    const double* ys = Y + p * nU;
-    double* yd = Ys + (int64_t)n * pitch;
-    for (int k = lane; k < nU; k += 32) cp_async8(yd + k, ys + k, true);
-    for (int k = lane; k < nb; k += 32) cp_async8(YB + n * bp + k, YT + p * nU + lo + k, true);
+    for (int k = lane; k < nb; k += 32) cp_async8(YB + n * zp + k, YT + p * nU + lo + k, true);
     for (int k = lane; k < zp; k += 32) cp_async8(ZWs + n * zp + k, Z + p * ldz + k, true);
     if (lane == 0) cp_async8(yes + n, ye + p, true);
     if (lane == 1) cp_async8(phs + n, ph + p, true);
   }
   cp_async_commit();
-  {
-    const double4* cg = node_consts + (int64_t)b * nU;
-    for (int k = threadIdx.x; k < nU; k += WARPS * 32) cU[k] = cg[k];
-  }
+  WB_CLK(2);
   const bool have = lane < ne;
   const int lq = have ? lane : 0;
   const int j = patch_elems[el_beg + lq];
@@ -1019,10 +1127,12 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
   double gq = 0.0, sj = 0.0;
   if (warp < 6) gq = g1e[6 * (int64_t)j + warp];
   if (warp == 0) sj = s_coef * area[j];
+  WB_CLK(3);
   cp_async_wait<0>();
-  __syncthreads();
+  __syncthreads();                                               // the small arrays of every warp are visible
+  WB_CLK(4);
   if (warp < 6) {
-    const double* yb = YB + la * bp;
+    const double* yb = YB + la * zp;
     const double* zw = ZWs + lb * zp;
     double a0 = yes[la] * zw[bp], a1 = 0.0;
     int jj = 0;
@@ -1034,6 +1144,7 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
     gbuf[warp * 32 + lane] = gq + (a0 + a1);
   }
   __syncthreads();
+  WB_CLK(5);
   // ---- one warp: the 3x3 solve, one lane per element -----------------------------------------------------
   if (warp == 0) {
     double g6[6];
@@ -1048,31 +1159,63 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
       ybuf[(3 + a) * 32 + lane] = yi[a];
     }
   }
+  if (bulk) mbar_wait(bar, 0);                                   // the Yh rows and constants (async proxy) have landed
   __syncthreads();
+  WB_CLK(6);
   const double yr0 = ybuf[lane], yr1 = ybuf[32 + lane], yr2 = ybuf[64 + lane];
   const double yi0 = ybuf[96 + lane], yi1 = ybuf[128 + lane], yi2 = ybuf[160 + lane];
   const double* y0 = Ys + (int64_t)l0 * pitch;
   const double* y1 = Ys + (int64_t)l1 * pitch;
   const double* y2 = Ys + (int64_t)l2 * pitch;
+  const double *cx = cst, *cy = cst + nUp, *cz = cst + 2 * nUp, *s0 = cst + 3 * nUp;
   // ---- amplitudes and weighted sums of this warp's electrodes -------------------------------------------
+  // term(k) = w |phi0| (sqrt(1 + x) - 1), x = (2 phi0 dr + |d|^2) / phi0^2 (phi0 real); two nodes per 16-byte load
+#define CEIT_WB_TERM(ACC, A0, A1, A2, CX, CY, CZ)                 \
+  {                                                               \
+    const double dr = fma(A0, yr0, fma(A1, yr1, (A2) * yr2));     \
+    const double di = fma(A0, yi0, fma(A1, yi1, (A2) * yi2));     \
+    const double qq = fma(dr, dr, di * di);                       \
+    const double x = fma(CX, dr, qq * (CY));                      \
+    hmax = max(hmax, abs_hi(x));                                  \
+    ACC = fma(CZ, sqrt1p_minus1_poly(x), ACC);                    \
+  }
   const bool write = have && j >= e_from && j < e_to;
   for (int m = warp; m < L; m += WARPS) {
     if (m == i) continue;
     const int ks = ue_ptr[m], ke = ue_ptr[m + 1];
-    double sum0 = 0.0, sumt = 0.0;
-#pragma unroll 4
-    for (int k = ks; k < ke; ++k) {
-      const double4 cu = cU[k];
-      const double a0 = y0[k], a1 = y1[k], a2 = y2[k];
-      const double dr = fma(a0, yr0, fma(a1, yr1, a2 * yr2));
-      const double di = fma(a0, yi0, fma(a1, yi1, a2 * yi2));
-      const double qq = fma(dr, dr, di * di);
-      const double x = fma(cu.x, dr, qq * cu.y);         // (2 phi0 dr + |d|^2) / phi0^2, phi0 real
-      sum0 += cu.z;
-      sumt = fma(cu.z, sqrt1p_minus1(x), sumt);
+    double sumt = 0.0, sumu = 0.0;
+    unsigned hmax = 0u;
+    int k = ks;
+    if ((k & 1) && k < ke) {
+      CEIT_WB_TERM(sumt, y0[k], y1[k], y2[k], cx[k], cy[k], cz[k]);
+      ++k;
     }
-    if (write) J[((int64_t)i * (L - 1) + m - (m > i ? 1 : 0)) * ldJ + j] = fabs(sum0 + sumt);
+#pragma unroll 2
+    for (; k + 1 < ke; k += 2) {
+      const double2 a0 = *reinterpret_cast<const double2*>(y0 + k);
+      const double2 a1 = *reinterpret_cast<const double2*>(y1 + k);
+      const double2 a2 = *reinterpret_cast<const double2*>(y2 + k);
+      const double2 vx = *reinterpret_cast<const double2*>(cx + k);
+      const double2 vy = *reinterpret_cast<const double2*>(cy + k);
+      const double2 vz = *reinterpret_cast<const double2*>(cz + k);
+      CEIT_WB_TERM(sumt, a0.x, a1.x, a2.x, vx.x, vy.x, vz.x);
+      CEIT_WB_TERM(sumu, a0.y, a1.y, a2.y, vx.y, vy.y, vz.y);
+    }
+    if (k < ke) CEIT_WB_TERM(sumt, y0[k], y1[k], y2[k], cx[k], cy[k], cz[k]);
+    sumt += sumu;
+    if (hmax >= SQRT1P_HI_LIMIT) {                       // rare: a large perturbation, exact square roots
+      sumt = 0.0;
+      for (int q = ks; q < ke; ++q) {
+        const double dr = fma(y0[q], yr0, fma(y1[q], yr1, y2[q] * yr2));
+        const double di = fma(y0[q], yi0, fma(y1[q], yi1, y2[q] * yi2));
+        const double qq = fma(dr, dr, di * di);
+        sumt = fma(cz[q], sqrt1p_minus1(fma(cx[q], dr, qq * cy[q])), sumt);
+      }
+    }
+    if (write) J[((int64_t)i * (L - 1) + m - (m > i ? 1 : 0)) * ldJ + j] = fabs(s0[m] + sumt);
   }
+#undef CEIT_WB_TERM
+  WB_CLK(7);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -570,10 +570,48 @@ void build_patches(HostPlan& p, int32_t node_cap, int32_t elem_cap) {
     }
     for (int32_t e : queue)
       if (!done[e]) queued[e] = 0;
-    for (int32_t v : cur_nodes) {
-      local_of[v] = -1;
-      p.patch_nodes.push_back(p.pos[v]);
+    // Shared-memory slot of every patch node.  The Woodbury kernel reads, per 16-byte load, one staged row per lane
+    // (lane = element, one load per corner); the 8 lanes of a quarter warp are conflict-free when their DISTINCT
+    // rows have distinct slot numbers mod 8 (woodbury_lr_pitch).  Greedy: nodes that appear in the most
+    // (quarter, corner) groups first, each takes the free slot whose residue collides least inside its groups.
+    {
+      const int32_t nn = (int32_t)cur_nodes.size();
+      const size_t l_beg = 3 * (size_t)p.patch_eptr.back();
+      const int32_t ne = (int32_t)(p.patch_elems.size() - (size_t)p.patch_eptr.back());
+      const int32_t n_groups = 3 * ((ne + 7) / 8);
+      std::vector<std::vector<int32_t>> groups_of(nn);
+      for (int32_t l = 0; l < ne; ++l)
+        for (int a = 0; a < 3; ++a) {
+          const int32_t v = p.patch_local[l_beg + 3 * l + a], g = 3 * (l / 8) + a;
+          if (std::find(groups_of[v].begin(), groups_of[v].end(), g) == groups_of[v].end()) groups_of[v].push_back(g);
+        }
+      std::vector<int32_t> order(nn), slot_of(nn, -1), cnt((size_t)n_groups * 8, 0);
+      for (int32_t v = 0; v < nn; ++v) order[v] = v;
+      std::stable_sort(order.begin(), order.end(),
+                       [&](int32_t a, int32_t b) { return groups_of[a].size() > groups_of[b].size(); });
+      std::vector<uint8_t> used(nn, 0);
+      for (int32_t v : order) {
+        int32_t best = -1, best_cost = 1 << 30;
+        for (int32_t sl = 0; sl < nn; ++sl) {
+          if (used[sl]) continue;
+          int32_t cost = 0;
+          for (int32_t g : groups_of[v]) cost += cnt[(size_t)g * 8 + (sl & 7)];
+          if (cost < best_cost) {
+            best_cost = cost;
+            best = sl;
+          }
+        }
+        used[best] = 1;
+        slot_of[v] = best;
+        for (int32_t g : groups_of[v]) cnt[(size_t)g * 8 + (best & 7)]++;
+      }
+      std::vector<int32_t> by_slot(nn);
+      for (int32_t v = 0; v < nn; ++v) by_slot[slot_of[v]] = cur_nodes[v];
+      for (size_t q = l_beg; q < p.patch_local.size(); ++q) p.patch_local[q] = (uint8_t)slot_of[p.patch_local[q]];
+      for (int32_t v : cur_nodes) local_of[v] = -1;
+      cur_nodes = by_slot;
     }
+    for (int32_t v : cur_nodes) p.patch_nodes.push_back(p.pos[v]);
     p.patch_eptr.push_back((int32_t)p.patch_elems.size());
     p.patch_nptr.push_back((int32_t)p.patch_nodes.size());
   }

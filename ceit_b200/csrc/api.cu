@@ -296,7 +296,7 @@ int alloc_numeric(ceit_plan* p) {
   if ((rc = dev_alloc(p, &p->ye, h.N * es))) return rc;
   if (!p->d_gamma && (rc = dev_alloc(p, (void**)&p->d_gamma, sizeof(double)))) return rc;
   if ((rc = dev_alloc(p, &p->g1e, 6 * h.E * es))) return rc;
-  if ((rc = dev_alloc(p, &p->splitk_ws, (size_t)splitk_slices(h.nU, h.nU, h.N0P) * h.nU * h.nU * sizeof(double)))) return rc;
+  if ((rc = dev_alloc(p, &p->splitk_ws, (size_t)splitk_slices(h.nU, h.nU, h.N0P, 1) * h.nU * h.nU * sizeof(double)))) return rc;
   if ((rc = dev_alloc(p, &p->KUU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->SU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Ptmp, maxS * es))) return rc;
@@ -388,8 +388,14 @@ inline void launch_g1(ceit_plan*, const cd*, const cd*, const cd*, cudaStream_t)
 
 inline void schur_u_gemm(ceit_plan* p, cudaStream_t st, int64_t nU, int64_t N0P, const double* K0U, const double* X,
                          double* SU) {
-  gemm_splitk(st, 1, 0, nU, nU, N0P, -1.0, K0U, nU, X, nU, 1.0, SU, nU, (double*)p->splitk_ws);
+  // K_0U^T K00^-1 K_0U is symmetric: only the lower triangle is accumulated; symmetrize_su() mirrors it afterwards
+  gemm_splitk(st, 1, 0, nU, nU, N0P, -1.0, K0U, nU, X, nU, 1.0, SU, nU, (double*)p->splitk_ws, /*lower_only=*/1);
 }
+inline void symmetrize_su(cudaStream_t st, int64_t nU, double* SU) {
+  symmetrize_from_lower_kernel<<<cdiv(nU * nU, 256), 256, 0, st>>>(nU, SU, nU);
+  CEIT_COUNT_LAUNCH();
+}
+inline void symmetrize_su(cudaStream_t, int64_t, cd*) {}   // the complex path forms the full product
 inline void schur_u_gemm(ceit_plan*, cudaStream_t st, int64_t nU, int64_t N0P, const cd* K0U, const cd* X, cd* SU) {
   gemm<cd>(st, 1, 0, nU, nU, N0P, neg(Sc<cd>::one()), K0U, nU, 0, X, nU, 0, Sc<cd>::one(), SU, nU, 0);
 }
@@ -544,6 +550,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   // dimensions: split-K on the real path.
   if (P > 0) schur_u_gemm(p, sr, nU, NI, K0U, Xh, SU);
   if (nC > 0) schur_u_gemm(p, sr, nU, nC, Xh + NI * nU, Xh + NI * nU, SU);
+  if (P > 0 || nC > 0) symmetrize_su(sr, nU, SU);
   cudaStream_t s_t = sr;
   if (g_multi_stream) {
     s_t = p->s3;
@@ -732,9 +739,15 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
   CEIT_COUNT_LAUNCH();
   phi_u_kernel<T><<<g3, 256, 0, sx>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 3);
   CEIT_COUNT_LAUNCH();
-  dim3 g4(cdiv(N0, 8), nbatch);
-  phi_f_kernel<T><<<g4, 256, 0, sx>>>(N0, (int)nU, Xh, phi0, N);
-  CEIT_COUNT_LAUNCH();
+  if (nbatch >= 4) {
+    // phi_F0 = -X phi_U for all excitations of the chunk as ONE product (X is read once, not once per excitation):
+    // Phi^T (nbatch x N0) = -Phi_U^T (nbatch x nU, the tail of each phi0 row) X^T
+    gemm<T>(sx, 0, 1, nbatch, N0, nU, neg(one), phi0 + N0, N, 0, Xh, nU, 0, zero, phi0, N, 0, 1);
+  } else {
+    dim3 g4(cdiv(N0, 8), nbatch);
+    phi_f_kernel<T><<<g4, 256, 0, sx>>>(N0, (int)nU, Xh, phi0, N);
+    CEIT_COUNT_LAUNCH();
+  }
   CEIT_AFTER(sx, st);
   KERNEL_CHECK();
   return 0;
@@ -1065,10 +1078,10 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
   if (form == 2) {
     // G = Jt Jt^T + lambda^2 I (m x m);  inv = Jt^T G^-1
     {
-      const int S = splitk_slices(n, n, n_det);
+      const int S = splitk_slices(n, n, n_det, 1);
       double* ws = nullptr;
       if (S > 1) CUDA_TRY(cudaMallocAsync((void**)&ws, (size_t)S * n * n * sizeof(double), st));
-      if (S > 1) gemm_splitk(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, Jt, n_det, 0.0, G, n, ws);
+      if (S > 1) gemm_splitk(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, Jt, n_det, 0.0, G, n, ws, /*lower_only=*/1);
       else gemm<double>(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0, 1, /*lower_only=*/1);
       if (ws) CUDA_TRY(cudaFreeAsync(ws, st));
     }
@@ -1113,7 +1126,17 @@ int ceit_gram_partial(const double* J, int64_t ldJ, int64_t m, const int64_t* de
   CUDA_TRY(cudaMallocAsync((void**)&Jt, m_sel * n_det * sizeof(double), st));
   gather_shift_kernel<<<cdiv(m_sel * n_det, 256), 256, 0, st>>>(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
   CEIT_COUNT_LAUNCH();
-  gemm<double>(st, 0, 1, m_sel, m_sel, n_det, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, m_sel, 0);
+  {
+    // symmetric: lower triangle only (split over K when its tiles cannot fill the chip), then mirrored so that the
+    // all-reduce over the ranks sums a complete matrix
+    const int S = splitk_slices(m_sel, m_sel, n_det, 1);
+    double* ws = nullptr;
+    if (S > 1) CUDA_TRY(cudaMallocAsync((void**)&ws, (size_t)S * m_sel * m_sel * sizeof(double), st));
+    gemm_splitk(st, 0, 1, m_sel, m_sel, n_det, 1.0, Jt, n_det, Jt, n_det, 0.0, G, m_sel, ws, /*lower_only=*/1);
+    if (ws) CUDA_TRY(cudaFreeAsync(ws, st));
+    symmetrize_from_lower_kernel<<<cdiv(m_sel * m_sel, 256), 256, 0, st>>>(m_sel, G, m_sel);
+    CEIT_COUNT_LAUNCH();
+  }
   KERNEL_CHECK();
   CUDA_TRY(cudaFreeAsync(Jt, st));
   return CEIT_OK;

@@ -540,17 +540,41 @@ inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N
 // is cut into `S` slices that run as one strided batch into partial results, then summed in fixed order.
 // ------------------------------------------------------------------------------------------------
 __global__ void splitk_reduce_kernel(int64_t n, int S, const double* __restrict__ P, double beta, double* __restrict__ C,
-                                     int64_t M, int64_t N, int64_t ldc) {
+                                     int64_t M, int64_t N, int64_t ldc, int lower_only) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
+  const int64_t r = q / N, c = q - r * N;
+  if (lower_only && c > r) return;                    // the slices only hold the tiles on and below the diagonal
   double acc = 0.0;
   for (int s = 0; s < S; ++s) acc += P[(int64_t)s * n + q];
-  const int64_t r = q / N, c = q - r * N;
   double* p = C + r * ldc + c;
   *p = (beta != 0.0) ? fma(beta, *p, acc) : acc;
 }
+// A[r][c] = A[c][r] for c > r (after a lower-only symmetric product)
+__global__ void symmetrize_from_lower_kernel(int64_t n, double* __restrict__ A, int64_t lda) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n * n) return;
+  const int64_t r = q / n, c = q - r * n;
+  if (c > r) A[r * lda + c] = A[c * lda + r];
+}
 
-inline int splitk_slices(int64_t M, int64_t N, int64_t K) {
+// Number of K slices.  Monotone in K (workspaces are sized with the largest K of a call site).
+//  * small outputs (< 384 wide): 32x32 tiles, ~4 CTAs per SM, slices >= 256 deep;
+//  * large outputs whose 64x64 tiles (only those on/below the diagonal when lower_only) cannot fill the chip
+//    (the 400x400-mesh Gram matrix: 136 tiles with K = 257 762; its S_U: 45 tiles with K = 160 000):
+//    slices >= 2048 deep, ~4 CTAs per SM.
+inline bool splitk_large(int64_t M, int64_t N) { return (M < N ? M : N) >= 384; }
+inline int splitk_slices(int64_t M, int64_t N, int64_t K, int lower_only = 0) {
+  if (splitk_large(M, N)) {
+    const int64_t tm = (M + 63) / 64, tn = (N + 63) / 64;
+    const int64_t t64 = (lower_only && M == N) ? tm * (tm + 1) / 2 : tm * tn;
+    if (t64 >= 444 || K < 8192) return 1;
+    int64_t S = (592 + t64 - 1) / t64;
+    const int64_t maxS = K / 2048;
+    if (S > maxS) S = maxS;
+    if (S > 64) S = 64;
+    return (int)(S < 2 ? 1 : S);
+  }
   const int64_t tiles = ((M + 31) / 32) * ((N + 31) / 32);
   if (K < 1024 || tiles >= 296) return 1;
   int64_t S = (592 + tiles - 1) / tiles;              // aim at ~4 CTAs per SM
@@ -560,27 +584,33 @@ inline int splitk_slices(int64_t M, int64_t N, int64_t K) {
   return (int)(S < 2 ? 1 : S);
 }
 
-// workspace: at least splitk_slices(M, N, K) * M * N doubles (ignored when no split is used)
+// workspace: at least splitk_slices(M, N, K, lower_only) * M * N doubles (ignored when no split is used).
+// lower_only (M == N, symmetric result): only the entries on and below the diagonal of C are produced.
 inline void gemm_splitk(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
                         int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
-                        double* workspace) {
-  const int S = workspace ? splitk_slices(M, N, K) : 1;
+                        double* workspace, int lower_only = 0) {
+  const int S = workspace ? splitk_slices(M, N, K, lower_only) : 1;
   if (S <= 1) {
-    gemm<double>(st, opA, opB, M, N, K, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0);
+    gemm<double>(st, opA, opB, M, N, K, alpha, A, lda, 0, B, ldb, 0, beta, C, ldc, 0, 1, lower_only);
     return;
   }
   int64_t Ks = ((K + S - 1) / S + 15) / 16 * 16;
   const int full = (int)(K / Ks);                     // slices of exactly Ks
   const int64_t rem = K - (int64_t)full * Ks;
   const int64_t sA = (opA == 0) ? Ks : Ks * lda, sB = (opB == 0) ? Ks * ldb : Ks;
-  if (full > 0) gemm<double>(st, opA, opB, M, N, Ks, alpha, A, lda, sA, B, ldb, sB, 0.0, workspace, N, M * N, full);
+  const int tile_keep = g_gemm_tile;
+  if (splitk_large(M, N) && g_gemm_tile == 0) g_gemm_tile = 2;   // every slice (and the remainder) on 64x64 tiles
+  if (full > 0)
+    gemm<double>(st, opA, opB, M, N, Ks, alpha, A, lda, sA, B, ldb, sB, 0.0, workspace, N, M * N, full, lower_only);
   int parts = full;
   if (rem > 0) {
     gemm<double>(st, opA, opB, M, N, rem, alpha, A + (int64_t)full * sA, lda, 0, B + (int64_t)full * sB, ldb, 0, 0.0,
-                 workspace + (int64_t)full * M * N, N, 0, 1);
+                 workspace + (int64_t)full * M * N, N, 0, 1, lower_only);
     ++parts;
   }
-  splitk_reduce_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(M * N, parts, workspace, beta, C, M, N, ldc);
+  g_gemm_tile = tile_keep;
+  splitk_reduce_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(M * N, parts, workspace, beta, C, M, N, ldc,
+                                                                       lower_only);
   CEIT_COUNT_LAUNCH();
 }
 

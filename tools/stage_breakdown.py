@@ -40,7 +40,7 @@ if cplx: var += 3e-8
 big = len(det_h) * L * (L - 1) * 8 > 20e9
 step(not big); torch.cuda.synchronize()
 _lib.set_option("stage_timers", 1); _lib.stage_times(); l0 = _lib.launch_count()
-reps = 3
+reps = int(os.environ.get("CEIT_REPS", "3"))
 t0 = time.time()
 for _ in range(reps): step(not big)
 torch.cuda.synchronize(); wall = (time.time() - t0) / reps

@@ -50,6 +50,8 @@ constexpr int N_STAGES = 8;
 int g_stage_timers = 0;
 int g_no_patch = 0;
 int g_no_lowrank = 0;
+int g_ex_overlap = 1;   // excitation stage: ZW / base potentials on a second stream beside the Yh update
+int g_ru_wc = 0, g_ru_cpt = 0, g_ru_waves = 8;   // rank_update_kernel layout overrides (tuning; 0 = auto)
 int g_direct_excitation = 0;
 int g_patch_nodes = 0;   // experiment: override the node cap of the element patches
 int64_t g_nd_interior = 64;   // target nodes per nested-dissection interior; <= 0 disables level 1
@@ -525,14 +527,22 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
     gemm<T>(srb, 0, 0, nk, nU, nk, one, Lik, nk, 0, Zw + r0 * nU, nU, 0, zero, Xh + r0 * nU, nU, 0);
     // Vsub_k = Linv_k B_{k-1} (n_k x n_{k-1}, stored in the slot of B_{k-1}) ; A_{k-1} -= Vsub_k^T Vsub_k
     gemm<T>(sb, 0, 0, nk, np, nk, one, Lik, nk, 0, Bs + h.offS[k - 1], np, 0, zero, Lsub + h.offS[k - 1], np, 0);
-    gemm<T>(sb, 1, 0, np, np, nk, mone, Lsub + h.offS[k - 1], np, 0, Lsub + h.offS[k - 1], np, 0, one,
-            Ad + h.offD[k - 1], np, 0, 1, /*lower_only=*/1);
+    // The update of the MIDDLE block is issued on st after the arms have joined: the downward arm accumulates into
+    // the same block (a read-modify-write from two streams loses updates).
+    if (k - 1 != mid)
+      gemm<T>(sb, 1, 0, np, np, nk, mone, Lsub + h.offS[k - 1], np, 0, Lsub + h.offS[k - 1], np, 0, one,
+              Ad + h.offD[k - 1], np, 0, 1, /*lower_only=*/1);
   }
   if (nbk > 0) {                                                       // middle block: both arms meet
     const int64_t nk = n_of(mid), r0 = row_of(mid);
     T* Lik = Linv + h.offD[mid];
     CEIT_AFTER(sb, st);
     CEIT_AFTER(srb, sr);
+    if (mid + 1 < nbk) {
+      const int64_t nn = n_of(mid + 1);
+      gemm<T>(st, 1, 0, nk, nk, nn, mone, Lsub + h.offS[mid], nk, 0, Lsub + h.offS[mid], nk, 0, one, Ad + h.offD[mid], nk,
+              0, 1, /*lower_only=*/1);
+    }
     if ((rc = factor_block(mid, st, sr, tmpPanel, &p->lane_a))) return rc;
     if (mid > 0) {
       const int64_t np = n_of(mid - 1), rp = row_of(mid - 1);
@@ -674,9 +684,11 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
       CUDA_TRY(cudaFuncSetAttribute(excite_small_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-#define CEIT_RU_ATTR(c) \
-  CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
-      CEIT_RU_ATTR(1); CEIT_RU_ATTR(2); CEIT_RU_ATTR(3);
+#define CEIT_RU_ATTR(c, w) \
+  CUDA_TRY(cudaFuncSetAttribute(rank_update_kernel<T, c, w>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024))
+      CEIT_RU_ATTR(1, 1); CEIT_RU_ATTR(2, 1); CEIT_RU_ATTR(3, 1);
+      CEIT_RU_ATTR(1, 2); CEIT_RU_ATTR(2, 2); CEIT_RU_ATTR(3, 2);
+      CEIT_RU_ATTR(1, 4); CEIT_RU_ATTR(2, 4); CEIT_RU_ATTR(3, 4);
 #undef CEIT_RU_ATTR
       attr_done = true;
     }
@@ -684,30 +696,47 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
                                                     stage_rows);
     CEIT_COUNT_LAUNCH();
     auto update = [&](cudaStream_t su, int64_t rows, const T* src, const T* yv, int zero_rows, T* out, int64_t stride) {
-      // columns in chunks of <= 384 (3 per thread) so that the staged part of D_i stays small enough for
-      // several CTAs per SM; D_i is staged once per CTA, so a CTA takes several row tiles, but keep >= 2 waves
-      const int nz = (int)cdiv(nU, 384);
-      const int cw = (int)cdiv(nU, nz);
-      const int cpt = (cw + 127) / 128;
-      const int rt = Sc<T>::is_complex ? 8 : 16;                             // rows per pass (kernel: 2 RH)
-      const size_t smu = (size_t)((bp + 1) * 128 * cpt + 16 * (bp + 1)) * es;
+      // column chunks of 32 WC CPT (WC warps across, CPT columns per thread): least cost over all chunks, where a
+      // padded column costs max(shared-memory wavefronts, FP64 issue) per useful FMA of a thread's RH x CPT tile
+      // (CPT = 3: 14/24, 2: 12/16, 1: 10/8 - the RH broadcast loads of the A column are shared by CPT columns);
+      // ties go to the widest chunk (D_i is staged once per CTA, fewer re-reads of the A columns)
+      int best_wc = 4, best_cpt = 3, best_nz = (int)cdiv(nU, 384);
+      double best_cost = 1e300;
+      for (int wc : {4, 2, 1})
+        for (int cpt = 3; cpt >= 1; --cpt) {
+          const int w = 32 * wc * cpt;
+          const int nzc = (int)cdiv(nU, w);
+          const double cost = (double)nzc * w * (cpt == 3 ? 14.0 / 24 : (cpt == 2 ? 12.0 / 16 : 10.0 / 8));
+          if (cost < best_cost * (1 - 1e-9)) { best_cost = cost; best_wc = wc; best_cpt = cpt; best_nz = nzc; }
+        }
+      if (g_ru_wc > 0 && g_ru_cpt > 0) {
+        best_wc = g_ru_wc; best_cpt = g_ru_cpt; best_nz = (int)cdiv(nU, 32 * best_wc * best_cpt);
+      }
+      const int wc = best_wc, cpt = best_cpt, nz = best_nz;
+      const int cw = (int)std::min<int64_t>(32 * wc * cpt, nU);              // chunk width (last chunk may be short)
+      const int rt = (Sc<T>::is_complex ? 4 : 8) * (8 / wc);                  // rows per pass
+      const size_t smu = (size_t)((bp + 1) * 32 * wc * cpt + rt * (bp + 1)) * es;
       const int64_t tiles = cdiv(rows, rt);
-      // one wave of persistent-style CTAs: D_i is staged once per CTA, each CTA walks `passes` row tiles
-      const int64_t slots = 148 * std::max<int64_t>(1, std::min<int64_t>(2, (200 * 1024) / (int64_t)smu));
-      const int64_t groups = std::max<int64_t>(1, slots / ((int64_t)nbatch * nz));     // CTAs per (excitation, chunk)
+      // CTAs per (excitation, chunk): with plenty of row tiles ~8 waves of CTAs (the hardware scheduler balances the
+      // SMs) that each walk >= 32 tiles, so staging D_i stays a few per cent of a CTA's work; small problems fill
+      // one wave instead
+      const int64_t per = (int64_t)nbatch * nz;
+      const int64_t g_fill = cdiv(296, per), g_waves = std::max<int64_t>(1, (148 * 2 * (int64_t)g_ru_waves) / per);
+      const int64_t groups = std::max<int64_t>(1, std::min<int64_t>(tiles, std::max(g_fill, std::min(g_waves, tiles / 32))));
       const int passes = (int)std::max<int64_t>(1, cdiv(tiles, groups));
       dim3 grid(nbatch, cdiv(tiles, passes), nz);
-#define CEIT_RU(c) rank_update_kernel<T, c><<<grid, 256, smu, su>>>(rows, (int)nU, bp, src, yv, Dcat, p->d_ue_ptr, i0, \
-                                                                  zero_rows, out, stride, passes, cw)
-      if (cpt <= 1) CEIT_RU(1);
-      else if (cpt == 2) CEIT_RU(2);
-      else CEIT_RU(3);
+#define CEIT_RU(c, w) rank_update_kernel<T, c, w><<<grid, 256, smu, su>>>(rows, (int)nU, bp, src, yv, Dcat, p->d_ue_ptr, \
+                                                                        i0, zero_rows, out, stride, passes, cw)
+#define CEIT_RU_W(w) \
+  if (cpt == 1) CEIT_RU(1, w); else if (cpt == 2) CEIT_RU(2, w); else CEIT_RU(3, w)
+      if (wc == 1) { CEIT_RU_W(1); } else if (wc == 2) { CEIT_RU_W(2); } else { CEIT_RU_W(4); }
+#undef CEIT_RU_W
 #undef CEIT_RU
       CEIT_COUNT_LAUNCH();
     };
     update(st, nU, Tinv, te, 1, Sinv, u2);
     // the big materialisation Yh_i (st) runs beside ZW and the baseline potentials (sx), which only need Sinv
-    if (g_multi_stream) {
+    if (g_multi_stream && g_ex_overlap) {
       if (int rc_ = ensure_aux_stream(p)) return rc_;
       sx = p->s2;
       CEIT_AFTER(st, sx);
@@ -1278,6 +1307,10 @@ int ceit_set_option(const char* name, int64_t value) {
     g_multi_stream = (int)value;
     return CEIT_OK;
   }
+  if (std::strcmp(name, "excitation_overlap") == 0) { g_ex_overlap = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "ru_wc") == 0) { g_ru_wc = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "ru_cpt") == 0) { g_ru_cpt = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "ru_waves") == 0) { g_ru_waves = (int)std::max<int64_t>(1, value); return CEIT_OK; }
   if (std::strcmp(name, "patch_nodes") == 0) {
     g_patch_nodes = (int)value;
     return CEIT_OK;

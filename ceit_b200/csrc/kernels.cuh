@@ -358,19 +358,22 @@ excite_small_kernel(int nU, int bp, const T* __restrict__ Tm, const T* __restric
   }
 }
 // out[b][n,k] = src[n,k] - sum_{j<b} src[n, lo+j] D[j,k] + yv[n] D[bp,k]; columns (and, if zero_rows, rows)
-// of B_i are set to exactly zero.  CTA = one excitation x `passes` tiles of RT rows x all columns: D_i is
-// staged in shared memory once per CTA; 128 threads span the columns (CPT = ceil(nU / 128) each), the two
-// thread halves take alternate rows of the tile.
-template <class T, int CPT>
+// of B_i are set to exactly zero.  CTA = one excitation x `passes` tiles of RT rows x one column chunk: D_i is
+// staged in shared memory once per CTA.  The 8 warps form WC column groups x 8/WC row groups: a thread owns
+// CPT columns (32 WC apart) of RH rows (8/WC apart), so a chunk is 32 WC CPT columns wide and the host picks
+// (WC, CPT, number of chunks) with the least padding (nU = 544: 2 x 3 x 3 chunks = 576; nU = 264: 1 x 3 x 3 = 288).
+template <class T, int CPT, int WC>
 __global__ void __launch_bounds__(256)
 rank_update_kernel(int64_t rows, int nU, int bp, const T* __restrict__ src, const T* __restrict__ yv,
                    const T* __restrict__ Dcat, const int32_t* __restrict__ ue_ptr, int i0, int zero_rows,
                    T* __restrict__ out, int64_t out_stride, int passes, int cw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int RH = Sc<T>::is_complex ? 4 : 8;   // rows per thread
-  constexpr int RT = 2 * RH;                       // rows per pass (power of two)
-  constexpr int CWP = 128 * CPT;                   // padded chunk width: no column predicates in the inner loop
-  const int tid = threadIdx.x, tx = tid & 127, ty = tid >> 7;
+  constexpr int TXN = 32 * WC;                     // threads across the columns
+  constexpr int NY = 256 / TXN;                    // row groups
+  constexpr int RT = NY * RH;                      // rows per pass (power of two)
+  constexpr int CWP = TXN * CPT;                   // padded chunk width: no column predicates in the inner loop
+  const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
   const int i = i0 + blockIdx.x;      // excitation fastest: the CTAs that share a row tile of src run together
   const int lo = ue_ptr[i], b = ue_ptr[i + 1] - lo;
   const int k_lo = blockIdx.z * cw, kw = min(cw, nU - k_lo);
@@ -386,7 +389,7 @@ rank_update_kernel(int64_t rows, int nU, int bp, const T* __restrict__ src, cons
   bool keep[CPT];                       // column inside the chunk and not a Dirichlet column of this excitation
 #pragma unroll
   for (int c = 0; c < CPT; ++c) {
-    const int k = tx + 128 * c, kg = k_lo + k;
+    const int k = tx + TXN * c, kg = k_lo + k;
     keep[c] = k < kw && !(kg >= lo && kg < lo + b);
   }
   T* o = out + (int64_t)blockIdx.x * out_stride + k_lo + tx;
@@ -406,10 +409,10 @@ rank_update_kernel(int64_t rows, int nU, int bp, const T* __restrict__ src, cons
       const T* sp = sbase + (n0 + ty) * nU;
 #pragma unroll
       for (int r = 0; r < RH; ++r) {
-        const bool rok = n0 + 2 * r + ty < rows;
+        const bool rok = n0 + NY * r + ty < rows;
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) acc[r][c] = (rok && tx + 128 * c < kw) ? sp[128 * c] : Sc<T>::zero();
-        sp += 2 * (int64_t)nU;
+        for (int c = 0; c < CPT; ++c) acc[r][c] = (rok && tx + TXN * c < kw) ? sp[TXN * c] : Sc<T>::zero();
+        sp += NY * (int64_t)nU;
       }
     }
     cp_async_wait<0>();
@@ -421,10 +424,10 @@ rank_update_kernel(int64_t rows, int nU, int bp, const T* __restrict__ src, cons
       for (int j = 0; j < b; ++j) {
         T dv[CPT];
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) dv[c] = dp[128 * c];
+        for (int c = 0; c < CPT; ++c) dv[c] = dp[TXN * c];
 #pragma unroll
         for (int r = 0; r < RH; ++r) {
-          const T a = ap[2 * r];
+          const T a = ap[NY * r];
 #pragma unroll
           for (int c = 0; c < CPT; ++c) acc[r][c] = sub(acc[r][c], mul(a, dv[c]));
         }
@@ -434,23 +437,23 @@ rank_update_kernel(int64_t rows, int nU, int bp, const T* __restrict__ src, cons
       // + y_e (alpha q)^T
 #pragma unroll
       for (int r = 0; r < RH; ++r) {
-        const T a = ap[2 * r];
+        const T a = ap[NY * r];
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) acc[r][c] = fma_(a, dp[128 * c], acc[r][c]);
+        for (int c = 0; c < CPT; ++c) acc[r][c] = fma_(a, dp[TXN * c], acc[r][c]);
       }
     }
     {
       T* op = o + (n0 + ty) * nU;
 #pragma unroll
       for (int r = 0; r < RH; ++r) {
-        const int64_t n = n0 + 2 * r + ty;
+        const int64_t n = n0 + NY * r + ty;
         if (n < rows) {
           const bool rowB = zero_rows && (n >= lo && n < lo + b);
 #pragma unroll
           for (int c = 0; c < CPT; ++c)
-            if (tx + 128 * c < kw) op[128 * c] = (keep[c] && !rowB) ? acc[r][c] : Sc<T>::zero();
+            if (tx + TXN * c < kw) op[TXN * c] = (keep[c] && !rowB) ? acc[r][c] : Sc<T>::zero();
         }
-        op += 2 * (int64_t)nU;
+        op += NY * (int64_t)nU;
       }
     }
   }

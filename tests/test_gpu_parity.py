@@ -105,6 +105,39 @@ def test_zgemm_matches_torch_complex128(torch_cuda, shape, tile):
         _lib.set_option("gemm_tile", 0)
 
 
+@pytest.mark.parametrize("target,nd", [(100, 40), (64, 0), (0, 64)])
+def test_step_is_bitwise_reproducible(torch_cuda, golden, target, nd):
+    """The path has no atomics, so repeated steps must agree bit for bit; a difference is a race between the
+    streams of the base stage (the two arms of the block chain once accumulated into the middle block from two
+    streams: 1 step in 10 was wrong for chains of >= 3 blocks).  tools/race_stress.py is the long version."""
+    t = torch_cuda
+    m, r = golden("50_50")
+    E, L = len(m["elem"]), 16
+    omega = 2 * np.pi * float(r["signal_frequency"])
+    _lib.set_option("nd_interior", nd)
+    try:
+        p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"], target_block=target)
+    finally:
+        _lib.set_option("nd_interior", 64)
+    perm = t.tensor(m["elem_perm"], device="cuda")
+    var = t.zeros(E, dtype=t.float64, device="cuda")
+    det = t.tensor(m["detection_index"], device="cuda")
+    J = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
+    first = None
+    for _ in range(60):
+        J.zero_()
+        p.assemble(perm, var, omega)
+        p.factor(False)
+        p.jacobian_block(0, L, 0, E, 1e-3, omega, J, E)
+        inv = _lib.inverse_model(J, det, 289)
+        t.cuda.synchronize()
+        if first is None:
+            first = (J.clone(), inv.clone())
+        else:
+            assert t.equal(J, first[0]) and t.equal(inv, first[1])
+    p.close()
+
+
 @pytest.mark.parametrize("tag", ["21_21", "50_50"])
 @pytest.mark.parametrize("target,nd", [(0, 64), (64, 0), (10 ** 6, 0), (0, 20), (100, 40)])
 def test_cabi_pipeline_against_reference(torch_cuda, golden, tag, target, nd):

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from .EFEM import EFEM
 from .models.mesh import MeshObj
-from .util.utilities import get_config, save_npy
+from .util.utilities import get_config, load_npy, save_npy_async, wait_npy
 
 
 class EJAC(object):
@@ -107,6 +107,7 @@ class EJAC(object):
                     ("jac", i_from, i_to, e_from, e_to, float(variable_change), float(freq), J.data_ptr()),
                     lambda: self._eng.plan.jacobian_block(i_from, i_to, e_from, e_to, variable_change, freq, J, E))
                 r0, r1 = i_from * (L - 1), i_to * (L - 1)
+                wait_npy(self.config["rootdir"] + "/" + self.config["folder_name"] + '/JAC_cache.npy')   # reads the pinned matrix
                 if self._J_is_pinned() and e_from == 0 and e_to == self.elem_num:
                     self._J_pinned[r0:r1].copy_(J[r0:r1], non_blocking=True)       # D2H into the pinned matrix
                     self._eng.torch.cuda.current_stream().synchronize()
@@ -185,14 +186,16 @@ class EJAC(object):
         """EJAC.py:231-243."""
         inv = self._inv_model(lmbda, 1.0)
         t = self._eng.torch
+        path = self.config["rootdir"] + "/" + self.config["folder_name"] + '/inv_mat.npy'
+        wait_npy(path)                                  # the previous write reads the pinned buffer
         if self._inv_pinned is None or tuple(self._inv_pinned.shape) != tuple(inv.shape):
             self._inv_pinned = t.empty(tuple(inv.shape), dtype=t.float64, pin_memory=True)
         self._inv_pinned.copy_(inv, non_blocking=True)
         t.cuda.current_stream().synchronize()
-        save_npy(self.config["rootdir"] + "/" + self.config["folder_name"] + '/inv_mat.npy', self._inv_pinned.numpy())
+        save_npy_async(path, self._inv_pinned.numpy())  # write-behind (joined before any reader, see utilities)
 
     def read_inv_matrix(self):
-        return np.load(self.config["rootdir"] + "/" + self.config["folder_name"] + '/inv_mat.npy')
+        return load_npy(self.config["rootdir"] + "/" + self.config["folder_name"] + '/inv_mat.npy')
 
     def eit_solve_direct(self, detect_potential):
         """EJAC.py:252-259."""
@@ -203,10 +206,16 @@ class EJAC(object):
 
     # -- persistence (EJAC.py:261-294) ------------------------------------------------------------------
     def save_JAC_np(self):
-        save_npy(self.config["rootdir"] + "/" + self.config["folder_name"] + '/JAC_cache.npy', self.JAC_matrix)
+        path = self.config["rootdir"] + "/" + self.config["folder_name"] + '/JAC_cache.npy'
+        if self._J_is_pinned():
+            save_npy_async(path, self.JAC_matrix)       # write-behind: overlaps the inverse model on the GPU
+        else:
+            wait_npy(path)
+            save_npy_async(path, np.array(self.JAC_matrix, dtype=np.float64))
+            wait_npy(path)
 
     def read_JAC_np(self):
-        self.JAC_matrix = np.load(self.config["rootdir"] + "/" + self.config["folder_name"] + '/JAC_cache.npy')
+        self.JAC_matrix = load_npy(self.config["rootdir"] + "/" + self.config["folder_name"] + '/JAC_cache.npy')
 
     def save_JAC_2file(self):
         with open(self.config["rootdir"] + "/" + self.config["folder_name"] + '/jac_cache.csv', "w",
@@ -216,6 +225,7 @@ class EJAC(object):
                 writer.writerow(row)
 
     def read_JAC_2file(self, mode='normal'):
+        wait_npy()                                     # a pending cache write reads JAC_matrix
         if mode == 'normal':
             with open(self.config["rootdir"] + "/" + self.config["folder_name"] + '/jac_cache.csv',
                       newline='') as csvfile:

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from .models.mesh import MeshObj
 from .readmesh import read_mesh_from_csv
-from .util.utilities import get_config, save_npy
+from .util.utilities import get_config, load_npy, save_npy
 
 
 class Solver(object):
@@ -49,14 +49,14 @@ class Solver(object):
 
     def read_JAC(self):
         assert os.path.exists(self._path('JAC_cache.npy')), "The JAC matrix is not generated"
-        self.JAC_mat = np.load(self._path('JAC_cache.npy'))
+        self.JAC_mat = load_npy(self._path('JAC_cache.npy'))
 
     def eliminate_non_detect_JAC(self):
         """Solver.py:76-86."""
         return np.array(self.JAC_mat[:, np.asarray(self.mesh.detection_index)])
 
     def read_inv_matrix(self):
-        self.inv_mat = np.load(self._path('inv_mat.npy'))
+        self.inv_mat = load_npy(self._path('inv_mat.npy'))
         self._inv_dev = None
 
     def _inv_on_device(self):

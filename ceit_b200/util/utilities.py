@@ -70,10 +70,7 @@ def read_parameter(filename, path_name):
         return pickle.load(file)
 
 
-def save_npy(path, arr):
-    """np.save-compatible writer (format 1.0, same bytes): when the file already exists with exactly the same
-    size it is overwritten in place instead of being truncated and re-allocated (the Jacobian / inverse-model
-    caches are rewritten with identical shapes on every run)."""
+def _write_npy(path, arr):
     import io
     arr = np.ascontiguousarray(arr)
     hdr = io.BytesIO()
@@ -90,3 +87,51 @@ def save_npy(path, arr):
     with open(path, "wb") as f:
         f.write(h)
         f.write(arr.data)
+
+
+def save_npy(path, arr):
+    """np.save-compatible writer (format 1.0, same bytes): when the file already exists with exactly the same
+    size it is overwritten in place instead of being truncated and re-allocated (the Jacobian / inverse-model
+    caches are rewritten with identical shapes on every run)."""
+    wait_npy(path)
+    _write_npy(path, arr)
+
+
+# ---- write-behind for the cache files ---------------------------------------------------------------------
+# JAC_cache.npy / inv_mat.npy are 8-10 MB memcpys into the page cache (~1 ms each at MESH_50_50, as long as the
+# whole Jacobian on the GPU).  save_npy_async hands the write to a worker thread (file.write releases the GIL) so
+# that it overlaps the next GPU stage; the caller must keep `arr` unchanged until wait_npy(path) - the classes
+# join before they overwrite the pinned source buffer, before anything in this package reads the file back, and
+# at interpreter exit.  OPT-IN (CEIT_B200_WRITE_BEHIND=1): by default every write is complete when the method
+# returns, as in the reference - with write-behind a raw np.load of the cache by the caller, or an in-place edit of
+# JAC_matrix, within the next millisecond would race the writer.
+_pending = {}
+_pool = None
+
+
+def save_npy_async(path, arr):
+    global _pool
+    if os.environ.get("CEIT_B200_WRITE_BEHIND") != "1":
+        return save_npy(path, arr)
+    import atexit
+    from concurrent.futures import ThreadPoolExecutor
+    path = os.path.abspath(path)
+    wait_npy(path)
+    if _pool is None:
+        _pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="ceit-npy")
+        atexit.register(wait_npy)
+    _pending[path] = _pool.submit(_write_npy, path, arr)
+
+
+def wait_npy(path=None):
+    """Block until the pending write of `path` (default: all pending writes) is on disk; re-raises its error."""
+    keys = list(_pending) if path is None else [os.path.abspath(path)]
+    for k in keys:
+        f = _pending.pop(k, None)
+        if f is not None:
+            f.result()
+
+
+def load_npy(path):
+    wait_npy(path)
+    return np.load(path)

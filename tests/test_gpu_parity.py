@@ -328,6 +328,34 @@ def test_example_03_ejac_with_resume(torch_cuda, workspace, golden):
     assert np.abs(jac3.read_inv_matrix() - ref).max() <= MODEL_TOL * np.abs(ref).max()
 
 
+def test_write_behind_cache_files(torch_cuda, workspace, golden, monkeypatch):
+    """opt-in write-behind (CEIT_B200_WRITE_BEHIND=1): the cache files are written by a worker thread; every reader
+    of this package joins first, and after wait_npy() the files hold the same bytes as the synchronous default"""
+    path = workspace("21_21")
+    m, r = golden("21_21")
+    folder = os.path.join(os.path.dirname(path), "MESH_21_21")
+    from ceit_b200.EJAC import EJAC
+    from ceit_b200.Solver import Solver
+    from ceit_b200.util.utilities import wait_npy
+    jac = EJAC()
+    J_sync = jac.JAC_calculation().copy()
+    jac.save_inv_matrix(289)
+    files_sync = [open(os.path.join(folder, f), "rb").read() for f in ("JAC_cache.npy", "inv_mat.npy")]
+    monkeypatch.setenv("CEIT_B200_WRITE_BEHIND", "1")
+    for _ in range(5):                                          # repeated steps reuse the pinned buffers
+        jac.fwd_FEM.invalidate()
+        J = jac.JAC_calculation()
+        jac.save_inv_matrix(289)
+    assert np.array_equal(jac.read_inv_matrix(), np.load(os.path.join(folder, "inv_mat.npy")))   # joins before reading
+    s = Solver()                                                # reads both caches through load_npy
+    assert np.array_equal(s.JAC_mat, J_sync) and np.array_equal(J, J_sync)
+    wait_npy()
+    files_async = [open(os.path.join(folder, f), "rb").read() for f in ("JAC_cache.npy", "inv_mat.npy")]
+    assert files_async[0] == files_sync[0]
+    assert np.abs(np.load(os.path.join(folder, "inv_mat.npy")) - r["inv_mat_289"]).max() <= \
+        MODEL_TOL * np.abs(r["inv_mat_289"]).max()
+
+
 def test_example_04_solver_and_reinitialize(torch_cuda, workspace, golden):
     path = workspace("21_21")
     m, r = golden("21_21")

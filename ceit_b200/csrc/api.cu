@@ -19,6 +19,7 @@ namespace ceit {
 std::atomic<int64_t> g_launches{0};
 int g_force_simt = 0;
 int g_gemm_tile = 0;
+int g_gemm_min_ctas64 = 120;
 static thread_local std::string g_err;
 }  // namespace ceit
 
@@ -1308,6 +1309,7 @@ int ceit_set_option(const char* name, int64_t value) {
     return CEIT_OK;
   }
   if (std::strcmp(name, "excitation_overlap") == 0) { g_ex_overlap = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "gemm_min_ctas64") == 0) { ceit::g_gemm_min_ctas64 = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "ru_wc") == 0) { g_ru_wc = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "ru_cpt") == 0) { g_ru_cpt = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "ru_waves") == 0) { g_ru_waves = (int)std::max<int64_t>(1, value); return CEIT_OK; }

@@ -14,6 +14,7 @@ namespace ceit {
 extern std::atomic<int64_t> g_launches;
 extern int g_force_simt;
 extern int g_gemm_tile;
+extern int g_gemm_min_ctas64;   // 64x64 tiles when they give at least this many CTAs (else 32x32)
 
 #define CEIT_COUNT_LAUNCH() (::ceit::g_launches.fetch_add(1, std::memory_order_relaxed))
 
@@ -67,8 +68,12 @@ template <int BM, int BN, int WM, int WN, int OPA, int OPB, int STAGES>
 __global__ void __launch_bounds__(WM * WN * 32)
 gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int64_t lda,
                  int64_t sA, const double* __restrict__ B, int64_t ldb, int64_t sB, double beta,
-                 double* __restrict__ C, int64_t ldc, int64_t sC, int lower_only) {
+                 double* __restrict__ C, int64_t ldc, int64_t sC, int flags) {
   using SM = DmmaSmem<BM, BN, OPA, OPB>;
+  // flags: bit 0 = lower_only; bits 1.. = inner dimension of the LAST batch entry (0 = K), so that the short last
+  // slice of a split-K product runs in the same launch as the full ones
+  if ((flags >> 1) != 0 && blockIdx.z == gridDim.z - 1) K = flags >> 1;
+  const int lower_only = flags & 1;
   // symmetric results whose consumers read the lower triangle only (A -= L L^T before a Cholesky):
   // tiles strictly above the block diagonal are skipped
   if (lower_only && (int)(blockIdx.x * BN) > (int)(blockIdx.y * BM + BM - 1)) return;
@@ -475,7 +480,7 @@ inline void gemm<cd>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, in
   }
   auto ctas = [&](int64_t bm, int64_t bn) { return ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch; };
   int cfg = g_gemm_tile;                       // 0 = auto, 1 = 32x32, 2/3 = 64x64
-  if (cfg == 0) cfg = (ctas(64, 64) >= 120) ? 2 : 1;
+  if (cfg == 0) cfg = (ctas(64, 64) >= g_gemm_min_ctas64) ? 2 : 1;
   if (cfg >= 2)
     gemm_zdmma_launch<64, 64, 2, 2, 3>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
   else
@@ -522,7 +527,7 @@ inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N
   int cfg = g_gemm_tile;                       // 0 = auto, 1 = 32x32, 2 = 64x64, 3 = 128x128
   // measured on B200 (tools/time_gemm.py): the 64x64 tile (2 CTAs/SM) beats 128x128 (1 CTA/SM) at every size
   // of this path (30.3 vs 25.3 TFLOP/s on the inverse-model GEMM, cuBLAS 34.9); 32x32 when 64x64 cannot fill the chip
-  if (cfg == 0) cfg = (ctas(64, 64) >= 120) ? 2 : 1;
+  if (cfg == 0) cfg = (ctas(64, 64) >= g_gemm_min_ctas64) ? 2 : 1;
   if (cfg == 3)
     gemm_dmma_launch<128, 128, 2, 4, 3>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
                                         lower_only);
@@ -600,13 +605,17 @@ inline void gemm_splitk(cudaStream_t st, int opA, int opB, int64_t M, int64_t N,
   const int64_t sA = (opA == 0) ? Ks : Ks * lda, sB = (opB == 0) ? Ks * ldb : Ks;
   const int tile_keep = g_gemm_tile;
   if (splitk_large(M, N) && g_gemm_tile == 0) g_gemm_tile = 2;   // every slice (and the remainder) on 64x64 tiles
-  if (full > 0)
-    gemm<double>(st, opA, opB, M, N, Ks, alpha, A, lda, sA, B, ldb, sB, 0.0, workspace, N, M * N, full, lower_only);
+  // one launch: `full` slices of Ks and, when K is not a multiple, a last slice of `rem` (kernel flags bits 1..)
   int parts = full;
-  if (rem > 0) {
-    gemm<double>(st, opA, opB, M, N, rem, alpha, A + (int64_t)full * sA, lda, 0, B + (int64_t)full * sB, ldb, 0, 0.0,
-                 workspace + (int64_t)full * M * N, N, 0, 1, lower_only);
-    ++parts;
+  if (rem > 0) ++parts;
+  if (!g_force_simt) {
+    gemm<double>(st, opA, opB, M, N, Ks, alpha, A, lda, sA, B, ldb, sB, 0.0, workspace, N, M * N, parts,
+                 (lower_only & 1) | (rem > 0 ? (int)(rem << 1) : 0));
+  } else {                                            // the SIMT cross-check kernel has no tail slice
+    if (full > 0) gemm<double>(st, opA, opB, M, N, Ks, alpha, A, lda, sA, B, ldb, sB, 0.0, workspace, N, M * N, full);
+    if (rem > 0)
+      gemm<double>(st, opA, opB, M, N, rem, alpha, A + (int64_t)full * sA, lda, 0, B + (int64_t)full * sB, ldb, 0, 0.0,
+                   workspace + (int64_t)full * M * N, N, 0, 1);
   }
   g_gemm_tile = tile_keep;
   splitk_reduce_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(M * N, parts, workspace, beta, C, M, N, ldc,

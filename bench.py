@@ -455,8 +455,9 @@ def run_gpu(args):
                   "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": bytes_per_col * cols_per_launch,
                   "timing": "CUDA events around the launch, second pass over the same K steps (stream launches; "
                             "the timed region replays the same kernels from a CUDA graph)",
-                  "note": "algorithmic bytes = (8 r + 96 + 8 (L-1)) per column (SURVEY.md 8d); at this size Yh is "
-                          "largely L2-resident, the kernel is shared-memory/FP64-issue bound (profiles/)"}
+                  "note": "algorithmic bytes = (8 r + 96 + 8 (L-1)) per column (SURVEY.md 8d); the stage timer wraps the "
+                          "Woodbury kernel alone; at this size Yh is largely L2-resident and the kernel is bound by "
+                          "shared-memory wavefronts (56 % of peak) and FP64 issue (33 %), see profiles/"}
         stage_ms = {k: v[0] / args.steps for k, v in stages.items() if v[1]}
         rooflines = {"stage_ms_per_step": stage_ms, "woodbury": k2}
         if realtime:

@@ -15,7 +15,7 @@ _lib = None
 
 SYMBOLS = [
     "ceit_last_error", "ceit_version", "ceit_launch_count", "ceit_plan_create", "ceit_plan_destroy",
-    "ceit_plan_info", "ceit_plan_tables", "ceit_assemble", "ceit_factor", "ceit_jacobian_block",
+    "ceit_plan_info", "ceit_plan_tables", "ceit_plan_patches", "ceit_assemble", "ceit_factor", "ceit_jacobian_block",
     "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm", "ceit_plan_csr_values",
     "ceit_set_option", "ceit_stage_times", "ceit_gram_partial", "ceit_inverse_from_gram", "ceit_debug_tile_clocks", "ceit_zgemm",
     "ceit_center_of_position",
@@ -49,6 +49,7 @@ def lib():
     L.ceit_plan_destroy.argtypes = [c_vp]
     L.ceit_plan_info.argtypes = [c_vp, c_vp]
     L.ceit_plan_tables.argtypes = [c_vp] * 7
+    L.ceit_plan_patches.argtypes = [c_vp] * 6
     L.ceit_assemble.argtypes = [c_vp, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp]
     L.ceit_factor.argtypes = [c_vp, c_int, c_vp]
     L.ceit_jacobian_block.argtypes = [c_vp, c_i64, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_i64, c_vp, c_vp]
@@ -197,6 +198,19 @@ class Plan:
         check(lib().ceit_plan_tables(self._h, _np_ptr(rowptr), _np_ptr(colidx), _np_ptr(pos), _np_ptr(blk_ptr),
                                      _np_ptr(U), _np_ptr(ppos)))
         return dict(rowptr=rowptr, colidx=colidx, pos=pos, blk_ptr=blk_ptr, U=U, ppos=ppos)
+
+    def patches(self):
+        """Element patches of the Woodbury kernel (host copies): see ceit_plan_patches in include/ceit_b200.h."""
+        info = self.info()
+        n_p, n_pn = int(info[14]), int(info[15])
+        eptr = np.zeros(n_p + 1, np.int64)
+        elems = np.zeros(self.E, np.int64)
+        nptr = np.zeros(n_p + 1, np.int64)
+        nodes = np.zeros(n_pn, np.int64)
+        local = np.zeros(3 * self.E, np.int64)
+        check(lib().ceit_plan_patches(self._h, _np_ptr(eptr), _np_ptr(elems), _np_ptr(nptr), _np_ptr(nodes),
+                                      _np_ptr(local)))
+        return dict(eptr=eptr, elems=elems, nptr=nptr, nodes=nodes, local=local, node_cap=int(info[22]))
 
     # -- numeric entry points (torch tensors as buffers) ------------------------------------------
     def assemble(self, perm, var, omega, vals=None, elem_param=None):

@@ -993,6 +993,7 @@ int ceit_plan_info(const ceit_plan_t* p, int64_t* info) {
   info[11] = (int64_t)p->dev_bytes; info[12] = p->mode;
   info[13] = 0; info[14] = (int64_t)h.patch_eptr.size() - 1; info[15] = (int64_t)h.patch_nodes.size();
   info[16] = h.P; info[17] = h.nI; info[18] = h.bmax; info[19] = h.nC; info[20] = h.NP; info[21] = h.N0P;
+  info[22] = h.patch_node_cap;
   if (p->uploaded && p->d_info) {
     int flag = 0;
     if (cudaMemcpy(&flag, p->d_info, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) info[13] = flag;
@@ -1010,6 +1011,18 @@ int ceit_plan_tables(const ceit_plan_t* p, int64_t* rowptr, int64_t* colidx, int
   if (ppos) for (int64_t k = 0; k < h.N; ++k) ppos[k] = h.ppos[k];
   if (blk_ptr) for (int64_t k = 0; k <= h.nb; ++k) blk_ptr[k] = h.blk_ptr[k];
   if (U) for (int64_t k = 0; k < h.nU; ++k) U[k] = h.U[k];
+  return CEIT_OK;
+}
+
+int ceit_plan_patches(const ceit_plan_t* p, int64_t* eptr, int64_t* elems, int64_t* nptr, int64_t* nodes,
+                      int64_t* local) {
+  if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_patches: null plan");
+  const HostPlan& h = p->h;
+  if (eptr) for (size_t k = 0; k < h.patch_eptr.size(); ++k) eptr[k] = h.patch_eptr[k];
+  if (elems) for (size_t k = 0; k < h.patch_elems.size(); ++k) elems[k] = h.patch_elems[k];
+  if (nptr) for (size_t k = 0; k < h.patch_nptr.size(); ++k) nptr[k] = h.patch_nptr[k];
+  if (nodes) for (size_t k = 0; k < h.patch_nodes.size(); ++k) nodes[k] = h.patch_nodes[k];
+  if (local) for (size_t k = 0; k < h.patch_local.size(); ++k) local[k] = h.patch_local[k];
   return CEIT_OK;
 }
 

@@ -56,7 +56,8 @@ int ceit_plan_destroy(ceit_plan_t* plan);
 /* info[0..23]: N, E, L, nU, N0, n_blocks, max_block, nnz, n_levels, sum n_k^2, sum n_k n_k+1,
  *              device bytes held, factor state (0 none,1 real,2 complex), numeric flag, n_patches,
  *              patch nodes, P (interiors), nI (slots per interior), bmax, nC (separator nodes),
- *              NP (position rows), N0P (position of the first electrode node), reserved x2 */
+ *              NP (position rows), N0P (position of the first electrode node), node cap of a Woodbury patch,
+ *              reserved */
 int ceit_plan_info(const ceit_plan_t* plan, int64_t* info24);
 /* host copies of the symbolic tables (any pointer may be NULL):
  * rowptr i64[N+1], colidx i64[nnz] (CSR pattern of K, sorted, == scipy.sparse.csr_matrix of the
@@ -66,6 +67,15 @@ int ceit_plan_info(const ceit_plan_t* plan, int64_t* info24);
  * in level-2 block order from P*nI, electrode nodes from N0P). */
 int ceit_plan_tables(const ceit_plan_t* plan, int64_t* rowptr, int64_t* colidx, int64_t* pos,
                      int64_t* blk_ptr, int64_t* U, int64_t* ppos);
+
+/* host copies of the element patches of the Woodbury kernel (any pointer may be NULL); sizes from
+ * ceit_plan_info: n_patches = info[14], total patch nodes = info[15], node cap per patch = info[22]:
+ * eptr i64[n_patches+1] / elems i64[E] (patch -> element ids, lane order), nptr i64[n_patches+1] /
+ * nodes i64[info[15]] (patch -> node POSITIONS, in shared-memory slot order), local i64[3E] (per patch
+ * element, in patch order: the slot of each of its three nodes).  No reference counterpart: the patches replace
+ * the element loop of EJAC.JAC_calculation (CEIT/EJAC.py:115-133). */
+int ceit_plan_patches(const ceit_plan_t* plan, int64_t* eptr, int64_t* elems, int64_t* nptr, int64_t* nodes,
+                      int64_t* local);
 
 /* ---- K1: element matrices -> CSR values ------------------------------------------------------
  * Replaces EFEM.construct_sparse_matrix (CEIT/EFEM.py:47-69) incl. its uniform factor 2 and the

@@ -235,3 +235,81 @@ def test_bench_reference_arm_contract(capsys):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"] == bench.WORKLOAD
+
+
+def _quarter_conflicts(local, eptr):
+    """wavefronts beyond the minimum of the Woodbury kernel's 16-byte row loads: per (quarter warp, corner) the number
+    of DISTINCT slots that share a residue mod 8 with another distinct slot (woodbury_lr_pitch: pitch/2 odd)."""
+    extra = groups = 0
+    for p in range(len(eptr) - 1):
+        loc = local[3 * eptr[p]:3 * eptr[p + 1]].reshape(-1, 3)
+        for q in range(0, len(loc), 8):
+            for a in range(3):
+                slots = np.unique(loc[q:q + 8, a])
+                extra += len(slots) - len(np.unique(slots % 8))
+                groups += 1
+    return extra, groups
+
+
+@pytest.mark.parametrize("tag", ["21_21", "50_50"])
+def test_woodbury_patches_cover_elements_and_slots_are_spread(golden, tag):
+    """ceit_plan_patches: every element in exactly one patch, <= 32 elements and <= node_cap nodes per patch, the slot
+    table consistent with the element connectivity, and the slot assignment of plan.cpp (build_patches) leaves few
+    shared-memory bank conflicts between the rows a quarter warp reads together."""
+    m, _ = golden(tag)
+    p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"], upload=False)
+    tb, pt = p.tables(), p.patches()
+    E = len(m["elem"])
+    assert sorted(pt["elems"].tolist()) == list(range(E))
+    ne = np.diff(pt["eptr"])
+    nn = np.diff(pt["nptr"])
+    assert ne.min() >= 1 and ne.max() <= 32 and nn.max() <= pt["node_cap"] <= 64
+    pos = tb["pos"]
+    for k in range(len(ne)):
+        nodes = pt["nodes"][pt["nptr"][k]:pt["nptr"][k + 1]]
+        assert len(set(nodes.tolist())) == len(nodes)                       # one slot per node
+        loc = pt["local"][3 * pt["eptr"][k]:3 * pt["eptr"][k + 1]].reshape(-1, 3)
+        assert loc.min() >= 0 and loc.max() < len(nodes)
+        assert set(loc.reshape(-1).tolist()) == set(range(len(nodes)))      # every staged row is used
+        el = pt["elems"][pt["eptr"][k]:pt["eptr"][k + 1]]
+        assert np.array_equal(nodes[loc], pos[m["elem"][el]])               # slot -> node position of each corner
+    extra, groups = _quarter_conflicts(pt["local"], pt["eptr"])
+    # first-occurrence numbering of the same patches, for comparison
+    first = pt["local"].copy()
+    for k in range(len(ne)):
+        seg = first[3 * pt["eptr"][k]:3 * pt["eptr"][k + 1]]
+        order = {}
+        for v in seg:
+            order.setdefault(int(v), len(order))
+        first[3 * pt["eptr"][k]:3 * pt["eptr"][k + 1]] = [order[int(v)] for v in seg]
+    extra0, _ = _quarter_conflicts(first, pt["eptr"])
+    assert extra <= extra0 and extra <= 0.25 * groups, (extra, extra0, groups)
+    p.close()
+
+
+def test_write_behind_npy_helpers(tmp_path, monkeypatch):
+    """save_npy_async / wait_npy / load_npy (util/utilities.py): synchronous unless CEIT_B200_WRITE_BEHIND=1; with it
+    the write runs on a worker thread, readers and rewriters of the same path join first, bytes == np.save"""
+    from ceit_b200.util import utilities as u
+    a = np.random.default_rng(0).random((240, 882))
+    ref = tmp_path / "ref.npy"
+    np.save(ref, a)
+    path = str(tmp_path / "JAC_cache.npy")
+    monkeypatch.delenv("CEIT_B200_WRITE_BEHIND", raising=False)
+    u.save_npy_async(path, a)
+    assert not u._pending and open(path, "rb").read() == open(ref, "rb").read()
+    monkeypatch.setenv("CEIT_B200_WRITE_BEHIND", "1")
+    for k in range(5):                                   # same size: overwritten in place, each time joined first
+        b = a + k
+        u.save_npy_async(path, b)
+        assert np.array_equal(u.load_npy(path), b)       # load_npy joins the pending write
+        assert not u._pending
+    u.save_npy_async(path, a)
+    u.save_npy_async(str(tmp_path / "inv_mat.npy"), a.T.copy())
+    u.wait_npy()
+    assert open(path, "rb").read() == open(ref, "rb").read()
+    assert np.array_equal(np.load(tmp_path / "inv_mat.npy"), a.T)
+    u.save_npy_async(str(tmp_path / "no_such_dir" / "x.npy"), a)
+    with pytest.raises(OSError):
+        u.wait_npy()                                     # the worker's error surfaces at the join
+    assert not u._pending

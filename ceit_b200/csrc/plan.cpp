@@ -605,6 +605,48 @@ void build_patches(HostPlan& p, int32_t node_cap, int32_t elem_cap) {
         slot_of[v] = best;
         for (int32_t g : groups_of[v]) cnt[(size_t)g * 8 + (best & 7)]++;
       }
+      // refinement: swap the slots of a node that still collides with any other node while that lowers the number
+      // of collisions (cost of a group = sum over residues of max(count - 1, 0))
+      auto group_cost = [&](int32_t g) {
+        int32_t c = 0;
+        for (int r = 0; r < 8; ++r) c += std::max(cnt[(size_t)g * 8 + r] - 1, 0);
+        return c;
+      };
+      auto move = [&](int32_t v, int32_t from, int32_t to) {
+        for (int32_t g : groups_of[v]) {
+          cnt[(size_t)g * 8 + from]--;
+          cnt[(size_t)g * 8 + to]++;
+        }
+      };
+      std::vector<int32_t> touched;
+      for (int pass = 0; pass < 4; ++pass) {
+        bool improved = false;
+        for (int32_t u = 0; u < nn; ++u) {
+          bool collides = false;
+          for (int32_t g : groups_of[u]) collides |= cnt[(size_t)g * 8 + (slot_of[u] & 7)] > 1;
+          if (!collides) continue;
+          for (int32_t v = 0; v < nn; ++v) {
+            const int32_t ru = slot_of[u] & 7, rv = slot_of[v] & 7;
+            if (v == u || ru == rv) continue;
+            touched = groups_of[u];
+            for (int32_t g : groups_of[v])
+              if (std::find(touched.begin(), touched.end(), g) == touched.end()) touched.push_back(g);
+            int32_t before = 0, after = 0;
+            for (int32_t g : touched) before += group_cost(g);
+            move(u, ru, rv);
+            move(v, rv, ru);
+            for (int32_t g : touched) after += group_cost(g);
+            if (after < before) {
+              std::swap(slot_of[u], slot_of[v]);
+              improved = true;
+              break;                      // u has a new slot: re-examine it on the next pass
+            }
+            move(u, rv, ru);
+            move(v, ru, rv);
+          }
+        }
+        if (!improved) break;
+      }
       std::vector<int32_t> by_slot(nn);
       for (int32_t v = 0; v < nn; ++v) by_slot[slot_of[v]] = cur_nodes[v];
       for (size_t q = l_beg; q < p.patch_local.size(); ++q) p.patch_local[q] = (uint8_t)slot_of[p.patch_local[q]];

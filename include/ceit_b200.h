@@ -184,6 +184,12 @@ int ceit_debug_tile_clocks(int64_t* out8);
  *   "nd_interior"       target nodes per nested-dissection interior for plans created afterwards (default 64)
  *   "patch_nodes"       node cap of the element patches for plans created afterwards (0 = automatic)
  *   "gemm_tile"         force the CTA tile of the DMMA GEMM (32 / 64 / 128, 0 = automatic)
+ *   "gemm_min_ctas64"   automatic tile choice: 64x64 tiles when they give at least this many CTAs, else 32x32
+ *                       (default 300)
+ *   "ru_wc", "ru_cpt", "ru_waves"
+ *                       rank-update kernel: force the column layout (warps across x columns per thread; 0 =
+ *                       cost model) and the number of CTA waves (default 8); tools/ru_sweep.sh
+ *   "excitation_overlap" (default 1) ZW / base potentials on a second stream beside the Yh update
  *   "force_simt_gemm", "direct_excitation", "no_patch_kernel", "no_lowrank_kernel"
  *                       route around the tensor-core GEMM / rank-update excitation stage / patch Woodbury
  *                       kernels (test coverage of the fallback kernels)

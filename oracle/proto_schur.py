@@ -253,3 +253,123 @@ class SchurModel:
                 amp = np.abs(phi0[self.N0:] + dU)
                 J[i * (L - 1):(i + 1) * (L - 1), j] = np.abs(self.W[rows] @ amp)
         return J, base
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Partitioned elimination of the block-tridiagonal chain: the model of how G ranks would share the level-2 system
+# (not on the product path yet).  G-1 single blocks are chosen as INTERFACES; removing them leaves G
+# mutually disconnected SEGMENTS, one per rank.  Rank g, independently:
+#     factorises its segment A_g (block-tridiagonal, the code above),
+#     W_g = A_g^-1 C_g      ("spikes": C_g couples the segment's first / last block to the interface on its left / right),
+#     t_g = A_g^-1 R_g,     S_g = C_g^T W_g,     r_g = C_g^T t_g.
+# One exchange (all-gather of S_g: <= 2x2 interface blocks, and r_g: <= 2 interface row blocks per rank) builds the
+# REDUCED system on the interfaces, A_red = A_I - sum_g S_g (block-tridiagonal again, G-1 blocks), which every rank
+# solves redundantly.  Then, again independently per rank,
+#     x_g = t_g - W_g x_I[lr],       Sigma_g = A_g^-1 + W_g Sigma_I[lr,lr] W_g^T   (only its tridiagonal pattern),
+#     Sigma[g-block, interface] = -W_g Sigma_I[lr, interface]                      (only the adjacent blocks),
+#     R^T M^-1 R = sum_g R_g^T t_g + (R_I - sum r_g)^T A_red^-1 (R_I - sum r_g)     (the S_U contribution).
+# Serial chain per rank: nb/G blocks + G-1 reduced blocks instead of nb/2 + 1.
+# ------------------------------------------------------------------------------------------------------------------
+def choose_interfaces(nb, G):
+    """G-1 interface blocks spread over 0..nb-1 with non-empty segments between them (fewer if nb is too small)."""
+    G = max(1, min(G, (nb + 1) // 2))
+    if G == 1:
+        return []
+    cuts = sorted({int(round((g * nb) / G - 0.5)) for g in range(1, G)})
+    cuts = [c for c in cuts if 0 < c < nb - 1]
+    out = []
+    for c in cuts:                                   # keep at least one block between consecutive interfaces
+        if not out or c - out[-1] >= 2:
+            out.append(c)
+    return out
+
+
+def partitioned_chain(M, blk_ptr, RHS, G):
+    """Model of the G-rank elimination of the SPD block-tridiagonal M (dense storage, blocks blk_ptr) with right-hand
+    sides RHS.  Returns X = M^-1 RHS, the diagonal / sub-diagonal blocks of M^-1 and RHS^T M^-1 RHS, computed only from
+    per-segment quantities, the exchanged (S_g, r_g) and the reduced interface system."""
+    nb = len(blk_ptr) - 1
+    sl = lambda k: slice(blk_ptr[k], blk_ptr[k + 1])
+    itf = choose_interfaces(nb, G)
+    bounds = [-1] + itf + [nb]
+    segs = [list(range(bounds[g] + 1, bounds[g + 1])) for g in range(len(bounds) - 1)]
+    nI = len(itf)
+    X = np.zeros_like(RHS)
+    Sd, So = [None] * nb, [None] * (nb - 1)
+    quad = np.zeros((RHS.shape[1], RHS.shape[1]), dtype=RHS.dtype)
+    per_rank, S_all, r_all = [], [], []
+    # ---- phase 1 (per rank, no communication) ----------------------------------------------------------------
+    for g, seg in enumerate(segs):
+        rows = np.concatenate([np.arange(blk_ptr[k], blk_ptr[k + 1]) for k in seg])
+        ptr = np.concatenate([[0], np.cumsum([blk_ptr[k + 1] - blk_ptr[k] for k in seg])])
+        A = M[np.ix_(rows, rows)]
+        Linv, Lsub = block_tridiag_factor(A, ptr)
+        left = bounds[g] if bounds[g] >= 0 else None
+        right = bounds[g + 1] if bounds[g + 1] < nb else None
+        cols = [k for k in (left, right) if k is not None]
+        C = np.zeros((len(rows), sum(blk_ptr[k + 1] - blk_ptr[k] for k in cols)), dtype=M.dtype)
+        off, col_sl = 0, {}
+        for k in cols:
+            w = blk_ptr[k + 1] - blk_ptr[k]
+            col_sl[k] = slice(off, off + w)
+            C[:, off:off + w] = M[rows, sl(k)]          # non-zero only in the segment block adjacent to interface k
+            off += w
+        both = block_tridiag_solve(Linv, Lsub, ptr, np.concatenate([C, RHS[rows]], axis=1))
+        W, t = both[:, :C.shape[1]], both[:, C.shape[1]:]
+        quad += RHS[rows].T @ t
+        S_all.append((cols, col_sl, C.T @ W))            # exchanged: (n_l + n_r)^2
+        r_all.append((cols, col_sl, C.T @ t))            # exchanged: (n_l + n_r) x nrhs
+        per_rank.append((seg, rows, ptr, Linv, Lsub, W, t, cols, col_sl))
+    # ---- phase 2 (after ONE all-gather; every rank redundantly): reduced interface system -------------------------
+    if nI:
+        iptr = np.concatenate([[0], np.cumsum([blk_ptr[k + 1] - blk_ptr[k] for k in itf])])
+        ipos = {k: q for q, k in enumerate(itf)}
+        isl = lambda k: slice(iptr[ipos[k]], iptr[ipos[k] + 1])
+        irows = np.concatenate([np.arange(blk_ptr[k], blk_ptr[k + 1]) for k in itf])
+        Ared = M[np.ix_(irows, irows)].copy()            # block diagonal: consecutive interfaces are never adjacent
+        Rred = RHS[irows].copy()
+        for (cols, col_sl, S), (_, _, r) in zip(S_all, r_all):
+            for a in cols:
+                Rred[isl(a)] -= r[col_sl[a]]
+                for b in cols:
+                    Ared[isl(a), isl(b)] -= S[col_sl[a], col_sl[b]]
+        Li, Ls = block_tridiag_factor(Ared, iptr)
+        xI = block_tridiag_solve(Li, Ls, iptr, Rred)
+        SdI, SoI = block_tridiag_selinv(Li, Ls, iptr)
+        quad += Rred.T @ xI
+        for q, k in enumerate(itf):
+            X[sl(k)] = xI[iptr[q]:iptr[q + 1]]
+            Sd[k] = SdI[q]
+
+        def sig_I(a, b):                                  # Sigma_I block (a, b) for |pos(a) - pos(b)| <= 1
+            qa, qb = ipos[a], ipos[b]
+            if qa == qb:
+                return SdI[qa]
+            return SoI[qb] if qa == qb + 1 else SoI[qa].T
+    # ---- phase 3 (per rank, no communication): back substitution and selected inverse of the segment -----------
+    for seg, rows, ptr, Linv, Lsub, W, t, cols, col_sl in per_rank:
+        x = t.copy()
+        nc = W.shape[1]
+        SigLR = np.zeros((nc, nc), dtype=M.dtype)
+        if cols:
+            xlr = np.concatenate([X[sl(k)] for k in cols])
+            x -= W @ xlr
+            for a in cols:
+                for b in cols:
+                    SigLR[col_sl[a], col_sl[b]] = sig_I(a, b)
+        X[rows] = x
+        sd, so = block_tridiag_selinv(Linv, Lsub, ptr)
+        V = W @ SigLR                                    # segment rows x (n_l + n_r)
+        for q, k in enumerate(seg):
+            rq = slice(ptr[q], ptr[q + 1])
+            Sd[k] = sd[q] + V[rq] @ W[rq].T
+            if q + 1 < len(seg):
+                rn = slice(ptr[q + 1], ptr[q + 2])
+                So[k] = so[q] + V[rn] @ W[rq].T
+        # blocks between the segment's end blocks and its interfaces: Sigma[seg row, interface] = -(W Sigma_I)[., interface]
+        for a in cols:
+            if a == seg[0] - 1:                          # interface on the left: sub-diagonal block (seg[0], a)
+                So[a] = -V[slice(ptr[0], ptr[1]), col_sl[a]]
+            if a == seg[-1] + 1:                         # interface on the right: sub-diagonal block (a, seg[-1])
+                So[seg[-1]] = -V[slice(ptr[len(seg) - 1], ptr[len(seg)]), col_sl[a]].T
+    return X, Sd, So, quad

@@ -513,30 +513,38 @@ inline void gemm_dmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int64
   CEIT_COUNT_LAUNCH();
 }
 
-template <>
-inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K,
-                         double alpha, const double* A, int64_t lda, int64_t sA, const double* B,
-                         int64_t ldb, int64_t sB, double beta, double* C, int64_t ldc, int64_t sC,
-                         int batch, int lower_only) {
+// real products; cfg: 0 = automatic tile choice, 1 = 32x32, 2 = 64x64, 3 = 128x128.  `flags`: bit 0 = lower_only,
+// bits 1.. = inner dimension of the last batch entry (see gemm_dmma_kernel)
+inline void gemm_real_tiled(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha,
+                            const double* A, int64_t lda, int64_t sA, const double* B, int64_t ldb, int64_t sB,
+                            double beta, double* C, int64_t ldc, int64_t sC, int batch, int flags, int cfg) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
   if (g_force_simt) {
     gemm_simt_launch<double>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
     return;
   }
   auto ctas = [&](int64_t bm, int64_t bn) { return ((M + bm - 1) / bm) * ((N + bn - 1) / bn) * batch; };
-  int cfg = g_gemm_tile;                       // 0 = auto, 1 = 32x32, 2 = 64x64, 3 = 128x128
   // measured on B200 (tools/time_gemm.py): the 64x64 tile (2 CTAs/SM) beats 128x128 (1 CTA/SM) at every size
   // of this path (30.3 vs 25.3 TFLOP/s on the inverse-model GEMM, cuBLAS 34.9); 32x32 when 64x64 cannot fill the chip
   if (cfg == 0) cfg = (ctas(64, 64) >= g_gemm_min_ctas64) ? 2 : 1;
   if (cfg == 3)
     gemm_dmma_launch<128, 128, 2, 4, 3>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
-                                        lower_only);
+                                        flags);
   else if (cfg == 2)
     gemm_dmma_launch<64, 64, 2, 2, 3>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
-                                      lower_only);   // 3 stages = 60 KB: 3 CTAs/SM
+                                      flags);   // 3 stages = 60 KB: 3 CTAs/SM
   else
     gemm_dmma_launch<32, 32, 2, 2, 4>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
-                                      lower_only);
+                                      flags);
+}
+
+template <>
+inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, int64_t K,
+                         double alpha, const double* A, int64_t lda, int64_t sA, const double* B,
+                         int64_t ldb, int64_t sB, double beta, double* C, int64_t ldc, int64_t sC,
+                         int batch, int lower_only) {
+  gemm_real_tiled(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, lower_only & 1,
+                  g_gemm_tile);           // g_gemm_tile: 0 = auto unless forced through ceit_set_option("gemm_tile")
 }
 
 
@@ -603,21 +611,20 @@ inline void gemm_splitk(cudaStream_t st, int opA, int opB, int64_t M, int64_t N,
   const int full = (int)(K / Ks);                     // slices of exactly Ks
   const int64_t rem = K - (int64_t)full * Ks;
   const int64_t sA = (opA == 0) ? Ks : Ks * lda, sB = (opB == 0) ? Ks * ldb : Ks;
-  const int tile_keep = g_gemm_tile;
-  if (splitk_large(M, N) && g_gemm_tile == 0) g_gemm_tile = 2;   // every slice (and the remainder) on 64x64 tiles
+  // every slice on 64x64 tiles when the output is large (the slice count was sized for them)
+  const int cfg = (splitk_large(M, N) && g_gemm_tile == 0) ? 2 : g_gemm_tile;
   // one launch: `full` slices of Ks and, when K is not a multiple, a last slice of `rem` (kernel flags bits 1..)
   int parts = full;
   if (rem > 0) ++parts;
   if (!g_force_simt) {
-    gemm<double>(st, opA, opB, M, N, Ks, alpha, A, lda, sA, B, ldb, sB, 0.0, workspace, N, M * N, parts,
-                 (lower_only & 1) | (rem > 0 ? (int)(rem << 1) : 0));
+    gemm_real_tiled(st, opA, opB, M, N, Ks, alpha, A, lda, sA, B, ldb, sB, 0.0, workspace, N, M * N, parts,
+                    (lower_only & 1) | (rem > 0 ? (int)(rem << 1) : 0), cfg);
   } else {                                            // the SIMT cross-check kernel has no tail slice
     if (full > 0) gemm<double>(st, opA, opB, M, N, Ks, alpha, A, lda, sA, B, ldb, sB, 0.0, workspace, N, M * N, full);
     if (rem > 0)
       gemm<double>(st, opA, opB, M, N, rem, alpha, A + (int64_t)full * sA, lda, 0, B + (int64_t)full * sB, ldb, 0, 0.0,
                    workspace + (int64_t)full * M * N, N, 0, 1);
   }
-  g_gemm_tile = tile_keep;
   splitk_reduce_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(M * N, parts, workspace, beta, C, M, N, ldc,
                                                                        lower_only);
   CEIT_COUNT_LAUNCH();

@@ -460,6 +460,16 @@ def run_gpu(args):
                           "shared-memory wavefronts (56 % of peak) and FP64 issue (33 %), see profiles/"}
         stage_ms = {k: v[0] / args.steps for k, v in stages.items() if v[1]}
         rooflines = {"stage_ms_per_step": stage_ms, "woodbury": k2}
+        if stages.get("assemble", (0, 0))[1] and stages["assemble"][0] > 0:
+            # K1: SURVEY.md 8d algorithmic bytes 16 N + 28 E + 16 nnz per launch
+            a_bytes = 16.0 * N + 28.0 * E + 16.0 * int(info[7])
+            a_ms = stages["assemble"][0] / stages["assemble"][1]
+            rooflines["assemble"] = {
+                "kernel": "assemble_csr_kernel", "bound": "hbm", "achieved": a_bytes / (a_ms * 1e-3) / 1e9, "peak": hbm,
+                "unit": "GB/s", "frac": a_bytes / (a_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                "ms_per_launch": a_ms, "algorithmic_bytes_per_launch": a_bytes,
+                "note": "launch-latency bound at this size (one ~9 us kernel over 0.5 MB); the byte count only "
+                        "becomes meaningful on the 400x400 mesh (29 MB)"}
         if realtime:
             rooflines["reconstruct_batched"] = {
                 "kernel": "gemm_dmma_kernel<0,0>", "bound": "tensor", "achieved": realtime["batched_tflops_f64"],

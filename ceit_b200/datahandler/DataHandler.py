@@ -3,17 +3,15 @@
 `get_COP(data)` keeps the reference contract (DataHandler.py:28-56): reconstruct the map of one recording and
 return the mean centroid and mean value of the detection elements above 90 % of the map's range.  The whole
 dataset goes through `get_COP_batch`, ONE batched reconstruction (`ceit_reconstruct`, frames resident in HBM) and
-ONE reduction kernel (`ceit_center_of_position`) instead of a Python loop of solves; `draw_COP`'s arithmetic
-(without the drawing) is `cop_table`.  Plotting is outside the scope of ceit_b200.
+ONE reduction kernel (`ceit_center_of_position`) instead of a Python loop of solves.  A "recording" here is anything
+with a `delta_V` attribute (m,), as the reference's `Data` objects have after `calc_delta_V`; the lab-file classes
+(`Data`, `CalibData`, `DataSet`, csv readers) and plotting are outside the scope of ceit_b200.
 """
-import csv
-
 import numpy as np
 
 from .. import _lib
 from ..Solver import Solver, reinitialize_solver
 from ..util.utilities import get_config
-from .Data import CalibData, Data
 
 THRESHOLD_PERCENTAGE = 0.9
 
@@ -59,49 +57,11 @@ class DataPlotter:
             raise ZeroDivisionError("float division by zero")
         return float(x[0]), float(y[0]), float(v[0])
 
-    def cop_table(self, dataset, calibration):
-        """The numbers draw_COP plots (DataHandler.py:58-93): reconstructed centres in mm (x 2000, as the
-        reference scales them), ground truth positions and the mean values, for a list of Data objects."""
-        for data in dataset:
-            data.calc_delta_V(calibration)
-        dV = np.stack([d.delta_V for d in dataset], axis=1)
-        x, y, v, count = self.get_COP_batch(dV)
-        if np.any(count == 0):
-            raise ZeroDivisionError("float division by zero")
-        return {"x_re": x * 2000, "y_re": y * 2000, "x_gt": np.array([d.x for d in dataset]),
-                "y_gt": np.array([d.y for d in dataset]), "values": np.array(v)}
-
     def draw_COP(self, dataset, calibration, ax, title="COP"):
         raise NotImplementedError("plotting is outside the scope of ceit_b200 (the numbers: cop_table)")
 
     def draw_one_situation(self, data, calibration, ax, vmax=None, vmin=None, title_prefix=""):
         raise NotImplementedError("plotting is outside the scope of ceit_b200")
-
-
-class DataHandler(DataPlotter):
-    """Reads recordings from <folder_path>/<file>.csv (DataHandler.py:131-186)."""
-
-    def __init__(self, folder_path, solver=None):
-        super().__init__(solver)
-        self.folder_path = folder_path
-
-    def set_folder_path(self, folder_path):
-        self.folder_path = folder_path
-
-    def read_from_csv(self, filename):
-        data = []
-        with open(self.folder_path + "/" + filename) as f:
-            for line in csv.reader(f, quoting=csv.QUOTE_NONNUMERIC):
-                data.append(line)
-        return np.array(data)
-
-    def read_one_calibration_file(self, filename, contain_excitation=False):
-        data = self.read_from_csv(filename)
-        return CalibData(data, get_height_idx_from_filename(filename), contain_excitation=contain_excitation)
-
-    def read_one_data_file(self, filename, contain_excitation=False):
-        x, y, z = get_corr_from_filename(filename)
-        return Data(self.read_from_csv(filename), x, y, z, contain_excitation=contain_excitation)
 
 
 def get_corr_from_filename(filename):

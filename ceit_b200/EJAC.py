@@ -47,6 +47,9 @@ class EJAC(object):
         self.initial_variable = np.copy(self.fwd_FEM.elem_variable)
         self._eng = self.fwd_FEM._engine
         self._J_dev = None
+        self._J_dev_valid = False
+        self._J_host_stamp = None
+        self._flag_dev = None
         self._base_dev = None
         self._det_dev = None
         self.calc_origin_potential()
@@ -108,12 +111,16 @@ class EJAC(object):
                     lambda: self._eng.plan.jacobian_block(i_from, i_to, e_from, e_to, variable_change, freq, J, E))
                 r0, r1 = i_from * (L - 1), i_to * (L - 1)
                 wait_npy(self.config["rootdir"] + "/" + self.config["folder_name"] + '/JAC_cache.npy')   # reads the pinned matrix
+                full = (i_from == 0 and i_to == L and e_from == 0 and e_to == self.elem_num)
                 if self._J_is_pinned() and e_from == 0 and e_to == self.elem_num:
                     self._J_pinned[r0:r1].copy_(J[r0:r1], non_blocking=True)       # D2H into the pinned matrix
                     self._eng.torch.cuda.current_stream().synchronize()
                 else:
                     self.JAC_matrix[r0:r1, e_from:e_to] = J[r0:r1, e_from:e_to].cpu().numpy()
                 self._eng.check_numeric()
+                # the device matrix equals the host one only when every row block came from this object
+                self._J_dev_valid = bool(full and self._J_is_pinned())
+                self._J_host_stamp = self._stamp_J() if self._J_dev_valid else None
             self.save_JAC_np()
             return self.JAC_matrix
         else:
@@ -125,19 +132,45 @@ class EJAC(object):
         return np.array(self.JAC_matrix[:, np.asarray(self.fwd_FEM.mesh.detection_index)])
 
     # -- inverse models on the device ------------------------------------------------------------------
+    def _current_J(self):
+        """Device copy of JAC_matrix.  After JAC_calculation() the device matrix IS the current Jacobian (the pinned
+        host matrix was filled from it), so nothing is uploaded; a Jacobian the caller loaded or assigned
+        (read_JAC_np, normalize_sensitivity, ...) or edited in place is staged through the pinned buffer."""
+        if (self._J_dev is not None and self._J_dev_valid and self._J_is_pinned()
+                and self._J_host_stamp == self._stamp_J()):
+            return self._J_dev
+        J = self._upload_J()
+        self._J_dev_valid = True
+        self._J_host_stamp = self._stamp_J()
+        return J
+
+    def _stamp_J(self):
+        """Cheap fingerprint of the host matrix (four strided samples + corner sums) to notice in-place edits."""
+        Jm = np.asarray(self.JAC_matrix)
+        flat = Jm.reshape(-1)
+        step = max(1, flat.shape[0] // 4096)
+        return (Jm.shape, float(flat[::step].sum()), float(flat[:64].sum()), float(flat[-64:].sum()))
+
     def _inv_model(self, lmbda, shift, rows=None, scale=1.0):
         t = self._eng.torch
-        J = self._upload_J()
+        J = self._current_J()
+        if self._flag_dev is None:
+            self._flag_dev = t.zeros(1, dtype=t.int32, device=self._eng.dev)
+        flag = self._flag_dev
         det_h = np.ascontiguousarray(self.fwd_FEM.mesh.detection_index, dtype=np.int64)
         if self._det_dev is None or self._det_dev[0].shape != det_h.shape or not np.array_equal(self._det_dev[0], det_h):
             self._det_dev = (det_h.copy(), t.from_numpy(det_h).to(self._eng.dev))
         det = self._det_dev[1]
         if rows is not None:
             rows_d = t.tensor(rows, dtype=t.int64, device=self._eng.dev)
-            return _lib.inverse_model(J, det, lmbda, rows=rows_d, shift=shift, scale=scale)
-        # the result lives in the graph's memory pool: valid until the same model is computed again
-        return self._eng.graphed(("inv", float(lmbda), float(shift), float(scale), J.data_ptr(), det.data_ptr()),
-                                 lambda: _lib.inverse_model(J, det, lmbda, shift=shift, scale=scale))
+            inv = _lib.inverse_model(J, det, lmbda, rows=rows_d, shift=shift, scale=scale, flag=flag)
+        else:
+            # the result lives in the graph's memory pool: valid until the same model is computed again
+            inv = self._eng.graphed(
+                ("inv", float(lmbda), float(shift), float(scale), J.data_ptr(), det.data_ptr()),
+                lambda: _lib.inverse_model(J, det, lmbda, shift=shift, scale=scale, flag=flag))
+        _lib.check_flag(flag)          # np.linalg.inv raises on a singular matrix (EJAC.py:165,241): never cache garbage
+        return inv
 
     def _apply(self, inv, delta_V):
         t = self._eng.torch

@@ -81,7 +81,9 @@ class Solver(object):
         self.read_JAC()
         J = t.from_numpy(np.ascontiguousarray(self.JAC_mat, dtype=np.float64)).to(self._dev)
         det = t.from_numpy(np.ascontiguousarray(self.mesh.detection_index, dtype=np.int64)).to(self._dev)
-        self._inv_dev = _lib.inverse_model(J, det, lmbda, shift=1.0, form=form)
+        flag = t.zeros(1, dtype=t.int32, device=self._dev)
+        self._inv_dev = _lib.inverse_model(J, det, lmbda, shift=1.0, form=form, flag=flag)
+        _lib.check_flag(flag)          # np.linalg.inv raises on a singular matrix (Solver.py:121): nothing is cached
         self.inv_mat = self._inv_dev.cpu().numpy()
         save_npy(self._path('inv_mat.npy'), self.inv_mat)
 

@@ -25,6 +25,7 @@ class Engine:
         # CUDA graphs of library-call sequences on static buffers, keyed by their frozen scalar arguments
         self.use_graphs = True
         self._graphs = {}
+        self._graph_gen = self.plan.generation()
 
     @staticmethod
     def for_mesh(mesh):
@@ -42,14 +43,31 @@ class Engine:
         CUDA graph, later ones replay it: no launch gaps between the ~100 short kernels of a step."""
         if not self.use_graphs or _lib._options.get("stage_timers", 0):
             return fn()
+        # A captured graph holds the plan's workspace pointers and kernel choices of the allocation generation it
+        # was captured in; a real <-> complex switch or a larger excitation chunk re-allocates them (the library
+        # bumps the generation), after which every older graph is stale and is dropped.
+        gen = self.plan.generation()
+        if gen != self._graph_gen:
+            self._graphs.clear()
+            self._graph_gen = gen
         ent = self._graphs.get(key)
         if ent is None:
+            out = fn()                               # eager: may allocate (never inside a capture)
+            gen2 = self.plan.generation()
+            if gen2 != gen:
+                self._graphs.clear()
+                self._graph_gen = gen2
             if len(self._graphs) >= self.MAX_GRAPHS:
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = "warm"
-            return fn()
+            return out
         if ent == "warm":
-            ent = self._graphs[key] = _lib.StepGraph(fn)
+            try:
+                ent = self._graphs[key] = _lib.StepGraph(fn)
+            except _lib.CeitError:
+                # the library refused to allocate inside the capture: stay eager for this key
+                self._graphs.pop(key, None)
+                return fn()
         return ent.replay()
 
     def set_material(self, perm, var, omega):

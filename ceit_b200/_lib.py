@@ -18,7 +18,7 @@ SYMBOLS = [
     "ceit_plan_info", "ceit_plan_tables", "ceit_plan_patches", "ceit_assemble", "ceit_factor", "ceit_jacobian_block",
     "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm", "ceit_plan_csr_values",
     "ceit_set_option", "ceit_stage_times", "ceit_gram_partial", "ceit_inverse_from_gram", "ceit_debug_tile_clocks", "ceit_zgemm",
-    "ceit_center_of_position",
+    "ceit_center_of_position", "ceit_plan_generation", "ceit_plan_numeric_flag",
 ]
 
 
@@ -31,14 +31,17 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    from . import build as _build
+    if not _build.is_current():          # absent, or older than the sources (content hash): never load a stale library
         try:
-            from . import build as _build
             _build.build()
         except Exception as e:  # pragma: no cover
-            raise CeitError(
-                f"native library {LIB_PATH} is missing and could not be built ({e}); "
-                "run `python -m ceit_b200.build` - there is no CPU fallback") from e
+            if not os.path.exists(LIB_PATH):
+                raise CeitError(
+                    f"native library {LIB_PATH} is missing and could not be built ({e}); "
+                    "run `python -m ceit_b200.build` - there is no CPU fallback") from e
+            raise CeitError(f"native library {LIB_PATH} is older than its sources and could not be rebuilt ({e}); "
+                            "run `python -m ceit_b200.build`") from e
     L = ctypes.CDLL(LIB_PATH)
     c_i64, c_dbl, c_vp, c_int = ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int
     L.ceit_last_error.restype = ctypes.c_char_p
@@ -55,7 +58,7 @@ def lib():
     L.ceit_jacobian_block.argtypes = [c_vp, c_i64, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_i64, c_vp, c_vp]
     L.ceit_forward.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]
     L.ceit_inverse_model.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_int,
-                                     c_dbl, c_vp, c_vp]
+                                     c_dbl, c_vp, c_vp, c_vp]
     L.ceit_reconstruct.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp]
     L.ceit_dgemm.argtypes = [c_int, c_int, c_i64, c_i64, c_i64, c_dbl, c_vp, c_i64, c_vp, c_i64, c_dbl,
                              c_vp, c_i64, c_vp]
@@ -63,13 +66,16 @@ def lib():
     L.ceit_plan_csr_values.argtypes = [c_vp, c_vp, c_vp]
     L.ceit_stage_times.argtypes = [c_vp, c_vp]
     L.ceit_gram_partial.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_vp]
-    L.ceit_inverse_from_gram.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp]
+    L.ceit_inverse_from_gram.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp]
+    L.ceit_plan_generation.argtypes = [c_vp]
+    L.ceit_plan_generation.restype = c_i64
+    L.ceit_plan_numeric_flag.argtypes = [c_vp, c_vp, c_vp]
     L.ceit_debug_tile_clocks.argtypes = [c_vp]
     L.ceit_center_of_position.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_dbl, c_vp, c_vp]
     L.ceit_zgemm.argtypes = [c_int, c_int, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl,
                              c_vp, c_i64, c_vp]
     for name in SYMBOLS:
-        if name not in ("ceit_last_error", "ceit_launch_count"):
+        if name not in ("ceit_last_error", "ceit_launch_count", "ceit_plan_generation"):
             getattr(L, name).restype = c_int
     _lib = L
     return L
@@ -232,8 +238,14 @@ class Plan:
                                  stream_ptr()))
 
     def numeric_flag(self):
-        """0 = ok, 1 = a Cholesky pivot was not positive (synchronises)."""
-        return int(self.info()[13])
+        """0 = ok, 1 = a Cholesky pivot was not positive (synchronises the current stream)."""
+        flag = ctypes.c_int(0)
+        check(lib().ceit_plan_numeric_flag(self._h, ctypes.byref(flag), stream_ptr()))
+        return int(flag.value)
+
+    def generation(self):
+        """Allocation generation of the plan's workspaces (graphs captured in an older one are stale)."""
+        return int(lib().ceit_plan_generation(self._h))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -247,19 +259,29 @@ class Plan:
             pass
 
 
-def inverse_model(J, det_idx, lmbda, rows=None, shift=1.0, form=0, scale=1.0):
-    """J: cuda f64 (m, E) tensor; det_idx: cuda int64; returns cuda f64 (n_det, m_sel)."""
+SINGULAR_MSG = "Singular matrix"      # numpy.linalg.LinAlgError text of np.linalg.inv (Solver.py:121, EJAC.py:165)
+
+
+def check_flag(flag):
+    """Raise like np.linalg.inv does when the regularised normal matrix had a non-positive pivot (synchronises)."""
+    if flag is not None and int(flag.item()) != 0:
+        raise np.linalg.LinAlgError(SINGULAR_MSG)
+
+
+def inverse_model(J, det_idx, lmbda, rows=None, shift=1.0, form=0, scale=1.0, flag=None):
+    """J: cuda f64 (m, E) tensor; det_idx: cuda int64; returns cuda f64 (n_det, m_sel).
+    flag: optional cuda int32[1] tensor receiving the pivot flag (see check_flag)."""
     torch = require_cuda()
     m, ldJ = J.shape[0], J.stride(0)
     n_det = det_idx.numel()
     m_sel = rows.numel() if rows is not None else m
     out = torch.empty((n_det, m_sel), dtype=torch.float64, device=J.device)
     check(lib().ceit_inverse_model(tptr(J), ldJ, m, tptr(det_idx), n_det, tptr(rows), m_sel, float(shift),
-                                   float(lmbda), int(form), float(scale), tptr(out), stream_ptr()))
+                                   float(lmbda), int(form), float(scale), tptr(out), tptr(flag), stream_ptr()))
     return out
 
 
-def inverse_model_sharded(J, det_idx_local, lmbda, shift=1.0, scale=1.0, group=None):
+def inverse_model_sharded(J, det_idx_local, lmbda, shift=1.0, scale=1.0, group=None, flag=None):
     """Dual-form inverse model with the detection elements sharded over the ranks of `group`:
     partial Gram matrices are summed with one all-reduce; returns this rank's rows (n_det_local, m)."""
     torch = require_cuda()
@@ -274,7 +296,7 @@ def inverse_model_sharded(J, det_idx_local, lmbda, shift=1.0, scale=1.0, group=N
     out = torch.empty((n_loc, m), dtype=torch.float64, device=J.device)
     if n_loc:
         check(lib().ceit_inverse_from_gram(tptr(J), ldJ, m, tptr(det_idx_local), n_loc, tptr(None), m, float(shift),
-                                           float(lmbda), float(scale), tptr(G), tptr(out), stream_ptr()))
+                                           float(lmbda), float(scale), tptr(G), tptr(out), tptr(flag), stream_ptr()))
     return out
 
 

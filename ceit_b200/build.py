@@ -19,17 +19,31 @@ NVCC_FLAGS = [
 ] + (["-DCEIT_TILE_CLOCKS"] if os.environ.get("CEIT_TILE_CLOCKS") else [])
 
 
-def _newest_source_mtime():
-    t = 0.0
+STAMP = LIB + ".srchash"
+
+
+def source_hash():
+    """Content hash of every native source + the public header + the flags (mtimes do not survive a snapshot)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     for root in (CSRC, os.path.join(HERE, "..", "include")):
-        for f in os.listdir(root):
-            t = max(t, os.path.getmtime(os.path.join(root, f)))
-    return t
+        for f in sorted(os.listdir(root)):
+            with open(os.path.join(root, f), "rb") as fh:
+                h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
+def is_current():
+    try:
+        with open(STAMP) as fh:
+            return os.path.exists(LIB) and fh.read().strip() == source_hash()
+    except OSError:
+        return False
 
 
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
+    if not force and is_current():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
@@ -39,6 +53,8 @@ def build(force=False, verbose=False):
         subprocess.run(cmd, check=True)
         objs.append(o)
     subprocess.run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"], check=True)
+    with open(STAMP, "w") as fh:
+        fh.write(source_hash())
     return LIB
 
 

@@ -171,6 +171,8 @@ struct ceit_plan {
   int32_t *d_rc_ptr = nullptr, *d_rc_src = nullptr;
   int64_t *d_m2_dst = nullptr, *d_sg_off = nullptr;
   int alloc_mode = 0;
+  int64_t generation = 0;   // bumped whenever a numeric / excitation workspace is (re)allocated: graphs captured
+                            // before hold stale pointers (ceit_plan_generation)
   // per-excitation workspace
   int ex_cap = 0, ex_mode = 0;
   void *St = nullptr, *Ls = nullptr, *Linvs = nullptr, *Sinv = nullptr, *Yh = nullptr, *phi0 = nullptr;
@@ -252,10 +254,25 @@ int upload_plan(ceit_plan* p) {
   return 0;
 }
 
+// workspaces are never (re)allocated while the caller's stream is being captured: cudaFree / cudaMalloc are not
+// capturable and a replay would not redo them.  The caller runs the sequence eagerly once first.
+inline int refuse_alloc_in_capture(cudaStream_t st, const char* what) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+    ceit::g_err = std::string(what) + ": workspace allocation needed during stream capture; run the same call "
+                  "sequence eagerly once before capturing it";
+    return CEIT_ERR_STATE;
+  }
+  return 0;
+}
+
 template <class T>
-int alloc_numeric(ceit_plan* p) {
+int alloc_numeric(ceit_plan* p, cudaStream_t st) {
   const int want = Sc<T>::is_complex ? 2 : 1;
   if (p->alloc_mode == want) return 0;
+  if (int rc_ = refuse_alloc_in_capture(st, "ceit_factor")) return rc_;
+  CUDA_TRY(cudaDeviceSynchronize());   // buffers of the other mode may still be in use on any stream
+  p->generation++;
   void** bufs[] = {&p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
                    &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->tmpT, &p->tmpPanel2, &p->Ptmp2, &p->g0e, &p->Aint, &p->Lint,
                    &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1, &p->XP, &p->Mreg, &p->LT,
@@ -313,9 +330,12 @@ int alloc_numeric(ceit_plan* p) {
 }
 
 template <class T>
-int alloc_excitation_ws(ceit_plan* p, int want_cap) {
+int alloc_excitation_ws(ceit_plan* p, int want_cap, cudaStream_t st) {
   const int want_mode = Sc<T>::is_complex ? 2 : 1;
   if (p->ex_cap >= want_cap && p->ex_mode == want_mode) return 0;
+  if (int rc_ = refuse_alloc_in_capture(st, "ceit_jacobian_block / ceit_forward")) return rc_;
+  CUDA_TRY(cudaDeviceSynchronize());
+  p->generation++;
   void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS,
                  &p->TBB, &p->LB, &p->LinvB, &p->Dcat, &p->ZW};
   for (auto b : ex) dev_free_tracked(p, *b);
@@ -413,7 +433,7 @@ inline void schur_u_gemm(ceit_plan*, cudaStream_t st, int64_t nU, int64_t N0P, c
 template <class T>
 int factor_impl(ceit_plan* p, cudaStream_t st) {
   const HostPlan& h = p->h;
-  int rc = alloc_numeric<T>(p);
+  int rc = alloc_numeric<T>(p, st);
   if (rc) return rc;
   T *Ad = (T*)p->Ad, *Bs = (T*)p->Bs, *Ld = (T*)p->Ld, *Linv = (T*)p->Linv, *Lsub = (T*)p->Lsub;
   T *Sel = (T*)p->Sel, *K0U = (T*)p->K0U, *Zw = (T*)p->Zw, *Xh = (T*)p->XP, *Xc = (T*)p->Xh, *KUU = (T*)p->KUU;   // Xh: padded rows here
@@ -846,7 +866,7 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
                   double* J, int64_t ldJ, double* base, cudaStream_t st) {
   const HostPlan& h = p->h;
   const int cap = std::min<int64_t>(excitation_chunk_cap(p, sizeof(T)), i_to - i_from);
-  int rc = alloc_excitation_ws<T>(p, cap);
+  int rc = alloc_excitation_ws<T>(p, cap, st);
   if (rc) return rc;
   const int warps = 8;
   const size_t smem = (size_t)warps * h.nU * sizeof(double);
@@ -895,7 +915,7 @@ template <class T>
 int forward_impl(ceit_plan* p, int64_t i, double* node_abs, double* elem_pot, double* electrode_pot,
                  cudaStream_t st) {
   const HostPlan& h = p->h;
-  int rc = alloc_excitation_ws<T>(p, std::max(1, p->ex_cap));
+  int rc = alloc_excitation_ws<T>(p, std::max(1, p->ex_cap), st);
   if (rc) return rc;
   rc = excitation_impl<T>(p, (int)i, 1, st);
   if (rc) return rc;
@@ -924,6 +944,49 @@ int forward_impl(ceit_plan* p, int64_t i, double* node_abs, double* elem_pot, do
   return 0;
 }
 
+}  // namespace
+
+namespace {
+// Stream-ordered temporaries of the plan-less inverse-model entry points.  They come from a pool OWNED by the
+// library (its release threshold keeps the memory across synchronisations; the device's default pool, which
+// PyTorch and other users share, is left alone) and are released on every exit path.
+cudaMemPool_t inverse_pool() {
+  static cudaMemPool_t pool = nullptr;
+  static int pool_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (pool && pool_dev == dev) return pool;
+  cudaMemPoolProps props;
+  std::memset(&props, 0, sizeof(props));
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = dev;
+  cudaMemPool_t np = nullptr;
+  if (cudaMemPoolCreate(&np, &props) != cudaSuccess) return nullptr;
+  uint64_t thr = UINT64_MAX;
+  cudaMemPoolSetAttribute(np, cudaMemPoolAttrReleaseThreshold, &thr);
+  pool = np;
+  pool_dev = dev;
+  return pool;
+}
+struct AsyncBufs {
+  cudaStream_t st;
+  std::vector<void*> bufs;
+  explicit AsyncBufs(cudaStream_t s) : st(s) {}
+  ~AsyncBufs() {
+    for (void* b : bufs) cudaFreeAsync(b, st);
+  }
+  cudaError_t get(void** out, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaMemPool_t pool = inverse_pool();
+    cudaError_t e = pool ? cudaMallocFromPoolAsync(out, bytes, pool, st) : cudaMallocAsync(out, bytes, st);
+    if (e == cudaSuccess) bufs.push_back(*out);
+    return e;
+  }
+  template <class V>
+  cudaError_t get(V** out, int64_t count) { return get((void**)out, (size_t)count * sizeof(V)); }
+};
 }  // namespace
 
 // ====================================================================================================
@@ -998,6 +1061,18 @@ int ceit_plan_info(const ceit_plan_t* p, int64_t* info) {
     int flag = 0;
     if (cudaMemcpy(&flag, p->d_info, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) info[13] = flag;
   }
+  return CEIT_OK;
+}
+
+int64_t ceit_plan_generation(const ceit_plan_t* p) { return p ? p->generation : -1; }
+
+int ceit_plan_numeric_flag(const ceit_plan_t* p, int* flag_out, void* stream) {
+  if (!p || !flag_out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_numeric_flag: null argument");
+  *flag_out = 0;
+  if (!p->uploaded || !p->d_info) return CEIT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(flag_out, p->d_info, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return CEIT_OK;
 }
 
@@ -1089,38 +1164,25 @@ int ceit_forward(ceit_plan_t* p, int64_t i, double* node_abs, double* elem_pot, 
 
 int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* det_idx, int64_t n_det,
                        const int64_t* rows, int64_t m_sel, double shift, double lambda, int form, double scale_,
-                       double* inv_out, void* stream) {
+                       double* inv_out, int* flag, void* stream) {
   if (!J || !det_idx || !inv_out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_model: null argument");
   if (m <= 0 || n_det <= 0 || ldJ <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_model: bad shape");
   if (!rows) m_sel = m;
   if (m_sel <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_model: empty row selection");
   cudaStream_t st = (cudaStream_t)stream;
-  {
-    // keep the stream-ordered pool's memory across synchronisations (the default threshold of 0 hands
-    // gigabytes back to the driver at every sync and re-maps them on the next call)
-    static bool pool_set = false;
-    if (!pool_set) {
-      int dev = 0;
-      cudaMemPool_t pool;
-      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-      }
-      pool_set = true;
-    }
-  }
   StageScope sc(4, st);
   if (form == 0) form = (m_sel <= n_det) ? 2 : 1;
   const int64_t n = (form == 2) ? m_sel : n_det;  // size of the SPD system
   double *Jt = nullptr, *G = nullptr, *Lg = nullptr, *Li = nullptr, *Gi = nullptr, *tmp = nullptr;
-  int* info = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&Jt, m_sel * n_det * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&G, n * n * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&Lg, n * n * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&Li, n * n * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&Gi, std::max(n * n, n_det * m_sel) * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&tmp, (int64_t)TILE * n * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&info, sizeof(int), st));
+  int* info = flag;
+  AsyncBufs ws(st);
+  CUDA_TRY(ws.get(&Jt, m_sel * n_det));
+  CUDA_TRY(ws.get(&G, n * n));
+  CUDA_TRY(ws.get(&Lg, n * n));
+  CUDA_TRY(ws.get(&Li, n * n));
+  CUDA_TRY(ws.get(&Gi, std::max(n * n, n_det * m_sel)));
+  CUDA_TRY(ws.get(&tmp, (int64_t)TILE * n));
+  if (!info) CUDA_TRY(ws.get(&info, 1));
   CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(Lg, 0, n * n * sizeof(double), st));
   CUDA_TRY(cudaMemsetAsync(Li, 0, n * n * sizeof(double), st));
@@ -1130,11 +1192,10 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
     // G = Jt Jt^T + lambda^2 I (m x m);  inv = Jt^T G^-1
     {
       const int S = splitk_slices(n, n, n_det, 1);
-      double* ws = nullptr;
-      if (S > 1) CUDA_TRY(cudaMallocAsync((void**)&ws, (size_t)S * n * n * sizeof(double), st));
-      if (S > 1) gemm_splitk(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, Jt, n_det, 0.0, G, n, ws, /*lower_only=*/1);
+      double* sws = nullptr;
+      if (S > 1) CUDA_TRY(ws.get(&sws, (int64_t)S * n * n));
+      if (S > 1) gemm_splitk(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, Jt, n_det, 0.0, G, n, sws, /*lower_only=*/1);
       else gemm<double>(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0, 1, /*lower_only=*/1);
-      if (ws) CUDA_TRY(cudaFreeAsync(ws, st));
     }
     add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, G, n);
     CEIT_COUNT_LAUNCH();
@@ -1151,13 +1212,6 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
     gemm<double>(st, 1, 0, n, m_sel, n, scale_, Li, n, 0, Gi, m_sel, 0, 0.0, inv_out, m_sel, 0);
   }
   KERNEL_CHECK();
-  CUDA_TRY(cudaFreeAsync(Jt, st));
-  CUDA_TRY(cudaFreeAsync(G, st));
-  CUDA_TRY(cudaFreeAsync(Lg, st));
-  CUDA_TRY(cudaFreeAsync(Li, st));
-  CUDA_TRY(cudaFreeAsync(Gi, st));
-  CUDA_TRY(cudaFreeAsync(tmp, st));
-  CUDA_TRY(cudaFreeAsync(info, st));
   return CEIT_OK;
 }
 
@@ -1174,28 +1228,27 @@ int ceit_gram_partial(const double* J, int64_t ldJ, int64_t m, const int64_t* de
     return CEIT_OK;
   }
   double* Jt = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&Jt, m_sel * n_det * sizeof(double), st));
+  AsyncBufs ws(st);
+  CUDA_TRY(ws.get(&Jt, m_sel * n_det));
   gather_shift_kernel<<<cdiv(m_sel * n_det, 256), 256, 0, st>>>(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
   CEIT_COUNT_LAUNCH();
   {
     // symmetric: lower triangle only (split over K when its tiles cannot fill the chip), then mirrored so that the
     // all-reduce over the ranks sums a complete matrix
     const int S = splitk_slices(m_sel, m_sel, n_det, 1);
-    double* ws = nullptr;
-    if (S > 1) CUDA_TRY(cudaMallocAsync((void**)&ws, (size_t)S * m_sel * m_sel * sizeof(double), st));
-    gemm_splitk(st, 0, 1, m_sel, m_sel, n_det, 1.0, Jt, n_det, Jt, n_det, 0.0, G, m_sel, ws, /*lower_only=*/1);
-    if (ws) CUDA_TRY(cudaFreeAsync(ws, st));
+    double* sws = nullptr;
+    if (S > 1) CUDA_TRY(ws.get(&sws, (int64_t)S * m_sel * m_sel));
+    gemm_splitk(st, 0, 1, m_sel, m_sel, n_det, 1.0, Jt, n_det, Jt, n_det, 0.0, G, m_sel, sws, /*lower_only=*/1);
     symmetrize_from_lower_kernel<<<cdiv(m_sel * m_sel, 256), 256, 0, st>>>(m_sel, G, m_sel);
     CEIT_COUNT_LAUNCH();
   }
   KERNEL_CHECK();
-  CUDA_TRY(cudaFreeAsync(Jt, st));
   return CEIT_OK;
 }
 
 int ceit_inverse_from_gram(const double* J, int64_t ldJ, int64_t m, const int64_t* det_idx, int64_t n_det,
                            const int64_t* rows, int64_t m_sel, double shift, double lambda, double scale_,
-                           const double* G, double* inv_out, void* stream) {
+                           const double* G, double* inv_out, int* flag, void* stream) {
   if (!J || !det_idx || !G || !inv_out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_from_gram: null argument");
   if (!rows) m_sel = m;
   if (m <= 0 || n_det <= 0 || m_sel <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_inverse_from_gram: bad shape");
@@ -1203,14 +1256,15 @@ int ceit_inverse_from_gram(const double* J, int64_t ldJ, int64_t m, const int64_
   StageScope sc(4, st);
   const int64_t n = m_sel;
   double *Jt = nullptr, *Gw = nullptr, *Lg = nullptr, *Li = nullptr, *Gi = nullptr, *tmp = nullptr;
-  int* info = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&Jt, m_sel * n_det * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&Gw, n * n * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&Lg, n * n * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&Li, n * n * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&Gi, n * n * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&tmp, (int64_t)TILE * n * sizeof(double), st));
-  CUDA_TRY(cudaMallocAsync((void**)&info, sizeof(int), st));
+  int* info = flag;
+  AsyncBufs ws(st);
+  CUDA_TRY(ws.get(&Jt, m_sel * n_det));
+  CUDA_TRY(ws.get(&Gw, n * n));
+  CUDA_TRY(ws.get(&Lg, n * n));
+  CUDA_TRY(ws.get(&Li, n * n));
+  CUDA_TRY(ws.get(&Gi, n * n));
+  CUDA_TRY(ws.get(&tmp, (int64_t)TILE * n));
+  if (!info) CUDA_TRY(ws.get(&info, 1));
   CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(Lg, 0, n * n * sizeof(double), st));
   CUDA_TRY(cudaMemsetAsync(Li, 0, n * n * sizeof(double), st));
@@ -1223,13 +1277,6 @@ int ceit_inverse_from_gram(const double* J, int64_t ldJ, int64_t m, const int64_
   gemm<double>(st, 1, 0, n, n, n, 1.0, Li, n, 0, Li, n, 0, 0.0, Gi, n, 0);
   gemm<double>(st, 1, 0, n_det, m_sel, m_sel, scale_, Jt, n_det, 0, Gi, n, 0, 0.0, inv_out, m_sel, 0);
   KERNEL_CHECK();
-  CUDA_TRY(cudaFreeAsync(Jt, st));
-  CUDA_TRY(cudaFreeAsync(Gw, st));
-  CUDA_TRY(cudaFreeAsync(Lg, st));
-  CUDA_TRY(cudaFreeAsync(Li, st));
-  CUDA_TRY(cudaFreeAsync(Gi, st));
-  CUDA_TRY(cudaFreeAsync(tmp, st));
-  CUDA_TRY(cudaFreeAsync(info, st));
   return CEIT_OK;
 }
 

@@ -59,6 +59,17 @@ int ceit_plan_destroy(ceit_plan_t* plan);
  *              NP (position rows), N0P (position of the first electrode node), node cap of a Woodbury patch,
  *              reserved */
 int ceit_plan_info(const ceit_plan_t* plan, int64_t* info24);
+/* Allocation generation of the plan: incremented whenever the numeric or per-excitation workspaces are
+ * (re)allocated (first use, real <-> complex switch, larger excitation chunk).  A CUDA graph captured from calls on
+ * this plan holds the workspace pointers of the generation it was captured in and must be dropped when the
+ * generation changes.  Workspaces are never (re)allocated while the stream is being captured: the call fails with
+ * CEIT_ERR_STATE instead (run the sequence eagerly once first).  No device access. */
+int64_t ceit_plan_generation(const ceit_plan_t* plan);
+/* Pivot flag of the factorisations enqueued on `stream` so far (0 ok, 1 = a Cholesky pivot was not positive /
+ * zero): copied on `stream` and synchronised there, so it is ordered after the work the caller enqueued on that
+ * stream (info[13] of ceit_plan_info reads the same flag with a blocking legacy-stream copy).
+ * Mirrors the LinAlgError np.linalg.inv raises on a singular K_ff (CEIT/EFEM.py:119). */
+int ceit_plan_numeric_flag(const ceit_plan_t* plan, int* flag_out, void* stream);
 /* host copies of the symbolic tables (any pointer may be NULL):
  * rowptr i64[N+1], colidx i64[nnz] (CSR pattern of K, sorted, == scipy.sparse.csr_matrix of the
  * reference's dense K_sparse), pos i64[N] (node -> row of Xh / Yh / phi0: a permutation, F0 nodes
@@ -123,10 +134,14 @@ int ceit_forward(ceit_plan_t* plan, int64_t i, double* node_abs, double* elem_po
  * (eit_solve_on_some_electrodes, EJAC.py:210-220; NULL = all m rows);
  * form: 0 = auto, 1 = primal (n_det x n_det normal equations, as the reference writes it),
  *       2 = dual (m x m push-through form, identical operator); scale multiplies the result
- * (1e-4 in EJAC.py:228).  inv_out [dev] f64[n_det * m_sel]. */
+ * (1e-4 in EJAC.py:228).  inv_out [dev] f64[n_det * m_sel].
+ * flag [dev] int, optional: set to 0, then to 1 if a pivot of the Cholesky factorisation of the regularised
+ * normal matrix is not positive (NaN / Inf in J, lambda = 0 with a rank-deficient Gram matrix) - the condition on
+ * which the reference's np.linalg.inv raises LinAlgError (Solver.py:121); the host classes check it before they
+ * cache inv_mat.npy. */
 int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* det_idx,
                        int64_t n_det, const int64_t* rows, int64_t m_sel, double shift,
-                       double lambda, int form, double scale, double* inv_out, void* stream);
+                       double lambda, int form, double scale, double* inv_out, int* flag, void* stream);
 
 /* ---- inverse model sharded over detection elements (multi-GPU, dual form) -------------------------
  * Each rank holds a slice det_idx[0..n_det) of the detection elements (J replicated):
@@ -138,7 +153,7 @@ int ceit_gram_partial(const double* J, int64_t ldJ, int64_t m, const int64_t* de
                       const int64_t* rows, int64_t m_sel, double shift, double* G, void* stream);
 int ceit_inverse_from_gram(const double* J, int64_t ldJ, int64_t m, const int64_t* det_idx, int64_t n_det,
                            const int64_t* rows, int64_t m_sel, double shift, double lambda, double scale,
-                           const double* G, double* inv_out, void* stream);
+                           const double* G, double* inv_out, int* flag, void* stream);
 
 /* ---- realtime reconstruction ---------------------------------------------------------------------
  * Replaces Solver.solve (CEIT/Solver.py:95-108): out = inv_mat . delta_V

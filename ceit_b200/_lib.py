@@ -188,6 +188,7 @@ class Plan:
         info = self.info()
         self.nU, self.N0, self.n_blocks, self.max_block, self.nnz = (int(info[k]) for k in (3, 4, 5, 6, 7))
         self.P, self.nI, self.bmax, self.nC, self.NP, self.N0P = (int(info[k]) for k in range(16, 22))
+        self.tree_levels = int(info[23])
 
     def info(self):
         out = np.zeros(24, dtype=np.int64)

@@ -10,6 +10,7 @@
 
 #include "../../include/ceit_b200.h"
 #include "dense.cuh"
+#include "factor_tree.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
 #include "plan.h"
@@ -55,7 +56,8 @@ int g_ex_overlap = 1;   // excitation stage: ZW / base potentials on a second st
 int g_ru_wc = 0, g_ru_cpt = 0, g_ru_waves = 8;   // rank_update_kernel layout overrides (tuning; 0 = auto)
 int g_direct_excitation = 0;
 int g_patch_nodes = 0;   // experiment: override the node cap of the element patches
-int64_t g_nd_interior = 64;   // target nodes per nested-dissection interior; <= 0 disables level 1
+int64_t g_nd_interior = 64;   // target nodes per nested-dissection interior / leaf; <= 0 disables the dissection
+int g_nd_tree = 1;            // 1: multi-level nested dissection (factor_tree.h); 0: interiors + block-tridiagonal chain
 struct StageEv {
   int stage;
   cudaEvent_t a, b;
@@ -170,6 +172,10 @@ struct ceit_plan {
   int32_t *d_node_at = nullptr, *d_bnd_loc = nullptr, *d_m2_src_ptr = nullptr, *d_m2_src = nullptr;
   int32_t *d_rc_ptr = nullptr, *d_rc_src = nullptr;
   int64_t *d_m2_dst = nullptr, *d_sg_off = nullptr;
+  // multi-level nested dissection tables (TreePlan)
+  int32_t *d_t_sib = nullptr, *d_t_ps = nullptr, *d_t_pb = nullptr, *d_t_rel = nullptr, *d_t_bnd_row = nullptr;
+  int32_t *d_t_rc_dst = nullptr, *d_t_rc_ptr = nullptr, *d_t_rc_src = nullptr;
+  int64_t *d_t_pA = nullptr, *d_t_pB = nullptr, *d_t_pC = nullptr, *d_t_pad = nullptr;
   int alloc_mode = 0;
   int64_t generation = 0;   // bumped whenever a numeric / excitation workspace is (re)allocated: graphs captured
                             // before hold stale pointers (ceit_plan_generation)
@@ -240,6 +246,21 @@ int upload_plan(ceit_plan* p) {
   if ((rc = upload_vec(p, &p->d_rc_ptr, h.rc_ptr))) return rc;
   if ((rc = upload_vec(p, &p->d_rc_src, h.rc_src))) return rc;
   if ((rc = upload_vec(p, &p->d_sg_off, h.sg_off))) return rc;
+  if (h.use_tree) {
+    const TreePlan& t = h.tree;
+    if ((rc = upload_vec(p, &p->d_t_sib, t.sib))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_ps, t.ps))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_pb, t.pb))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_rel, t.rel))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_bnd_row, t.bnd_row))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_rc_dst, t.rc_dst))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_rc_ptr, t.rc_ptr))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_rc_src, t.rc_src))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_pA, t.pA))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_pB, t.pB))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_pC, t.pC))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_pad, t.pad_diag))) return rc;
+  }
   if ((rc = upload_vec(p, &p->d_ue_ptr, h.ue_ptr))) return rc;
   if ((rc = upload_vec(p, &p->d_wk, h.wk))) return rc;
   if ((rc = dev_alloc(p, (void**)&p->d_area, h.E * sizeof(double)))) return rc;
@@ -296,7 +317,7 @@ int alloc_numeric(ceit_plan* p, cudaStream_t st) {
   if ((rc = dev_alloc(p, &p->Lsub, h.szS * es))) return rc;
   if ((rc = dev_alloc(p, &p->Sel, (h.szD + h.szS + h.szPP + h.szV) * es))) return rc;
   if ((rc = dev_alloc(p, &p->K0U, h.N0P * h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->Zw, h.N0P * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Zw, (h.use_tree ? 0 : h.N0P * h.nU) * es))) return rc;
   if ((rc = dev_alloc(p, &p->Xh, h.N * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->XP, h.N0P * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Aint, h.szPP * es))) return rc;
@@ -305,8 +326,8 @@ int alloc_numeric(ceit_plan* p, cudaStream_t st) {
   if ((rc = dev_alloc(p, &p->Ainv, h.szPP * es))) return rc;
   if ((rc = dev_alloc(p, &p->Bt, h.szV * es))) return rc;
   if ((rc = dev_alloc(p, &p->Wn, h.szV * es))) return rc;
-  if ((rc = dev_alloc(p, &p->Tm, h.P * h.bmax * h.bmax * es))) return rc;
-  if ((rc = dev_alloc(p, &p->G1, h.P * h.bmax * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Tm, std::max<int64_t>(h.P * h.bmax * h.bmax, h.tree.szC) * es))) return rc;
+  if ((rc = dev_alloc(p, &p->G1, std::max<int64_t>(h.P * h.bmax, h.tree.maxG) * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Mreg, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->LT, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->LinvT, h.nU * h.nU * es))) return rc;
@@ -321,7 +342,10 @@ int alloc_numeric(ceit_plan* p, cudaStream_t st) {
   if ((rc = dev_alloc(p, &p->SU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Ptmp, maxS * es))) return rc;
   if ((rc = dev_alloc(p, &p->Ptmp2, maxS * es))) return rc;
-  if ((rc = dev_alloc(p, &p->tmpPanel, (int64_t)TILE * h.max_block * es))) return rc;
+  int64_t panel = (int64_t)TILE * h.max_block;
+  for (const TreeLevel& lv : h.tree.lv)
+    if (lv.s > TILE) panel = std::max<int64_t>(panel, (int64_t)lv.n * TILE * lv.s);
+  if ((rc = dev_alloc(p, &p->tmpPanel, panel * es))) return rc;
   if ((rc = dev_alloc(p, &p->tmpT, (int64_t)TILE * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->tmpPanel2, (int64_t)TILE * h.max_block * es))) return rc;
   if ((rc = dev_alloc(p, &p->g0e, 6 * h.E * es))) return rc;
@@ -423,6 +447,106 @@ inline void schur_u_gemm(ceit_plan*, cudaStream_t st, int64_t nU, int64_t N0P, c
   gemm<cd>(st, 1, 0, nU, nU, N0P, neg(Sc<cd>::one()), K0U, nU, 0, X, nU, 0, Sc<cd>::one(), SU, nU, 0);
 }
 
+// T = (S_U + gamma e e^T)^-1 and t_e = T e on stream s_t: shared by every excitation (rank-update excitation stage)
+template <class T>
+int base_shared_inverse(ceit_plan* p, cudaStream_t s_t) {
+  const HostPlan& h = p->h;
+  const int64_t nU = h.nU;
+  const size_t es = sizeof(T);
+  const T one = Sc<T>::one(), zero = Sc<T>::zero();
+  T* SU = (T*)p->SU;
+  if (use_rank_update(p)) {
+    // T, t_e = T e: shared by every excitation (Y_T = Xh T and y_e = Y_T e follow once X is complete)
+    T *Mreg = (T*)p->Mreg, *LT = (T*)p->LT, *LinvT = (T*)p->LinvT, *Tinv = (T*)p->Tinv, *te = (T*)p->te;
+    trace_gamma_kernel<T><<<1, 256, 0, s_t>>>((int)nU, SU, p->d_gamma);
+    CEIT_COUNT_LAUNCH();
+    add_rank1_e_kernel<T><<<cdiv(nU * nU, 256), 256, 0, s_t>>>((int)nU, SU, p->d_gamma, Mreg);
+    CEIT_COUNT_LAUNCH();
+    CUDA_TRY(cudaMemsetAsync(LT, 0, nU * nU * es, s_t));
+    CUDA_TRY(cudaMemsetAsync(LinvT, 0, nU * nU * es, s_t));
+    potrf_trtri_blocked<T>(s_t, nU, Mreg, nU, 0, LT, nU, 0, LinvT, nU, 0, (T*)p->tmpT, 0, 1, p->d_info,
+                           g_multi_stream ? &p->lane_b : nullptr);
+    gemm<T>(s_t, 1, 0, nU, nU, nU, one, LinvT, nU, 0, LinvT, nU, 0, zero, Tinv, nU, 0);
+    rowsum_e_kernel<T><<<cdiv(nU, 8), 256, 0, s_t>>>(nU, (int)nU, Tinv, te);
+    CEIT_COUNT_LAUNCH();
+  }
+  return 0;
+}
+
+// end of the base stage: element blocks of the selected inverse, compact X, Xh = [X ; -I], Y_T = Xh T, G1
+template <class T>
+int base_tail(ceit_plan* p, cudaStream_t st, cudaStream_t sr, cudaStream_t s_t) {
+  const HostPlan& h = p->h;
+  const int64_t nU = h.nU;
+  const T one = Sc<T>::one(), zero = Sc<T>::zero();
+  T *Sel = (T*)p->Sel, *g0e = (T*)p->g0e, *Xh = (T*)p->XP, *Xc = (T*)p->Xh;
+  gather_g0_kernel<T><<<cdiv(6 * h.E, 256), 256, 0, st>>>(6 * h.E, p->d_g0_off, Sel, g0e);
+  CEIT_COUNT_LAUNCH();
+  compact_rows_kernel<T><<<cdiv(h.N0, 8), 256, 0, sr>>>(h.N0, (int)nU, p->d_row_map, Xh, Xc);
+  CEIT_COUNT_LAUNCH();
+  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>((int)nU, Xc + h.N0 * nU);
+  CEIT_COUNT_LAUNCH();
+  if (use_rank_update(p)) {
+    T *Tinv = (T*)p->Tinv, *YT = (T*)p->YT, *ye = (T*)p->ye;
+    CEIT_AFTER(s_t, sr);
+    gemm<T>(sr, 0, 0, h.N, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);                 // Y_T = Xh T
+    rowsum_e_kernel<T><<<cdiv(h.N, 8), 256, 0, sr>>>(h.N, (int)nU, YT, ye);
+    CEIT_COUNT_LAUNCH();
+    CEIT_AFTER(sr, st);
+    launch_g1(p, g0e, YT, Xc, st);
+  } else {
+    CEIT_AFTER(s_t, sr);
+    CEIT_AFTER(sr, st);
+  }
+  return 0;
+}
+
+// ---- CUDA backend of factor_tree.h: batched DMMA GEMMs, the tile factorisation and the gather / scatter kernels on
+// two streams (lane 0 = the caller's stream: matrix chain; lane 1: right-hand-side chain) --------------------------
+template <class T>
+struct CudaTreeBK {
+  ceit_plan* p;
+  cudaStream_t lane[2];
+  T* panel;
+  int rc = 0;
+  void after(int from, int to) {
+    if (!rc) rc = stream_after(p, lane[from], lane[to]);
+  }
+  void gemm(int ln, int opA, int opB, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t lda, int64_t sA,
+            const T* B, int64_t ldb, int64_t sB, T beta, T* C, int64_t ldc, int64_t sC, int batch, int lower_only) {
+    ceit::gemm<T>(lane[ln], opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch, lower_only);
+  }
+  void potrf(int ln, int64_t n, T* A, T* L, T* Li, int batch) {
+    potrf_trtri_blocked<T>(lane[ln], n, A, n, n * n, L, n, n * n, Li, n, n * n, panel, (int64_t)TILE * n, batch,
+                           p->d_info, (g_multi_stream && ln == 0) ? &p->lane_a : nullptr);
+  }
+  void extend_add(int ln, const TreePlan&, const TreeLevel& lv, int pass, const T* U, T* A, T* Bt, T* C) {
+    dim3 grid(cdiv((int64_t)lv.b * lv.b, 256), lv.n);
+    extend_add_kernel<T><<<grid, 256, 0, lane[ln]>>>(lv.b, pass, p->d_t_sib + lv.f0, p->d_t_pA + lv.f0,
+                                                     p->d_t_pB + lv.f0, p->d_t_pC + lv.f0, p->d_t_ps + lv.f0,
+                                                     p->d_t_pb + lv.f0, p->d_t_rel + lv.offR, U, A, Bt, C);
+    CEIT_COUNT_LAUNCH();
+  }
+  void extend_gather(int ln, const TreePlan&, const TreeLevel& lv, const T* Sg, const T* V, T* C) {
+    dim3 grid(cdiv((int64_t)lv.b * lv.b, 256), lv.n);
+    extend_gather_kernel<T><<<grid, 256, 0, lane[ln]>>>(lv.b, p->d_t_pA + lv.f0, p->d_t_pB + lv.f0, p->d_t_pC + lv.f0,
+                                                        p->d_t_ps + lv.f0, p->d_t_pb + lv.f0, p->d_t_rel + lv.offR, Sg,
+                                                        V, C, C + lv.offC);
+    CEIT_COUNT_LAUNCH();
+  }
+  void rhs_scatter(int ln, const TreePlan&, const TreeLevel& lv, int64_t nU, const T* G, T* R) {
+    if (lv.rc_n == 0) return;
+    rhs_scatter_kernel<T><<<cdiv(lv.rc_n, 8), 256, 0, lane[ln]>>>(lv.rc_n, (int)nU, p->d_t_rc_dst + lv.rc0,
+                                                                  p->d_t_rc_ptr + lv.rc0, p->d_t_rc_src, G, R);
+    CEIT_COUNT_LAUNCH();
+  }
+  void rows_gather(int ln, const TreePlan&, const TreeLevel& lv, int64_t nU, const T* Xp, T* G) {
+    const int64_t rows = (int64_t)lv.n * lv.b;
+    bnd_rows_gather_kernel<T><<<cdiv(rows, 8), 256, 0, lane[ln]>>>(rows, (int)nU, p->d_t_bnd_row + lv.offR, Xp, G);
+    CEIT_COUNT_LAUNCH();
+  }
+};
+
 // ---- base stage -----------------------------------------------------------------------------------
 // K00 = K[F0,F0] in the ordering [interiors | separators]:
 //   level 1: the P mutually disconnected interiors (<= 64 nodes each) are factorised and eliminated as
@@ -455,13 +579,22 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(K0U, 0, N0P * nU * es, st));
   CUDA_TRY(cudaMemsetAsync(KUU, 0, nU * nU * es, st));
   CUDA_TRY(cudaMemsetAsync(p->d_info, 0, sizeof(int), st));
-  if (P > 0) {
+  if (P > 0 || h.use_tree) {
     CUDA_TRY(cudaMemsetAsync(Aint, 0, h.szPP * es, st));
     CUDA_TRY(cudaMemsetAsync(Lint, 0, h.szPP * es, st));
     CUDA_TRY(cudaMemsetAsync(LintInv, 0, h.szPP * es, st));
     CUDA_TRY(cudaMemsetAsync(Bt, 0, h.szV * es, st));
-    pad_identity_kernel<T><<<cdiv(P * nI, 256), 256, 0, st>>>((int)P, (int)nI, p->d_node_at, Aint);
-    CEIT_COUNT_LAUNCH();
+    if (h.use_tree) {
+      CUDA_TRY(cudaMemsetAsync(Tm, 0, h.tree.szC * es, st));
+      const int64_t npad = (int64_t)h.tree.pad_diag.size();
+      if (npad > 0) {
+        pad_diag_list_kernel<T><<<cdiv(npad, 256), 256, 0, st>>>(npad, p->d_t_pad, Aint);
+        CEIT_COUNT_LAUNCH();
+      }
+    } else {
+      pad_identity_kernel<T><<<cdiv(P * nI, 256), 256, 0, st>>>((int)P, (int)nI, p->d_node_at, Aint);
+      CEIT_COUNT_LAUNCH();
+    }
   }
   scatter_dense_kernel<T><<<cdiv(h.nnz, 256), 256, 0, st>>>((int)h.nnz, p->d_vals, p->d_slot_dst, p->d_slot_kind, Ad,
                                                             Bs, K0U, KUU, Aint, Bt);
@@ -476,6 +609,33 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   if (g_multi_stream) {
     if ((rc = ensure_aux_stream(p))) return rc;
     sr = p->s2;
+  }
+  if (h.use_tree) {
+    // ---- multi-level nested dissection (factor_tree.h): bottom-up, S_U -> T on its own stream, top-down ----------
+    const TreePlan& t = h.tree;
+    TreeBufs<T> m;
+    m.A = Aint; m.Lf = Lint; m.Linv = LintInv; m.Ainv = Ainv; m.Bt = Bt; m.W = Wn;
+    m.SigPP = Sel; m.V = Sel + t.szA; m.C = Tm; m.R = K0U; m.Xp = Xh; m.G = G1;
+    CudaTreeBK<T> bk{p, {st, sr}, tmpPanel};
+    tree_bottom_up<T>(t, nU, m, bk, one, zero, mone);
+    if (bk.rc) return bk.rc;
+    KERNEL_CHECK();
+    schur_u_gemm(p, sr, nU, N0P, K0U, Xh, SU);          // S_U = K_UU - r^T t over all levels (swept r, t = A^-1 r)
+    symmetrize_su(sr, nU, SU);
+    cudaStream_t s_t = sr;
+    if (g_multi_stream) {
+      s_t = p->s3;
+      CEIT_AFTER(sr, s_t);
+    }
+    if ((rc = base_shared_inverse<T>(p, s_t))) return rc;
+    CEIT_AFTER(sr, st);                                   // W of every level, A^-1
+    CUDA_TRY(cudaMemcpyAsync(Sel, Ainv, t.szA * es, cudaMemcpyDeviceToDevice, st));
+    tree_top_down<T>(t, nU, m, bk, one, zero, mone);
+    if (bk.rc) return bk.rc;
+    if ((rc = base_tail<T>(p, st, sr, s_t))) return rc;
+    KERNEL_CHECK();
+    p->mode = Sc<T>::is_complex ? 2 : 1;
+    return 0;
   }
   // ---- level 1: eliminate the interiors (batched) -----------------------------------------------------
   if (P > 0) {
@@ -587,21 +747,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
     s_t = p->s3;
     CEIT_AFTER(sr, s_t);
   }
-  if (use_rank_update(p)) {
-    // T, t_e = T e: shared by every excitation (Y_T = Xh T and y_e = Y_T e follow once X is complete)
-    T *Mreg = (T*)p->Mreg, *LT = (T*)p->LT, *LinvT = (T*)p->LinvT, *Tinv = (T*)p->Tinv, *te = (T*)p->te;
-    trace_gamma_kernel<T><<<1, 256, 0, s_t>>>((int)nU, SU, p->d_gamma);
-    CEIT_COUNT_LAUNCH();
-    add_rank1_e_kernel<T><<<cdiv(nU * nU, 256), 256, 0, s_t>>>((int)nU, SU, p->d_gamma, Mreg);
-    CEIT_COUNT_LAUNCH();
-    CUDA_TRY(cudaMemsetAsync(LT, 0, nU * nU * es, s_t));
-    CUDA_TRY(cudaMemsetAsync(LinvT, 0, nU * nU * es, s_t));
-    potrf_trtri_blocked<T>(s_t, nU, Mreg, nU, 0, LT, nU, 0, LinvT, nU, 0, (T*)p->tmpT, 0, 1, p->d_info,
-                           g_multi_stream ? &p->lane_b : nullptr);
-    gemm<T>(s_t, 1, 0, nU, nU, nU, one, LinvT, nU, 0, LinvT, nU, 0, zero, Tinv, nU, 0);
-    rowsum_e_kernel<T><<<cdiv(nU, 8), 256, 0, s_t>>>(nU, (int)nU, Tinv, te);
-    CEIT_COUNT_LAUNCH();
-  }
+  if ((rc = base_shared_inverse<T>(p, s_t))) return rc;
   // backward sweep and selected inverse, from the middle block outwards along both arms:
   //   X_k = Linv_k^T (Z_k - Lsub_k^T X_{k+1}) (k < m),  X_k = Linv_k^T (Z_k - Vsub_k X_{k-1}) (k > m)
   //   k < m: P = Lsub_k Linv_k,  So_k = -Sd_{k+1} P,      Sd_k = Linv_k^T Linv_k - P^T So_k
@@ -655,24 +801,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
     CUDA_TRY(cudaMemcpyAsync(SigPP, Ainv, h.szPP * es, cudaMemcpyDeviceToDevice, st));
     gemm<T>(st, 0, 1, nI, nI, bmax, mone, Vneg, bmax, sV, Wn, bmax, sV, one, SigPP, nI, sPP, (int)P);    // + V W^T
   }
-  gather_g0_kernel<T><<<cdiv(6 * h.E, 256), 256, 0, st>>>(6 * h.E, p->d_g0_off, Sel, g0e);
-  CEIT_COUNT_LAUNCH();
-  compact_rows_kernel<T><<<cdiv(h.N0, 8), 256, 0, sr>>>(h.N0, (int)nU, p->d_row_map, Xh, Xc);
-  CEIT_COUNT_LAUNCH();
-  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>((int)nU, Xc + h.N0 * nU);
-  CEIT_COUNT_LAUNCH();
-  if (use_rank_update(p)) {
-    T *Tinv = (T*)p->Tinv, *YT = (T*)p->YT, *ye = (T*)p->ye;
-    CEIT_AFTER(s_t, sr);
-    gemm<T>(sr, 0, 0, h.N, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);                 // Y_T = Xh T
-    rowsum_e_kernel<T><<<cdiv(h.N, 8), 256, 0, sr>>>(h.N, (int)nU, YT, ye);
-    CEIT_COUNT_LAUNCH();
-    CEIT_AFTER(sr, st);
-    launch_g1(p, g0e, YT, Xc, st);
-  } else {
-    CEIT_AFTER(s_t, sr);
-    CEIT_AFTER(sr, st);
-  }
+  if ((rc = base_tail<T>(p, st, sr, s_t))) return rc;
   KERNEL_CHECK();
   p->mode = Sc<T>::is_complex ? 2 : 1;
   return 0;
@@ -1001,7 +1130,8 @@ int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_
   if (!nodes || !elem || !el_ptr || !el_elems || !out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_create: null argument");
   ceit_plan* p = new ceit_plan();
   try {
-    build_host_plan(p->h, nodes, elem, N, E, el_ptr, el_elems, L, target_block, g_nd_interior);
+    build_host_plan(p->h, nodes, elem, N, E, el_ptr, el_elems, L, target_block, g_nd_interior,
+                    g_nd_tree != 0 && target_block <= 0);
     {
       // patches of <= 32 elements whose distinct node rows fit the shared-memory budget
       const bool lr = rank_update_shape_ok(p->h) && !g_direct_excitation && !g_no_lowrank;
@@ -1057,6 +1187,7 @@ int ceit_plan_info(const ceit_plan_t* p, int64_t* info) {
   info[13] = 0; info[14] = (int64_t)h.patch_eptr.size() - 1; info[15] = (int64_t)h.patch_nodes.size();
   info[16] = h.P; info[17] = h.nI; info[18] = h.bmax; info[19] = h.nC; info[20] = h.NP; info[21] = h.N0P;
   info[22] = h.patch_node_cap;
+  info[23] = h.use_tree ? h.tree.H : 0;
   if (p->uploaded && p->d_info) {
     int flag = 0;
     if (cudaMemcpy(&flag, p->d_info, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) info[13] = flag;
@@ -1366,6 +1497,10 @@ int ceit_set_option(const char* name, int64_t value) {
   }
   if (std::strcmp(name, "direct_excitation") == 0) {
     g_direct_excitation = (int)value;
+    return CEIT_OK;
+  }
+  if (std::strcmp(name, "nd_tree") == 0) {
+    g_nd_tree = (int)value;
     return CEIT_OK;
   }
   if (std::strcmp(name, "nd_interior") == 0) {

@@ -141,6 +141,86 @@ bnd_rows_gather_kernel(int64_t nrows, int nU, const int32_t* __restrict__ bnd_lo
   for (int k = lane; k < nU; k += 32) G1[r * nU + k] = (c < 0) ? Sc<T>::zero() : X_C[(int64_t)c * nU + k];
 }
 
+// ---- multi-level nested dissection (factor_tree.h) ------------------------------------------------------------------
+// identity on the diagonal of every padding slot of the own blocks (host list of A offsets)
+template <class T>
+__global__ void pad_diag_list_kernel(int64_t n, const int64_t* __restrict__ dst, T* __restrict__ A) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) A[dst[q]] = Sc<T>::one();
+}
+// Extend-add of one level: the update matrix U_f (b x b, lower triangle valid) of every front whose sibling index is
+// `pass` is added into its parent's own block A, coupling block Bt (own rows x boundary columns) and boundary block C
+// through the relative indices rel (index of the boundary node in the parent's front index space: [0, ps) own slots,
+// then boundary slots).  Siblings are separated by `pass` launches and rel is injective, so no two threads of a
+// launch touch the same entry: no atomics, bitwise reproducible.  blockIdx.y = front of the level.
+template <class T>
+__global__ void __launch_bounds__(256)
+extend_add_kernel(int b, int pass, const int32_t* __restrict__ sib, const int64_t* __restrict__ pA,
+                  const int64_t* __restrict__ pB, const int64_t* __restrict__ pC, const int32_t* __restrict__ ps,
+                  const int32_t* __restrict__ pb, const int32_t* __restrict__ rel, const T* __restrict__ U,
+                  T* __restrict__ A, T* __restrict__ Bt, T* __restrict__ C) {
+  const int f = blockIdx.y;
+  if (sib[f] != pass || pA[f] < 0) return;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= b * b) return;
+  const int a = q / b, c = q - a * b;
+  const int ra = rel[(int64_t)f * b + a], rc = rel[(int64_t)f * b + c];
+  if (ra < 0 || rc < 0) return;
+  const T* u = U + (int64_t)f * b * b;
+  const T v = (a >= c) ? u[(int64_t)a * b + c] : u[(int64_t)c * b + a];
+  const int s_ = ps[f], b_ = pb[f];
+  if (ra < s_) {
+    if (rc < s_) {
+      T* d = A + pA[f] + (int64_t)ra * s_ + rc;
+      *d = add(*d, v);
+    } else {
+      T* d = Bt + pB[f] + (int64_t)ra * b_ + (rc - s_);
+      *d = add(*d, v);
+    }
+  } else if (rc >= s_) {
+    T* d = C + pC[f] + (int64_t)(ra - s_) * b_ + (rc - s_);
+    *d = add(*d, v);
+  }
+}
+// The transpose of extend-add for the selected inverse: Sigma_bb(f)[a][c] = entry (rel a, rel c) of the parent's
+// selected inverse [[Sigma_own, V], [V^T, Sigma_bb(parent)]]; zero on padding / for roots.  Out = C block of f.
+template <class T>
+__global__ void __launch_bounds__(256)
+extend_gather_kernel(int b, const int64_t* __restrict__ pA, const int64_t* __restrict__ pB,
+                     const int64_t* __restrict__ pC, const int32_t* __restrict__ ps, const int32_t* __restrict__ pb,
+                     const int32_t* __restrict__ rel, const T* __restrict__ Sg, const T* __restrict__ V,
+                     const T* __restrict__ Call, T* __restrict__ out) {
+  const int f = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= b * b) return;
+  const int a = q / b, c = q - a * b;
+  const int ra = rel[(int64_t)f * b + a], rc = rel[(int64_t)f * b + c];
+  T v = Sc<T>::zero();
+  if (ra >= 0 && rc >= 0 && pA[f] >= 0) {
+    const int s_ = ps[f], b_ = pb[f];
+    if (ra < s_ && rc < s_) v = Sg[pA[f] + (int64_t)ra * s_ + rc];
+    else if (ra < s_) v = V[pB[f] + (int64_t)ra * b_ + (rc - s_)];
+    else if (rc < s_) v = V[pB[f] + (int64_t)rc * b_ + (ra - s_)];
+    else v = Call[pC[f] + (int64_t)(ra - s_) * b_ + (rc - s_)];
+  }
+  out[(int64_t)f * b * b + q] = v;
+}
+// R[dst[q], :] -= sum_s G[src[s], :] (destination-major lists: deterministic); one warp per destination row
+template <class T>
+__global__ void __launch_bounds__(256)
+rhs_scatter_kernel(int64_t nd, int nU, const int32_t* __restrict__ dst, const int32_t* __restrict__ ptr,
+                   const int32_t* __restrict__ src, const T* __restrict__ G, T* __restrict__ R) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= nd) return;
+  T* r = R + (int64_t)dst[q] * nU;
+  for (int k = lane; k < nU; k += 32) {
+    T acc = r[k];
+    for (int s = ptr[q]; s < ptr[q + 1]; ++s) acc = sub(acc, G[(int64_t)src[s] * nU + k]);
+    r[k] = acc;
+  }
+}
+
 // Xh[c,:] = XP[row_map[c],:]: drop the padding slots of the interiors (one warp per row)
 template <class T>
 __global__ void __launch_bounds__(256)

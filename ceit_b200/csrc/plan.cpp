@@ -41,11 +41,13 @@ void bfs_levels(const std::vector<int32_t>& rowptr, const std::vector<int32_t>& 
   }
 }
 
+void build_tree_plan(HostPlan& p, int64_t leaf_cap);
+
 }  // namespace
 
 void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
                      const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
-                     int64_t target_block, int64_t nd_interior) {
+                     int64_t target_block, int64_t nd_interior, bool nd_tree) {
   if (N <= 0 || E <= 0 || L <= 0) throw std::runtime_error("plan: N, E, L must be positive");
   if (N > (int64_t)2000000000 / 16 || E > (int64_t)2000000000 / 16)
     throw std::runtime_error("plan: mesh too large for 32-bit indices");
@@ -149,6 +151,30 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
       p.rowptr[v + 1] = (int32_t)p.colidx.size();
     }
     p.nnz = (int64_t)p.colidx.size();
+  }
+  // ---- gather lists for the deterministic assembly + dense destinations ----------------------
+  p.src_ptr.assign(p.nnz + 1, 0);
+  p.src.assign(9 * E, 0);
+  {
+    std::vector<int32_t> slot_of(9 * E);
+    for (int64_t e = 0; e < E; ++e)
+      for (int a = 0; a < 3; ++a) {
+        int32_t r = p.elem[3 * e + a];
+        for (int b = 0; b < 3; ++b) {
+          int32_t c2 = p.elem[3 * e + b];
+          auto it = std::lower_bound(p.colidx.begin() + p.rowptr[r], p.colidx.begin() + p.rowptr[r + 1], c2);
+          int32_t s = (int32_t)(it - p.colidx.begin());
+          slot_of[9 * e + 3 * a + b] = s;
+          p.src_ptr[s + 1]++;
+        }
+      }
+    for (int64_t s = 0; s < p.nnz; ++s) p.src_ptr[s + 1] += p.src_ptr[s];
+    std::vector<int32_t> fill(p.src_ptr.begin(), p.src_ptr.end() - 1);
+    for (int64_t q = 0; q < 9 * E; ++q) p.src[fill[slot_of[q]]++] = (int32_t)q;  // ascending element order
+  }
+  if (nd_tree && nd_interior > 0 && p.N0 > std::max<int64_t>(nd_interior, 8)) {
+    build_tree_plan(p, std::min<int64_t>(nd_interior, 64));
+    return;
   }
   // ---- level 1 (nested dissection): geometric boxes -> interiors I_p (<= 64 nodes, mutually
   // disconnected) and the separator set C.  A node goes to C when it has an F0 neighbour in a box with
@@ -393,26 +419,6 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
           p.sg_off[ip * p.bmax * p.bmax + a * p.bmax + b2] =
               pair_off(p.bnd_loc[ip * p.bmax + a], p.bnd_loc[ip * p.bmax + b2]);
   }
-  // ---- gather lists for the deterministic assembly + dense destinations ----------------------
-  p.src_ptr.assign(p.nnz + 1, 0);
-  p.src.assign(9 * E, 0);
-  {
-    std::vector<int32_t> slot_of(9 * E);
-    for (int64_t e = 0; e < E; ++e)
-      for (int a = 0; a < 3; ++a) {
-        int32_t r = p.elem[3 * e + a];
-        for (int b = 0; b < 3; ++b) {
-          int32_t c2 = p.elem[3 * e + b];
-          auto it = std::lower_bound(p.colidx.begin() + p.rowptr[r], p.colidx.begin() + p.rowptr[r + 1], c2);
-          int32_t s = (int32_t)(it - p.colidx.begin());
-          slot_of[9 * e + 3 * a + b] = s;
-          p.src_ptr[s + 1]++;
-        }
-      }
-    for (int64_t s = 0; s < p.nnz; ++s) p.src_ptr[s + 1] += p.src_ptr[s];
-    std::vector<int32_t> fill(p.src_ptr.begin(), p.src_ptr.end() - 1);
-    for (int64_t q = 0; q < 9 * E; ++q) p.src[fill[slot_of[q]]++] = (int32_t)q;  // ascending element order
-  }
   // node classes: 0 interior, 1 separator, 2 electrode
   auto cls = [&](int32_t v) { return p.u_of[v] >= 0 ? 2 : (interior_of[v] >= 0 ? 0 : 1); };
   p.slot_dst.assign(p.nnz, -1);
@@ -500,6 +506,339 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
     for (int a = 0; a < 3; ++a) p.elem_pos[3 * e + a] = p.pos[p.elem[3 * e + a]];
 }
 
+
+namespace {
+
+// ---- multi-level nested dissection (TreePlan) -------------------------------------------------------------------
+// Recursive coordinate bisection of the F0 graph: a sub-domain of more than leaf_cap nodes is cut across its longer
+// extent at the median coordinate (snapped to a coordinate value, so that a structured grid is cut along a grid
+// line); the separator is the set of nodes of the lower half that have a neighbour in the upper half, so the two
+// remaining halves are disconnected.  The reference has no ordering at all (dense inverse, CEIT/EFEM.py:111-119).
+struct TreeBuilder {
+  HostPlan& p;
+  int64_t leaf_cap;
+  std::vector<std::vector<int32_t>> own;       // per front (creation order)
+  std::vector<int32_t> parent;
+  std::vector<std::vector<int32_t>> children;
+  std::vector<int32_t> mark;                   // node -> stamp of the upper half it belongs to
+  int32_t stamp = 0;
+  TreeBuilder(HostPlan& p_, int64_t cap) : p(p_), leaf_cap(cap), mark(p_.N, -1) {}
+
+  int32_t new_front(std::vector<int32_t>&& nodes_) {
+    own.push_back(std::move(nodes_));
+    parent.push_back(-1);
+    children.emplace_back();
+    return (int32_t)own.size() - 1;
+  }
+  // returns the roots of the forest that covers `set`
+  std::vector<int32_t> dissect(std::vector<int32_t>& set) {
+    if (set.empty()) return {};
+    if ((int64_t)set.size() <= leaf_cap) {
+      std::sort(set.begin(), set.end());
+      return {new_front(std::move(set))};
+    }
+    double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+    for (int32_t v : set)
+      for (int d = 0; d < 2; ++d) {
+        lo[d] = std::min(lo[d], p.nodes[2 * v + d]);
+        hi[d] = std::max(hi[d], p.nodes[2 * v + d]);
+      }
+    const int ax = (hi[0] - lo[0] >= hi[1] - lo[1]) ? 0 : 1, ot = 1 - ax;
+    const double eps = 1e-9 * std::max(hi[ax] - lo[ax], 1e-300);
+    std::sort(set.begin(), set.end(), [&](int32_t a, int32_t b) {
+      const double ca = p.nodes[2 * a + ax], cb = p.nodes[2 * b + ax];
+      if (ca != cb) return ca < cb;
+      const double oa = p.nodes[2 * a + ot], ob = p.nodes[2 * b + ot];
+      if (oa != ob) return oa < ob;
+      return a < b;
+    });
+    size_t mid = set.size() / 2;
+    {
+      // snap the cut to a coordinate value: every node within eps of the median coordinate goes to the upper half
+      const double cm = p.nodes[2 * set[mid] + ax];
+      size_t first = mid, last = mid;
+      while (first > 0 && p.nodes[2 * set[first - 1] + ax] >= cm - eps) --first;
+      while (last < set.size() && p.nodes[2 * set[last] + ax] <= cm + eps) ++last;
+      if (first > 0) mid = first;
+      else if (last < set.size()) mid = last;
+      // else: every node has the same coordinate along ax (degenerate): keep the index split
+    }
+    const int32_t st = stamp++;
+    for (size_t k = mid; k < set.size(); ++k) mark[set[k]] = st;
+    std::vector<int32_t> sep, lower, upper(set.begin() + mid, set.end());
+    for (size_t k = 0; k < mid; ++k) {
+      const int32_t v = set[k];
+      bool cut = false;
+      for (int32_t q = p.rowptr[v]; q < p.rowptr[v + 1] && !cut; ++q) cut = (mark[p.colidx[q]] == st);
+      (cut ? sep : lower).push_back(v);
+    }
+    set.clear();
+    set.shrink_to_fit();
+    std::vector<int32_t> kids = dissect(lower);
+    {
+      std::vector<int32_t> k2 = dissect(upper);
+      kids.insert(kids.end(), k2.begin(), k2.end());
+    }
+    if (sep.empty()) return kids;                 // the halves were not connected: no front, the forest passes up
+    std::sort(sep.begin(), sep.end());
+    const int32_t f = new_front(std::move(sep));
+    for (int32_t c : kids) parent[c] = f;
+    children[f] = kids;
+    return {f};
+  }
+};
+
+void build_tree_plan(HostPlan& p, int64_t leaf_cap) {
+  const int64_t N = p.N, E = p.E;
+  TreeBuilder tb(p, leaf_cap);
+  {
+    std::vector<int32_t> all;
+    all.reserve(p.N0);
+    for (int64_t v = 0; v < N; ++v)
+      if (p.u_of[v] < 0) all.push_back((int32_t)v);
+    tb.dissect(all);
+  }
+  const int32_t nF = (int32_t)tb.own.size();
+  // heights -> levels; global front ids level by level (creation order inside a level)
+  std::vector<int32_t> height(nF, 0);
+  for (int32_t f = 0; f < nF; ++f)            // children are created before their parent
+    for (int32_t c : tb.children[f]) height[f] = std::max(height[f], height[c] + 1);
+  int32_t H = 0;
+  for (int32_t f = 0; f < nF; ++f) H = std::max(H, height[f] + 1);
+  std::vector<int32_t> gid(nF, -1), old_of(nF, -1);
+  TreePlan& t = p.tree;
+  t = TreePlan();
+  t.H = H;
+  t.nF = nF;
+  t.lv.assign(H, TreeLevel());
+  {
+    int32_t next = 0;
+    for (int32_t l = 0; l < H; ++l) {
+      t.lv[l].f0 = next;
+      for (int32_t f = 0; f < nF; ++f)
+        if (height[f] == l) {
+          gid[f] = next;
+          old_of[next] = f;
+          ++next;
+        }
+      t.lv[l].n = next - t.lv[l].f0;
+    }
+  }
+  // owner / slot of every F0 node, Euler intervals for ancestor tests
+  std::vector<int32_t> owner(N, -1), slot(N, -1), level_of(nF, 0);
+  for (int32_t g = 0; g < nF; ++g) {
+    const auto& o = tb.own[old_of[g]];
+    level_of[g] = height[old_of[g]];
+    for (size_t a = 0; a < o.size(); ++a) {
+      owner[o[a]] = g;
+      slot[o[a]] = (int32_t)a;
+    }
+  }
+  std::vector<int32_t> par(nF, -1);
+  for (int32_t g = 0; g < nF; ++g) par[g] = tb.parent[old_of[g]] < 0 ? -1 : gid[tb.parent[old_of[g]]];
+  auto is_proper_ancestor = [&](int32_t a, int32_t f) {     // a is a proper ancestor of f (levels strictly increase)
+    int32_t x = par[f];
+    while (x >= 0 && level_of[x] < level_of[a]) x = par[x];
+    return x == a;
+  };
+  // boundary lists bottom-up (sorted by node id)
+  std::vector<std::vector<int32_t>> bnd(nF);
+  for (int32_t g = 0; g < nF; ++g) {                        // level order: children before parents
+    auto& b = bnd[g];
+    for (int32_t v : tb.own[old_of[g]])
+      for (int32_t q = p.rowptr[v]; q < p.rowptr[v + 1]; ++q) {
+        const int32_t w = p.colidx[q];
+        if (p.u_of[w] >= 0 || owner[w] == g) continue;
+        if (level_of[owner[w]] > level_of[g]) {
+          if (!is_proper_ancestor(owner[w], g)) throw std::runtime_error("plan: sub-domains are not separated");
+          b.push_back(w);
+        }
+        // else: w belongs to a descendant, which lists v in its own boundary
+      }
+    for (int32_t c : tb.children[old_of[g]])
+      for (int32_t w : bnd[gid[c]])
+        if (owner[w] != g) b.push_back(w);
+    std::sort(b.begin(), b.end());
+    b.erase(std::unique(b.begin(), b.end()), b.end());
+    if (par[g] < 0 && !b.empty()) throw std::runtime_error("plan: a root front has a boundary");
+  }
+  // level sizes and offsets
+  p.N0P = 0;
+  for (int32_t l = 0; l < H; ++l) {
+    TreeLevel& lv = t.lv[l];
+    int32_t s = 0, b = 0;
+    for (int32_t k = 0; k < lv.n; ++k) {
+      s = std::max<int32_t>(s, (int32_t)tb.own[old_of[lv.f0 + k]].size());
+      b = std::max<int32_t>(b, (int32_t)bnd[lv.f0 + k].size());
+    }
+    lv.s = (s + 7) / 8 * 8;
+    lv.b = (b + 7) / 8 * 8;
+    lv.row0 = p.N0P;
+    lv.offA = t.szA;
+    lv.offB = t.szB;
+    lv.offC = t.szC;
+    lv.offR = (int64_t)t.rel.size();
+    p.N0P += (int64_t)lv.n * lv.s;
+    t.szA += (int64_t)lv.n * lv.s * lv.s;
+    t.szB += (int64_t)lv.n * lv.s * lv.b;
+    t.szC += (int64_t)lv.n * lv.b * lv.b;
+    t.maxG = std::max<int64_t>(t.maxG, (int64_t)lv.n * lv.b);
+    t.maxC = std::max<int64_t>(t.maxC, (int64_t)lv.n * lv.b * lv.b);
+    t.rel.resize(t.rel.size() + (size_t)lv.n * lv.b, -1);
+  }
+  if (p.N0P > (int64_t)2000000000) throw std::runtime_error("plan: padded row space exceeds 32-bit indices");
+  t.bnd_row.assign(t.rel.size(), -1);
+  // positions
+  p.P = p.nI = p.bmax = p.nC = p.NI = p.nb = p.max_block = p.n_levels = 0;
+  p.szD = p.szS = 0;
+  p.szPP = t.szA;
+  p.szV = t.szB;
+  p.NP = p.N0P + p.nU;
+  p.pos.assign(N, -1);
+  p.node_at.assign(p.NP, -1);
+  auto prow = [&](int32_t v) -> int64_t {
+    const int32_t g = owner[v];
+    const TreeLevel& lv = t.lv[level_of[g]];
+    return lv.row0 + (int64_t)(g - lv.f0) * lv.s + slot[v];
+  };
+  for (int64_t v = 0; v < N; ++v)
+    if (p.u_of[v] < 0) {
+      p.pos[v] = (int32_t)prow((int32_t)v);
+      p.node_at[p.pos[v]] = (int32_t)v;
+    }
+  for (int64_t u = 0; u < p.nU; ++u) {
+    p.pos[p.U[u]] = (int32_t)(p.N0P + u);
+    p.node_at[p.N0P + u] = p.U[u];
+  }
+  for (const TreeLevel& lv : t.lv)
+    for (int64_t f = 0; f < lv.n; ++f)
+      for (int64_t a = 0; a < lv.s; ++a)
+        if (p.node_at[lv.row0 + f * lv.s + a] < 0) t.pad_diag.push_back(lv.offA + f * lv.s * lv.s + a * lv.s + a);
+  auto bidx = [&](int32_t g, int32_t node) -> int64_t {
+    auto it = std::lower_bound(bnd[g].begin(), bnd[g].end(), node);
+    if (it == bnd[g].end() || *it != node) throw std::runtime_error("plan: node is not on the front's boundary");
+    return (int64_t)(it - bnd[g].begin());
+  };
+  auto blockA = [&](int32_t g) { const TreeLevel& lv = t.lv[level_of[g]]; return lv.offA + (int64_t)(g - lv.f0) * lv.s * lv.s; };
+  auto blockB = [&](int32_t g) { const TreeLevel& lv = t.lv[level_of[g]]; return lv.offB + (int64_t)(g - lv.f0) * lv.s * lv.b; };
+  auto blockC = [&](int32_t g) { const TreeLevel& lv = t.lv[level_of[g]]; return lv.offC + (int64_t)(g - lv.f0) * lv.b * lv.b; };
+  // per-front parent data, relative indices, boundary rows, sibling index
+  t.parent = par;
+  t.sib.assign(nF, 0);
+  t.pA.assign(nF, -1);
+  t.pB.assign(nF, -1);
+  t.pC.assign(nF, -1);
+  t.ps.assign(nF, 0);
+  t.pb.assign(nF, 0);
+  for (int32_t g = 0; g < nF; ++g) {
+    const auto& kids = tb.children[old_of[g]];
+    for (size_t k = 0; k < kids.size(); ++k) t.sib[gid[kids[k]]] = (int32_t)k;
+  }
+  for (int32_t l = 0; l < H; ++l) {
+    TreeLevel& lv = t.lv[l];
+    for (int32_t k = 0; k < lv.n; ++k) {
+      const int32_t g = lv.f0 + k, pg = par[g];
+      lv.passes = std::max(lv.passes, t.sib[g] + 1);
+      if (pg >= 0) {
+        const TreeLevel& pl = t.lv[level_of[pg]];
+        t.pA[g] = blockA(pg);
+        t.pB[g] = blockB(pg);
+        t.pC[g] = blockC(pg);
+        t.ps[g] = pl.s;
+        t.pb[g] = pl.b;
+      }
+      for (size_t a = 0; a < bnd[g].size(); ++a) {
+        const int32_t w = bnd[g][a];
+        const int64_t q = lv.offR + (int64_t)k * lv.b + (int64_t)a;
+        t.bnd_row[q] = p.pos[w];
+        t.rel[q] = (owner[w] == pg) ? slot[w] : (int32_t)(t.ps[g] + bidx(pg, w));
+      }
+    }
+  }
+  // right-hand-side scatter lists per level (destination-major, deterministic source order)
+  t.rc_ptr.assign(1, 0);
+  for (int32_t l = 0; l < H; ++l) {
+    TreeLevel& lv = t.lv[l];
+    std::vector<std::pair<int32_t, int32_t>> items;
+    for (int32_t k = 0; k < lv.n; ++k)
+      for (size_t a = 0; a < bnd[lv.f0 + k].size(); ++a)
+        items.emplace_back(p.pos[bnd[lv.f0 + k][a]], (int32_t)(k * lv.b + (int32_t)a));
+    std::sort(items.begin(), items.end());
+    lv.rc0 = (int64_t)t.rc_dst.size();
+    for (size_t q = 0; q < items.size(); ++q) {
+      if (q == 0 || items[q].first != items[q - 1].first) {
+        if (q) t.rc_ptr.push_back((int32_t)t.rc_src.size());
+        t.rc_dst.push_back(items[q].first);
+      }
+      t.rc_src.push_back(items[q].second);
+    }
+    if (!items.empty()) t.rc_ptr.push_back((int32_t)t.rc_src.size());
+    lv.rc_n = (int64_t)t.rc_dst.size() - lv.rc0;
+  }
+  // ---- CSR slot -> dense destination: kind 5 own block (A storage), 6 coupling (B storage, the row's owner is the
+  // descendant), 3 K0U, 4 KUU; the mirrored entry of a coupling pair is not stored -----------------------------------
+  p.slot_dst.assign(p.nnz, -1);
+  p.slot_kind.assign(p.nnz, 0);
+  for (int64_t r = 0; r < N; ++r)
+    for (int32_t s = p.rowptr[r]; s < p.rowptr[r + 1]; ++s) {
+      const int32_t c2 = p.colidx[s];
+      const bool ru = p.u_of[r] >= 0, cu = p.u_of[c2] >= 0;
+      if (!ru && !cu) {
+        const int32_t gr = owner[r], gc = owner[c2];
+        if (gr == gc) {
+          p.slot_kind[s] = 5;
+          p.slot_dst[s] = blockA(gr) + (int64_t)slot[r] * t.lv[level_of[gr]].s + slot[c2];
+        } else if (level_of[gr] < level_of[gc]) {
+          p.slot_kind[s] = 6;
+          p.slot_dst[s] = blockB(gr) + (int64_t)slot[r] * t.lv[level_of[gr]].b + bidx(gr, c2);
+        }
+      } else if (!ru && cu) {
+        p.slot_kind[s] = 3;
+        p.slot_dst[s] = (int64_t)p.pos[r] * p.nU + p.u_of[c2];
+      } else if (ru && cu) {
+        p.slot_kind[s] = 4;
+        p.slot_dst[s] = (int64_t)p.u_of[r] * p.nU + p.u_of[c2];
+      }
+    }
+  // ---- per-element gather offsets into the selected inverse [Sigma_own (A storage) | V (B storage)] ---------------
+  p.g0_off.assign(6 * E, -1);
+  static const int PA[6] = {0, 1, 2, 0, 1, 2}, PB[6] = {0, 1, 2, 1, 2, 0};
+  for (int64_t e = 0; e < E; ++e)
+    for (int q = 0; q < 6; ++q) {
+      const int32_t va = p.elem[3 * e + PA[q]], vb = p.elem[3 * e + PB[q]];
+      if (p.u_of[va] >= 0 || p.u_of[vb] >= 0) continue;
+      const int32_t ga = owner[va], gb = owner[vb];
+      if (ga == gb) p.g0_off[6 * e + q] = blockA(ga) + (int64_t)slot[va] * t.lv[level_of[ga]].s + slot[vb];
+      else if (level_of[ga] < level_of[gb])
+        p.g0_off[6 * e + q] = t.szA + blockB(ga) + (int64_t)slot[va] * t.lv[level_of[ga]].b + bidx(ga, vb);
+      else
+        p.g0_off[6 * e + q] = t.szA + blockB(gb) + (int64_t)slot[vb] * t.lv[level_of[gb]].b + bidx(gb, va);
+    }
+  // ---- compact position space (padding slots dropped) ----------------------------------------------------------------
+  p.ppos = p.pos;
+  p.row_map.assign(p.N0, -1);
+  {
+    int32_t q = 0;
+    for (int64_t r = 0; r < p.N0P; ++r)
+      if (p.node_at[r] >= 0) {
+        p.pos[p.node_at[r]] = q;
+        p.row_map[q] = (int32_t)r;
+        ++q;
+      }
+    if (q != p.N0) throw std::runtime_error("plan: position compaction lost nodes");
+    for (int64_t u = 0; u < p.nU; ++u) p.pos[p.U[u]] = (int32_t)(p.N0 + u);
+  }
+  p.elem_pos.resize(3 * E);
+  for (int64_t e = 0; e < E; ++e)
+    for (int a = 0; a < 3; ++a) p.elem_pos[3 * e + a] = p.pos[p.elem[3 * e + a]];
+  p.blk_ptr.assign(1, 0);
+  p.offD.assign(1, 0);
+  p.offS.assign(1, 0);
+  p.use_tree = true;
+  p.n_levels = H;
+}
+
+}  // namespace
 
 // Greedy clustering: grow a patch breadth-first over the element adjacency (elements sharing a node),
 // always taking a queued element if it fits the node cap; close the patch when nothing queued fits.

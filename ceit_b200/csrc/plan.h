@@ -7,7 +7,39 @@
 
 namespace ceit {
 
+// Multi-level nested dissection of F0 (the non-electrode nodes): an elimination FOREST of fronts.  A leaf front owns
+// the <= leaf_cap nodes of one final sub-domain, an internal front owns the vertex separator that split its
+// sub-domain.  bnd(f) = the nodes of proper ancestors that are adjacent to f's sub-domain once it is eliminated.
+// Fronts of equal height form a LEVEL and are processed as one batch (own / boundary sizes padded to the level's
+// maximum s / b).  Front index space of f: [0, s) own slots, [s, s + b) boundary slots.
+struct TreeLevel {
+  int32_t n = 0, s = 0, b = 0;       // fronts, padded own size, padded boundary size (b = 0: roots only)
+  int32_t passes = 0;                // 1 + largest sibling index (extend-add passes: siblings hit the same parent)
+  int32_t f0 = 0;                    // global id of the level's first front
+  int64_t row0 = 0;                  // first padded row (own slots of front k: row0 + k s ...)
+  int64_t offA = 0, offB = 0, offC = 0;   // element offsets of the level in the (n s s) / (n s b) / (n b b) storages
+  int64_t offR = 0;                  // offset of the level in rel / bnd_row (n b entries)
+  int64_t rc0 = 0, rc_n = 0;         // destinations of the level's right-hand-side scatter: rc_dst[rc0 .. rc0 + rc_n)
+};
+struct TreePlan {
+  int32_t H = 0;                     // levels, 0 = leaves
+  int64_t nF = 0, szA = 0, szB = 0, szC = 0, maxG = 0, maxC = 0;   // maxG = max n b, maxC = max n b b over levels
+  std::vector<TreeLevel> lv;
+  // per front (global id, level by level)
+  std::vector<int32_t> parent, sib;  // parent front (-1: root), index among the parent's children
+  std::vector<int64_t> pA, pB, pC;   // element offsets of the PARENT's own / coupling / boundary blocks
+  std::vector<int32_t> ps, pb;       // padded own / boundary size of the parent's level
+  // per (front, boundary slot), level by level with stride b of the level
+  std::vector<int32_t> rel;          // index in the parent's front index space (-1 padding)
+  std::vector<int32_t> bnd_row;      // padded row of the boundary node (-1 padding)
+  // right-hand-side scatter, destination-major: R[rc_dst[q], :] -= sum_s G[rc_src[s], :], s in rc_ptr[q .. q+1)
+  std::vector<int32_t> rc_dst, rc_ptr, rc_src;
+  std::vector<int64_t> pad_diag;     // A-storage offsets of the diagonal entries of the padding slots (set to 1)
+};
+
 struct HostPlan {
+  bool use_tree = false;
+  TreePlan tree;
   int64_t N = 0, E = 0, L = 0;
   int64_t nU = 0, N0 = 0, nb = 0, max_block = 0, nnz = 0, n_levels = 0;
   // nested dissection level 1: P interiors of <= nI nodes (padded to nI slots each), boundary lists of
@@ -64,6 +96,6 @@ void build_patches(HostPlan& p, int32_t node_cap, int32_t elem_cap);
 // Throws std::runtime_error on invalid input.
 void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
                      const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
-                     int64_t target_block, int64_t nd_interior);
+                     int64_t target_block, int64_t nd_interior, bool nd_tree = false);
 
 }  // namespace ceit

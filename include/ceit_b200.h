@@ -57,7 +57,7 @@ int ceit_plan_destroy(ceit_plan_t* plan);
  *              device bytes held, factor state (0 none,1 real,2 complex), numeric flag, n_patches,
  *              patch nodes, P (interiors), nI (slots per interior), bmax, nC (separator nodes),
  *              NP (position rows), N0P (position of the first electrode node), node cap of a Woodbury patch,
- *              reserved */
+ *              levels of the multi-level nested dissection (0: interiors + block-tridiagonal chain) */
 int ceit_plan_info(const ceit_plan_t* plan, int64_t* info24);
 /* Allocation generation of the plan: incremented whenever the numeric or per-excitation workspaces are
  * (re)allocated (first use, real <-> complex switch, larger excitation chunk).  A CUDA graph captured from calls on

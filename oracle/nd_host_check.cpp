@@ -1,0 +1,190 @@
+// TEST INFRASTRUCTURE (not part of the product; only tests/ build and call this).
+// Host backend for ceit_b200/csrc/factor_tree.h: runs the multi-level nested-dissection base stage of the
+// library - the SAME symbolic tables (plan.cpp) and the SAME level schedule (factor_tree.h) as the CUDA path - with
+// plain loops, so that X = K00^-1 K0U, S_U and the selected inverse on the mesh pattern can be compared with a dense
+// numpy inverse on the CPU.  The reference has no counterpart (it inverts the dense matrix, CEIT/EFEM.py:111-119).
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../ceit_b200/csrc/factor_tree.h"
+#include "../ceit_b200/csrc/plan.h"
+
+using namespace ceit;
+
+namespace {
+struct HostBK {
+  int bad_pivot = 0;
+  void after(int, int) {}
+  void gemm(int, int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+            int64_t sA, const double* B, int64_t ldb, int64_t sB, double beta, double* C, int64_t ldc, int64_t sC,
+            int batch, int lower_only) {
+    for (int z = 0; z < batch; ++z) {
+      const double *a = A + z * sA, *b = B + z * sB;
+      double* c = C + z * sC;
+      for (int64_t i = 0; i < M; ++i)
+        for (int64_t j = 0; j < N; ++j) {
+          if (lower_only && j > i) continue;      // entries above the diagonal are NOT produced (the GPU skips whole tiles)
+          double acc = 0.0;
+          for (int64_t q = 0; q < K; ++q)
+            acc += (opA ? a[q * lda + i] : a[i * lda + q]) * (opB ? b[j * ldb + q] : b[q * ldb + j]);
+          c[i * ldc + j] = alpha * acc + (beta == 0.0 ? 0.0 : beta * c[i * ldc + j]);
+        }
+    }
+  }
+  void potrf(int, int64_t n, double* A, double* L, double* Li, int batch) {
+    for (int z = 0; z < batch; ++z) {
+      double *a = A + z * n * n, *l = L + z * n * n, *x = Li + z * n * n;
+      for (int64_t j = 0; j < n; ++j) {                     // lower triangle of A only
+        double d = a[j * n + j];
+        for (int64_t q = 0; q < j; ++q) d -= l[j * n + q] * l[j * n + q];
+        if (!(d > 0.0)) bad_pivot = 1;
+        l[j * n + j] = std::sqrt(d);
+        for (int64_t i = j + 1; i < n; ++i) {
+          double v = a[i * n + j];
+          for (int64_t q = 0; q < j; ++q) v -= l[i * n + q] * l[j * n + q];
+          l[i * n + j] = v / l[j * n + j];
+        }
+      }
+      for (int64_t c = 0; c < n; ++c)                       // X = L^-1 by forward substitution
+        for (int64_t i = c; i < n; ++i) {
+          double v = (i == c) ? 1.0 : 0.0;
+          for (int64_t q = c; q < i; ++q) v -= l[i * n + q] * x[q * n + c];
+          x[i * n + c] = v / l[i * n + i];
+        }
+    }
+  }
+  void extend_add(int, const TreePlan& t, const TreeLevel& lv, int pass, const double* U, double* A, double* Bt,
+                  double* C) {
+    const int64_t b = lv.b;
+    for (int32_t f = 0; f < lv.n; ++f) {
+      const int32_t g = lv.f0 + f;
+      if (t.sib[g] != pass || t.parent[g] < 0) continue;
+      const int32_t* rel = t.rel.data() + lv.offR + (int64_t)f * b;
+      const double* u = U + (int64_t)f * b * b;
+      const int64_t ps = t.ps[g], pb = t.pb[g];
+      for (int64_t a = 0; a < b; ++a)
+        for (int64_t c = 0; c < b; ++c) {
+          const int64_t ra = rel[a], rc = rel[c];
+          if (ra < 0 || rc < 0) continue;
+          const double v = (a >= c) ? u[a * b + c] : u[c * b + a];
+          if (ra < ps) {
+            if (rc < ps) A[t.pA[g] + ra * ps + rc] += v;
+            else Bt[t.pB[g] + ra * pb + (rc - ps)] += v;
+          } else if (rc >= ps) {
+            C[t.pC[g] + (ra - ps) * pb + (rc - ps)] += v;
+          }
+        }
+    }
+  }
+  void extend_gather(int, const TreePlan& t, const TreeLevel& lv, const double* Sg, const double* V, double* C) {
+    const int64_t b = lv.b;
+    for (int32_t f = 0; f < lv.n; ++f) {
+      const int32_t g = lv.f0 + f;
+      const int32_t* rel = t.rel.data() + lv.offR + (int64_t)f * b;
+      double* out = C + lv.offC + (int64_t)f * b * b;
+      const int64_t ps = t.ps[g], pb = t.pb[g];
+      for (int64_t a = 0; a < b; ++a)
+        for (int64_t c = 0; c < b; ++c) {
+          const int64_t ra = rel[a], rc = rel[c];
+          double v = 0.0;
+          if (ra >= 0 && rc >= 0 && t.parent[g] >= 0) {
+            if (ra < ps && rc < ps) v = Sg[t.pA[g] + ra * ps + rc];
+            else if (ra < ps) v = V[t.pB[g] + ra * pb + (rc - ps)];
+            else if (rc < ps) v = V[t.pB[g] + rc * pb + (ra - ps)];
+            else v = C[t.pC[g] + (ra - ps) * pb + (rc - ps)];
+          }
+          out[a * b + c] = v;
+        }
+    }
+  }
+  void rhs_scatter(int, const TreePlan& t, const TreeLevel& lv, int64_t nU, const double* G, double* R) {
+    for (int64_t q = lv.rc0; q < lv.rc0 + lv.rc_n; ++q)
+      for (int64_t c = 0; c < nU; ++c) {
+        double acc = 0.0;
+        for (int32_t s = t.rc_ptr[q]; s < t.rc_ptr[q + 1]; ++s) acc += G[(int64_t)t.rc_src[s] * nU + c];
+        R[(int64_t)t.rc_dst[q] * nU + c] -= acc;
+      }
+  }
+  void rows_gather(int, const TreePlan& t, const TreeLevel& lv, int64_t nU, const double* Xp, double* G) {
+    for (int64_t r = 0; r < (int64_t)lv.n * lv.b; ++r) {
+      const int32_t src = t.bnd_row[lv.offR + r];
+      for (int64_t c = 0; c < nU; ++c) G[r * nU + c] = src < 0 ? 0.0 : Xp[(int64_t)src * nU + c];
+    }
+  }
+};
+thread_local std::string g_msg;
+}  // namespace
+
+extern "C" {
+
+const char* nd_host_last_error() { return g_msg.c_str(); }
+
+// K: dense symmetric N x N (row-major, the reference's doubled matrix or any SPD-on-F0 matrix with the mesh pattern).
+// Outputs (caller-allocated): info i64[8] = {nU, N0, H, nF, N0P, max s, max b, bad_pivot}; pos i64[N] (compact
+// positions), U i64[nU]; X f64[N0 * nU] (rows in compact position order) = K00^-1 K0U; SU f64[nU*nU];
+// g0 f64[6 E] selected-inverse entries of the element node pairs (0,0),(1,1),(2,2),(0,1),(1,2),(2,0) (0 if a node is
+// an electrode node).  Any output pointer may be NULL (info first to size the others).
+int nd_host_check(const double* nodes, const int64_t* elem, int64_t N, int64_t E, const int64_t* el_ptr,
+                  const int64_t* el_elems, int64_t L, int64_t leaf_cap, const double* K, int64_t* info, int64_t* pos,
+                  int64_t* U, double* X, double* SU, double* g0) {
+  try {
+    HostPlan h;
+    build_host_plan(h, nodes, elem, N, E, el_ptr, el_elems, L, 0, leaf_cap, /*nd_tree=*/true);
+    if (!h.use_tree) throw std::runtime_error("mesh too small for the tree plan");
+    const TreePlan& t = h.tree;
+    int64_t smax = 0, bmax = 0;
+    for (auto& lv : t.lv) { smax = std::max<int64_t>(smax, lv.s); bmax = std::max<int64_t>(bmax, lv.b); }
+    if (info) {
+      info[0] = h.nU; info[1] = h.N0; info[2] = t.H; info[3] = t.nF; info[4] = h.N0P; info[5] = smax; info[6] = bmax;
+      info[7] = 0;
+    }
+    if (pos) for (int64_t v = 0; v < N; ++v) pos[v] = h.pos[v];
+    if (U) for (int64_t u = 0; u < h.nU; ++u) U[u] = h.U[u];
+    if (!K || !X || !SU || !g0) return 0;
+    const int64_t nU = h.nU, N0P = h.N0P;
+    std::vector<double> A(t.szA, 0.0), Lf(t.szA, 0.0), Li(t.szA, 0.0), Ai(t.szA, 0.0), Bt(t.szB, 0.0), W(t.szB, 0.0);
+    std::vector<double> Sel(t.szA + t.szB, 0.0), C(t.szC, 0.0), R(N0P * nU, 0.0), Xp(N0P * nU, 0.0);
+    std::vector<double> G(std::max<int64_t>(t.maxG, 1) * nU, 0.0), KUU(nU * nU, 0.0);
+    // identity on the padding slots (pad_identity_kernel) and the CSR scatter (scatter_dense_kernel)
+    for (int64_t d : t.pad_diag) A[d] = 1.0;
+    for (int64_t r = 0; r < N; ++r)
+      for (int32_t s = h.rowptr[r]; s < h.rowptr[r + 1]; ++s) {
+        const double v = K[r * N + h.colidx[s]];
+        const int64_t d = h.slot_dst[s];
+        switch (h.slot_kind[s]) {
+          case 5: A[d] = v; break;
+          case 6: Bt[d] = v; break;
+          case 3: R[d] = v; break;
+          case 4: KUU[d] = v; break;
+          default: break;
+        }
+      }
+    TreeBufs<double> m;
+    m.A = A.data(); m.Lf = Lf.data(); m.Linv = Li.data(); m.Ainv = Ai.data(); m.Bt = Bt.data(); m.W = W.data();
+    m.SigPP = Sel.data(); m.V = Sel.data() + t.szA; m.C = C.data(); m.R = R.data(); m.Xp = Xp.data(); m.G = G.data();
+    HostBK bk;
+    tree_bottom_up<double>(t, nU, m, bk, 1.0, 0.0, -1.0);
+    // S_U = K_UU - r^T t (the swept right-hand sides against t = A^-1 r, all levels at once)
+    for (int64_t a = 0; a < nU; ++a)
+      for (int64_t b = 0; b < nU; ++b) {
+        double acc = 0.0;
+        for (int64_t r = 0; r < N0P; ++r) acc += R[r * nU + a] * Xp[r * nU + b];
+        SU[a * nU + b] = KUU[a * nU + b] - acc;
+      }
+    std::memcpy(Sel.data(), Ai.data(), sizeof(double) * t.szA);
+    tree_top_down<double>(t, nU, m, bk, 1.0, 0.0, -1.0);
+    for (int64_t q = 0; q < h.N0; ++q)
+      std::memcpy(X + q * nU, Xp.data() + (int64_t)h.row_map[q] * nU, sizeof(double) * nU);
+    for (int64_t q = 0; q < 6 * E; ++q) g0[q] = h.g0_off[q] < 0 ? 0.0 : Sel[h.g0_off[q]];
+    if (info) info[7] = bk.bad_pivot;
+    return 0;
+  } catch (const std::exception& e) {
+    g_msg = e.what();
+    return -1;
+  }
+}
+}

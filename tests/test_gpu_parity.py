@@ -105,7 +105,7 @@ def test_zgemm_matches_torch_complex128(torch_cuda, shape, tile):
         _lib.set_option("gemm_tile", 0)
 
 
-@pytest.mark.parametrize("target,nd", [(100, 40), (64, 0), (0, 64)])
+@pytest.mark.parametrize("target,nd", [(100, 40), (64, 0), (0, 64), (0, 16)])
 def test_step_is_bitwise_reproducible(torch_cuda, golden, target, nd):
     """The path has no atomics, so repeated steps must agree bit for bit; a difference is a race between the
     streams of the base stage (the two arms of the block chain once accumulated into the middle block from two
@@ -139,7 +139,7 @@ def test_step_is_bitwise_reproducible(torch_cuda, golden, target, nd):
 
 
 @pytest.mark.parametrize("tag", ["21_21", "50_50"])
-@pytest.mark.parametrize("target,nd", [(0, 64), (64, 0), (10 ** 6, 0), (0, 20), (100, 40)])
+@pytest.mark.parametrize("target,nd", [(0, 64), (64, 0), (10 ** 6, 0), (0, 20), (100, 40), (0, 9), (192, 64)])
 def test_cabi_pipeline_against_reference(torch_cuda, golden, tag, target, nd):
     """every ordering variant: nested-dissection interiors on/off x block-tridiagonal block size
     (target 10**6 with nd 0 = one dense block)"""
@@ -153,7 +153,8 @@ def test_cabi_pipeline_against_reference(torch_cuda, golden, tag, target, nd):
         p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"], target_block=target)
     finally:
         _lib.set_option("nd_interior", 64)
-    assert (p.P > 0) == (nd > 0)
+    assert (p.P > 0 or p.tree_levels > 0) == (nd > 0)
+    assert (p.tree_levels > 0) == (target == 0 and nd > 0)     # target 0 = default ordering: multi-level dissection
     perm = t.tensor(m["elem_perm"], device="cuda")
     var = t.zeros(E, dtype=t.float64, device="cuda")
     vals = t.zeros((p.nnz, 2), dtype=t.float64, device="cuda")

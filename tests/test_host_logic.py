@@ -44,7 +44,7 @@ def test_compute_entry_fails_loudly_without_plan_state():
 
 
 @pytest.mark.parametrize("tag", ["21_21", "50_50"])
-@pytest.mark.parametrize("target,nd", [(0, 40), (1, 40), (64, 0), (10 ** 6, 0), (0, 20)])
+@pytest.mark.parametrize("target,nd", [(0, 40), (1, 40), (64, 0), (10 ** 6, 0), (0, 20), (192, 20)])
 def test_plan_tables(golden, tag, target, nd):
     m, r = golden(tag)
     _lib.set_option("nd_interior", nd)
@@ -68,8 +68,16 @@ def test_plan_tables(golden, tag, target, nd):
                 expect_U.append(int(n))
     assert U.tolist() == expect_U
     assert np.array_equal(pos[U], p.N0P + np.arange(p.nU))
+    assert p.NP == p.N0P + p.nU
+    if target == 0 and nd > 0:
+        # default: multi-level nested dissection (the numerics of this plan are checked against a dense inverse in
+        # tests/test_nd_tree_host.py); here only the shape of the tables
+        assert p.tree_levels >= 3 and p.P == 0 and p.n_blocks == 0 and p.N0P >= p.N0
+        p.close()
+        return
+    assert p.tree_levels == 0
     NI = p.P * p.nI
-    assert p.N0P == NI + p.nC and p.NP == p.N0P + p.nU
+    assert p.N0P == NI + p.nC
     rows = np.repeat(np.arange(N), np.diff(tb["rowptr"]))
     pr, pc = pos[rows], pos[tb["colidx"]]
     # level 2: every edge between separator nodes joins the same or adjacent blocks

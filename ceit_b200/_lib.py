@@ -18,7 +18,7 @@ SYMBOLS = [
     "ceit_plan_info", "ceit_plan_tables", "ceit_plan_patches", "ceit_assemble", "ceit_factor", "ceit_jacobian_block",
     "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm", "ceit_plan_csr_values",
     "ceit_set_option", "ceit_stage_times", "ceit_gram_partial", "ceit_inverse_from_gram", "ceit_debug_tile_clocks", "ceit_zgemm",
-    "ceit_center_of_position", "ceit_plan_generation", "ceit_plan_numeric_flag",
+    "ceit_center_of_position", "ceit_plan_generation", "ceit_plan_numeric_flag", "ceit_stage_flops",
 ]
 
 
@@ -65,6 +65,7 @@ def lib():
     L.ceit_set_option.argtypes = [ctypes.c_char_p, c_i64]
     L.ceit_plan_csr_values.argtypes = [c_vp, c_vp, c_vp]
     L.ceit_stage_times.argtypes = [c_vp, c_vp]
+    L.ceit_stage_flops.argtypes = [c_vp]
     L.ceit_gram_partial.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_vp]
     L.ceit_inverse_from_gram.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp]
     L.ceit_plan_generation.argtypes = [c_vp]
@@ -104,6 +105,13 @@ def stage_times():
     cnt = np.zeros(8, dtype=np.int64)
     check(lib().ceit_stage_times(_np_ptr(ms), _np_ptr(cnt)))
     return {STAGES[k]: (float(ms[k]), int(cnt[k])) for k in range(8)}
+
+
+def stage_flops():
+    """{stage: algorithmic real flops of the dense work} since the last call (with stage timers on)."""
+    fl = np.zeros(8, dtype=np.float64)
+    check(lib().ceit_stage_flops(_np_ptr(fl)))
+    return {STAGES[k]: float(fl[k]) for k in range(8)}
 
 
 def launch_count():

@@ -20,6 +20,7 @@ namespace ceit {
 std::atomic<int64_t> g_launches{0};
 int g_force_simt = 0;
 int g_gemm_tile = 0;
+double g_flops = 0.0;
 int g_gemm_min_ctas64 = 300;   // measured (tools/stage_breakdown.py --opt gemm_min_ctas64=...): 120 -> 300 is 2 % at 50_50 / 200x200
 static thread_local std::string g_err;
 }  // namespace ceit
@@ -63,12 +64,15 @@ struct StageEv {
   cudaEvent_t a, b;
 };
 std::vector<StageEv> g_stage_events;
+double g_stage_flops[N_STAGES] = {0, 0, 0, 0, 0, 0, 0, 0};
 struct StageScope {
   int stage;
   cudaStream_t st;
   cudaEvent_t a = nullptr, b = nullptr;
+  double f0 = 0.0;
   StageScope(int s, cudaStream_t st_) : stage(s), st(st_) {
     if (!g_stage_timers) return;
+    f0 = ceit::g_flops;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
     cudaEventRecord(a, st);
@@ -77,6 +81,7 @@ struct StageScope {
     if (!a) return;
     cudaEventRecord(b, st);
     g_stage_events.push_back({stage, a, b});
+    g_stage_flops[stage] += ceit::g_flops - f0;
   }
 };
 
@@ -506,7 +511,7 @@ int base_tail(ceit_plan* p, cudaStream_t st, cudaStream_t sr, cudaStream_t s_t) 
 template <class T>
 struct CudaTreeBK {
   ceit_plan* p;
-  cudaStream_t lane[2];
+  cudaStream_t lane[3];
   T* panel;
   int rc = 0;
   void after(int from, int to) {
@@ -536,8 +541,8 @@ struct CudaTreeBK {
   }
   void rhs_scatter(int ln, const TreePlan&, const TreeLevel& lv, int64_t nU, const T* G, T* R) {
     if (lv.rc_n == 0) return;
-    rhs_scatter_kernel<T><<<cdiv(lv.rc_n, 8), 256, 0, lane[ln]>>>(lv.rc_n, (int)nU, p->d_t_rc_dst + lv.rc0,
-                                                                  p->d_t_rc_ptr + lv.rc0, p->d_t_rc_src, G, R);
+    rhs_scatter_kernel<T><<<dim3((unsigned)lv.rc_n, cdiv(nU, 128)), 128, 0, lane[ln]>>>(
+        lv.rc_n, (int)nU, p->d_t_rc_dst + lv.rc0, p->d_t_rc_ptr + lv.rc0, p->d_t_rc_src, G, R);
     CEIT_COUNT_LAUNCH();
   }
   void rows_gather(int ln, const TreePlan&, const TreeLevel& lv, int64_t nU, const T* Xp, T* G) {
@@ -616,8 +621,9 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
     TreeBufs<T> m;
     m.A = Aint; m.Lf = Lint; m.Linv = LintInv; m.Ainv = Ainv; m.Bt = Bt; m.W = Wn;
     m.SigPP = Sel; m.V = Sel + t.szA; m.C = Tm; m.R = K0U; m.Xp = Xh; m.G = G1;
-    CudaTreeBK<T> bk{p, {st, sr}, tmpPanel};
+    CudaTreeBK<T> bk{p, {st, sr, g_multi_stream ? p->s4 : sr}, tmpPanel};
     tree_bottom_up<T>(t, nU, m, bk, one, zero, mone);
+    bk.after(2, 1);                                       // W of every level: needed by both top-down chains
     if (bk.rc) return bk.rc;
     KERNEL_CHECK();
     schur_u_gemm(p, sr, nU, N0P, K0U, Xh, SU);          // S_U = K_UU - r^T t over all levels (swept r, t = A^-1 r)
@@ -1472,6 +1478,15 @@ int ceit_stage_times(double* ms, int64_t* counts) {
     cudaEventDestroy(e.b);
   }
   g_stage_events.clear();
+  return CEIT_OK;
+}
+
+int ceit_stage_flops(double* flops) {
+  if (!flops) CEIT_FAIL(CEIT_ERR_ARG, "ceit_stage_flops: null argument");
+  for (int k = 0; k < N_STAGES; ++k) {
+    flops[k] = g_stage_flops[k];
+    g_stage_flops[k] = 0.0;
+  }
   return CEIT_OK;
 }
 

@@ -328,6 +328,7 @@ inline void potrf_trtri_blocked(cudaStream_t st, int64_t n, T* A, int64_t lda, i
     potrf_trtri_tile_kernel<T><<<batch, 256, smem, st>>>((int)bt, A + o * lda + o, lda, sA, L + o * ldl + o, ldl, sL,
                                                          Linv + o * ldi + o, ldi, sI, info);
     CEIT_COUNT_LAUNCH();
+    g_flops += (Sc<T>::is_complex ? 4.0 : 1.0) * (2.0 / 3.0) * (double)bt * bt * bt * batch;
     if (lane && t >= 1) {
       lane->order(st, sl);          // tile t (Linv_tt) and the panels L[t, 0:t] of the earlier steps
       linv_row(t);

@@ -12,7 +12,8 @@
 //               right-hand sides: t_f = A_f^-1 r_f,  r[bnd(f)] -= Bt_f^T t_f;
 //   top-down    Sigma_bb(f) gathered from the parent's selected inverse;  V_f = -W_f Sigma_bb  (W = A^-1 Bt);
 //               Sigma_ff = A_f^-1 - V_f W_f^T;   x_f = t_f - W_f x[bnd(f)].
-// Lanes: 0 = matrix chain (caller's stream), 1 = right-hand-side chain.
+// Lanes: 0 = matrix chain (caller's stream), 1 = right-hand-side chain, 2 = W = A^-1 Bt (needed top-down only, so it is
+// kept off both bottom-up chains).
 #pragma once
 #include <cstdint>
 
@@ -50,7 +51,10 @@ void tree_bottom_up(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, 
     }
     // ---- right-hand-side chain ----
     k.gemm(1, 1, 0, s, s, s, one, Li, s, sA, Li, s, sA, zero, Ai, s, sA, (int)n, 0);           // A^-1 = Linv^T Linv
-    if (b > 0) k.gemm(1, 0, 0, s, b, s, one, Ai, s, sA, Bt, b, sB, zero, W, b, sB, (int)n, 0);  // W = A^-1 Bt
+    if (b > 0) {
+      k.after(1, 2);
+      k.gemm(2, 0, 0, s, b, s, one, Ai, s, sA, Bt, b, sB, zero, W, b, sB, (int)n, 0);          // W = A^-1 Bt
+    }
     k.gemm(1, 0, 0, s, nU, s, one, Ai, s, sA, R, nU, sX, zero, X, nU, sX, (int)n, 0);          // t = A^-1 r
     if (b > 0) {
       k.gemm(1, 1, 0, b, nU, s, one, Bt, b, sB, X, nU, sX, zero, m.G, nU, sG, (int)n, 0);      // Bt^T t
@@ -59,7 +63,7 @@ void tree_bottom_up(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, 
   }
 }
 
-// Requires SigPP == A^-1 (copied by the caller after the bottom-up pass) and lane 0 ordered after lane 1 (W).
+// Requires SigPP == A^-1 (copied by the caller after the bottom-up pass) and lanes 0 and 1 ordered after lane 2 (W).
 template <class T, class BK>
 void tree_top_down(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, T one, T zero, T mone) {
   for (int32_t l = t.H - 1; l >= 0; --l) {

@@ -15,6 +15,10 @@ extern std::atomic<int64_t> g_launches;
 extern int g_force_simt;
 extern int g_gemm_tile;
 extern int g_gemm_min_ctas64;   // 64x64 tiles when they give at least this many CTAs (else 32x32)
+// Algorithmic real flops of the dense work enqueued so far (host-side count, single caller thread): 2 M N K per
+// real product (8 M N K complex; half for a lower-only symmetric result), 2/3 n^3 per tile factorisation + inverse.
+// ceit_stage_flops() reports the per-stage differences next to the stage timers (roofline numerators).
+extern double g_flops;
 
 #define CEIT_COUNT_LAUNCH() (::ceit::g_launches.fetch_add(1, std::memory_order_relaxed))
 
@@ -474,6 +478,7 @@ inline void gemm<cd>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N, in
                      int64_t lda, int64_t sA, const cd* B, int64_t ldb, int64_t sB, cd beta, cd* C, int64_t ldc,
                      int64_t sC, int batch, int /*lower_only: full result for complex*/) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
+  g_flops += 8.0 * (double)M * (double)N * (double)K * batch;
   if (g_force_simt) {
     gemm_simt_launch<cd>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
     return;
@@ -519,6 +524,10 @@ inline void gemm_real_tiled(cudaStream_t st, int opA, int opB, int64_t M, int64_
                             const double* A, int64_t lda, int64_t sA, const double* B, int64_t ldb, int64_t sB,
                             double beta, double* C, int64_t ldc, int64_t sC, int batch, int flags, int cfg) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
+  {
+    const double k_total = (flags >> 1) ? (double)(batch - 1) * K + (double)(flags >> 1) : (double)batch * K;
+    g_flops += ((flags & 1) ? 1.0 : 2.0) * (double)M * (double)N * k_total;
+  }
   if (g_force_simt) {
     gemm_simt_launch<double>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch);
     return;

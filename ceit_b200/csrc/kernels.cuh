@@ -205,20 +205,20 @@ extend_gather_kernel(int b, const int64_t* __restrict__ pA, const int64_t* __res
   }
   out[(int64_t)f * b * b + q] = v;
 }
-// R[dst[q], :] -= sum_s G[src[s], :] (destination-major lists: deterministic); one warp per destination row
+// R[dst[q], :] -= sum_s G[src[s], :] (destination-major lists: deterministic); blockIdx.x = destination row,
+// blockIdx.y = chunk of 128 columns, one column per thread (all loads of a thread are independent)
 template <class T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 rhs_scatter_kernel(int64_t nd, int nU, const int32_t* __restrict__ dst, const int32_t* __restrict__ ptr,
                    const int32_t* __restrict__ src, const T* __restrict__ G, T* __restrict__ R) {
-  const int lane = threadIdx.x & 31;
-  const int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (q >= nd) return;
-  T* r = R + (int64_t)dst[q] * nU;
-  for (int k = lane; k < nU; k += 32) {
-    T acc = r[k];
-    for (int s = ptr[q]; s < ptr[q + 1]; ++s) acc = sub(acc, G[(int64_t)src[s] * nU + k]);
-    r[k] = acc;
-  }
+  const int64_t q = blockIdx.x;
+  const int k = blockIdx.y * 128 + threadIdx.x;
+  if (q >= nd || k >= nU) return;
+  T* r = R + (int64_t)dst[q] * nU + k;
+  const int s0 = ptr[q], s1 = ptr[q + 1];
+  T acc = *r;
+  for (int s = s0; s < s1; ++s) acc = sub(acc, G[(int64_t)src[s] * nU + k]);
+  *r = acc;
 }
 
 // Xh[c,:] = XP[row_map[c],:]: drop the padding slots of the interiors (one warp per row)

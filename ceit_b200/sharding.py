@@ -66,3 +66,83 @@ def gather_jacobian(J_local, L, E, group=None):
     dist.all_reduce(mask, op=dist.ReduceOp.SUM, group=group)
     J_local.copy_(mask)
     return J_local
+
+
+class ShardedStep:
+    """The exchange half of a multi-GPU step (one process per GPU, NCCL through torch.distributed).
+
+    After the local part (each rank's excitation rows of J), the inverse model needs, per rank, ALL rows of J at
+    that rank's slice of the detection elements, and the reference contract wants J replicated.  Two collectives:
+
+      * critical path - an ALL-TO-ALL of the row block restricted to each peer's detection columns: 1/ws of the
+        volume of an all-gather; it lands directly in the rows of the compact matrix J_r (m x n_det_local), from
+        which the rank forms its partial Gram matrix (one all-reduce of m x m doubles) and its rows of inv_mat;
+      * off the critical path - the replication of J as an IN-PLACE all-gather of the row blocks (no staging copies)
+        on a second communicator, so it overlaps the Gram / Cholesky / inverse-model GEMMs; `finish()` joins it.
+
+    Falls back to `gather_jacobian` + the replicated-J form when the shards are not equal row blocks (ws does not
+    divide L, or ws > L: element-range shards).
+    """
+
+    def __init__(self, L, E, det, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.group = group
+        self.ws = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.L, self.E, self.m = L, E, L * (L - 1)
+        self.shards = all_shards(L, E, self.ws)
+        self.equal_rows = self.ws <= L and L % self.ws == 0
+        n_det = det.numel()
+        self.bounds = [(n_det * r) // self.ws for r in range(self.ws + 1)]
+        self.det = det
+        self.det_slices = [det[self.bounds[q]:self.bounds[q + 1]].contiguous() for q in range(self.ws)]
+        self.det_local = self.det_slices[self.rank]
+        self.nd_local = self.det_local.numel()
+        self._work = None
+        self.nccl = dist.get_backend(group) == "nccl"
+        if self.equal_rows:
+            # second communicator: the replication all-gather must not queue in front of the Gram all-reduce
+            self.repl_group = dist.new_group(ranks=list(range(self.ws)), backend="nccl") if self.nccl else None
+            self.J_r = torch.empty((self.m, max(self.nd_local, 1)), dtype=torch.float64, device=det.device)
+            self.cols_local = torch.arange(self.nd_local, dtype=torch.int64, device=det.device)
+            rows = self.m // self.ws
+            self.recv = [self.J_r[p * rows:(p + 1) * rows] for p in range(self.ws)]
+            self.send = [torch.empty((rows, self.det_slices[q].numel()), dtype=torch.float64, device=det.device)
+                         for q in range(self.ws)]
+            self.nvlink_bytes_per_step = 8 * rows * (n_det - self.nd_local) + 8 * rows * E * (self.ws - 1)
+
+    def exchange(self, J):
+        """Start both collectives; returns the matrix / index pair to feed the sharded inverse model with."""
+        torch, dist = self.torch, self.dist
+        if not self.equal_rows:
+            gather_jacobian(J, self.L, self.E, self.group)
+            return J, self.det_local
+        rows = self.m // self.ws
+        r0 = self.rank * rows
+        mine = J[r0:r0 + rows]
+        for q in range(self.ws):
+            torch.index_select(mine, 1, self.det_slices[q], out=self.send[q])
+        if self.nccl:
+            dist.all_to_all(self.recv, self.send, group=self.group)
+            self._work = dist.all_gather_into_tensor(J, mine, group=self.repl_group, async_op=True)
+        else:
+            # gloo (CPU tests of the host logic): no all_to_all, no in-place all-gather
+            reqs = []
+            for q in range(self.ws):
+                if q == self.rank:
+                    self.recv[q].copy_(self.send[q])
+                else:
+                    reqs.append(dist.isend(self.send[q], q, group=self.group))
+                    reqs.append(dist.irecv(self.recv[q], q, group=self.group))
+            for r in reqs:
+                r.wait()
+            dist.all_gather_into_tensor(J, mine.clone(), group=self.group)
+        return self.J_r, self.cols_local
+
+    def finish(self):
+        """Join the replication of J (the current stream waits for the all-gather)."""
+        if self._work is not None:
+            self._work.wait()
+            self._work = None

@@ -188,6 +188,11 @@ int ceit_zgemm(int opA, int opB, int64_t M, int64_t N, int64_t K, double alpha_r
  * factorisation, 2 per-excitation stage, 3 Woodbury kernel, 4 inverse model, 5 reconstruct.
  * Synchronises on the recorded events. */
 int ceit_stage_times(double* ms, int64_t* counts);
+/* algorithmic real flops of the dense work (DMMA GEMMs: 2 M N K, half for lower-only symmetric results, 8 M N K
+ * complex; tile factorisation + triangular inverse: 2/3 n^3) enqueued inside each stage's timed regions since the last
+ * call (same stage indices, same switch as ceit_stage_times): the numerator of the per-stage FP64 roofline.
+ * flops f64[8].  Host-side count, no device access. */
+int ceit_stage_flops(double* flops);
 
 /* debug: clock64 phase stamps of the last tile-factorisation CTA (only with -DCEIT_TILE_CLOCKS) */
 int ceit_debug_tile_clocks(int64_t* out8);

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from ceit_b200.sharding import gather_jacobian, shard_ranges
+from ceit_b200.sharding import ShardedStep, gather_jacobian, shard_ranges
 
 
 def _free_port():
@@ -44,3 +44,39 @@ def test_gather_jacobian_gloo(ws, L, E):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res)
+
+
+def _worker_step(rank, ws, port, L, E, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    m = L * (L - 1)
+    full = torch.arange(m * E, dtype=torch.float64).reshape(m, E) * 0.25 + 1.0
+    det = torch.tensor([e for e in range(E) if e % 3 != 1], dtype=torch.int64)
+    i0, i1, e0, e1 = shard_ranges(L, E, ws, rank)
+    J = torch.zeros_like(full)
+    J[i0 * (L - 1): i1 * (L - 1), e0:e1] = full[i0 * (L - 1): i1 * (L - 1), e0:e1]
+    step = ShardedStep(L, E, det)
+    Jr, cols = step.exchange(J)
+    step.finish()
+    lo, hi = step.bounds[rank], step.bounds[rank + 1]
+    ok = bool(torch.equal(J, full))                                       # J replicated
+    ok &= bool(torch.equal(Jr.index_select(1, cols), full[:, det[lo:hi]]))  # all rows at this rank's detection slice
+    ok &= sum(step.bounds[r + 1] - step.bounds[r] for r in range(ws)) == det.numel()
+    q.put((rank, ok, step.equal_rows))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ws,L,E,equal", [(2, 4, 37, True), (3, 6, 20, True), (3, 4, 20, False), (3, 2, 11, False)])
+def test_sharded_step_exchange_gloo(ws, L, E, equal):
+    """all-to-all of the detection-column slices + replication of J (equal row blocks), and the gather fallback"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_step, args=(r, ws, port, L, E, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res) and all(eq == equal for _, _, eq in res)

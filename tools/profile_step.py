@@ -1,4 +1,4 @@
-"""One warm step + N profiled steps of the MESH_50_50 hot path (for ncu launch lists)."""
+"""One warm step + N profiled steps of the hot path (for ncu launch lists): tools/profile_step.py [50_50|21_21|200|400] [steps]"""
 import sys, os
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -7,7 +7,7 @@ from ceit_b200 import _lib
 import bench
 tag = sys.argv[1] if len(sys.argv) > 1 else "50_50"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-mesh = bench.load_mesh(tag)
+mesh = bench.load_workload(tag) if tag in bench.CONFIGS else bench.load_mesh(tag)
 N, E, L = len(mesh["nodes"]), len(mesh["elem"]), len(mesh["electrodes"])
 omega = 2 * np.pi * 2e4
 plan = _lib.Plan(mesh["nodes"], mesh["elem"], mesh["electrodes"])

@@ -21,6 +21,7 @@ std::atomic<int64_t> g_launches{0};
 int g_force_simt = 0;
 int g_gemm_tile = 0;
 double g_flops = 0.0;
+int g_gemm_vec = 1;
 int g_gemm_min_ctas64 = 300;   // measured (tools/stage_breakdown.py --opt gemm_min_ctas64=...): 120 -> 300 is 2 % at 50_50 / 200x200
 static thread_local std::string g_err;
 }  // namespace ceit
@@ -581,7 +582,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(Bs, 0, h.szS * es, st));
   CUDA_TRY(cudaMemsetAsync(Ld, 0, h.szD * es, st));
   CUDA_TRY(cudaMemsetAsync(Linv, 0, h.szD * es, st));
-  CUDA_TRY(cudaMemsetAsync(K0U, 0, N0P * nU * es, st));
+  CUDA_TRY(cudaMemsetAsync(K0U, 0, (h.use_tree ? h.tree.rowsA : N0P) * nU * es, st));
   CUDA_TRY(cudaMemsetAsync(KUU, 0, nU * nU * es, st));
   CUDA_TRY(cudaMemsetAsync(p->d_info, 0, sizeof(int), st));
   if (P > 0 || h.use_tree) {
@@ -626,7 +627,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
     bk.after(2, 1);                                       // W of every level: needed by both top-down chains
     if (bk.rc) return bk.rc;
     KERNEL_CHECK();
-    schur_u_gemm(p, sr, nU, N0P, K0U, Xh, SU);          // S_U = K_UU - r^T t over all levels (swept r, t = A^-1 r)
+    schur_u_gemm(p, sr, nU, t.rowsA, K0U, Xh, SU);      // S_U = K_UU - r^T t over the active rows of all levels
     symmetrize_su(sr, nU, SU);
     cudaStream_t s_t = sr;
     if (g_multi_stream) {
@@ -1541,6 +1542,10 @@ int ceit_set_option(const char* name, int64_t value) {
   }
   if (std::strcmp(name, "no_patch_kernel") == 0) {
     g_no_patch = (int)value;
+    return CEIT_OK;
+  }
+  if (std::strcmp(name, "gemm_vec") == 0) {
+    ceit::g_gemm_vec = (int)value;
     return CEIT_OK;
   }
   if (std::strcmp(name, "gemm_tile") == 0) {

@@ -9,7 +9,8 @@
 // Per front f (own block A_f: s x s, coupling Bt_f: s x b = own rows x boundary columns, boundary block C_f: b x b):
 //   bottom-up   A_f = L L^T, Linv;  Y = Linv Bt;  U_f = C_f - Y^T Y  (update matrix, lower triangle valid);
 //               extend-add U_f into the parent's (A, Bt, C) through the relative indices `rel`;
-//               right-hand sides: t_f = A_f^-1 r_f,  r[bnd(f)] -= Bt_f^T t_f;
+//               right-hand sides: t_f = A_f^-1 r_f,  r[bnd(f)] -= Bt_f^T t_f - only for the ACTIVE fronts (K_0U is zero
+//               away from the electrodes, so most leaves have r = 0, t = 0; their rows sit after row rowsA);
 //   top-down    Sigma_bb(f) gathered from the parent's selected inverse;  V_f = -W_f Sigma_bb  (W = A^-1 Bt);
 //               Sigma_ff = A_f^-1 - V_f W_f^T;   x_f = t_f - W_f x[bnd(f)].
 // Lanes: 0 = matrix chain (caller's stream), 1 = right-hand-side chain, 2 = W = A^-1 Bt (needed top-down only, so it is
@@ -40,7 +41,8 @@ void tree_bottom_up(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, 
     const int64_t sA = s * s, sB = s * b, sC = b * b, sX = s * nU, sG = b * nU;
     T *A = m.A + lv.offA, *Lf = m.Lf + lv.offA, *Li = m.Linv + lv.offA, *Ai = m.Ainv + lv.offA;
     T *Bt = m.Bt + lv.offB, *W = m.W + lv.offB, *Y = m.V + lv.offB, *C = m.C + lv.offC;
-    T *R = m.R + lv.row0 * nU, *X = m.Xp + lv.row0 * nU;
+    T *R = m.R + lv.row0 * nU, *X = m.Xp + lv.row0 * nU;      // rows of the ACTIVE fronts (non-zero right-hand side)
+    const int na = lv.na;
     // ---- matrix chain ----
     k.potrf(0, s, A, Lf, Li, (int)n);
     k.after(0, 1);
@@ -55,10 +57,12 @@ void tree_bottom_up(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, 
       k.after(1, 2);
       k.gemm(2, 0, 0, s, b, s, one, Ai, s, sA, Bt, b, sB, zero, W, b, sB, (int)n, 0);          // W = A^-1 Bt
     }
-    k.gemm(1, 0, 0, s, nU, s, one, Ai, s, sA, R, nU, sX, zero, X, nU, sX, (int)n, 0);          // t = A^-1 r
-    if (b > 0) {
-      k.gemm(1, 1, 0, b, nU, s, one, Bt, b, sB, X, nU, sX, zero, m.G, nU, sG, (int)n, 0);      // Bt^T t
-      k.rhs_scatter(1, t, lv, nU, m.G, m.R);
+    if (na > 0) {
+      k.gemm(1, 0, 0, s, nU, s, one, Ai, s, sA, R, nU, sX, zero, X, nU, sX, na, 0);            // t = A^-1 r
+      if (b > 0) {
+        k.gemm(1, 1, 0, b, nU, s, one, Bt, b, sB, X, nU, sX, zero, m.G, nU, sG, na, 0);        // Bt^T t
+        k.rhs_scatter(1, t, lv, nU, m.G, m.R);
+      }
     }
   }
 }
@@ -72,14 +76,18 @@ void tree_top_down(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, T
     if (n == 0 || s == 0 || b == 0) continue;
     const int64_t sA = s * s, sB = s * b, sC = b * b, sX = s * nU, sG = b * nU;
     T *W = m.W + lv.offB, *V = m.V + lv.offB, *C = m.C + lv.offC, *Sg = m.SigPP + lv.offA;
-    T* X = m.Xp + lv.row0 * nU;
+    T *X = m.Xp + lv.row0 * nU, *Xi = m.Xp + lv.row0i * nU;
+    const int na = lv.na, ni = (int)n - lv.na;
     // ---- selected inverse ----
     k.extend_gather(0, t, lv, m.SigPP, m.V, m.C);                                               // C_f = Sigma_bb(f)
     k.gemm(0, 0, 0, s, b, b, mone, W, b, sB, C, b, sC, zero, V, b, sB, (int)n, 0);              // V = -W Sigma_bb
     k.gemm(0, 0, 1, s, s, b, mone, V, b, sB, W, b, sB, one, Sg, s, sA, (int)n, 0);              // Sigma_ff = A^-1 - V W^T
     // ---- solution ----
     k.rows_gather(1, t, lv, nU, m.Xp, m.G);
-    k.gemm(1, 0, 0, s, nU, b, mone, W, b, sB, m.G, nU, sG, one, X, nU, sX, (int)n, 0);          // x = t - W x_bnd
+    if (na > 0) k.gemm(1, 0, 0, s, nU, b, mone, W, b, sB, m.G, nU, sG, one, X, nU, sX, na, 0);  // x = t - W x_bnd
+    if (ni > 0)                                                                                 // t = 0: x = -W x_bnd
+      k.gemm(1, 0, 0, s, nU, b, mone, W + (int64_t)na * sB, b, sB, m.G + (int64_t)na * sG, nU, sG, zero, Xi, nU, sX, ni,
+             0);
   }
 }
 

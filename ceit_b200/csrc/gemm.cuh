@@ -19,6 +19,7 @@ extern int g_gemm_min_ctas64;   // 64x64 tiles when they give at least this many
 // real product (8 M N K complex; half for a lower-only symmetric result), 2/3 n^3 per tile factorisation + inverse.
 // ceit_stage_flops() reports the per-stage differences next to the stage timers (roofline numerators).
 extern double g_flops;
+extern int g_gemm_vec;   // 1 (default): 16-byte cp.async staging where the operand layout allows it
 
 #define CEIT_COUNT_LAUNCH() (::ceit::g_launches.fetch_add(1, std::memory_order_relaxed))
 
@@ -39,6 +40,11 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, 
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   const int sz = valid ? 8 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+// 16-byte copy of which the first `bytes` (0, 8 or 16) come from global memory, the rest is zero-filled
+__device__ __forceinline__ void cp_async16_partial(double* smem_dst, const double* gsrc, int bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes));
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -72,8 +78,11 @@ template <int BM, int BN, int WM, int WN, int OPA, int OPB, int STAGES>
 __global__ void __launch_bounds__(WM * WN * 32)
 gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int64_t lda,
                  int64_t sA, const double* __restrict__ B, int64_t ldb, int64_t sB, double beta,
-                 double* __restrict__ C, int64_t ldc, int64_t sC, int flags) {
+                 double* __restrict__ C, int64_t ldc, int64_t sC, int flags, int vec) {
   using SM = DmmaSmem<BM, BN, OPA, OPB>;
+  // vec: bit 0 / bit 1 = the A / B operand is staged with 16-byte cp.async (two doubles along its contiguous
+  // dimension; needs a 16-byte aligned base, an even leading dimension and an even batch stride - decided by the
+  // host launcher); an 8-byte LDGSTS occupies the LSU as long as a 16-byte one, so this halves the staging issue
   // flags: bit 0 = lower_only; bits 1.. = inner dimension of the LAST batch entry (0 = K), so that the short last
   // slice of a split-K product runs in the same launch as the full ones
   if ((flags >> 1) != 0 && blockIdx.z == gridDim.z - 1) K = flags >> 1;
@@ -103,37 +112,77 @@ gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A
     double* As = dsm + buf * SM::STAGE;
     double* Bs = As + SM::A_ELEMS;
     const int k0 = kt * BK;
+    if (vec & 1) {
 #pragma unroll
-    for (int r = 0; r < (BM * BK) / NT; ++r) {
-      const int idx = tid + r * NT;
-      int m, k;
-      if (OPA == 0) {
-        k = idx & 15;
-        m = idx >> 4;
-      } else {
-        m = idx % BM;
-        k = idx / BM;
+      for (int r = 0; r < (BM * BK / 2) / NT; ++r) {
+        const int idx = tid + r * NT;
+        int m, k;                                   // first element of the pair along the contiguous dimension
+        if (OPA == 0) {
+          k = (idx & 7) * 2;
+          m = idx >> 3;
+        } else {
+          m = (idx % (BM / 2)) * 2;
+          k = idx / (BM / 2);
+        }
+        const int gm = m0 + m, gk = k0 + k;
+        int cnt = 0;                                // valid elements of the pair
+        if (gm < M && gk < K) cnt = (OPA == 0) ? (gk + 1 < K ? 2 : 1) : (gm + 1 < M ? 2 : 1);
+        const double* src = cnt ? ((OPA == 0) ? A + (int64_t)gm * lda + gk : A + (int64_t)gk * lda + gm) : A;
+        cp_async16_partial(As + ((OPA == 0) ? m * SA + k : k * SA + m), src, 8 * cnt);
       }
-      const int gm = m0 + m, gk = k0 + k;
-      const bool ok = (gm < M) && (gk < K);
-      const double* src = ok ? ((OPA == 0) ? A + (int64_t)gm * lda + gk : A + (int64_t)gk * lda + gm) : A;
-      cp_async8(As + ((OPA == 0) ? m * SA + k : k * SA + m), src, ok);
+    } else {
+#pragma unroll
+      for (int r = 0; r < (BM * BK) / NT; ++r) {
+        const int idx = tid + r * NT;
+        int m, k;
+        if (OPA == 0) {
+          k = idx & 15;
+          m = idx >> 4;
+        } else {
+          m = idx % BM;
+          k = idx / BM;
+        }
+        const int gm = m0 + m, gk = k0 + k;
+        const bool ok = (gm < M) && (gk < K);
+        const double* src = ok ? ((OPA == 0) ? A + (int64_t)gm * lda + gk : A + (int64_t)gk * lda + gm) : A;
+        cp_async8(As + ((OPA == 0) ? m * SA + k : k * SA + m), src, ok);
+      }
     }
+    if (vec & 2) {
 #pragma unroll
-    for (int r = 0; r < (BN * BK) / NT; ++r) {
-      const int idx = tid + r * NT;
-      int n, k;
-      if (OPB == 0) {
-        n = idx % BN;
-        k = idx / BN;
-      } else {
-        k = idx & 15;
-        n = idx >> 4;
+      for (int r = 0; r < (BN * BK / 2) / NT; ++r) {
+        const int idx = tid + r * NT;
+        int n, k;
+        if (OPB == 0) {
+          n = (idx % (BN / 2)) * 2;
+          k = idx / (BN / 2);
+        } else {
+          k = (idx & 7) * 2;
+          n = idx >> 3;
+        }
+        const int gn = n0 + n, gk = k0 + k;
+        int cnt = 0;
+        if (gn < N && gk < K) cnt = (OPB == 0) ? (gn + 1 < N ? 2 : 1) : (gk + 1 < K ? 2 : 1);
+        const double* src = cnt ? ((OPB == 0) ? B + (int64_t)gk * ldb + gn : B + (int64_t)gn * ldb + gk) : B;
+        cp_async16_partial(Bs + ((OPB == 0) ? k * SB + n : n * SB + k), src, 8 * cnt);
       }
-      const int gn = n0 + n, gk = k0 + k;
-      const bool ok = (gn < N) && (gk < K);
-      const double* src = ok ? ((OPB == 0) ? B + (int64_t)gk * ldb + gn : B + (int64_t)gn * ldb + gk) : B;
-      cp_async8(Bs + ((OPB == 0) ? k * SB + n : n * SB + k), src, ok);
+    } else {
+#pragma unroll
+      for (int r = 0; r < (BN * BK) / NT; ++r) {
+        const int idx = tid + r * NT;
+        int n, k;
+        if (OPB == 0) {
+          n = idx % BN;
+          k = idx / BN;
+        } else {
+          k = idx & 15;
+          n = idx >> 4;
+        }
+        const int gn = n0 + n, gk = k0 + k;
+        const bool ok = (gn < N) && (gk < K);
+        const double* src = ok ? ((OPB == 0) ? B + (int64_t)gk * ldb + gn : B + (int64_t)gn * ldb + gk) : B;
+        cp_async8(Bs + ((OPB == 0) ? k * SB + n : n * SB + k), src, ok);
+      }
     }
   };
 
@@ -497,6 +546,10 @@ inline void gemm_dmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int64
                              const double* A, int64_t lda, int64_t sA, const double* B, int64_t ldb, int64_t sB,
                              double beta, double* C, int64_t ldc, int64_t sC, int batch, int lower_only) {
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)batch), block(WM * WN * 32);
+  auto vec_ok = [](const double* p, int64_t ld, int64_t stride) {
+    return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 2 == 0) && (stride % 2 == 0);
+  };
+  const int vec = g_gemm_vec ? ((vec_ok(A, lda, sA) ? 1 : 0) | (vec_ok(B, ldb, sB) ? 2 : 0)) : 0;
 #define CEIT_DMMA_CASE(a, b)                                                                              \
   {                                                                                                       \
     constexpr size_t smem = (size_t)STAGES * DmmaSmem<BM, BN, a, b>::STAGE * sizeof(double);              \
@@ -508,7 +561,7 @@ inline void gemm_dmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int64
     }                                                                                                     \
     gemm_dmma_kernel<BM, BN, WM, WN, a, b, STAGES><<<grid, block, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, \
                                                                              sA, B, ldb, sB, beta, C, ldc, sC,      \
-                                                                             lower_only);                           \
+                                                                             lower_only, vec);                      \
   }
   if (opA == 0 && opB == 0) CEIT_DMMA_CASE(0, 0)
   else if (opA == 0 && opB == 1) CEIT_DMMA_CASE(0, 1)

@@ -605,6 +605,13 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap) {
     for (int32_t c : tb.children[f]) height[f] = std::max(height[f], height[c] + 1);
   int32_t H = 0;
   for (int32_t f = 0; f < nF; ++f) H = std::max(H, height[f] + 1);
+  // fronts with a non-zero right-hand side K_0U: a node next to an electrode node, or an active child
+  std::vector<uint8_t> active(nF, 0);
+  for (int32_t f = 0; f < nF; ++f) {          // children are created before their parent
+    for (int32_t v : tb.own[f])
+      for (int32_t q = p.rowptr[v]; q < p.rowptr[v + 1] && !active[f]; ++q) active[f] = (p.u_of[p.colidx[q]] >= 0);
+    for (int32_t c : tb.children[f]) active[f] |= active[c];
+  }
   std::vector<int32_t> gid(nF, -1), old_of(nF, -1);
   TreePlan& t = p.tree;
   t = TreePlan();
@@ -615,12 +622,15 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap) {
     int32_t next = 0;
     for (int32_t l = 0; l < H; ++l) {
       t.lv[l].f0 = next;
-      for (int32_t f = 0; f < nF; ++f)
-        if (height[f] == l) {
-          gid[f] = next;
-          old_of[next] = f;
-          ++next;
-        }
+      for (int pass = 1; pass >= 0; --pass) {   // active fronts first
+        for (int32_t f = 0; f < nF; ++f)
+          if (height[f] == l && active[f] == pass) {
+            gid[f] = next;
+            old_of[next] = f;
+            ++next;
+          }
+        if (pass == 1) t.lv[l].na = next - t.lv[l].f0;
+      }
       t.lv[l].n = next - t.lv[l].f0;
     }
   }
@@ -673,18 +683,25 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap) {
     }
     lv.s = (s + 7) / 8 * 8;
     lv.b = (b + 7) / 8 * 8;
-    lv.row0 = p.N0P;
     lv.offA = t.szA;
     lv.offB = t.szB;
     lv.offC = t.szC;
     lv.offR = (int64_t)t.rel.size();
-    p.N0P += (int64_t)lv.n * lv.s;
     t.szA += (int64_t)lv.n * lv.s * lv.s;
     t.szB += (int64_t)lv.n * lv.s * lv.b;
     t.szC += (int64_t)lv.n * lv.b * lv.b;
     t.maxG = std::max<int64_t>(t.maxG, (int64_t)lv.n * lv.b);
     t.maxC = std::max<int64_t>(t.maxC, (int64_t)lv.n * lv.b * lv.b);
     t.rel.resize(t.rel.size() + (size_t)lv.n * lv.b, -1);
+  }
+  for (int32_t l = 0; l < H; ++l) {            // padded rows: the active fronts of every level, then the inactive ones
+    t.lv[l].row0 = p.N0P;
+    p.N0P += (int64_t)t.lv[l].na * t.lv[l].s;
+  }
+  t.rowsA = p.N0P;
+  for (int32_t l = 0; l < H; ++l) {
+    t.lv[l].row0i = p.N0P;
+    p.N0P += (int64_t)(t.lv[l].n - t.lv[l].na) * t.lv[l].s;
   }
   if (p.N0P > (int64_t)2000000000) throw std::runtime_error("plan: padded row space exceeds 32-bit indices");
   t.bnd_row.assign(t.rel.size(), -1);
@@ -699,7 +716,8 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap) {
   auto prow = [&](int32_t v) -> int64_t {
     const int32_t g = owner[v];
     const TreeLevel& lv = t.lv[level_of[g]];
-    return lv.row0 + (int64_t)(g - lv.f0) * lv.s + slot[v];
+    const int64_t k = g - lv.f0;
+    return (k < lv.na ? lv.row0 + k * lv.s : lv.row0i + (k - lv.na) * lv.s) + slot[v];
   };
   for (int64_t v = 0; v < N; ++v)
     if (p.u_of[v] < 0) {
@@ -711,9 +729,11 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap) {
     p.node_at[p.N0P + u] = p.U[u];
   }
   for (const TreeLevel& lv : t.lv)
-    for (int64_t f = 0; f < lv.n; ++f)
+    for (int64_t f = 0; f < lv.n; ++f) {
+      const int64_t r0 = f < lv.na ? lv.row0 + f * lv.s : lv.row0i + (f - lv.na) * lv.s;
       for (int64_t a = 0; a < lv.s; ++a)
-        if (p.node_at[lv.row0 + f * lv.s + a] < 0) t.pad_diag.push_back(lv.offA + f * lv.s * lv.s + a * lv.s + a);
+        if (p.node_at[r0 + a] < 0) t.pad_diag.push_back(lv.offA + f * lv.s * lv.s + a * lv.s + a);
+    }
   auto bidx = [&](int32_t g, int32_t node) -> int64_t {
     auto it = std::lower_bound(bnd[g].begin(), bnd[g].end(), node);
     if (it == bnd[g].end() || *it != node) throw std::runtime_error("plan: node is not on the front's boundary");
@@ -760,7 +780,7 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap) {
   for (int32_t l = 0; l < H; ++l) {
     TreeLevel& lv = t.lv[l];
     std::vector<std::pair<int32_t, int32_t>> items;
-    for (int32_t k = 0; k < lv.n; ++k)
+    for (int32_t k = 0; k < lv.na; ++k)           // inactive fronts have a zero right-hand side: no contribution
       for (size_t a = 0; a < bnd[lv.f0 + k].size(); ++a)
         items.emplace_back(p.pos[bnd[lv.f0 + k][a]], (int32_t)(k * lv.b + (int32_t)a));
     std::sort(items.begin(), items.end());
@@ -793,6 +813,7 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap) {
           p.slot_dst[s] = blockB(gr) + (int64_t)slot[r] * t.lv[level_of[gr]].b + bidx(gr, c2);
         }
       } else if (!ru && cu) {
+        if (p.pos[r] >= t.rowsA) throw std::runtime_error("plan: a right-hand-side row lies outside the active region");
         p.slot_kind[s] = 3;
         p.slot_dst[s] = (int64_t)p.pos[r] * p.nU + p.u_of[c2];
       } else if (ru && cu) {

@@ -16,7 +16,10 @@ struct TreeLevel {
   int32_t n = 0, s = 0, b = 0;       // fronts, padded own size, padded boundary size (b = 0: roots only)
   int32_t passes = 0;                // 1 + largest sibling index (extend-add passes: siblings hit the same parent)
   int32_t f0 = 0;                    // global id of the level's first front
-  int64_t row0 = 0;                  // first padded row (own slots of front k: row0 + k s ...)
+  int32_t na = 0;                    // fronts with a non-zero right-hand side (they come first in the level): a front
+                                     // is ACTIVE when one of its nodes neighbours an electrode node or a child is active
+  int64_t row0 = 0;                  // first padded row of the active fronts (front k < na: row0 + k s ...)
+  int64_t row0i = 0;                 // first padded row of the inactive fronts (front k >= na: row0i + (k - na) s ...)
   int64_t offA = 0, offB = 0, offC = 0;   // element offsets of the level in the (n s s) / (n s b) / (n b b) storages
   int64_t offR = 0;                  // offset of the level in rel / bnd_row (n b entries)
   int64_t rc0 = 0, rc_n = 0;         // destinations of the level's right-hand-side scatter: rc_dst[rc0 .. rc0 + rc_n)
@@ -24,6 +27,7 @@ struct TreeLevel {
 struct TreePlan {
   int32_t H = 0;                     // levels, 0 = leaves
   int64_t nF = 0, szA = 0, szB = 0, szC = 0, maxG = 0, maxC = 0;   // maxG = max n b, maxC = max n b b over levels
+  int64_t rowsA = 0;                 // padded rows [0, rowsA) = the active fronts of every level (K0U is zero elsewhere)
   std::vector<TreeLevel> lv;
   // per front (global id, level by level)
   std::vector<int32_t> parent, sib;  // parent front (-1: root), index among the parent's children

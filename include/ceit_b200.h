@@ -204,6 +204,10 @@ int ceit_debug_tile_clocks(int64_t* out8);
  *   "nd_interior"       target nodes per nested-dissection interior for plans created afterwards (default 64)
  *   "patch_nodes"       node cap of the element patches for plans created afterwards (0 = automatic)
  *   "gemm_tile"         force the CTA tile of the DMMA GEMM (32 / 64 / 128, 0 = automatic)
+ *   "gemm_vec"          (default 1) stage the GEMM operands with 16-byte cp.async when base / leading dimension /
+ *                       batch stride are even; 0 = always 8-byte copies
+ *   "nd_tree"           (default 1) multi-level nested dissection of the base stage for plans created afterwards;
+ *                       0 = one level of interiors + block-tridiagonal separator chain (round-1 ordering)
  *   "gemm_min_ctas64"   automatic tile choice: 64x64 tiles when they give at least this many CTAs, else 32x32
  *                       (default 300)
  *   "ru_wc", "ru_cpt", "ru_waves"

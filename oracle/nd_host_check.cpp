@@ -148,6 +148,7 @@ int nd_host_check(const double* nodes, const int64_t* elem, int64_t N, int64_t E
     const int64_t nU = h.nU, N0P = h.N0P;
     std::vector<double> A(t.szA, 0.0), Lf(t.szA, 0.0), Li(t.szA, 0.0), Ai(t.szA, 0.0), Bt(t.szB, 0.0), W(t.szB, 0.0);
     std::vector<double> Sel(t.szA + t.szB, 0.0), C(t.szC, 0.0), R(N0P * nU, 0.0), Xp(N0P * nU, 0.0);
+    for (int64_t q = t.rowsA * nU; q < N0P * nU; ++q) R[q] = Xp[q] = std::nan("");   // inactive rows: never read before written
     std::vector<double> G(std::max<int64_t>(t.maxG, 1) * nU, 0.0), KUU(nU * nU, 0.0);
     // identity on the padding slots (pad_identity_kernel) and the CSR scatter (scatter_dense_kernel)
     for (int64_t d : t.pad_diag) A[d] = 1.0;
@@ -172,7 +173,7 @@ int nd_host_check(const double* nodes, const int64_t* elem, int64_t N, int64_t E
     for (int64_t a = 0; a < nU; ++a)
       for (int64_t b = 0; b < nU; ++b) {
         double acc = 0.0;
-        for (int64_t r = 0; r < N0P; ++r) acc += R[r * nU + a] * Xp[r * nU + b];
+        for (int64_t r = 0; r < t.rowsA; ++r) acc += R[r * nU + a] * Xp[r * nU + b];
         SU[a * nU + b] = KUU[a * nU + b] - acc;
       }
     std::memcpy(Sel.data(), Ai.data(), sizeof(double) * t.szA);

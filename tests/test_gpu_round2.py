@@ -1,0 +1,301 @@
+"""Round-2 parity additions (VERDICT r01 'weak' list): branches of the product path that no test reached, full-matrix
+checks where only samples existed, numerics of every one-shot Gauss-Newton variant through the class API."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ceit_oracle as o  # noqa: E402
+
+from ceit_b200 import _lib, meshgen  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+RAW_TOL = 1e-9
+SIGNAL_TOL = 1e-4
+MODEL_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback")
+    return torch
+
+
+@pytest.fixture()
+def workspace(tmp_path, golden, monkeypatch):
+    def make(tag, **overrides):
+        m, _ = golden(tag)
+        cfg = dict(meshgen.REFERENCE_CONFIG)
+        cfg["folder_name"] = "MESH_" + tag
+        cfg.update(overrides)
+        path = meshgen.make_workspace(str(tmp_path / tag), m["nodes"], m["elem"], cfg)
+        monkeypatch.setenv("CEIT_B200_CONFIG", path)
+        monkeypatch.chdir(os.path.dirname(path))
+        return path
+    return make
+
+
+def _rows(i, L):
+    return slice(i * (L - 1), (i + 1) * (L - 1))
+
+
+def test_full_mesh_50_50_jacobian_against_woodbury_oracle(torch_cuda, golden):
+    """ALL 240 x 5000 entries of the MESH_50_50 Jacobian against the oracle's exact rank-3 restatement
+    (oracle.jacobian_woodbury, itself pinned on the reference's full MESH_21_21 Jacobian and on 84 reference columns
+    of this mesh in tests/test_oracle_golden.py)."""
+    t = torch_cuda
+    m, r = golden("50_50")
+    N, E, L = len(m["nodes"]), len(m["elem"]), 16
+    omega = 2 * np.pi * float(r["signal_frequency"])
+    c = float(r["variable_change_for_JAC"])
+    p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"])
+    p.assemble(t.tensor(m["elem_perm"], device="cuda"), t.zeros(E, dtype=t.float64, device="cuda"), omega)
+    p.factor(False)
+    J = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
+    p.jacobian_block(0, L, 0, E, c, omega, J, E)
+    assert p.numeric_flag() == 0
+    Jh = J.cpu().numpy()
+    param = o.elem_param(m["nodes"], m["elem"])
+    Jo = o.jacobian_woodbury(m["elem"], param, m["elem_perm"], np.zeros(E), omega, m["electrodes"], c, N)
+    assert Jo.shape == Jh.shape
+    assert np.abs(Jh - Jo).max() < RAW_TOL
+    assert np.linalg.norm(Jh - Jo) / np.linalg.norm(Jo - 1) < SIGNAL_TOL
+    p.close()
+
+
+def test_odd_number_of_electrode_nodes_takes_the_cp_async_staging_branch(torch_cuda):
+    """woodbury_lr_kernel stages the Yh rows with TMA bulk copies when nU is even (16-byte aligned rows) and with
+    8-byte cp.async otherwise; every shipped / synthetic layout has an even nU, so this mesh drops one electrode
+    element to make nU odd."""
+    t = torch_cuda
+    n = 33
+    cfg = meshgen.synthetic_config(n, 5)
+    nodes, elem = meshgen.structured_mesh(n)
+    param = o.elem_param(nodes, elem)
+    els = o.electrode_elements(param, np.array(cfg["electrode_centers"]) / 1000, cfg["electrode_radius"] / 1000)
+    els = [np.asarray(e) for e in els]
+    p = None
+    for drop in range(len(els[3])):                        # find an element whose removal removes exactly one node
+        trial = list(els)
+        trial[3] = np.delete(els[3], drop)
+        nU = len(set(np.concatenate([elem[e].reshape(-1) for e in trial]).tolist()))
+        if nU % 2 == 1:
+            els = trial
+            break
+    else:
+        pytest.fail("could not build an odd electrode-node count")
+    L, E = len(els), len(elem)
+    omega = 2 * np.pi * cfg["signal_frequency"]
+    p = _lib.Plan(nodes, elem, els)
+    assert p.nU % 2 == 1
+    p.assemble(t.ones(E, dtype=t.float64, device="cuda"), t.zeros(E, dtype=t.float64, device="cuda"), omega)
+    p.factor(False)
+    J = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
+    p.jacobian_block(0, L, 0, E, 1e-3, omega, J, E)
+    assert p.numeric_flag() == 0
+    rng = np.random.default_rng(11)
+    pairs = [(int(rng.integers(L)), int(rng.integers(E))) for _ in range(10)] + [(3, int(els[3][0])), (2, int(els[3][1]))]
+    cols = o.jacobian_columns_bruteforce(elem, param, np.ones(E), np.zeros(E), omega, els, pairs, 1e-3, len(nodes))
+    Jh = J.cpu().numpy()
+    for k, (i, j) in enumerate(pairs):
+        assert np.abs(Jh[_rows(i, L), j] - cols[k]).max() < RAW_TOL
+        sig = np.abs(cols[k] - 1).max()
+        if sig > 1e-10:
+            assert np.abs(Jh[_rows(i, L), j] - cols[k]).max() < 1e-3 * sig
+    p.close()
+
+
+def test_inverse_model_400x400_dual_splitk_against_numpy(torch_cuda):
+    """BASELINE config C4 shape: m = 992, n_det = 257 762 (dual form, split-K Gram matrix).  A seeded J of that shape
+    with the signal level of the real one; a sample of detection rows of inv_mat against numpy on the same J."""
+    t = torch_cuda
+    m_rows, E = 992, 318402
+    g = t.Generator(device="cuda").manual_seed(4)
+    J = 1.0 - 1e-8 * t.rand((m_rows, E), dtype=t.float64, device="cuda", generator=g)
+    det_h = np.sort(np.random.default_rng(4).choice(E, size=257762, replace=False)).astype(np.int64)
+    det = t.tensor(det_h, device="cuda")
+    for lam in (289.0, 3e-6):
+        flag = t.zeros(1, dtype=t.int32, device="cuda")
+        inv = _lib.inverse_model(J, det, lam, flag=flag)
+        assert int(flag.item()) == 0
+        Jt = J.index_select(1, det) - 1.0
+        G = (Jt @ Jt.T + lam * lam * t.eye(m_rows, dtype=t.float64, device="cuda")).cpu().numpy()
+        Gi = np.linalg.inv(G)
+        rows = np.random.default_rng(5).choice(len(det_h), size=400, replace=False)
+        ref = Jt[:, t.tensor(rows, device="cuda")].cpu().numpy().T @ Gi
+        got = inv[t.tensor(rows, device="cuda")].cpu().numpy()
+        assert np.abs(got - ref).max() <= (MODEL_TOL if lam > 1 else 1e-6) * np.abs(ref).max()
+        del inv, Jt
+
+
+def test_singular_normal_matrix_raises_like_numpy(torch_cuda, workspace, golden):
+    """np.linalg.inv raises LinAlgError('Singular matrix') on a singular normal matrix (Solver.py:121); the device
+    path reports the non-positive Cholesky pivot through the flag and the classes raise before caching inv_mat.npy"""
+    t = torch_cuda
+    path = workspace("21_21")
+    m, r = golden("21_21")
+    folder = os.path.join(os.path.dirname(path), "MESH_21_21")
+    J = t.ones((240, 882), dtype=t.float64, device="cuda")            # J - 1 == 0: Gram matrix 0, lambda = 0
+    det = t.tensor(m["detection_index"], device="cuda")
+    flag = t.zeros(1, dtype=t.int32, device="cuda")
+    _lib.inverse_model(J, det, 0.0, flag=flag)
+    assert int(flag.item()) == 1
+    with pytest.raises(np.linalg.LinAlgError, match="Singular matrix"):
+        _lib.check_flag(flag)
+    _lib.inverse_model(J, det, 1.0, flag=flag)                        # the flag is reset by every call
+    assert int(flag.item()) == 0
+    Jn = np.ones((240, 882))
+    Jn[0, 0] = np.nan
+    np.save(os.path.join(folder, "JAC_cache.npy"), Jn)
+    from ceit_b200.Solver import Solver
+    with pytest.raises(np.linalg.LinAlgError):
+        Solver(289)
+    assert not os.path.exists(os.path.join(folder, "inv_mat.npy"))    # nothing cached
+
+
+def test_real_complex_real_on_one_engine_with_repeats(torch_cuda, workspace, golden):
+    """alternating material type on ONE engine with repeated (graph-replayed) calls.  The library
+    re-allocates its workspaces on a real <-> complex switch; graphs captured before hold stale pointers and must be
+    dropped (allocation generation), and nothing may be allocated inside a capture."""
+    workspace("21_21")
+    m, r = golden("21_21")
+    from ceit_b200.EFEM import EFEM
+    from ceit_b200.EJAC import EJAC
+    fwd = EFEM()
+    eng = fwd._engine
+    for rep in range(3):
+        fwd.reset_variable(0)
+        for _ in range(3):                                            # eager, captured, replayed
+            node_u, _, ep = fwd.calculation(7)
+            assert np.abs(node_u - r["base_node_potential"][7]).max() < RAW_TOL
+            assert np.abs(ep - r["base_electrode_potential"][7]).max() < RAW_TOL
+        fwd.change_add_variable_geometry([-20 / 1000, -10 / 1000], 10 / 1000, 1e-7, "square")
+        for _ in range(3):
+            node_u, elem_u, ep = fwd.calculation(2)
+            assert np.abs(node_u - r["obj_node_potential"]).max() < RAW_TOL
+            assert np.abs(ep - r["obj_electrode_potential"]).max() < RAW_TOL
+    gen = eng.plan.generation()
+    assert gen >= 4                                                   # the workspaces were re-allocated on the switches
+    jac = EJAC(fwd.mesh)                                              # same mesh -> same engine
+    assert jac._eng is eng
+    for _ in range(3):
+        jac.fwd_FEM.invalidate()
+        J = jac.JAC_calculation()
+        assert np.abs(J - r["JAC"]).max() < RAW_TOL
+    fwd.change_add_variable_geometry([-20 / 1000, -10 / 1000], 10 / 1000, 1e-7, "square")
+    node_u, _, _ = fwd.calculation(2)                                 # complex again after the real Jacobian graphs
+    assert np.abs(node_u - r["obj_node_potential"]).max() < RAW_TOL
+    for _ in range(2):
+        jac.fwd_FEM.invalidate()
+        assert np.abs(jac.JAC_calculation() - r["JAC"]).max() < RAW_TOL
+    # a captured sequence that would need a larger workspace is refused, not silently re-allocated under capture
+    t = torch_cuda
+    E, L = len(m["elem"]), 16
+    p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"])
+    perm = t.tensor(m["elem_perm"], device="cuda")
+    var = t.zeros(E, dtype=t.float64, device="cuda")
+    Jd = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
+    p.assemble(perm, var, 2 * np.pi * 2e4)
+    p.factor(False)
+    p.jacobian_block(0, 1, 0, E, 1e-3, 2 * np.pi * 2e4, Jd, E)      # workspace for ONE excitation
+    with pytest.raises(Exception):
+        _lib.StepGraph(lambda: p.jacobian_block(0, L, 0, E, 1e-3, 2 * np.pi * 2e4, Jd, E))   # needs 16: refused
+    t.cuda.synchronize()
+    p.jacobian_block(0, L, 0, E, 1e-3, 2 * np.pi * 2e4, Jd, E)      # eager: allocates, correct
+    assert np.abs(Jd.cpu().numpy() - r["JAC"]).max() < RAW_TOL
+    p.close()
+
+
+def test_every_one_shot_gauss_newton_variant_numerically(torch_cuda, workspace, golden):
+    """EJAC.eit_solve_direct, the 4- and 8-electrode wrappers in both modes and eit_solve_on_some_electrodes
+    (mode='direct') against numpy restatements of CEIT/EJAC.py:184-229,252-259 on the reference's own J."""
+    path = workspace("21_21", is_first_JAC_calculation=False)
+    m, r = golden("21_21")
+    folder = os.path.join(os.path.dirname(path), "MESH_21_21")
+    np.save(os.path.join(folder, "JAC_cache.npy"), r["JAC"])
+    from ceit_b200.EJAC import EJAC
+    jac = EJAC()
+    J = jac.JAC_calculation()
+    assert np.array_equal(J, r["JAC"])
+    det = m["detection_index"]
+    L = 16
+    rng = np.random.default_rng(8)
+    V = 1.0 + 1e-3 * rng.random(240)
+    base = jac.electrode_original_potential
+
+    def ref_subset(electrodes, potential, lmbda, mode):
+        sl = []
+        for i in electrodes:
+            for j in electrodes:
+                if j < i:
+                    sl.append(i * (L - 1) + j)
+                if j > i:
+                    sl.append(i * (L - 1) + j - 1)
+        dV = (potential - base)[sl] if mode == "direct" else potential
+        Jt = J[:, det][sl] - 1
+        return np.linalg.inv(Jt.T @ Jt + lmbda ** 2 * np.eye(len(det))) @ Jt.T @ dV * 1e-4
+
+    cases = [
+        (jac.eit_solve_4electrodes(V), ref_subset([2, 6, 10, 14], V, 90, "direct")),
+        (jac.eit_solve_4electrodes_delta_V(np.arange(12.0) * 1e-3), ref_subset([2, 6, 10, 14], np.arange(12.0) * 1e-3, 90, "diff")),
+        (jac.eit_solve_8electrodes(V), ref_subset([0, 2, 4, 6, 8, 10, 12, 14], V, 265, "direct")),
+        (jac.eit_solve_8electrodes_delta_V(np.arange(56.0) * 1e-3),
+         ref_subset([0, 2, 4, 6, 8, 10, 12, 14], np.arange(56.0) * 1e-3, 265, "diff")),
+        (jac.eit_solve_on_some_electrodes([1, 5, 9], V, 120, mode="direct"), ref_subset([1, 5, 9], V, 120, "direct")),
+    ]
+    for got, ref in cases:
+        assert got.shape == ref.shape == (len(det),)
+        assert np.abs(got - ref).max() <= MODEL_TOL * np.abs(ref).max()
+    with pytest.raises(AssertionError, match="Please enter the right solver mode"):
+        jac.eit_solve_on_some_electrodes([1, 5], V, 10, mode="nope")
+    # eit_solve_direct: reads inv_mat.npy (EJAC.py:252-259)
+    jac.save_inv_matrix(203)
+    inv = o.inverse_model(J, det, 203)
+    ref = inv @ (V - base)
+    got = jac.eit_solve_direct(V)
+    assert np.abs(got - ref).max() <= MODEL_TOL * np.abs(ref).max()
+    # a Jacobian assigned by the caller after a calculation is picked up (no stale device copy)
+    jac.JAC_matrix = np.array(J) * 1.0
+    jac.JAC_matrix[:, det[5]] += 1e-9
+    got2 = jac.eit_solve(V, 295)
+    ref2 = o.reconstruct(o.inverse_model(jac.JAC_matrix, det, 295), V - base)
+    assert np.abs(got2 - ref2).max() <= MODEL_TOL * np.abs(ref2).max()
+
+
+@pytest.mark.parametrize("tile", [0, 1, 2, 3])
+def test_dgemm_vector_staging_edges(torch_cuda, tile):
+    """16-byte cp.async staging (even leading dimensions) with ODD logical sizes: the last pair of every row is half
+    valid and must be zero-filled, in all four transpose cases; and 8-byte-misaligned bases fall back to 8-byte copies."""
+    import ctypes
+    t = torch_cuda
+    g = t.Generator(device="cuda").manual_seed(7)
+    L = _lib.lib()
+    _lib.set_option("gemm_tile", tile)
+    try:
+        for (M, N, K) in ((65, 33, 47), (129, 71, 17), (31, 130, 99)):
+            for ta in (0, 1):
+                for tb in (0, 1):
+                    for off in (0, 1):                                # off = 1: base pointer only 8-byte aligned
+                        Ab = t.randn((K if ta else M, (M if ta else K) + 3 + off), dtype=t.float64, device="cuda", generator=g)
+                        Bb = t.randn((N if tb else K, (K if tb else N) + 5 + off), dtype=t.float64, device="cuda", generator=g)
+                        if Ab.stride(0) % 2:
+                            Ab = t.cat([Ab, Ab[:, :1]], 1).contiguous()
+                        if Bb.stride(0) % 2:
+                            Bb = t.cat([Bb, Bb[:, :1]], 1).contiguous()
+                        A = Ab[:, off:off + (M if ta else K)]
+                        B = Bb[:, off:off + (K if tb else N)]
+                        C = t.zeros((M, N + 1), dtype=t.float64, device="cuda")
+                        rc = L.ceit_dgemm(ta, tb, M, N, K, 1.0, ctypes.c_void_p(A.data_ptr()), A.stride(0),
+                                          ctypes.c_void_p(B.data_ptr()), B.stride(0), 0.0, ctypes.c_void_p(C.data_ptr()),
+                                          C.stride(0), _lib.stream_ptr())
+                        assert rc == 0
+                        ref = (A.T if ta else A) @ (B.T if tb else B)
+                        assert ((C[:, :N] - ref).abs().max() / ref.abs().max()).item() < 1e-13
+                        assert C[:, N].abs().max().item() == 0.0
+    finally:
+        _lib.set_option("gemm_tile", 0)

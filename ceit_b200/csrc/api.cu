@@ -60,6 +60,11 @@ int g_direct_excitation = 0;
 int g_patch_nodes = 0;   // experiment: override the node cap of the element patches
 int64_t g_nd_interior = 64;   // target nodes per nested-dissection interior / leaf; <= 0 disables the dissection
 int g_nd_tree = 1;            // 1: multi-level nested dissection (factor_tree.h); 0: interiors + block-tridiagonal chain
+int g_nd_pull = 0;            // plans created afterwards: 1 = levels of small fronts pull their children and run the
+                              // fused front kernel.  Measured on MESH_50_50: 25-50 us per level on ONE SM (global-load
+                              // latency chains + FP64 products) against ~32 us for the 5 chip-wide launches it replaces,
+                              // step 0.77 -> 0.82 ms: kept as a tested option, off by default
+int g_no_front_kernel = 0;    // 1: pull levels run pull_children_kernel + the separate steps (test coverage of that path)
 struct StageEv {
   int stage;
   cudaEvent_t a, b;
@@ -182,6 +187,9 @@ struct ceit_plan {
   int32_t *d_t_sib = nullptr, *d_t_ps = nullptr, *d_t_pb = nullptr, *d_t_rel = nullptr, *d_t_bnd_row = nullptr;
   int32_t *d_t_rc_dst = nullptr, *d_t_rc_ptr = nullptr, *d_t_rc_src = nullptr;
   int64_t *d_t_pA = nullptr, *d_t_pB = nullptr, *d_t_pC = nullptr, *d_t_pad = nullptr;
+  int32_t *d_t_child_ptr = nullptr, *d_t_child_ids = nullptr, *d_t_fb = nullptr;
+  int64_t *d_t_foffC = nullptr, *d_t_frelOff = nullptr;
+  uint8_t* d_t_push = nullptr;
   int alloc_mode = 0;
   int64_t generation = 0;   // bumped whenever a numeric / excitation workspace is (re)allocated: graphs captured
                             // before hold stale pointers (ceit_plan_generation)
@@ -266,6 +274,12 @@ int upload_plan(ceit_plan* p) {
     if ((rc = upload_vec(p, &p->d_t_pB, t.pB))) return rc;
     if ((rc = upload_vec(p, &p->d_t_pC, t.pC))) return rc;
     if ((rc = upload_vec(p, &p->d_t_pad, t.pad_diag))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_child_ptr, t.child_ptr))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_child_ids, t.child_ids))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_fb, t.f_b))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_foffC, t.f_offC))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_frelOff, t.f_relOff))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_push, t.push))) return rc;
   }
   if ((rc = upload_vec(p, &p->d_ue_ptr, h.ue_ptr))) return rc;
   if ((rc = upload_vec(p, &p->d_wk, h.wk))) return rc;
@@ -343,7 +357,7 @@ int alloc_numeric(ceit_plan* p, cudaStream_t st) {
   if ((rc = dev_alloc(p, &p->ye, h.N * es))) return rc;
   if (!p->d_gamma && (rc = dev_alloc(p, (void**)&p->d_gamma, sizeof(double)))) return rc;
   if ((rc = dev_alloc(p, &p->g1e, 6 * h.E * es))) return rc;
-  if ((rc = dev_alloc(p, &p->splitk_ws, (size_t)splitk_slices(h.nU, h.nU, h.N0P, 1) * h.nU * h.nU * sizeof(double)))) return rc;
+  if ((rc = dev_alloc(p, &p->splitk_ws, (size_t)splitk_max_slices(h.nU, h.nU, h.N0P) * h.nU * h.nU * sizeof(double)))) return rc;
   if ((rc = dev_alloc(p, &p->KUU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->SU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Ptmp, maxS * es))) return rc;
@@ -515,8 +529,36 @@ struct CudaTreeBK {
   cudaStream_t lane[3];
   T* panel;
   int rc = 0;
+  bool lane2_used = false;
   void after(int from, int to) {
+    if (from == 2 && !lane2_used) return;      // nothing was forked to lane 2 (every level ran the fused front step)
+    if (to == 2) lane2_used = true;
     if (!rc) rc = stream_after(p, lane[from], lane[to]);
+  }
+  FrontFusedArgs front_args(const TreeLevel& lv) const {
+    return FrontFusedArgs{lv.s, lv.b, lv.f0, p->d_t_child_ptr, p->d_t_child_ids, p->d_t_fb, p->d_t_rel, p->d_t_foffC,
+                          p->d_t_frelOff};
+  }
+  bool can_fuse() const { return !Sc<T>::is_complex && !g_no_front_kernel; }
+  void front_fused(int ln, const TreePlan&, const TreeLevel& lv, T* A, T* Bt, T* C, T* Ainv, T* W) {
+    launch_front_fused(ln, lv, A, Bt, C, Ainv, W);
+  }
+  void launch_front_fused(int ln, const TreeLevel& lv, double* A, double* Bt, double* C, double* Ainv, double* W) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(front_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM);
+      attr_done = true;
+    }
+    front_fused_kernel<<<lv.n, 256, FRONT_SMEM, lane[ln]>>>(front_args(lv), A + lv.offA, Bt + lv.offB, C, C + lv.offC,
+                                                            Ainv + lv.offA, W + lv.offB, p->d_info);
+    CEIT_COUNT_LAUNCH();
+    g_flops += (double)lv.n * ((2.0 / 3.0 + 1.0) * lv.s * lv.s * lv.s + 3.0 * lv.s * lv.s * lv.b +
+                               (double)lv.s * lv.b * lv.b);
+  }
+  void launch_front_fused(int, const TreeLevel&, cd*, cd*, cd*, cd*, cd*) {}   // complex: pull + separate steps
+  void pull_children(int ln, const TreePlan&, const TreeLevel& lv, T* A, T* Bt, T* C) {
+    pull_children_kernel<T><<<lv.n, 256, 0, lane[ln]>>>(front_args(lv), A + lv.offA, Bt + lv.offB, C, C + lv.offC);
+    CEIT_COUNT_LAUNCH();
   }
   void gemm(int ln, int opA, int opB, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t lda, int64_t sA,
             const T* B, int64_t ldb, int64_t sB, T beta, T* C, int64_t ldc, int64_t sC, int batch, int lower_only) {
@@ -528,7 +570,7 @@ struct CudaTreeBK {
   }
   void extend_add(int ln, const TreePlan&, const TreeLevel& lv, int pass, const T* U, T* A, T* Bt, T* C) {
     dim3 grid(cdiv((int64_t)lv.b * lv.b, 256), lv.n);
-    extend_add_kernel<T><<<grid, 256, 0, lane[ln]>>>(lv.b, pass, p->d_t_sib + lv.f0, p->d_t_pA + lv.f0,
+    extend_add_kernel<T><<<grid, 256, 0, lane[ln]>>>(lv.b, pass, p->d_t_push + lv.f0, p->d_t_sib + lv.f0, p->d_t_pA + lv.f0,
                                                      p->d_t_pB + lv.f0, p->d_t_pC + lv.f0, p->d_t_ps + lv.f0,
                                                      p->d_t_pb + lv.f0, p->d_t_rel + lv.offR, U, A, Bt, C);
     CEIT_COUNT_LAUNCH();
@@ -1138,7 +1180,7 @@ int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_
   ceit_plan* p = new ceit_plan();
   try {
     build_host_plan(p->h, nodes, elem, N, E, el_ptr, el_elems, L, target_block, g_nd_interior,
-                    g_nd_tree != 0 && target_block <= 0);
+                    g_nd_tree != 0 && target_block <= 0, g_nd_pull != 0);
     {
       // patches of <= 32 elements whose distinct node rows fit the shared-memory budget
       const bool lr = rank_update_shape_ok(p->h) && !g_direct_excitation && !g_no_lowrank;
@@ -1515,6 +1557,8 @@ int ceit_set_option(const char* name, int64_t value) {
     g_direct_excitation = (int)value;
     return CEIT_OK;
   }
+  if (std::strcmp(name, "nd_pull") == 0) { g_nd_pull = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "no_front_kernel") == 0) { g_no_front_kernel = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "nd_tree") == 0) {
     g_nd_tree = (int)value;
     return CEIT_OK;

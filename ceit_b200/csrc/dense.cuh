@@ -134,48 +134,14 @@ __device__ __forceinline__ void tri_inverse_level(const T* __restrict__ S, T* __
   __syncthreads();
 }
 
-// One CTA factors one n x n (n <= 64) tile held in shared memory.
-//   A (read), L (write, lower incl. zeros above the diagonal), Linv (write, same shape).
-// info: set to 1 if a pivot is not positive (real) / zero (complex).
-//
-// Elimination is done UNSCALED (S[i][k] -= S[i][j] S[k][j] / S[j][j]) so that a column step needs one
-// barrier and no serial sqrt: the pivots are final when their column is reached, and L = S diag(p)^-1/2
-// is applied in one pass at the end.  The triangular inverse is built by block recursion
-// (16 -> 32 -> 64): X21 = -X22 (L21 X11), i.e. small matrix products that use all 256 threads.
+// Factorisation + triangular inverse of a 64 x 64 tile held in shared memory (leading dimension 65).
+// In: S = the matrix (identity-padded beyond n), X = 0, all threads synchronised.  Out: S = L (zeros above the
+// diagonal), X = L^-1, synchronised.  W: scratch tile; rdiag / rpiv: 64 / 65 scalars.  256 threads.
 template <class T>
-__global__ void __launch_bounds__(256)
-potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA, T* __restrict__ L,
-                        int64_t ldl, int64_t sL, T* __restrict__ Linv, int64_t ldi, int64_t sI,
-                        int* __restrict__ info) {
+__device__ __forceinline__ void tile_factor_in_smem(T* __restrict__ S, T* __restrict__ X, T* __restrict__ W,
+                                                    T* __restrict__ rdiag, T* __restrict__ rpiv, int n, int tid,
+                                                    int* __restrict__ info) {
   constexpr int LD = TILE + 1;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* S = reinterpret_cast<T*>(smem_raw);   // [64][65] matrix -> L
-  T* X = S + TILE * LD;                    // [64][65] inverse
-  T* W = X + TILE * LD;                    // [64][65] scratch for the recursion
-  __shared__ T rdiag[TILE];
-  __shared__ T rpiv[TILE + 1];
-  const int tid = threadIdx.x;
-  A += (int64_t)blockIdx.x * sA;
-  L += (int64_t)blockIdx.x * sL;
-  Linv += (int64_t)blockIdx.x * sI;
-  CEIT_CLK(0);
-  {
-    T v[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {   // all 16 global loads in flight before the first shared store
-      const int r = (tid >> 6) + 4 * u, cc = tid & 63;
-      v[u] = (r == cc) ? Sc<T>::one() : Sc<T>::zero();   // identity padding for n < 64
-      if (r < n && cc < n) v[u] = A[(int64_t)r * lda + cc];
-    }
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int r = (tid >> 6) + 4 * u, cc = tid & 63;
-      S[r * LD + cc] = v[u];
-      X[r * LD + cc] = Sc<T>::zero();
-    }
-  }
-  __syncthreads();
-  CEIT_CLK(1);
   // ---- unscaled right-looking elimination, one barrier per TWO columns -----------------------------
   // Thread (rb, cb) owns the 4x4 interleaved register tile {rb+16u} x {cb+16v} for the whole
   // elimination (interleaving balances the triangular work and keeps shared accesses conflict-free).
@@ -244,8 +210,54 @@ potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA,
   __syncthreads();
   // ---- recursion X21 = -X22 (L21 X11): half = 16 (two pairs, 2 outputs/thread), half = 32 (4/thread) ----
   CEIT_CLK(4);
-  tri_inverse_level<T, 16>(S, X, W, tid);
-  tri_inverse_level<T, 32>(S, X, W, tid);
+  // (a tile of n <= 16 / n <= 32 is identity beyond its first / first two diagonal blocks: nothing to recurse on)
+  if (n > 16) tri_inverse_level<T, 16>(S, X, W, tid);
+  if (n > 32) tri_inverse_level<T, 32>(S, X, W, tid);
+}
+
+// One CTA factors one n x n (n <= 64) tile held in shared memory.
+//   A (read), L (write, lower incl. zeros above the diagonal), Linv (write, same shape).
+// info: set to 1 if a pivot is not positive (real) / zero (complex).
+//
+// Elimination is done UNSCALED (S[i][k] -= S[i][j] S[k][j] / S[j][j]) so that a column step needs one
+// barrier and no serial sqrt: the pivots are final when their column is reached, and L = S diag(p)^-1/2
+// is applied in one pass at the end.  The triangular inverse is built by block recursion
+// (16 -> 32 -> 64): X21 = -X22 (L21 X11), i.e. small matrix products that use all 256 threads.
+template <class T>
+__global__ void __launch_bounds__(256)
+potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA, T* __restrict__ L,
+                        int64_t ldl, int64_t sL, T* __restrict__ Linv, int64_t ldi, int64_t sI,
+                        int* __restrict__ info) {
+  constexpr int LD = TILE + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* S = reinterpret_cast<T*>(smem_raw);   // [64][65] matrix -> L
+  T* X = S + TILE * LD;                    // [64][65] inverse
+  T* W = X + TILE * LD;                    // [64][65] scratch for the recursion
+  __shared__ T rdiag[TILE];
+  __shared__ T rpiv[TILE + 1];
+  const int tid = threadIdx.x;
+  A += (int64_t)blockIdx.x * sA;
+  L += (int64_t)blockIdx.x * sL;
+  Linv += (int64_t)blockIdx.x * sI;
+  CEIT_CLK(0);
+  {
+    T v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {   // all 16 global loads in flight before the first shared store
+      const int r = (tid >> 6) + 4 * u, cc = tid & 63;
+      v[u] = (r == cc) ? Sc<T>::one() : Sc<T>::zero();   // identity padding for n < 64
+      if (r < n && cc < n) v[u] = A[(int64_t)r * lda + cc];
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int r = (tid >> 6) + 4 * u, cc = tid & 63;
+      S[r * LD + cc] = v[u];
+      X[r * LD + cc] = Sc<T>::zero();
+    }
+  }
+  __syncthreads();
+  CEIT_CLK(1);
+  tile_factor_in_smem<T>(S, X, W, rdiag, rpiv, n, tid, info);
   CEIT_CLK(5);
   // the caller zero-initialises L and Linv, so only the lower triangle is written
   for (int q = tid; q < TILE * TILE; q += 256) {
@@ -256,6 +268,257 @@ potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA,
     }
   }
   CEIT_CLK(6);
+}
+
+
+// ---- multi-level nested dissection: the whole front step of a level of SMALL fronts in one kernel -------------------
+// (factor_tree.h, levels with pull = 1: padded own size s <= 64, padded boundary size b <= 64.)  One CTA per front:
+//   1. load the own block A (s x s, identity-padded to 64) and the coupling block Bt (s x b) from the assembled
+//      matrix, C = 0, then PULL the update matrices of the children (in the child order of the plan; the entries of
+//      one child hit distinct destinations, a barrier separates the children: no atomics, bitwise reproducible);
+//   2. A = L L^T and Linv in shared memory (tile_factor_in_smem);
+//   3. A^-1 = Linv^T Linv -> global;  Y = Linv Bt;  W = A^-1 Bt -> global;  U = C - Y^T Y -> global C (lower triangle,
+//      what the parent pulls / the extend-add pushes);  the updated Bt -> global (right-hand-side chain).
+// Replaces 6-8 dependent launches per level (tile factorisation, 4 GEMMs, 2 extend-add passes) on the serial spine
+// of the base stage: MESH_50_50 has 7 levels, all of this kind.
+struct FrontFusedArgs {
+  int s, b, f0;                 // padded sizes of the level, global id of its first front
+  const int32_t *child_ptr, *child_ids, *f_b, *rel;
+  const int64_t *f_offC, *f_relOff;
+};
+constexpr int FRONT_LD = TILE + 1;
+constexpr size_t FRONT_SMEM = (size_t)(6 * TILE * FRONT_LD + 2 * TILE + 8) * sizeof(double);
+__global__ void __launch_bounds__(256)
+front_fused_kernel(FrontFusedArgs a, double* __restrict__ A, double* __restrict__ Bt, double* __restrict__ Call,
+                   double* __restrict__ Cout, double* __restrict__ Ainv, double* __restrict__ Wg,
+                   int* __restrict__ info) {
+  constexpr int LD = FRONT_LD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* S = reinterpret_cast<double*>(smem_raw);   // matrix -> L
+  double* X = S + TILE * LD;                          // Linv
+  double* Wsc = X + TILE * LD;                        // scratch of the inverse recursion, then A^-1
+  double* Bs = Wsc + TILE * LD;                       // Bt (s x b)
+  double* Ys = Bs + TILE * LD;                        // Y = Linv Bt
+  double* Cs = Ys + TILE * LD;                        // C (b x b)
+  double* rdiag = Cs + TILE * LD;
+  double* rpiv = rdiag + TILE;
+  const int tid = threadIdx.x, f = blockIdx.x, s = a.s, b = a.b;
+  const int g = a.f0 + f;
+  A += (int64_t)f * s * s;
+  Bt += (int64_t)f * s * b;
+  Cout += (int64_t)f * b * b;
+  Ainv += (int64_t)f * s * s;
+  Wg += (int64_t)f * s * b;
+  {
+    double va[16], vb[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {   // all global loads in flight before the first shared store
+      const int r = (tid >> 6) + 4 * u, c = tid & 63;
+      va[u] = (r == c) ? 1.0 : 0.0;
+      if (r < s && c < s) va[u] = A[(int64_t)r * s + c];
+      vb[u] = (r < s && c < b) ? Bt[(int64_t)r * b + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int r = (tid >> 6) + 4 * u, c = tid & 63;
+      S[r * LD + c] = va[u];
+      Bs[r * LD + c] = vb[u];
+      X[r * LD + c] = 0.0;
+      Cs[r * LD + c] = 0.0;
+    }
+  }
+  __syncthreads();
+  for (int qc = a.child_ptr[g]; qc < a.child_ptr[g + 1]; ++qc) {
+    const int ch = a.child_ids[qc];
+    const int cb = a.f_b[ch];                       // <= 64 is not guaranteed for a child: handled in chunks below
+    const double* __restrict__ U = Call + a.f_offC[ch];
+    const int32_t* __restrict__ rel = a.rel + a.f_relOff[ch];
+    const int total = cb * cb;
+    for (int base = 0; base < total; base += 256 * 8) {
+      double v[8];
+      int ra[8], rc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {                 // 8 independent (rel, rel, U) load triples per thread in flight
+        const int q = base + j * 256 + tid;
+        ra[j] = rc[j] = -1;
+        v[j] = 0.0;
+        if (q < total) {
+          const int x = q / cb, y = q - x * cb;
+          ra[j] = rel[x];
+          rc[j] = rel[y];
+          v[j] = (x >= y) ? U[(int64_t)x * cb + y] : U[(int64_t)y * cb + x];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (ra[j] < 0 || rc[j] < 0) continue;
+        if (ra[j] < s) {
+          if (rc[j] < s) S[ra[j] * LD + rc[j]] += v[j];
+          else Bs[ra[j] * LD + (rc[j] - s)] += v[j];
+        } else if (rc[j] >= s) {
+          Cs[(ra[j] - s) * LD + (rc[j] - s)] += v[j];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  tile_factor_in_smem<double>(S, X, Wsc, rdiag, rpiv, s, tid, info);
+  // The four small products below use the register tiling of the elimination: thread (tr, tc) owns the 4 x 4
+  // interleaved outputs {tr + 16 u} x {tc + 16 v}, i.e. 16 independent FMA chains per thread over the 64-deep inner
+  // dimension (a single chain per output ran at the FMA latency: 3x slower than the tile factorisation itself).
+  // Rows / columns beyond s or b are padding (identity / zero) and are masked at the stores.
+  const int tr = tid >> 4, tc = tid & 15;
+  double acc[4][4];
+  // A^-1 = X^T X -> Wsc and global
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+  // (inner dimension: rows k >= s of X are the identity padding and contribute nothing to outputs r, c < s; the
+  //  16 x 16 output blocks with u >= nu or v >= nu lie entirely in the padding and are skipped)
+  const int nu = (s + 15) >> 4, nvb = (b + 15) >> 4;
+#pragma unroll 4
+  for (int k = 0; k < s; ++k) {
+    double xr[4], xc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xr[u] = X[k * LD + tr + 16 * u];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) xc[v] = X[k * LD + tc + 16 * v];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (u < nu) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (v < nu) acc[u][v] = fma(xr[u], xc[v], acc[u][v]);
+      }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int r = tr + 16 * u, c = tc + 16 * v;
+      Wsc[r * LD + c] = (r < s && c < s) ? acc[u][v] : 0.0;
+      if (r < s && c < s) Ainv[(int64_t)r * s + c] = acc[u][v];
+    }
+  if (b > 0) {
+    // Y = X Bt
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < s; ++k) {
+      double xr[4], bc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xr[u] = X[(tr + 16 * u) * LD + k];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) bc[v] = Bs[k * LD + tc + 16 * v];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < nu) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (v < nvb) acc[u][v] = fma(xr[u], bc[v], acc[u][v]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int r = tr + 16 * u, c = tc + 16 * v;
+        Ys[r * LD + c] = acc[u][v];
+        if (r < s && c < b) Bt[(int64_t)r * b + c] = Bs[r * LD + c];   // coupling block incl. the children's part
+      }
+  }
+  __syncthreads();
+  if (b > 0) {
+    // W = A^-1 Bt
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < s; ++k) {
+      double ar[4], bc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ar[u] = Wsc[(tr + 16 * u) * LD + k];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) bc[v] = Bs[k * LD + tc + 16 * v];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < nu) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (v < nvb) acc[u][v] = fma(ar[u], bc[v], acc[u][v]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int r = tr + 16 * u, c = tc + 16 * v;
+        if (r < s && c < b) Wg[(int64_t)r * b + c] = acc[u][v];
+      }
+    // U = C - Y^T Y, lower triangle
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = Cs[(tr + 16 * u) * LD + tc + 16 * v];
+#pragma unroll 4
+    for (int k = 0; k < s; ++k) {
+      double yx[4], yy[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) yx[u] = Ys[k * LD + tr + 16 * u];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) yy[v] = Ys[k * LD + tc + 16 * v];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < nvb) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (v <= u) acc[u][v] = fma(-yx[u], yy[v], acc[u][v]);   // lower triangle: blocks v <= u only
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int x = tr + 16 * u, y = tc + 16 * v;
+        if (x < b && y <= x) Cout[(int64_t)x * b + y] = acc[u][v];
+      }
+  }
+}
+
+// The pull alone, on global memory, for backends that run the separate steps on a pull level (complex path):
+// (A, Bt, C) of every front of the level += its children's update matrices, children in plan order.
+template <class T>
+__global__ void __launch_bounds__(256)
+pull_children_kernel(FrontFusedArgs a, T* __restrict__ A, T* __restrict__ Bt, const T* __restrict__ Call,
+                     T* __restrict__ Cout) {
+  const int tid = threadIdx.x, f = blockIdx.x, s = a.s, b = a.b;
+  const int g = a.f0 + f;
+  A += (int64_t)f * s * s;
+  Bt += (int64_t)f * s * b;
+  Cout += (int64_t)f * b * b;
+  for (int qc = a.child_ptr[g]; qc < a.child_ptr[g + 1]; ++qc) {
+    const int ch = a.child_ids[qc];
+    const int cb = a.f_b[ch];
+    const T* __restrict__ U = Call + a.f_offC[ch];
+    const int32_t* __restrict__ rel = a.rel + a.f_relOff[ch];
+    for (int q = tid; q < cb * cb; q += 256) {
+      const int x = q / cb, y = q - x * cb;
+      const int ra = rel[x], rc = rel[y];
+      if (ra < 0 || rc < 0) continue;
+      const T v = (x >= y) ? U[(int64_t)x * cb + y] : U[(int64_t)y * cb + x];
+      if (ra < s) {
+        if (rc < s) A[(int64_t)ra * s + rc] = add(A[(int64_t)ra * s + rc], v);
+        else Bt[(int64_t)ra * b + (rc - s)] = add(Bt[(int64_t)ra * b + (rc - s)], v);
+      } else if (rc >= s) {
+        Cout[(int64_t)(ra - s) * b + (rc - s)] = add(Cout[(int64_t)(ra - s) * b + (rc - s)], v);
+      }
+    }
+    __syncthreads();
+  }
 }
 
 template <class T>

@@ -8,7 +8,9 @@
 //
 // Per front f (own block A_f: s x s, coupling Bt_f: s x b = own rows x boundary columns, boundary block C_f: b x b):
 //   bottom-up   A_f = L L^T, Linv;  Y = Linv Bt;  U_f = C_f - Y^T Y  (update matrix, lower triangle valid);
-//               extend-add U_f into the parent's (A, Bt, C) through the relative indices `rel`;
+//               extend-add U_f into the parent's (A, Bt, C) through the relative indices `rel` - pushed by the child
+//               level (one pass per sibling index) or, for levels of small fronts (`pull`), pulled by the parent:
+//               there the whole front step (pull, factorisation, A^-1, Y, U, W) is ONE kernel per level;
 //               right-hand sides: t_f = A_f^-1 r_f,  r[bnd(f)] -= Bt_f^T t_f - only for the ACTIVE fronts (K_0U is zero
 //               away from the electrodes, so most leaves have r = 0, t = 0; their rows sit after row rowsA);
 //   top-down    Sigma_bb(f) gathered from the parent's selected inverse;  V_f = -W_f Sigma_bb  (W = A^-1 Bt);
@@ -44,18 +46,27 @@ void tree_bottom_up(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, 
     T *R = m.R + lv.row0 * nU, *X = m.Xp + lv.row0 * nU;      // rows of the ACTIVE fronts (non-zero right-hand side)
     const int na = lv.na;
     // ---- matrix chain ----
-    k.potrf(0, s, A, Lf, Li, (int)n);
-    k.after(0, 1);
-    if (b > 0) {
-      k.gemm(0, 0, 0, s, b, s, one, Li, s, sA, Bt, b, sB, zero, Y, b, sB, (int)n, 0);          // Y = Linv Bt
-      k.gemm(0, 1, 0, b, b, s, mone, Y, b, sB, Y, b, sB, one, C, b, sC, (int)n, 1);           // U = C - Y^T Y (lower)
+    const bool fused = lv.pull && k.can_fuse();
+    if (fused) {
+      // ONE kernel per level: pull the children's update matrices, factorise, A^-1, Y, U, W (small fronts)
+      k.front_fused(0, t, lv, m.A, m.Bt, m.C, m.Ainv, m.W);
+      k.after(0, 1);
       for (int pass = 0; pass < lv.passes; ++pass) k.extend_add(0, t, lv, pass, C, m.A, m.Bt, m.C);
-    }
-    // ---- right-hand-side chain ----
-    k.gemm(1, 1, 0, s, s, s, one, Li, s, sA, Li, s, sA, zero, Ai, s, sA, (int)n, 0);           // A^-1 = Linv^T Linv
-    if (b > 0) {
-      k.after(1, 2);
-      k.gemm(2, 0, 0, s, b, s, one, Ai, s, sA, Bt, b, sB, zero, W, b, sB, (int)n, 0);          // W = A^-1 Bt
+    } else {
+      if (lv.pull) k.pull_children(0, t, lv, m.A, m.Bt, m.C);
+      k.potrf(0, s, A, Lf, Li, (int)n);
+      k.after(0, 1);
+      if (b > 0) {
+        k.gemm(0, 0, 0, s, b, s, one, Li, s, sA, Bt, b, sB, zero, Y, b, sB, (int)n, 0);        // Y = Linv Bt
+        k.gemm(0, 1, 0, b, b, s, mone, Y, b, sB, Y, b, sB, one, C, b, sC, (int)n, 1);         // U = C - Y^T Y (lower)
+        for (int pass = 0; pass < lv.passes; ++pass) k.extend_add(0, t, lv, pass, C, m.A, m.Bt, m.C);
+      }
+      // ---- right-hand-side chain ----
+      k.gemm(1, 1, 0, s, s, s, one, Li, s, sA, Li, s, sA, zero, Ai, s, sA, (int)n, 0);         // A^-1 = Linv^T Linv
+      if (b > 0) {
+        k.after(1, 2);
+        k.gemm(2, 0, 0, s, b, s, one, Ai, s, sA, Bt, b, sB, zero, W, b, sB, (int)n, 0);        // W = A^-1 Bt
+      }
     }
     if (na > 0) {
       k.gemm(1, 0, 0, s, nU, s, one, Ai, s, sA, R, nU, sX, zero, X, nU, sX, na, 0);            // t = A^-1 r

@@ -6,6 +6,7 @@
 //   * complex f64: the same DMMA kernel structure on split re/im planes (four DMMA chains per complex
 //     tile product); a SIMT FMA tile kernel is kept as a cross-check (force_simt_gemm).
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include "scalar.cuh"
 
@@ -87,16 +88,20 @@ gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A
   // slice of a split-K product runs in the same launch as the full ones
   if ((flags >> 1) != 0 && blockIdx.z == gridDim.z - 1) K = flags >> 1;
   const int lower_only = flags & 1;
+  // vec bit 2: the grid is transposed (blockIdx.x walks the M tiles): consecutive CTAs then share one B tile and
+  // sweep A, which streams the LARGER operand from HBM once when N >> M (batched reconstruction: dV is 192 MB, inv_mat
+  // 7.8 MB - with the N tiles on the fast index every row of tiles re-read dV: 12.3 GB of DRAM reads for 0.2 GB of data)
+  const unsigned tile_n = (vec & 4) ? blockIdx.y : blockIdx.x, tile_m = (vec & 4) ? blockIdx.x : blockIdx.y;
   // symmetric results whose consumers read the lower triangle only (A -= L L^T before a Cholesky):
   // tiles strictly above the block diagonal are skipped
-  if (lower_only && (int)(blockIdx.x * BN) > (int)(blockIdx.y * BM + BM - 1)) return;
+  if (lower_only && (int)(tile_n * BN) > (int)(tile_m * BM + BM - 1)) return;
   constexpr int BK = 16, NT = WM * WN * 32;
   constexpr int SA = SM::SA, SB = SM::SB;
   constexpr int TM = BM / WM, TN = BN / WN, MI = TM / 8, NI = TN / 8;
   extern __shared__ __align__(16) double dsm[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
   const int wm = (warp / WN) * TM, wn = (warp % WN) * TN;
   A += (int64_t)blockIdx.z * sA;
   B += (int64_t)blockIdx.z * sB;
@@ -549,7 +554,11 @@ inline void gemm_dmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int64
   auto vec_ok = [](const double* p, int64_t ld, int64_t stride) {
     return ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (ld % 2 == 0) && (stride % 2 == 0);
   };
-  const int vec = g_gemm_vec ? ((vec_ok(A, lda, sA) ? 1 : 0) | (vec_ok(B, ldb, sB) ? 2 : 0)) : 0;
+  int vec = g_gemm_vec ? ((vec_ok(A, lda, sA) ? 1 : 0) | (vec_ok(B, ldb, sB) ? 2 : 0)) : 0;
+  if (N > M && grid.x <= 65535u && (double)K * (double)N * 8.0 > 32.0e6) {   // B is the big operand: M tiles fastest
+    vec |= 4;
+    grid = dim3(grid.y, grid.x, grid.z);
+  }
 #define CEIT_DMMA_CASE(a, b)                                                                              \
   {                                                                                                       \
     constexpr size_t smem = (size_t)STAGES * DmmaSmem<BM, BN, a, b>::STAGE * sizeof(double);              \
@@ -633,7 +642,8 @@ __global__ void symmetrize_from_lower_kernel(int64_t n, double* __restrict__ A, 
   if (c > r) A[r * lda + c] = A[c * lda + r];
 }
 
-// Number of K slices.  Monotone in K (workspaces are sized with the largest K of a call site).
+// Number of K slices (not monotone in K: a workspace shared by several inner dimensions is sized with
+// splitk_max_slices).
 //  * small outputs (< 384 wide): 32x32 tiles, ~4 CTAs per SM, slices >= 256 deep;
 //  * large outputs whose 64x64 tiles (only those on/below the diagonal when lower_only) cannot fill the chip
 //    (the 400x400-mesh Gram matrix: 136 tiles with K = 257 762; its S_U: 45 tiles with K = 160 000):
@@ -644,11 +654,17 @@ inline int splitk_slices(int64_t M, int64_t N, int64_t K, int lower_only = 0) {
     const int64_t tm = (M + 63) / 64, tn = (N + 63) / 64;
     const int64_t t64 = (lower_only && M == N) ? tm * (tm + 1) / 2 : tm * tn;
     if (t64 >= 444 || K < 8192) return 1;
-    int64_t S = (592 + t64 - 1) / t64;
-    const int64_t maxS = K / 2048;
-    if (S > maxS) S = maxS;
-    if (S > 64) S = 64;
-    return (int)(S < 2 ? 1 : S);
+    // 444 CTAs are resident (148 SMs x 3): pick the slice count whose t64 * S CTAs leave the smallest idle tail in
+    // their last wave (the 400x400 Gram matrix: 136 tiles x 5 slices = 1.53 waves ran at 77 %; x 13 = 3.98 waves)
+    const int64_t maxS = std::min<int64_t>(K / 2048, 32);
+    int64_t best = 1;
+    double best_eff = 0.0;
+    for (int64_t S = 2; S <= maxS; ++S) {
+      const int64_t ctas = t64 * S, waves = (ctas + 443) / 444;
+      const double eff = (double)ctas / (double)(waves * 444);
+      if (eff > best_eff + 0.02) { best_eff = eff; best = S; }      // prefer fewer slices unless clearly better
+    }
+    return (int)best;
   }
   const int64_t tiles = ((M + 31) / 32) * ((N + 31) / 32);
   if (K < 1024 || tiles >= 296) return 1;
@@ -657,6 +673,12 @@ inline int splitk_slices(int64_t M, int64_t N, int64_t K, int lower_only = 0) {
   if (S > maxS) S = maxS;
   if (S > 64) S = 64;
   return (int)(S < 2 ? 1 : S);
+}
+
+// upper bound of splitk_slices over every inner dimension <= Kmax
+inline int splitk_max_slices(int64_t M, int64_t N, int64_t Kmax) {
+  const int64_t cap = splitk_large(M, N) ? std::min<int64_t>(Kmax / 2048, 32) : std::min<int64_t>(Kmax / 256, 64);
+  return (int)std::max<int64_t>(cap, 1);
 }
 
 // workspace: at least splitk_slices(M, N, K, lower_only) * M * N doubles (ignored when no split is used).

@@ -155,12 +155,13 @@ __global__ void pad_diag_list_kernel(int64_t n, const int64_t* __restrict__ dst,
 // launch touch the same entry: no atomics, bitwise reproducible.  blockIdx.y = front of the level.
 template <class T>
 __global__ void __launch_bounds__(256)
-extend_add_kernel(int b, int pass, const int32_t* __restrict__ sib, const int64_t* __restrict__ pA,
+extend_add_kernel(int b, int pass, const uint8_t* __restrict__ push, const int32_t* __restrict__ sib,
+                  const int64_t* __restrict__ pA,
                   const int64_t* __restrict__ pB, const int64_t* __restrict__ pC, const int32_t* __restrict__ ps,
                   const int32_t* __restrict__ pb, const int32_t* __restrict__ rel, const T* __restrict__ U,
                   T* __restrict__ A, T* __restrict__ Bt, T* __restrict__ C) {
   const int f = blockIdx.y;
-  if (sib[f] != pass || pA[f] < 0) return;
+  if (sib[f] != pass || pA[f] < 0 || !push[f]) return;   // fronts whose parent level pulls do not push
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= b * b) return;
   const int a = q / b, c = q - a * b;

@@ -41,13 +41,13 @@ void bfs_levels(const std::vector<int32_t>& rowptr, const std::vector<int32_t>& 
   }
 }
 
-void build_tree_plan(HostPlan& p, int64_t leaf_cap);
+void build_tree_plan(HostPlan& p, int64_t leaf_cap, bool allow_pull);
 
 }  // namespace
 
 void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
                      const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
-                     int64_t target_block, int64_t nd_interior, bool nd_tree) {
+                     int64_t target_block, int64_t nd_interior, bool nd_tree, bool nd_pull) {
   if (N <= 0 || E <= 0 || L <= 0) throw std::runtime_error("plan: N, E, L must be positive");
   if (N > (int64_t)2000000000 / 16 || E > (int64_t)2000000000 / 16)
     throw std::runtime_error("plan: mesh too large for 32-bit indices");
@@ -173,7 +173,7 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
     for (int64_t q = 0; q < 9 * E; ++q) p.src[fill[slot_of[q]]++] = (int32_t)q;  // ascending element order
   }
   if (nd_tree && nd_interior > 0 && p.N0 > std::max<int64_t>(nd_interior, 8)) {
-    build_tree_plan(p, std::min<int64_t>(nd_interior, 64));
+    build_tree_plan(p, std::min<int64_t>(nd_interior, 64), nd_pull);
     return;
   }
   // ---- level 1 (nested dissection): geometric boxes -> interiors I_p (<= 64 nodes, mutually
@@ -588,7 +588,7 @@ struct TreeBuilder {
   }
 };
 
-void build_tree_plan(HostPlan& p, int64_t leaf_cap) {
+void build_tree_plan(HostPlan& p, int64_t leaf_cap, bool allow_pull) {
   const int64_t N = p.N, E = p.E;
   TreeBuilder tb(p, leaf_cap);
   {
@@ -774,6 +774,30 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap) {
         t.rel[q] = (owner[w] == pg) ? slot[w] : (int32_t)(t.ps[g] + bidx(pg, w));
       }
     }
+  }
+  // pull levels (small fronts) and the child lists they read; children of a pulling parent do not push
+  for (int32_t l = 0; l < H; ++l) t.lv[l].pull = (allow_pull && t.lv[l].s <= 64 && t.lv[l].b <= 64) ? 1 : 0;
+  t.child_ptr.assign(nF + 1, 0);
+  t.f_b.assign(nF, 0);
+  t.f_offC.assign(nF, 0);
+  t.f_relOff.assign(nF, 0);
+  t.push.assign(nF, 0);
+  for (int32_t g = 0; g < nF; ++g) t.child_ptr[g + 1] = t.child_ptr[g] + (int32_t)tb.children[old_of[g]].size();
+  t.child_ids.resize(t.child_ptr[nF]);
+  for (int32_t g = 0; g < nF; ++g) {
+    const auto& kids = tb.children[old_of[g]];
+    for (size_t k = 0; k < kids.size(); ++k) t.child_ids[t.child_ptr[g] + (int32_t)k] = gid[kids[k]];
+    const TreeLevel& lv = t.lv[level_of[g]];
+    t.f_b[g] = lv.b;
+    t.f_offC[g] = blockC(g);
+    t.f_relOff[g] = lv.offR + (int64_t)(g - lv.f0) * lv.b;
+    t.push[g] = (par[g] >= 0 && !t.lv[level_of[par[g]]].pull) ? 1 : 0;
+  }
+  for (int32_t l = 0; l < H; ++l) {               // extend-add passes of a level: only for the fronts that push
+    TreeLevel& lv = t.lv[l];
+    lv.passes = 0;
+    for (int32_t k = 0; k < lv.n; ++k)
+      if (t.push[lv.f0 + k]) lv.passes = std::max(lv.passes, t.sib[lv.f0 + k] + 1);
   }
   // right-hand-side scatter lists per level (destination-major, deterministic source order)
   t.rc_ptr.assign(1, 0);

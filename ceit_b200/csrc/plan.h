@@ -23,6 +23,10 @@ struct TreeLevel {
   int64_t offA = 0, offB = 0, offC = 0;   // element offsets of the level in the (n s s) / (n s b) / (n b b) storages
   int64_t offR = 0;                  // offset of the level in rel / bnd_row (n b entries)
   int64_t rc0 = 0, rc_n = 0;         // destinations of the level's right-hand-side scatter: rc_dst[rc0 .. rc0 + rc_n)
+  int32_t pull = 0;                  // 1: the fronts of this level PULL their children's update matrices (child lists,
+                                     // children in fixed order: deterministic) - small fronts (s <= 64, b <= 64), where
+                                     // pull + factorisation + Y / U / A^-1 / W run as ONE kernel per level; 0: the
+                                     // children push (extend-add passes at the child's level)
 };
 struct TreePlan {
   int32_t H = 0;                     // levels, 0 = leaves
@@ -39,6 +43,12 @@ struct TreePlan {
   // right-hand-side scatter, destination-major: R[rc_dst[q], :] -= sum_s G[rc_src[s], :], s in rc_ptr[q .. q+1)
   std::vector<int32_t> rc_dst, rc_ptr, rc_src;
   std::vector<int64_t> pad_diag;     // A-storage offsets of the diagonal entries of the padding slots (set to 1)
+  // pull lists: children of front g = child_ids[child_ptr[g] .. child_ptr[g + 1]); per front (as a child): padded
+  // boundary size of its level, offset of its C block, offset of its rel list, and whether it pushes (parent level
+  // does not pull)
+  std::vector<int32_t> child_ptr, child_ids, f_b;
+  std::vector<int64_t> f_offC, f_relOff;
+  std::vector<uint8_t> push;
 };
 
 struct HostPlan {
@@ -100,6 +110,6 @@ void build_patches(HostPlan& p, int32_t node_cap, int32_t elem_cap);
 // Throws std::runtime_error on invalid input.
 void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
                      const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
-                     int64_t target_block, int64_t nd_interior, bool nd_tree = false);
+                     int64_t target_block, int64_t nd_interior, bool nd_tree = false, bool nd_pull = true);
 
 }  // namespace ceit

@@ -206,6 +206,11 @@ int ceit_debug_tile_clocks(int64_t* out8);
  *   "gemm_tile"         force the CTA tile of the DMMA GEMM (32 / 64 / 128, 0 = automatic)
  *   "gemm_vec"          (default 1) stage the GEMM operands with 16-byte cp.async when base / leading dimension /
  *                       batch stride are even; 0 = always 8-byte copies
+ *   "nd_pull"           (default 0) plans created afterwards: levels of small fronts (own <= 64, boundary <= 64) pull
+ *                       their children's update matrices, which lets the whole front step run as one kernel per level
+ *                       (measured slower than the separate chip-wide launches on MESH_50_50: one SM per front)
+ *   "no_front_kernel"   1: run pull levels as pull_children_kernel + the separate factorisation / GEMM steps (what
+ *                       the complex path always does; test coverage)
  *   "nd_tree"           (default 1) multi-level nested dissection of the base stage for plans created afterwards;
  *                       0 = one level of interiors + block-tridiagonal separator chain (round-1 ordering)
  *   "gemm_min_ctas64"   automatic tile choice: 64x64 tiles when they give at least this many CTAs, else 32x32

@@ -57,12 +57,56 @@ struct HostBK {
         }
     }
   }
+  bool fuse = true;
+  bool can_fuse() const { return fuse; }
+  // parent-side pull of the children's update matrices into (A, Bt, C) of every front of the level
+  void pull_children(int, const TreePlan& t, const TreeLevel& lv, double* A, double* Bt, double* C) {
+    const int64_t s = lv.s, b = lv.b;
+    for (int32_t f = 0; f < lv.n; ++f) {
+      const int32_t g = lv.f0 + f;
+      double *a_ = A + lv.offA + (int64_t)f * s * s, *bt = Bt + lv.offB + (int64_t)f * s * b;
+      double* c_ = C + lv.offC + (int64_t)f * b * b;
+      for (int32_t q = t.child_ptr[g]; q < t.child_ptr[g + 1]; ++q) {
+        const int32_t ch = t.child_ids[q];
+        const int64_t cb = t.f_b[ch];
+        const double* u = C + t.f_offC[ch];
+        const int32_t* rel = t.rel.data() + t.f_relOff[ch];
+        for (int64_t x = 0; x < cb; ++x)
+          for (int64_t y = 0; y < cb; ++y) {
+            const int64_t ra = rel[x], rc = rel[y];
+            if (ra < 0 || rc < 0) continue;
+            const double v = (x >= y) ? u[x * cb + y] : u[y * cb + x];
+            if (ra < s) {
+              if (rc < s) a_[ra * s + rc] += v;
+              else bt[ra * b + (rc - s)] += v;
+            } else if (rc >= s) {
+              c_[(ra - s) * b + (rc - s)] += v;
+            }
+          }
+      }
+    }
+  }
+  // the fused front step of a pull level, with the same outputs as the CUDA kernel: A^-1, W, U (in C, lower) and
+  // the updated Bt; L / Linv are not kept
+  void front_fused(int, const TreePlan& t, const TreeLevel& lv, double* A, double* Bt, double* C, double* Ainv,
+                   double* W) {
+    const int64_t s = lv.s, b = lv.b, n = lv.n;
+    pull_children(0, t, lv, A, Bt, C);
+    std::vector<double> L(n * s * s, 0.0), X(n * s * s, 0.0), Y(std::max<int64_t>(n * s * b, 1), 0.0);
+    potrf(0, s, A + lv.offA, L.data(), X.data(), (int)n);
+    gemm(0, 1, 0, s, s, s, 1.0, X.data(), s, s * s, X.data(), s, s * s, 0.0, Ainv + lv.offA, s, s * s, (int)n, 0);
+    if (b > 0) {
+      gemm(0, 0, 0, s, b, s, 1.0, X.data(), s, s * s, Bt + lv.offB, b, s * b, 0.0, Y.data(), b, s * b, (int)n, 0);
+      gemm(0, 1, 0, b, b, s, -1.0, Y.data(), b, s * b, Y.data(), b, s * b, 1.0, C + lv.offC, b, b * b, (int)n, 1);
+      gemm(0, 0, 0, s, b, s, 1.0, Ainv + lv.offA, s, s * s, Bt + lv.offB, b, s * b, 0.0, W + lv.offB, b, s * b, (int)n, 0);
+    }
+  }
   void extend_add(int, const TreePlan& t, const TreeLevel& lv, int pass, const double* U, double* A, double* Bt,
                   double* C) {
     const int64_t b = lv.b;
     for (int32_t f = 0; f < lv.n; ++f) {
       const int32_t g = lv.f0 + f;
-      if (t.sib[g] != pass || t.parent[g] < 0) continue;
+      if (t.sib[g] != pass || t.parent[g] < 0 || !t.push[g]) continue;
       const int32_t* rel = t.rel.data() + lv.offR + (int64_t)f * b;
       const double* u = U + (int64_t)f * b * b;
       const int64_t ps = t.ps[g], pb = t.pb[g];
@@ -130,10 +174,12 @@ const char* nd_host_last_error() { return g_msg.c_str(); }
 // an electrode node).  Any output pointer may be NULL (info first to size the others).
 int nd_host_check(const double* nodes, const int64_t* elem, int64_t N, int64_t E, const int64_t* el_ptr,
                   const int64_t* el_elems, int64_t L, int64_t leaf_cap, const double* K, int64_t* info, int64_t* pos,
-                  int64_t* U, double* X, double* SU, double* g0) {
+                  int64_t* U, double* X, double* SU, double* g0, int mode) {
+  // mode: 0 = pull levels run the fused front step, 1 = pull levels run pull + the separate steps (the complex path of
+  // the CUDA backend), 2 = plan without pull levels (children push everywhere)
   try {
     HostPlan h;
-    build_host_plan(h, nodes, elem, N, E, el_ptr, el_elems, L, 0, leaf_cap, /*nd_tree=*/true);
+    build_host_plan(h, nodes, elem, N, E, el_ptr, el_elems, L, 0, leaf_cap, /*nd_tree=*/true, /*nd_pull=*/mode != 2);
     if (!h.use_tree) throw std::runtime_error("mesh too small for the tree plan");
     const TreePlan& t = h.tree;
     int64_t smax = 0, bmax = 0;
@@ -141,6 +187,9 @@ int nd_host_check(const double* nodes, const int64_t* elem, int64_t N, int64_t E
     if (info) {
       info[0] = h.nU; info[1] = h.N0; info[2] = t.H; info[3] = t.nF; info[4] = h.N0P; info[5] = smax; info[6] = bmax;
       info[7] = 0;
+      int64_t npull = 0;
+      for (auto& lv : t.lv) npull += lv.pull;
+      info[6] = bmax + 100000 * npull;           // packed: number of pull levels in the upper digits
     }
     if (pos) for (int64_t v = 0; v < N; ++v) pos[v] = h.pos[v];
     if (U) for (int64_t u = 0; u < h.nU; ++u) U[u] = h.U[u];
@@ -168,6 +217,7 @@ int nd_host_check(const double* nodes, const int64_t* elem, int64_t N, int64_t E
     m.A = A.data(); m.Lf = Lf.data(); m.Linv = Li.data(); m.Ainv = Ai.data(); m.Bt = Bt.data(); m.W = W.data();
     m.SigPP = Sel.data(); m.V = Sel.data() + t.szA; m.C = C.data(); m.R = R.data(); m.Xp = Xp.data(); m.G = G.data();
     HostBK bk;
+    bk.fuse = (mode == 0);
     tree_bottom_up<double>(t, nU, m, bk, 1.0, 0.0, -1.0);
     // S_U = K_UU - r^T t (the swept right-hand sides against t = A^-1 r, all levels at once)
     for (int64_t a = 0; a < nU; ++a)

@@ -299,3 +299,39 @@ def test_dgemm_vector_staging_edges(torch_cuda, tile):
                         assert C[:, N].abs().max().item() == 0.0
     finally:
         _lib.set_option("gemm_tile", 0)
+
+
+@pytest.mark.parametrize("tag", ["21_21", "50_50"])
+def test_front_step_variants_agree(torch_cuda, golden, tag):
+    """The three schedules of the multi-level base stage - children pushing their update matrices (default), fused
+    front kernel on pull levels (nd_pull = 1), pull kernel + separate steps (what the complex path runs on a pull
+    plan) - give the same Jacobian, and each matches the reference."""
+    t = torch_cuda
+    m, r = golden(tag)
+    E, L = len(m["elem"]), 16
+    omega = 2 * np.pi * float(r["signal_frequency"])
+    perm = t.tensor(m["elem_perm"], device="cuda")
+    var = t.zeros(E, dtype=t.float64, device="cuda")
+    outs = []
+    for opts in ({}, {"nd_pull": 1}, {"nd_pull": 1, "no_front_kernel": 1}):
+        for k, v in opts.items():
+            _lib.set_option(k, v)
+        try:
+            p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"])
+            assert p.tree_levels >= 3
+            p.assemble(perm, var, omega)
+            p.factor(False)
+            J = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
+            p.jacobian_block(0, L, 0, E, 1e-3, omega, J, E)
+            assert p.numeric_flag() == 0
+            outs.append(J.cpu().numpy())
+            p.close()
+        finally:
+            for k in opts:
+                _lib.set_option(k, 0)
+    for Jh in outs:
+        for k, (i, j) in enumerate(r["sample_pairs"]):
+            assert np.abs(Jh[_rows(i, L), j] - r["sample_cols"][k]).max() < RAW_TOL
+        if "JAC" in r:
+            assert np.abs(Jh - r["JAC"]).max() < RAW_TOL
+    assert np.abs(outs[0] - outs[1]).max() < 1e-12 and np.abs(outs[0] - outs[2]).max() < 1e-12

@@ -18,7 +18,7 @@ SYMBOLS = [
     "ceit_plan_info", "ceit_plan_tables", "ceit_plan_patches", "ceit_assemble", "ceit_factor", "ceit_jacobian_block",
     "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm", "ceit_plan_csr_values",
     "ceit_set_option", "ceit_stage_times", "ceit_gram_partial", "ceit_inverse_from_gram", "ceit_debug_tile_clocks", "ceit_zgemm",
-    "ceit_center_of_position", "ceit_plan_generation", "ceit_plan_numeric_flag", "ceit_stage_flops",
+    "ceit_center_of_position", "ceit_plan_generation", "ceit_plan_numeric_flag", "ceit_stage_flops", "ceit_mesh_model",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
     L.ceit_plan_csr_values.argtypes = [c_vp, c_vp, c_vp]
     L.ceit_stage_times.argtypes = [c_vp, c_vp]
     L.ceit_stage_flops.argtypes = [c_vp]
+    L.ceit_mesh_model.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp]
     L.ceit_gram_partial.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_vp]
     L.ceit_inverse_from_gram.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp]
     L.ceit_plan_generation.argtypes = [c_vp]
@@ -318,6 +319,37 @@ def reconstruct(inv, dV, out=None):
         out = torch.empty((n_det,) if dV.dim() == 1 else (n_det, F), dtype=torch.float64, device=inv.device)
     check(lib().ceit_reconstruct(tptr(inv), tptr(dV), tptr(out), n_det, m, F, stream_ptr()))
     return out
+
+
+def cuda_available():
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return False
+
+
+def mesh_model(nodes, elem, centers, radius, det_bound):
+    """Device mesh model: (elem_param f64[E,9], electrode element lists, detection_index i64[n_det]) from host
+    arrays (MeshObj.initialize_parameters / calc_electrode_elements / calc_detection_elements in one kernel)."""
+    torch = require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nodes_d = torch.from_numpy(np.ascontiguousarray(nodes, dtype=np.float64)).to(dev)
+    elem_d = torch.from_numpy(np.ascontiguousarray(elem, dtype=np.int64)).to(dev)
+    N, E = nodes_d.shape[0], elem_d.shape[0]
+    cen = np.ascontiguousarray(np.asarray(centers, dtype=np.float64).reshape(-1, 2))
+    L = cen.shape[0]
+    cen_d = torch.from_numpy(cen).to(dev)
+    param = torch.empty((E, 9), dtype=torch.float64, device=dev)
+    in_el = torch.empty((max(L, 1), E), dtype=torch.uint8, device=dev)
+    in_det = torch.empty(E, dtype=torch.uint8, device=dev)
+    check(lib().ceit_mesh_model(tptr(nodes_d), tptr(elem_d), N, E, tptr(cen_d), L, float(radius), float(det_bound),
+                                tptr(param), tptr(in_el), tptr(in_det), stream_ptr()))
+    pairs = torch.nonzero(in_el[:L]).cpu().numpy()            # (electrode, element), lexicographic = ascending lists
+    counts = np.bincount(pairs[:, 0], minlength=L) if L else np.zeros(0, np.int64)
+    lists = np.split(pairs[:, 1], np.cumsum(counts)[:-1]) if L else []
+    det_idx = torch.nonzero(in_det).reshape(-1).cpu().numpy()
+    return param.cpu().numpy(), [x.astype(np.int64) for x in lists], det_idx.astype(np.int64)
 
 
 def center_of_position(maps, cx, cy, frac=0.9, out=None):

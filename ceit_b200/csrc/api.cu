@@ -168,6 +168,7 @@ struct ceit_plan {
   void *tmpPanel = nullptr, *g0e = nullptr, *tmpT = nullptr, *tmpPanel2 = nullptr, *Ptmp2 = nullptr;
   void *Aint = nullptr, *Lint = nullptr, *LintInv = nullptr, *Ainv = nullptr, *Bt = nullptr, *Wn = nullptr;
   void *Tm = nullptr, *G1 = nullptr;
+  void *tAct = nullptr, *YP = nullptr;   // Y_T through a second backward sweep: t of the active rows, padded Y_T
   void *Mreg = nullptr, *LT = nullptr, *LinvT = nullptr, *Tinv = nullptr, *te = nullptr, *YT = nullptr, *ye = nullptr;
   double* d_gamma = nullptr;
   void* splitk_ws = nullptr;
@@ -295,6 +296,19 @@ int upload_plan(ceit_plan* p) {
   return 0;
 }
 
+inline bool rank_update_shape_ok(const HostPlan& h) {
+  return h.u_contiguous && h.bp <= 64 && h.nU <= 1024 && h.nU > h.bp;
+}
+inline bool use_rank_update(const ceit_plan* p) { return !g_direct_excitation && rank_update_shape_ok(p->h); }
+// Y_T = Xh T as a second backward sweep over the elimination forest instead of an N x nU x nU product: pays when the
+// product is large (400x400: 9.5e10 flops = 3.2 ms against ~1 ms of sweep); "yt_sweep" = 0 / 1 forces it off / on
+int g_yt_sweep = -1;
+inline bool yt_by_sweep(const ceit_plan* p) {
+  if (!p->h.use_tree || !use_rank_update(p)) return false;
+  if (g_yt_sweep >= 0) return g_yt_sweep != 0;
+  return 2.0 * (double)p->h.N * (double)p->h.nU * (double)p->h.nU > 2.0e10;
+}
+
 // workspaces are never (re)allocated while the caller's stream is being captured: cudaFree / cudaMalloc are not
 // capturable and a replay would not redo them.  The caller runs the sequence eagerly once first.
 inline int refuse_alloc_in_capture(cudaStream_t st, const char* what) {
@@ -317,7 +331,7 @@ int alloc_numeric(ceit_plan* p, cudaStream_t st) {
   void** bufs[] = {&p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
                    &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->tmpT, &p->tmpPanel2, &p->Ptmp2, &p->g0e, &p->Aint, &p->Lint,
                    &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1, &p->XP, &p->Mreg, &p->LT,
-                   &p->LinvT, &p->Tinv, &p->te, &p->YT, &p->ye, &p->splitk_ws, &p->g1e};
+                   &p->LinvT, &p->Tinv, &p->te, &p->YT, &p->ye, &p->splitk_ws, &p->g1e, &p->tAct, &p->YP};
   for (auto b : bufs) dev_free_tracked(p, *b);
   // excitation workspace depends on the type too
   void** ex[] = {&p->St, &p->Ls, &p->Linvs, &p->Sinv, &p->Yh, &p->phi0, &p->tvec, &p->tmpS,
@@ -357,6 +371,10 @@ int alloc_numeric(ceit_plan* p, cudaStream_t st) {
   if ((rc = dev_alloc(p, &p->ye, h.N * es))) return rc;
   if (!p->d_gamma && (rc = dev_alloc(p, (void**)&p->d_gamma, sizeof(double)))) return rc;
   if ((rc = dev_alloc(p, &p->g1e, 6 * h.E * es))) return rc;
+  if (yt_by_sweep(p)) {
+    if ((rc = dev_alloc(p, &p->tAct, h.tree.rowsA * h.nU * es))) return rc;
+    if ((rc = dev_alloc(p, &p->YP, h.N0P * h.nU * es))) return rc;
+  }
   if ((rc = dev_alloc(p, &p->splitk_ws, (size_t)splitk_max_slices(h.nU, h.nU, h.N0P) * h.nU * h.nU * sizeof(double)))) return rc;
   if ((rc = dev_alloc(p, &p->KUU, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->SU, h.nU * h.nU * es))) return rc;
@@ -440,11 +458,6 @@ inline SideLane* inv_lane() {
   return lane.init() == cudaSuccess ? &lane : nullptr;
 }
 
-inline bool rank_update_shape_ok(const HostPlan& h) {
-  return h.u_contiguous && h.bp <= 64 && h.nU <= 1024 && h.nU > h.bp;
-}
-inline bool use_rank_update(const ceit_plan* p) { return !g_direct_excitation && rank_update_shape_ok(p->h); }
-
 // excitation-independent part of the element blocks for the low-rank Woodbury kernel (real path only)
 inline void launch_g1(ceit_plan* p, const double* g0e, const double* YT, const double* Xh, cudaStream_t st) {
   const HostPlan& h = p->h;
@@ -509,7 +522,15 @@ int base_tail(ceit_plan* p, cudaStream_t st, cudaStream_t sr, cudaStream_t s_t) 
   if (use_rank_update(p)) {
     T *Tinv = (T*)p->Tinv, *YT = (T*)p->YT, *ye = (T*)p->ye;
     CEIT_AFTER(s_t, sr);
-    gemm<T>(sr, 0, 0, h.N, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);                 // Y_T = Xh T
+    if (yt_by_sweep(p)) {
+      // the padded Y_T rows come from the second backward sweep (factor_impl); rows of U: Xh[U] T = -T
+      compact_rows_kernel<T><<<cdiv(h.N0, 8), 256, 0, sr>>>(h.N0, (int)nU, p->d_row_map, (const T*)p->YP, YT);
+      CEIT_COUNT_LAUNCH();
+      negate_copy_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>(nU * nU, Tinv, YT + h.N0 * nU);
+      CEIT_COUNT_LAUNCH();
+    } else {
+      gemm<T>(sr, 0, 0, h.N, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);               // Y_T = Xh T
+    }
     rowsum_e_kernel<T><<<cdiv(h.N, 8), 256, 0, sr>>>(h.N, (int)nU, YT, ye);
     CEIT_COUNT_LAUNCH();
     CEIT_AFTER(sr, st);
@@ -588,6 +609,7 @@ struct CudaTreeBK {
         lv.rc_n, (int)nU, p->d_t_rc_dst + lv.rc0, p->d_t_rc_ptr + lv.rc0, p->d_t_rc_src, G, R);
     CEIT_COUNT_LAUNCH();
   }
+  void zero_rows(int ln, T* ptr, int64_t count) { cudaMemsetAsync(ptr, 0, (size_t)count * sizeof(T), lane[ln]); }
   void rows_gather(int ln, const TreePlan&, const TreeLevel& lv, int64_t nU, const T* Xp, T* G) {
     const int64_t rows = (int64_t)lv.n * lv.b;
     bnd_rows_gather_kernel<T><<<cdiv(rows, 8), 256, 0, lane[ln]>>>(rows, (int)nU, p->d_t_bnd_row + lv.offR, Xp, G);
@@ -679,8 +701,19 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
     if ((rc = base_shared_inverse<T>(p, s_t))) return rc;
     CEIT_AFTER(sr, st);                                   // W of every level, A^-1
     CUDA_TRY(cudaMemcpyAsync(Sel, Ainv, t.szA * es, cudaMemcpyDeviceToDevice, st));
+    const bool yt_sweep = yt_by_sweep(p);
+    if (yt_sweep)                                         // the X sweep overwrites t in place: keep the active rows
+      CUDA_TRY(cudaMemcpyAsync(p->tAct, Xh, t.rowsA * nU * es, cudaMemcpyDeviceToDevice, sr));
     tree_top_down<T>(t, nU, m, bk, one, zero, mone);
     if (bk.rc) return bk.rc;
+    if (yt_sweep) {
+      // Y_T = Xh T without the N x nU x nU product: (t T) over the active rows, then the same backward sweep
+      T *YP = (T*)p->YP, *Tinv = (T*)p->Tinv;
+      CEIT_AFTER(s_t, sr);
+      gemm<T>(sr, 0, 0, t.rowsA, nU, nU, one, (const T*)p->tAct, nU, 0, Tinv, nU, 0, zero, YP, nU, 0);
+      tree_back_sweep<T>(t, nU, Wn, G1, YP, bk, 1, zero, one, mone);
+      if (bk.rc) return bk.rc;
+    }
     if ((rc = base_tail<T>(p, st, sr, s_t))) return rc;
     KERNEL_CHECK();
     p->mode = Sc<T>::is_complex ? 2 : 1;
@@ -1476,6 +1509,19 @@ int ceit_reconstruct(const double* inv, const double* dV, double* out, int64_t n
   return CEIT_OK;
 }
 
+int ceit_mesh_model(const double* nodes, const int64_t* elem, int64_t N, int64_t E, const double* centers, int64_t L,
+                    double radius, double det_bound, double* elem_param, uint8_t* in_electrode, uint8_t* in_detection,
+                    void* stream) {
+  if (!nodes || !elem || (in_electrode && !centers)) CEIT_FAIL(CEIT_ERR_ARG, "ceit_mesh_model: null argument");
+  if (N <= 0 || E <= 0 || L < 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_mesh_model: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  mesh_model_kernel<<<cdiv(E, 256), 256, 0, st>>>(E, (int)L, nodes, elem, centers, radius, det_bound, elem_param,
+                                                  in_electrode, in_detection);
+  CEIT_COUNT_LAUNCH();
+  KERNEL_CHECK();
+  return CEIT_OK;
+}
+
 int ceit_center_of_position(const double* maps, int64_t n_det, int64_t F, const double* cx, const double* cy,
                             double frac, double* out, void* stream) {
   if (!maps || !cx || !cy || !out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_center_of_position: null argument");
@@ -1558,6 +1604,7 @@ int ceit_set_option(const char* name, int64_t value) {
     return CEIT_OK;
   }
   if (std::strcmp(name, "nd_pull") == 0) { g_nd_pull = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "yt_sweep") == 0) { g_yt_sweep = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "no_front_kernel") == 0) { g_no_front_kernel = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "nd_tree") == 0) {
     g_nd_tree = (int)value;

@@ -102,4 +102,29 @@ void tree_top_down(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, T
   }
 }
 
+// The solution half of the top-down pass on its own, for ANOTHER block of right-hand sides held in `X` (N0P x nU, rows
+// of the active fronts = t, anything elsewhere): x_f = t_f - W_f x[bnd(f)] (t_f = 0 for inactive fronts).
+// Used for Y_T = X T without the N x nU x nU product: (t - W x_bnd) T = (t T) - W (x_bnd T), so the same sweep applied
+// to t T (a product over the few ACTIVE rows only) yields X T for every row.
+template <class T, class BK>
+void tree_back_sweep(const TreePlan& t, int64_t nU, const T* Wall, T* G, T* X, BK& k, int lane, T zero, T one, T mone) {
+  for (int32_t l = t.H - 1; l >= 0; --l) {
+    const TreeLevel& lv = t.lv[l];
+    const int64_t s = lv.s, b = lv.b, n = lv.n;
+    if (n == 0 || s == 0) continue;
+    const int64_t sB = s * b, sX = s * nU, sG = b * nU;
+    const int na = lv.na, ni = (int)n - lv.na;
+    T *Xa = X + lv.row0 * nU, *Xi = X + lv.row0i * nU;
+    if (b == 0) {                                   // roots: x = t (inactive roots: x = 0)
+      if (ni > 0) k.zero_rows(lane, Xi, (int64_t)ni * s * nU);
+      continue;
+    }
+    const T* W = Wall + lv.offB;
+    k.rows_gather(lane, t, lv, nU, X, G);
+    if (na > 0) k.gemm(lane, 0, 0, s, nU, b, mone, W, b, sB, G, nU, sG, one, Xa, nU, sX, na, 0);
+    if (ni > 0)
+      k.gemm(lane, 0, 0, s, nU, b, mone, W + (int64_t)na * sB, b, sB, G + (int64_t)na * sG, nU, sG, zero, Xi, nU, sX, ni, 0);
+  }
+}
+
 }  // namespace ceit

@@ -71,6 +71,38 @@ elem_param_kernel(int E, const double* __restrict__ nodes, const int32_t* __rest
   }
 }
 
+// Mesh model on the device (MeshObj.initialize_parameters / calc_electrode_elements / calc_detection_elements,
+// CEIT/models/mesh.py:41-75,90-113,127-155): per element [A, b0..2, c0..2, xbar, ybar], membership of the closed square
+// of every electrode (centroid test, mesh.py:104-107) and of the open detection square (mesh.py:148-151).  The
+// comparisons use exactly the reference's expressions (centre +- radius against the centroid), so the sets are
+// bit-identical to the host model's; int64 connectivity as MeshObj holds it.
+__global__ void __launch_bounds__(256)
+mesh_model_kernel(int64_t E, int L, const double* __restrict__ nodes, const int64_t* __restrict__ elem,
+                  const double* __restrict__ centers, double radius, double det_bound, double* __restrict__ param,
+                  uint8_t* __restrict__ in_electrode, uint8_t* __restrict__ in_detection) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const double2* nd = reinterpret_cast<const double2*>(nodes);
+  const double2 p0 = nd[elem[3 * e]], p1 = nd[elem[3 * e + 1]], p2 = nd[elem[3 * e + 2]];
+  const double det = (p0.x * (p1.y - p2.y) - p0.y * (p1.x - p2.x)) + (p1.x * p2.y - p2.x * p1.y);
+  const double xb = __dadd_rn(__dadd_rn(p0.x, p1.x), p2.x) / 3.0, yb = __dadd_rn(__dadd_rn(p0.y, p1.y), p2.y) / 3.0;
+  if (param) {
+    double* p = param + 9 * e;
+    p[0] = fabs(det / 2);
+    p[1] = (p1.y - p2.y) / det; p[2] = (p2.y - p0.y) / det; p[3] = (p0.y - p1.y) / det;
+    p[4] = (p2.x - p1.x) / det; p[5] = (p0.x - p2.x) / det; p[6] = (p1.x - p0.x) / det;
+    p[7] = xb; p[8] = yb;
+  }
+  if (in_detection) in_detection[e] = (fabs(xb) < det_bound && fabs(yb) < det_bound) ? 1 : 0;
+  if (in_electrode)
+    for (int m = 0; m < L; ++m) {
+      const double cx = centers[2 * m], cy = centers[2 * m + 1];
+      in_electrode[(int64_t)m * E + e] =
+          (__dadd_rn(cx, radius) >= xb && xb >= __dsub_rn(cx, radius) && __dadd_rn(cy, radius) >= yb &&
+           yb >= __dsub_rn(cy, radius)) ? 1 : 0;
+    }
+}
+
 // CSR values -> dense block storage (diag blocks, sub-diagonal blocks, K0U, KUU), type T.
 template <class T>
 __global__ void __launch_bounds__(256)
@@ -232,6 +264,13 @@ compact_rows_kernel(int64_t N0, int nU, const int32_t* __restrict__ row_map, con
   if (r >= N0) return;
   const T* s = XP + (int64_t)row_map[r] * nU;
   for (int k = lane; k < nU; k += 32) Xh[r * nU + k] = s[k];
+}
+
+// out = -in
+template <class T>
+__global__ void negate_copy_kernel(int64_t n, const T* __restrict__ in, T* __restrict__ out) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) out[q] = neg(in[q]);
 }
 
 // rows [N0, N) of Xh = -I

@@ -4,10 +4,14 @@ Attributes: nodes f64[N,2] (metres), elem int64[E,3], elem_p
 elem_param f64[E,9] = [A, b0,b1,b2, c0,c1,c2, xbar, ybar], electrode_mesh {i: [element ids]},
 detection_index int64[n_det] ascending, detection_elem int64[n_det,3].
 The per-element Python loops with 3x3 np.linalg.inv of the reference (mesh.py:41-75) are closed-form
-vectorised expressions here (agreement ~1e-16 relative); the GPU recomputes the same quantities
-inside the assembly kernel from `nodes` and `elem`.
+expressions here (agreement ~1e-16 relative).  With a CUDA device the three per-element passes - elem_param, the
+electrode element sets and the detection set - run as ONE kernel (`ceit_mesh_model`); the element sets it produces are
+bit-identical to the host expressions below, which remain for hosts without a GPU (mesh preparation such as
+`init_mesh`, the CPU test-suite) - the model is input preparation, not the compute path.
 """
 import numpy as np
+
+from .. import _lib
 
 from ..readmesh import read_mesh_from_csv
 from ..util.utilities import get_config
@@ -33,8 +37,25 @@ class MeshObj(object):
         self.elem_param = np.zeros((np.shape(self.elem)[0], 9))
         for i in range(self.electrode_num):
             self.electrode_mesh[i] = list()
-        self.initialize_parameters()
-        self.calc_detection_elements()
+        self.on_device = False
+        if _lib.cuda_available() and self.electrode_num > 0:
+            self._device_model()
+        else:
+            self.initialize_parameters()
+            self.calc_detection_elements()
+
+    def _device_model(self):
+        """elem_param, electrode element sets and detection set in one kernel launch (ceit_mesh_model)."""
+        param, lists, det_idx = _lib.mesh_model(self.nodes, self.elem, self.electrode_center_list,
+                                                self.electrode_radius, self.config["detection_bound"])
+        self.elem_param = param
+        for i in range(self.electrode_num):
+            if len(lists[i]) == 0:
+                raise Exception("No element is selected, please check the input")       # mesh.py:111-113
+            self.electrode_mesh[i] = [int(e) for e in lists[i]]
+        self.detection_index = det_idx
+        self.detection_elem = np.array(self.elem[det_idx])
+        self.on_device = True
 
     def initialize_parameters(self):
         """elem_param + electrode element sets (mesh.py:41-75)."""

@@ -161,6 +161,18 @@ int ceit_inverse_from_gram(const double* J, int64_t ldJ, int64_t m, const int64_
 int ceit_reconstruct(const double* inv, const double* dV, double* out, int64_t n_det, int64_t m,
                      int64_t F, void* stream);
 
+/* ---- mesh model on the device ------------------------------------------------------------------------------
+ * Replaces the per-element Python loops of MeshObj.initialize_parameters (3x3 np.linalg.inv per element,
+ * CEIT/models/mesh.py:41-75), calc_electrode_elements (mesh.py:90-113) and calc_detection_elements (mesh.py:127-155).
+ * nodes [dev] f64[N*2]; elem [dev] i64[E*3]; centers [dev] f64[L*2] and radius: the electrode squares (metres);
+ * det_bound: half-width of the detection square.  Outputs (each optional): elem_param [dev] f64[E*9] =
+ * [A, b0,b1,b2, c0,c1,c2, xbar, ybar]; in_electrode [dev] u8[L*E]: 1 when the centroid of element e lies in the CLOSED
+ * square of electrode m (row m); in_detection [dev] u8[E]: 1 when |xbar| < det_bound and |ybar| < det_bound.  The
+ * ascending index lists the reference keeps (electrode_mesh, detection_index) are the non-zero positions. */
+int ceit_mesh_model(const double* nodes, const int64_t* elem, int64_t N, int64_t E, const double* centers, int64_t L,
+                    double radius, double det_bound, double* elem_param, uint8_t* in_electrode, uint8_t* in_detection,
+                    void* stream);
+
 /* ---- consumer of the reconstructed maps: centre of position -------------------------------------------
  * Replaces DataPlotter.get_COP (CEIT/datahandler/DataHandler.py:28-56), batched over frames:
  * threshold = frac * max + (1 - frac) * min of a frame (the reference's THRESHOLD_PERCENTAGE = 0.9), then the
@@ -211,6 +223,9 @@ int ceit_debug_tile_clocks(int64_t* out8);
  *                       (measured slower than the separate chip-wide launches on MESH_50_50: one SM per front)
  *   "no_front_kernel"   1: run pull levels as pull_children_kernel + the separate factorisation / GEMM steps (what
  *                       the complex path always does; test coverage)
+ *   "yt_sweep"          -1 (default): Y_T = Xh T by a second backward sweep over the elimination forest when the
+ *                       N x nU x nU product would exceed 2e10 flops; 0 / 1 force the product / the sweep (set before
+ *                       the first ceit_factor of a plan: the sweep needs two extra N0P x nU buffers)
  *   "nd_tree"           (default 1) multi-level nested dissection of the base stage for plans created afterwards;
  *                       0 = one level of interiors + block-tridiagonal separator chain (round-1 ordering)
  *   "gemm_min_ctas64"   automatic tile choice: 64x64 tiles when they give at least this many CTAs, else 32x32

@@ -153,6 +153,7 @@ struct HostBK {
         R[(int64_t)t.rc_dst[q] * nU + c] -= acc;
       }
   }
+  void zero_rows(int, double* ptr, int64_t count) { std::memset(ptr, 0, sizeof(double) * (size_t)count); }
   void rows_gather(int, const TreePlan& t, const TreeLevel& lv, int64_t nU, const double* Xp, double* G) {
     for (int64_t r = 0; r < (int64_t)lv.n * lv.b; ++r) {
       const int32_t src = t.bnd_row[lv.offR + r];
@@ -227,7 +228,27 @@ int nd_host_check(const double* nodes, const int64_t* elem, int64_t N, int64_t E
         SU[a * nU + b] = KUU[a * nU + b] - acc;
       }
     std::memcpy(Sel.data(), Ai.data(), sizeof(double) * t.szA);
+    std::vector<double> tAct(Xp.begin(), Xp.begin() + t.rowsA * nU);       // t of the active rows (the sweep is in place)
     tree_top_down<double>(t, nU, m, bk, 1.0, 0.0, -1.0);
+    // second backward sweep on t T' (T' = a fixed dense nU x nU matrix): must equal X T' on every row
+    {
+      std::vector<double> Tp(nU * nU), YP(N0P * nU, std::nan(""));
+      for (int64_t a = 0; a < nU; ++a)
+        for (int64_t b = 0; b < nU; ++b) Tp[a * nU + b] = 1.0 / (1.0 + (double)((a > b) ? a - b : b - a)) + (a == b ? 2.0 : 0.0);
+      bk.gemm(0, 0, 0, t.rowsA, nU, nU, 1.0, tAct.data(), nU, 0, Tp.data(), nU, 0, 0.0, YP.data(), nU, 0, 1, 0);
+      tree_back_sweep<double>(t, nU, W.data(), G.data(), YP.data(), bk, 1, 0.0, 1.0, -1.0);
+      double worst = 0.0, scale = 0.0;
+      for (int64_t q = 0; q < h.N0; ++q) {
+        const int64_t r = h.row_map[q];
+        for (int64_t b = 0; b < nU; ++b) {
+          double ref = 0.0;
+          for (int64_t a = 0; a < nU; ++a) ref += Xp[r * nU + a] * Tp[a * nU + b];
+          worst = std::max(worst, std::fabs(ref - YP[r * nU + b]));
+          scale = std::max(scale, std::fabs(ref));
+        }
+      }
+      if (!(worst <= 1e-11 * std::max(scale, 1.0))) throw std::runtime_error("second backward sweep differs from X T'");
+    }
     for (int64_t q = 0; q < h.N0; ++q)
       std::memcpy(X + q * nU, Xp.data() + (int64_t)h.row_map[q] * nU, sizeof(double) * nU);
     for (int64_t q = 0; q < 6 * E; ++q) g0[q] = h.g0_off[q] < 0 ? 0.0 : Sel[h.g0_off[q]];

@@ -335,3 +335,66 @@ def test_front_step_variants_agree(torch_cuda, golden, tag):
         if "JAC" in r:
             assert np.abs(Jh - r["JAC"]).max() < RAW_TOL
     assert np.abs(outs[0] - outs[1]).max() < 1e-12 and np.abs(outs[0] - outs[2]).max() < 1e-12
+
+
+def test_shared_inverse_product_by_second_sweep(torch_cuda, golden):
+    """Y_T = Xh T as a second backward sweep over the elimination forest (the default on large meshes) against the
+    N x nU x nU product (the default on small ones): same Jacobian, and the reference's."""
+    t = torch_cuda
+    m, r = golden("50_50")
+    E, L = len(m["elem"]), 16
+    omega = 2 * np.pi * float(r["signal_frequency"])
+    perm = t.tensor(m["elem_perm"], device="cuda")
+    var = t.zeros(E, dtype=t.float64, device="cuda")
+    outs = []
+    for sweep in (0, 1):
+        _lib.set_option("yt_sweep", sweep)
+        try:
+            p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"])
+            for _ in range(2):                                   # twice: buffers are reused across steps
+                p.assemble(perm, var, omega)
+                p.factor(False)
+                J = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
+                p.jacobian_block(0, L, 0, E, 1e-3, omega, J, E)
+            assert p.numeric_flag() == 0
+            outs.append(J.cpu().numpy())
+            p.close()
+        finally:
+            _lib.set_option("yt_sweep", -1)
+    for Jh in outs:
+        for k, (i, j) in enumerate(r["sample_pairs"]):
+            assert np.abs(Jh[_rows(i, L), j] - r["sample_cols"][k]).max() < RAW_TOL
+    assert np.abs(outs[0] - outs[1]).max() < 1e-12
+
+
+def test_mesh_model_on_device_matches_reference_and_host_model(torch_cuda, workspace, golden, tmp_path, monkeypatch):
+    """MeshObj's elem_param / electrode element sets / detection set from ONE kernel (ceit_mesh_model):
+    index sets bit-exact against the reference's MeshObj (goldens) on the shipped meshes and against the host
+    expressions on the 400x400 / 32-electrode mesh; elem_param <= 1e-12 relative."""
+    from ceit_b200.models.mesh import MeshObj
+    for tag in ("21_21", "50_50"):
+        workspace(tag)
+        m, _ = golden(tag)
+        mesh = MeshObj()
+        assert mesh.on_device
+        scale = np.abs(m["elem_param"]).max(axis=0)
+        assert (np.abs(mesh.elem_param - m["elem_param"]) / scale).max() < 1e-12
+        for i, e in enumerate(m["electrodes"]):
+            assert mesh.electrode_mesh[i] == [int(x) for x in e]
+        assert np.array_equal(mesh.detection_index, m["detection_index"])
+        assert np.array_equal(mesh.detection_elem, m["detection_elem"])
+    path = meshgen.make_synthetic_workspace(str(tmp_path / "syn400"), 400, 9)
+    monkeypatch.setenv("CEIT_B200_CONFIG", path)
+    dev_mesh = MeshObj()
+    assert dev_mesh.on_device and dev_mesh.electrode_num == 32
+    monkeypatch.setattr(_lib, "cuda_available", lambda: False)
+    host_mesh = MeshObj()
+    assert not host_mesh.on_device
+    assert np.array_equal(dev_mesh.detection_index, host_mesh.detection_index)
+    assert all(dev_mesh.electrode_mesh[i] == host_mesh.electrode_mesh[i] for i in range(32))
+    scale = np.abs(host_mesh.elem_param).max(axis=0)
+    assert (np.abs(dev_mesh.elem_param - host_mesh.elem_param) / scale).max() < 1e-12
+    # an electrode square that contains no centroid raises the reference's exception text
+    monkeypatch.setattr(_lib, "cuda_available", lambda: True)
+    with pytest.raises(Exception, match="No element is selected"):
+        MeshObj(dev_mesh.mesh_obj, 1, [[10.0, 10.0]], 1e-4)

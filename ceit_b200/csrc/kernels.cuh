@@ -84,7 +84,10 @@ mesh_model_kernel(int64_t E, int L, const double* __restrict__ nodes, const int6
   if (e >= E) return;
   const double2* nd = reinterpret_cast<const double2*>(nodes);
   const double2 p0 = nd[elem[3 * e]], p1 = nd[elem[3 * e + 1]], p2 = nd[elem[3 * e + 2]];
-  const double det = (p0.x * (p1.y - p2.y) - p0.y * (p1.x - p2.x)) + (p1.x * p2.y - p2.x * p1.y);
+  // explicitly rounded products and sums (no FMA contraction): the same roundings as the host expressions of
+  // MeshObj.initialize_parameters, so elem_param agrees bit for bit (det cancels ~1e5 : 1 on a 0.8 m sheet)
+  const double det = __dadd_rn(__dsub_rn(__dmul_rn(p0.x, __dsub_rn(p1.y, p2.y)), __dmul_rn(p0.y, __dsub_rn(p1.x, p2.x))),
+                               __dsub_rn(__dmul_rn(p1.x, p2.y), __dmul_rn(p2.x, p1.y)));
   const double xb = __dadd_rn(__dadd_rn(p0.x, p1.x), p2.x) / 3.0, yb = __dadd_rn(__dadd_rn(p0.y, p1.y), p2.y) / 3.0;
   if (param) {
     double* p = param + 9 * e;

@@ -60,11 +60,12 @@ int g_direct_excitation = 0;
 int g_patch_nodes = 0;   // experiment: override the node cap of the element patches
 int64_t g_nd_interior = 64;   // target nodes per nested-dissection interior / leaf; <= 0 disables the dissection
 int g_nd_tree = 1;            // 1: multi-level nested dissection (factor_tree.h); 0: interiors + block-tridiagonal chain
-int g_nd_pull = 0;            // plans created afterwards: 1 = levels of small fronts pull their children and run the
-                              // fused front kernel.  Measured on MESH_50_50: 25-50 us per level on ONE SM (global-load
-                              // latency chains + FP64 products) against ~32 us for the 5 chip-wide launches it replaces,
-                              // step 0.77 -> 0.82 ms: kept as a tested option, off by default
-int g_no_front_kernel = 0;    // 1: pull levels run pull_children_kernel + the separate steps (test coverage of that path)
+int g_nd_pull = 1;            // plans created afterwards: 1 = every level pulls its children's update matrices (one
+                              // destination-centric launch per level), 0 = children push (one pass per sibling index)
+int g_nd_ways = 4;            // plans created afterwards: 4 = two cuts per front (half as many levels), 2 = one cut
+int g_front_kernel = 0;       // 1: levels of small fronts run the fused front kernel.  Measured on MESH_50_50: 25-50 us
+                              // per level on ONE SM (global-load latency chains + FP64 products) against ~32 us for the
+                              // chip-wide launches it replaces, step 0.77 -> 0.82 ms: a tested option, off by default
 struct StageEv {
   int stage;
   cudaEvent_t a, b;
@@ -188,8 +189,8 @@ struct ceit_plan {
   int32_t *d_t_sib = nullptr, *d_t_ps = nullptr, *d_t_pb = nullptr, *d_t_rel = nullptr, *d_t_bnd_row = nullptr;
   int32_t *d_t_rc_dst = nullptr, *d_t_rc_ptr = nullptr, *d_t_rc_src = nullptr;
   int64_t *d_t_pA = nullptr, *d_t_pB = nullptr, *d_t_pC = nullptr, *d_t_pad = nullptr;
-  int32_t *d_t_child_ptr = nullptr, *d_t_child_ids = nullptr, *d_t_fb = nullptr;
-  int64_t *d_t_foffC = nullptr, *d_t_frelOff = nullptr;
+  int32_t *d_t_child_ptr = nullptr, *d_t_child_ids = nullptr, *d_t_fb = nullptr, *d_t_inv_rel = nullptr;
+  int64_t *d_t_foffC = nullptr, *d_t_frelOff = nullptr, *d_t_finvOff = nullptr;
   uint8_t* d_t_push = nullptr;
   int alloc_mode = 0;
   int64_t generation = 0;   // bumped whenever a numeric / excitation workspace is (re)allocated: graphs captured
@@ -281,6 +282,8 @@ int upload_plan(ceit_plan* p) {
     if ((rc = upload_vec(p, &p->d_t_foffC, t.f_offC))) return rc;
     if ((rc = upload_vec(p, &p->d_t_frelOff, t.f_relOff))) return rc;
     if ((rc = upload_vec(p, &p->d_t_push, t.push))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_inv_rel, t.inv_rel))) return rc;
+    if ((rc = upload_vec(p, &p->d_t_finvOff, t.f_invOff))) return rc;
   }
   if ((rc = upload_vec(p, &p->d_ue_ptr, h.ue_ptr))) return rc;
   if ((rc = upload_vec(p, &p->d_wk, h.wk))) return rc;
@@ -495,8 +498,7 @@ int base_shared_inverse(ceit_plan* p, cudaStream_t s_t) {
     CEIT_COUNT_LAUNCH();
     add_rank1_e_kernel<T><<<cdiv(nU * nU, 256), 256, 0, s_t>>>((int)nU, SU, p->d_gamma, Mreg);
     CEIT_COUNT_LAUNCH();
-    CUDA_TRY(cudaMemsetAsync(LT, 0, nU * nU * es, s_t));
-    CUDA_TRY(cudaMemsetAsync(LinvT, 0, nU * nU * es, s_t));
+    // (LT and LinvT were zeroed at the start of the stage, off this chain)
     potrf_trtri_blocked<T>(s_t, nU, Mreg, nU, 0, LT, nU, 0, LinvT, nU, 0, (T*)p->tmpT, 0, 1, p->d_info,
                            g_multi_stream ? &p->lane_b : nullptr);
     gemm<T>(s_t, 1, 0, nU, nU, nU, one, LinvT, nU, 0, LinvT, nU, 0, zero, Tinv, nU, 0);
@@ -558,9 +560,9 @@ struct CudaTreeBK {
   }
   FrontFusedArgs front_args(const TreeLevel& lv) const {
     return FrontFusedArgs{lv.s, lv.b, lv.f0, p->d_t_child_ptr, p->d_t_child_ids, p->d_t_fb, p->d_t_rel, p->d_t_foffC,
-                          p->d_t_frelOff};
+                          p->d_t_frelOff, p->d_t_inv_rel, p->d_t_finvOff};
   }
-  bool can_fuse() const { return !Sc<T>::is_complex && !g_no_front_kernel; }
+  bool can_fuse() const { return !Sc<T>::is_complex && g_front_kernel; }
   void front_fused(int ln, const TreePlan&, const TreeLevel& lv, T* A, T* Bt, T* C, T* Ainv, T* W) {
     launch_front_fused(ln, lv, A, Bt, C, Ainv, W);
   }
@@ -578,7 +580,10 @@ struct CudaTreeBK {
   }
   void launch_front_fused(int, const TreeLevel&, cd*, cd*, cd*, cd*, cd*) {}   // complex: pull + separate steps
   void pull_children(int ln, const TreePlan&, const TreeLevel& lv, T* A, T* Bt, T* C) {
-    pull_children_kernel<T><<<lv.n, 256, 0, lane[ln]>>>(front_args(lv), A + lv.offA, Bt + lv.offB, C, C + lv.offC);
+    if (lv.f0 == 0 && p->h.tree.child_ptr[lv.n] == 0) return;       // the leaf level has no children
+    const int64_t span = (int64_t)lv.s + lv.b;
+    dim3 grid(cdiv(span * span, 256), lv.n);
+    pull_children_kernel<T><<<grid, 256, 0, lane[ln]>>>(front_args(lv), A + lv.offA, Bt + lv.offB, C, C + lv.offC);
     CEIT_COUNT_LAUNCH();
   }
   void gemm(int ln, int opA, int opB, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t lda, int64_t sA,
@@ -649,6 +654,10 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   CUDA_TRY(cudaMemsetAsync(K0U, 0, (h.use_tree ? h.tree.rowsA : N0P) * nU * es, st));
   CUDA_TRY(cudaMemsetAsync(KUU, 0, nU * nU * es, st));
   CUDA_TRY(cudaMemsetAsync(p->d_info, 0, sizeof(int), st));
+  if (use_rank_update(p)) {      // factors of the shared inverse T: zero-initialised here, off the critical chain
+    CUDA_TRY(cudaMemsetAsync(p->LT, 0, nU * nU * es, st));
+    CUDA_TRY(cudaMemsetAsync(p->LinvT, 0, nU * nU * es, st));
+  }
   if (P > 0 || h.use_tree) {
     CUDA_TRY(cudaMemsetAsync(Aint, 0, h.szPP * es, st));
     CUDA_TRY(cudaMemsetAsync(Lint, 0, h.szPP * es, st));
@@ -1213,7 +1222,7 @@ int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_
   ceit_plan* p = new ceit_plan();
   try {
     build_host_plan(p->h, nodes, elem, N, E, el_ptr, el_elems, L, target_block, g_nd_interior,
-                    g_nd_tree != 0 && target_block <= 0, g_nd_pull != 0);
+                    g_nd_tree != 0 && target_block <= 0, g_nd_pull, g_nd_ways);
     {
       // patches of <= 32 elements whose distinct node rows fit the shared-memory budget
       const bool lr = rank_update_shape_ok(p->h) && !g_direct_excitation && !g_no_lowrank;
@@ -1605,7 +1614,8 @@ int ceit_set_option(const char* name, int64_t value) {
   }
   if (std::strcmp(name, "nd_pull") == 0) { g_nd_pull = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "yt_sweep") == 0) { g_yt_sweep = (int)value; return CEIT_OK; }
-  if (std::strcmp(name, "no_front_kernel") == 0) { g_no_front_kernel = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "front_kernel") == 0) { g_front_kernel = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "nd_ways") == 0) { g_nd_ways = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "nd_tree") == 0) {
     g_nd_tree = (int)value;
     return CEIT_OK;

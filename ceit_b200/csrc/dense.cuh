@@ -285,6 +285,8 @@ struct FrontFusedArgs {
   int s, b, f0;                 // padded sizes of the level, global id of its first front
   const int32_t *child_ptr, *child_ids, *f_b, *rel;
   const int64_t *f_offC, *f_relOff;
+  const int32_t* inv_rel;       // destination-centric pull: parent front index -> boundary slot of the child
+  const int64_t* f_invOff;
 };
 constexpr int FRONT_LD = TILE + 1;
 constexpr size_t FRONT_SMEM = (size_t)(6 * TILE * FRONT_LD + 2 * TILE + 8) * sizeof(double);
@@ -489,36 +491,39 @@ front_fused_kernel(FrontFusedArgs a, double* __restrict__ A, double* __restrict_
   }
 }
 
-// The pull alone, on global memory, for backends that run the separate steps on a pull level (complex path):
-// (A, Bt, C) of every front of the level += its children's update matrices, children in plan order.
+// The pull alone, on global memory (every pull level unless the fused kernel runs it): one thread per DESTINATION entry
+// (ra, rc) of the parent's front index space [0, s + b)^2; it looks the entry up in every child through the inverse
+// relative indices and adds the children's contributions in plan order.  Any number of children in ONE launch, no two
+// threads share a destination: no atomics, bitwise reproducible.  Entries with ra in the boundary and rc in the own
+// block are the mirror of a coupling entry and are not stored.
 template <class T>
 __global__ void __launch_bounds__(256)
 pull_children_kernel(FrontFusedArgs a, T* __restrict__ A, T* __restrict__ Bt, const T* __restrict__ Call,
                      T* __restrict__ Cout) {
-  const int tid = threadIdx.x, f = blockIdx.x, s = a.s, b = a.b;
+  const int f = blockIdx.y, s = a.s, b = a.b, span = s + b;
   const int g = a.f0 + f;
-  A += (int64_t)f * s * s;
-  Bt += (int64_t)f * s * b;
-  Cout += (int64_t)f * b * b;
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (int64_t)span * span) return;
+  const int ra = (int)(q / span), rc = (int)(q - (int64_t)ra * span);
+  if (ra >= s && rc < s) return;
+  T acc = Sc<T>::zero();
+  bool hit = false;
   for (int qc = a.child_ptr[g]; qc < a.child_ptr[g + 1]; ++qc) {
     const int ch = a.child_ids[qc];
+    const int32_t* __restrict__ inv = a.inv_rel + a.f_invOff[ch];
+    const int ia = inv[ra], ic = inv[rc];
+    if (ia < 0 || ic < 0) continue;
     const int cb = a.f_b[ch];
     const T* __restrict__ U = Call + a.f_offC[ch];
-    const int32_t* __restrict__ rel = a.rel + a.f_relOff[ch];
-    for (int q = tid; q < cb * cb; q += 256) {
-      const int x = q / cb, y = q - x * cb;
-      const int ra = rel[x], rc = rel[y];
-      if (ra < 0 || rc < 0) continue;
-      const T v = (x >= y) ? U[(int64_t)x * cb + y] : U[(int64_t)y * cb + x];
-      if (ra < s) {
-        if (rc < s) A[(int64_t)ra * s + rc] = add(A[(int64_t)ra * s + rc], v);
-        else Bt[(int64_t)ra * b + (rc - s)] = add(Bt[(int64_t)ra * b + (rc - s)], v);
-      } else if (rc >= s) {
-        Cout[(int64_t)(ra - s) * b + (rc - s)] = add(Cout[(int64_t)(ra - s) * b + (rc - s)], v);
-      }
-    }
-    __syncthreads();
+    acc = add(acc, (ia >= ic) ? U[(int64_t)ia * cb + ic] : U[(int64_t)ic * cb + ia]);
+    hit = true;
   }
+  if (!hit) return;
+  T* dst;
+  if (ra < s) dst = (rc < s) ? A + ((int64_t)f * s * s + (int64_t)ra * s + rc)
+                             : Bt + ((int64_t)f * s * b + (int64_t)ra * b + (rc - s));
+  else dst = Cout + ((int64_t)f * b * b + (int64_t)(ra - s) * b + (rc - s));
+  *dst = add(*dst, acc);
 }
 
 template <class T>

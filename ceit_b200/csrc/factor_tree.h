@@ -46,7 +46,7 @@ void tree_bottom_up(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, 
     T *R = m.R + lv.row0 * nU, *X = m.Xp + lv.row0 * nU;      // rows of the ACTIVE fronts (non-zero right-hand side)
     const int na = lv.na;
     // ---- matrix chain ----
-    const bool fused = lv.pull && k.can_fuse();
+    const bool fused = lv.fusable && k.can_fuse();
     if (fused) {
       // ONE kernel per level: pull the children's update matrices, factorise, A^-1, Y, U, W (small fronts)
       k.front_fused(0, t, lv, m.A, m.Bt, m.C, m.Ainv, m.W);

@@ -41,13 +41,13 @@ void bfs_levels(const std::vector<int32_t>& rowptr, const std::vector<int32_t>& 
   }
 }
 
-void build_tree_plan(HostPlan& p, int64_t leaf_cap, bool allow_pull);
+void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways);
 
 }  // namespace
 
 void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
                      const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
-                     int64_t target_block, int64_t nd_interior, bool nd_tree, bool nd_pull) {
+                     int64_t target_block, int64_t nd_interior, bool nd_tree, int nd_pull, int nd_ways) {
   if (N <= 0 || E <= 0 || L <= 0) throw std::runtime_error("plan: N, E, L must be positive");
   if (N > (int64_t)2000000000 / 16 || E > (int64_t)2000000000 / 16)
     throw std::runtime_error("plan: mesh too large for 32-bit indices");
@@ -173,7 +173,7 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
     for (int64_t q = 0; q < 9 * E; ++q) p.src[fill[slot_of[q]]++] = (int32_t)q;  // ascending element order
   }
   if (nd_tree && nd_interior > 0 && p.N0 > std::max<int64_t>(nd_interior, 8)) {
-    build_tree_plan(p, std::min<int64_t>(nd_interior, 64), nd_pull);
+    build_tree_plan(p, std::min<int64_t>(nd_interior, 64), nd_pull, nd_ways);
     return;
   }
   // ---- level 1 (nested dissection): geometric boxes -> interiors I_p (<= 64 nodes, mutually
@@ -531,12 +531,9 @@ struct TreeBuilder {
     return (int32_t)own.size() - 1;
   }
   // returns the roots of the forest that covers `set`
-  std::vector<int32_t> dissect(std::vector<int32_t>& set) {
-    if (set.empty()) return {};
-    if ((int64_t)set.size() <= leaf_cap) {
-      std::sort(set.begin(), set.end());
-      return {new_front(std::move(set))};
-    }
+  // One cut of `set` (destroyed) across its longer extent: (separator, lower part, upper part).
+  void cut(std::vector<int32_t>& set, std::vector<int32_t>& sep, std::vector<int32_t>& lower,
+           std::vector<int32_t>& upper) {
     double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
     for (int32_t v : set)
       for (int d = 0; d < 2; ++d) {
@@ -565,21 +562,50 @@ struct TreeBuilder {
     }
     const int32_t st = stamp++;
     for (size_t k = mid; k < set.size(); ++k) mark[set[k]] = st;
-    std::vector<int32_t> sep, lower, upper(set.begin() + mid, set.end());
+    upper.assign(set.begin() + mid, set.end());
     for (size_t k = 0; k < mid; ++k) {
       const int32_t v = set[k];
-      bool cut = false;
-      for (int32_t q = p.rowptr[v]; q < p.rowptr[v + 1] && !cut; ++q) cut = (mark[p.colidx[q]] == st);
-      (cut ? sep : lower).push_back(v);
+      bool is_cut = false;
+      for (int32_t q = p.rowptr[v]; q < p.rowptr[v + 1] && !is_cut; ++q) is_cut = (mark[p.colidx[q]] == st);
+      (is_cut ? sep : lower).push_back(v);
     }
     set.clear();
     set.shrink_to_fit();
-    std::vector<int32_t> kids = dissect(lower);
-    {
-      std::vector<int32_t> k2 = dissect(upper);
+  }
+  // returns the roots of the forest that covers `set`.  ways = 2: one cut per front; ways = 4: both halves are cut
+  // again (across the other direction on a square-ish sub-domain) and the three separators form ONE front with up to
+  // four children - half as many levels on the serial spine of the base stage for a slightly larger dense block.
+  int ways = 2;
+  std::vector<int32_t> dissect(std::vector<int32_t>& set) {
+    if (set.empty()) return {};
+    if ((int64_t)set.size() <= leaf_cap) {
+      std::sort(set.begin(), set.end());
+      return {new_front(std::move(set))};
+    }
+    std::vector<int32_t> sep, lower, upper;
+    cut(set, sep, lower, upper);
+    std::vector<std::vector<int32_t>> parts;
+    if (ways == 4) {
+      for (auto* half : {&lower, &upper}) {
+        if ((int64_t)half->size() > leaf_cap) {
+          std::vector<int32_t> a, b;
+          cut(*half, sep, a, b);                  // its separator joins this front's own set
+          parts.push_back(std::move(a));
+          parts.push_back(std::move(b));
+        } else {
+          parts.push_back(std::move(*half));
+        }
+      }
+    } else {
+      parts.push_back(std::move(lower));
+      parts.push_back(std::move(upper));
+    }
+    std::vector<int32_t> kids;
+    for (auto& part : parts) {
+      std::vector<int32_t> k2 = dissect(part);
       kids.insert(kids.end(), k2.begin(), k2.end());
     }
-    if (sep.empty()) return kids;                 // the halves were not connected: no front, the forest passes up
+    if (sep.empty()) return kids;                 // the parts were not connected: no front, the forest passes up
     std::sort(sep.begin(), sep.end());
     const int32_t f = new_front(std::move(sep));
     for (int32_t c : kids) parent[c] = f;
@@ -588,9 +614,10 @@ struct TreeBuilder {
   }
 };
 
-void build_tree_plan(HostPlan& p, int64_t leaf_cap, bool allow_pull) {
+void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
   const int64_t N = p.N, E = p.E;
   TreeBuilder tb(p, leaf_cap);
+  tb.ways = (ways == 4) ? 4 : 2;
   {
     std::vector<int32_t> all;
     all.reserve(p.N0);
@@ -776,7 +803,12 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, bool allow_pull) {
     }
   }
   // pull levels (small fronts) and the child lists they read; children of a pulling parent do not push
-  for (int32_t l = 0; l < H; ++l) t.lv[l].pull = (allow_pull && t.lv[l].s <= 64 && t.lv[l].b <= 64) ? 1 : 0;
+  // pull_mode 0: children push (extend-add passes at the child's level); 1: every level pulls (one launch per level,
+  // any number of children); levels of small fronts (s, b <= 64) may additionally run the fused front kernel
+  for (int32_t l = 0; l < H; ++l) {
+    t.lv[l].pull = pull_mode ? 1 : 0;
+    t.lv[l].fusable = (pull_mode && t.lv[l].s <= 64 && t.lv[l].b <= 64) ? 1 : 0;
+  }
   t.child_ptr.assign(nF + 1, 0);
   t.f_b.assign(nF, 0);
   t.f_offC.assign(nF, 0);
@@ -792,6 +824,22 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, bool allow_pull) {
     t.f_offC[g] = blockC(g);
     t.f_relOff[g] = lv.offR + (int64_t)(g - lv.f0) * lv.b;
     t.push[g] = (par[g] >= 0 && !t.lv[level_of[par[g]]].pull) ? 1 : 0;
+  }
+  // inverse relative indices for the destination-centric pull: for child ch, position q of the PARENT's front index
+  // space [0, ps + pb) -> boundary slot of ch that maps there, or -1
+  t.f_invOff.assign(nF, 0);
+  if (pull_mode) {
+    for (int32_t g = 0; g < nF; ++g) {
+      t.f_invOff[g] = (int64_t)t.inv_rel.size();
+      if (par[g] < 0) continue;
+      const int64_t span = (int64_t)t.ps[g] + t.pb[g];
+      t.inv_rel.resize(t.inv_rel.size() + span, -1);
+      const TreeLevel& lv = t.lv[level_of[g]];
+      for (int32_t a = 0; a < lv.b; ++a) {
+        const int32_t r = t.rel[t.f_relOff[g] + a];
+        if (r >= 0) t.inv_rel[t.f_invOff[g] + r] = a;
+      }
+    }
   }
   for (int32_t l = 0; l < H; ++l) {               // extend-add passes of a level: only for the fronts that push
     TreeLevel& lv = t.lv[l];

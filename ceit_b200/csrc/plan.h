@@ -23,10 +23,11 @@ struct TreeLevel {
   int64_t offA = 0, offB = 0, offC = 0;   // element offsets of the level in the (n s s) / (n s b) / (n b b) storages
   int64_t offR = 0;                  // offset of the level in rel / bnd_row (n b entries)
   int64_t rc0 = 0, rc_n = 0;         // destinations of the level's right-hand-side scatter: rc_dst[rc0 .. rc0 + rc_n)
-  int32_t pull = 0;                  // 1: the fronts of this level PULL their children's update matrices (child lists,
-                                     // children in fixed order: deterministic) - small fronts (s <= 64, b <= 64), where
-                                     // pull + factorisation + Y / U / A^-1 / W run as ONE kernel per level; 0: the
-                                     // children push (extend-add passes at the child's level)
+  int32_t pull = 0;                  // 1: the fronts of this level PULL their children's update matrices (one launch per
+                                     // level whatever the number of children; children in fixed order: deterministic);
+                                     // 0: the children push (one extend-add pass per sibling index at the child's level)
+  int32_t fusable = 0;               // pull level of small fronts (s <= 64, b <= 64): pull + factorisation + Y / U /
+                                     // A^-1 / W may run as ONE kernel per level (front_fused_kernel)
 };
 struct TreePlan {
   int32_t H = 0;                     // levels, 0 = leaves
@@ -47,7 +48,8 @@ struct TreePlan {
   // boundary size of its level, offset of its C block, offset of its rel list, and whether it pushes (parent level
   // does not pull)
   std::vector<int32_t> child_ptr, child_ids, f_b;
-  std::vector<int64_t> f_offC, f_relOff;
+  std::vector<int64_t> f_offC, f_relOff, f_invOff;
+  std::vector<int32_t> inv_rel;      // per child: parent front index -> boundary slot of the child (-1: none)
   std::vector<uint8_t> push;
 };
 
@@ -110,6 +112,6 @@ void build_patches(HostPlan& p, int32_t node_cap, int32_t elem_cap);
 // Throws std::runtime_error on invalid input.
 void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
                      const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
-                     int64_t target_block, int64_t nd_interior, bool nd_tree = false, bool nd_pull = true);
+                     int64_t target_block, int64_t nd_interior, bool nd_tree = false, int nd_pull = 1, int nd_ways = 4);
 
 }  // namespace ceit

@@ -218,11 +218,14 @@ int ceit_debug_tile_clocks(int64_t* out8);
  *   "gemm_tile"         force the CTA tile of the DMMA GEMM (32 / 64 / 128, 0 = automatic)
  *   "gemm_vec"          (default 1) stage the GEMM operands with 16-byte cp.async when base / leading dimension /
  *                       batch stride are even; 0 = always 8-byte copies
- *   "nd_pull"           (default 0) plans created afterwards: levels of small fronts (own <= 64, boundary <= 64) pull
- *                       their children's update matrices, which lets the whole front step run as one kernel per level
- *                       (measured slower than the separate chip-wide launches on MESH_50_50: one SM per front)
- *   "no_front_kernel"   1: run pull levels as pull_children_kernel + the separate factorisation / GEMM steps (what
- *                       the complex path always does; test coverage)
+ *   "nd_ways"           (default 4) plans created afterwards: cuts per front of the nested dissection - 4 = both halves
+ *                       of a sub-domain are cut again and the three separators form one front with up to four children
+ *                       (half as many levels on the serial spine), 2 = plain bisection
+ *   "nd_pull"           (default 1) plans created afterwards: 1 = every level pulls its children's update matrices in
+ *                       one destination-centric launch, 0 = children push (one extend-add pass per sibling index)
+ *   "front_kernel"      (default 0) 1: pull levels of small fronts (own <= 64, boundary <= 64) run pull +
+ *                       factorisation + A^-1 / Y / U / W as ONE kernel per level (measured slower on MESH_50_50: one
+ *                       SM per front); the complex path always runs the separate steps
  *   "yt_sweep"          -1 (default): Y_T = Xh T by a second backward sweep over the elimination forest when the
  *                       N x nU x nU product would exceed 2e10 flops; 0 / 1 force the product / the sweep (set before
  *                       the first ceit_factor of a plan: the sweep needs two extra N0P x nU buffers)

@@ -59,31 +59,37 @@ struct HostBK {
   }
   bool fuse = true;
   bool can_fuse() const { return fuse; }
-  // parent-side pull of the children's update matrices into (A, Bt, C) of every front of the level
+  // destination-centric pull of the children's update matrices into (A, Bt, C) of every front of the level (the
+  // loop structure of pull_children_kernel: one "thread" per entry of the parent's front index space)
   void pull_children(int, const TreePlan& t, const TreeLevel& lv, double* A, double* Bt, double* C) {
-    const int64_t s = lv.s, b = lv.b;
+    const int64_t s = lv.s, b = lv.b, span = s + b;
     for (int32_t f = 0; f < lv.n; ++f) {
       const int32_t g = lv.f0 + f;
       double *a_ = A + lv.offA + (int64_t)f * s * s, *bt = Bt + lv.offB + (int64_t)f * s * b;
       double* c_ = C + lv.offC + (int64_t)f * b * b;
-      for (int32_t q = t.child_ptr[g]; q < t.child_ptr[g + 1]; ++q) {
-        const int32_t ch = t.child_ids[q];
-        const int64_t cb = t.f_b[ch];
-        const double* u = C + t.f_offC[ch];
-        const int32_t* rel = t.rel.data() + t.f_relOff[ch];
-        for (int64_t x = 0; x < cb; ++x)
-          for (int64_t y = 0; y < cb; ++y) {
-            const int64_t ra = rel[x], rc = rel[y];
-            if (ra < 0 || rc < 0) continue;
-            const double v = (x >= y) ? u[x * cb + y] : u[y * cb + x];
-            if (ra < s) {
-              if (rc < s) a_[ra * s + rc] += v;
-              else bt[ra * b + (rc - s)] += v;
-            } else if (rc >= s) {
-              c_[(ra - s) * b + (rc - s)] += v;
-            }
+      for (int64_t ra = 0; ra < span; ++ra)
+        for (int64_t rc = 0; rc < span; ++rc) {
+          if (ra >= s && rc < s) continue;
+          double acc = 0.0;
+          bool hit = false;
+          for (int32_t q = t.child_ptr[g]; q < t.child_ptr[g + 1]; ++q) {
+            const int32_t ch = t.child_ids[q];
+            const int32_t* inv = t.inv_rel.data() + t.f_invOff[ch];
+            const int64_t ia = inv[ra], ic = inv[rc];
+            if (ia < 0 || ic < 0) continue;
+            const int64_t cb = t.f_b[ch];
+            const double* u = C + t.f_offC[ch];
+            acc += (ia >= ic) ? u[ia * cb + ic] : u[ic * cb + ia];
+            hit = true;
           }
-      }
+          if (!hit) continue;
+          if (ra < s) {
+            if (rc < s) a_[ra * s + rc] += acc;
+            else bt[ra * b + (rc - s)] += acc;
+          } else {
+            c_[(ra - s) * b + (rc - s)] += acc;
+          }
+        }
     }
   }
   // the fused front step of a pull level, with the same outputs as the CUDA kernel: A^-1, W, U (in C, lower) and
@@ -175,12 +181,12 @@ const char* nd_host_last_error() { return g_msg.c_str(); }
 // an electrode node).  Any output pointer may be NULL (info first to size the others).
 int nd_host_check(const double* nodes, const int64_t* elem, int64_t N, int64_t E, const int64_t* el_ptr,
                   const int64_t* el_elems, int64_t L, int64_t leaf_cap, const double* K, int64_t* info, int64_t* pos,
-                  int64_t* U, double* X, double* SU, double* g0, int mode) {
-  // mode: 0 = pull levels run the fused front step, 1 = pull levels run pull + the separate steps (the complex path of
-  // the CUDA backend), 2 = plan without pull levels (children push everywhere)
+                  int64_t* U, double* X, double* SU, double* g0, int mode, int ways) {
+  // mode: 0 = pull plan, fusable levels run the fused front step, 1 = pull plan, separate steps everywhere (default of
+  // the CUDA backend), 2 = push plan (one extend-add pass per sibling index); ways = 2 / 4 cuts per front
   try {
     HostPlan h;
-    build_host_plan(h, nodes, elem, N, E, el_ptr, el_elems, L, 0, leaf_cap, /*nd_tree=*/true, /*nd_pull=*/mode != 2);
+    build_host_plan(h, nodes, elem, N, E, el_ptr, el_elems, L, 0, leaf_cap, /*nd_tree=*/true, /*nd_pull=*/mode != 2 ? 1 : 0, ways);
     if (!h.use_tree) throw std::runtime_error("mesh too small for the tree plan");
     const TreePlan& t = h.tree;
     int64_t smax = 0, bmax = 0;

@@ -303,9 +303,9 @@ def test_dgemm_vector_staging_edges(torch_cuda, tile):
 
 @pytest.mark.parametrize("tag", ["21_21", "50_50"])
 def test_front_step_variants_agree(torch_cuda, golden, tag):
-    """The three schedules of the multi-level base stage - children pushing their update matrices (default), fused
-    front kernel on pull levels (nd_pull = 1), pull kernel + separate steps (what the complex path runs on a pull
-    plan) - give the same Jacobian, and each matches the reference."""
+    """The schedules of the multi-level base stage - 4-way dissection with the destination-centric pull (default), the
+    fused front kernel on small fronts, children pushing their update matrices, plain bisection with pull / push -
+    give the same Jacobian, and each matches the reference."""
     t = torch_cuda
     m, r = golden(tag)
     E, L = len(m["elem"]), 16
@@ -313,7 +313,8 @@ def test_front_step_variants_agree(torch_cuda, golden, tag):
     perm = t.tensor(m["elem_perm"], device="cuda")
     var = t.zeros(E, dtype=t.float64, device="cuda")
     outs = []
-    for opts in ({}, {"nd_pull": 1}, {"nd_pull": 1, "no_front_kernel": 1}):
+    defaults = {"nd_pull": 1, "nd_ways": 4, "front_kernel": 0}
+    for opts in ({}, {"front_kernel": 1}, {"nd_pull": 0}, {"nd_ways": 2}, {"nd_ways": 2, "nd_pull": 0}):
         for k, v in opts.items():
             _lib.set_option(k, v)
         try:
@@ -328,13 +329,13 @@ def test_front_step_variants_agree(torch_cuda, golden, tag):
             p.close()
         finally:
             for k in opts:
-                _lib.set_option(k, 0)
+                _lib.set_option(k, defaults[k])
     for Jh in outs:
         for k, (i, j) in enumerate(r["sample_pairs"]):
             assert np.abs(Jh[_rows(i, L), j] - r["sample_cols"][k]).max() < RAW_TOL
         if "JAC" in r:
             assert np.abs(Jh - r["JAC"]).max() < RAW_TOL
-    assert np.abs(outs[0] - outs[1]).max() < 1e-12 and np.abs(outs[0] - outs[2]).max() < 1e-12
+    assert all(np.abs(outs[0] - o_).max() < 1e-12 for o_ in outs[1:])
 
 
 def test_shared_inverse_product_by_second_sweep(torch_cuda, golden):

@@ -29,11 +29,11 @@ def checker():
     L = ctypes.CDLL(SO)
     L.nd_host_last_error.restype = ctypes.c_char_p
     L.nd_host_check.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int64] * 2 + [ctypes.c_void_p] * 2 + \
-        [ctypes.c_int64] * 2 + [ctypes.c_void_p] * 7 + [ctypes.c_int]
+        [ctypes.c_int64] * 2 + [ctypes.c_void_p] * 7 + [ctypes.c_int] * 2
     return L
 
 
-def _run(L, nodes, elem, electrodes, leaf_cap, K, mode=0):
+def _run(L, nodes, elem, electrodes, leaf_cap, K, mode=0, ways=4):
     nodes = np.ascontiguousarray(nodes, np.float64)
     elem = np.ascontiguousarray(elem, np.int64)
     N, E = len(nodes), len(elem)
@@ -44,14 +44,14 @@ def _run(L, nodes, elem, electrodes, leaf_cap, K, mode=0):
     P = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)  # noqa: E731
     info = np.zeros(8, np.int64)
     rc = L.nd_host_check(P(nodes), P(elem), N, E, P(ptr), P(idx), len(electrodes), leaf_cap, None, P(info), None, None,
-                         None, None, None, mode)
+                         None, None, None, mode, ways)
     assert rc == 0, L.nd_host_last_error()
     nU, N0 = int(info[0]), int(info[1])
     pos, U = np.zeros(N, np.int64), np.zeros(nU, np.int64)
     X, SU, g0 = np.zeros((N0, nU)), np.zeros((nU, nU)), np.zeros((E, 6))
     Kd = np.ascontiguousarray(K, np.float64)
     rc = L.nd_host_check(P(nodes), P(elem), N, E, P(ptr), P(idx), len(electrodes), leaf_cap, P(Kd), P(info), P(pos),
-                         P(U), P(X), P(SU), P(g0), mode)
+                         P(U), P(X), P(SU), P(g0), mode, ways)
     assert rc == 0, L.nd_host_last_error()
     return info, pos, U, X, SU, g0
 
@@ -80,10 +80,10 @@ def _check(L, nodes, elem, electrodes, leaf_cap, perm=None):
     param = o.elem_param(nodes, elem)
     K = o.assemble_csr(elem, param, np.ones(E) if perm is None else perm, np.zeros(E), 2 * np.pi * 2e4, N)
     K = np.asarray(K.todense()).real
-    # three schedules of the same plan family: fused front step on the pull levels, pull + separate steps (the
-    # complex path of the CUDA backend), and children pushing everywhere (no pull levels)
-    for mode in (0, 1, 2):
-        info, pos, U, X, SU, g0 = _run(L, nodes, elem, electrodes, leaf_cap, K, mode)
+    # the schedules of the plan family: destination-centric pull with the separate steps (default), with the fused
+    # front step on small fronts, children pushing (no pull levels); 4-way and 2-way dissection
+    for mode, ways in ((1, 4), (0, 4), (2, 4), (1, 2), (2, 2)):
+        info, pos, U, X, SU, g0 = _run(L, nodes, elem, electrodes, leaf_cap, K, mode, ways)
         assert info[7] == 0                                  # every pivot positive
         assert (info[6] // 100000 > 0) == (mode != 2)        # pull levels exist unless disabled
         info[6] %= 100000

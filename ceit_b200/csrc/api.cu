@@ -1001,6 +1001,8 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
   gemm<T>(st, 0, 0, N, nU, nU, one, Xh, nU, 0, Sinv, nU, u2, zero, Yh, nU, N * nU, nbatch);
   }
   dim3 g3(cdiv(nU, 8), nbatch);
+  // (one CTA per excitation running the four stages back to back was tried: 80 us slower at nU = 264 - a single SM
+  //  streams the nU x nU matrices at its load latency; the four chip-wide launches stay)
   phi_u_kernel<T><<<g3, 256, 0, sx>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 0);
   CEIT_COUNT_LAUNCH();
   phi_u_kernel<T><<<g3, 256, 0, sx>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 1);

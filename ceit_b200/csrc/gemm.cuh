@@ -598,6 +598,8 @@ inline void gemm_real_tiled(cudaStream_t st, int opA, int opB, int64_t M, int64_
   // measured on B200 (tools/time_gemm.py): the 64x64 tile (2 CTAs/SM) beats 128x128 (1 CTA/SM) at every size
   // of this path (30.3 vs 25.3 TFLOP/s on the inverse-model GEMM, cuBLAS 34.9); 32x32 when 64x64 cannot fill the chip
   if (cfg == 0) cfg = (ctas(64, 64) >= g_gemm_min_ctas64) ? 2 : 1;
+  // (128 x 64 and 64 x 128 tiles with 8 warps, 2 CTAs/SM, were measured too: 25-29 TFLOP/s against 30-32 for the
+  //  64 x 64 tile on the four large products of the path, tools/time_gemm_tiles.py)
   if (cfg == 3)
     gemm_dmma_launch<128, 128, 2, 4, 3>(st, opA, opB, M, N, K, alpha, A, lda, sA, B, ldb, sB, beta, C, ldc, sC, batch,
                                         flags);

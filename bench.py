@@ -506,6 +506,16 @@ def realtime_leg(ctx, inv, n_det, m_rows):
     if not (err < 1e-12 and chk < 1e-9):
         raise SystemExit(f"batched reconstruction differs from torch.matmul: {err} {chk}")
     del ref
+    # cuBLAS DGEMM on the SAME shape (library baseline for this product; the 4096^3 figure is the roofline peak)
+    for _ in range(2):
+        torch.matmul(inv, dV, out=out)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        torch.matmul(inv, dV, out=out)
+    b.record()
+    torch.cuda.synchronize()
+    t_cublas_same = a.elapsed_time(b) / reps * 1e-3
     # single frame: eager launches and a replayed CUDA graph of 100 frames (the realtime loop of Example_04)
     one = dV[:, 0].contiguous()
     o1 = torch.empty(n_det, dtype=torch.float64, device=dev)
@@ -554,6 +564,8 @@ def realtime_leg(ctx, inv, n_det, m_rows):
         "frames_per_s_batched_100k": N_FRAMES / t_batch, "ms_batched_100k": t_batch * 1e3,
         "batched_tflops_f64": flops / t_batch / 1e12, "cublas_dgemm_4096_tflops": dgemm_tf,
         "batched_frac_of_cublas_dgemm": flops / t_batch / 1e12 / dgemm_tf,
+        "cublas_dgemm_same_shape_tflops": flops / t_cublas_same / 1e12,
+        "batched_frac_of_cublas_same_shape": t_cublas_same / t_batch,
         "batched_max_rel_err_vs_torch_matmul_f64": err, "batched_checksum_rel_err": chk,
         "frames_per_s_single": 1.0 / t_one, "us_single_frame": t_one * 1e6,
         "us_single_frame_graph_replay": t_one_graph * 1e6,

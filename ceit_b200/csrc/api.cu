@@ -59,6 +59,7 @@ int g_ru_wc = 0, g_ru_cpt = 0, g_ru_waves = 8;   // rank_update_kernel layout ov
 int g_direct_excitation = 0;
 int g_patch_nodes = 0;   // experiment: override the node cap of the element patches
 int64_t g_nd_interior = 64;   // target nodes per nested-dissection interior / leaf; <= 0 disables the dissection
+int g_assemble_gather = 0;    // 1: the slot-gather form of K1 (one thread per CSR slot re-derives the geometry)
 int g_nd_tree = 1;            // 1: multi-level nested dissection (factor_tree.h); 0: interiors + block-tridiagonal chain
 int g_nd_pull = 1;            // plans created afterwards: 1 = every level pulls its children's update matrices (one
                               // destination-centric launch per level), 0 = children push (one pass per sibling index)
@@ -143,6 +144,8 @@ struct ceit_plan {
   int32_t* d_elem = nullptr;
   int32_t* d_src_ptr = nullptr;
   int32_t* d_src = nullptr;
+  int32_t* d_elem_dst = nullptr;   // inverse of d_src: (element, a, b) -> position in the slot-sorted contribution list
+  void* d_contrib = nullptr;       // 9E (re, im) pairs
   int64_t* d_slot_dst = nullptr;
   uint8_t* d_slot_kind = nullptr;
   int32_t* d_pos = nullptr;
@@ -238,6 +241,12 @@ int upload_plan(ceit_plan* p) {
   if ((rc = upload_vec(p, &p->d_elem, h.elem))) return rc;
   if ((rc = upload_vec(p, &p->d_src_ptr, h.src_ptr))) return rc;
   if ((rc = upload_vec(p, &p->d_src, h.src))) return rc;
+  {
+    std::vector<int32_t> inv(h.src.size());
+    for (size_t q = 0; q < h.src.size(); ++q) inv[(size_t)h.src[q]] = (int32_t)q;
+    if ((rc = upload_vec(p, &p->d_elem_dst, inv))) return rc;
+    if ((rc = dev_alloc(p, &p->d_contrib, h.src.size() * 2 * sizeof(double)))) return rc;
+  }
   if ((rc = upload_vec(p, &p->d_slot_dst, h.slot_dst))) return rc;
   if ((rc = upload_vec(p, &p->d_slot_kind, h.slot_kind))) return rc;
   if ((rc = upload_vec(p, &p->d_pos, h.pos))) return rc;
@@ -1332,9 +1341,18 @@ int ceit_assemble(ceit_plan_t* p, const double* perm, const double* var, double 
   cudaStream_t st = (cudaStream_t)stream;
   const HostPlan& h = p->h;
   StageScope sc(0, st);
-  assemble_csr_kernel<<<cdiv(h.nnz, 256), 256, 0, st>>>((int)h.nnz, p->d_src_ptr, p->d_src, p->d_nodes, p->d_elem,
-                                                        perm, var, omega, p->d_vals);
-  CEIT_COUNT_LAUNCH();
+  if (g_assemble_gather) {
+    assemble_csr_kernel<<<cdiv(h.nnz, 256), 256, 0, st>>>((int)h.nnz, p->d_src_ptr, p->d_src, p->d_nodes, p->d_elem,
+                                                          perm, var, omega, p->d_vals);
+    CEIT_COUNT_LAUNCH();
+  } else {
+    assemble_elem_kernel<<<cdiv(h.E, 256), 256, 0, st>>>((int)h.E, p->d_nodes, p->d_elem, perm, var, omega,
+                                                         p->d_elem_dst, (double2*)p->d_contrib);
+    CEIT_COUNT_LAUNCH();
+    assemble_reduce_kernel<<<cdiv(h.nnz, 256), 256, 0, st>>>((int)h.nnz, p->d_src_ptr, (const double2*)p->d_contrib,
+                                                             p->d_vals);
+    CEIT_COUNT_LAUNCH();
+  }
   KERNEL_CHECK();
   if (vals) CUDA_TRY(cudaMemcpyAsync(vals, p->d_vals, h.nnz * sizeof(cd), cudaMemcpyDeviceToDevice, st));
   if (elem_param) {
@@ -1615,6 +1633,7 @@ int ceit_set_option(const char* name, int64_t value) {
     return CEIT_OK;
   }
   if (std::strcmp(name, "nd_pull") == 0) { g_nd_pull = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "assemble_gather") == 0) { g_assemble_gather = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "yt_sweep") == 0) { g_yt_sweep = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "front_kernel") == 0) { g_front_kernel = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "nd_ways") == 0) { g_nd_ways = (int)value; return CEIT_OK; }

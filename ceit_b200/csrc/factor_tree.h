@@ -34,12 +34,21 @@ struct TreeBufs {
   T* G = nullptr;                                                      // maxG x nU scratch
 };
 
+// Domain-decomposed plans (TreePlan::parts > 1): a rank runs the segments of its own sub-trees and of
+// the shared top.  Bottom-up is split at t.n_own_segs: [0, n_own_segs) = the rank-owned segments, then ONE exchange
+// (update matrices of the sub-tree roots all-gathered into their C slots, right-hand-side rows of the top and the
+// partial S_U all-reduced), then [n_own_segs, H) = the top, replicated.  The top-down passes need no exchange: a
+// front reads only its ancestors, which are its own or the top's.
+inline bool tree_segment_is_mine(const TreePlan& t, const TreeLevel& lv) { return lv.owner < 0 || lv.owner == t.part; }
+
 template <class T, class BK>
-void tree_bottom_up(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, T one, T zero, T mone) {
-  for (int32_t l = 0; l < t.H; ++l) {
+void tree_bottom_up(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, T one, T zero, T mone,
+                    int32_t seg_from = 0, int32_t seg_to = -1) {
+  if (seg_to < 0) seg_to = t.H;
+  for (int32_t l = seg_from; l < seg_to; ++l) {
     const TreeLevel& lv = t.lv[l];
     const int64_t s = lv.s, b = lv.b, n = lv.n;
-    if (n == 0 || s == 0) continue;
+    if (n == 0 || s == 0 || !tree_segment_is_mine(t, lv)) continue;
     const int64_t sA = s * s, sB = s * b, sC = b * b, sX = s * nU, sG = b * nU;
     T *A = m.A + lv.offA, *Lf = m.Lf + lv.offA, *Li = m.Linv + lv.offA, *Ai = m.Ainv + lv.offA;
     T *Bt = m.Bt + lv.offB, *W = m.W + lv.offB, *Y = m.V + lv.offB, *C = m.C + lv.offC;
@@ -84,7 +93,7 @@ void tree_top_down(const TreePlan& t, int64_t nU, const TreeBufs<T>& m, BK& k, T
   for (int32_t l = t.H - 1; l >= 0; --l) {
     const TreeLevel& lv = t.lv[l];
     const int64_t s = lv.s, b = lv.b, n = lv.n;
-    if (n == 0 || s == 0 || b == 0) continue;
+    if (n == 0 || s == 0 || b == 0 || !tree_segment_is_mine(t, lv)) continue;
     const int64_t sA = s * s, sB = s * b, sC = b * b, sX = s * nU, sG = b * nU;
     T *W = m.W + lv.offB, *V = m.V + lv.offB, *C = m.C + lv.offC, *Sg = m.SigPP + lv.offA;
     T *X = m.Xp + lv.row0 * nU, *Xi = m.Xp + lv.row0i * nU;
@@ -111,7 +120,7 @@ void tree_back_sweep(const TreePlan& t, int64_t nU, const T* Wall, T* G, T* X, B
   for (int32_t l = t.H - 1; l >= 0; --l) {
     const TreeLevel& lv = t.lv[l];
     const int64_t s = lv.s, b = lv.b, n = lv.n;
-    if (n == 0 || s == 0) continue;
+    if (n == 0 || s == 0 || !tree_segment_is_mine(t, lv)) continue;
     const int64_t sB = s * b, sX = s * nU, sG = b * nU;
     const int na = lv.na, ni = (int)n - lv.na;
     T *Xa = X + lv.row0 * nU, *Xi = X + lv.row0i * nU;

@@ -54,6 +54,51 @@ assemble_csr_kernel(int nnz, const int32_t* __restrict__ src_ptr, const int32_t*
   vals[s] = mk(re, im);
 }
 
+// K1, element-parallel form (default).  Pass 1: one thread per ELEMENT reads its connectivity (12 contiguous bytes,
+// coalesced across the warp), gathers the three node coordinates as 16-byte loads, derives the triangle geometry ONCE
+// and stores the nine (a, b) contributions as 16-byte (re, im) pairs at their position in the slot-sorted contribution
+// list (`elem_dst`, the inverse of the gather list `src`): the contributions of a CSR slot end up contiguous, in
+// ascending element order.  Pass 2: one thread per CSR slot sums its contiguous run (a segmented reduction over a
+// coalesced stream, the same order as the gather form, so the result does not depend on the launch geometry).
+// Against the gather form this removes the ~9x redundant geometry and 6/7 of the scattered 16-byte gathers.
+__global__ void __launch_bounds__(256)
+assemble_elem_kernel(int E, const double* __restrict__ nodes, const int32_t* __restrict__ elem,
+                     const double* __restrict__ perm, const double* __restrict__ var, double omega,
+                     const int32_t* __restrict__ elem_dst, double2* __restrict__ contrib) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  double area, b[3], c[3], xb, yb;
+  tri_geometry(nodes, elem, e, area, b, c, xb, yb);
+  const double pe = perm[e], a4 = 4.0 * area;
+  const double ms = omega * var[e] * area;
+  const double md = 2.0 * (ms / 6.0), mo = 2.0 * (ms / 12.0);
+  const int32_t* d = elem_dst + 9 * (int64_t)e;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int bb = a; bb < 3; ++bb) {
+      const double kst = 2.0 * (pe * fma(b[a], b[bb], c[a] * c[bb]) * a4);   // symmetric in (a, b) bit for bit
+      const double2 v = make_double2(kst, a == bb ? md : mo);
+      contrib[d[3 * a + bb]] = v;
+      if (a != bb) contrib[d[3 * bb + a]] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+assemble_reduce_kernel(int nnz, const int32_t* __restrict__ src_ptr, const double2* __restrict__ contrib,
+                       cd* __restrict__ vals) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nnz) return;
+  double re = 0.0, im = 0.0;
+  const int q1 = src_ptr[s + 1];
+  for (int q = src_ptr[s]; q < q1; ++q) {
+    const double2 v = contrib[q];
+    re += v.x;
+    im += v.y;
+  }
+  vals[s] = mk(re, im);
+}
+
 __global__ void __launch_bounds__(256)
 elem_param_kernel(int E, const double* __restrict__ nodes, const int32_t* __restrict__ elem,
                   double* __restrict__ param, double* __restrict__ area_out) {

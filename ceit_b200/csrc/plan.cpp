@@ -41,14 +41,16 @@ void bfs_levels(const std::vector<int32_t>& rowptr, const std::vector<int32_t>& 
   }
 }
 
-void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways);
+void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways, int parts, int part);
 
 }  // namespace
 
 void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
                      const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
-                     int64_t target_block, int64_t nd_interior, bool nd_tree, int nd_pull, int nd_ways) {
+                     int64_t target_block, int64_t nd_interior, bool nd_tree, int nd_pull, int nd_ways, int parts,
+                     int part) {
   if (N <= 0 || E <= 0 || L <= 0) throw std::runtime_error("plan: N, E, L must be positive");
+  if (parts < 1 || part < 0 || part >= parts) throw std::runtime_error("plan: invalid domain decomposition (parts, part)");
   if (N > (int64_t)2000000000 / 16 || E > (int64_t)2000000000 / 16)
     throw std::runtime_error("plan: mesh too large for 32-bit indices");
   if (target_block <= 0) target_block = 192;
@@ -89,6 +91,9 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
   p.nU = (int64_t)p.U.size();
   p.N0 = N - p.nU;
   if (p.N0 <= 0) throw std::runtime_error("plan: every node belongs to an electrode");
+  p.N0c = p.N0;
+  p.Nc = N;
+  p.elem_own.assign(E, 1);
   p.inB.assign(L * p.nU, 0);
   for (int64_t i = 0; i < L; ++i)
     for (int32_t n : node_sets[i]) p.inB[i * p.nU + p.u_of[n]] = 1;
@@ -173,9 +178,10 @@ void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int6
     for (int64_t q = 0; q < 9 * E; ++q) p.src[fill[slot_of[q]]++] = (int32_t)q;  // ascending element order
   }
   if (nd_tree && nd_interior > 0 && p.N0 > std::max<int64_t>(nd_interior, 8)) {
-    build_tree_plan(p, std::min<int64_t>(nd_interior, 64), nd_pull, nd_ways);
+    build_tree_plan(p, std::min<int64_t>(nd_interior, 64), nd_pull, nd_ways, parts, part);
     return;
   }
+  if (parts > 1) throw std::runtime_error("plan: the domain decomposition needs the multi-level nested-dissection ordering");
   // ---- level 1 (nested dissection): geometric boxes -> interiors I_p (<= 64 nodes, mutually
   // disconnected) and the separator set C.  A node goes to C when it has an F0 neighbour in a box with
   // a larger id, so every edge between two boxes has its lower endpoint in C. ----------------------
@@ -614,8 +620,9 @@ struct TreeBuilder {
   }
 };
 
-void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
+void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways, int parts, int part) {
   const int64_t N = p.N, E = p.E;
+  if (parts > 1 && !pull_mode) throw std::runtime_error("plan: the domain decomposition needs the pull schedule (nd_pull = 1)");
   TreeBuilder tb(p, leaf_cap);
   tb.ways = (ways == 4) ? 4 : 2;
   {
@@ -630,8 +637,8 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
   std::vector<int32_t> height(nF, 0);
   for (int32_t f = 0; f < nF; ++f)            // children are created before their parent
     for (int32_t c : tb.children[f]) height[f] = std::max(height[f], height[c] + 1);
-  int32_t H = 0;
-  for (int32_t f = 0; f < nF; ++f) H = std::max(H, height[f] + 1);
+  int32_t Hh = 0;
+  for (int32_t f = 0; f < nF; ++f) Hh = std::max(Hh, height[f] + 1);
   // fronts with a non-zero right-hand side K_0U: a node next to an electrode node, or an active child
   std::vector<uint8_t> active(nF, 0);
   for (int32_t f = 0; f < nF; ++f) {          // children are created before their parent
@@ -639,33 +646,82 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
       for (int32_t q = p.rowptr[v]; q < p.rowptr[v + 1] && !active[f]; ++q) active[f] = (p.u_of[p.colidx[q]] >= 0);
     for (int32_t c : tb.children[f]) active[f] |= active[c];
   }
+  // ---- domain decomposition: cut the forest at the smallest depth that has >= parts fronts; the sub-trees rooted
+  // there go to the ranks in contiguous groups of creation order (balanced by node count), everything above is the
+  // shared top (frank = -1) ----------------------------------------------------------------------------------------
+  std::vector<int32_t> frank(nF, -1);
+  int32_t dcut = 0;
+  if (parts > 1) {
+    std::vector<int32_t> depth(nF, 0);
+    for (int32_t f = nF - 1; f >= 0; --f) depth[f] = tb.parent[f] < 0 ? 0 : depth[tb.parent[f]] + 1;   // parents have larger ids
+    int32_t dmax = 0;
+    for (int32_t f = 0; f < nF; ++f) dmax = std::max(dmax, depth[f]);
+    std::vector<int32_t> cnt(dmax + 1, 0);
+    for (int32_t f = 0; f < nF; ++f) cnt[depth[f]]++;
+    dcut = -1;
+    for (int32_t d = 0; d <= dmax && dcut < 0; ++d)
+      if (cnt[d] >= parts) dcut = d;
+    if (dcut < 0) throw std::runtime_error("plan: the elimination forest has fewer sub-trees than ranks");
+    std::vector<int64_t> weight(nF, 0);
+    for (int32_t f = 0; f < nF; ++f) {        // children first
+      weight[f] += (int64_t)tb.own[f].size();
+      if (tb.parent[f] >= 0) weight[tb.parent[f]] += weight[f];
+    }
+    int64_t total = 0;
+    for (int32_t f = 0; f < nF; ++f)
+      if (depth[f] == dcut) total += weight[f];
+    int64_t cum = 0;
+    for (int32_t f = 0; f < nF; ++f)
+      if (depth[f] == dcut) {
+        frank[f] = (int32_t)std::min<int64_t>(parts - 1, ((2 * cum + weight[f]) * parts) / (2 * std::max<int64_t>(total, 1)));
+        cum += weight[f];
+      }
+    for (int32_t f = nF - 1; f >= 0; --f)
+      if (depth[f] > dcut) frank[f] = frank[tb.parent[f]];
+  }
+  // segments: (height, owner) classes; the rank-owned ones first, ordered by (height, owner), then the top by height
   std::vector<int32_t> gid(nF, -1), old_of(nF, -1);
   TreePlan& t = p.tree;
   t = TreePlan();
-  t.H = H;
   t.nF = nF;
-  t.lv.assign(H, TreeLevel());
+  t.parts = parts;
+  t.part = part;
+  t.dcut = dcut;
+  std::vector<int32_t> seg_of_old(nF, -1);
   {
     int32_t next = 0;
-    for (int32_t l = 0; l < H; ++l) {
-      t.lv[l].f0 = next;
-      for (int pass = 1; pass >= 0; --pass) {   // active fronts first
-        for (int32_t f = 0; f < nF; ++f)
-          if (height[f] == l && active[f] == pass) {
-            gid[f] = next;
-            old_of[next] = f;
-            ++next;
+    for (int top = 0; top < 2; ++top)
+      for (int32_t l = 0; l < Hh; ++l)
+        for (int32_t r = (top ? -1 : 0); r < (top ? 0 : parts); ++r) {
+          TreeLevel lv;
+          lv.f0 = next;
+          lv.owner = r;
+          lv.height = l;
+          for (int pass = 1; pass >= 0; --pass) {   // active fronts first
+            for (int32_t f = 0; f < nF; ++f)
+              if (height[f] == l && frank[f] == r && active[f] == pass) {
+                gid[f] = next;
+                old_of[next] = f;
+                seg_of_old[f] = (int32_t)t.lv.size();
+                ++next;
+              }
+            if (pass == 1) lv.na = next - lv.f0;
           }
-        if (pass == 1) t.lv[l].na = next - t.lv[l].f0;
-      }
-      t.lv[l].n = next - t.lv[l].f0;
-    }
+          lv.n = next - lv.f0;
+          if (lv.n == 0) continue;
+          if (!top) t.n_own_segs = (int32_t)t.lv.size() + 1;
+          t.lv.push_back(lv);
+        }
+    if (next != nF) throw std::runtime_error("plan: segment numbering lost fronts");
   }
+  const int32_t H = (int32_t)t.lv.size();
+  t.H = H;
   // owner / slot of every F0 node, Euler intervals for ancestor tests
-  std::vector<int32_t> owner(N, -1), slot(N, -1), level_of(nF, 0);
+  std::vector<int32_t> owner(N, -1), slot(N, -1), level_of(nF, 0), seg_of(nF, 0);
   for (int32_t g = 0; g < nF; ++g) {
     const auto& o = tb.own[old_of[g]];
-    level_of[g] = height[old_of[g]];
+    level_of[g] = height[old_of[g]];            // height: ordering / ancestor tests
+    seg_of[g] = seg_of_old[old_of[g]];          // segment: storage
     for (size_t a = 0; a < o.size(); ++a) {
       owner[o[a]] = g;
       slot[o[a]] = (int32_t)a;
@@ -721,14 +777,28 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
     t.maxC = std::max<int64_t>(t.maxC, (int64_t)lv.n * lv.b * lv.b);
     t.rel.resize(t.rel.size() + (size_t)lv.n * lv.b, -1);
   }
-  for (int32_t l = 0; l < H; ++l) {            // padded rows: the active fronts of every level, then the inactive ones
-    t.lv[l].row0 = p.N0P;
-    p.N0P += (int64_t)t.lv[l].na * t.lv[l].s;
-  }
-  t.rowsA = p.N0P;
-  for (int32_t l = 0; l < H; ++l) {
-    t.lv[l].row0i = p.N0P;
-    p.N0P += (int64_t)(t.lv[l].n - t.lv[l].na) * t.lv[l].s;
+  {
+    // padded rows: the active fronts rank by rank (each rank's segments by height), then the active fronts of the top,
+    // then the inactive ones - so that S_U and the sweeps over non-zero right-hand sides touch [0, rowsA) only and a
+    // rank's share of them is one contiguous range
+    t.ra0.assign(parts, 0);
+    t.ra1.assign(parts, 0);
+    for (int32_t r = 0; r <= parts; ++r) {
+      const int32_t who = (r == parts) ? -1 : r;
+      if (who >= 0) t.ra0[who] = p.N0P;
+      else t.ra_top0 = p.N0P;
+      for (int32_t l = 0; l < H; ++l)
+        if (t.lv[l].owner == who) {
+          t.lv[l].row0 = p.N0P;
+          p.N0P += (int64_t)t.lv[l].na * t.lv[l].s;
+        }
+      if (who >= 0) t.ra1[who] = p.N0P;
+    }
+    t.rowsA = p.N0P;
+    for (int32_t l = 0; l < H; ++l) {
+      t.lv[l].row0i = p.N0P;
+      p.N0P += (int64_t)(t.lv[l].n - t.lv[l].na) * t.lv[l].s;
+    }
   }
   if (p.N0P > (int64_t)2000000000) throw std::runtime_error("plan: padded row space exceeds 32-bit indices");
   t.bnd_row.assign(t.rel.size(), -1);
@@ -742,7 +812,7 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
   p.node_at.assign(p.NP, -1);
   auto prow = [&](int32_t v) -> int64_t {
     const int32_t g = owner[v];
-    const TreeLevel& lv = t.lv[level_of[g]];
+    const TreeLevel& lv = t.lv[seg_of[g]];
     const int64_t k = g - lv.f0;
     return (k < lv.na ? lv.row0 + k * lv.s : lv.row0i + (k - lv.na) * lv.s) + slot[v];
   };
@@ -766,9 +836,9 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
     if (it == bnd[g].end() || *it != node) throw std::runtime_error("plan: node is not on the front's boundary");
     return (int64_t)(it - bnd[g].begin());
   };
-  auto blockA = [&](int32_t g) { const TreeLevel& lv = t.lv[level_of[g]]; return lv.offA + (int64_t)(g - lv.f0) * lv.s * lv.s; };
-  auto blockB = [&](int32_t g) { const TreeLevel& lv = t.lv[level_of[g]]; return lv.offB + (int64_t)(g - lv.f0) * lv.s * lv.b; };
-  auto blockC = [&](int32_t g) { const TreeLevel& lv = t.lv[level_of[g]]; return lv.offC + (int64_t)(g - lv.f0) * lv.b * lv.b; };
+  auto blockA = [&](int32_t g) { const TreeLevel& lv = t.lv[seg_of[g]]; return lv.offA + (int64_t)(g - lv.f0) * lv.s * lv.s; };
+  auto blockB = [&](int32_t g) { const TreeLevel& lv = t.lv[seg_of[g]]; return lv.offB + (int64_t)(g - lv.f0) * lv.s * lv.b; };
+  auto blockC = [&](int32_t g) { const TreeLevel& lv = t.lv[seg_of[g]]; return lv.offC + (int64_t)(g - lv.f0) * lv.b * lv.b; };
   // per-front parent data, relative indices, boundary rows, sibling index
   t.parent = par;
   t.sib.assign(nF, 0);
@@ -787,7 +857,7 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
       const int32_t g = lv.f0 + k, pg = par[g];
       lv.passes = std::max(lv.passes, t.sib[g] + 1);
       if (pg >= 0) {
-        const TreeLevel& pl = t.lv[level_of[pg]];
+        const TreeLevel& pl = t.lv[seg_of[pg]];
         t.pA[g] = blockA(pg);
         t.pB[g] = blockB(pg);
         t.pC[g] = blockC(pg);
@@ -819,11 +889,11 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
   for (int32_t g = 0; g < nF; ++g) {
     const auto& kids = tb.children[old_of[g]];
     for (size_t k = 0; k < kids.size(); ++k) t.child_ids[t.child_ptr[g] + (int32_t)k] = gid[kids[k]];
-    const TreeLevel& lv = t.lv[level_of[g]];
+    const TreeLevel& lv = t.lv[seg_of[g]];
     t.f_b[g] = lv.b;
     t.f_offC[g] = blockC(g);
     t.f_relOff[g] = lv.offR + (int64_t)(g - lv.f0) * lv.b;
-    t.push[g] = (par[g] >= 0 && !t.lv[level_of[par[g]]].pull) ? 1 : 0;
+    t.push[g] = (par[g] >= 0 && !t.lv[seg_of[par[g]]].pull) ? 1 : 0;
   }
   // inverse relative indices for the destination-centric pull: for child ch, position q of the PARENT's front index
   // space [0, ps + pb) -> boundary slot of ch that maps there, or -1
@@ -834,7 +904,7 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
       if (par[g] < 0) continue;
       const int64_t span = (int64_t)t.ps[g] + t.pb[g];
       t.inv_rel.resize(t.inv_rel.size() + span, -1);
-      const TreeLevel& lv = t.lv[level_of[g]];
+      const TreeLevel& lv = t.lv[seg_of[g]];
       for (int32_t a = 0; a < lv.b; ++a) {
         const int32_t r = t.rel[t.f_relOff[g] + a];
         if (r >= 0) t.inv_rel[t.f_invOff[g] + r] = a;
@@ -879,10 +949,10 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
         const int32_t gr = owner[r], gc = owner[c2];
         if (gr == gc) {
           p.slot_kind[s] = 5;
-          p.slot_dst[s] = blockA(gr) + (int64_t)slot[r] * t.lv[level_of[gr]].s + slot[c2];
+          p.slot_dst[s] = blockA(gr) + (int64_t)slot[r] * t.lv[seg_of[gr]].s + slot[c2];
         } else if (level_of[gr] < level_of[gc]) {
           p.slot_kind[s] = 6;
-          p.slot_dst[s] = blockB(gr) + (int64_t)slot[r] * t.lv[level_of[gr]].b + bidx(gr, c2);
+          p.slot_dst[s] = blockB(gr) + (int64_t)slot[r] * t.lv[seg_of[gr]].b + bidx(gr, c2);
         }
       } else if (!ru && cu) {
         if (p.pos[r] >= t.rowsA) throw std::runtime_error("plan: a right-hand-side row lies outside the active region");
@@ -901,29 +971,82 @@ void build_tree_plan(HostPlan& p, int64_t leaf_cap, int pull_mode, int ways) {
       const int32_t va = p.elem[3 * e + PA[q]], vb = p.elem[3 * e + PB[q]];
       if (p.u_of[va] >= 0 || p.u_of[vb] >= 0) continue;
       const int32_t ga = owner[va], gb = owner[vb];
-      if (ga == gb) p.g0_off[6 * e + q] = blockA(ga) + (int64_t)slot[va] * t.lv[level_of[ga]].s + slot[vb];
+      if (ga == gb) p.g0_off[6 * e + q] = blockA(ga) + (int64_t)slot[va] * t.lv[seg_of[ga]].s + slot[vb];
       else if (level_of[ga] < level_of[gb])
-        p.g0_off[6 * e + q] = t.szA + blockB(ga) + (int64_t)slot[va] * t.lv[level_of[ga]].b + bidx(ga, vb);
+        p.g0_off[6 * e + q] = t.szA + blockB(ga) + (int64_t)slot[va] * t.lv[seg_of[ga]].b + bidx(ga, vb);
       else
-        p.g0_off[6 * e + q] = t.szA + blockB(gb) + (int64_t)slot[vb] * t.lv[level_of[gb]].b + bidx(gb, va);
+        p.g0_off[6 * e + q] = t.szA + blockB(gb) + (int64_t)slot[vb] * t.lv[seg_of[gb]].b + bidx(gb, va);
     }
-  // ---- compact position space (padding slots dropped) ----------------------------------------------------------------
-  p.ppos = p.pos;
-  p.row_map.assign(p.N0, -1);
-  {
-    int32_t q = 0;
-    for (int64_t r = 0; r < p.N0P; ++r)
-      if (p.node_at[r] >= 0) {
-        p.pos[p.node_at[r]] = q;
-        p.row_map[q] = (int32_t)r;
-        ++q;
+  // ---- domain decomposition: export slots of the sub-tree roots, element ownership ----------------------------------
+  auto rank_of_front = [&](int32_t g) { return t.lv[seg_of[g]].owner; };
+  if (parts > 1) {
+    std::vector<std::vector<int32_t>> roots(parts);
+    for (int32_t g = 0; g < nF; ++g) {
+      const int32_t r = rank_of_front(g);
+      if (r >= 0 && par[g] >= 0 && rank_of_front(par[g]) < 0) roots[r].push_back(g);
+    }
+    t.roots_per_rank = 0;
+    t.slot_sz = 0;
+    for (int32_t r = 0; r < parts; ++r) {
+      t.roots_per_rank = std::max<int32_t>(t.roots_per_rank, (int32_t)roots[r].size());
+      for (int32_t g : roots[r]) t.slot_sz = std::max<int64_t>(t.slot_sz, (int64_t)t.f_b[g] * t.f_b[g]);
+    }
+    t.exp_b.assign((size_t)parts * t.roots_per_rank, 0);
+    t.exp_offC.assign((size_t)parts * t.roots_per_rank, 0);
+    for (int32_t r = 0; r < parts; ++r)
+      for (size_t k = 0; k < roots[r].size(); ++k) {
+        t.exp_b[(size_t)r * t.roots_per_rank + k] = t.f_b[roots[r][k]];
+        t.exp_offC[(size_t)r * t.roots_per_rank + k] = t.f_offC[roots[r][k]];
       }
-    if (q != p.N0) throw std::runtime_error("plan: position compaction lost nodes");
-    for (int64_t u = 0; u < p.nU; ++u) p.pos[p.U[u]] = (int32_t)(p.N0 + u);
+    // an element belongs to the rank whose sub-trees hold one of its nodes (its other nodes are then in the same
+    // rank's sub-trees, in the top or on an electrode: sub-domains of different ranks are separated by the top);
+    // elements that touch only the top / electrodes are dealt round-robin
+    for (int64_t e = 0; e < E; ++e) {
+      int32_t r = -1;
+      for (int a = 0; a < 3; ++a) {
+        const int32_t v = p.elem[3 * e + a];
+        if (p.u_of[v] >= 0) continue;
+        const int32_t rv = rank_of_front(owner[v]);
+        if (rv < 0) continue;
+        if (r >= 0 && rv != r) throw std::runtime_error("plan: an element spans the regions of two ranks");
+        r = rv;
+      }
+      if (r < 0) r = (int32_t)(e % parts);
+      p.elem_own[e] = (r == part) ? 1 : 0;
+      if (!p.elem_own[e])
+        for (int q = 0; q < 6; ++q) p.g0_off[6 * e + q] = -1;
+    }
+  }
+  // ---- compact position space (padding slots dropped; a domain-decomposed plan keeps only the rows of this rank's
+  // segments and of the top) --------------------------------------------------------------------------------------------
+  p.ppos = p.pos;
+  {
+    std::vector<int32_t> rows;
+    for (int64_t r = 0; r < p.N0P; ++r) {
+      const int32_t v = p.node_at[r];
+      if (v < 0) continue;
+      const int32_t rk = rank_of_front(owner[v]);
+      if (rk >= 0 && rk != part) {
+        p.pos[v] = -1;                               // foreign region: no row on this rank
+        continue;
+      }
+      p.pos[v] = (int32_t)rows.size();
+      rows.push_back((int32_t)r);
+    }
+    p.row_map = rows;
+    p.N0c = (int64_t)rows.size();
+    p.Nc = p.N0c + p.nU;
+    if (parts == 1 && p.N0c != p.N0) throw std::runtime_error("plan: position compaction lost nodes");
+    for (int64_t u = 0; u < p.nU; ++u) p.pos[p.U[u]] = (int32_t)(p.N0c + u);
   }
   p.elem_pos.resize(3 * E);
   for (int64_t e = 0; e < E; ++e)
     for (int a = 0; a < 3; ++a) p.elem_pos[3 * e + a] = p.pos[p.elem[3 * e + a]];
+  if (parts > 1)
+    for (int64_t e = 0; e < E; ++e)
+      if (p.elem_own[e])
+        for (int a = 0; a < 3; ++a)
+          if (p.elem_pos[3 * e + a] < 0) throw std::runtime_error("plan: an owned element has a node outside the rank's rows");
   p.blk_ptr.assign(1, 0);
   p.offD.assign(1, 0);
   p.offS.assign(1, 0);
@@ -950,6 +1073,8 @@ void build_patches(HostPlan& p, int32_t node_cap, int32_t elem_cap) {
       for (int a = 0; a < 3; ++a) nel[fill[p.elem[3 * e + a]]++] = (int32_t)e;
   }
   std::vector<uint8_t> done(E, 0), queued(E, 0);
+  if ((int64_t)p.elem_own.size() == E)
+    for (int64_t e = 0; e < E; ++e) done[e] = p.elem_own[e] ? 0 : 1;   // domain-decomposed plan: own elements only
   std::vector<int32_t> local_of(N, -1);
   p.patch_eptr.assign(1, 0);
   p.patch_nptr.assign(1, 0);

@@ -28,9 +28,28 @@ struct TreeLevel {
                                      // 0: the children push (one extend-add pass per sibling index at the child's level)
   int32_t fusable = 0;               // pull level of small fronts (s <= 64, b <= 64): pull + factorisation + Y / U /
                                      // A^-1 / W may run as ONE kernel per level (front_fused_kernel)
+  int32_t owner = -1;                // domain-decomposed plans (TreePlan::parts > 1): rank that owns the fronts of this
+                                     // SEGMENT (fronts of one height inside one rank's sub-trees); -1 = the shared top of
+                                     // the forest, processed by every rank.  A rank executes owner == part and owner == -1.
+  int32_t height = 0;                // height of the segment's fronts in the forest (0 = leaves)
 };
 struct TreePlan {
-  int32_t H = 0;                     // levels, 0 = leaves
+  int32_t H = 0;                     // segments (= levels when parts == 1), children before parents: the rank-owned
+                                     // segments [0, n_own_segs) ordered by (height, owner), then the shared top by height
+  // ---- domain decomposition over `parts` ranks (multi-GPU base stage) --------------------------
+  // The forest is cut at depth `dcut`: the sub-trees below belong to one rank each (contiguous groups in creation
+  // order = spatially compact regions), the fronts above are the TOP and are replicated.  One exchange between the
+  // two halves of the bottom-up pass: the update matrices of the sub-tree roots are all-gathered (`exp_*`: one slot of
+  // slot_sz elements per root, roots_per_rank slots per rank), the right-hand-side rows of the top and the partial
+  // S_U products are all-reduced; everything after that is local to the rank's own region.
+  int32_t parts = 1, part = 0, dcut = 0;
+  int32_t n_own_segs = 0;
+  std::vector<int64_t> ra0, ra1;     // per rank: padded rows [ra0, ra1) = the active fronts of its segments
+  int64_t ra_top0 = 0;               // padded rows [ra_top0, rowsA) = the active fronts of the top
+  int32_t roots_per_rank = 0;
+  int64_t slot_sz = 0;               // elements per export slot (max b^2 over the sub-tree roots)
+  std::vector<int32_t> exp_b;        // parts * roots_per_rank: padded boundary size of the slot's front (0 = empty slot)
+  std::vector<int64_t> exp_offC;     // offset of its update matrix in the C storage
   int64_t nF = 0, szA = 0, szB = 0, szC = 0, maxG = 0, maxC = 0;   // maxG = max n b, maxC = max n b b over levels
   int64_t rowsA = 0;                 // padded rows [0, rowsA) = the active fronts of every level (K0U is zero elsewhere)
   std::vector<TreeLevel> lv;
@@ -57,6 +76,10 @@ struct HostPlan {
   bool use_tree = false;
   TreePlan tree;
   int64_t N = 0, E = 0, L = 0;
+  // compact position space of THIS rank (domain-decomposed plans hold only the rank's own region + the shared top):
+  // N0c non-electrode nodes then the nU electrode nodes; Nc = N0c + nU.  parts == 1: N0c = N0, Nc = N.
+  int64_t Nc = 0, N0c = 0;
+  std::vector<uint8_t> elem_own;     // E: 1 = this rank computes the element's Jacobian columns (all 1 when parts == 1)
   int64_t nU = 0, N0 = 0, nb = 0, max_block = 0, nnz = 0, n_levels = 0;
   // nested dissection level 1: P interiors of <= nI nodes (padded to nI slots each), boundary lists of
   // <= bmax separator nodes; level 2: the nC separator nodes in block-tridiagonal order.
@@ -112,6 +135,7 @@ void build_patches(HostPlan& p, int32_t node_cap, int32_t elem_cap);
 // Throws std::runtime_error on invalid input.
 void build_host_plan(HostPlan& p, const double* nodes, const int64_t* elem, int64_t N, int64_t E,
                      const int64_t* el_ptr, const int64_t* el_elems, int64_t L,
-                     int64_t target_block, int64_t nd_interior, bool nd_tree = false, int nd_pull = 1, int nd_ways = 4);
+                     int64_t target_block, int64_t nd_interior, bool nd_tree = false, int nd_pull = 1, int nd_ways = 4,
+                     int parts = 1, int part = 0);
 
 }  // namespace ceit

@@ -236,6 +236,9 @@ int ceit_debug_tile_clocks(int64_t* out8);
  *   "ru_wc", "ru_cpt", "ru_waves"
  *                       rank-update kernel: force the column layout (warps across x columns per thread; 0 =
  *                       cost model) and the number of CTA waves (default 8); tools/ru_sweep.sh
+ *   "assemble_gather"   (default 0) 1: K1 as one thread per CSR slot re-deriving the triangle geometry of each of its
+ *                       contributions (round-1 form); 0 = element-parallel pass (geometry once per element, stores
+ *                       into the slot-sorted contribution list) + segmented sum per CSR slot
  *   "excitation_overlap" (default 1) ZW / base potentials on a second stream beside the Yh update
  *   "force_simt_gemm", "direct_excitation", "no_patch_kernel", "no_lowrank_kernel"
  *                       route around the tensor-core GEMM / rank-update excitation stage / patch Woodbury

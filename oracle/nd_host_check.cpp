@@ -265,4 +265,143 @@ int nd_host_check(const double* nodes, const int64_t* elem, int64_t N, int64_t E
     return -1;
   }
 }
+
+// ---- domain-decomposed base stage (TreePlan::parts > 1): the ranks are simulated one after the other on the host,
+// the NCCL exchange of the product (all-gather of the sub-tree roots' update matrices, all-reduce of the top's
+// right-hand-side rows and of the partial S_U) is done with plain copies / sums.  Outputs per rank r:
+//   n0c i64[parts], pos i64[parts * N] (compact positions, -1 = foreign), X f64[parts * N0 * nU] (first n0c[r] rows of
+//   slab r), SU f64[parts * nU * nU], g0 f64[6 E] (from each element's owner), owner i64[E] (rank of each element; -2
+//   if owned by none or by several = an error the test reports).
+namespace {
+struct RankState {
+  HostPlan h;
+  std::vector<double> A, Lf, Li, Ai, Bt, W, Sel, C, R, Xp, G, KUU, P;
+  TreeBufs<double> m;
+  HostBK bk;
+};
+}  // namespace
+
+int nd_host_check_parts(const double* nodes, const int64_t* elem, int64_t N, int64_t E, const int64_t* el_ptr,
+                        const int64_t* el_elems, int64_t L, int64_t leaf_cap, const double* K, int parts, int ways,
+                        int64_t* info, int64_t* n0c, int64_t* pos, double* X, double* SU, double* g0, int64_t* owner) {
+  try {
+    std::vector<RankState> rk(parts);
+    for (int r = 0; r < parts; ++r) {
+      RankState& s = rk[r];
+      build_host_plan(s.h, nodes, elem, N, E, el_ptr, el_elems, L, 0, leaf_cap, true, 1, ways, parts, r);
+      if (!s.h.use_tree) throw std::runtime_error("mesh too small for the tree plan");
+      build_patches(s.h, 24, 32);
+    }
+    const TreePlan& t0 = rk[0].h.tree;
+    const int64_t nU = rk[0].h.nU, N0P = rk[0].h.N0P, N0 = rk[0].h.N0;
+    if (info) {
+      info[0] = nU; info[1] = N0; info[2] = t0.H; info[3] = t0.nF; info[4] = N0P; info[5] = t0.n_own_segs;
+      info[6] = t0.roots_per_rank; info[7] = 0; info[8] = t0.dcut; info[9] = t0.rowsA - t0.ra_top0;
+    }
+    for (int r = 0; r < parts; ++r) {
+      if (n0c) n0c[r] = rk[r].h.N0c;
+      if (pos) for (int64_t v = 0; v < N; ++v) pos[r * N + v] = rk[r].h.pos[v];
+    }
+    if (owner) {
+      for (int64_t e = 0; e < E; ++e) owner[e] = -2;
+      for (int r = 0; r < parts; ++r) {
+        const HostPlan& h = rk[r].h;
+        for (int64_t e = 0; e < E; ++e)
+          if (h.elem_own[e]) owner[e] = (owner[e] == -2) ? r : -3;
+        // every owned element sits in exactly one patch of its rank, foreign elements in none
+        std::vector<int> seen(E, 0);
+        for (int32_t e : h.patch_elems) seen[e]++;
+        for (int64_t e = 0; e < E; ++e)
+          if (seen[e] != (h.elem_own[e] ? 1 : 0)) throw std::runtime_error("patches do not cover exactly the owned elements");
+        for (int32_t q : h.patch_nodes)
+          if (q < 0 || q >= h.Nc) throw std::runtime_error("a patch node has no row on its rank");
+      }
+    }
+    if (!K || !X || !SU || !g0) return 0;
+    // phase A on every rank: scatter, own segments bottom-up, partial S_U over the rank's active rows
+    for (int r = 0; r < parts; ++r) {
+      RankState& s = rk[r];
+      const HostPlan& h = s.h;
+      const TreePlan& t = h.tree;
+      s.A.assign(t.szA, 0.0); s.Lf.assign(t.szA, 0.0); s.Li.assign(t.szA, 0.0); s.Ai.assign(t.szA, 0.0);
+      s.Bt.assign(t.szB, 0.0); s.W.assign(t.szB, 0.0); s.Sel.assign(t.szA + t.szB, 0.0); s.C.assign(t.szC, 0.0);
+      s.R.assign(N0P * nU, 0.0); s.Xp.assign(N0P * nU, 0.0);
+      s.G.assign(std::max<int64_t>(t.maxG, 1) * nU, 0.0); s.KUU.assign(nU * nU, 0.0); s.P.assign(nU * nU, 0.0);
+      for (int64_t d : t.pad_diag) s.A[d] = 1.0;
+      for (int64_t q = 0; q < N; ++q)
+        for (int32_t c = h.rowptr[q]; c < h.rowptr[q + 1]; ++c) {
+          const double v = K[q * N + h.colidx[c]];
+          const int64_t d = h.slot_dst[c];
+          switch (h.slot_kind[c]) {
+            case 5: s.A[d] = v; break;
+            case 6: s.Bt[d] = v; break;
+            case 3: s.R[d] = v; break;
+            case 4: s.KUU[d] = v; break;
+            default: break;
+          }
+        }
+      if (r != 0)                                            // the assembled rows of the top count once in the sum
+        std::fill(s.R.begin() + t.ra_top0 * nU, s.R.begin() + t.rowsA * nU, 0.0);
+      // foreign rows must never be read: poison them
+      for (int q = 0; q < parts; ++q)
+        if (q != r)
+          for (int64_t x = t.ra0[q] * nU; x < t.ra1[q] * nU; ++x) s.R[x] = s.Xp[x] = std::nan("");
+      s.m.A = s.A.data(); s.m.Lf = s.Lf.data(); s.m.Linv = s.Li.data(); s.m.Ainv = s.Ai.data(); s.m.Bt = s.Bt.data();
+      s.m.W = s.W.data(); s.m.SigPP = s.Sel.data(); s.m.V = s.Sel.data() + t.szA; s.m.C = s.C.data();
+      s.m.R = s.R.data(); s.m.Xp = s.Xp.data(); s.m.G = s.G.data();
+      s.bk.fuse = false;
+      tree_bottom_up<double>(t, nU, s.m, s.bk, 1.0, 0.0, -1.0, 0, t.n_own_segs);
+      for (int64_t a = 0; a < nU; ++a)
+        for (int64_t b = 0; b < nU; ++b) {
+          double acc = 0.0;
+          for (int64_t q = t.ra0[r]; q < t.ra1[r]; ++q) acc += s.R[q * nU + a] * s.Xp[q * nU + b];
+          s.P[a * nU + b] = acc;
+        }
+    }
+    // the exchange
+    for (int r = 0; r < parts; ++r)
+      for (int32_t k = 0; k < t0.roots_per_rank; ++k) {
+        const int64_t b = t0.exp_b[(size_t)r * t0.roots_per_rank + k], off = t0.exp_offC[(size_t)r * t0.roots_per_rank + k];
+        for (int q = 0; q < parts; ++q)
+          if (q != r) std::memcpy(rk[q].C.data() + off, rk[r].C.data() + off, sizeof(double) * (size_t)(b * b));
+      }
+    {
+      std::vector<double> sumR((t0.rowsA - t0.ra_top0) * nU, 0.0), sumP(nU * nU, 0.0);
+      for (int r = 0; r < parts; ++r) {
+        for (size_t x = 0; x < sumR.size(); ++x) sumR[x] += rk[r].R[t0.ra_top0 * nU + x];
+        for (size_t x = 0; x < sumP.size(); ++x) sumP[x] += rk[r].P[x];
+      }
+      for (int r = 0; r < parts; ++r) {
+        std::copy(sumR.begin(), sumR.end(), rk[r].R.begin() + t0.ra_top0 * nU);
+        rk[r].P = sumP;
+      }
+    }
+    // phase B on every rank
+    for (int r = 0; r < parts; ++r) {
+      RankState& s = rk[r];
+      const HostPlan& h = s.h;
+      const TreePlan& t = h.tree;
+      tree_bottom_up<double>(t, nU, s.m, s.bk, 1.0, 0.0, -1.0, t.n_own_segs, t.H);
+      double* su = SU + (int64_t)r * nU * nU;
+      for (int64_t a = 0; a < nU; ++a)
+        for (int64_t b = 0; b < nU; ++b) {
+          double acc = 0.0;
+          for (int64_t q = t.ra_top0; q < t.rowsA; ++q) acc += s.R[q * nU + a] * s.Xp[q * nU + b];
+          su[a * nU + b] = s.KUU[a * nU + b] - s.P[a * nU + b] - acc;
+        }
+      std::memcpy(s.Sel.data(), s.Ai.data(), sizeof(double) * t.szA);
+      tree_top_down<double>(t, nU, s.m, s.bk, 1.0, 0.0, -1.0);
+      for (int64_t q = 0; q < h.N0c; ++q)
+        std::memcpy(X + ((int64_t)r * N0 + q) * nU, s.Xp.data() + (int64_t)h.row_map[q] * nU, sizeof(double) * nU);
+      for (int64_t e = 0; e < E; ++e)
+        if (h.elem_own[e])
+          for (int q = 0; q < 6; ++q) g0[6 * e + q] = h.g0_off[6 * e + q] < 0 ? 0.0 : s.Sel[h.g0_off[6 * e + q]];
+      if (info) info[7] |= s.bk.bad_pivot;
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_msg = e.what();
+    return -1;
+  }
+}
 }

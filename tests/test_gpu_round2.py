@@ -399,3 +399,38 @@ def test_mesh_model_on_device_matches_reference_and_host_model(torch_cuda, works
     monkeypatch.setattr(_lib, "cuda_available", lambda: True)
     with pytest.raises(Exception, match="No element is selected"):
         MeshObj(dev_mesh.mesh_obj, 1, [[10.0, 10.0]], 1e-4)
+
+
+@pytest.mark.parametrize("tag", ["21_21", "50_50"])
+def test_element_parallel_assembly_equals_gather_form_and_reference(torch_cuda, golden, tag):
+    """K1 (CEIT/EFEM.py:47-69): the element-parallel form (default: geometry once per element, slot-sorted contribution
+    list, segmented sum) against the slot-gather form and the reference's K, real and complex material."""
+    t = torch_cuda
+    m, r = golden(tag)
+    E = len(m["elem"])
+    omega = 2 * np.pi * float(r["signal_frequency"])
+    p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"])
+    perm = t.tensor(m["elem_perm"], device="cuda")
+    rng = np.random.default_rng(5)
+    for var_h in (np.zeros(E), rng.random(E) * 1e-7):
+        var = t.tensor(var_h, device="cuda")
+        out = []
+        for gather in (0, 1):
+            _lib.set_option("assemble_gather", gather)
+            try:
+                vals = t.zeros((p.nnz, 2), dtype=t.float64, device="cuda")
+                p.assemble(perm, var, omega, vals)
+            finally:
+                _lib.set_option("assemble_gather", 0)
+            out.append(vals.cpu().numpy())
+        scale = np.abs(out[1]).max(axis=0) + 1e-300
+        assert (np.abs(out[0] - out[1]) / scale).max() < 4e-16
+        if not var_h.any():
+            v = out[0]
+            assert np.abs(v[:, 0] + 1j * v[:, 1] - r["K_data"]).max() <= 1e-12 * np.abs(r["K_data"]).max()
+    # symmetric bit for bit: K[a, b] == K[b, a]
+    tb = p.tables()
+    rowptr, colidx = tb["rowptr"], tb["colidx"]
+    import scipy.sparse as sp
+    K = sp.csr_matrix((out[0][:, 0] + 1j * out[0][:, 1], colidx, rowptr), shape=(len(m["nodes"]),) * 2)
+    assert abs(K - K.T).max() == 0

@@ -19,6 +19,7 @@ SYMBOLS = [
     "ceit_forward", "ceit_inverse_model", "ceit_reconstruct", "ceit_dgemm", "ceit_plan_csr_values",
     "ceit_set_option", "ceit_stage_times", "ceit_gram_partial", "ceit_inverse_from_gram", "ceit_debug_tile_clocks", "ceit_zgemm",
     "ceit_center_of_position", "ceit_plan_generation", "ceit_plan_numeric_flag", "ceit_stage_flops", "ceit_mesh_model",
+    "ceit_factor_phase", "ceit_plan_exchange", "ceit_plan_own_elements",
 ]
 
 
@@ -69,6 +70,9 @@ def lib():
     L.ceit_mesh_model.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp]
     L.ceit_gram_partial.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_vp, c_vp]
     L.ceit_inverse_from_gram.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp, c_vp]
+    L.ceit_factor_phase.argtypes = [c_vp, c_int, c_vp]
+    L.ceit_plan_exchange.argtypes = [c_vp, c_vp, c_vp, c_vp]
+    L.ceit_plan_own_elements.argtypes = [c_vp, c_vp]
     L.ceit_plan_generation.argtypes = [c_vp]
     L.ceit_plan_generation.restype = c_i64
     L.ceit_plan_numeric_flag.argtypes = [c_vp, c_vp, c_vp]
@@ -176,7 +180,8 @@ class StepGraph:
 class Plan:
     """Opaque `ceit_plan_t*` + the few host tables the Python classes need."""
 
-    def __init__(self, nodes, elem, electrode_lists, target_block=0, upload=True):
+    def __init__(self, nodes, elem, electrode_lists, target_block=0, upload=True, parts=1, part=0):
+        """parts > 1: domain-decomposed plan of rank `part` (include/ceit_b200.h, ceit_factor_phase)."""
         nodes = np.ascontiguousarray(nodes, dtype=np.float64)
         elem = np.ascontiguousarray(elem, dtype=np.int64)
         if nodes.ndim != 2 or nodes.shape[1] != 2:
@@ -192,8 +197,15 @@ class Plan:
             require_cuda()
         self._h = ctypes.c_void_p()
         self.N, self.E, self.L = nodes.shape[0], elem.shape[0], len(electrode_lists)
-        check(lib().ceit_plan_create(_np_ptr(nodes), _np_ptr(elem), self.N, self.E, _np_ptr(ptr), _np_ptr(idx),
-                                     self.L, int(target_block), 1 if upload else 0, ctypes.byref(self._h)))
+        self.parts, self.part = int(parts), int(part)
+        lib().ceit_set_option(b"shard_parts", self.parts)
+        lib().ceit_set_option(b"shard_part", self.part)
+        try:
+            check(lib().ceit_plan_create(_np_ptr(nodes), _np_ptr(elem), self.N, self.E, _np_ptr(ptr), _np_ptr(idx),
+                                         self.L, int(target_block), 1 if upload else 0, ctypes.byref(self._h)))
+        finally:
+            lib().ceit_set_option(b"shard_parts", 1)
+            lib().ceit_set_option(b"shard_part", 0)
         info = self.info()
         self.nU, self.N0, self.n_blocks, self.max_block, self.nnz = (int(info[k]) for k in (3, 4, 5, 6, 7))
         self.P, self.nI, self.bmax, self.nC, self.NP, self.N0P = (int(info[k]) for k in range(16, 22))
@@ -238,6 +250,22 @@ class Plan:
 
     def factor(self, is_complex):
         check(lib().ceit_factor(self._h, 1 if is_complex else 0, stream_ptr()))
+
+    def factor_phase(self, phase):
+        """Half of the base stage of a domain-decomposed plan (1: own sub-trees, 2: after the exchange)."""
+        check(lib().ceit_factor_phase(self._h, int(phase), stream_ptr()))
+
+    def exchange_info(self):
+        """(info, gather_ptr, reduce_ptr) of ceit_plan_exchange; pointers are device addresses (0 before phase 1)."""
+        info = np.zeros(8, np.int64)
+        g, r = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib().ceit_plan_exchange(self._h, _np_ptr(info), ctypes.byref(g), ctypes.byref(r)))
+        return info, g.value or 0, r.value or 0
+
+    def own_elements(self):
+        own = np.zeros(self.E, np.uint8)
+        check(lib().ceit_plan_own_elements(self._h, _np_ptr(own)))
+        return own.astype(bool)
 
     def jacobian_block(self, i_from, i_to, e_from, e_to, c, omega, J, ldJ, base=None):
         check(lib().ceit_jacobian_block(self._h, int(i_from), int(i_to), int(e_from), int(e_to), float(c),

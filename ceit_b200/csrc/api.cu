@@ -54,6 +54,8 @@ constexpr int N_STAGES = 8;
 int g_stage_timers = 0;
 int g_no_patch = 0;
 int g_no_lowrank = 0;
+int g_shard_parts = 1, g_shard_part = 0;   // plans created afterwards: domain decomposition (ranks, this rank)
+int g_wb_persist = 1;   // 1: persistent pipelined low-rank Woodbury kernel when the shapes allow it (even nU)
 int g_ex_overlap = 1;   // excitation stage: ZW / base potentials on a second stream beside the Yh update
 int g_ru_wc = 0, g_ru_cpt = 0, g_ru_waves = 8;   // rank_update_kernel layout overrides (tuning; 0 = auto)
 int g_direct_excitation = 0;
@@ -122,6 +124,51 @@ inline int woodbury_lr_cap(int64_t nU, int64_t bp, int64_t L) {
   }
   return 0;
 }
+// persistent pipelined kernel: column chunks (electrode ranges starting at an even column) and the node cap that lets
+// WBQ_SLOTS slots fit one SM; fewest chunks that leave room for patches of >= 26 nodes (~32 elements), else the
+// split with the largest cap.  Returns false when the kernel does not apply (odd nU, no even split, tiny cap).
+inline bool wbq_configure(const HostPlan& h, WbqChunks* out, int* cap_out) {
+  if ((h.nU & 1) || !h.u_contiguous || h.bp > 64 || h.L < 2) return false;
+  const int64_t budget = 227 * 1024 - 1024;
+  WbqChunks best{};
+  int best_cap = 0;
+  for (int n = 1; n <= 4 && n <= h.L; ++n) {
+    WbqChunks c{};
+    c.n = n;
+    c.el[0] = 0;
+    bool ok = true;
+    for (int q = 1; q < n && ok; ++q) {
+      int m = (int)((h.L * q + n / 2) / n);               // nearest electrode boundary with an even first column
+      int found = -1;
+      for (int d = 0; d < h.L && found < 0; ++d) {
+        if (m + d < h.L && m + d > c.el[q - 1] && (h.ue_ptr[m + d] & 1) == 0) found = m + d;
+        else if (m - d > c.el[q - 1] && m - d < h.L && (h.ue_ptr[m - d] & 1) == 0) found = m - d;
+      }
+      if (found < 0) ok = false;
+      c.el[q] = found;
+    }
+    if (!ok) continue;
+    c.el[n] = (int)h.L;
+    c.wmax = 0;
+    for (int q = 0; q < n; ++q) {
+      const int w = h.ue_ptr[c.el[q + 1]] - h.ue_ptr[c.el[q]];
+      if (w & 1) ok = false;
+      c.wmax = std::max(c.wmax, w);
+    }
+    if (!ok) continue;
+    int cap = 40;
+    while (cap > 0 && wbq_smem_bytes(c.wmax, (int)h.L, cap, (int)h.bp) > budget) --cap;
+    if (cap > best_cap) {
+      best_cap = cap;
+      best = c;
+    }
+    if (cap >= 26) break;
+  }
+  if (best_cap < 16) return false;
+  *out = best;
+  *cap_out = best_cap;
+  return true;
+}
 inline int woodbury_patch_cap(int64_t nU) {
   for (int per_sm = 2; per_sm >= 1; --per_sm) {
     int64_t budget = WB_SMEM_SM / per_sm - 1024;
@@ -136,6 +183,12 @@ inline int woodbury_patch_cap(int64_t nU) {
 
 struct ceit_plan {
   HostPlan h;
+  void* xg = nullptr;             // decomposed plans: export slots of the sub-tree roots' update matrices (all ranks)
+  int32_t* d_exp_b = nullptr;
+  int64_t* d_exp_offC = nullptr;
+  bool wbq_ok = false;            // the persistent pipelined Woodbury kernel applies (patches were built for it)
+  WbqChunks wbq{};
+  int sm_count = 0;
   bool uploaded = false;
   size_t dev_bytes = 0;
   std::vector<void*> allocs;
@@ -247,6 +300,8 @@ int upload_plan(ceit_plan* p) {
     if ((rc = upload_vec(p, &p->d_elem_dst, inv))) return rc;
     if ((rc = dev_alloc(p, &p->d_contrib, h.src.size() * 2 * sizeof(double)))) return rc;
   }
+  if ((rc = upload_vec(p, &p->d_exp_b, h.tree.exp_b))) return rc;
+  if ((rc = upload_vec(p, &p->d_exp_offC, h.tree.exp_offC))) return rc;
   if ((rc = upload_vec(p, &p->d_slot_dst, h.slot_dst))) return rc;
   if ((rc = upload_vec(p, &p->d_slot_kind, h.slot_kind))) return rc;
   if ((rc = upload_vec(p, &p->d_pos, h.pos))) return rc;
@@ -318,7 +373,7 @@ int g_yt_sweep = -1;
 inline bool yt_by_sweep(const ceit_plan* p) {
   if (!p->h.use_tree || !use_rank_update(p)) return false;
   if (g_yt_sweep >= 0) return g_yt_sweep != 0;
-  return 2.0 * (double)p->h.N * (double)p->h.nU * (double)p->h.nU > 2.0e10;
+  return 2.0 * (double)p->h.Nc * (double)p->h.nU * (double)p->h.nU > 2.0e10;
 }
 
 // workspaces are never (re)allocated while the caller's stream is being captured: cudaFree / cudaMalloc are not
@@ -340,7 +395,7 @@ int alloc_numeric(ceit_plan* p, cudaStream_t st) {
   if (int rc_ = refuse_alloc_in_capture(st, "ceit_factor")) return rc_;
   CUDA_TRY(cudaDeviceSynchronize());   // buffers of the other mode may still be in use on any stream
   p->generation++;
-  void** bufs[] = {&p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
+  void** bufs[] = {&p->xg, &p->Ad, &p->Bs, &p->Ld, &p->Linv, &p->Lsub, &p->Sel, &p->K0U, &p->Zw,
                    &p->Xh, &p->KUU, &p->SU, &p->Ptmp, &p->tmpPanel, &p->tmpT, &p->tmpPanel2, &p->Ptmp2, &p->g0e, &p->Aint, &p->Lint,
                    &p->LintInv, &p->Ainv, &p->Bt, &p->Wn, &p->Tm, &p->G1, &p->XP, &p->Mreg, &p->LT,
                    &p->LinvT, &p->Tinv, &p->te, &p->YT, &p->ye, &p->splitk_ws, &p->g1e, &p->tAct, &p->YP};
@@ -362,9 +417,10 @@ int alloc_numeric(ceit_plan* p, cudaStream_t st) {
   if ((rc = dev_alloc(p, &p->Linv, h.szD * es))) return rc;
   if ((rc = dev_alloc(p, &p->Lsub, h.szS * es))) return rc;
   if ((rc = dev_alloc(p, &p->Sel, (h.szD + h.szS + h.szPP + h.szV) * es))) return rc;
-  if ((rc = dev_alloc(p, &p->K0U, h.N0P * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->K0U, (h.N0P + h.nU) * h.nU * es))) return rc;   // + nU rows: partial S_U of a decomposed plan
+  if ((rc = dev_alloc(p, &p->xg, (int64_t)h.tree.parts * h.tree.roots_per_rank * h.tree.slot_sz * es))) return rc;
   if ((rc = dev_alloc(p, &p->Zw, (h.use_tree ? 0 : h.N0P * h.nU) * es))) return rc;
-  if ((rc = dev_alloc(p, &p->Xh, h.N * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Xh, h.Nc * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->XP, h.N0P * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Aint, h.szPP * es))) return rc;
   if ((rc = dev_alloc(p, &p->Lint, h.szPP * es))) return rc;
@@ -379,8 +435,8 @@ int alloc_numeric(ceit_plan* p, cudaStream_t st) {
   if ((rc = dev_alloc(p, &p->LinvT, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Tinv, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->te, h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->YT, h.N * h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->ye, h.N * es))) return rc;
+  if ((rc = dev_alloc(p, &p->YT, h.Nc * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->ye, h.Nc * es))) return rc;
   if (!p->d_gamma && (rc = dev_alloc(p, (void**)&p->d_gamma, sizeof(double)))) return rc;
   if ((rc = dev_alloc(p, &p->g1e, 6 * h.E * es))) return rc;
   if (yt_by_sweep(p)) {
@@ -422,15 +478,15 @@ int alloc_excitation_ws(ceit_plan* p, int want_cap, cudaStream_t st) {
   if ((rc = dev_alloc(p, &p->Ls, c * u2 * es))) return rc;
   if ((rc = dev_alloc(p, &p->Linvs, c * u2 * es))) return rc;
   if ((rc = dev_alloc(p, &p->Sinv, c * u2 * es))) return rc;
-  if ((rc = dev_alloc(p, &p->Yh, c * h.N * h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->phi0, c * h.N * es))) return rc;
+  if ((rc = dev_alloc(p, &p->Yh, c * h.Nc * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->phi0, c * h.Nc * es))) return rc;
   if ((rc = dev_alloc(p, &p->tvec, c * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->tmpS, c * (int64_t)TILE * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->TBB, c * (int64_t)h.bp * h.bp * es))) return rc;
   if ((rc = dev_alloc(p, &p->LB, c * (int64_t)h.bp * h.bp * es))) return rc;
   if ((rc = dev_alloc(p, &p->LinvB, c * (int64_t)h.bp * h.bp * es))) return rc;
   if ((rc = dev_alloc(p, &p->Dcat, c * (int64_t)(h.bp + 1) * h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->ZW, c * h.N * (int64_t)(h.bp + 1) * es))) return rc;
+  if ((rc = dev_alloc(p, &p->ZW, c * h.Nc * (int64_t)(h.bp + 1) * es))) return rc;
   if ((rc = dev_alloc(p, (void**)&p->d_elec, c * h.L * sizeof(double)))) return rc;
   p->ex_cap = want_cap;
   p->ex_mode = want_mode;
@@ -526,23 +582,23 @@ int base_tail(ceit_plan* p, cudaStream_t st, cudaStream_t sr, cudaStream_t s_t) 
   T *Sel = (T*)p->Sel, *g0e = (T*)p->g0e, *Xh = (T*)p->XP, *Xc = (T*)p->Xh;
   gather_g0_kernel<T><<<cdiv(6 * h.E, 256), 256, 0, st>>>(6 * h.E, p->d_g0_off, Sel, g0e);
   CEIT_COUNT_LAUNCH();
-  compact_rows_kernel<T><<<cdiv(h.N0, 8), 256, 0, sr>>>(h.N0, (int)nU, p->d_row_map, Xh, Xc);
+  compact_rows_kernel<T><<<cdiv(h.N0c, 8), 256, 0, sr>>>(h.N0c, (int)nU, p->d_row_map, Xh, Xc);
   CEIT_COUNT_LAUNCH();
-  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>((int)nU, Xc + h.N0 * nU);
+  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>((int)nU, Xc + h.N0c * nU);
   CEIT_COUNT_LAUNCH();
   if (use_rank_update(p)) {
     T *Tinv = (T*)p->Tinv, *YT = (T*)p->YT, *ye = (T*)p->ye;
     CEIT_AFTER(s_t, sr);
     if (yt_by_sweep(p)) {
       // the padded Y_T rows come from the second backward sweep (factor_impl); rows of U: Xh[U] T = -T
-      compact_rows_kernel<T><<<cdiv(h.N0, 8), 256, 0, sr>>>(h.N0, (int)nU, p->d_row_map, (const T*)p->YP, YT);
+      compact_rows_kernel<T><<<cdiv(h.N0c, 8), 256, 0, sr>>>(h.N0c, (int)nU, p->d_row_map, (const T*)p->YP, YT);
       CEIT_COUNT_LAUNCH();
-      negate_copy_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>(nU * nU, Tinv, YT + h.N0 * nU);
+      negate_copy_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>(nU * nU, Tinv, YT + h.N0c * nU);
       CEIT_COUNT_LAUNCH();
     } else {
-      gemm<T>(sr, 0, 0, h.N, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);               // Y_T = Xh T
+      gemm<T>(sr, 0, 0, h.Nc, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);               // Y_T = Xh T
     }
-    rowsum_e_kernel<T><<<cdiv(h.N, 8), 256, 0, sr>>>(h.N, (int)nU, YT, ye);
+    rowsum_e_kernel<T><<<cdiv(h.Nc, 8), 256, 0, sr>>>(h.Nc, (int)nU, YT, ye);
     CEIT_COUNT_LAUNCH();
     CEIT_AFTER(sr, st);
     launch_g1(p, g0e, YT, Xc, st);
@@ -631,6 +687,110 @@ struct CudaTreeBK {
   }
 };
 
+template <class T>
+TreeBufs<T> tree_bufs(ceit_plan* p) {
+  const TreePlan& t = p->h.tree;
+  TreeBufs<T> m;
+  m.A = (T*)p->Aint; m.Lf = (T*)p->Lint; m.Linv = (T*)p->LintInv; m.Ainv = (T*)p->Ainv; m.Bt = (T*)p->Bt; m.W = (T*)p->Wn;
+  m.SigPP = (T*)p->Sel; m.V = (T*)p->Sel + t.szA; m.C = (T*)p->Tm; m.R = (T*)p->K0U; m.Xp = (T*)p->XP; m.G = (T*)p->G1;
+  return m;
+}
+
+// partial S_U of a decomposed plan: P = -K_0U[rows]^T t[rows] (lower triangle; the slab was zeroed with K0U)
+inline void schur_u_partial(ceit_plan* p, cudaStream_t st, int64_t nU, int64_t rows, const double* K0U, const double* X,
+                            double* P) {
+  gemm_splitk(st, 1, 0, nU, nU, rows, -1.0, K0U, nU, X, nU, 0.0, P, nU, (double*)p->splitk_ws, /*lower_only=*/1);
+}
+inline void schur_u_partial(ceit_plan*, cudaStream_t, int64_t, int64_t, const cd*, const cd*, cd*) {}
+
+// common tail of the tree base stage once S_U (lower triangle) is complete on `sr`: T on its own stream, the
+// top-down passes, Y_T, the element blocks
+template <class T>
+int factor_tree_finish(ceit_plan* p, cudaStream_t st, cudaStream_t sr, CudaTreeBK<T>& bk) {
+  const HostPlan& h = p->h;
+  const TreePlan& t = h.tree;
+  const int64_t nU = h.nU;
+  const size_t es = sizeof(T);
+  const T one = Sc<T>::one(), zero = Sc<T>::zero(), mone = neg(Sc<T>::one());
+  T *Sel = (T*)p->Sel, *Ainv = (T*)p->Ainv, *Xh = (T*)p->XP, *Wn = (T*)p->Wn, *G1 = (T*)p->G1, *SU = (T*)p->SU;
+  TreeBufs<T> m = tree_bufs<T>(p);
+  int rc;
+  symmetrize_su(sr, nU, SU);
+  cudaStream_t s_t = sr;
+  if (g_multi_stream) {
+    s_t = p->s3;
+    CEIT_AFTER(sr, s_t);
+  }
+  if ((rc = base_shared_inverse<T>(p, s_t))) return rc;
+  CEIT_AFTER(sr, st);                                   // W of every level, A^-1
+  CUDA_TRY(cudaMemcpyAsync(Sel, Ainv, t.szA * es, cudaMemcpyDeviceToDevice, st));
+  const bool yt_sweep = yt_by_sweep(p);
+  // active rows this rank holds: everything, or (decomposed) its own block and the top's
+  const int64_t own0 = t.parts > 1 ? t.ra0[t.part] : 0, own1 = t.parts > 1 ? t.ra1[t.part] : t.rowsA;
+  const int64_t top0 = t.parts > 1 ? t.ra_top0 : t.rowsA;
+  if (yt_sweep) {                                       // the X sweep overwrites t in place: keep the active rows
+    T* tAct = (T*)p->tAct;
+    if (own1 > own0)
+      CUDA_TRY(cudaMemcpyAsync(tAct + own0 * nU, Xh + own0 * nU, (own1 - own0) * nU * es, cudaMemcpyDeviceToDevice, sr));
+    if (t.rowsA > top0)
+      CUDA_TRY(cudaMemcpyAsync(tAct + top0 * nU, Xh + top0 * nU, (t.rowsA - top0) * nU * es, cudaMemcpyDeviceToDevice, sr));
+  }
+  tree_top_down<T>(t, nU, m, bk, one, zero, mone);
+  if (bk.rc) return bk.rc;
+  if (yt_sweep) {
+    // Y_T = Xh T without the N x nU x nU product: (t T) over the active rows, then the same backward sweep
+    T *YP = (T*)p->YP, *Tinv = (T*)p->Tinv, *tAct = (T*)p->tAct;
+    CEIT_AFTER(s_t, sr);
+    if (own1 > own0)
+      gemm<T>(sr, 0, 0, own1 - own0, nU, nU, one, tAct + own0 * nU, nU, 0, Tinv, nU, 0, zero, YP + own0 * nU, nU, 0);
+    if (t.rowsA > top0)
+      gemm<T>(sr, 0, 0, t.rowsA - top0, nU, nU, one, tAct + top0 * nU, nU, 0, Tinv, nU, 0, zero, YP + top0 * nU, nU, 0);
+    tree_back_sweep<T>(t, nU, Wn, G1, YP, bk, 1, zero, one, mone);
+    if (bk.rc) return bk.rc;
+  }
+  if ((rc = base_tail<T>(p, st, sr, s_t))) return rc;
+  KERNEL_CHECK();
+  p->mode = Sc<T>::is_complex ? 2 : 1;
+  return 0;
+}
+
+// second half of a decomposed base stage (after the caller's exchange): import the foreign sub-tree roots' update
+// matrices, the top bottom-up, S_U = K_UU + sum of the partial products - the top's own rows, then the common tail
+template <class T>
+int factor_tree_second_half(ceit_plan* p, cudaStream_t st) {
+  const HostPlan& h = p->h;
+  const TreePlan& t = h.tree;
+  if (!h.use_tree || t.parts <= 1 || p->mode != -1)
+    CEIT_FAIL(CEIT_ERR_STATE, "ceit_factor_phase(2): call ceit_factor_phase(1) and the exchange first");
+  const int64_t nU = h.nU;
+  const T one = Sc<T>::one(), zero = Sc<T>::zero(), mone = neg(Sc<T>::one());
+  T *K0U = (T*)p->K0U, *Xh = (T*)p->XP, *SU = (T*)p->SU;
+  int rc;
+  cudaStream_t sr = st;
+  if (g_multi_stream) {
+    if ((rc = ensure_aux_stream(p))) return rc;
+    sr = p->s2;
+  }
+  TreeBufs<T> m = tree_bufs<T>(p);
+  CudaTreeBK<T> bk{p, {st, sr, g_multi_stream ? p->s4 : sr}, (T*)p->tmpPanel};
+  if (t.roots_per_rank > 0) {
+    dim3 grid(cdiv(t.slot_sz, 256), t.parts * t.roots_per_rank);
+    export_copy_kernel<T><<<grid, 256, 0, st>>>(0, t.part * t.roots_per_rank, (t.part + 1) * t.roots_per_rank, p->d_exp_b,
+                                                p->d_exp_offC, t.slot_sz, (T*)p->Tm, (T*)p->xg, 0);
+    CEIT_COUNT_LAUNCH();
+  }
+  bk.after(0, 1);                                       // the exchange results and the imports reach every lane
+  bk.after(0, 2);
+  tree_bottom_up<T>(t, nU, m, bk, one, zero, mone, t.n_own_segs, t.H);
+  bk.after(2, 1);
+  if (bk.rc) return bk.rc;
+  add_lower_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>(nU * nU, K0U + t.rowsA * nU, SU);
+  CEIT_COUNT_LAUNCH();
+  if (t.rowsA > t.ra_top0)
+    schur_u_gemm(p, sr, nU, t.rowsA - t.ra_top0, K0U + t.ra_top0 * nU, Xh + t.ra_top0 * nU, SU);
+  return factor_tree_finish<T>(p, st, sr, bk);
+}
+
 // ---- base stage -----------------------------------------------------------------------------------
 // K00 = K[F0,F0] in the ordering [interiors | separators]:
 //   level 1: the P mutually disconnected interiors (<= 64 nodes each) are factorised and eliminated as
@@ -638,11 +798,15 @@ struct CudaTreeBK {
 //   level 2: the separator Schur complement M2 = K_CC - sum_p Bt_p^T A_p^-1 Bt_p is block-tridiagonal
 //            over its BFS level sets: block Cholesky, nU right-hand sides, selected inverse;
 //   then the interior parts of X and of the selected inverse follow from batched GEMMs.
+// phase: 0 = the whole stage (plans without domain decomposition); decomposed plans (TreePlan::parts > 1) run it in two
+// halves around the caller's NCCL exchange (ceit_factor_phase): 1 = assembly scatter, the rank's own segments
+// bottom-up, its partial S_U, export of the sub-tree roots' update matrices; 2 = import, the top, S_U, T, top-down.
 template <class T>
-int factor_impl(ceit_plan* p, cudaStream_t st) {
+int factor_impl(ceit_plan* p, cudaStream_t st, int phase = 0) {
   const HostPlan& h = p->h;
   int rc = alloc_numeric<T>(p, st);
   if (rc) return rc;
+  if (phase == 2) return factor_tree_second_half<T>(p, st);
   T *Ad = (T*)p->Ad, *Bs = (T*)p->Bs, *Ld = (T*)p->Ld, *Linv = (T*)p->Linv, *Lsub = (T*)p->Lsub;
   T *Sel = (T*)p->Sel, *K0U = (T*)p->K0U, *Zw = (T*)p->Zw, *Xh = (T*)p->XP, *Xc = (T*)p->Xh, *KUU = (T*)p->KUU;   // Xh: padded rows here
   T *SU = (T*)p->SU, *Ptmp = (T*)p->Ptmp, *tmpPanel = (T*)p->tmpPanel, *g0e = (T*)p->g0e;
@@ -701,40 +865,35 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
   if (h.use_tree) {
     // ---- multi-level nested dissection (factor_tree.h): bottom-up, S_U -> T on its own stream, top-down ----------
     const TreePlan& t = h.tree;
-    TreeBufs<T> m;
-    m.A = Aint; m.Lf = Lint; m.Linv = LintInv; m.Ainv = Ainv; m.Bt = Bt; m.W = Wn;
-    m.SigPP = Sel; m.V = Sel + t.szA; m.C = Tm; m.R = K0U; m.Xp = Xh; m.G = G1;
+    TreeBufs<T> m = tree_bufs<T>(p);
     CudaTreeBK<T> bk{p, {st, sr, g_multi_stream ? p->s4 : sr}, tmpPanel};
+    if (phase == 1) {
+      // the assembled right-hand-side rows of the top count once in the all-reduce: rank 0 keeps them
+      if (t.part != 0 && t.rowsA > t.ra_top0)
+        CUDA_TRY(cudaMemsetAsync(K0U + t.ra_top0 * nU, 0, (t.rowsA - t.ra_top0) * nU * es, st));
+      tree_bottom_up<T>(t, nU, m, bk, one, zero, mone, 0, t.n_own_segs);
+      if (bk.rc) return bk.rc;
+      const int64_t r0 = t.ra0[t.part], r1 = t.ra1[t.part];
+      if (r1 > r0)                        // partial S_U over this rank's active rows -> the nU rows after the active block
+        schur_u_partial(p, sr, nU, r1 - r0, K0U + r0 * nU, Xh + r0 * nU, K0U + t.rowsA * nU);
+      if (t.roots_per_rank > 0) {
+        dim3 grid(cdiv(t.slot_sz, 256), t.roots_per_rank);
+        export_copy_kernel<T><<<grid, 256, 0, st>>>(t.part * t.roots_per_rank, -1, -1, p->d_exp_b, p->d_exp_offC, t.slot_sz,
+                                                    (T*)p->Tm, (T*)p->xg, 1);
+        CEIT_COUNT_LAUNCH();
+      }
+      bk.after(2, 1);
+      CEIT_AFTER(sr, st);
+      KERNEL_CHECK();
+      p->mode = -1;                        // half-factorised: only ceit_factor_phase(2) may follow
+      return 0;
+    }
     tree_bottom_up<T>(t, nU, m, bk, one, zero, mone);
     bk.after(2, 1);                                       // W of every level: needed by both top-down chains
     if (bk.rc) return bk.rc;
     KERNEL_CHECK();
     schur_u_gemm(p, sr, nU, t.rowsA, K0U, Xh, SU);      // S_U = K_UU - r^T t over the active rows of all levels
-    symmetrize_su(sr, nU, SU);
-    cudaStream_t s_t = sr;
-    if (g_multi_stream) {
-      s_t = p->s3;
-      CEIT_AFTER(sr, s_t);
-    }
-    if ((rc = base_shared_inverse<T>(p, s_t))) return rc;
-    CEIT_AFTER(sr, st);                                   // W of every level, A^-1
-    CUDA_TRY(cudaMemcpyAsync(Sel, Ainv, t.szA * es, cudaMemcpyDeviceToDevice, st));
-    const bool yt_sweep = yt_by_sweep(p);
-    if (yt_sweep)                                         // the X sweep overwrites t in place: keep the active rows
-      CUDA_TRY(cudaMemcpyAsync(p->tAct, Xh, t.rowsA * nU * es, cudaMemcpyDeviceToDevice, sr));
-    tree_top_down<T>(t, nU, m, bk, one, zero, mone);
-    if (bk.rc) return bk.rc;
-    if (yt_sweep) {
-      // Y_T = Xh T without the N x nU x nU product: (t T) over the active rows, then the same backward sweep
-      T *YP = (T*)p->YP, *Tinv = (T*)p->Tinv;
-      CEIT_AFTER(s_t, sr);
-      gemm<T>(sr, 0, 0, t.rowsA, nU, nU, one, (const T*)p->tAct, nU, 0, Tinv, nU, 0, zero, YP, nU, 0);
-      tree_back_sweep<T>(t, nU, Wn, G1, YP, bk, 1, zero, one, mone);
-      if (bk.rc) return bk.rc;
-    }
-    if ((rc = base_tail<T>(p, st, sr, s_t))) return rc;
-    KERNEL_CHECK();
-    p->mode = Sc<T>::is_complex ? 2 : 1;
+    if ((rc = factor_tree_finish<T>(p, st, sr, bk))) return rc;
     return 0;
   }
   // ---- level 1: eliminate the interiors (batched) -----------------------------------------------------
@@ -911,7 +1070,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st) {
 template <class T>
 int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
   const HostPlan& h = p->h;
-  const int64_t nU = h.nU, N = h.N, N0 = h.N0, u2 = nU * nU;   // compact position space
+  const int64_t nU = h.nU, N = h.Nc, N0 = h.N0c, u2 = nU * nU;   // compact position space
   T *St = (T*)p->St, *Ls = (T*)p->Ls, *Linvs = (T*)p->Linvs, *Sinv = (T*)p->Sinv, *Yh = (T*)p->Yh;
   T *phi0 = (T*)p->phi0, *tvec = (T*)p->tvec, *tmpS = (T*)p->tmpS, *Xh = (T*)p->Xh, *SU = (T*)p->SU;
   const T one = Sc<T>::one(), zero = Sc<T>::zero();
@@ -1037,7 +1196,7 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
 int excitation_chunk_cap(const ceit_plan* p, size_t es) {
   const HostPlan& h = p->h;
   const double budget = 24.0e9;  // bytes of Yh kept at once
-  double per = (double)h.N * h.nU * es + 4.0 * h.nU * h.nU * es;
+  double per = (double)h.Nc * h.nU * es + 4.0 * h.nU * h.nU * es;
   int cap = (int)std::max(1.0, std::min((double)h.L, budget / per));
   return cap;
 }
@@ -1048,12 +1207,12 @@ int launch_woodbury_patch(ceit_plan* p, const double* g0e, const double* Xh, con
   const HostPlan& h = p->h;
   const size_t psm = woodbury_patch_smem(h.nU, h.patch_node_cap);
   double4* consts = (double4*)p->tmpS;      // free after the batched factorisation of the excitation stage
-  node_consts_kernel<<<dim3(cdiv(h.nU, 128), nbatch), 128, 0, st>>>((int)h.nU, h.N, h.N0, phi0, p->d_wk, consts);
+  node_consts_kernel<<<dim3(cdiv(h.nU, 128), nbatch), 128, 0, st>>>((int)h.nU, h.Nc, h.N0c, phi0, p->d_wk, consts);
   CEIT_COUNT_LAUNCH();
   CUDA_TRY(cudaFuncSetAttribute(woodbury_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
   dim3 grid((unsigned)((int64_t)p->n_patches * nbatch));
   woodbury_patch_kernel<<<grid, WBP_WARPS * 32, psm, st>>>(e_from, e_to, (int)h.L, (int)h.nU, (int)woodbury_pitch(h.nU),
-                                                          h.N, h.N0, p->d_patch_eptr, p->d_patch_elems, p->d_patch_nptr,
+                                                          h.Nc, h.N0c, p->d_patch_eptr, p->d_patch_elems, p->d_patch_nptr,
                                                           p->d_patch_nodes, p->d_patch_local, p->d_area, g0e, Xh, Yh,
                                                           phi0, p->d_ue_ptr, consts, i0, s_coef, J, ldJ,
                                                           (int)h.patch_node_cap, nbatch);
@@ -1067,7 +1226,7 @@ int launch_woodbury_lr_consts(ceit_plan* p, int nbatch, cudaStream_t st) {
   const int nUp = (int)((h.nU + 1) & ~1LL), cst_len = (int)woodbury_lr_cst_len(h.nU, h.L);
   double* consts = (double*)p->tmpS;        // free after the batched factorisation of the excitation stage
   node_consts_soa_kernel<<<dim3(cdiv(std::max(h.nU, h.L), 128), nbatch), 128, 0, st>>>(
-      (int)h.nU, nUp, (int)h.L, cst_len, h.N, h.N0, (const double*)p->phi0, p->d_wk, p->d_ue_ptr, consts);
+      (int)h.nU, nUp, (int)h.L, cst_len, h.Nc, h.N0c, (const double*)p->phi0, p->d_wk, p->d_ue_ptr, consts);
   CEIT_COUNT_LAUNCH();
   return 0;
 }
@@ -1079,10 +1238,33 @@ int launch_woodbury_lr(ceit_plan* p, int e_from, int e_to, int nbatch, int i0, d
   CUDA_TRY(cudaFuncSetAttribute(woodbury_lr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
   dim3 grid((unsigned)((int64_t)p->n_patches * nbatch));
   woodbury_lr_kernel<<<grid, WBP_WARPS * 32, psm, st>>>(
-      e_from, e_to, (int)h.L, (int)h.nU, woodbury_lr_pitch((int)h.nU), (int)h.bp, h.N, h.N0, p->d_patch_eptr,
+      e_from, e_to, (int)h.L, (int)h.nU, woodbury_lr_pitch((int)h.nU), (int)h.bp, h.Nc, h.N0c, p->d_patch_eptr,
       p->d_patch_elems, p->d_patch_nptr, p->d_patch_nodes, p->d_patch_local, p->d_area, (const double*)p->g1e,
       (const double*)p->YT, (const double*)p->ye, (const double*)p->ZW, (const double*)p->Yh, (const double*)p->phi0,
       p->d_ue_ptr, consts, i0, s_coef, J, ldJ, (int)h.patch_node_cap, nbatch);
+  CEIT_COUNT_LAUNCH();
+  return 0;
+}
+
+int launch_woodbury_lr_persist(ceit_plan* p, int e_from, int e_to, int nbatch, int i0, double s_coef, double* J,
+                               int64_t ldJ, cudaStream_t st) {
+  const HostPlan& h = p->h;
+  const size_t psm = (size_t)wbq_smem_bytes(p->wbq.wmax, (int)h.L, h.patch_node_cap, (int)h.bp);
+  const double* consts = (const double*)p->tmpS;
+  if (p->sm_count == 0) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  CUDA_TRY(cudaFuncSetAttribute(woodbury_lr_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+  const int64_t n_items = (int64_t)p->n_patches * nbatch * p->wbq.n;
+  if (n_items == 0) return 0;
+  dim3 grid((unsigned)std::min<int64_t>(p->sm_count, n_items));
+  woodbury_lr_persist_kernel<<<grid, WBQ_THREADS, psm, st>>>(
+      e_from, e_to, (int)h.L, (int)h.nU, (int)h.bp, h.Nc, h.N0c, (int)n_items, p->wbq, p->d_patch_eptr, p->d_patch_elems,
+      p->d_patch_nptr, p->d_patch_nodes, p->d_patch_local, p->d_area, (const double*)p->g1e, (const double*)p->YT,
+      (const double*)p->ye, (const double*)p->ZW, (const double*)p->Yh, (const double*)p->phi0, p->d_ue_ptr, consts, i0,
+      s_coef, J, ldJ, (int)h.patch_node_cap, nbatch);
   CEIT_COUNT_LAUNCH();
   return 0;
 }
@@ -1111,7 +1293,7 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
     }
     if (rc) return rc;
     if (base) {
-      baseline_kernel<T><<<nbatch, 64, 0, st>>>((int)h.L, (int)h.nU, h.N, h.N0, (const T*)p->phi0, p->d_we_ptr,
+      baseline_kernel<T><<<nbatch, 64, 0, st>>>((int)h.L, (int)h.nU, h.Nc, h.N0c, (const T*)p->phi0, p->d_we_ptr,
                                                 p->d_we_u, p->d_we_w, (int)i0, base, nullptr);
       CEIT_COUNT_LAUNCH();
     }
@@ -1122,7 +1304,9 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
     if (e_to > e_from && J && use_patch) {
       if (lowrank && (rc = launch_woodbury_lr_consts(p, nbatch, st))) return rc;
       StageScope sc(3, st);
-      if (lowrank)
+      if (lowrank && p->wbq_ok && g_wb_persist)
+        rc = launch_woodbury_lr_persist(p, (int)e_from, (int)e_to, nbatch, (int)i0, 2.0 * omega * c, J, ldJ, st);
+      else if (lowrank)
         rc = launch_woodbury_lr(p, (int)e_from, (int)e_to, nbatch, (int)i0, 2.0 * omega * c, J, ldJ, st);
       else
         rc = launch_woodbury_patch(p, (const T*)p->g0e, (const T*)p->Xh, (const T*)p->Yh, (const T*)p->phi0, (int)e_from,
@@ -1131,7 +1315,7 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
     } else if (e_to > e_from && J) {
       StageScope sc(3, st);
       dim3 grid(cdiv(e_to - e_from, warps), nbatch);
-      woodbury_kernel<T><<<grid, warps * 32, smem, st>>>((int)e_from, (int)e_to, (int)h.L, (int)h.nU, h.N, h.N0,
+      woodbury_kernel<T><<<grid, warps * 32, smem, st>>>((int)e_from, (int)e_to, (int)h.L, (int)h.nU, h.Nc, h.N0c,
                                                          p->d_elem_pos, p->d_area, (const T*)p->g0e, (const T*)p->Xh,
                                                          (const T*)p->Yh, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
                                                          p->d_we_w, (int)i0, 2.0 * omega * c, J, ldJ);
@@ -1151,7 +1335,7 @@ int forward_impl(ceit_plan* p, int64_t i, double* node_abs, double* elem_pot, do
   rc = excitation_impl<T>(p, (int)i, 1, st);
   if (rc) return rc;
   if (electrode_pot) {
-    baseline_kernel<T><<<1, 64, 0, st>>>((int)h.L, (int)h.nU, h.N, h.N0, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
+    baseline_kernel<T><<<1, 64, 0, st>>>((int)h.L, (int)h.nU, h.Nc, h.N0c, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
                                          p->d_we_w, (int)i, nullptr, electrode_pot);
     CEIT_COUNT_LAUNCH();
   }
@@ -1233,12 +1417,17 @@ int ceit_plan_create(const double* nodes, const int64_t* elem, int64_t N, int64_
   ceit_plan* p = new ceit_plan();
   try {
     build_host_plan(p->h, nodes, elem, N, E, el_ptr, el_elems, L, target_block, g_nd_interior,
-                    g_nd_tree != 0 && target_block <= 0, g_nd_pull, g_nd_ways);
+                    g_nd_tree != 0 && target_block <= 0, g_nd_pull, g_nd_ways, g_shard_parts, g_shard_part);
     {
       // patches of <= 32 elements whose distinct node rows fit the shared-memory budget
       const bool lr = rank_update_shape_ok(p->h) && !g_direct_excitation && !g_no_lowrank;
       int64_t cap = g_patch_nodes > 0 ? std::min(g_patch_nodes, 64)
                                       : (lr ? woodbury_lr_cap(p->h.nU, p->h.bp, p->h.L) : woodbury_patch_cap(p->h.nU));
+      int qcap = 0;
+      if (lr && g_wb_persist && g_patch_nodes <= 0 && wbq_configure(p->h, &p->wbq, &qcap)) {
+        p->wbq_ok = true;
+        cap = qcap;
+      }
       if (cap < 3) cap = 3;
       build_patches(p->h, (int32_t)cap, 32);
     }
@@ -1376,14 +1565,46 @@ int ceit_factor(ceit_plan_t* p, int is_complex, void* stream) {
   if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_factor: null plan");
   if (!p->assembled) CEIT_FAIL(CEIT_ERR_STATE, "ceit_factor: call ceit_assemble first");
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->h.tree.parts > 1 && p->h.use_tree)
+    CEIT_FAIL(CEIT_ERR_STATE, "ceit_factor: a domain-decomposed plan is factorised with ceit_factor_phase(1), the exchange, ceit_factor_phase(2)");
   StageScope sc(1, st);
   return is_complex ? factor_impl<cd>(p, st) : factor_impl<double>(p, st);
+}
+
+int ceit_factor_phase(ceit_plan_t* p, int phase, void* stream) {
+  if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_factor_phase: null plan");
+  if (!p->assembled) CEIT_FAIL(CEIT_ERR_STATE, "ceit_factor_phase: call ceit_assemble first");
+  if (!p->h.use_tree || p->h.tree.parts <= 1) CEIT_FAIL(CEIT_ERR_STATE, "ceit_factor_phase: the plan is not domain-decomposed");
+  if (phase != 1 && phase != 2) CEIT_FAIL(CEIT_ERR_ARG, "ceit_factor_phase: phase must be 1 or 2");
+  if (!use_rank_update(p)) CEIT_FAIL(CEIT_ERR_STATE, "ceit_factor_phase: the decomposed path needs the rank-update excitation stage");
+  cudaStream_t st = (cudaStream_t)stream;
+  StageScope sc(1, st);
+  return factor_impl<double>(p, st, phase);
+}
+
+int ceit_plan_exchange(const ceit_plan_t* p, int64_t* info, void** gather_buf, void** reduce_buf) {
+  if (!p || !info) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_exchange: null argument");
+  const HostPlan& h = p->h;
+  const TreePlan& t = h.tree;
+  info[0] = t.parts; info[1] = t.part;
+  info[2] = (int64_t)t.roots_per_rank * t.slot_sz;                       // doubles per rank in the all-gather buffer
+  info[3] = h.use_tree ? (t.rowsA - t.ra_top0 + h.nU) * h.nU : 0;         // doubles in the all-reduce region
+  info[4] = h.Nc; info[5] = h.N0c; info[6] = t.dcut; info[7] = t.n_own_segs;
+  if (gather_buf) *gather_buf = p->xg;
+  if (reduce_buf) *reduce_buf = (p->K0U && h.use_tree) ? (void*)((double*)p->K0U + t.ra_top0 * h.nU) : nullptr;
+  return CEIT_OK;
+}
+
+int ceit_plan_own_elements(const ceit_plan_t* p, uint8_t* own) {
+  if (!p || !own) CEIT_FAIL(CEIT_ERR_ARG, "ceit_plan_own_elements: null argument");
+  for (int64_t e = 0; e < p->h.E; ++e) own[e] = p->h.elem_own[e];
+  return CEIT_OK;
 }
 
 int ceit_jacobian_block(ceit_plan_t* p, int64_t i_from, int64_t i_to, int64_t e_from, int64_t e_to, double c,
                         double omega, double* J, int64_t ldJ, double* base, void* stream) {
   if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_jacobian_block: null plan");
-  if (p->mode == 0) CEIT_FAIL(CEIT_ERR_STATE, "ceit_jacobian_block: call ceit_factor first");
+  if (p->mode <= 0) CEIT_FAIL(CEIT_ERR_STATE, "ceit_jacobian_block: call ceit_factor first");
   const HostPlan& h = p->h;
   if (i_from < 0 || i_to > h.L || i_from > i_to || e_from < 0 || e_to > h.E || e_from > e_to)
     CEIT_FAIL(CEIT_ERR_ARG, "ceit_jacobian_block: range out of bounds");
@@ -1397,8 +1618,10 @@ int ceit_jacobian_block(ceit_plan_t* p, int64_t i_from, int64_t i_to, int64_t e_
 int ceit_forward(ceit_plan_t* p, int64_t i, double* node_abs, double* elem_pot, double* electrode_pot,
                  void* stream) {
   if (!p) CEIT_FAIL(CEIT_ERR_ARG, "ceit_forward: null plan");
-  if (p->mode == 0) CEIT_FAIL(CEIT_ERR_STATE, "ceit_forward: call ceit_factor first");
+  if (p->mode <= 0) CEIT_FAIL(CEIT_ERR_STATE, "ceit_forward: call ceit_factor first");
   if (i < 0 || i >= p->h.L) CEIT_FAIL(CEIT_ERR_ARG, "ceit_forward: electrode index out of range");
+  if (p->h.tree.parts > 1 && p->h.use_tree)
+    CEIT_FAIL(CEIT_ERR_STATE, "ceit_forward: node potentials of the whole mesh need a plan without domain decomposition");
   cudaStream_t st = (cudaStream_t)stream;
   return p->mode == 2 ? forward_impl<cd>(p, i, node_abs, elem_pot, electrode_pot, st)
                       : forward_impl<double>(p, i, node_abs, elem_pot, electrode_pot, st);
@@ -1633,6 +1856,9 @@ int ceit_set_option(const char* name, int64_t value) {
     return CEIT_OK;
   }
   if (std::strcmp(name, "nd_pull") == 0) { g_nd_pull = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "shard_parts") == 0) { g_shard_parts = (int)std::max<int64_t>(1, value); return CEIT_OK; }
+  if (std::strcmp(name, "shard_part") == 0) { g_shard_part = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "wb_persist") == 0) { g_wb_persist = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "assemble_gather") == 0) { g_assemble_gather = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "yt_sweep") == 0) { g_yt_sweep = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "front_kernel") == 0) { g_front_kernel = (int)value; return CEIT_OK; }

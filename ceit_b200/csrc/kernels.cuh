@@ -171,6 +171,27 @@ scatter_dense_kernel(int nnz, const cd* __restrict__ vals, const int64_t* __rest
   else Bt[d] = v;
 }
 
+// Domain-decomposed base stage: the update matrices (b x b, boundary-padded) of the sub-tree roots travel through export
+// slots of `slot_sz` elements.  to_xg = 1: C storage -> slots [slot0, slot0 + gridDim.y) (this rank's roots);
+// to_xg = 0: slots -> C storage for every slot outside [skip0, skip1) (the other ranks' roots, after the all-gather).
+template <class T>
+__global__ void __launch_bounds__(256)
+export_copy_kernel(int slot0, int skip0, int skip1, const int32_t* __restrict__ exp_b, const int64_t* __restrict__ exp_offC,
+                   int64_t slot_sz, T* __restrict__ C, T* __restrict__ xg, int to_xg) {
+  const int slot = slot0 + blockIdx.y;
+  if (slot >= skip0 && slot < skip1) return;
+  const int64_t b = exp_b[slot], n = b * b;
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n) return;
+  if (to_xg) xg[slot * slot_sz + q] = C[exp_offC[slot] + q];
+  else C[exp_offC[slot] + q] = xg[slot * slot_sz + q];
+}
+template <class T>
+__global__ void add_lower_kernel(int64_t n, const T* __restrict__ P, T* __restrict__ S) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) S[q] = add(S[q], P[q]);
+}
+
 // nested dissection helpers ------------------------------------------------------------------------
 // identity on the diagonal of the unused (padding) slots of every interior block
 template <class T>
@@ -1127,6 +1148,7 @@ g1_kernel(int64_t E, int nU, const int32_t* __restrict__ elem_pos, const double*
   const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (e >= E) return;
   const int64_t p0 = elem_pos[3 * e], p1 = elem_pos[3 * e + 1], p2 = elem_pos[3 * e + 2];
+  if ((p0 | p1 | p2) < 0) return;                      // decomposed plan: an element of another rank's region
   const double *y0 = YT + p0 * nU, *y1 = YT + p1 * nU, *y2 = YT + p2 * nU;
   const double *x0 = Xh + p0 * nU, *x1 = Xh + p1 * nU, *x2 = Xh + p2 * nU;
   double d[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -1387,6 +1409,239 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
   }
 #undef CEIT_WB_TERM
   WB_CLK(7);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2, persistent pipelined form of the low-rank kernel (default when the shapes allow it).
+// The one-CTA-per-(patch, excitation) kernel above spends 45 % of a CTA's life before its main loop (staging,
+// 3x3 correction and solve; tools/wb_clocks.py) and a third of the SM time between CTAs.  Here ONE CTA per SM stays
+// resident and walks its share of the work items
+//     item = (patch, excitation, column chunk)         (chunks = electrode ranges whose first column is even)
+// through a ring of WBQ_SLOTS shared-memory slots: a PRODUCER warp stages item k + 2 (TMA bulk copies of the patch's
+// Yh rows and of the per-excitation constants, 8-byte cp.async for the small per-node arrays, all completing on the
+// slot's `full` mbarrier) while WBQ_GROUPS consumer groups of 8 warps each work on items k and k + 1 (correction of
+// the 3x3 blocks, solve, amplitude loop - the code of the kernel above); a group releases its slot through the `empty`
+// mbarrier.  Launch overhead, staging latency and the solve of one item hide behind the amplitude loops of the others.
+// Requires even nU (16-byte aligned rows).  Shared memory: 64 B of barriers, 12 x 32 doubles per group, then the slots
+//   [ cx | cy | cz (Wp each) | s0 (Lp) | Ys cap x pitchW | YB cap x zp | ZW cap x zp | ye cap | phi0 cap ].
+// ------------------------------------------------------------------------------------------------
+constexpr int WBQ_GROUPS = 2, WBQ_SLOTS = 3, WBQ_GW = 8;          // consumer groups, ring slots, warps per group
+constexpr int WBQ_THREADS = (WBQ_GROUPS * WBQ_GW + 1) * 32;
+struct WbqChunks {
+  int n;            // column chunks per (patch, excitation)
+  int el[5];        // electrode boundaries of the chunks: chunk c = electrodes [el[c], el[c + 1])
+  int wmax;         // widest chunk in columns (even)
+};
+__host__ __device__ inline int64_t wbq_slot_doubles(int wmax, int L, int cap, int bp) {
+  const int Wp = (wmax + 1) & ~1, Lp = (L + 1) & ~1;
+  int64_t d = 3 * (int64_t)Wp + Lp + (int64_t)cap * woodbury_lr_pitch(wmax) + 2 * (int64_t)cap * (bp + 1) + 2 * cap;
+  return (d + 1) & ~(int64_t)1;
+}
+__host__ __device__ inline int64_t wbq_smem_bytes(int wmax, int L, int cap, int bp) {
+  return 64 + (int64_t)WBQ_GROUPS * 12 * 32 * 8 + WBQ_SLOTS * wbq_slot_doubles(wmax, L, cap, bp) * 8;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// the barrier receives one arrival when every cp.async issued so far by this thread has landed (counted in the
+// barrier's initial count: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void group_bar(int g) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(1 + g), "r"(WBQ_GW * 32) : "memory");
+}
+
+__global__ void __launch_bounds__(WBQ_THREADS, 1)
+woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t N, int64_t N0, int n_items,
+                           WbqChunks ch, const int32_t* __restrict__ patch_eptr,
+                           const int32_t* __restrict__ patch_elems, const int32_t* __restrict__ patch_nptr,
+                           const int32_t* __restrict__ patch_nodes, const uint8_t* __restrict__ patch_local,
+                           const double* __restrict__ area, const double* __restrict__ g1e,
+                           const double* __restrict__ YT, const double* __restrict__ ye,
+                           const double* __restrict__ ZW, const double* __restrict__ Yh,
+                           const double* __restrict__ phi0, const int32_t* __restrict__ ue_ptr,
+                           const double* __restrict__ node_consts, int i0, double s_coef, double* __restrict__ J,
+                           int64_t ldJ, int cap, int nbatch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int zp = bp + 1;
+  const int nUp = (nU + 1) & ~1, Lp = (L + 1) & ~1, cst_len = 3 * nUp + Lp;
+  const int Wp = (ch.wmax + 1) & ~1, pitch = woodbury_lr_pitch(ch.wmax);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);          // [WBQ_SLOTS]
+  uint64_t* empty = full + WBQ_SLOTS;                              // [WBQ_SLOTS]
+  double* gbase = reinterpret_cast<double*>(smem_raw + 64);        // per group: ybuf [6][32], gbuf [6][32]
+  double* slots = gbase + WBQ_GROUPS * 12 * 32;
+  const int64_t slot_d = wbq_slot_doubles(ch.wmax, L, cap, bp);
+  // contiguous share of the items (excitation fastest, then chunk, then patch)
+  const int q0 = (int)(((int64_t)blockIdx.x * n_items) / gridDim.x);
+  const int q1 = (int)(((int64_t)(blockIdx.x + 1) * n_items) / gridDim.x);
+  const int n_my = q1 - q0;
+  if (threadIdx.x == 0) {
+    for (int sl = 0; sl < WBQ_SLOTS; ++sl) {
+      mbar_init(full + sl, 33);                                    // expect_tx arrival + 32 cp.async arrivals
+      mbar_init(empty + sl, WBQ_GW);                               // one arrival per consumer warp
+    }
+  }
+  __syncthreads();
+  const int per = nbatch * ch.n;
+  if (warp == WBQ_GROUPS * WBQ_GW) {
+    // ---------------------------------------- producer ------------------------------------------------
+    for (int it = 0; it < n_my; ++it) {
+      const int q = q0 + it, sl = it % WBQ_SLOTS, use = it / WBQ_SLOTS;
+      const int patch = q / per, r = q - patch * per, c = r / nbatch, b = r - c * nbatch;
+      const int i = i0 + b;
+      const int n_beg = patch_nptr[patch], nn = patch_nptr[patch + 1] - n_beg;
+      const int lo = ue_ptr[i], nb = ue_ptr[i + 1] - lo;
+      const int k0 = ue_ptr[ch.el[c]], W = ue_ptr[ch.el[c + 1]] - k0;
+      const int pn_a = (lane < nn) ? patch_nodes[n_beg + lane] : 0;
+      const int pn_b = (lane + 32 < nn) ? patch_nodes[n_beg + lane + 32] : 0;
+      double* cst = slots + sl * slot_d;
+      double* Ys = cst + 3 * Wp + Lp;
+      double* YB = Ys + (int64_t)cap * pitch;
+      double* ZWs = YB + cap * zp;
+      double* yes = ZWs + cap * zp;
+      double* phs = yes + cap;
+      const double* Y = Yh + (int64_t)b * N * nU + k0;
+      const double* ph = phi0 + (int64_t)b * N;
+      const double* Z = ZW + (int64_t)b * zp;
+      const int64_t ldz = (int64_t)nbatch * zp;
+      const double* cg = node_consts + (int64_t)b * cst_len;
+      if (use > 0) mbar_wait(empty + sl, (use - 1) & 1);           // the slot's previous item has been consumed
+      if (lane == 0) {
+        mbar_expect_tx(full + sl, (uint32_t)(((int64_t)nn * W + 3 * W + Lp) * 8));
+        bulk_g2s(cst, cg + k0, (uint32_t)(W * 8), full + sl);
+        bulk_g2s(cst + Wp, cg + nUp + k0, (uint32_t)(W * 8), full + sl);
+        bulk_g2s(cst + 2 * Wp, cg + 2 * nUp + k0, (uint32_t)(W * 8), full + sl);
+        bulk_g2s(cst + 3 * Wp, cg + 3 * nUp, (uint32_t)(Lp * 8), full + sl);
+      }
+      __syncwarp();
+      if (lane < nn) bulk_g2s(Ys + (int64_t)lane * pitch, Y + (int64_t)pn_a * nU, (uint32_t)(W * 8), full + sl);
+      if (lane + 32 < nn) bulk_g2s(Ys + (int64_t)(lane + 32) * pitch, Y + (int64_t)pn_b * nU, (uint32_t)(W * 8), full + sl);
+      for (int n = 0; n < nn; ++n) {
+        const int64_t pp = __shfl_sync(0xffffffffu, (n < 32) ? pn_a : pn_b, n & 31);
+        if (lane < nb) cp_async8(YB + n * zp + lane, YT + pp * nU + lo + lane, true);
+        if (lane + 32 < nb) cp_async8(YB + n * zp + lane + 32, YT + pp * nU + lo + lane + 32, true);
+        if (lane < zp) cp_async8(ZWs + n * zp + lane, Z + pp * ldz + lane, true);
+        if (lane + 32 < zp) cp_async8(ZWs + n * zp + lane + 32, Z + pp * ldz + lane + 32, true);
+        if (lane + 64 < zp) cp_async8(ZWs + n * zp + lane + 64, Z + pp * ldz + lane + 64, true);
+        if (lane == 0) cp_async8(yes + n, ye + pp, true);
+        if (lane == 1) cp_async8(phs + n, ph + pp, true);
+      }
+      cp_async_mbar_arrive(full + sl);
+    }
+    return;
+  }
+  // ------------------------------------------ consumers ----------------------------------------------
+  const int g = warp / WBQ_GW, wg = warp % WBQ_GW;
+  double* ybuf = gbase + g * 12 * 32;
+  double* gbuf = ybuf + 6 * 32;
+  for (int it = g; it < n_my; it += WBQ_GROUPS) {
+    const int q = q0 + it, sl = it % WBQ_SLOTS, use = it / WBQ_SLOTS;
+    const int patch = q / per, r = q - patch * per, c = r / nbatch, b = r - c * nbatch;
+    const int i = i0 + b;
+    const int el_beg = patch_eptr[patch], ne = patch_eptr[patch + 1] - el_beg;
+    const int nb = ue_ptr[i + 1] - ue_ptr[i];
+    const int k0 = ue_ptr[ch.el[c]];
+    const double* cst = slots + sl * slot_d;
+    const double* Ys = cst + 3 * Wp + Lp;
+    const double* YB = Ys + (int64_t)cap * pitch;
+    const double* ZWs = YB + cap * zp;
+    const double* yes = ZWs + cap * zp;
+    const double* phs = yes + cap;
+    const bool have = lane < ne;
+    const int lq = have ? lane : 0;
+    const int j = patch_elems[el_beg + lq];
+    const int l0 = patch_local[3 * (el_beg + lq)], l1 = patch_local[3 * (el_beg + lq) + 1],
+              l2 = patch_local[3 * (el_beg + lq) + 2];
+    const int la = (wg == 0 || wg == 3) ? l0 : ((wg == 1 || wg == 4) ? l1 : l2);
+    const int lb = (wg == 0 || wg == 5) ? l0 : ((wg == 1 || wg == 3) ? l1 : l2);
+    double gq = 0.0, sj = 0.0;
+    if (wg < 6) gq = g1e[6 * (int64_t)j + wg];
+    if (wg == 0) sj = s_coef * area[j];
+    mbar_wait(full + sl, use & 1);
+    if (wg < 6) {
+      const double* yb = YB + la * zp;
+      const double* zw = ZWs + lb * zp;
+      double a0 = yes[la] * zw[bp], a1 = 0.0;
+      int jj = 0;
+      for (; jj + 1 < nb; jj += 2) {
+        a0 = fma(-yb[jj], zw[jj], a0);
+        a1 = fma(-yb[jj + 1], zw[jj + 1], a1);
+      }
+      if (jj < nb) a0 = fma(-yb[jj], zw[jj], a0);
+      gbuf[wg * 32 + lane] = gq + (a0 + a1);
+    }
+    group_bar(g);
+    if (wg == 0) {
+      double g6[6];
+#pragma unroll
+      for (int qq = 0; qq < 6; ++qq) g6[qq] = gbuf[qq * 32 + lane];
+      const double f[3] = {phs[l0], phs[l1], phs[l2]};
+      double yr[3], yi[3];
+      solve3_real(g6, sj, f, yr, yi);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        ybuf[a * 32 + lane] = yr[a];
+        ybuf[(3 + a) * 32 + lane] = yi[a];
+      }
+    }
+    group_bar(g);
+    const double yr0 = ybuf[lane], yr1 = ybuf[32 + lane], yr2 = ybuf[64 + lane];
+    const double yi0 = ybuf[96 + lane], yi1 = ybuf[128 + lane], yi2 = ybuf[160 + lane];
+    // pointers biased by -k0 so that k stays the global electrode-node index (k0 is even: 16-byte alignment of even k)
+    const double* y0 = Ys + (int64_t)l0 * pitch - k0;
+    const double* y1 = Ys + (int64_t)l1 * pitch - k0;
+    const double* y2 = Ys + (int64_t)l2 * pitch - k0;
+    const double *cx = cst - k0, *cy = cst + Wp - k0, *cz = cst + 2 * Wp - k0, *s0 = cst + 3 * Wp;
+#define CEIT_WB_TERM(ACC, A0, A1, A2, CX, CY, CZ)                 \
+  {                                                               \
+    const double dr = fma(A0, yr0, fma(A1, yr1, (A2) * yr2));     \
+    const double di = fma(A0, yi0, fma(A1, yi1, (A2) * yi2));     \
+    const double qq = fma(dr, dr, di * di);                       \
+    const double x = fma(CX, dr, qq * (CY));                      \
+    hmax = max(hmax, abs_hi(x));                                  \
+    ACC = fma(CZ, sqrt1p_minus1_poly(x), ACC);                    \
+  }
+    const bool write = have && j >= e_from && j < e_to;
+    for (int m = ch.el[c] + wg; m < ch.el[c + 1]; m += WBQ_GW) {
+      if (m == i) continue;
+      const int ks = ue_ptr[m], ke = ue_ptr[m + 1];
+      double sumt = 0.0, sumu = 0.0;
+      unsigned hmax = 0u;
+      int k = ks;
+      if ((k & 1) && k < ke) {
+        CEIT_WB_TERM(sumt, y0[k], y1[k], y2[k], cx[k], cy[k], cz[k]);
+        ++k;
+      }
+#pragma unroll 2
+      for (; k + 1 < ke; k += 2) {
+        const double2 a0 = *reinterpret_cast<const double2*>(y0 + k);
+        const double2 a1 = *reinterpret_cast<const double2*>(y1 + k);
+        const double2 a2 = *reinterpret_cast<const double2*>(y2 + k);
+        const double2 vx = *reinterpret_cast<const double2*>(cx + k);
+        const double2 vy = *reinterpret_cast<const double2*>(cy + k);
+        const double2 vz = *reinterpret_cast<const double2*>(cz + k);
+        CEIT_WB_TERM(sumt, a0.x, a1.x, a2.x, vx.x, vy.x, vz.x);
+        CEIT_WB_TERM(sumu, a0.y, a1.y, a2.y, vx.y, vy.y, vz.y);
+      }
+      if (k < ke) CEIT_WB_TERM(sumt, y0[k], y1[k], y2[k], cx[k], cy[k], cz[k]);
+      sumt += sumu;
+      if (hmax >= SQRT1P_HI_LIMIT) {                       // rare: a large perturbation, exact square roots
+        sumt = 0.0;
+        for (int qx = ks; qx < ke; ++qx) {
+          const double dr = fma(y0[qx], yr0, fma(y1[qx], yr1, y2[qx] * yr2));
+          const double di = fma(y0[qx], yi0, fma(y1[qx], yi1, y2[qx] * yi2));
+          const double qq = fma(dr, dr, di * di);
+          sumt = fma(cz[qx], sqrt1p_minus1(fma(cx[qx], dr, qq * cy[qx])), sumt);
+        }
+      }
+      if (write) J[((int64_t)i * (L - 1) + m - (m > i ? 1 : 0)) * ldJ + j] = fabs(s0[m] + sumt);
+    }
+#undef CEIT_WB_TERM
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + sl);                 // this warp no longer reads the slot
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -146,3 +146,129 @@ class ShardedStep:
         if self._work is not None:
             self._work.wait()
             self._work = None
+
+
+class _DevMem:
+    """A library-owned device allocation seen as a 1-D float64 array (zero copy, __cuda_array_interface__)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
+class DomainStep:
+    """One material state on G GPUs by DOMAIN DECOMPOSITION (north_star: "the element loop shards by element range").
+
+    The reference's parallel axis is the excitation range (`calc_from` / `calc_end`, CEIT/EJAC.py:107-119); sharding
+    the excitations leaves the base stage replicated.  Here the mesh itself is decomposed: the plan of rank r
+    (`Plan(..., parts=G, part=r)`) owns the sub-trees of one region of the elimination forest, the top of the forest is
+    replicated.  Per step:
+
+      assemble -> factor_phase(1) -> exchange (ONE all-gather of the sub-tree roots' update matrices, ONE all-reduce of
+      the top's right-hand-side rows + the partial S_U) -> factor_phase(2) -> jacobian: the columns of the rank's OWN
+      elements for all L excitations -> inverse model: partial Gram matrix of the rank's own detection columns, one
+      all-reduce of m x m, the rank's rows of inv_mat.
+
+    The base stage, the per-excitation stage, the Woodbury kernel and the inverse model all work on 1/G of the mesh; J
+    never has to be exchanged for the inverse model - `gather_jacobian()` replicates it only because the reference's
+    contract returns the whole matrix (it can overlap the inverse model on a second communicator).
+    """
+
+    def __init__(self, nodes, elem, electrodes, det, group=None, plan=None):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self.torch, self.dist, self._lib = torch, dist, _lib
+        self.group = group
+        self.ws = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.plan = plan if plan is not None else _lib.Plan(nodes, elem, electrodes, parts=self.ws, part=self.rank)
+        self.L, self.E = self.plan.L, self.plan.E
+        self.m = self.L * (self.L - 1)
+        dev = det.device
+        own = torch.from_numpy(self.plan.own_elements()).to(dev)
+        self.own_idx = torch.nonzero(own).flatten()                       # element ids of this rank, ascending
+        counts = torch.zeros(self.ws, dtype=torch.int64, device=dev)
+        counts[self.rank] = self.own_idx.numel()
+        dist.all_reduce(counts, group=group)
+        self.counts = [int(c) for c in counts.tolist()]
+        self.e_max = max(self.counts)
+        det_own = own[det]
+        self.det = det
+        self.det_pos = torch.nonzero(det_own).flatten()                    # rows of inv_mat this rank produces
+        self.det_local = det[det_own].contiguous()                         # their element ids (columns of J)
+        self._xg = self._red = None
+        self._pack = torch.zeros((self.m, self.e_max), dtype=torch.float64, device=dev)
+        self._all = torch.empty((self.ws, self.m, self.e_max), dtype=torch.float64, device=dev)
+        self._idx_all = None
+        self.nccl = dist.get_backend(group) == "nccl"
+        self.repl_group = dist.new_group(ranks=list(range(self.ws)), backend="nccl") if self.nccl else group
+        self._work = None
+        self.exchange_bytes = 0
+
+    # ---- base stage -------------------------------------------------------------------------------------------
+    def _buffers(self):
+        info, g, r = self.plan.exchange_info()
+        per, nred = int(info[2]), int(info[3])
+        dev = self.det.device
+        self._xg = self.torch.as_tensor(_DevMem(g, max(per * self.ws, 1)), device=dev) if g and per else None
+        self._red = self.torch.as_tensor(_DevMem(r, nred), device=dev) if r and nred else None
+        self._per = per
+        self._gen = self.plan.generation()
+        self.exchange_bytes = 8 * (per * (self.ws - 1) + 2 * nred)
+
+    def base_exchange(self):
+        """The one exchange of the base stage (between factor_phase(1) and factor_phase(2)), on the current stream."""
+        if self._red is None or self._gen != self.plan.generation():
+            self._buffers()
+        if self._xg is not None:
+            mine = self._xg[self.rank * self._per:(self.rank + 1) * self._per]
+            self.dist.all_gather_into_tensor(self._xg, mine, group=self.group)
+        self.dist.all_reduce(self._red, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def factor(self, perm, var, omega):
+        self.plan.assemble(perm, var, omega)
+        self.plan.factor_phase(1)
+        self.base_exchange()
+        self.plan.factor_phase(2)
+
+    # ---- Jacobian columns of this rank's elements ----------------------------------------------------------------
+    def jacobian(self, c, omega, J, base=None):
+        self.plan.jacobian_block(0, self.L, 0, self.E, c, omega, J, J.stride(0), base)
+
+    def inverse_model(self, J, lmbda, shift=1.0, flag=None):
+        """This rank's rows of inv_mat (rows `det_pos` of the whole model), from its own columns of J."""
+        return self._lib.inverse_model_sharded(J, self.det_local, lmbda, shift=shift, group=self.group, flag=flag)
+
+    # ---- replication of J (output contract only) ------------------------------------------------------------------
+    def gather_jacobian(self, J, async_op=False):
+        torch, dist = self.torch, self.dist
+        if self._idx_all is None:
+            idx = torch.full((self.ws, self.e_max), -1, dtype=torch.int64, device=J.device)
+            idx[self.rank, :self.own_idx.numel()] = self.own_idx
+            mine = idx[self.rank].clone()
+            dist.all_gather_into_tensor(idx, mine, group=self.group)
+            self._idx_all = [idx[r, :self.counts[r]].contiguous() for r in range(self.ws)]
+        n = self.own_idx.numel()
+        if n:
+            torch.index_select(J, 1, self.own_idx, out=self._pack[:, :n])
+        if self.nccl:
+            work = dist.all_gather_into_tensor(self._all, self._pack, group=self.repl_group, async_op=True)
+            self._work = (work, J)
+            if not async_op:
+                self.finish()
+        else:
+            dist.all_gather_into_tensor(self._all, self._pack, group=self.group)
+            self._work = (None, J)
+            self.finish()
+        return J
+
+    def finish(self):
+        if self._work is None:
+            return
+        work, J = self._work
+        if work is not None:
+            work.wait()
+        for r in range(self.ws):
+            if r != self.rank and self.counts[r]:
+                J.index_copy_(1, self._idx_all[r], self._all[r][:, :self.counts[r]])
+        self._work = None

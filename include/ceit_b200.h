@@ -107,6 +107,27 @@ int ceit_plan_csr_values(const ceit_plan_t* plan, double* vals, void* stream);
  * is_complex: 0 = real path (requires var == 0 everywhere), 1 = complex symmetric path. */
 int ceit_factor(ceit_plan_t* plan, int is_complex, void* stream);
 
+/* ---- K3 on several GPUs: domain-decomposed base stage ------------------------------------------------
+ * The reference's only parallel axis is the excitation range calc_from / calc_end (CEIT/EJAC.py:107-119); here the
+ * MESH is decomposed instead (north_star: "the element loop shards by element range"): a plan created after
+ * ceit_set_option("shard_parts", G) / ("shard_part", r) cuts the elimination forest of K00 at the smallest depth with
+ * >= G sub-trees; rank r factorises the sub-trees of its region, every rank the shared top, and everything downstream
+ * (X, Y_T, the per-excitation updates, the Woodbury kernel) runs on the rank's own node rows and elements only - so
+ * the base stage, the excitation stage and the element loop all shrink with G, and the inverse model is fed by the
+ * rank's own Jacobian columns (ceit_gram_partial / ceit_inverse_from_gram; J itself is only gathered for output).
+ * Sequence per material state (real path):
+ *     ceit_assemble; ceit_factor_phase(plan, 1, s);
+ *     [caller, NCCL on stream s]  all-gather(gather_buf: info[2] doubles per rank, in place),
+ *                                 all-reduce-sum(reduce_buf: info[3] doubles)
+ *     ceit_factor_phase(plan, 2, s); ceit_jacobian_block(...)   -> columns of ceit_plan_own_elements only
+ * ceit_plan_exchange: info i64[8] = {G, r, doubles per rank of gather_buf, doubles of reduce_buf, rows held by this
+ * rank (Nc), of which non-electrode (N0c), cut depth, rank-owned segments}; the buffer pointers [dev] are valid
+ * after the first ceit_factor_phase(1) and until the plan is destroyed or changes between real and complex. */
+int ceit_factor_phase(ceit_plan_t* plan, int phase, void* stream);
+int ceit_plan_exchange(const ceit_plan_t* plan, int64_t* info, void** gather_buf, void** reduce_buf);
+/* own [host] u8[E]: 1 = this rank computes the element's Jacobian columns (all 1 without decomposition) */
+int ceit_plan_own_elements(const ceit_plan_t* plan, uint8_t* own);
+
 /* ---- K2: Jacobian block ------------------------------------------------------------------------
  * Replaces EJAC.JAC_calculation's double loop (CEIT/EJAC.py:115-133): for excitations
  * [i_from,i_to) (calc_from/calc_end semantics) and elements [e_from,e_to): perturb element j by
@@ -236,6 +257,12 @@ int ceit_debug_tile_clocks(int64_t* out8);
  *   "ru_wc", "ru_cpt", "ru_waves"
  *                       rank-update kernel: force the column layout (warps across x columns per thread; 0 =
  *                       cost model) and the number of CTA waves (default 8); tools/ru_sweep.sh
+ *   "shard_parts", "shard_part"
+ *                       plans created afterwards: domain decomposition over G ranks, this process being rank r
+ *                       (default 1 / 0 = none); see ceit_factor_phase
+ *   "wb_persist"        (default 1) low-rank Woodbury stage as ONE persistent CTA per SM walking (patch, excitation,
+ *                       column chunk) items through a 3-slot TMA ring with two consumer groups (even nU); 0 = one CTA
+ *                       per (patch, excitation)
  *   "assemble_gather"   (default 0) 1: K1 as one thread per CSR slot re-deriving the triangle geometry of each of its
  *                       contributions (round-1 form); 0 = element-parallel pass (geometry once per element, stores
  *                       into the slot-sorted contribution list) + segmented sum per CSR slot

@@ -434,3 +434,121 @@ def test_element_parallel_assembly_equals_gather_form_and_reference(torch_cuda, 
     import scipy.sparse as sp
     K = sp.csr_matrix((out[0][:, 0] + 1j * out[0][:, 1], colidx, rowptr), shape=(len(m["nodes"]),) * 2)
     assert abs(K - K.T).max() == 0
+
+
+@pytest.mark.parametrize("tag,parts", [("50_50", 2), ("50_50", 4), ("21_21", 4)])
+def test_domain_decomposed_step_equals_single_plan(torch_cuda, golden, tag, parts):
+    """The multi-GPU base stage (ceit_factor_phase) with its ranks run one after the other on ONE device: the
+    exchange between the two halves is done here with plain copies / sums instead of NCCL.  Every rank's Jacobian
+    columns (its own elements, all excitations) and its rows of the inverse model against the undecomposed plan and
+    the reference's J."""
+    from ceit_b200.sharding import _DevMem
+    t = torch_cuda
+    m, r = golden(tag)
+    N, E, L = len(m["nodes"]), len(m["elem"]), 16
+    omega = 2 * np.pi * float(r["signal_frequency"])
+    c = float(r["variable_change_for_JAC"])
+    perm = t.tensor(m["elem_perm"], device="cuda")
+    var = t.zeros(E, dtype=t.float64, device="cuda")
+    det = t.tensor(m["detection_index"], device="cuda")
+    # the undecomposed plan
+    p0 = _lib.Plan(m["nodes"], m["elem"], m["electrodes"])
+    J0 = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
+    b0 = t.zeros(L * (L - 1), dtype=t.float64, device="cuda")
+    p0.assemble(perm, var, omega)
+    p0.factor(False)
+    p0.jacobian_block(0, L, 0, E, c, omega, J0, E, b0)
+    inv0 = _lib.inverse_model(J0, det, 289.0, shift=1.0, form=2)
+    with pytest.raises(_lib.CeitError):
+        _lib.Plan(m["nodes"], m["elem"], m["electrodes"], parts=parts, part=0).factor(False)
+    plans = [_lib.Plan(m["nodes"], m["elem"], m["electrodes"], parts=parts, part=q) for q in range(parts)]
+    own = np.stack([p.own_elements() for p in plans])
+    assert (own.sum(axis=0) == 1).all()                       # the elements are partitioned
+    for p in plans:
+        p.assemble(perm, var, omega)
+        p.factor_phase(1)
+    t.cuda.synchronize()
+    bufs = []
+    for p in plans:
+        info, g, rr = p.exchange_info()
+        assert info[0] == parts and info[4] < N               # a strict subset of the node rows per rank
+        per, nred = int(info[2]), int(info[3])
+        bufs.append((t.as_tensor(_DevMem(g, per * parts), device="cuda") if per else None,
+                     t.as_tensor(_DevMem(rr, nred), device="cuda")))
+    total = sum(b[1] for b in bufs)
+    for q, (xg, red) in enumerate(bufs):
+        red.copy_(total)
+        if xg is not None:
+            for s in range(parts):
+                if s != q:
+                    xg[s * per:(s + 1) * per] = bufs[s][0][s * per:(s + 1) * per]
+    J = t.zeros_like(J0)
+    for q, p in enumerate(plans):
+        p.factor_phase(2)
+        Jq = t.zeros_like(J0)
+        bq = t.zeros_like(b0)
+        p.jacobian_block(0, L, 0, E, c, omega, Jq, E, bq)
+        assert p.numeric_flag() == 0
+        mask = t.from_numpy(own[q]).to("cuda")
+        assert float(Jq[:, ~mask].abs().max()) == 0.0         # nothing outside the rank's own columns
+        assert float((bq - b0).abs().max()) < 1e-12
+        J[:, mask] = Jq[:, mask]
+        # this rank's rows of the inverse model from its own detection columns (Gram matrices summed by hand below)
+    assert float((J - J0).abs().max()) < 1e-12
+    assert float(t.linalg.norm(J - J0) / t.linalg.norm(J0 - 1)) < 1e-6
+    if "JAC" in r:
+        Jh = J.cpu().numpy()
+        assert np.abs(Jh - r["JAC"]).max() < RAW_TOL
+        assert np.linalg.norm(Jh - r["JAC"]) / np.linalg.norm(r["JAC"] - 1) < SIGNAL_TOL
+    # inverse model sharded by the same element ownership: partial Gram matrices of the own detection columns
+    mrows = L * (L - 1)
+    G = t.zeros((mrows, mrows), dtype=t.float64, device="cuda")
+    dets = []
+    for q in range(parts):
+        mask = t.from_numpy(own[q]).to("cuda")
+        sel = mask[det]
+        dets.append((t.nonzero(sel).flatten(), det[sel].contiguous()))
+        Gq = t.empty_like(G)
+        _lib.check(_lib.lib().ceit_gram_partial(_lib.tptr(J), E, mrows, _lib.tptr(dets[q][1]), dets[q][1].numel(),
+                                                _lib.tptr(None), mrows, 1.0, _lib.tptr(Gq), _lib.stream_ptr()))
+        G += Gq
+    inv = t.zeros_like(inv0)
+    for q in range(parts):
+        posq, dq = dets[q]
+        out = t.empty((dq.numel(), mrows), dtype=t.float64, device="cuda")
+        _lib.check(_lib.lib().ceit_inverse_from_gram(_lib.tptr(J), E, mrows, _lib.tptr(dq), dq.numel(), _lib.tptr(None),
+                                                     mrows, 1.0, 289.0, 1.0, _lib.tptr(G), _lib.tptr(out), _lib.tptr(None),
+                                                     _lib.stream_ptr()))
+        inv[posq] = out
+    assert float((inv - inv0).abs().max() / inv0.abs().max()) < MODEL_TOL
+
+
+def test_persistent_woodbury_kernel_equals_per_cta_kernel(torch_cuda, golden):
+    """K2: the persistent pipelined kernel (default) against the one-CTA-per-(patch, excitation) kernel, bit for bit
+    (same arithmetic per column), incl. a partial excitation / element range."""
+    t = torch_cuda
+    for tag in ("21_21", "50_50"):
+        m, r = golden(tag)
+        E, L = len(m["elem"]), 16
+        omega = 2 * np.pi * float(r["signal_frequency"])
+        c = float(r["variable_change_for_JAC"])
+        perm = t.tensor(m["elem_perm"], device="cuda")
+        var = t.zeros(E, dtype=t.float64, device="cuda")
+        p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"])
+        p.assemble(perm, var, omega)
+        p.factor(False)
+        outs = []
+        for persist in (1, 0):
+            _lib.set_option("wb_persist", persist)
+            try:
+                J = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
+                p.jacobian_block(0, L, 0, E, c, omega, J, E)
+                J2 = t.zeros_like(J)
+                p.jacobian_block(3, 7, E // 5, E // 2, c, omega, J2, E)
+            finally:
+                _lib.set_option("wb_persist", 1)
+            outs.append((J, J2))
+        assert t.equal(outs[0][0], outs[1][0]) and t.equal(outs[0][1], outs[1][1])
+        assert float(outs[0][1][:3 * (L - 1)].abs().max()) == 0.0 and float(outs[0][1][:, :E // 5].abs().max()) == 0.0
+        if "JAC" in r:
+            assert np.abs(outs[0][0].cpu().numpy() - r["JAC"]).max() < RAW_TOL

@@ -1838,6 +1838,13 @@ int ceit_debug_wb_clocks(int64_t* out) {   // out[16]: CTA 81 (first wave) in [0
   return CEIT_OK;
 }
 
+int ceit_debug_wbq_clocks(int64_t* out) {  // out[512]: see WBQ_CLK in kernels.cuh
+  static long long h[512];
+  CUDA_TRY(cudaMemcpyFromSymbol(h, ceit::g_wbq_clk, sizeof(h)));
+  for (int k = 0; k < 512; ++k) out[k] = h[k];
+  return CEIT_OK;
+}
+
 int ceit_debug_tile_clocks(int64_t* out) {
   long long h[8];
   CUDA_TRY(cudaMemcpyFromSymbol(h, ceit::g_tile_clk, sizeof(h)));

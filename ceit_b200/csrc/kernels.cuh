@@ -917,6 +917,14 @@ __device__ long long g_wb_clk[16];
 #else
 #define WB_CLK(q) do { } while (0)
 #endif
+// persistent kernel: per item of CTA 7, consumer group 0 (6 stamps) in [16 it, 16 it + 6) and the producer (3 stamps)
+// in [16 it + 8, 16 it + 11)
+__device__ long long g_wbq_clk[32 * 16];
+#ifdef CEIT_TILE_CLOCKS
+#define WBQ_CLK(it, q) do { if (blockIdx.x == 7 && lane == 0 && (it) < 32) g_wbq_clk[16 * (it) + (q)] = clock64(); } while (0)
+#else
+#define WBQ_CLK(it, q) do { } while (0)
+#endif
 
 // Real-base closed form of y = (I + j B)^-1 (j g), B = s M G real, g = s M f real (f = phi0 at the
 // element's nodes, real on the real path):  (I + jB)^-1 = C (I - jB), C = (I + B^2)^-1  =>
@@ -1417,7 +1425,7 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
 // 3x3 correction and solve; tools/wb_clocks.py) and a third of the SM time between CTAs.  Here ONE CTA per SM stays
 // resident and walks its share of the work items
 //     item = (patch, excitation, column chunk)         (chunks = electrode ranges whose first column is even)
-// through a ring of WBQ_SLOTS shared-memory slots: a PRODUCER warp stages item k + 2 (TMA bulk copies of the patch's
+// through a ring of WBQ_SLOTS shared-memory slots: WBQ_PW PRODUCER warps stage item k + 2 (TMA bulk copies of the patch's
 // Yh rows and of the per-excitation constants, 8-byte cp.async for the small per-node arrays, all completing on the
 // slot's `full` mbarrier) while WBQ_GROUPS consumer groups of 8 warps each work on items k and k + 1 (correction of
 // the 3x3 blocks, solve, amplitude loop - the code of the kernel above); a group releases its slot through the `empty`
@@ -1426,7 +1434,9 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
 //   [ cx | cy | cz (Wp each) | s0 (Lp) | Ys cap x pitchW | YB cap x zp | ZW cap x zp | ye cap | phi0 cap ].
 // ------------------------------------------------------------------------------------------------
 constexpr int WBQ_GROUPS = 2, WBQ_SLOTS = 3, WBQ_GW = 8;          // consumer groups, ring slots, warps per group
-constexpr int WBQ_THREADS = (WBQ_GROUPS * WBQ_GW + 1) * 32;
+constexpr int WBQ_PW = 4;                                         // producer warps (the 8-byte cp.async of the small
+                                                                  // per-node arrays cost ~80 issue cycles each: one warp took 10k cycles per item)
+constexpr int WBQ_THREADS = (WBQ_GROUPS * WBQ_GW + WBQ_PW) * 32;
 struct WbqChunks {
   int n;            // column chunks per (patch, excitation)
   int el[5];        // electrode boundaries of the chunks: chunk c = electrodes [el[c], el[c + 1])
@@ -1479,18 +1489,20 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
   const int n_my = q1 - q0;
   if (threadIdx.x == 0) {
     for (int sl = 0; sl < WBQ_SLOTS; ++sl) {
-      mbar_init(full + sl, 33);                                    // expect_tx arrival + 32 cp.async arrivals
+      mbar_init(full + sl, 1 + 32 * WBQ_PW);                       // expect_tx arrival + one cp.async arrival per producer thread
       mbar_init(empty + sl, WBQ_GW);                               // one arrival per consumer warp
     }
   }
   __syncthreads();
   const int per = nbatch * ch.n;
-  if (warp == WBQ_GROUPS * WBQ_GW) {
-    // ---------------------------------------- producer ------------------------------------------------
+  if (warp >= WBQ_GROUPS * WBQ_GW) {
+    // ---------------------------------------- producers -----------------------------------------------
+    const int pw = warp - WBQ_GROUPS * WBQ_GW;                     // warp 0: TMA rows + constants; all: the small arrays
     for (int it = 0; it < n_my; ++it) {
       const int q = q0 + it, sl = it % WBQ_SLOTS, use = it / WBQ_SLOTS;
       const int patch = q / per, r = q - patch * per, c = r / nbatch, b = r - c * nbatch;
       const int i = i0 + b;
+      WBQ_CLK(it, 8);
       const int n_beg = patch_nptr[patch], nn = patch_nptr[patch + 1] - n_beg;
       const int lo = ue_ptr[i], nb = ue_ptr[i + 1] - lo;
       const int k0 = ue_ptr[ch.el[c]], W = ue_ptr[ch.el[c + 1]] - k0;
@@ -1508,27 +1520,38 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
       const int64_t ldz = (int64_t)nbatch * zp;
       const double* cg = node_consts + (int64_t)b * cst_len;
       if (use > 0) mbar_wait(empty + sl, (use - 1) & 1);           // the slot's previous item has been consumed
-      if (lane == 0) {
-        mbar_expect_tx(full + sl, (uint32_t)(((int64_t)nn * W + 3 * W + Lp) * 8));
-        bulk_g2s(cst, cg + k0, (uint32_t)(W * 8), full + sl);
-        bulk_g2s(cst + Wp, cg + nUp + k0, (uint32_t)(W * 8), full + sl);
-        bulk_g2s(cst + 2 * Wp, cg + 2 * nUp + k0, (uint32_t)(W * 8), full + sl);
-        bulk_g2s(cst + 3 * Wp, cg + 3 * nUp, (uint32_t)(Lp * 8), full + sl);
+      WBQ_CLK(it, 9);
+      if (pw == 0) {
+        if (lane == 0) {
+          mbar_expect_tx(full + sl, (uint32_t)(((int64_t)nn * W + 3 * W + Lp) * 8));
+          bulk_g2s(cst, cg + k0, (uint32_t)(W * 8), full + sl);
+          bulk_g2s(cst + Wp, cg + nUp + k0, (uint32_t)(W * 8), full + sl);
+          bulk_g2s(cst + 2 * Wp, cg + 2 * nUp + k0, (uint32_t)(W * 8), full + sl);
+          bulk_g2s(cst + 3 * Wp, cg + 3 * nUp, (uint32_t)(Lp * 8), full + sl);
+        }
+        __syncwarp();
+        if (lane < nn) bulk_g2s(Ys + (int64_t)lane * pitch, Y + (int64_t)pn_a * nU, (uint32_t)(W * 8), full + sl);
+        if (lane + 32 < nn) bulk_g2s(Ys + (int64_t)(lane + 32) * pitch, Y + (int64_t)pn_b * nU, (uint32_t)(W * 8), full + sl);
+        // y_e and phi0 of the patch nodes: lane = node
+        if (lane < nn) {
+          cp_async8(yes + lane, ye + pn_a, true);
+          cp_async8(phs + lane, ph + pn_a, true);
+        }
+        if (lane + 32 < nn) {
+          cp_async8(yes + lane + 32, ye + pn_b, true);
+          cp_async8(phs + lane + 32, ph + pn_b, true);
+        }
       }
-      __syncwarp();
-      if (lane < nn) bulk_g2s(Ys + (int64_t)lane * pitch, Y + (int64_t)pn_a * nU, (uint32_t)(W * 8), full + sl);
-      if (lane + 32 < nn) bulk_g2s(Ys + (int64_t)(lane + 32) * pitch, Y + (int64_t)pn_b * nU, (uint32_t)(W * 8), full + sl);
-      for (int n = 0; n < nn; ++n) {
+      for (int n = pw; n < nn; n += WBQ_PW) {
         const int64_t pp = __shfl_sync(0xffffffffu, (n < 32) ? pn_a : pn_b, n & 31);
         if (lane < nb) cp_async8(YB + n * zp + lane, YT + pp * nU + lo + lane, true);
         if (lane + 32 < nb) cp_async8(YB + n * zp + lane + 32, YT + pp * nU + lo + lane + 32, true);
         if (lane < zp) cp_async8(ZWs + n * zp + lane, Z + pp * ldz + lane, true);
         if (lane + 32 < zp) cp_async8(ZWs + n * zp + lane + 32, Z + pp * ldz + lane + 32, true);
         if (lane + 64 < zp) cp_async8(ZWs + n * zp + lane + 64, Z + pp * ldz + lane + 64, true);
-        if (lane == 0) cp_async8(yes + n, ye + pp, true);
-        if (lane == 1) cp_async8(phs + n, ph + pp, true);
       }
       cp_async_mbar_arrive(full + sl);
+      WBQ_CLK(it, 10);
     }
     return;
   }
@@ -1540,6 +1563,7 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
     const int q = q0 + it, sl = it % WBQ_SLOTS, use = it / WBQ_SLOTS;
     const int patch = q / per, r = q - patch * per, c = r / nbatch, b = r - c * nbatch;
     const int i = i0 + b;
+    if (warp == 0) WBQ_CLK(it, 0);
     const int el_beg = patch_eptr[patch], ne = patch_eptr[patch + 1] - el_beg;
     const int nb = ue_ptr[i + 1] - ue_ptr[i];
     const int k0 = ue_ptr[ch.el[c]];
@@ -1559,7 +1583,9 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
     double gq = 0.0, sj = 0.0;
     if (wg < 6) gq = g1e[6 * (int64_t)j + wg];
     if (wg == 0) sj = s_coef * area[j];
+    if (warp == 0) WBQ_CLK(it, 1);
     mbar_wait(full + sl, use & 1);
+    if (warp == 0) WBQ_CLK(it, 2);
     if (wg < 6) {
       const double* yb = YB + la * zp;
       const double* zw = ZWs + lb * zp;
@@ -1573,6 +1599,7 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
       gbuf[wg * 32 + lane] = gq + (a0 + a1);
     }
     group_bar(g);
+    if (warp == 0) WBQ_CLK(it, 3);
     if (wg == 0) {
       double g6[6];
 #pragma unroll
@@ -1587,6 +1614,7 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
       }
     }
     group_bar(g);
+    if (warp == 0) WBQ_CLK(it, 4);
     const double yr0 = ybuf[lane], yr1 = ybuf[32 + lane], yr2 = ybuf[64 + lane];
     const double yi0 = ybuf[96 + lane], yi1 = ybuf[128 + lane], yi2 = ybuf[160 + lane];
     // pointers biased by -k0 so that k stays the global electrode-node index (k0 is even: 16-byte alignment of even k)
@@ -1640,6 +1668,7 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
     }
 #undef CEIT_WB_TERM
     __syncwarp();
+    if (warp == 0) WBQ_CLK(it, 5);
     if (lane == 0) mbar_arrive(empty + sl);                 // this warp no longer reads the slot
   }
 }

@@ -64,6 +64,27 @@ def _worker(rank, ws, port, tag, q):
         plan.jacobian_block(0, L, ea, eb, 1e-3, omega, J2, E)
         dist.all_reduce(J2, op=dist.ReduceOp.SUM)
         out["elem_range_bit_equal"] = bool(torch.equal(J2, J1))
+        # (c) domain decomposition (DomainStep): each rank factorises its own sub-trees, one exchange inside the base
+        # stage, the rank's own Jacobian columns, sharded inverse model from them, J replicated afterwards
+        if tag != "21_21" or ws <= 4:
+            from ceit_b200.sharding import DomainStep
+            dom = DomainStep(m["nodes"], m["elem"], m["electrodes"], det)
+            J3 = torch.zeros_like(J1)
+            for _ in range(2):                                  # twice: buffers and graph-free replays are reusable
+                J3.zero_()
+                dom.factor(perm, var, omega)
+                dom.jacobian(1e-3, omega, J3)
+                dom.gather_jacobian(J3, async_op=True)
+                rows3 = dom.inverse_model(J3, 289)
+                dom.finish()
+            torch.cuda.synchronize()
+            inv3 = _lib.inverse_model(J3, det, 289, form=2)
+            out["dom_J_max_abs"] = float((J3 - J1).abs().max().item())
+            out["dom_signal_rel"] = float((torch.linalg.norm(J3 - J1) / torch.linalg.norm(J1 - 1)).item())
+            out["dom_inv_rel_same_J"] = float(((rows3 - inv3[dom.det_pos]).abs().max() / inv3.abs().max()).item())
+            out["dom_rows"] = int(dom.plan.exchange_info()[0][4])
+            out["dom_N"] = len(m["nodes"])
+            dom.plan.close()
         plan.close()
         q.put((rank, out))
     finally:
@@ -93,3 +114,6 @@ def test_two_rank_nccl_matches_single_rank(tag):
         assert o["J_max_abs"] <= 1e-13, o                 # raw J entries are ~1: 1e-13 is < 1 ulp of the signal floor
         assert o["inv_rel"] <= 1e-9, o
         assert o["elem_range_bit_equal"], o               # element ranges of one excitation batch: bit-equal
+        assert o["dom_J_max_abs"] <= 1e-11 and o["dom_signal_rel"] <= 1e-4, o   # another elimination order: rounding only
+        assert o["dom_inv_rel_same_J"] <= 1e-9, o
+        assert o["dom_rows"] < o["dom_N"], o              # the rank holds a strict subset of the node rows

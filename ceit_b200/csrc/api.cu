@@ -169,6 +169,7 @@ inline bool wbq_configure(const HostPlan& h, WbqChunks* out, int* cap_out) {
   *cap_out = best_cap;
   return true;
 }
+inline int64_t zw_ld(int64_t nbatch, int64_t bp) { return (nbatch * (bp + 1) + 1) & ~(int64_t)1; }
 inline int woodbury_patch_cap(int64_t nU) {
   for (int per_sm = 2; per_sm >= 1; --per_sm) {
     int64_t budget = WB_SMEM_SM / per_sm - 1024;
@@ -184,6 +185,7 @@ inline int woodbury_patch_cap(int64_t nU) {
 struct ceit_plan {
   HostPlan h;
   void* xg = nullptr;             // decomposed plans: export slots of the sub-tree roots' update matrices (all ranks)
+  WbqPatchRec* d_patch_rec = nullptr;   // per (patch, lane): element id, packed local node slots, 2 omega c A factor
   int32_t* d_exp_b = nullptr;
   int64_t* d_exp_offC = nullptr;
   bool wbq_ok = false;            // the persistent pipelined Woodbury kernel applies (patches were built for it)
@@ -357,6 +359,12 @@ int upload_plan(ceit_plan* p) {
   CUDA_TRY(cudaMemset(p->d_info, 0, sizeof(int)));
   elem_param_kernel<<<cdiv(h.E, 256), 256>>>((int)h.E, p->d_nodes, p->d_elem, nullptr, p->d_area);
   CEIT_COUNT_LAUNCH();
+  if (p->n_patches > 0) {
+    if ((rc = dev_alloc(p, (void**)&p->d_patch_rec, (size_t)p->n_patches * 32 * sizeof(WbqPatchRec)))) return rc;
+    patch_rec_kernel<<<cdiv((int64_t)p->n_patches * 32, 256), 256>>>(p->n_patches, p->d_patch_eptr, p->d_patch_elems,
+                                                                     p->d_patch_local, p->d_area, p->d_patch_rec);
+    CEIT_COUNT_LAUNCH();
+  }
   KERNEL_CHECK();
   CUDA_TRY(cudaDeviceSynchronize());
   p->uploaded = true;
@@ -435,7 +443,7 @@ int alloc_numeric(ceit_plan* p, cudaStream_t st) {
   if ((rc = dev_alloc(p, &p->LinvT, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->Tinv, h.nU * h.nU * es))) return rc;
   if ((rc = dev_alloc(p, &p->te, h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->YT, h.Nc * h.nU * es))) return rc;
+  if ((rc = dev_alloc(p, &p->YT, (h.Nc * h.nU + 2) * es))) return rc;
   if ((rc = dev_alloc(p, &p->ye, h.Nc * es))) return rc;
   if (!p->d_gamma && (rc = dev_alloc(p, (void**)&p->d_gamma, sizeof(double)))) return rc;
   if ((rc = dev_alloc(p, &p->g1e, 6 * h.E * es))) return rc;
@@ -486,7 +494,7 @@ int alloc_excitation_ws(ceit_plan* p, int want_cap, cudaStream_t st) {
   if ((rc = dev_alloc(p, &p->LB, c * (int64_t)h.bp * h.bp * es))) return rc;
   if ((rc = dev_alloc(p, &p->LinvB, c * (int64_t)h.bp * h.bp * es))) return rc;
   if ((rc = dev_alloc(p, &p->Dcat, c * (int64_t)(h.bp + 1) * h.nU * es))) return rc;
-  if ((rc = dev_alloc(p, &p->ZW, c * h.Nc * (int64_t)(h.bp + 1) * es))) return rc;
+  if ((rc = dev_alloc(p, &p->ZW, (h.Nc * zw_ld(c, h.bp) + 2) * es))) return rc;   // + 2: aligned windows may read one past
   if ((rc = dev_alloc(p, (void**)&p->d_elec, c * h.L * sizeof(double)))) return rc;
   p->ex_cap = want_cap;
   p->ex_mode = want_mode;
@@ -1153,8 +1161,9 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
     update(st, N, YT, ye, 0, Yh, N * nU);
     // ZW_i = Xh Dcat_i^T (N x (bp+1)): the rank-(b+1) correction of the element blocks (woodbury_lr_kernel)
     // all excitations of the chunk in one product: Dcat is a (nbatch (bp+1)) x nU matrix
+    // (leading dimension rounded up to even: 16-byte aligned rows for the bulk copies of the persistent Woodbury kernel)
     gemm<T>(sx, 0, 1, N, (int64_t)nbatch * (bp + 1), nU, one, Xh, nU, 0, Dcat, nU, 0, zero, (T*)p->ZW,
-            (int64_t)nbatch * (bp + 1), 0, 1);
+            zw_ld(nbatch, bp), 0, 1);
   } else {
   dim3 g2(cdiv(u2, 256), nbatch);
   build_stilde_kernel<T><<<g2, 256, 0, st>>>((int)nU, SU, p->d_inB, i0, St);
@@ -1241,7 +1250,7 @@ int launch_woodbury_lr(ceit_plan* p, int e_from, int e_to, int nbatch, int i0, d
       e_from, e_to, (int)h.L, (int)h.nU, woodbury_lr_pitch((int)h.nU), (int)h.bp, h.Nc, h.N0c, p->d_patch_eptr,
       p->d_patch_elems, p->d_patch_nptr, p->d_patch_nodes, p->d_patch_local, p->d_area, (const double*)p->g1e,
       (const double*)p->YT, (const double*)p->ye, (const double*)p->ZW, (const double*)p->Yh, (const double*)p->phi0,
-      p->d_ue_ptr, consts, i0, s_coef, J, ldJ, (int)h.patch_node_cap, nbatch);
+      p->d_ue_ptr, consts, i0, s_coef, J, ldJ, (int)h.patch_node_cap, nbatch, zw_ld(nbatch, h.bp));
   CEIT_COUNT_LAUNCH();
   return 0;
 }
@@ -1261,10 +1270,10 @@ int launch_woodbury_lr_persist(ceit_plan* p, int e_from, int e_to, int nbatch, i
   if (n_items == 0) return 0;
   dim3 grid((unsigned)std::min<int64_t>(p->sm_count, n_items));
   woodbury_lr_persist_kernel<<<grid, WBQ_THREADS, psm, st>>>(
-      e_from, e_to, (int)h.L, (int)h.nU, (int)h.bp, h.Nc, h.N0c, (int)n_items, p->wbq, p->d_patch_eptr, p->d_patch_elems,
-      p->d_patch_nptr, p->d_patch_nodes, p->d_patch_local, p->d_area, (const double*)p->g1e, (const double*)p->YT,
+      e_from, e_to, (int)h.L, (int)h.nU, (int)h.bp, h.Nc, h.N0c, (int)n_items, p->wbq, p->d_patch_eptr,
+      p->d_patch_nptr, p->d_patch_nodes, p->d_patch_rec, (const double*)p->g1e, (const double*)p->YT,
       (const double*)p->ye, (const double*)p->ZW, (const double*)p->Yh, (const double*)p->phi0, p->d_ue_ptr, consts, i0,
-      s_coef, J, ldJ, (int)h.patch_node_cap, nbatch);
+      s_coef, J, ldJ, (int)h.patch_node_cap, nbatch, zw_ld(nbatch, h.bp));
   CEIT_COUNT_LAUNCH();
   return 0;
 }

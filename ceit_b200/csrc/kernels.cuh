@@ -1255,7 +1255,7 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
                    const double* __restrict__ g1e, const double* __restrict__ YT, const double* __restrict__ ye,
                    const double* __restrict__ ZW, const double* __restrict__ Yh, const double* __restrict__ phi0,
                    const int32_t* __restrict__ ue_ptr, const double* __restrict__ node_consts, int i0,
-                   double s_coef, double* __restrict__ J, int64_t ldJ, int cap, int nbatch) {
+                   double s_coef, double* __restrict__ J, int64_t ldJ, int cap, int nbatch, int64_t ldz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = WBP_WARPS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1279,7 +1279,6 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
   const double* Y = Yh + (int64_t)b * N * nU;
   const double* ph = phi0 + (int64_t)b * N;
   const double* Z = ZW + (int64_t)b * zp;                        // ZW is N x (nbatch zp), excitation b's columns
-  const int64_t ldz = (int64_t)nbatch * zp;
   const double* cg = node_consts + (int64_t)b * cst_len;
   WB_CLK(0);
   if (threadIdx.x == 0 && bulk) mbar_init(bar, 1);
@@ -1434,17 +1433,40 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
 //   [ cx | cy | cz (Wp each) | s0 (Lp) | Ys cap x pitchW | YB cap x zp | ZW cap x zp | ye cap | phi0 cap ].
 // ------------------------------------------------------------------------------------------------
 constexpr int WBQ_GROUPS = 2, WBQ_SLOTS = 3, WBQ_GW = 8;          // consumer groups, ring slots, warps per group
-constexpr int WBQ_PW = 4;                                         // producer warps (the 8-byte cp.async of the small
-                                                                  // per-node arrays cost ~80 issue cycles each: one warp took 10k cycles per item)
+constexpr int WBQ_PW = 4;   // producer warps: a bulk copy costs ~75 issue cycles and the copies of one warp serialise
 constexpr int WBQ_THREADS = (WBQ_GROUPS * WBQ_GW + WBQ_PW) * 32;
 struct WbqChunks {
   int n;            // column chunks per (patch, excitation)
   int el[5];        // electrode boundaries of the chunks: chunk c = electrodes [el[c], el[c + 1])
   int wmax;         // widest chunk in columns (even)
 };
+// per (patch, lane): what a consumer lane needs of its element, in ONE 16-byte load that does not depend on
+// patch_eptr (the chain patch_eptr -> patch_elems -> patch_local -> area was ~1.2k cycles per item)
+struct __align__(16) WbqPatchRec {
+  int32_t j;        // element id (lane >= elements of the patch: the first element's data, valid = 0)
+  uint32_t pack;    // l0 | l1 << 8 | l2 << 16 | valid << 24
+  double area;
+};
+__global__ void patch_rec_kernel(int n_patches, const int32_t* __restrict__ patch_eptr,
+                                 const int32_t* __restrict__ patch_elems, const uint8_t* __restrict__ patch_local,
+                                 const double* __restrict__ area, WbqPatchRec* __restrict__ rec) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n_patches * 32) return;
+  const int patch = (int)(t >> 5), lane = (int)(t & 31);
+  const int el_beg = patch_eptr[patch], ne = patch_eptr[patch + 1] - el_beg;
+  const bool have = lane < ne;
+  const int q = el_beg + (have ? lane : 0);
+  WbqPatchRec r;
+  r.j = patch_elems[q];
+  r.pack = (uint32_t)patch_local[3 * q] | ((uint32_t)patch_local[3 * q + 1] << 8) | ((uint32_t)patch_local[3 * q + 2] << 16) |
+           ((have ? 1u : 0u) << 24);
+  r.area = area[r.j];
+  rec[t] = r;
+}
+// slot: [ cx | cy | cz (Wp each) | s0 (Lp) | Ys cap x pitchW | YB cap x zs | ZW cap x zs | ye cap | phi0 cap ], zs = bp + 2
 __host__ __device__ inline int64_t wbq_slot_doubles(int wmax, int L, int cap, int bp) {
   const int Wp = (wmax + 1) & ~1, Lp = (L + 1) & ~1;
-  int64_t d = 3 * (int64_t)Wp + Lp + (int64_t)cap * woodbury_lr_pitch(wmax) + 2 * (int64_t)cap * (bp + 1) + 2 * cap;
+  int64_t d = 3 * (int64_t)Wp + Lp + (int64_t)cap * woodbury_lr_pitch(wmax) + 2 * (int64_t)cap * (bp + 2) + 2 * cap;
   return (d + 1) & ~(int64_t)1;
 }
 __host__ __device__ inline int64_t wbq_smem_bytes(int wmax, int L, int cap, int bp) {
@@ -1465,17 +1487,16 @@ __device__ __forceinline__ void group_bar(int g) {
 __global__ void __launch_bounds__(WBQ_THREADS, 1)
 woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t N, int64_t N0, int n_items,
                            WbqChunks ch, const int32_t* __restrict__ patch_eptr,
-                           const int32_t* __restrict__ patch_elems, const int32_t* __restrict__ patch_nptr,
-                           const int32_t* __restrict__ patch_nodes, const uint8_t* __restrict__ patch_local,
-                           const double* __restrict__ area, const double* __restrict__ g1e,
+                           const int32_t* __restrict__ patch_nptr, const int32_t* __restrict__ patch_nodes,
+                           const WbqPatchRec* __restrict__ patch_rec, const double* __restrict__ g1e,
                            const double* __restrict__ YT, const double* __restrict__ ye,
                            const double* __restrict__ ZW, const double* __restrict__ Yh,
                            const double* __restrict__ phi0, const int32_t* __restrict__ ue_ptr,
                            const double* __restrict__ node_consts, int i0, double s_coef, double* __restrict__ J,
-                           int64_t ldJ, int cap, int nbatch) {
+                           int64_t ldJ, int cap, int nbatch, int64_t ldz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int zp = bp + 1;
+  const int zp = bp + 1, zs = bp + 2;                              // small rows: zp values inside aligned windows of zs
   const int nUp = (nU + 1) & ~1, Lp = (L + 1) & ~1, cst_len = 3 * nUp + Lp;
   const int Wp = (ch.wmax + 1) & ~1, pitch = woodbury_lr_pitch(ch.wmax);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);          // [WBQ_SLOTS]
@@ -1497,58 +1518,54 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
   const int per = nbatch * ch.n;
   if (warp >= WBQ_GROUPS * WBQ_GW) {
     // ---------------------------------------- producers -----------------------------------------------
-    const int pw = warp - WBQ_GROUPS * WBQ_GW;                     // warp 0: TMA rows + constants; all: the small arrays
+    const int pw = warp - WBQ_GROUPS * WBQ_GW;                     // node n is staged by producer warp n % WBQ_PW
+    // every array of an item is staged with bulk copies, one instruction per node row (lane = node): the rows of
+    // Yh_i, and 16-byte aligned windows of zs doubles around Y_T[node, B_i] and ZW_i[node, :] (an 8-byte cp.async
+    // costs ~80 issue cycles: 130 of them per item made one warp the bottleneck of the whole ring)
     for (int it = 0; it < n_my; ++it) {
       const int q = q0 + it, sl = it % WBQ_SLOTS, use = it / WBQ_SLOTS;
       const int patch = q / per, r = q - patch * per, c = r / nbatch, b = r - c * nbatch;
       const int i = i0 + b;
       WBQ_CLK(it, 8);
       const int n_beg = patch_nptr[patch], nn = patch_nptr[patch + 1] - n_beg;
-      const int lo = ue_ptr[i], nb = ue_ptr[i + 1] - lo;
+      const int lo = ue_ptr[i];
       const int k0 = ue_ptr[ch.el[c]], W = ue_ptr[ch.el[c + 1]] - k0;
       const int pn_a = (lane < nn) ? patch_nodes[n_beg + lane] : 0;
       const int pn_b = (lane + 32 < nn) ? patch_nodes[n_beg + lane + 32] : 0;
       double* cst = slots + sl * slot_d;
       double* Ys = cst + 3 * Wp + Lp;
       double* YB = Ys + (int64_t)cap * pitch;
-      double* ZWs = YB + cap * zp;
-      double* yes = ZWs + cap * zp;
+      double* ZWs = YB + cap * zs;
+      double* yes = ZWs + cap * zs;
       double* phs = yes + cap;
       const double* Y = Yh + (int64_t)b * N * nU + k0;
       const double* ph = phi0 + (int64_t)b * N;
-      const double* Z = ZW + (int64_t)b * zp;
-      const int64_t ldz = (int64_t)nbatch * zp;
+      const int lo_al = lo & ~1, len_y = min(zs, nU - lo_al);      // window of Y_T[node, B_i]
+      const int z_al = (b * zp) & ~1;                              // window of ZW_i[node, :]
       const double* cg = node_consts + (int64_t)b * cst_len;
       if (use > 0) mbar_wait(empty + sl, (use - 1) & 1);           // the slot's previous item has been consumed
       WBQ_CLK(it, 9);
-      if (pw == 0) {
-        if (lane == 0) {
-          mbar_expect_tx(full + sl, (uint32_t)(((int64_t)nn * W + 3 * W + Lp) * 8));
-          bulk_g2s(cst, cg + k0, (uint32_t)(W * 8), full + sl);
-          bulk_g2s(cst + Wp, cg + nUp + k0, (uint32_t)(W * 8), full + sl);
-          bulk_g2s(cst + 2 * Wp, cg + 2 * nUp + k0, (uint32_t)(W * 8), full + sl);
-          bulk_g2s(cst + 3 * Wp, cg + 3 * nUp, (uint32_t)(Lp * 8), full + sl);
-        }
-        __syncwarp();
-        if (lane < nn) bulk_g2s(Ys + (int64_t)lane * pitch, Y + (int64_t)pn_a * nU, (uint32_t)(W * 8), full + sl);
-        if (lane + 32 < nn) bulk_g2s(Ys + (int64_t)(lane + 32) * pitch, Y + (int64_t)pn_b * nU, (uint32_t)(W * 8), full + sl);
-        // y_e and phi0 of the patch nodes: lane = node
-        if (lane < nn) {
-          cp_async8(yes + lane, ye + pn_a, true);
-          cp_async8(phs + lane, ph + pn_a, true);
-        }
-        if (lane + 32 < nn) {
-          cp_async8(yes + lane + 32, ye + pn_b, true);
-          cp_async8(phs + lane + 32, ph + pn_b, true);
-        }
+      if (lane == 0 && pw == 0) {
+        mbar_expect_tx(full + sl, (uint32_t)(((int64_t)nn * (W + len_y + zs) + 3 * W + Lp) * 8));
+        bulk_g2s(cst, cg + k0, (uint32_t)(W * 8), full + sl);
+        bulk_g2s(cst + Wp, cg + nUp + k0, (uint32_t)(W * 8), full + sl);
+        bulk_g2s(cst + 2 * Wp, cg + 2 * nUp + k0, (uint32_t)(W * 8), full + sl);
+        bulk_g2s(cst + 3 * Wp, cg + 3 * nUp, (uint32_t)(Lp * 8), full + sl);
       }
-      for (int n = pw; n < nn; n += WBQ_PW) {
-        const int64_t pp = __shfl_sync(0xffffffffu, (n < 32) ? pn_a : pn_b, n & 31);
-        if (lane < nb) cp_async8(YB + n * zp + lane, YT + pp * nU + lo + lane, true);
-        if (lane + 32 < nb) cp_async8(YB + n * zp + lane + 32, YT + pp * nU + lo + lane + 32, true);
-        if (lane < zp) cp_async8(ZWs + n * zp + lane, Z + pp * ldz + lane, true);
-        if (lane + 32 < zp) cp_async8(ZWs + n * zp + lane + 32, Z + pp * ldz + lane + 32, true);
-        if (lane + 64 < zp) cp_async8(ZWs + n * zp + lane + 64, Z + pp * ldz + lane + 64, true);
+      __syncwarp();
+      if (lane < nn && (lane % WBQ_PW) == pw) {
+        bulk_g2s(Ys + (int64_t)lane * pitch, Y + (int64_t)pn_a * nU, (uint32_t)(W * 8), full + sl);
+        bulk_g2s(YB + lane * zs, YT + (int64_t)pn_a * nU + lo_al, (uint32_t)(len_y * 8), full + sl);
+        bulk_g2s(ZWs + lane * zs, ZW + (int64_t)pn_a * ldz + z_al, (uint32_t)(zs * 8), full + sl);
+        cp_async8(yes + lane, ye + pn_a, true);
+        cp_async8(phs + lane, ph + pn_a, true);
+      }
+      if (lane + 32 < nn && (lane % WBQ_PW) == pw) {
+        bulk_g2s(Ys + (int64_t)(lane + 32) * pitch, Y + (int64_t)pn_b * nU, (uint32_t)(W * 8), full + sl);
+        bulk_g2s(YB + (lane + 32) * zs, YT + (int64_t)pn_b * nU + lo_al, (uint32_t)(len_y * 8), full + sl);
+        bulk_g2s(ZWs + (lane + 32) * zs, ZW + (int64_t)pn_b * ldz + z_al, (uint32_t)(zs * 8), full + sl);
+        cp_async8(yes + lane + 32, ye + pn_b, true);
+        cp_async8(phs + lane + 32, ph + pn_b, true);
       }
       cp_async_mbar_arrive(full + sl);
       WBQ_CLK(it, 10);
@@ -1559,44 +1576,49 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
   const int g = warp / WBQ_GW, wg = warp % WBQ_GW;
   double* ybuf = gbase + g * 12 * 32;
   double* gbuf = ybuf + 6 * 32;
+  WbqPatchRec rec{};
+  double gq = 0.0;
+  if (g < n_my) {                                                  // element data of the first item of this group
+    const int patch = (q0 + g) / per;
+    rec = patch_rec[(int64_t)patch * 32 + lane];
+    if (wg < 6) gq = g1e[6 * (int64_t)rec.j + wg];
+  }
   for (int it = g; it < n_my; it += WBQ_GROUPS) {
     const int q = q0 + it, sl = it % WBQ_SLOTS, use = it / WBQ_SLOTS;
     const int patch = q / per, r = q - patch * per, c = r / nbatch, b = r - c * nbatch;
     const int i = i0 + b;
     if (warp == 0) WBQ_CLK(it, 0);
-    const int el_beg = patch_eptr[patch], ne = patch_eptr[patch + 1] - el_beg;
-    const int nb = ue_ptr[i + 1] - ue_ptr[i];
+    const int lo = ue_ptr[i], nb = ue_ptr[i + 1] - lo;
     const int k0 = ue_ptr[ch.el[c]];
     const double* cst = slots + sl * slot_d;
     const double* Ys = cst + 3 * Wp + Lp;
     const double* YB = Ys + (int64_t)cap * pitch;
-    const double* ZWs = YB + cap * zp;
-    const double* yes = ZWs + cap * zp;
+    const double* ZWs = YB + cap * zs;
+    const double* yes = ZWs + cap * zs;
     const double* phs = yes + cap;
-    const bool have = lane < ne;
-    const int lq = have ? lane : 0;
-    const int j = patch_elems[el_beg + lq];
-    const int l0 = patch_local[3 * (el_beg + lq)], l1 = patch_local[3 * (el_beg + lq) + 1],
-              l2 = patch_local[3 * (el_beg + lq) + 2];
+    const bool have = (rec.pack >> 24) != 0;
+    const int j = rec.j;
+    const int l0 = rec.pack & 255, l1 = (rec.pack >> 8) & 255, l2 = (rec.pack >> 16) & 255;
     const int la = (wg == 0 || wg == 3) ? l0 : ((wg == 1 || wg == 4) ? l1 : l2);
     const int lb = (wg == 0 || wg == 5) ? l0 : ((wg == 1 || wg == 3) ? l1 : l2);
-    double gq = 0.0, sj = 0.0;
-    if (wg < 6) gq = g1e[6 * (int64_t)j + wg];
-    if (wg == 0) sj = s_coef * area[j];
+    const double sj = s_coef * rec.area;
+    const double gq_cur = gq;
     if (warp == 0) WBQ_CLK(it, 1);
     mbar_wait(full + sl, use & 1);
     if (warp == 0) WBQ_CLK(it, 2);
     if (wg < 6) {
-      const double* yb = YB + la * zp;
-      const double* zw = ZWs + lb * zp;
-      double a0 = yes[la] * zw[bp], a1 = 0.0;
+      const double* yb = YB + la * zs + (lo & 1);
+      const double* zw = ZWs + lb * zs + ((b * zp) & 1);
+      double a0 = yes[la] * zw[bp], a1 = 0.0, a2 = 0.0, a3 = 0.0;
       int jj = 0;
-      for (; jj + 1 < nb; jj += 2) {
+      for (; jj + 3 < nb; jj += 4) {
         a0 = fma(-yb[jj], zw[jj], a0);
         a1 = fma(-yb[jj + 1], zw[jj + 1], a1);
+        a2 = fma(-yb[jj + 2], zw[jj + 2], a2);
+        a3 = fma(-yb[jj + 3], zw[jj + 3], a3);
       }
-      if (jj < nb) a0 = fma(-yb[jj], zw[jj], a0);
-      gbuf[wg * 32 + lane] = gq + (a0 + a1);
+      for (; jj < nb; ++jj) a0 = fma(-yb[jj], zw[jj], a0);
+      gbuf[wg * 32 + lane] = gq_cur + ((a0 + a1) + (a2 + a3));
     }
     group_bar(g);
     if (warp == 0) WBQ_CLK(it, 3);
@@ -1613,6 +1635,10 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
         ybuf[(3 + a) * 32 + lane] = yi[a];
       }
     }
+    // element data of this group's NEXT item: the loads fly during the amplitude loop
+    WbqPatchRec rec_n = rec;
+    const bool new_patch = it + WBQ_GROUPS < n_my && (q + WBQ_GROUPS) / per != patch;
+    if (new_patch) rec_n = patch_rec[(int64_t)((q + WBQ_GROUPS) / per) * 32 + lane];
     group_bar(g);
     if (warp == 0) WBQ_CLK(it, 4);
     const double yr0 = ybuf[lane], yr1 = ybuf[32 + lane], yr2 = ybuf[64 + lane];
@@ -1642,7 +1668,7 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
         CEIT_WB_TERM(sumt, y0[k], y1[k], y2[k], cx[k], cy[k], cz[k]);
         ++k;
       }
-#pragma unroll 2
+#pragma unroll 4
       for (; k + 1 < ke; k += 2) {
         const double2 a0 = *reinterpret_cast<const double2*>(y0 + k);
         const double2 a1 = *reinterpret_cast<const double2*>(y1 + k);
@@ -1670,6 +1696,8 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
     __syncwarp();
     if (warp == 0) WBQ_CLK(it, 5);
     if (lane == 0) mbar_arrive(empty + sl);                 // this warp no longer reads the slot
+    if (new_patch && wg < 6) gq = g1e[6 * (int64_t)rec_n.j + wg];   // lands during the next item's correction loop
+    rec = rec_n;
   }
 }
 

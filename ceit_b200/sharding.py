@@ -241,6 +241,9 @@ class DomainStep:
 
     # ---- replication of J (output contract only) ------------------------------------------------------------------
     def gather_jacobian(self, J, async_op=False):
+        """Replicate J: pack this rank's columns, all-gather, scatter the other ranks' columns into place.  The whole
+        chain runs on a side stream (and its own communicator), so with async_op=True it overlaps whatever the caller
+        enqueues next on the current stream (the inverse model) until `finish()`."""
         torch, dist = self.torch, self.dist
         if self._idx_all is None:
             idx = torch.full((self.ws, self.e_max), -1, dtype=torch.int64, device=J.device)
@@ -248,27 +251,33 @@ class DomainStep:
             mine = idx[self.rank].clone()
             dist.all_gather_into_tensor(idx, mine, group=self.group)
             self._idx_all = [idx[r, :self.counts[r]].contiguous() for r in range(self.ws)]
+            self._side = torch.cuda.Stream(device=J.device) if J.is_cuda else None
         n = self.own_idx.numel()
-        if n:
-            torch.index_select(J, 1, self.own_idx, out=self._pack[:, :n])
-        if self.nccl:
-            work = dist.all_gather_into_tensor(self._all, self._pack, group=self.repl_group, async_op=True)
-            self._work = (work, J)
-            if not async_op:
-                self.finish()
-        else:
+        if self._side is None:                                   # gloo / CPU: everything in line
+            if n:
+                torch.index_select(J, 1, self.own_idx, out=self._pack[:, :n])
             dist.all_gather_into_tensor(self._all, self._pack, group=self.group)
-            self._work = (None, J)
+            self._scatter(J)
+            return J
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            if n:
+                torch.index_select(J, 1, self.own_idx, out=self._pack[:, :n])
+            dist.all_gather_into_tensor(self._all, self._pack, group=self.repl_group)
+            self._scatter(J)
+        self._work = True
+        if not async_op:
             self.finish()
         return J
 
-    def finish(self):
-        if self._work is None:
-            return
-        work, J = self._work
-        if work is not None:
-            work.wait()
+    def _scatter(self, J):
         for r in range(self.ws):
             if r != self.rank and self.counts[r]:
                 J.index_copy_(1, self._idx_all[r], self._all[r][:, :self.counts[r]])
-        self._work = None
+
+    def finish(self):
+        """Join the replication of J: the current stream waits for the side stream."""
+        if self._work:
+            self.torch.cuda.current_stream().wait_stream(self._side)
+            self._work = None

@@ -602,13 +602,13 @@ def stage_rooflines(ctx, st, name):
         ach = bytes_per_col * cols_per_launch / (per_launch_ms * 1e-3) / 1e9
         traffic, traffic_src = None, None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))["woodbury_lr_kernel"][name]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))["woodbury_lr_persist_kernel"][name]
             if ctx.ws == 1:                      # the capture is of the full single-GPU launch
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         except Exception:
             pass
         out["woodbury"] = {
-            "kernel": "woodbury_lr_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
+            "kernel": "woodbury_lr_persist_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
             "frac": ach / hbm, "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
             "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": bytes_per_col * cols_per_launch,
             "timing": "CUDA events around the launch, second pass over the same K steps (stream launches; the timed "
@@ -619,7 +619,7 @@ def stage_rooflines(ctx, st, name):
     if a_n and a_ms > 0:
         a_bytes = 16.0 * N + 28.0 * E + 16.0 * int(info[7])        # 16 N + 28 E + 16 nnz
         per = a_ms / a_n
-        out["assemble"] = {"kernel": "assemble_csr_kernel", "bound": "hbm", "achieved": a_bytes / (per * 1e-3) / 1e9,
+        out["assemble"] = {"kernel": "assemble_elem_kernel + assemble_reduce_kernel", "bound": "hbm", "achieved": a_bytes / (per * 1e-3) / 1e9,
                            "peak": hbm, "unit": "GB/s", "frac": a_bytes / (per * 1e-3) / 1e9 / hbm, "traffic": None,
                            "ms_per_launch": per, "algorithmic_bytes_per_launch": a_bytes, "peak_source": hbm_src}
     return out

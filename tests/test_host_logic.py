@@ -323,3 +323,36 @@ def test_write_behind_npy_helpers(tmp_path, monkeypatch):
     with pytest.raises(OSError):
         u.wait_npy()                                     # the worker's error surfaces at the join
     assert not u._pending
+
+
+@pytest.mark.parametrize("tag,parts", [("21_21", 2), ("50_50", 2), ("50_50", 4), ("50_50", 8)])
+def test_domain_decomposed_plans_partition_the_elements(golden, tag, parts):
+    """Multi-GPU plans (ceit_factor_phase): the ranks' element sets are a partition, every rank holds a strict subset of
+    the node rows, the exchange buffers have the same shape on every rank, and every patch of a rank only touches rows
+    that rank holds (host tables only, no device)."""
+    m, _ = golden(tag)
+    N, E = len(m["nodes"]), len(m["elem"])
+    plans = [_lib.Plan(m["nodes"], m["elem"], m["electrodes"], upload=False, parts=parts, part=r) for r in range(parts)]
+    own = np.stack([p.own_elements() for p in plans])
+    assert (own.sum(axis=0) == 1).all()
+    assert own.sum(axis=1).min() > 0
+    infos = [p.exchange_info()[0] for p in plans]
+    for r, (p, info) in enumerate(zip(plans, infos)):
+        assert info[0] == parts and info[1] == r
+        assert (info[2:4] == infos[0][2:4]).all() and info[6] == infos[0][6]      # same exchange shapes, same cut depth
+        assert info[5] < p.N0 and info[4] == info[5] + p.nU                       # a strict subset of the F0 rows
+        pos = p.tables()["pos"]
+        held = pos >= 0
+        assert held.sum() == info[4]
+        assert held[np.asarray(m["elem"])[own[r]]].all()                          # nodes of the own elements are held
+        pt = p.patches()
+        n_el = int(pt["eptr"][-1])
+        assert sorted(pt["elems"][:n_el].tolist()) == np.flatnonzero(own[r]).tolist()   # patches = exactly the own elements
+        assert pt["nodes"].min() >= 0 and pt["nodes"].max() < info[4]
+    # the union of the held non-electrode rows covers the mesh
+    covered = np.zeros(N, bool)
+    for p in plans:
+        covered |= p.tables()["pos"] >= 0
+    assert covered.all()
+    with pytest.raises(_lib.CeitError):
+        _lib.Plan(m["nodes"], m["elem"], m["electrodes"], upload=False, parts=2, part=2)

@@ -22,6 +22,7 @@ int g_force_simt = 0;
 int g_gemm_tile = 0;
 double g_flops = 0.0;
 int g_gemm_vec = 1;
+int g_pdl = 1;              // programmatic dependent launch of the GEMM / tile kernels (gemm.cuh: launch_pdl)
 int g_gemm_min_ctas64 = 300;   // measured (tools/stage_breakdown.py --opt gemm_min_ctas64=...): 120 -> 300 is 2 % at 50_50 / 200x200
 static thread_local std::string g_err;
 }  // namespace ceit
@@ -1874,6 +1875,7 @@ int ceit_set_option(const char* name, int64_t value) {
   if (std::strcmp(name, "nd_pull") == 0) { g_nd_pull = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "shard_parts") == 0) { g_shard_parts = (int)std::max<int64_t>(1, value); return CEIT_OK; }
   if (std::strcmp(name, "shard_part") == 0) { g_shard_part = (int)value; return CEIT_OK; }
+  if (std::strcmp(name, "pdl") == 0) { g_pdl = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "wb_persist") == 0) { g_wb_persist = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "assemble_gather") == 0) { g_assemble_gather = (int)value; return CEIT_OK; }
   if (std::strcmp(name, "yt_sweep") == 0) { g_yt_sweep = (int)value; return CEIT_OK; }

@@ -236,6 +236,8 @@ potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA,
   __shared__ T rdiag[TILE];
   __shared__ T rpiv[TILE + 1];
   const int tid = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   A += (int64_t)blockIdx.x * sA;
   L += (int64_t)blockIdx.x * sL;
   Linv += (int64_t)blockIdx.x * sI;
@@ -593,8 +595,8 @@ inline void potrf_trtri_blocked(cudaStream_t st, int64_t n, T* A, int64_t lda, i
   };
   for (int64_t t = 0; t < nt; ++t) {
     const int64_t o = t * TILE, bt = (n - o < TILE) ? n - o : TILE;
-    potrf_trtri_tile_kernel<T><<<batch, 256, smem, st>>>((int)bt, A + o * lda + o, lda, sA, L + o * ldl + o, ldl, sL,
-                                                         Linv + o * ldi + o, ldi, sI, info);
+    launch_pdl(potrf_trtri_tile_kernel<T>, dim3((unsigned)batch), dim3(256), smem, st, (int)bt,
+               (const T*)(A + o * lda + o), lda, sA, L + o * ldl + o, ldl, sL, Linv + o * ldi + o, ldi, sI, info);
     CEIT_COUNT_LAUNCH();
     g_flops += (Sc<T>::is_complex ? 4.0 : 1.0) * (2.0 / 3.0) * (double)bt * bt * bt * batch;
     if (lane && t >= 1) {

@@ -59,6 +59,33 @@ __device__ __forceinline__ void cp_async_elem(double* smem_dst, const double* gs
 __device__ __forceinline__ void cp_async_elem(cd* smem_dst, const cd* gsrc, bool valid) {
   cp_async16(smem_dst, gsrc, valid);
 }
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The hot path is a chain of ~100 short dependent kernels.  A kernel launched through launch_pdl() may be SCHEDULED
+// while its same-stream predecessor still runs (the predecessor signals pdl_trigger() at its start, i.e. as soon as all
+// of its CTAs are resident); it blocks in pdl_wait() until the predecessor has completed and its writes are visible.
+// Everything before pdl_wait() - parameter reads, index arithmetic, shared-memory set-up - overlaps the predecessor's
+// tail, and the launch latency itself is hidden.  Both instructions are no-ops for a normally launched kernel, and a
+// kernel launched normally after a triggering one is serialised as usual, so kernels can adopt this one by one.
+// ceit_set_option("pdl", 0) switches the launch attribute off.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -81,6 +108,7 @@ gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A
                  int64_t sA, const double* __restrict__ B, int64_t ldb, int64_t sB, double beta,
                  double* __restrict__ C, int64_t ldc, int64_t sC, int flags, int vec) {
   using SM = DmmaSmem<BM, BN, OPA, OPB>;
+  pdl_trigger();
   // vec: bit 0 / bit 1 = the A / B operand is staged with 16-byte cp.async (two doubles along its contiguous
   // dimension; needs a 16-byte aligned base, an even leading dimension and an even batch stride - decided by the
   // host launcher); an 8-byte LDGSTS occupies the LSU as long as a 16-byte one, so this halves the staging issue
@@ -191,6 +219,7 @@ gemm_dmma_kernel(int M, int N, int K, double alpha, const double* __restrict__ A
     }
   };
 
+  pdl_wait();                                       // operands come from the predecessor: block until it has completed
   const int nk = (K + BK - 1) / BK;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
@@ -568,9 +597,8 @@ inline void gemm_dmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int64
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                       \
       attr_done = true;                                                                                   \
     }                                                                                                     \
-    gemm_dmma_kernel<BM, BN, WM, WN, a, b, STAGES><<<grid, block, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, \
-                                                                             sA, B, ldb, sB, beta, C, ldc, sC,      \
-                                                                             lower_only, vec);                      \
+    launch_pdl(gemm_dmma_kernel<BM, BN, WM, WN, a, b, STAGES>, grid, block, smem, st, (int)M, (int)N, (int)K, alpha, A,  \
+               lda, sA, B, ldb, sB, beta, C, ldc, sC, lower_only, vec);                                               \
   }
   if (opA == 0 && opB == 0) CEIT_DMMA_CASE(0, 0)
   else if (opA == 0 && opB == 1) CEIT_DMMA_CASE(0, 1)

@@ -538,7 +538,7 @@ inline SideLane* inv_lane() {
 // excitation-independent part of the element blocks for the low-rank Woodbury kernel (real path only)
 inline void launch_g1(ceit_plan* p, const double* g0e, const double* YT, const double* Xh, cudaStream_t st) {
   const HostPlan& h = p->h;
-  g1_kernel<<<cdiv(h.E, 8), 256, 0, st>>>(h.E, (int)h.nU, p->d_elem_pos, g0e, YT, Xh, (double*)p->g1e);
+  pdl(g1_kernel, cdiv(h.E, 8), 256, 0, st)(h.E, (int)h.nU, p->d_elem_pos, g0e, YT, Xh, (double*)p->g1e);
   CEIT_COUNT_LAUNCH();
 }
 inline void launch_g1(ceit_plan*, const cd*, const cd*, const cd*, cudaStream_t) {}
@@ -549,7 +549,7 @@ inline void schur_u_gemm(ceit_plan* p, cudaStream_t st, int64_t nU, int64_t N0P,
   gemm_splitk(st, 1, 0, nU, nU, N0P, -1.0, K0U, nU, X, nU, 1.0, SU, nU, (double*)p->splitk_ws, /*lower_only=*/1);
 }
 inline void symmetrize_su(cudaStream_t st, int64_t nU, double* SU) {
-  symmetrize_from_lower_kernel<<<cdiv(nU * nU, 256), 256, 0, st>>>(nU, SU, nU);
+  pdl(symmetrize_from_lower_kernel, cdiv(nU * nU, 256), 256, 0, st)(nU, SU, nU);
   CEIT_COUNT_LAUNCH();
 }
 inline void symmetrize_su(cudaStream_t, int64_t, cd*) {}   // the complex path forms the full product
@@ -568,15 +568,15 @@ int base_shared_inverse(ceit_plan* p, cudaStream_t s_t) {
   if (use_rank_update(p)) {
     // T, t_e = T e: shared by every excitation (Y_T = Xh T and y_e = Y_T e follow once X is complete)
     T *Mreg = (T*)p->Mreg, *LT = (T*)p->LT, *LinvT = (T*)p->LinvT, *Tinv = (T*)p->Tinv, *te = (T*)p->te;
-    trace_gamma_kernel<T><<<1, 256, 0, s_t>>>((int)nU, SU, p->d_gamma);
+    pdl(trace_gamma_kernel<T>, 1, 256, 0, s_t)((int)nU, SU, p->d_gamma);
     CEIT_COUNT_LAUNCH();
-    add_rank1_e_kernel<T><<<cdiv(nU * nU, 256), 256, 0, s_t>>>((int)nU, SU, p->d_gamma, Mreg);
+    pdl(add_rank1_e_kernel<T>, cdiv(nU * nU, 256), 256, 0, s_t)((int)nU, SU, p->d_gamma, Mreg);
     CEIT_COUNT_LAUNCH();
     // (LT and LinvT were zeroed at the start of the stage, off this chain)
     potrf_trtri_blocked<T>(s_t, nU, Mreg, nU, 0, LT, nU, 0, LinvT, nU, 0, (T*)p->tmpT, 0, 1, p->d_info,
                            g_multi_stream ? &p->lane_b : nullptr);
     gemm<T>(s_t, 1, 0, nU, nU, nU, one, LinvT, nU, 0, LinvT, nU, 0, zero, Tinv, nU, 0);
-    rowsum_e_kernel<T><<<cdiv(nU, 8), 256, 0, s_t>>>(nU, (int)nU, Tinv, te);
+    pdl(rowsum_e_kernel<T>, cdiv(nU, 8), 256, 0, s_t)(nU, (int)nU, Tinv, te);
     CEIT_COUNT_LAUNCH();
   }
   return 0;
@@ -589,25 +589,25 @@ int base_tail(ceit_plan* p, cudaStream_t st, cudaStream_t sr, cudaStream_t s_t) 
   const int64_t nU = h.nU;
   const T one = Sc<T>::one(), zero = Sc<T>::zero();
   T *Sel = (T*)p->Sel, *g0e = (T*)p->g0e, *Xh = (T*)p->XP, *Xc = (T*)p->Xh;
-  gather_g0_kernel<T><<<cdiv(6 * h.E, 256), 256, 0, st>>>(6 * h.E, p->d_g0_off, Sel, g0e);
+  pdl(gather_g0_kernel<T>, cdiv(6 * h.E, 256), 256, 0, st)(6 * h.E, p->d_g0_off, Sel, g0e);
   CEIT_COUNT_LAUNCH();
-  compact_rows_kernel<T><<<cdiv(h.N0c, 8), 256, 0, sr>>>(h.N0c, (int)nU, p->d_row_map, Xh, Xc);
+  pdl(compact_rows_kernel<T>, cdiv(h.N0c, 8), 256, 0, sr)(h.N0c, (int)nU, p->d_row_map, Xh, Xc);
   CEIT_COUNT_LAUNCH();
-  fill_neg_identity_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>((int)nU, Xc + h.N0c * nU);
+  pdl(fill_neg_identity_kernel<T>, cdiv(nU * nU, 256), 256, 0, sr)((int)nU, Xc + h.N0c * nU);
   CEIT_COUNT_LAUNCH();
   if (use_rank_update(p)) {
     T *Tinv = (T*)p->Tinv, *YT = (T*)p->YT, *ye = (T*)p->ye;
     CEIT_AFTER(s_t, sr);
     if (yt_by_sweep(p)) {
       // the padded Y_T rows come from the second backward sweep (factor_impl); rows of U: Xh[U] T = -T
-      compact_rows_kernel<T><<<cdiv(h.N0c, 8), 256, 0, sr>>>(h.N0c, (int)nU, p->d_row_map, (const T*)p->YP, YT);
+      pdl(compact_rows_kernel<T>, cdiv(h.N0c, 8), 256, 0, sr)(h.N0c, (int)nU, p->d_row_map, (const T*)p->YP, YT);
       CEIT_COUNT_LAUNCH();
-      negate_copy_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>(nU * nU, Tinv, YT + h.N0c * nU);
+      pdl(negate_copy_kernel<T>, cdiv(nU * nU, 256), 256, 0, sr)(nU * nU, Tinv, YT + h.N0c * nU);
       CEIT_COUNT_LAUNCH();
     } else {
       gemm<T>(sr, 0, 0, h.Nc, nU, nU, one, Xc, nU, 0, Tinv, nU, 0, zero, YT, nU, 0);               // Y_T = Xh T
     }
-    rowsum_e_kernel<T><<<cdiv(h.Nc, 8), 256, 0, sr>>>(h.Nc, (int)nU, YT, ye);
+    pdl(rowsum_e_kernel<T>, cdiv(h.Nc, 8), 256, 0, sr)(h.Nc, (int)nU, YT, ye);
     CEIT_COUNT_LAUNCH();
     CEIT_AFTER(sr, st);
     launch_g1(p, g0e, YT, Xc, st);
@@ -646,7 +646,7 @@ struct CudaTreeBK {
       cudaFuncSetAttribute(front_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FRONT_SMEM);
       attr_done = true;
     }
-    front_fused_kernel<<<lv.n, 256, FRONT_SMEM, lane[ln]>>>(front_args(lv), A + lv.offA, Bt + lv.offB, C, C + lv.offC,
+    pdl(front_fused_kernel, lv.n, 256, FRONT_SMEM, lane[ln])(front_args(lv), A + lv.offA, Bt + lv.offB, C, C + lv.offC,
                                                             Ainv + lv.offA, W + lv.offB, p->d_info);
     CEIT_COUNT_LAUNCH();
     g_flops += (double)lv.n * ((2.0 / 3.0 + 1.0) * lv.s * lv.s * lv.s + 3.0 * lv.s * lv.s * lv.b +
@@ -657,7 +657,7 @@ struct CudaTreeBK {
     if (lv.f0 == 0 && p->h.tree.child_ptr[lv.n] == 0) return;       // the leaf level has no children
     const int64_t span = (int64_t)lv.s + lv.b;
     dim3 grid(cdiv(span * span, 256), lv.n);
-    pull_children_kernel<T><<<grid, 256, 0, lane[ln]>>>(front_args(lv), A + lv.offA, Bt + lv.offB, C, C + lv.offC);
+    pdl(pull_children_kernel<T>, grid, 256, 0, lane[ln])(front_args(lv), A + lv.offA, Bt + lv.offB, C, C + lv.offC);
     CEIT_COUNT_LAUNCH();
   }
   void gemm(int ln, int opA, int opB, int64_t M, int64_t N, int64_t K, T alpha, const T* A, int64_t lda, int64_t sA,
@@ -670,28 +670,28 @@ struct CudaTreeBK {
   }
   void extend_add(int ln, const TreePlan&, const TreeLevel& lv, int pass, const T* U, T* A, T* Bt, T* C) {
     dim3 grid(cdiv((int64_t)lv.b * lv.b, 256), lv.n);
-    extend_add_kernel<T><<<grid, 256, 0, lane[ln]>>>(lv.b, pass, p->d_t_push + lv.f0, p->d_t_sib + lv.f0, p->d_t_pA + lv.f0,
+    pdl(extend_add_kernel<T>, grid, 256, 0, lane[ln])(lv.b, pass, p->d_t_push + lv.f0, p->d_t_sib + lv.f0, p->d_t_pA + lv.f0,
                                                      p->d_t_pB + lv.f0, p->d_t_pC + lv.f0, p->d_t_ps + lv.f0,
                                                      p->d_t_pb + lv.f0, p->d_t_rel + lv.offR, U, A, Bt, C);
     CEIT_COUNT_LAUNCH();
   }
   void extend_gather(int ln, const TreePlan&, const TreeLevel& lv, const T* Sg, const T* V, T* C) {
     dim3 grid(cdiv((int64_t)lv.b * lv.b, 256), lv.n);
-    extend_gather_kernel<T><<<grid, 256, 0, lane[ln]>>>(lv.b, p->d_t_pA + lv.f0, p->d_t_pB + lv.f0, p->d_t_pC + lv.f0,
+    pdl(extend_gather_kernel<T>, grid, 256, 0, lane[ln])(lv.b, p->d_t_pA + lv.f0, p->d_t_pB + lv.f0, p->d_t_pC + lv.f0,
                                                         p->d_t_ps + lv.f0, p->d_t_pb + lv.f0, p->d_t_rel + lv.offR, Sg,
                                                         V, C, C + lv.offC);
     CEIT_COUNT_LAUNCH();
   }
   void rhs_scatter(int ln, const TreePlan&, const TreeLevel& lv, int64_t nU, const T* G, T* R) {
     if (lv.rc_n == 0) return;
-    rhs_scatter_kernel<T><<<dim3((unsigned)lv.rc_n, cdiv(nU, 128)), 128, 0, lane[ln]>>>(
+    pdl(rhs_scatter_kernel<T>, dim3((unsigned)lv.rc_n, cdiv(nU, 128)), 128, 0, lane[ln])(
         lv.rc_n, (int)nU, p->d_t_rc_dst + lv.rc0, p->d_t_rc_ptr + lv.rc0, p->d_t_rc_src, G, R);
     CEIT_COUNT_LAUNCH();
   }
   void zero_rows(int ln, T* ptr, int64_t count) { cudaMemsetAsync(ptr, 0, (size_t)count * sizeof(T), lane[ln]); }
   void rows_gather(int ln, const TreePlan&, const TreeLevel& lv, int64_t nU, const T* Xp, T* G) {
     const int64_t rows = (int64_t)lv.n * lv.b;
-    bnd_rows_gather_kernel<T><<<cdiv(rows, 8), 256, 0, lane[ln]>>>(rows, (int)nU, p->d_t_bnd_row + lv.offR, Xp, G);
+    pdl(bnd_rows_gather_kernel<T>, cdiv(rows, 8), 256, 0, lane[ln])(rows, (int)nU, p->d_t_bnd_row + lv.offR, Xp, G);
     CEIT_COUNT_LAUNCH();
   }
 };
@@ -784,7 +784,7 @@ int factor_tree_second_half(ceit_plan* p, cudaStream_t st) {
   CudaTreeBK<T> bk{p, {st, sr, g_multi_stream ? p->s4 : sr}, (T*)p->tmpPanel};
   if (t.roots_per_rank > 0) {
     dim3 grid(cdiv(t.slot_sz, 256), t.parts * t.roots_per_rank);
-    export_copy_kernel<T><<<grid, 256, 0, st>>>(0, t.part * t.roots_per_rank, (t.part + 1) * t.roots_per_rank, p->d_exp_b,
+    pdl(export_copy_kernel<T>, grid, 256, 0, st)(0, t.part * t.roots_per_rank, (t.part + 1) * t.roots_per_rank, p->d_exp_b,
                                                 p->d_exp_offC, t.slot_sz, (T*)p->Tm, (T*)p->xg, 0);
     CEIT_COUNT_LAUNCH();
   }
@@ -793,7 +793,7 @@ int factor_tree_second_half(ceit_plan* p, cudaStream_t st) {
   tree_bottom_up<T>(t, nU, m, bk, one, zero, mone, t.n_own_segs, t.H);
   bk.after(2, 1);
   if (bk.rc) return bk.rc;
-  add_lower_kernel<T><<<cdiv(nU * nU, 256), 256, 0, sr>>>(nU * nU, K0U + t.rowsA * nU, SU);
+  pdl(add_lower_kernel<T>, cdiv(nU * nU, 256), 256, 0, sr)(nU * nU, K0U + t.rowsA * nU, SU);
   CEIT_COUNT_LAUNCH();
   if (t.rowsA > t.ra_top0)
     schur_u_gemm(p, sr, nU, t.rowsA - t.ra_top0, K0U + t.ra_top0 * nU, Xh + t.ra_top0 * nU, SU);
@@ -849,15 +849,15 @@ int factor_impl(ceit_plan* p, cudaStream_t st, int phase = 0) {
       CUDA_TRY(cudaMemsetAsync(Tm, 0, h.tree.szC * es, st));
       const int64_t npad = (int64_t)h.tree.pad_diag.size();
       if (npad > 0) {
-        pad_diag_list_kernel<T><<<cdiv(npad, 256), 256, 0, st>>>(npad, p->d_t_pad, Aint);
+        pdl(pad_diag_list_kernel<T>, cdiv(npad, 256), 256, 0, st)(npad, p->d_t_pad, Aint);
         CEIT_COUNT_LAUNCH();
       }
     } else {
-      pad_identity_kernel<T><<<cdiv(P * nI, 256), 256, 0, st>>>((int)P, (int)nI, p->d_node_at, Aint);
+      pdl(pad_identity_kernel<T>, cdiv(P * nI, 256), 256, 0, st)((int)P, (int)nI, p->d_node_at, Aint);
       CEIT_COUNT_LAUNCH();
     }
   }
-  scatter_dense_kernel<T><<<cdiv(h.nnz, 256), 256, 0, st>>>((int)h.nnz, p->d_vals, p->d_slot_dst, p->d_slot_kind, Ad,
+  pdl(scatter_dense_kernel<T>, cdiv(h.nnz, 256), 256, 0, st)((int)h.nnz, p->d_vals, p->d_slot_dst, p->d_slot_kind, Ad,
                                                             Bs, K0U, KUU, Aint, Bt);
   CEIT_COUNT_LAUNCH();
   KERNEL_CHECK();
@@ -887,7 +887,7 @@ int factor_impl(ceit_plan* p, cudaStream_t st, int phase = 0) {
         schur_u_partial(p, sr, nU, r1 - r0, K0U + r0 * nU, Xh + r0 * nU, K0U + t.rowsA * nU);
       if (t.roots_per_rank > 0) {
         dim3 grid(cdiv(t.slot_sz, 256), t.roots_per_rank);
-        export_copy_kernel<T><<<grid, 256, 0, st>>>(t.part * t.roots_per_rank, -1, -1, p->d_exp_b, p->d_exp_offC, t.slot_sz,
+        pdl(export_copy_kernel<T>, grid, 256, 0, st)(t.part * t.roots_per_rank, -1, -1, p->d_exp_b, p->d_exp_offC, t.slot_sz,
                                                     (T*)p->Tm, (T*)p->xg, 1);
         CEIT_COUNT_LAUNCH();
       }
@@ -914,13 +914,13 @@ int factor_impl(ceit_plan* p, cudaStream_t st, int phase = 0) {
     gemm<T>(st, 1, 0, bmax, bmax, nI, one, Bt, bmax, sV, Wn, bmax, sV, zero, Tm, bmax, sT, (int)P);         // Bt^T W
     const int64_t nd = (int64_t)h.m2_dst.size();
     if (nd > 0) {
-      m2_gather_kernel<T><<<cdiv(nd, 256), 256, 0, st>>>(nd, p->d_m2_dst, p->d_m2_src_ptr, p->d_m2_src, Tm, h.szD, Ad, Bs);
+      pdl(m2_gather_kernel<T>, cdiv(nd, 256), 256, 0, st)(nd, p->d_m2_dst, p->d_m2_src_ptr, p->d_m2_src, Tm, h.szD, Ad, Bs);
       CEIT_COUNT_LAUNCH();
     }
     // right-hand sides: t_I = A^-1 K_IU (kept in the interior rows of Xh), r_C = K_CU - Bt^T t_I
     gemm<T>(sr, 0, 0, nI, nU, nI, one, Ainv, nI, sPP, K0U, nU, sX, zero, Xh, nU, sX, (int)P);
     gemm<T>(sr, 1, 0, bmax, nU, nI, one, Bt, bmax, sV, Xh, nU, sX, zero, G1, nU, sG, (int)P);
-    rc_gather_kernel<T><<<cdiv(nC, 8), 256, 0, sr>>>(nC, (int)nU, p->d_rc_ptr, p->d_rc_src, G1, K0U + NI * nU,
+    pdl(rc_gather_kernel<T>, cdiv(nC, 8), 256, 0, sr)(nC, (int)nU, p->d_rc_ptr, p->d_rc_src, G1, K0U + NI * nU,
                                                      Zw + NI * nU);
     CEIT_COUNT_LAUNCH();
   } else {
@@ -1060,10 +1060,10 @@ int factor_impl(ceit_plan* p, cudaStream_t st, int phase = 0) {
   // ---- back to the interiors: x_I = t_I - W x_C[bnd] (sr), selected inverse blocks (st) ----------------
   if (P > 0) {
     if (h.nb == 0) CEIT_AFTER(st, sr);   // W_p (no separator block ordered the streams yet)
-    bnd_rows_gather_kernel<T><<<cdiv(P * bmax, 8), 256, 0, sr>>>(P * bmax, (int)nU, p->d_bnd_loc, Xh + NI * nU, G1);
+    pdl(bnd_rows_gather_kernel<T>, cdiv(P * bmax, 8), 256, 0, sr)(P * bmax, (int)nU, p->d_bnd_loc, Xh + NI * nU, G1);
     CEIT_COUNT_LAUNCH();
     gemm<T>(sr, 0, 0, nI, nU, bmax, mone, Wn, bmax, sV, G1, nU, sG, one, Xh, nU, sX, (int)P);
-    gather_g0_kernel<T><<<cdiv(P * sT, 256), 256, 0, st>>>(P * sT, p->d_sg_off, Sel, Tm);        // Sigma2 on the cliques
+    pdl(gather_g0_kernel<T>, cdiv(P * sT, 256), 256, 0, st)(P * sT, p->d_sg_off, Sel, Tm);        // Sigma2 on the cliques
     CEIT_COUNT_LAUNCH();
     gemm<T>(st, 0, 0, nI, bmax, bmax, mone, Wn, bmax, sV, Tm, bmax, sT, zero, Vneg, bmax, sV, (int)P);   // -W Sg
     CUDA_TRY(cudaMemcpyAsync(SigPP, Ainv, h.szPP * es, cudaMemcpyDeviceToDevice, st));
@@ -1090,7 +1090,7 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
     const int bp = h.bp;
     T *TBB = (T*)p->TBB, *LB = (T*)p->LB, *LinvB = (T*)p->LinvB, *Dcat = (T*)p->Dcat;
     T *Tinv = (T*)p->Tinv, *te = (T*)p->te, *YT = (T*)p->YT, *ye = (T*)p->ye;
-    gather_tbb_kernel<T><<<dim3(cdiv(bp * bp, 256), nbatch), 256, 0, st>>>((int)nU, bp, Tinv, p->d_ue_ptr, i0, TBB);
+    pdl(gather_tbb_kernel<T>, dim3(cdiv(bp * bp, 256), nbatch), 256, 0, st)((int)nU, bp, Tinv, p->d_ue_ptr, i0, TBB);
     CEIT_COUNT_LAUNCH();
     CUDA_TRY(cudaMemsetAsync(LB, 0, (int64_t)nbatch * bp * bp * es, st));
     CUDA_TRY(cudaMemsetAsync(LinvB, 0, (int64_t)nbatch * bp * bp * es, st));
@@ -1110,7 +1110,7 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
 #undef CEIT_RU_ATTR
       attr_done = true;
     }
-    excite_small_kernel<T><<<nbatch, 256, sm1, st>>>((int)nU, bp, Tinv, te, LinvB, p->d_ue_ptr, i0, p->d_gamma, Dcat,
+    pdl(excite_small_kernel<T>, nbatch, 256, sm1, st)((int)nU, bp, Tinv, te, LinvB, p->d_ue_ptr, i0, p->d_gamma, Dcat,
                                                     stage_rows);
     CEIT_COUNT_LAUNCH();
     auto update = [&](cudaStream_t su, int64_t rows, const T* src, const T* yv, int zero_rows, T* out, int64_t stride) {
@@ -1143,7 +1143,7 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
       const int64_t groups = std::max<int64_t>(1, std::min<int64_t>(tiles, std::max(g_fill, std::min(g_waves, tiles / 32))));
       const int passes = (int)std::max<int64_t>(1, cdiv(tiles, groups));
       dim3 grid(nbatch, cdiv(tiles, passes), nz);
-#define CEIT_RU(c, w) rank_update_kernel<T, c, w><<<grid, 256, smu, su>>>(rows, (int)nU, bp, src, yv, Dcat, p->d_ue_ptr, \
+#define CEIT_RU(c, w) pdl(rank_update_kernel<T, c, w>, grid, 256, smu, su)(rows, (int)nU, bp, src, yv, Dcat, p->d_ue_ptr, \
                                                                         i0, zero_rows, out, stride, passes, cw)
 #define CEIT_RU_W(w) \
   if (cpt == 1) CEIT_RU(1, w); else if (cpt == 2) CEIT_RU(2, w); else CEIT_RU(3, w)
@@ -1167,13 +1167,13 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
             zw_ld(nbatch, bp), 0, 1);
   } else {
   dim3 g2(cdiv(u2, 256), nbatch);
-  build_stilde_kernel<T><<<g2, 256, 0, st>>>((int)nU, SU, p->d_inB, i0, St);
+  pdl(build_stilde_kernel<T>, g2, 256, 0, st)((int)nU, SU, p->d_inB, i0, St);
   CEIT_COUNT_LAUNCH();
   CUDA_TRY(cudaMemsetAsync(Ls, 0, nbatch * u2 * es, st));
   CUDA_TRY(cudaMemsetAsync(Linvs, 0, nbatch * u2 * es, st));
   potrf_trtri_blocked<T>(st, nU, St, nU, u2, Ls, nU, u2, Linvs, nU, u2, tmpS, (int64_t)TILE * nU, nbatch, p->d_info);
   gemm<T>(st, 1, 0, nU, nU, nU, one, Linvs, nU, u2, Linvs, nU, u2, zero, Sinv, nU, u2, nbatch);
-  mask_sinv_kernel<T><<<g2, 256, 0, st>>>((int)nU, p->d_inB, i0, Sinv);
+  pdl(mask_sinv_kernel<T>, g2, 256, 0, st)((int)nU, p->d_inB, i0, Sinv);
   CEIT_COUNT_LAUNCH();
   // Yh[b] = Xh Sinv[b]
   gemm<T>(st, 0, 0, N, nU, nU, one, Xh, nU, 0, Sinv, nU, u2, zero, Yh, nU, N * nU, nbatch);
@@ -1181,13 +1181,13 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
   dim3 g3(cdiv(nU, 8), nbatch);
   // (one CTA per excitation running the four stages back to back was tried: 80 us slower at nU = 264 - a single SM
   //  streams the nU x nU matrices at its load latency; the four chip-wide launches stay)
-  phi_u_kernel<T><<<g3, 256, 0, sx>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 0);
+  pdl(phi_u_kernel<T>, g3, 256, 0, sx)((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 0);
   CEIT_COUNT_LAUNCH();
-  phi_u_kernel<T><<<g3, 256, 0, sx>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 1);
+  pdl(phi_u_kernel<T>, g3, 256, 0, sx)((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 1);
   CEIT_COUNT_LAUNCH();
-  phi_u_kernel<T><<<g3, 256, 0, sx>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 2);
+  pdl(phi_u_kernel<T>, g3, 256, 0, sx)((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 2);
   CEIT_COUNT_LAUNCH();
-  phi_u_kernel<T><<<g3, 256, 0, sx>>>((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 3);
+  pdl(phi_u_kernel<T>, g3, 256, 0, sx)((int)nU, SU, Sinv, p->d_inB, i0, tvec, phi0, N, N0, 3);
   CEIT_COUNT_LAUNCH();
   if (nbatch >= 4) {
     // phi_F0 = -X phi_U for all excitations of the chunk as ONE product (X is read once, not once per excitation):
@@ -1195,7 +1195,7 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
     gemm<T>(sx, 0, 1, nbatch, N0, nU, neg(one), phi0 + N0, N, 0, Xh, nU, 0, zero, phi0, N, 0, 1);
   } else {
     dim3 g4(cdiv(N0, 8), nbatch);
-    phi_f_kernel<T><<<g4, 256, 0, sx>>>(N0, (int)nU, Xh, phi0, N);
+    pdl(phi_f_kernel<T>, g4, 256, 0, sx)(N0, (int)nU, Xh, phi0, N);
     CEIT_COUNT_LAUNCH();
   }
   CEIT_AFTER(sx, st);
@@ -1217,11 +1217,11 @@ int launch_woodbury_patch(ceit_plan* p, const double* g0e, const double* Xh, con
   const HostPlan& h = p->h;
   const size_t psm = woodbury_patch_smem(h.nU, h.patch_node_cap);
   double4* consts = (double4*)p->tmpS;      // free after the batched factorisation of the excitation stage
-  node_consts_kernel<<<dim3(cdiv(h.nU, 128), nbatch), 128, 0, st>>>((int)h.nU, h.Nc, h.N0c, phi0, p->d_wk, consts);
+  pdl(node_consts_kernel, dim3(cdiv(h.nU, 128), nbatch), 128, 0, st)((int)h.nU, h.Nc, h.N0c, phi0, p->d_wk, consts);
   CEIT_COUNT_LAUNCH();
   CUDA_TRY(cudaFuncSetAttribute(woodbury_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
   dim3 grid((unsigned)((int64_t)p->n_patches * nbatch));
-  woodbury_patch_kernel<<<grid, WBP_WARPS * 32, psm, st>>>(e_from, e_to, (int)h.L, (int)h.nU, (int)woodbury_pitch(h.nU),
+  pdl(woodbury_patch_kernel, grid, WBP_WARPS * 32, psm, st)(e_from, e_to, (int)h.L, (int)h.nU, (int)woodbury_pitch(h.nU),
                                                           h.Nc, h.N0c, p->d_patch_eptr, p->d_patch_elems, p->d_patch_nptr,
                                                           p->d_patch_nodes, p->d_patch_local, p->d_area, g0e, Xh, Yh,
                                                           phi0, p->d_ue_ptr, consts, i0, s_coef, J, ldJ,
@@ -1235,7 +1235,7 @@ int launch_woodbury_lr_consts(ceit_plan* p, int nbatch, cudaStream_t st) {
   const HostPlan& h = p->h;
   const int nUp = (int)((h.nU + 1) & ~1LL), cst_len = (int)woodbury_lr_cst_len(h.nU, h.L);
   double* consts = (double*)p->tmpS;        // free after the batched factorisation of the excitation stage
-  node_consts_soa_kernel<<<dim3(cdiv(std::max(h.nU, h.L), 128), nbatch), 128, 0, st>>>(
+  pdl(node_consts_soa_kernel, dim3(cdiv(std::max(h.nU, h.L), 128), nbatch), 128, 0, st)(
       (int)h.nU, nUp, (int)h.L, cst_len, h.Nc, h.N0c, (const double*)p->phi0, p->d_wk, p->d_ue_ptr, consts);
   CEIT_COUNT_LAUNCH();
   return 0;
@@ -1247,7 +1247,7 @@ int launch_woodbury_lr(ceit_plan* p, int e_from, int e_to, int nbatch, int i0, d
   const double* consts = (const double*)p->tmpS;
   CUDA_TRY(cudaFuncSetAttribute(woodbury_lr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
   dim3 grid((unsigned)((int64_t)p->n_patches * nbatch));
-  woodbury_lr_kernel<<<grid, WBP_WARPS * 32, psm, st>>>(
+  pdl(woodbury_lr_kernel, grid, WBP_WARPS * 32, psm, st)(
       e_from, e_to, (int)h.L, (int)h.nU, woodbury_lr_pitch((int)h.nU), (int)h.bp, h.Nc, h.N0c, p->d_patch_eptr,
       p->d_patch_elems, p->d_patch_nptr, p->d_patch_nodes, p->d_patch_local, p->d_area, (const double*)p->g1e,
       (const double*)p->YT, (const double*)p->ye, (const double*)p->ZW, (const double*)p->Yh, (const double*)p->phi0,
@@ -1270,7 +1270,7 @@ int launch_woodbury_lr_persist(ceit_plan* p, int e_from, int e_to, int nbatch, i
   const int64_t n_items = (int64_t)p->n_patches * nbatch * p->wbq.n;
   if (n_items == 0) return 0;
   dim3 grid((unsigned)std::min<int64_t>(p->sm_count, n_items));
-  woodbury_lr_persist_kernel<<<grid, WBQ_THREADS, psm, st>>>(
+  pdl(woodbury_lr_persist_kernel, grid, WBQ_THREADS, psm, st)(
       e_from, e_to, (int)h.L, (int)h.nU, (int)h.bp, h.Nc, h.N0c, (int)n_items, p->wbq, p->d_patch_eptr,
       p->d_patch_nptr, p->d_patch_nodes, p->d_patch_rec, (const double*)p->g1e, (const double*)p->YT,
       (const double*)p->ye, (const double*)p->ZW, (const double*)p->Yh, (const double*)p->phi0, p->d_ue_ptr, consts, i0,
@@ -1303,7 +1303,7 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
     }
     if (rc) return rc;
     if (base) {
-      baseline_kernel<T><<<nbatch, 64, 0, st>>>((int)h.L, (int)h.nU, h.Nc, h.N0c, (const T*)p->phi0, p->d_we_ptr,
+      pdl(baseline_kernel<T>, nbatch, 64, 0, st)((int)h.L, (int)h.nU, h.Nc, h.N0c, (const T*)p->phi0, p->d_we_ptr,
                                                 p->d_we_u, p->d_we_w, (int)i0, base, nullptr);
       CEIT_COUNT_LAUNCH();
     }
@@ -1325,7 +1325,7 @@ int jacobian_impl(ceit_plan* p, int64_t i_from, int64_t i_to, int64_t e_from, in
     } else if (e_to > e_from && J) {
       StageScope sc(3, st);
       dim3 grid(cdiv(e_to - e_from, warps), nbatch);
-      woodbury_kernel<T><<<grid, warps * 32, smem, st>>>((int)e_from, (int)e_to, (int)h.L, (int)h.nU, h.Nc, h.N0c,
+      pdl(woodbury_kernel<T>, grid, warps * 32, smem, st)((int)e_from, (int)e_to, (int)h.L, (int)h.nU, h.Nc, h.N0c,
                                                          p->d_elem_pos, p->d_area, (const T*)p->g0e, (const T*)p->Xh,
                                                          (const T*)p->Yh, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
                                                          p->d_we_w, (int)i0, 2.0 * omega * c, J, ldJ);
@@ -1345,7 +1345,7 @@ int forward_impl(ceit_plan* p, int64_t i, double* node_abs, double* elem_pot, do
   rc = excitation_impl<T>(p, (int)i, 1, st);
   if (rc) return rc;
   if (electrode_pot) {
-    baseline_kernel<T><<<1, 64, 0, st>>>((int)h.L, (int)h.nU, h.Nc, h.N0c, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
+    pdl(baseline_kernel<T>, 1, 64, 0, st)((int)h.L, (int)h.nU, h.Nc, h.N0c, (const T*)p->phi0, p->d_we_ptr, p->d_we_u,
                                          p->d_we_w, (int)i, nullptr, electrode_pot);
     CEIT_COUNT_LAUNCH();
   }
@@ -1358,10 +1358,10 @@ int forward_impl(ceit_plan* p, int64_t i, double* node_abs, double* elem_pot, do
       }
       na = p->d_node_abs;
     }
-    node_abs_kernel<T><<<cdiv(h.N, 256), 256, 0, st>>>(h.N, (const T*)p->phi0, p->d_pos, na);
+    pdl(node_abs_kernel<T>, cdiv(h.N, 256), 256, 0, st)(h.N, (const T*)p->phi0, p->d_pos, na);
     CEIT_COUNT_LAUNCH();
     if (elem_pot) {
-      elem_mean_kernel<<<cdiv(h.E, 256), 256, 0, st>>>(h.E, p->d_elem, na, elem_pot);
+      pdl(elem_mean_kernel, cdiv(h.E, 256), 256, 0, st)(h.E, p->d_elem, na, elem_pot);
       CEIT_COUNT_LAUNCH();
     }
   }
@@ -1541,21 +1541,21 @@ int ceit_assemble(ceit_plan_t* p, const double* perm, const double* var, double 
   const HostPlan& h = p->h;
   StageScope sc(0, st);
   if (g_assemble_gather) {
-    assemble_csr_kernel<<<cdiv(h.nnz, 256), 256, 0, st>>>((int)h.nnz, p->d_src_ptr, p->d_src, p->d_nodes, p->d_elem,
+    pdl(assemble_csr_kernel, cdiv(h.nnz, 256), 256, 0, st)((int)h.nnz, p->d_src_ptr, p->d_src, p->d_nodes, p->d_elem,
                                                           perm, var, omega, p->d_vals);
     CEIT_COUNT_LAUNCH();
   } else {
-    assemble_elem_kernel<<<cdiv(h.E, 256), 256, 0, st>>>((int)h.E, p->d_nodes, p->d_elem, perm, var, omega,
+    pdl(assemble_elem_kernel, cdiv(h.E, 256), 256, 0, st)((int)h.E, p->d_nodes, p->d_elem, perm, var, omega,
                                                          p->d_elem_dst, (double2*)p->d_contrib);
     CEIT_COUNT_LAUNCH();
-    assemble_reduce_kernel<<<cdiv(h.nnz, 256), 256, 0, st>>>((int)h.nnz, p->d_src_ptr, (const double2*)p->d_contrib,
+    pdl(assemble_reduce_kernel, cdiv(h.nnz, 256), 256, 0, st)((int)h.nnz, p->d_src_ptr, (const double2*)p->d_contrib,
                                                              p->d_vals);
     CEIT_COUNT_LAUNCH();
   }
   KERNEL_CHECK();
   if (vals) CUDA_TRY(cudaMemcpyAsync(vals, p->d_vals, h.nnz * sizeof(cd), cudaMemcpyDeviceToDevice, st));
   if (elem_param) {
-    elem_param_kernel<<<cdiv(h.E, 256), 256, 0, st>>>((int)h.E, p->d_nodes, p->d_elem, elem_param, nullptr);
+    pdl(elem_param_kernel, cdiv(h.E, 256), 256, 0, st)((int)h.E, p->d_nodes, p->d_elem, elem_param, nullptr);
     CEIT_COUNT_LAUNCH();
     KERNEL_CHECK();
   }
@@ -1661,7 +1661,7 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
   CUDA_TRY(cudaMemsetAsync(info, 0, sizeof(int), st));
   CUDA_TRY(cudaMemsetAsync(Lg, 0, n * n * sizeof(double), st));
   CUDA_TRY(cudaMemsetAsync(Li, 0, n * n * sizeof(double), st));
-  gather_shift_kernel<<<cdiv(m_sel * n_det, 256), 256, 0, st>>>(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
+  pdl(gather_shift_kernel, cdiv(m_sel * n_det, 256), 256, 0, st)(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
   CEIT_COUNT_LAUNCH();
   if (form == 2) {
     // G = Jt Jt^T + lambda^2 I (m x m);  inv = Jt^T G^-1
@@ -1672,7 +1672,7 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
       if (S > 1) gemm_splitk(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, Jt, n_det, 0.0, G, n, sws, /*lower_only=*/1);
       else gemm<double>(st, 0, 1, n, n, n_det, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0, 1, /*lower_only=*/1);
     }
-    add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, G, n);
+    pdl(add_diag_kernel, cdiv(n, 256), 256, 0, st)(n, lambda * lambda, G, n);
     CEIT_COUNT_LAUNCH();
     potrf_trtri_blocked<double>(st, n, G, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info, inv_lane());
     gemm<double>(st, 1, 0, n, n, n, 1.0, Li, n, 0, Li, n, 0, 0.0, Gi, n, 0);
@@ -1680,7 +1680,7 @@ int ceit_inverse_model(const double* J, int64_t ldJ, int64_t m, const int64_t* d
   } else {
     // A = Jt^T Jt + lambda^2 I (n_det x n_det); inv = Linv^T (Linv Jt^T)
     gemm<double>(st, 1, 0, n, n, m_sel, 1.0, Jt, n_det, 0, Jt, n_det, 0, 0.0, G, n, 0, 1, /*lower_only=*/1);
-    add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, G, n);
+    pdl(add_diag_kernel, cdiv(n, 256), 256, 0, st)(n, lambda * lambda, G, n);
     CEIT_COUNT_LAUNCH();
     potrf_trtri_blocked<double>(st, n, G, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info, inv_lane());
     gemm<double>(st, 0, 1, n, m_sel, n, 1.0, Li, n, 0, Jt, n_det, 0, 0.0, Gi, m_sel, 0);
@@ -1705,7 +1705,7 @@ int ceit_gram_partial(const double* J, int64_t ldJ, int64_t m, const int64_t* de
   double* Jt = nullptr;
   AsyncBufs ws(st);
   CUDA_TRY(ws.get(&Jt, m_sel * n_det));
-  gather_shift_kernel<<<cdiv(m_sel * n_det, 256), 256, 0, st>>>(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
+  pdl(gather_shift_kernel, cdiv(m_sel * n_det, 256), 256, 0, st)(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
   CEIT_COUNT_LAUNCH();
   {
     // symmetric: lower triangle only (split over K when its tiles cannot fill the chip), then mirrored so that the
@@ -1714,7 +1714,7 @@ int ceit_gram_partial(const double* J, int64_t ldJ, int64_t m, const int64_t* de
     double* sws = nullptr;
     if (S > 1) CUDA_TRY(ws.get(&sws, (int64_t)S * m_sel * m_sel));
     gemm_splitk(st, 0, 1, m_sel, m_sel, n_det, 1.0, Jt, n_det, Jt, n_det, 0.0, G, m_sel, sws, /*lower_only=*/1);
-    symmetrize_from_lower_kernel<<<cdiv(m_sel * m_sel, 256), 256, 0, st>>>(m_sel, G, m_sel);
+    pdl(symmetrize_from_lower_kernel, cdiv(m_sel * m_sel, 256), 256, 0, st)(m_sel, G, m_sel);
     CEIT_COUNT_LAUNCH();
   }
   KERNEL_CHECK();
@@ -1744,9 +1744,9 @@ int ceit_inverse_from_gram(const double* J, int64_t ldJ, int64_t m, const int64_
   CUDA_TRY(cudaMemsetAsync(Lg, 0, n * n * sizeof(double), st));
   CUDA_TRY(cudaMemsetAsync(Li, 0, n * n * sizeof(double), st));
   CUDA_TRY(cudaMemcpyAsync(Gw, G, n * n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  add_diag_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, lambda * lambda, Gw, n);
+  pdl(add_diag_kernel, cdiv(n, 256), 256, 0, st)(n, lambda * lambda, Gw, n);
   CEIT_COUNT_LAUNCH();
-  gather_shift_kernel<<<cdiv(m_sel * n_det, 256), 256, 0, st>>>(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
+  pdl(gather_shift_kernel, cdiv(m_sel * n_det, 256), 256, 0, st)(m_sel, n_det, J, ldJ, rows, det_idx, shift, Jt);
   CEIT_COUNT_LAUNCH();
   potrf_trtri_blocked<double>(st, n, Gw, n, 0, Lg, n, 0, Li, n, 0, tmp, 0, 1, info, inv_lane());
   gemm<double>(st, 1, 0, n, n, n, 1.0, Li, n, 0, Li, n, 0, 0.0, Gi, n, 0);
@@ -1762,7 +1762,7 @@ int ceit_reconstruct(const double* inv, const double* dV, double* out, int64_t n
   cudaStream_t st = (cudaStream_t)stream;
   StageScope sc(5, st);
   if (F == 1) {
-    gemv_rows_kernel<<<cdiv(n_det, 8), 256, 0, st>>>(n_det, (int)m, inv, dV, out);
+    pdl(gemv_rows_kernel, cdiv(n_det, 8), 256, 0, st)(n_det, (int)m, inv, dV, out);
     CEIT_COUNT_LAUNCH();
   } else {
     gemm<double>(st, 0, 0, n_det, F, m, 1.0, inv, m, 0, dV, F, 0, 0.0, out, F, 0);
@@ -1777,7 +1777,7 @@ int ceit_mesh_model(const double* nodes, const int64_t* elem, int64_t N, int64_t
   if (!nodes || !elem || (in_electrode && !centers)) CEIT_FAIL(CEIT_ERR_ARG, "ceit_mesh_model: null argument");
   if (N <= 0 || E <= 0 || L < 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_mesh_model: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  mesh_model_kernel<<<cdiv(E, 256), 256, 0, st>>>(E, (int)L, nodes, elem, centers, radius, det_bound, elem_param,
+  pdl(mesh_model_kernel, cdiv(E, 256), 256, 0, st)(E, (int)L, nodes, elem, centers, radius, det_bound, elem_param,
                                                   in_electrode, in_detection);
   CEIT_COUNT_LAUNCH();
   KERNEL_CHECK();
@@ -1789,7 +1789,7 @@ int ceit_center_of_position(const double* maps, int64_t n_det, int64_t F, const 
   if (!maps || !cx || !cy || !out) CEIT_FAIL(CEIT_ERR_ARG, "ceit_center_of_position: null argument");
   if (n_det <= 0 || F <= 0) CEIT_FAIL(CEIT_ERR_ARG, "ceit_center_of_position: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  cop_frames_kernel<<<cdiv(F, 32), 256, 0, st>>>(n_det, F, maps, cx, cy, frac, out);
+  pdl(cop_frames_kernel, cdiv(F, 32), 256, 0, st)(n_det, F, maps, cx, cy, frac, out);
   CEIT_COUNT_LAUNCH();
   KERNEL_CHECK();
   return CEIT_OK;

@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(256)
 potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA, T* __restrict__ L,
                         int64_t ldl, int64_t sL, T* __restrict__ Linv, int64_t ldi, int64_t sI,
                         int* __restrict__ info) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int LD = TILE + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* S = reinterpret_cast<T*>(smem_raw);   // [64][65] matrix -> L
@@ -236,8 +238,6 @@ potrf_trtri_tile_kernel(int n, const T* __restrict__ A, int64_t lda, int64_t sA,
   __shared__ T rdiag[TILE];
   __shared__ T rpiv[TILE + 1];
   const int tid = threadIdx.x;
-  pdl_trigger();
-  pdl_wait();
   A += (int64_t)blockIdx.x * sA;
   L += (int64_t)blockIdx.x * sL;
   Linv += (int64_t)blockIdx.x * sI;
@@ -296,6 +296,8 @@ __global__ void __launch_bounds__(256)
 front_fused_kernel(FrontFusedArgs a, double* __restrict__ A, double* __restrict__ Bt, double* __restrict__ Call,
                    double* __restrict__ Cout, double* __restrict__ Ainv, double* __restrict__ Wg,
                    int* __restrict__ info) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int LD = FRONT_LD;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* S = reinterpret_cast<double*>(smem_raw);   // matrix -> L
@@ -502,6 +504,8 @@ template <class T>
 __global__ void __launch_bounds__(256)
 pull_children_kernel(FrontFusedArgs a, T* __restrict__ A, T* __restrict__ Bt, const T* __restrict__ Call,
                      T* __restrict__ Cout) {
+  pdl_trigger();
+  pdl_wait();
   const int f = blockIdx.y, s = a.s, b = a.b, span = s + b;
   const int g = a.f0 + f;
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -66,13 +66,13 @@ __device__ __forceinline__ void cp_async_elem(cd* smem_dst, const cd* gsrc, bool
 // Everything before pdl_wait() - parameter reads, index arithmetic, shared-memory set-up - overlaps the predecessor's
 // tail, and the launch latency itself is hidden.  Both instructions are no-ops for a normally launched kernel, and a
 // kernel launched normally after a triggering one is serialised as usual, so kernels can adopt this one by one.
-// ceit_set_option("pdl", 0) switches the launch attribute off.
+// ceit_set_option("pdl", 0) switches the launch attribute off, 1 (default) = GEMM + tile kernels, 2 = every kernel.
 extern int g_pdl;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 template <class... KArgs, class... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                              Args... args) {
+inline cudaError_t launch_pdl_level(int level, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                    cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -80,10 +80,24 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl >= level ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// pdl(kernel, grid, block, smem, stream)(args...) - drop-in for pdl(kernel, grid, block, smem, stream)(args...)
+template <class... KArgs>
+struct PdlLaunch {
+  void (*k)(KArgs...);
+  dim3 g, b;
+  size_t s;
+  cudaStream_t st;
+  template <class... A>
+  void operator()(A... a) const { launch_pdl_level(2, k, g, b, s, st, a...); }
+};
+template <class... KArgs>
+inline PdlLaunch<KArgs...> pdl(void (*k)(KArgs...), dim3 g, dim3 b, size_t s, cudaStream_t st) {
+  return PdlLaunch<KArgs...>{k, g, b, s, st};
 }
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
@@ -287,6 +301,8 @@ __global__ void __launch_bounds__(WM * WN * 32)
 gemm_zdmma_kernel(int M, int N, int K, cd alpha, const cd* __restrict__ A, int64_t lda, int64_t sA,
                   const cd* __restrict__ B, int64_t ldb, int64_t sB, cd beta, cd* __restrict__ C, int64_t ldc,
                   int64_t sC, int beta_zero) {
+  pdl_trigger();
+  pdl_wait();
   using SM = DmmaSmem<BM, BN, OPA, OPB>;
   constexpr int BK = 16, NT = WM * WN * 32;
   constexpr int SA = SM::SA, SB = SM::SB;
@@ -429,6 +445,8 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(int M, int N, int K, T alpha, const T* __restrict__ A, int64_t lda, int64_t sA,
                  const T* __restrict__ B, int64_t ldb, int64_t sB, T beta, T* __restrict__ C,
                  int64_t ldc, int64_t sC, int beta_zero) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int BM = 64, BN = 64, BK = 16;
   __shared__ T As[BK][BM + 1];
   __shared__ T Bs[BK][BN + 1];
@@ -514,7 +532,7 @@ inline void gemm_simt_launch(cudaStream_t st, int opA, int opB, int64_t M, int64
   dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64), (unsigned)batch), block(256);
   int bz = is_zero(beta) ? 1 : 0;
 #define CEIT_SIMT_CASE(a, b)                                                                      \
-  gemm_simt_kernel<T, a, b><<<grid, block, 0, st>>>((int)M, (int)N, (int)K, alpha, A, lda, sA, B, \
+  pdl(gemm_simt_kernel<T, a, b>, grid, block, 0, st)((int)M, (int)N, (int)K, alpha, A, lda, sA, B, \
                                                     ldb, sB, beta, C, ldc, sC, bz)
   if (opA == 0 && opB == 0) CEIT_SIMT_CASE(0, 0);
   else if (opA == 0 && opB == 1) CEIT_SIMT_CASE(0, 1);
@@ -545,7 +563,7 @@ inline void gemm_zdmma_launch(cudaStream_t st, int opA, int opB, int64_t M, int6
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
       attr_done = true;                                                                                    \
     }                                                                                                      \
-    gemm_zdmma_kernel<BM, BN, WM, WN, a, b, STAGES><<<grid, block, smem, st>>>((int)M, (int)N, (int)K, alpha, A, lda, \
+    pdl(gemm_zdmma_kernel<BM, BN, WM, WN, a, b, STAGES>, grid, block, smem, st)((int)M, (int)N, (int)K, alpha, A, lda, \
                                                                               sA, B, ldb, sB, beta, C, ldc, sC, bz); \
   }
   if (opA == 0 && opB == 0) CEIT_ZDMMA_CASE(0, 0)
@@ -655,6 +673,8 @@ inline void gemm<double>(cudaStream_t st, int opA, int opB, int64_t M, int64_t N
 // ------------------------------------------------------------------------------------------------
 __global__ void splitk_reduce_kernel(int64_t n, int S, const double* __restrict__ P, double beta, double* __restrict__ C,
                                      int64_t M, int64_t N, int64_t ldc, int lower_only) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
   const int64_t r = q / N, c = q - r * N;
@@ -666,6 +686,8 @@ __global__ void splitk_reduce_kernel(int64_t n, int S, const double* __restrict_
 }
 // A[r][c] = A[c][r] for c > r (after a lower-only symmetric product)
 __global__ void symmetrize_from_lower_kernel(int64_t n, double* __restrict__ A, int64_t lda) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n * n) return;
   const int64_t r = q / n, c = q - r * n;
@@ -739,7 +761,7 @@ inline void gemm_splitk(cudaStream_t st, int opA, int opB, int64_t M, int64_t N,
       gemm<double>(st, opA, opB, M, N, rem, alpha, A + (int64_t)full * sA, lda, 0, B + (int64_t)full * sB, ldb, 0, 0.0,
                    workspace + (int64_t)full * M * N, N, 0, 1);
   }
-  splitk_reduce_kernel<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(M * N, parts, workspace, beta, C, M, N, ldc,
+  pdl(splitk_reduce_kernel, (unsigned)((M * N + 255) / 256), 256, 0, st)(M * N, parts, workspace, beta, C, M, N, ldc,
                                                                        lower_only);
   CEIT_COUNT_LAUNCH();
 }

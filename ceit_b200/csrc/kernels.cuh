@@ -38,6 +38,8 @@ assemble_csr_kernel(int nnz, const int32_t* __restrict__ src_ptr, const int32_t*
                     const double* __restrict__ nodes, const int32_t* __restrict__ elem,
                     const double* __restrict__ perm, const double* __restrict__ var, double omega,
                     cd* __restrict__ vals) {
+  pdl_trigger();
+  pdl_wait();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nnz) return;
   double re = 0.0, im = 0.0;
@@ -65,6 +67,8 @@ __global__ void __launch_bounds__(256)
 assemble_elem_kernel(int E, const double* __restrict__ nodes, const int32_t* __restrict__ elem,
                      const double* __restrict__ perm, const double* __restrict__ var, double omega,
                      const int32_t* __restrict__ elem_dst, double2* __restrict__ contrib) {
+  pdl_trigger();
+  pdl_wait();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   double area, b[3], c[3], xb, yb;
@@ -87,6 +91,8 @@ assemble_elem_kernel(int E, const double* __restrict__ nodes, const int32_t* __r
 __global__ void __launch_bounds__(256)
 assemble_reduce_kernel(int nnz, const int32_t* __restrict__ src_ptr, const double2* __restrict__ contrib,
                        cd* __restrict__ vals) {
+  pdl_trigger();
+  pdl_wait();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nnz) return;
   double re = 0.0, im = 0.0;
@@ -102,6 +108,8 @@ assemble_reduce_kernel(int nnz, const int32_t* __restrict__ src_ptr, const doubl
 __global__ void __launch_bounds__(256)
 elem_param_kernel(int E, const double* __restrict__ nodes, const int32_t* __restrict__ elem,
                   double* __restrict__ param, double* __restrict__ area_out) {
+  pdl_trigger();
+  pdl_wait();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   double area, b[3], c[3], xb, yb;
@@ -125,6 +133,8 @@ __global__ void __launch_bounds__(256)
 mesh_model_kernel(int64_t E, int L, const double* __restrict__ nodes, const int64_t* __restrict__ elem,
                   const double* __restrict__ centers, double radius, double det_bound, double* __restrict__ param,
                   uint8_t* __restrict__ in_electrode, uint8_t* __restrict__ in_detection) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   const double2* nd = reinterpret_cast<const double2*>(nodes);
@@ -157,6 +167,8 @@ __global__ void __launch_bounds__(256)
 scatter_dense_kernel(int nnz, const cd* __restrict__ vals, const int64_t* __restrict__ dst,
                      const uint8_t* __restrict__ kind, T* __restrict__ Ad, T* __restrict__ Bs,
                      T* __restrict__ K0U, T* __restrict__ KUU, T* __restrict__ Aint, T* __restrict__ Bt) {
+  pdl_trigger();
+  pdl_wait();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nnz) return;
   const int k = kind[s];
@@ -178,6 +190,8 @@ template <class T>
 __global__ void __launch_bounds__(256)
 export_copy_kernel(int slot0, int skip0, int skip1, const int32_t* __restrict__ exp_b, const int64_t* __restrict__ exp_offC,
                    int64_t slot_sz, T* __restrict__ C, T* __restrict__ xg, int to_xg) {
+  pdl_trigger();
+  pdl_wait();
   const int slot = slot0 + blockIdx.y;
   if (slot >= skip0 && slot < skip1) return;
   const int64_t b = exp_b[slot], n = b * b;
@@ -188,6 +202,8 @@ export_copy_kernel(int slot0, int skip0, int skip1, const int32_t* __restrict__ 
 }
 template <class T>
 __global__ void add_lower_kernel(int64_t n, const T* __restrict__ P, T* __restrict__ S) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n) S[q] = add(S[q], P[q]);
 }
@@ -196,6 +212,8 @@ __global__ void add_lower_kernel(int64_t n, const T* __restrict__ P, T* __restri
 // identity on the diagonal of the unused (padding) slots of every interior block
 template <class T>
 __global__ void pad_identity_kernel(int P, int nI, const int32_t* __restrict__ node_at, T* __restrict__ Aint) {
+  pdl_trigger();
+  pdl_wait();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= P * nI) return;
   if (node_at[q] < 0) {
@@ -208,6 +226,8 @@ template <class T>
 __global__ void m2_gather_kernel(int64_t nd, const int64_t* __restrict__ dst, const int32_t* __restrict__ src_ptr,
                                  const int32_t* __restrict__ src, const T* __restrict__ Tm, int64_t szD,
                                  T* __restrict__ Ad, T* __restrict__ Bs) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nd) return;
   T acc = Sc<T>::zero();
@@ -221,6 +241,8 @@ template <class T>
 __global__ void __launch_bounds__(256)
 rc_gather_kernel(int64_t nC, int nU, const int32_t* __restrict__ rc_ptr, const int32_t* __restrict__ rc_src,
                  const T* __restrict__ G1, const T* __restrict__ K0U_C, T* __restrict__ Z_C) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= nC) return;
@@ -235,6 +257,8 @@ template <class T>
 __global__ void __launch_bounds__(256)
 bnd_rows_gather_kernel(int64_t nrows, int nU, const int32_t* __restrict__ bnd_loc, const T* __restrict__ X_C,
                        T* __restrict__ G1) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= nrows) return;
@@ -246,6 +270,8 @@ bnd_rows_gather_kernel(int64_t nrows, int nU, const int32_t* __restrict__ bnd_lo
 // identity on the diagonal of every padding slot of the own blocks (host list of A offsets)
 template <class T>
 __global__ void pad_diag_list_kernel(int64_t n, const int64_t* __restrict__ dst, T* __restrict__ A) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n) A[dst[q]] = Sc<T>::one();
 }
@@ -261,6 +287,8 @@ extend_add_kernel(int b, int pass, const uint8_t* __restrict__ push, const int32
                   const int64_t* __restrict__ pB, const int64_t* __restrict__ pC, const int32_t* __restrict__ ps,
                   const int32_t* __restrict__ pb, const int32_t* __restrict__ rel, const T* __restrict__ U,
                   T* __restrict__ A, T* __restrict__ Bt, T* __restrict__ C) {
+  pdl_trigger();
+  pdl_wait();
   const int f = blockIdx.y;
   if (sib[f] != pass || pA[f] < 0 || !push[f]) return;   // fronts whose parent level pulls do not push
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -292,6 +320,8 @@ extend_gather_kernel(int b, const int64_t* __restrict__ pA, const int64_t* __res
                      const int64_t* __restrict__ pC, const int32_t* __restrict__ ps, const int32_t* __restrict__ pb,
                      const int32_t* __restrict__ rel, const T* __restrict__ Sg, const T* __restrict__ V,
                      const T* __restrict__ Call, T* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int f = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= b * b) return;
@@ -313,6 +343,8 @@ template <class T>
 __global__ void __launch_bounds__(128)
 rhs_scatter_kernel(int64_t nd, int nU, const int32_t* __restrict__ dst, const int32_t* __restrict__ ptr,
                    const int32_t* __restrict__ src, const T* __restrict__ G, T* __restrict__ R) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t q = blockIdx.x;
   const int k = blockIdx.y * 128 + threadIdx.x;
   if (q >= nd || k >= nU) return;
@@ -328,6 +360,8 @@ template <class T>
 __global__ void __launch_bounds__(256)
 compact_rows_kernel(int64_t N0, int nU, const int32_t* __restrict__ row_map, const T* __restrict__ XP,
                     T* __restrict__ Xh) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= N0) return;
@@ -338,6 +372,8 @@ compact_rows_kernel(int64_t N0, int nU, const int32_t* __restrict__ row_map, con
 // out = -in
 template <class T>
 __global__ void negate_copy_kernel(int64_t n, const T* __restrict__ in, T* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n) out[q] = neg(in[q]);
 }
@@ -345,6 +381,8 @@ __global__ void negate_copy_kernel(int64_t n, const T* __restrict__ in, T* __res
 // rows [N0, N) of Xh = -I
 template <class T>
 __global__ void fill_neg_identity_kernel(int nU, T* __restrict__ Xh_tail) {
+  pdl_trigger();
+  pdl_wait();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nU * nU) return;
   const int r = q / nU, c = q - r * nU;
@@ -355,6 +393,8 @@ __global__ void fill_neg_identity_kernel(int nU, T* __restrict__ Xh_tail) {
 template <class T>
 __global__ void gather_g0_kernel(int64_t n, const int64_t* __restrict__ off, const T* __restrict__ Sel,
                                  T* __restrict__ g0e) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
   const int64_t o = off[q];
@@ -365,6 +405,8 @@ __global__ void gather_g0_kernel(int64_t n, const int64_t* __restrict__ off, con
 template <class T>
 __global__ void build_stilde_kernel(int nU, const T* __restrict__ SU, const uint8_t* __restrict__ inB, int i0,
                                     T* __restrict__ St) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const uint8_t* mask = inB + (int64_t)(i0 + b) * nU;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,6 +420,8 @@ __global__ void build_stilde_kernel(int nU, const T* __restrict__ SU, const uint
 // zero rows/cols of B_i in Sinv[b]
 template <class T>
 __global__ void mask_sinv_kernel(int nU, const uint8_t* __restrict__ inB, int i0, T* __restrict__ Sinv) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const uint8_t* mask = inB + (int64_t)(i0 + b) * nU;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -395,6 +439,8 @@ __global__ void mask_sinv_kernel(int nU, const uint8_t* __restrict__ inB, int i0
 // ------------------------------------------------------------------------------------------------
 template <class T>
 __global__ void trace_gamma_kernel(int nU, const T* __restrict__ SU, double* __restrict__ gamma) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double red[256];
   double s = 0.0;
   for (int k = threadIdx.x; k < nU; k += 256) s += to_cd(SU[(int64_t)k * nU + k]).x;
@@ -409,6 +455,8 @@ __global__ void trace_gamma_kernel(int nU, const T* __restrict__ SU, double* __r
 template <class T>
 __global__ void add_rank1_e_kernel(int nU, const T* __restrict__ SU, const double* __restrict__ gamma,
                                    T* __restrict__ M) {
+  pdl_trigger();
+  pdl_wait();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nU * nU) return;
   M[q] = add(SU[q], Sc<T>::from_real(gamma[0] / nU));
@@ -417,6 +465,8 @@ __global__ void add_rank1_e_kernel(int nU, const T* __restrict__ SU, const doubl
 template <class T>
 __global__ void __launch_bounds__(256)
 rowsum_e_kernel(int64_t rows, int nU, const T* __restrict__ A, T* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -434,6 +484,8 @@ rowsum_e_kernel(int64_t rows, int nU, const T* __restrict__ A, T* __restrict__ o
 template <class T>
 __global__ void gather_tbb_kernel(int nU, int bp, const T* __restrict__ Tm, const int32_t* __restrict__ ue_ptr,
                                   int i0, T* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int i = i0 + blockIdx.y;
   const int lo = ue_ptr[i], b = ue_ptr[i + 1] - lo;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -451,6 +503,8 @@ __global__ void __launch_bounds__(256)
 excite_small_kernel(int nU, int bp, const T* __restrict__ Tm, const T* __restrict__ te,
                     const T* __restrict__ LinvB, const int32_t* __restrict__ ue_ptr, int i0,
                     const double* __restrict__ gamma, T* __restrict__ Dcat, int stage_rows) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Li = reinterpret_cast<T*>(smem_raw);   // [bp][bp]
   T* Bi = Li + bp * bp;                     // [bp][bp]  T_BB^-1
@@ -556,6 +610,8 @@ __global__ void __launch_bounds__(256)
 rank_update_kernel(int64_t rows, int nU, int bp, const T* __restrict__ src, const T* __restrict__ yv,
                    const T* __restrict__ Dcat, const int32_t* __restrict__ ue_ptr, int i0, int zero_rows,
                    T* __restrict__ out, int64_t out_stride, int passes, int cw) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int RH = Sc<T>::is_complex ? 4 : 8;   // rows per thread
   constexpr int TXN = 32 * WC;                     // threads across the columns
@@ -655,6 +711,8 @@ template <class T>
 __global__ void __launch_bounds__(256)
 phi_u_kernel(int nU, const T* __restrict__ SU, const T* __restrict__ Sinv, const uint8_t* __restrict__ inB,
              int i0, T* __restrict__ tvec, T* __restrict__ phi0, int64_t N, int64_t N0, int stage) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const uint8_t* mask = inB + (int64_t)(i0 + b) * nU;
   const int lane = threadIdx.x & 31;
@@ -693,6 +751,8 @@ phi_u_kernel(int nU, const T* __restrict__ SU, const T* __restrict__ Sinv, const
 template <class T>
 __global__ void __launch_bounds__(256)
 phi_f_kernel(int64_t N0, int nU, const T* __restrict__ X, T* __restrict__ phi0, int64_t N) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -716,6 +776,8 @@ __global__ void baseline_kernel(int L, int nU, int64_t N, int64_t N0, const T* _
                                 const int32_t* __restrict__ we_ptr, const int32_t* __restrict__ we_u,
                                 const double* __restrict__ we_w, int i0, double* __restrict__ base,
                                 double* __restrict__ electrode_pot) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const int i = i0 + b;
   const T* pu = phi0 + (int64_t)b * N + N0;
@@ -731,11 +793,15 @@ __global__ void baseline_kernel(int L, int nU, int64_t N, int64_t N0, const T* _
 template <class T>
 __global__ void node_abs_kernel(int64_t N, const T* __restrict__ phi0, const int32_t* __restrict__ pos,
                                 double* __restrict__ node_abs) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v < N) node_abs[v] = abs_(phi0[pos[v]]);
 }
 __global__ void elem_mean_kernel(int64_t E, const int32_t* __restrict__ elem, const double* __restrict__ node_abs,
                                  double* __restrict__ elem_pot) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e < E) elem_pot[e] = (node_abs[elem[3 * e]] + node_abs[elem[3 * e + 1]] + node_abs[elem[3 * e + 2]]) / 3.0;
 }
@@ -780,6 +846,8 @@ woodbury_kernel(int e_from, int e_to, int L, int nU, int64_t N, int64_t N0,
                 const T* __restrict__ phi0, const int32_t* __restrict__ we_ptr,
                 const int32_t* __restrict__ we_u, const double* __restrict__ we_w, int i0, double s_coef,
                 double* __restrict__ J, int64_t ldJ) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warps = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -982,6 +1050,8 @@ __device__ __forceinline__ void solve3_real(const double G6[6], double s, const 
 // Per-excitation constants of the electrode nodes for the real path: {2/phi0, 1/phi0^2, w |phi0|, 0}.
 __global__ void node_consts_kernel(int nU, int64_t N, int64_t N0, const double* __restrict__ phi0,
                                    const double* __restrict__ wk, double4* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nU) return;
@@ -1000,6 +1070,8 @@ woodbury_patch_kernel(int e_from, int e_to, int L, int nU, int pitch, int64_t N,
                       const double* __restrict__ Yh, const double* __restrict__ phi0,
                       const int32_t* __restrict__ ue_ptr, const double4* __restrict__ node_consts, int i0,
                       double s_coef, double* __restrict__ J, int64_t ldJ, int cap, int nbatch) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = WBP_WARPS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1152,6 +1224,8 @@ woodbury_patch_kernel(int e_from, int e_to, int L, int nU, int pitch, int64_t N,
 __global__ void __launch_bounds__(256)
 g1_kernel(int64_t E, int nU, const int32_t* __restrict__ elem_pos, const double* __restrict__ g0e,
           const double* __restrict__ YT, const double* __restrict__ Xh, double* __restrict__ g1e) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (e >= E) return;
@@ -1221,6 +1295,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __global__ void node_consts_soa_kernel(int nU, int nUp, int L, int cst_len, int64_t N, int64_t N0,
                                        const double* __restrict__ phi0, const double* __restrict__ wk,
                                        const int32_t* __restrict__ ue_ptr, double* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const double* ph = phi0 + (int64_t)b * N + N0;
@@ -1256,6 +1332,8 @@ woodbury_lr_kernel(int e_from, int e_to, int L, int nU, int pitch, int bp, int64
                    const double* __restrict__ ZW, const double* __restrict__ Yh, const double* __restrict__ phi0,
                    const int32_t* __restrict__ ue_ptr, const double* __restrict__ node_consts, int i0,
                    double s_coef, double* __restrict__ J, int64_t ldJ, int cap, int nbatch, int64_t ldz) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int WARPS = WBP_WARPS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1450,6 +1528,8 @@ struct __align__(16) WbqPatchRec {
 __global__ void patch_rec_kernel(int n_patches, const int32_t* __restrict__ patch_eptr,
                                  const int32_t* __restrict__ patch_elems, const uint8_t* __restrict__ patch_local,
                                  const double* __restrict__ area, WbqPatchRec* __restrict__ rec) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)n_patches * 32) return;
   const int patch = (int)(t >> 5), lane = (int)(t & 31);
@@ -1494,6 +1574,8 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
                            const double* __restrict__ phi0, const int32_t* __restrict__ ue_ptr,
                            const double* __restrict__ node_consts, int i0, double s_coef, double* __restrict__ J,
                            int64_t ldJ, int cap, int nbatch, int64_t ldz) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int zp = bp + 1, zs = bp + 2;                              // small rows: zp values inside aligned windows of zs
@@ -1708,6 +1790,8 @@ woodbury_lr_persist_kernel(int e_from, int e_to, int L, int nU, int bp, int64_t 
 __global__ void gather_shift_kernel(int64_t m_sel, int64_t n_det, const double* __restrict__ J, int64_t ldJ,
                                     const int64_t* __restrict__ rows, const int64_t* __restrict__ det,
                                     double shift, double* __restrict__ Jt) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= m_sel * n_det) return;
   const int64_t r = q / n_det, c = q - r * n_det;
@@ -1715,6 +1799,8 @@ __global__ void gather_shift_kernel(int64_t m_sel, int64_t n_det, const double* 
   Jt[q] = J[rr * ldJ + det[c]] - shift;
 }
 __global__ void add_diag_kernel(int64_t n, double v, double* __restrict__ A, int64_t lda) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n) A[q * lda + q] += v;
 }
@@ -1722,6 +1808,8 @@ __global__ void add_diag_kernel(int64_t n, double v, double* __restrict__ A, int
 __global__ void __launch_bounds__(256)
 gemv_rows_kernel(int64_t n_det, int m, const double* __restrict__ inv, const double* __restrict__ dV,
                  double* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_det) return;
@@ -1741,6 +1829,8 @@ gemv_rows_kernel(int64_t n_det, int m, const double* __restrict__ inv, const dou
 __global__ void __launch_bounds__(256)
 cop_frames_kernel(int64_t n_det, int64_t F, const double* __restrict__ maps, const double* __restrict__ cx,
                   const double* __restrict__ cy, double frac, double* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double red[4][8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t f = (int64_t)blockIdx.x * 32 + lane;

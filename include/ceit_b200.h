@@ -260,6 +260,10 @@ int ceit_debug_tile_clocks(int64_t* out8);
  *   "shard_parts", "shard_part"
  *                       plans created afterwards: domain decomposition over G ranks, this process being rank r
  *                       (default 1 / 0 = none); see ceit_factor_phase
+ *   "pdl"               (default 1) programmatic dependent launch: 1 = the DMMA GEMM and tile-factorisation kernels are
+ *                       launched with the programmatic-stream-serialisation attribute (they wait for their predecessor
+ *                       with griddepcontrol.wait after their prologue; in a captured graph the edges become
+ *                       programmatic), 2 = every kernel of the path, 0 = plain launches
  *   "wb_persist"        (default 1) low-rank Woodbury stage as ONE persistent CTA per SM walking (patch, excitation,
  *                       column chunk) items through a 3-slot TMA ring with two consumer groups (even nU); 0 = one CTA
  *                       per (patch, excitation)

@@ -85,7 +85,16 @@ inline cudaError_t launch_pdl_level(int level, void (*kernel)(KArgs...), dim3 gr
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
-// pdl(kernel, grid, block, smem, stream)(args...) - drop-in for pdl(kernel, grid, block, smem, stream)(args...)
+// level 1 (default): the DMMA GEMM and the tile factorisation - the kernels that make up the serial spine
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  return launch_pdl_level(1, kernel, grid, block, smem, st, args...);
+}
+// pdl(kernel, grid, block, smem, stream)(args...) - drop-in for the triple-chevron launch; the attribute is set from
+// level 2 on (ceit_set_option("pdl", 2)): measured on MESH_50_50, programmatic edges between the short gather / scatter /
+// element-wise kernels (whose first instruction already needs the predecessor's data) do not pay - step 0.675 ms with
+// level 1, 0.685 ms with level 2, and a graph of 100 single-frame GEMVs 3.25 -> 3.68 us per frame
 template <class... KArgs>
 struct PdlLaunch {
   void (*k)(KArgs...);

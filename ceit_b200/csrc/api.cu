@@ -1139,8 +1139,20 @@ int excitation_impl(ceit_plan* p, int i0, int nbatch, cudaStream_t st) {
       // SMs) that each walk >= 32 tiles, so staging D_i stays a few per cent of a CTA's work; small problems fill
       // one wave instead
       const int64_t per = (int64_t)nbatch * nz;
-      const int64_t g_fill = cdiv(296, per), g_waves = std::max<int64_t>(1, (148 * 2 * (int64_t)g_ru_waves) / per);
-      const int64_t groups = std::max<int64_t>(1, std::min<int64_t>(tiles, std::max(g_fill, std::min(g_waves, tiles / 32))));
+      const int64_t slots = 148 * 2;      // 126 registers x 256 threads: two CTAs per SM
+      const int64_t g_fill = std::max<int64_t>(1, slots / per), g_waves = std::max<int64_t>(1, (slots * (int64_t)g_ru_waves) / per);
+      int64_t groups = std::max<int64_t>(1, std::min<int64_t>(tiles, std::max(g_fill, std::min(g_waves, tiles / 32))));
+      {
+        // wave quantisation: 336 CTAs on 296 slots ran as two waves (MESH_50_50: 61 us; 288 CTAs: one wave), 912 as
+        // four (200x200).  Among the group counts down to 2/3 of the target take the one whose last wave is fullest.
+        auto ctas = [&](int64_t g) { return per * (int64_t)cdiv(tiles, cdiv(tiles, g)); };
+        auto eff = [&](int64_t g) { const int64_t c = ctas(g); return (double)c / ((double)cdiv(c, slots) * slots); };
+        int64_t best_g = groups;
+        double best_e = eff(groups);
+        for (int64_t g = groups - 1; g >= std::max<int64_t>(1, (2 * groups) / 3); --g)
+          if (eff(g) > best_e + 0.02) { best_e = eff(g); best_g = g; }
+        groups = best_g;
+      }
       const int passes = (int)std::max<int64_t>(1, cdiv(tiles, groups));
       dim3 grid(nbatch, cdiv(tiles, passes), nz);
 #define CEIT_RU(c, w) pdl(rank_update_kernel<T, c, w>, grid, 256, smu, su)(rows, (int)nU, bp, src, yv, Dcat, p->d_ue_ptr, \

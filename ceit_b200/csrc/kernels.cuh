@@ -1221,7 +1221,7 @@ woodbury_patch_kernel(int e_from, int e_to, int L, int nU, int pitch, int64_t N,
 // become 6 (b+1) FMAs, the Xh rows are no longer staged, and a patch needs half the shared memory.
 // ------------------------------------------------------------------------------------------------
 // g1e[e][q] = g0e[e][q] + sum_k Y_T[pa,k] Xh[pb,k]; one warp per element
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)   // <= 51 registers: 40 warps per SM hold MESH_50_50's 5000 elements in one wave (was 1.06)
 g1_kernel(int64_t E, int nU, const int32_t* __restrict__ elem_pos, const double* __restrict__ g0e,
           const double* __restrict__ YT, const double* __restrict__ Xh, double* __restrict__ g1e) {
   pdl_trigger();

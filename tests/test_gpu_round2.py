@@ -528,8 +528,9 @@ def test_domain_decomposed_step_equals_single_plan(torch_cuda, golden, tag, part
 
 
 def test_persistent_woodbury_kernel_equals_per_cta_kernel(torch_cuda, golden):
-    """K2: the persistent pipelined kernel (default) against the one-CTA-per-(patch, excitation) kernel, bit for bit
-    (same arithmetic per column), incl. a partial excitation / element range."""
+    """K2: the persistent ring kernel (wb_persist = 1, default) against the one-CTA-per-(patch, excitation) kernel on
+    the same plan (same arithmetic per column; the 3x3 corrections are summed in a different order, far below one ulp
+    of J), incl. a partial excitation / element range."""
     t = torch_cuda
     for tag in ("21_21", "50_50"):
         m, r = golden(tag)
@@ -538,21 +539,27 @@ def test_persistent_woodbury_kernel_equals_per_cta_kernel(torch_cuda, golden):
         c = float(r["variable_change_for_JAC"])
         perm = t.tensor(m["elem_perm"], device="cuda")
         var = t.zeros(E, dtype=t.float64, device="cuda")
-        p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"])
-        p.assemble(perm, var, omega)
-        p.factor(False)
-        outs = []
-        for persist in (1, 0):
-            _lib.set_option("wb_persist", persist)
+        for mode in (1,):
+            _lib.set_option("wb_persist", mode)
             try:
-                J = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
-                p.jacobian_block(0, L, 0, E, c, omega, J, E)
-                J2 = t.zeros_like(J)
-                p.jacobian_block(3, 7, E // 5, E // 2, c, omega, J2, E)
+                p = _lib.Plan(m["nodes"], m["elem"], m["electrodes"])
+                p.assemble(perm, var, omega)
+                p.factor(False)
+                outs = []
+                for persist in (mode, 0):
+                    _lib.set_option("wb_persist", persist)
+                    l0 = _lib.launch_count()
+                    J = t.zeros((L * (L - 1), E), dtype=t.float64, device="cuda")
+                    p.jacobian_block(0, L, 0, E, c, omega, J, E)
+                    J2 = t.zeros_like(J)
+                    p.jacobian_block(3, 7, E // 5, E // 2, c, omega, J2, E)
+                    outs.append((J, J2))
             finally:
                 _lib.set_option("wb_persist", 1)
-            outs.append((J, J2))
-        assert t.equal(outs[0][0], outs[1][0]) and t.equal(outs[0][1], outs[1][1])
-        assert float(outs[0][1][:3 * (L - 1)].abs().max()) == 0.0 and float(outs[0][1][:, :E // 5].abs().max()) == 0.0
-        if "JAC" in r:
-            assert np.abs(outs[0][0].cpu().numpy() - r["JAC"]).max() < RAW_TOL
+            assert float((outs[0][0] - outs[1][0]).abs().max()) <= 4.5e-16
+            assert float((outs[0][1] - outs[1][1]).abs().max()) <= 4.5e-16
+            assert float((outs[0][0] - 1).abs().max()) > 1e-9                     # the kernels did write the signal
+            assert float(outs[0][1][:3 * (L - 1)].abs().max()) == 0.0 and float(outs[0][1][:, :E // 5].abs().max()) == 0.0
+            if "JAC" in r:
+                assert np.abs(outs[0][0].cpu().numpy() - r["JAC"]).max() < RAW_TOL
+            p.close()

@@ -291,12 +291,25 @@ def _measure_domain(ctx, name, steps, warmup, use_graph, sample_clocks, mesh, pl
         plan.assemble(perm, var, omega)
         plan.factor_phase(1)
 
+    # a large Jacobian is computed and replicated in two halves of the excitations: the all-gather of the first half
+    # runs beside the second half's excitation stage / Woodbury kernel, the second beside the inverse model
+    split = 8.0 * m_rows * dom.e_max > 64e6 and L >= 4
+    half = L // 2 if split else L
+
     def part_b():
         plan.factor_phase(2)
-        plan.jacobian_block(0, L, 0, E, C_PERT, omega, J, E, base)
+        plan.jacobian_block(0, half, 0, E, C_PERT, omega, J, E, base)
 
-    def tail():
-        dom.gather_jacobian(J, async_op=True)                 # replication of J: off the critical path
+    def part_c():
+        plan.jacobian_block(half, L, 0, E, C_PERT, omega, J, E, base)
+
+    def tail(graphs=None):
+        if split:
+            dom.gather_jacobian(J, async_op=True, rows=(0, half * (L - 1)))
+            (graphs[2].replay if graphs else part_c)()
+            dom.gather_jacobian(J, async_op=True, rows=(half * (L - 1), m_rows))
+        else:
+            dom.gather_jacobian(J, async_op=True)             # replication of J: off the critical path
         holder["inv"] = dom.inverse_model(J, LAMBDA, shift=1.0, flag=flag)
         dom.finish()
 
@@ -310,13 +323,13 @@ def _measure_domain(ctx, name, steps, warmup, use_graph, sample_clocks, mesh, pl
     ctx.barrier()
     run_step = step
     if use_graph:
-        ga, gb = _lib.StepGraph(part_a), _lib.StepGraph(part_b)
+        graphs = [_lib.StepGraph(part_a), _lib.StepGraph(part_b)] + ([_lib.StepGraph(part_c)] if split else [])
 
         def run_step():
-            ga.replay()
+            graphs[0].replay()
             dom.base_exchange()
-            gb.replay()
-            tail()
+            graphs[1].replay()
+            tail(graphs)
     for _ in range(max(warmup, 3)):
         ctx.flush.zero_()
         run_step()

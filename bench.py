@@ -291,25 +291,12 @@ def _measure_domain(ctx, name, steps, warmup, use_graph, sample_clocks, mesh, pl
         plan.assemble(perm, var, omega)
         plan.factor_phase(1)
 
-    # a large Jacobian is computed and replicated in two halves of the excitations: the all-gather of the first half
-    # runs beside the second half's excitation stage / Woodbury kernel, the second beside the inverse model
-    split = 8.0 * m_rows * dom.e_max > 64e6 and L >= 4
-    half = L // 2 if split else L
-
     def part_b():
         plan.factor_phase(2)
-        plan.jacobian_block(0, half, 0, E, C_PERT, omega, J, E, base)
+        plan.jacobian_block(0, L, 0, E, C_PERT, omega, J, E, base)
 
-    def part_c():
-        plan.jacobian_block(half, L, 0, E, C_PERT, omega, J, E, base)
-
-    def tail(graphs=None):
-        if split:
-            dom.gather_jacobian(J, async_op=True, rows=(0, half * (L - 1)))
-            (graphs[2].replay if graphs else part_c)()
-            dom.gather_jacobian(J, async_op=True, rows=(half * (L - 1), m_rows))
-        else:
-            dom.gather_jacobian(J, async_op=True)             # replication of J: off the critical path
+    def tail():
+        dom.gather_jacobian(J, async_op=True)                 # replication of J: off the critical path
         holder["inv"] = dom.inverse_model(J, LAMBDA, shift=1.0, flag=flag)
         dom.finish()
 
@@ -323,13 +310,13 @@ def _measure_domain(ctx, name, steps, warmup, use_graph, sample_clocks, mesh, pl
     ctx.barrier()
     run_step = step
     if use_graph:
-        graphs = [_lib.StepGraph(part_a), _lib.StepGraph(part_b)] + ([_lib.StepGraph(part_c)] if split else [])
+        ga, gb = _lib.StepGraph(part_a), _lib.StepGraph(part_b)
 
         def run_step():
-            graphs[0].replay()
+            ga.replay()
             dom.base_exchange()
-            graphs[1].replay()
-            tail(graphs)
+            gb.replay()
+            tail()
     for _ in range(max(warmup, 3)):
         ctx.flush.zero_()
         run_step()

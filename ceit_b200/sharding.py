@@ -240,11 +240,10 @@ class DomainStep:
         return self._lib.inverse_model_sharded(J, self.det_local, lmbda, shift=shift, group=self.group, flag=flag)
 
     # ---- replication of J (output contract only) ------------------------------------------------------------------
-    def gather_jacobian(self, J, async_op=False, rows=None):
-        """Replicate J (or its row range `rows` = (r0, r1): excitation blocks can be replicated while the next ones are
-        still being computed): pack this rank's columns, all-gather, scatter the other ranks' columns into place.  The
-        whole chain runs on a side stream (and its own communicator), so with async_op=True it overlaps whatever the
-        caller enqueues next on the current stream until `finish()`."""
+    def gather_jacobian(self, J, async_op=False):
+        """Replicate J: pack this rank's columns, all-gather, scatter the other ranks' columns into place.  The whole
+        chain runs on a side stream (and its own communicator), so with async_op=True it overlaps whatever the caller
+        enqueues next on the current stream (the inverse model) until `finish()`."""
         torch, dist = self.torch, self.dist
         if self._idx_all is None:
             idx = torch.full((self.ws, self.e_max), -1, dtype=torch.int64, device=J.device)
@@ -253,39 +252,29 @@ class DomainStep:
             dist.all_gather_into_tensor(idx, mine, group=self.group)
             self._idx_all = [idx[r, :self.counts[r]].contiguous() for r in range(self.ws)]
             self._side = torch.cuda.Stream(device=J.device) if J.is_cuda else None
-            self._bufs = {}
-        r0, r1 = (0, self.m) if rows is None else (int(rows[0]), int(rows[1]))
-        if (r0, r1) not in self._bufs:
-            if (r0, r1) == (0, self.m):
-                self._bufs[(r0, r1)] = (self._pack, self._all)
-            else:
-                self._bufs[(r0, r1)] = (torch.zeros((r1 - r0, self.e_max), dtype=torch.float64, device=J.device),
-                                        torch.empty((self.ws, r1 - r0, self.e_max), dtype=torch.float64, device=J.device))
-        pack, allb = self._bufs[(r0, r1)]
-        Jv = J[r0:r1]
         n = self.own_idx.numel()
         if self._side is None:                                   # gloo / CPU: everything in line
             if n:
-                torch.index_select(Jv, 1, self.own_idx, out=pack[:, :n])
-            dist.all_gather_into_tensor(allb, pack, group=self.group)
-            self._scatter(Jv, allb)
+                torch.index_select(J, 1, self.own_idx, out=self._pack[:, :n])
+            dist.all_gather_into_tensor(self._all, self._pack, group=self.group)
+            self._scatter(J)
             return J
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             if n:
-                torch.index_select(Jv, 1, self.own_idx, out=pack[:, :n])
-            dist.all_gather_into_tensor(allb, pack, group=self.repl_group)
-            self._scatter(Jv, allb)
+                torch.index_select(J, 1, self.own_idx, out=self._pack[:, :n])
+            dist.all_gather_into_tensor(self._all, self._pack, group=self.repl_group)
+            self._scatter(J)
         self._work = True
         if not async_op:
             self.finish()
         return J
 
-    def _scatter(self, Jv, allb):
+    def _scatter(self, J):
         for r in range(self.ws):
             if r != self.rank and self.counts[r]:
-                Jv.index_copy_(1, self._idx_all[r], allb[r][:, :self.counts[r]])
+                J.index_copy_(1, self._idx_all[r], self._all[r][:, :self.counts[r]])
 
     def finish(self):
         """Join the replication of J: the current stream waits for the side stream."""

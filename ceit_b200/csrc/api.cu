@@ -880,6 +880,9 @@ int factor_impl(ceit_plan* p, cudaStream_t st, int phase = 0) {
       // the assembled right-hand-side rows of the top count once in the all-reduce: rank 0 keeps them
       if (t.part != 0 && t.rowsA > t.ra_top0)
         CUDA_TRY(cudaMemsetAsync(K0U + t.ra_top0 * nU, 0, (t.rowsA - t.ra_top0) * nU * es, st));
+      // the partial-S_U slab behind the active rows: a rank without active fronts (an interior region: no electrode
+      // nearby) contributes zeros, and the product below writes the lower triangle only
+      CUDA_TRY(cudaMemsetAsync(K0U + t.rowsA * nU, 0, nU * nU * es, st));
       tree_bottom_up<T>(t, nU, m, bk, one, zero, mone, 0, t.n_own_segs);
       if (bk.rc) return bk.rc;
       const int64_t r0 = t.ra0[t.part], r1 = t.ra1[t.part];

@@ -229,6 +229,10 @@ int ceit_stage_flops(double* flops);
 
 /* debug: clock64 phase stamps of the last tile-factorisation CTA (only with -DCEIT_TILE_CLOCKS) */
 int ceit_debug_tile_clocks(int64_t* out8);
+/* debug: phase stamps of the Woodbury kernels (only with -DCEIT_TILE_CLOCKS): out16 = two sample CTAs of the
+ * one-CTA-per-item kernel; out512 = per item of CTA 7 of the persistent kernel (tools/wb_clocks.py, wbq_clocks.py) */
+int ceit_debug_wb_clocks(int64_t* out16);
+int ceit_debug_wbq_clocks(int64_t* out512);
 
 /* switches (value 0/1 unless noted):
  *   "stage_timers"      record CUDA events around every stage (ceit_stage_times); not capturable

@@ -436,7 +436,7 @@ def test_element_parallel_assembly_equals_gather_form_and_reference(torch_cuda, 
     assert abs(K - K.T).max() == 0
 
 
-@pytest.mark.parametrize("tag,parts", [("50_50", 2), ("50_50", 4), ("21_21", 4)])
+@pytest.mark.parametrize("tag,parts", [("50_50", 2), ("50_50", 4), ("21_21", 4), ("50_50", 3), ("50_50", 8)])
 def test_domain_decomposed_step_equals_single_plan(torch_cuda, golden, tag, parts):
     """The multi-GPU base stage (ceit_factor_phase) with its ranks run one after the other on ONE device: the
     exchange between the two halves is done here with plain copies / sums instead of NCCL.  Every rank's Jacobian

@@ -249,14 +249,14 @@ class DomainStep:
             idx = torch.full((self.ws, self.e_max), -1, dtype=torch.int64, device=J.device)
             idx[self.rank, :self.own_idx.numel()] = self.own_idx
             mine = idx[self.rank].clone()
-            dist.all_gather_into_tensor(idx, mine, group=self.group)
+            dist.all_gather_into_tensor(idx.view(-1), mine, group=self.group)    # flat views: gloo and NCCL agree on them
             self._idx_all = [idx[r, :self.counts[r]].contiguous() for r in range(self.ws)]
             self._side = torch.cuda.Stream(device=J.device) if J.is_cuda else None
         n = self.own_idx.numel()
         if self._side is None:                                   # gloo / CPU: everything in line
             if n:
                 torch.index_select(J, 1, self.own_idx, out=self._pack[:, :n])
-            dist.all_gather_into_tensor(self._all, self._pack, group=self.group)
+            dist.all_gather_into_tensor(self._all.view(-1), self._pack.view(-1), group=self.group)
             self._scatter(J)
             return J
         cur = torch.cuda.current_stream()
@@ -264,7 +264,7 @@ class DomainStep:
         with torch.cuda.stream(self._side):
             if n:
                 torch.index_select(J, 1, self.own_idx, out=self._pack[:, :n])
-            dist.all_gather_into_tensor(self._all, self._pack, group=self.repl_group)
+            dist.all_gather_into_tensor(self._all.view(-1), self._pack.view(-1), group=self.repl_group)
             self._scatter(J)
         self._work = True
         if not async_op:

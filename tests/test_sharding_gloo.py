@@ -80,3 +80,57 @@ def test_sharded_step_exchange_gloo(ws, L, E, equal):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res) and all(eq == equal for _, _, eq in res)
+
+
+def _worker_domain(rank, ws, port, q):
+    """Host logic of the domain-decomposed schedule on CPU tensors: element ownership from the decomposed plans
+    (host tables only), replication of J from the ranks' own columns, the detection split that feeds the sharded
+    inverse model."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        from ceit_b200 import _lib
+        from ceit_b200.sharding import DomainStep
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        m = dict(np.load(os.path.join(root, "tests", "golden", "mesh_50_50.npz")))
+        ptr, ee = m["electrode_ptr"], m["electrode_elems"]
+        els = [ee[ptr[i]:ptr[i + 1]] for i in range(16)]
+        E, L = len(m["elem"]), 16
+        mrows = L * (L - 1)
+        det = torch.tensor(m["detection_index"], dtype=torch.int64)
+        plan = _lib.Plan(m["nodes"], m["elem"], els, upload=False, parts=ws, part=rank)
+        step = DomainStep(m["nodes"], m["elem"], els, det, plan=plan)
+        full = (torch.arange(mrows * E, dtype=torch.float64).reshape(mrows, E) * 0.125 + 1.0)
+        J = torch.zeros_like(full)
+        J[:, step.own_idx] = full[:, step.own_idx]                        # what the rank's Woodbury kernel writes
+        for _ in range(2):                                                # buffers are reusable
+            step.gather_jacobian(J, async_op=True)
+            step.finish()
+        ok = bool(torch.equal(J, full))
+        # detection split: the ranks' rows of inv_mat partition the detection elements, in the order of `det`
+        n_det = torch.tensor([step.det_pos.numel()], dtype=torch.int64)
+        dist.all_reduce(n_det)
+        ok &= int(n_det.item()) == det.numel()
+        ok &= bool(torch.equal(det[step.det_pos], step.det_local))
+        own = torch.zeros(E, dtype=torch.bool)
+        own[step.own_idx] = True
+        ok &= bool(own[step.det_local].all())
+        ok &= sum(step.counts) == E and step.counts[rank] == step.own_idx.numel()
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ws", [2, 3])
+def test_domain_step_host_logic_gloo(ws):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_domain, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in res)
